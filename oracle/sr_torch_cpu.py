@@ -1,0 +1,117 @@
+"""CPU oracle #2 (TEST INFRASTRUCTURE ONLY) -- functional torch-CPU restatement, fp32.
+
+The reference's arithmetic for this path lives in PyTorch/ATen (requirements.txt:1, unpinned
+`pytorch>=1.10.0`; this image: torch 2.11.0+cu128, CPU path = oneDNN).  This module restates the
+EDSR/RCAN forward with `torch.nn.functional` calls on the *same* ATen CPU kernels the reference's
+`nn.Conv2d` / `nn.AdaptiveAvgPool2d` / `nn.PixelShuffle` modules dispatch to, driven by a plain
+state_dict (reference key layout), and gets backward from autograd exactly like the reference's
+`loss.backward()` (base_architecture.py:432).  It is therefore the faithful *performance* port of
+the reference's CPU path and is what `bench.py` times as `cpu_baseline` / `--impl reference`
+(kind "port"), while `oracle/sr_numpy.py` is the independent arithmetic restatement.
+
+Only tests/, __graft_entry__.smoke() and bench.py may import this file; the product never does.
+
+Reference lines restated (relative to /root/reference):
+  RCAN.forward  rumpy/SISR/models/advanced/architectures.py:171-176
+  ResidualGroup :121-124   RCAB :81-84   CALayer :41-44
+  EDSR.forward  :236-241   ResBlock common.py:71-75   Upsampler common.py:29-44
+  train step    rumpy/shared_framework/models/base_architecture.py:425-440,457-485
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _conv(sd, key, x):
+    w = sd[key + '.weight']
+    return F.conv2d(x, w, sd[key + '.bias'], padding=w.shape[-1] // 2)
+
+
+def _ca(sd, key, x):
+    y = F.adaptive_avg_pool2d(x, 1)
+    y = F.relu(_conv(sd, key + '.conv_du.0', y))
+    y = torch.sigmoid(_conv(sd, key + '.conv_du.2', y))
+    return x * y
+
+
+def _tail(sd, x, scale):
+    if scale & (scale - 1) == 0:
+        for i in range(int(math.log2(scale))):
+            x = F.pixel_shuffle(_conv(sd, f'tail.0.{2 * i}', x), 2)
+    elif scale == 3:
+        x = F.pixel_shuffle(_conv(sd, 'tail.0.0', x), 3)
+    else:
+        raise NotImplementedError
+    return _conv(sd, 'tail.1', x)
+
+
+def rcan_forward(sd, x, n_resgroups=10, n_resblocks=20, scale=4):
+    x = _conv(sd, 'head.0', x)
+    res = x
+    for g in range(n_resgroups):
+        gin = res
+        for b in range(n_resblocks):
+            p = f'body.{g}.body.{b}.body'
+            t = F.relu(_conv(sd, p + '.0', res))
+            res = _ca(sd, p + '.3', _conv(sd, p + '.2', t)) + res
+        res = _conv(sd, f'body.{g}.body.{n_resblocks}', res) + gin
+    res = _conv(sd, f'body.{n_resgroups}', res) + x
+    return _tail(sd, res, scale)
+
+
+def edsr_forward(sd, x, num_blocks=16, res_scale=0.1, scale=4):
+    x = _conv(sd, 'head.0', x)
+    res = x
+    for b in range(num_blocks):
+        t = F.relu(_conv(sd, f'body.{b}.body.0', res))
+        res = _conv(sd, f'body.{b}.body.2', t).mul(res_scale) + res
+    res = _conv(sd, f'body.{num_blocks}', res) + x
+    return _tail(sd, res, scale)
+
+
+def infer_arch(sd):
+    """Recover (arch, kwargs) from a reference-layout state_dict."""
+    keys = list(sd.keys())
+    n_feats = sd['head.0.weight'].shape[0]
+    scale_convs = sorted({int(k.split('.')[2]) for k in keys if k.startswith('tail.0.')})
+    cout = sd['tail.0.0.weight'].shape[0]
+    scale = 3 if cout == 9 * n_feats else 2 ** len(scale_convs)
+    if any('.conv_du.' in k for k in keys):
+        groups = sorted({int(k.split('.')[1]) for k in keys if k.startswith('body.')})
+        n_resgroups = max(groups)
+        blocks = {int(k.split('.')[3]) for k in keys if k.startswith('body.0.body.')}
+        return 'rcan', dict(n_resgroups=n_resgroups, n_resblocks=max(blocks), n_feats=n_feats, scale=scale)
+    blocks = sorted({int(k.split('.')[1]) for k in keys if k.startswith('body.')})
+    return 'edsr', dict(num_blocks=max(blocks), n_feats=n_feats, scale=scale)
+
+
+def forward(sd, x, arch, **kw):
+    if arch == 'rcan':
+        return rcan_forward(sd, x, kw['n_resgroups'], kw['n_resblocks'], kw.get('scale', 4))
+    return edsr_forward(sd, x, kw['num_blocks'], kw.get('res_scale', 0.1), kw.get('scale', 4))
+
+
+class Trainer:
+    """Restates BaseModel.run_train (base_architecture.py:457-485): L1 loss, Adam(lr), optional
+    clip_grad_norm_, per-batch scheduler omitted (constant lr unless `lr_fn` given)."""
+
+    def __init__(self, sd, arch, lr=1e-4, grad_clip=None, **kw):
+        self.params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        self.arch, self.kw, self.grad_clip = arch, kw, grad_clip
+        self.opt = torch.optim.Adam(list(self.params.values()), lr=lr)
+
+    def step(self, x, y):
+        out = forward(self.params, x, self.arch, **self.kw)
+        loss = F.l1_loss(out, y)
+        self.opt.zero_grad()
+        loss.backward()
+        if self.grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(list(self.params.values()), self.grad_clip)
+        self.opt.step()
+        return float(loss.detach()), out.detach()
+
+    def grads(self):
+        return {k: v.grad.detach().clone() for k, v in self.params.items()}

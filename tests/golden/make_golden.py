@@ -1,0 +1,204 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference is pure Python on top of torch; it imports with two shims:
+`collections.Callable` (removed in py3.10) and stub modules for third-party packages the
+EDSR/RCAN trunk never uses.  Nothing from the reference is copied: it is imported, executed on
+recipe inputs (tests/golden/recipe.py) and only its OUTPUTS are stored.
+"""
+from __future__ import annotations
+
+import collections
+import collections.abc
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import tempfile
+import types
+from unittest import mock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import recipe  # noqa: E402
+
+REF = '/root/reference'
+
+
+# ---------------------------------------------------------------------------- import shims
+class _StubLoader(importlib.abc.Loader):
+    def create_module(self, spec):
+        m = mock.MagicMock(name=spec.name)
+        m.__name__ = spec.name
+        m.__path__ = []
+        m.__spec__ = spec
+        m.__loader__ = self
+        return m
+
+    def exec_module(self, module):
+        pass
+
+
+class _StubFinder(importlib.abc.MetaPathFinder):
+    ROOTS = ('timm', 'matplotlib', 'deepdiff', 'colorama', 'torchinfo', 'prefetch_generator', 'skimage',
+             'lpips', 'h5py', 'skvideo', 'moviepy', 'umap', 'click_config_file', 'imageio', 'aim', 'seaborn',
+             'facenet_pytorch', 'mtcnn', 'keras', 'tensorflow', 'onnx', 'onnxruntime')
+
+    def find_spec(self, name, path=None, target=None):
+        if name.split('.')[0] in self.ROOTS:
+            return importlib.machinery.ModuleSpec(name, _StubLoader(), is_package=True)
+        return None
+
+
+def import_reference():
+    collections.Callable = collections.abc.Callable
+    sys.meta_path.append(_StubFinder())
+    sys.path.insert(0, REF)
+    from rumpy.SISR.models.advanced import architectures, common  # noqa
+    return architectures, common
+
+
+# ---------------------------------------------------------------------------- helpers
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def checksum(a: np.ndarray):
+    a64 = a.astype(np.float64)
+    return np.array([a64.sum(), np.abs(a64).sum(), (a64 * a64).sum()])
+
+
+def build_ref_net(arch_mod, arch, kw):
+    if arch == 'rcan':
+        return arch_mod.RCAN(n_resblocks=kw['n_resblocks'], n_resgroups=kw['n_resgroups'], n_feats=kw['n_feats'],
+                             scale=kw['scale'])
+    return arch_mod.EDSR(net_features=kw['n_feats'], num_blocks=kw['num_blocks'], scale=kw['scale'],
+                         res_scale=kw['res_scale'])
+
+
+def net_case(arch_mod, name):
+    arch, kw, sd, x, y = recipe.case_tensors(name)
+    torch.manual_seed(0)
+    net = build_ref_net(arch_mod, arch, kw)
+    # strict load: proves recipe key names / shapes / ORDER equal the reference's
+    assert list(net.state_dict().keys()) == list(sd.keys()), 'key order mismatch vs reference'
+    net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    net.train()
+    xt, yt = t(x), t(y)
+    out = net(xt)
+    loss = torch.nn.L1Loss()(out, yt)
+    loss.backward()
+    rec = {'out': out.detach().numpy(), 'loss': np.float32(loss.item())}
+    grads = {k: p.grad.numpy() for k, p in net.named_parameters()}
+    keys = list(grads.keys())
+    rec['grad_keys'] = np.array(keys)
+    rec['grad_checksums'] = np.stack([checksum(grads[k]) for k in keys])
+    # every gradient tensor, strided-subsampled to <= ~4k values (recipe.subsample)
+    for k in keys:
+        rec['gradsub::' + k] = recipe.subsample(grads[k]).copy()
+
+    # 3 Adam steps through the reference's own optimiser recipe (base_architecture.py:93-95, 425-440)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, net.parameters()), lr=1e-4)
+    losses = []
+    for _ in range(3):
+        o = net(xt)
+        l = torch.nn.L1Loss()(o, yt)
+        opt.zero_grad()
+        l.backward()
+        opt.step()
+        losses.append(l.item())
+    rec['train_losses'] = np.array(losses, dtype=np.float32)
+    sd_after = net.state_dict()
+    rec['after3::' + keys[0]] = sd_after[keys[0]].numpy()
+    rec['after3::' + keys[-1]] = sd_after[keys[-1]].numpy()
+    rec['after3sub::' + keys[2]] = recipe.subsample(sd_after[keys[2]].numpy()).copy()
+    rec['after3_checksums'] = np.stack([checksum(sd_after[k].numpy()) for k in keys])
+    net.eval()
+    with torch.no_grad():
+        rec['out_after3'] = net(xt).numpy()
+    return rec
+
+
+def block_cases(arch_mod, common):
+    """Per-block golden: forward, input-grad and param-grads for a fixed upstream gradient."""
+    rs = np.random.RandomState(77)
+    rec = {}
+
+    def run(tag, mod, xshape):
+        spec = [(k, tuple(v.shape)) for k, v in mod.state_dict().items()]
+        sd = recipe.make_weights(spec, seed=sum(map(ord, tag)))
+        mod.load_state_dict({k: t(v) for k, v in sd.items()})
+        x = rs.uniform(-1, 1, size=xshape).astype(np.float32)
+        xt = t(x).requires_grad_(True)
+        out = mod(xt.clone())       # reference blocks use in-place `+=`; keep the leaf intact
+        g = rs.uniform(-1, 1, size=tuple(out.shape)).astype(np.float32)
+        out.backward(t(g))
+        rec[tag + '::spec_keys'] = np.array([k for k, _ in spec])
+        rec[tag + '::x'] = x
+        rec[tag + '::g'] = g
+        rec[tag + '::out'] = out.detach().numpy()
+        rec[tag + '::dx'] = xt.grad.numpy()
+        for k, p in mod.named_parameters():
+            rec[tag + '::gradsub::' + k] = recipe.subsample(p.grad.numpy()).copy()
+            rec[tag + '::gradsum::' + k] = checksum(p.grad.numpy())
+
+    act = torch.nn.ReLU(True)
+    run('calayer', arch_mod.CALayer(64, 16), (2, 64, 9, 11))
+    run('rcab', arch_mod.RCAB(common.default_conv, 64, 3, 16, act=act), (2, 64, 9, 11))
+    run('resgroup', arch_mod.ResidualGroup(common.default_conv, 64, 3, 16, act=act, res_scale=1, n_resblocks=2),
+        (1, 64, 10, 7))
+    run('resblock', common.ResBlock(common.default_conv, 64, 3, act=act, res_scale=0.1), (2, 64, 8, 13))
+    run('upsampler2', common.Upsampler(common.default_conv, 2, 64, act=False), (1, 64, 6, 5))
+    run('upsampler3', common.Upsampler(common.default_conv, 3, 64, act=False), (1, 64, 5, 4))
+    run('upsampler4', common.Upsampler(common.default_conv, 4, 64, act=False), (1, 64, 4, 6))
+    run('conv64', common.default_conv(64, 64, 3), (2, 64, 11, 18))
+    return rec
+
+
+def set5_case(arch_mod):
+    """BASELINE.json configs[0]: EDSR-baseline x4 on Data/example_data/Set5 (LR random-blur PNGs)."""
+    from PIL import Image
+    lr_dir = os.path.join(REF, 'Data/example_data/Set5/lr_random_blur')
+    hr_dir = os.path.join(REF, 'Data/example_data/Set5/hr')
+    spec = recipe.edsr_spec(16, 64, 4)
+    sd = recipe.make_weights(spec, seed=5)
+    net = arch_mod.EDSR()
+    net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    net.eval()
+    rec = {}
+    names = sorted(f for f in os.listdir(lr_dir) if f.endswith('.png'))
+    rec['names'] = np.array(names)
+    for f in names:
+        lr = np.asarray(Image.open(os.path.join(lr_dir, f)).convert('RGB'))
+        hr = np.asarray(Image.open(os.path.join(hr_dir, f)).convert('RGB'))
+        x = (lr.astype(np.float32) / 255.0).transpose(2, 0, 1)[None]     # ToTensor() semantics
+        with torch.no_grad():
+            out = net(t(x)).numpy()
+        rec[f + '::lr_u8'] = lr
+        rec[f + '::hr_u8'] = hr
+        rec[f + '::out_checksum'] = checksum(out)
+        rec[f + '::out_crop'] = out[:, :, :32, :32].copy()
+        rec[f + '::out_ds8'] = out[:, :, ::8, ::8].copy()
+    return rec
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    arch_mod, common = import_reference()
+    for name in recipe.CASES:
+        rec = net_case(arch_mod, name)
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **rec)
+        print(name, 'loss', rec['loss'], 'train', rec['train_losses'], 'out', rec['out'].shape)
+    np.savez_compressed(os.path.join(HERE, 'blocks.npz'), **block_cases(arch_mod, common))
+    np.savez_compressed(os.path.join(HERE, 'set5_edsr_baseline.npz'), **set5_case(arch_mod))
+    print('done')
+
+
+if __name__ == '__main__':
+    main()

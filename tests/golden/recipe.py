@@ -1,0 +1,106 @@
+"""Deterministic weights / inputs shared by the golden generator and the tests.
+
+Everything here is numpy-RandomState driven so the same tensors can be rebuilt on any box
+(the GPU box has no /root/reference).  Key names / shapes / order follow the reference's
+state_dict layout (rumpy/SISR/models/advanced/architectures.py:140-241).
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+
+
+def _conv_spec(spec, key, cout, cin, k):
+    spec.append((key + '.weight', (cout, cin, k, k)))
+    spec.append((key + '.bias', (cout,)))
+
+
+def _tail_spec(spec, n_feats, out_feats, scale):
+    if scale & (scale - 1) == 0:
+        for i in range(int(math.log2(scale))):
+            _conv_spec(spec, f'tail.0.{2 * i}', 4 * n_feats, n_feats, 3)
+    elif scale == 3:
+        _conv_spec(spec, 'tail.0.0', 9 * n_feats, n_feats, 3)
+    else:
+        raise NotImplementedError(scale)
+    _conv_spec(spec, 'tail.1', out_feats, n_feats, 3)
+
+
+def rcan_spec(n_resgroups=10, n_resblocks=20, n_feats=64, reduction=16, scale=4, in_feats=3, out_feats=3):
+    spec = []
+    _conv_spec(spec, 'head.0', n_feats, in_feats, 3)
+    for g in range(n_resgroups):
+        for b in range(n_resblocks):
+            p = f'body.{g}.body.{b}.body'
+            _conv_spec(spec, p + '.0', n_feats, n_feats, 3)
+            _conv_spec(spec, p + '.2', n_feats, n_feats, 3)
+            _conv_spec(spec, p + '.3.conv_du.0', n_feats // reduction, n_feats, 1)
+            _conv_spec(spec, p + '.3.conv_du.2', n_feats, n_feats // reduction, 1)
+        _conv_spec(spec, f'body.{g}.body.{n_resblocks}', n_feats, n_feats, 3)
+    _conv_spec(spec, f'body.{n_resgroups}', n_feats, n_feats, 3)
+    _tail_spec(spec, n_feats, out_feats, scale)
+    return spec
+
+
+def edsr_spec(num_blocks=16, n_feats=64, scale=4, in_feats=3, out_feats=3):
+    spec = []
+    _conv_spec(spec, 'head.0', n_feats, in_feats, 3)
+    for b in range(num_blocks):
+        _conv_spec(spec, f'body.{b}.body.0', n_feats, n_feats, 3)
+        _conv_spec(spec, f'body.{b}.body.2', n_feats, n_feats, 3)
+    _conv_spec(spec, f'body.{num_blocks}', n_feats, n_feats, 3)
+    _tail_spec(spec, n_feats, out_feats, scale)
+    return spec
+
+
+def make_weights(spec, seed, gain=1.0):
+    """U(-b, b), b = gain/sqrt(fan_in): the distribution of nn.Conv2d's default init."""
+    rs = np.random.RandomState(seed)
+    sd = OrderedDict()
+    fan_in = None
+    for key, shape in spec:
+        if key == 'weight' or key.endswith('.weight'):
+            fan_in = shape[1] * shape[2] * shape[3]
+        b = gain / math.sqrt(fan_in)
+        sd[key] = rs.uniform(-b, b, size=shape).astype(np.float32)
+    return sd
+
+
+def subsample(a, limit=4096):
+    """Deterministic strided subsample used to keep golden gradient fixtures small."""
+    flat = np.asarray(a).reshape(-1)
+    return flat[::max(1, flat.size // limit)]
+
+
+def make_input(shape, seed):
+    return np.random.RandomState(seed).uniform(0.0, 1.0, size=shape).astype(np.float32)
+
+
+# name -> (arch, kwargs, lr-input shape, weight seed, input seed)
+CASES = OrderedDict(
+    rcan_small=('rcan', dict(n_resgroups=2, n_resblocks=2, n_feats=64, scale=4), (2, 3, 12, 20), 11, 12),
+    rcan_x2=('rcan', dict(n_resgroups=1, n_resblocks=1, n_feats=64, scale=2), (1, 3, 7, 9), 21, 22),
+    rcan_x3=('rcan', dict(n_resgroups=1, n_resblocks=2, n_feats=64, scale=3), (1, 3, 10, 6), 31, 32),
+    edsr_small=('edsr', dict(num_blocks=3, n_feats=64, scale=4, res_scale=0.1), (2, 3, 9, 17), 41, 42),
+    edsr_wide=('edsr', dict(num_blocks=1, n_feats=256, scale=2, res_scale=0.1), (1, 3, 8, 16), 51, 52),
+)
+
+
+def case_spec(name):
+    arch, kw, shape, wseed, xseed = CASES[name]
+    if arch == 'rcan':
+        spec = rcan_spec(kw['n_resgroups'], kw['n_resblocks'], kw['n_feats'], 16, kw['scale'])
+    else:
+        spec = edsr_spec(kw['num_blocks'], kw['n_feats'], kw['scale'])
+    return arch, kw, shape, spec, wseed, xseed
+
+
+def case_tensors(name):
+    arch, kw, shape, spec, wseed, xseed = case_spec(name)
+    sd = make_weights(spec, wseed)
+    x = make_input(shape, xseed)
+    s = kw['scale']
+    y = make_input((shape[0], 3, shape[2] * s, shape[3] * s), xseed + 1000)
+    return arch, kw, sd, x, y
