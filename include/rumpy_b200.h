@@ -1,0 +1,95 @@
+/* rumpy_b200 -- C ABI of the B200-native EDSR/RCAN trunk (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference (um-dsrg/RUMpy) has no native code:
+ * its trunk calls stock torch.nn modules.  Each entry point below replaces one of those call sites;
+ * the Python mirror of the reference's block library (rumpy_b200/SISR/models/advanced/*.py) binds them
+ * through ctypes (see INTEGRATION.md for the stub a RUMpy maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only: device pointers as void* / float*, sizes as int, the CUDA stream as void*
+ *     (a cudaStream_t); no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, a negative code on failure; the message is available from
+ *     rumpy_last_error() (thread-local).  Nothing throws, nothing calls exit().
+ *   - the caller owns every buffer (activations, packed weights, workspaces).  All work is enqueued on
+ *     the caller's stream: the calls compose with CUDA-graph capture, autograd streams and NCCL streams.
+ *   - activations are NHWC: bf16 operand tensors (64 channels = 128 contiguous bytes) and fp32
+ *     residual-stream tensors; channel counts on the tensor-core path are multiples of 64.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point fails.
+ *
+ * Reference citations are relative to /root/reference (um-dsrg/RUMpy v1.0).
+ */
+#ifndef RUMPY_B200_H_
+#define RUMPY_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RUMPY_B200_VERSION 100
+
+/* error codes */
+#define RUMPY_OK 0
+#define RUMPY_ERR_ARG (-1)     /* bad argument (shape / alignment / null pointer) */
+#define RUMPY_ERR_DEVICE (-2)  /* no sm_100 device, or the driver lacks cuTensorMapEncodeTiled */
+#define RUMPY_ERR_CUDA (-3)    /* a CUDA runtime / driver call failed */
+
+int rumpy_version(void);
+const char* rumpy_last_error(void);
+/* 0 when the current device is an sm_100 part and the TMA driver entry point resolves. */
+int rumpy_device_check(void);
+
+/* flags for rumpy_conv3x3 (epilogue fusions) */
+#define RUMPY_CONV_RELU 1u     /* v = max(v,0)                         (nn.ReLU(True), architectures.py:150) */
+#define RUMPY_CONV_POOL 32u    /* emit per-tile channel sums for CALayer's AdaptiveAvgPool2d(1) (:32)        */
+
+/* OIHW fp32 conv weights -> packed bf16 tensor-core operand.
+ *   dgrad == 0: P[tap][row][ci]; rows_padded >= cout rows (extra rows zero).  shuffle_r > 1 orders the rows
+ *               so that output chunk q = i*r+j holds PixelShuffle sub-pixel (i,j)  (common.py:33,40).
+ *   dgrad == 1: P[tap][ci][co] with taps rotated 180 degrees -- the operand of dX = conv_transpose(g, W).
+ * Replaces: the implicit weight layout of nn.Conv2d (common.py:6-9).  w_packed holds 9*rows*k bf16. */
+int rumpy_pack_conv3x3(const float* w_oihw, void* w_packed, int cout, int cin, int rows_padded, int shuffle_r,
+                       int dgrad, void* stream);
+int rumpy_pack_bias(const float* bias, float* bias_packed, int cout, int rows_padded, int shuffle_r, void* stream);
+
+/* 3x3, stride 1, zero pad 1 convolution on tcgen05 tensor cores with a fused epilogue:
+ *     v = alpha * act(conv(x, W) + bias);  v = mask > 0 ? v : 0;  v += residual
+ *   x_bf16    [N,H,W,Cin] bf16, or when in_unshuffle_r = r > 1 the tensor [N,H*r,W*r,Cin/r^2] read through
+ *             a pixel-unshuffle (gradient of PixelShuffle, SURVEY 8a')
+ *   w_packed  from rumpy_pack_conv3x3 (rows = Cout, k = Cin)
+ *   bias      [Cout] fp32 in packed-row order, or NULL
+ *   residual  [N,H,W,Cout] fp32 or NULL          (`res += x`, architectures.py:83,123,174; common.py:72-73)
+ *   mask      [N,H,W,Cout] bf16 or NULL           (ReLU backward: the saved post-ReLU activation)
+ *   y_bf16    [N,H,W,Cout] bf16 or NULL; with out_shuffle_r = r > 1 the tensor [N,H*r,W*r,Cout/r^2] written
+ *             in pixel-shuffled order (conv + nn.PixelShuffle of common.Upsampler, common.py:30-41)
+ *   y_f32     [N,H,W,Cout] fp32 or NULL
+ *   pool_partial [N*ceil(H/8)*ceil(W/16)][2][Cout] fp32, required with RUMPY_CONV_POOL
+ * Replaces: nn.Conv2d.forward at common.py:6-9 (+ the elementwise ops fused above); with dgrad-packed
+ * weights it is also the conv's input-gradient (autograd's convolution_backward, base_architecture.py:432). */
+int rumpy_conv3x3(const void* x_bf16, const void* w_packed, const float* bias, const float* residual,
+                  const void* mask_bf16, void* y_bf16, float* y_f32, float* pool_partial, int N, int H, int W,
+                  int Cin, int Cout, int in_unshuffle_r, int out_shuffle_r, unsigned flags, float alpha,
+                  void* stream);
+
+/* Thin tail conv C -> cout_real (<=16) on tensor cores; w_packed has 16 (zero padded) rows; output is the
+ * reference's fp32 NCHW tensor.  Replaces: tail.1 = default_conv(n_feats, out_feats, 3) (architectures.py:165). */
+int rumpy_conv3x3_tail(const void* x_bf16, const void* w_packed, const float* bias16, float* y_nchw, int N, int H,
+                       int W, int Cin, int cout_real, void* stream);
+
+/* Head conv in_feats (<=4) -> C on CUDA cores in fp32: NCHW fp32 in, NHWC fp32 + bf16 out.
+ * Replaces: head.0 = default_conv(in_feats, n_feats, 3) (architectures.py:153,172). */
+int rumpy_head_conv(const float* x_nchw, const float* w_oihw, const float* bias, float* y_f32, void* y_bf16, int N,
+                    int H, int W, int Cin, int C, void* stream);
+
+/* Channel attention + RCAB skip, fused: y = sigmoid(W2 relu(W1 mean(u)+b1)+b2); x_out = x_in + u*y.
+ * `pool_partial` comes from rumpy_conv3x3(..., RUMPY_CONV_POOL) on the same N,H,W.  u is fp32 (u_is_f32) or
+ * bf16 NHWC.  save_* (N x C / N x Cr fp32) may be NULL; they keep mean / hidden / y for backward.
+ * Replaces: CALayer.forward (architectures.py:41-44) and `res += x` (:83). */
+int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const float* x_in, const float* w1,
+                   const float* b1, const float* w2, const float* b2, float* x_out, void* x_out_bf16,
+                   float* save_mean, float* save_hid, float* save_y, int N, int H, int W, int C, int Cr,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUMPY_B200_H_ */

@@ -1,0 +1,63 @@
+"""ctypes binding of librumpy_b200.so (C ABI declared in include/rumpy_b200.h).
+
+The library is the product: if it is missing, or no sm_100 device is present, every compute call raises.
+There is deliberately no CPU / eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librumpy_b200.so')
+
+_c = ctypes
+_vp, _fp, _i, _u, _f = _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_uint, _c.c_float
+
+# name -> argtypes (restype is int unless noted); must list every symbol of include/rumpy_b200.h
+SIGNATURES = {
+    'rumpy_version': [],
+    'rumpy_last_error': [],
+    'rumpy_device_check': [],
+    'rumpy_pack_conv3x3': [_fp, _vp, _i, _i, _i, _i, _i, _vp],
+    'rumpy_pack_bias': [_fp, _fp, _i, _i, _i, _vp],
+    'rumpy_conv3x3': [_vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _u, _f, _vp],
+    'rumpy_conv3x3_tail': [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp],
+    'rumpy_head_conv': [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
+    'rumpy_ca_apply': [_fp, _vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp],
+}
+
+_lib = None
+
+
+class RumpyB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RumpyB200Error(
+            f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(rumpy_b200 has no CPU fallback)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_char_p if name == 'rumpy_last_error' else ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str = ''):
+    if code != 0:
+        msg = load().rumpy_last_error()
+        raise RumpyB200Error(f'{what} failed ({code}): {msg.decode() if msg else "?"}')
+
+
+def call(name: str, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)

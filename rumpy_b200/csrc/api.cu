@@ -1,0 +1,311 @@
+// C-ABI entry points (include/rumpy_b200.h): argument checks, TMA tensor-map encoding, kernel launches.
+#include "../../include/rumpy_b200.h"
+#include "host_util.cuh"
+#include "conv3x3_tc.cuh"
+#include "misc_kernels.cuh"
+
+namespace rb {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+// ------------------------------------------------------------------ driver entry point for TMA descriptors
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int device_info(int* num_sms) {
+  static int cached_sms = -1;
+  if (cached_sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return set_error(RUMPY_ERR_DEVICE, "no CUDA device (rumpy_b200 has no CPU fallback)");
+    }
+    int major = 0, sms = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10) return set_error(RUMPY_ERR_DEVICE, "device compute capability %d.x is not sm_100", major);
+    if (!get_encode_fn()) return set_error(RUMPY_ERR_DEVICE, "driver lacks cuTensorMapEncodeTiled");
+    cached_sms = sms;
+  }
+  if (num_sms) *num_sms = cached_sms;
+  return RUMPY_OK;
+}
+
+// 4-D NHWC map {C, W, H, N} with explicit strides (bytes) and box {box_c, 16, 8, 1}, 128B swizzle, zero OOB fill.
+int make_map_nhwc(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, uint64_t stride_w,
+                  uint64_t stride_h, uint64_t stride_n) {
+  const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+  const cuuint64_t strides[3] = {stride_w, stride_h, stride_n};
+  const cuuint32_t box[4] = {cuuint32_t(f32 ? 32 : 64), kTileW, kTileH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "tensor base not 16B aligned");
+  CUresult r = get_encode_fn()(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                               const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(RUMPY_ERR_CUDA, "cuTensorMapEncodeTiled(NHWC) failed: %d", int(r));
+  return RUMPY_OK;
+}
+
+// Dense NHWC tensor, optionally viewed through a pixel (un)shuffle of factor r: sub-pixel q=(i,j) of the
+// [N, H*r, W*r, C] tensor is the strided [N,H,W,C] view starting at (i, j).
+int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q) {
+  const uint64_t es = f32 ? 4 : 2;
+  const int i = q / r, j = q % r;
+  const uint64_t Wf = uint64_t(W) * r, Hf = uint64_t(H) * r;
+  const char* b = static_cast<const char*>(base) + (uint64_t(i) * Wf + j) * C * es;
+  return make_map_nhwc(m, f32, b, C, W, H, N, uint64_t(r) * C * es, uint64_t(r) * Wf * C * es, Hf * Wf * C * es);
+}
+
+// packed weights [9][rows][k] bf16 -> 3-D map {k, rows, 9}, box {64, bn, 1}
+int make_map_weights(CUtensorMap* m, const void* base, int k, int rows, int bn) {
+  const cuuint64_t dims[3] = {cuuint64_t(k), cuuint64_t(rows), 9};
+  const cuuint64_t strides[2] = {cuuint64_t(k) * 2, cuuint64_t(k) * 2 * rows};
+  const cuuint32_t box[3] = {64, cuuint32_t(bn), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "weights not 16B aligned");
+  CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(RUMPY_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", int(r));
+  return RUMPY_OK;
+}
+
+// ------------------------------------------------------------------ conv launch plan
+int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
+  int sms = 0;
+  if (int e = device_info(&sms)) return e;
+  if (d.N <= 0 || d.H <= 0 || d.W <= 0) return set_error(RUMPY_ERR_ARG, "conv3x3: bad shape %dx%dx%d", d.N, d.H, d.W);
+  if (d.Cin % 64 != 0 || d.Cin <= 0) return set_error(RUMPY_ERR_ARG, "conv3x3: Cin=%d must be a multiple of 64", d.Cin);
+  if (!d.x || !d.w) return set_error(RUMPY_ERR_ARG, "conv3x3: null input / weights");
+  const int rin = d.in_r < 1 ? 1 : d.in_r, rout = d.out_r < 1 ? 1 : d.out_r;
+  if (rin > 3 || rout > 3) return set_error(RUMPY_ERR_ARG, "conv3x3: shuffle factor > 3 unsupported");
+  ConvArgs& a = p->args;
+  memset(p, 0, sizeof(*p));
+  const bool thin = d.out_nchw != nullptr;
+  int bn;
+  if (thin) {
+    if (d.cout_real > 16 || d.cout_real < 1) return set_error(RUMPY_ERR_ARG, "tail conv: cout_real=%d", d.cout_real);
+    bn = 16;
+  } else {
+    if (d.Cout % 64 != 0 || d.Cout <= 0)
+      return set_error(RUMPY_ERR_ARG, "conv3x3: Cout=%d must be a multiple of 64", d.Cout);
+    if (d.Cin % (64 * rin * rin) != 0 || d.Cout % (64 * rout * rout) != 0)
+      return set_error(RUMPY_ERR_ARG, "conv3x3: channels/shuffle mismatch");
+    bn = (d.Cin > 64 && d.Cout % 128 == 0) ? 128 : 64;
+    if (d.force_bn) bn = d.force_bn;
+    if (d.Cout % bn != 0) return set_error(RUMPY_ERR_ARG, "conv3x3: Cout %% BN != 0");
+  }
+  const int cin_chunks = d.Cin / 64;
+  const bool resident = size_t(9) * cin_chunks * bn * 128 <= 96 * 1024;
+  p->bn = bn;
+  p->resident = resident;
+  a.N = d.N; a.H = d.H; a.W = d.W;
+  a.tiles_x = (d.W + kTileW - 1) / kTileW;
+  a.tiles_y = (d.H + kTileH - 1) / kTileH;
+  a.m_tiles = d.N * a.tiles_x * a.tiles_y;
+  a.n_tiles = thin ? 1 : d.Cout / bn;
+  a.cin_chunks = cin_chunks;
+  a.a_chunks_per_map = cin_chunks / (rin * rin);
+  a.o_chunks_per_map = thin ? 1 : (d.Cout / 64) / (rout * rout);
+  a.cout = thin ? 16 : d.Cout;
+  a.alpha = d.alpha;
+  a.bias = d.bias;
+  a.pool_partial = d.pool_partial;
+  a.out_nchw = d.out_nchw;
+  a.cout_real = d.cout_real;
+  uint32_t flags = d.flags & (kConvRelu | kConvPool);
+  if (d.y_bf16) flags |= kConvOutBf16;
+  if (d.y_f32) flags |= kConvOutF32;
+  if (d.residual) flags |= kConvResF32;
+  if (d.mask) flags |= kConvMask;
+  if (!thin && !(flags & (kConvOutBf16 | kConvOutF32))) return set_error(RUMPY_ERR_ARG, "conv3x3: no output");
+  if ((flags & kConvPool) && !d.pool_partial) return set_error(RUMPY_ERR_ARG, "conv3x3: POOL needs pool_partial");
+  if (rout > 1 && (flags & (kConvOutF32 | kConvResF32 | kConvMask | kConvPool)))
+    return set_error(RUMPY_ERR_ARG, "conv3x3: shuffle store supports bf16 output only");
+  a.flags = flags;
+  // pipeline depth from the 227 KB budget
+  const size_t budget = 227 * 1024 - 3072;
+  int stages = kMaxStages;
+  while (stages > 2 && conv_smem_bytes(bn, resident, cin_chunks, stages) > budget) --stages;
+  if (conv_smem_bytes(bn, resident, cin_chunks, stages) > budget)
+    return set_error(RUMPY_ERR_ARG, "conv3x3: configuration does not fit shared memory");
+  a.stages = stages;
+  p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages);
+  int grid = sms < a.m_tiles * a.n_tiles ? sms : a.m_tiles * a.n_tiles;
+  grid -= grid % a.n_tiles;
+  if (grid < a.n_tiles) grid = a.n_tiles;
+  p->grid = grid;
+  // tensor maps
+  const int cin_sub = d.Cin / (rin * rin);
+  for (int q = 0; q < rin * rin; ++q)
+    if (int e = make_map_nhwc_sub(&p->maps.a[q], false, d.x, cin_sub, d.W, d.H, d.N, rin, q)) return e;
+  if (int e = make_map_weights(&p->maps.w, d.w, d.Cin, thin ? 16 : d.Cout, bn)) return e;
+  if (d.y_bf16) {
+    const int cout_sub = d.Cout / (rout * rout);
+    for (int q = 0; q < rout * rout; ++q)
+      if (int e = make_map_nhwc_sub(&p->maps.ob[q], false, d.y_bf16, cout_sub, d.W, d.H, d.N, rout, q)) return e;
+  }
+  if (d.y_f32)
+    if (int e = make_map_nhwc_sub(&p->maps.of, true, d.y_f32, d.Cout, d.W, d.H, d.N, 1, 0)) return e;
+  if (d.residual)
+    if (int e = make_map_nhwc_sub(&p->maps.rf, true, d.residual, d.Cout, d.W, d.H, d.N, 1, 0)) return e;
+  if (d.mask)
+    if (int e = make_map_nhwc_sub(&p->maps.mb, false, d.mask, d.Cout, d.W, d.H, d.N, 1, 0)) return e;
+  return RUMPY_OK;
+}
+
+template <int BN, bool RES>
+static int launch_conv_t(const ConvPlan& p, cudaStream_t s) {
+  auto kern = conv3x3_tc_kernel<BN, RES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 3072) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  kern<<<p.grid, kConvThreads, p.smem, s>>>(p.maps, p.args);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "conv3x3 launch: %s", cudaGetErrorString(e));
+  return RUMPY_OK;
+}
+
+int conv_plan_launch(const ConvPlan& p, cudaStream_t s) {
+  switch (p.bn) {
+    case 16: return p.resident ? launch_conv_t<16, true>(p, s) : launch_conv_t<16, false>(p, s);
+    case 64: return p.resident ? launch_conv_t<64, true>(p, s) : launch_conv_t<64, false>(p, s);
+    case 128: return p.resident ? launch_conv_t<128, true>(p, s) : launch_conv_t<128, false>(p, s);
+    case 256: return p.resident ? launch_conv_t<256, true>(p, s) : launch_conv_t<256, false>(p, s);
+  }
+  return set_error(RUMPY_ERR_ARG, "conv3x3: unsupported BN %d", p.bn);
+}
+
+int grid_for(size_t work_items, int block, int per_sm = 8) {
+  int sms = 148;
+  device_info(&sms);
+  size_t blocks = (work_items + block - 1) / block;
+  size_t cap = size_t(sms) * per_sm;
+  return int(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" {
+
+int rumpy_version(void) { return RUMPY_B200_VERSION; }
+const char* rumpy_last_error(void) { return g_last_error.c_str(); }
+int rumpy_device_check(void) { return device_info(nullptr); }
+
+int rumpy_pack_conv3x3(const float* w, void* p, int cout, int cin, int rows_padded, int r, int dgrad, void* stream) {
+  if (int e = device_info(nullptr)) return e;
+  if (!w || !p || cout <= 0 || cin <= 0) return set_error(RUMPY_ERR_ARG, "pack_conv3x3: bad args");
+  if (r < 1) r = 1;
+  if (rows_padded < cout) rows_padded = cout;
+  if (cout % (r * r) != 0) return set_error(RUMPY_ERR_ARG, "pack_conv3x3: cout %% r^2 != 0");
+  const size_t total = size_t(9) * (dgrad ? size_t(cin) * cout : size_t(rows_padded) * cin);
+  pack_conv3x3_kernel<<<grid_for(total, 256), 256, 0, cudaStream_t(stream)>>>(
+      w, static_cast<__nv_bfloat16*>(p), cout, cin, rows_padded, r, dgrad);
+  return check_launch("pack_conv3x3");
+}
+
+int rumpy_pack_bias(const float* b, float* p, int cout, int rows_padded, int r, void* stream) {
+  if (int e = device_info(nullptr)) return e;
+  if (!b || !p) return set_error(RUMPY_ERR_ARG, "pack_bias: null");
+  if (r < 1) r = 1;
+  if (rows_padded < cout) rows_padded = cout;
+  pack_bias_kernel<<<grid_for(rows_padded, 128), 128, 0, cudaStream_t(stream)>>>(b, p, cout, rows_padded, r);
+  return check_launch("pack_bias");
+}
+
+int rumpy_conv3x3(const void* x, const void* w, const float* bias, const float* residual, const void* mask,
+                  void* y_bf16, float* y_f32, float* pool_partial, int N, int H, int W, int Cin, int Cout,
+                  int in_unshuffle_r, int out_shuffle_r, unsigned flags, float alpha, void* stream) {
+  ConvDesc d{};
+  d.x = x; d.w = w; d.bias = bias; d.residual = residual; d.mask = mask; d.y_bf16 = y_bf16; d.y_f32 = y_f32;
+  d.pool_partial = pool_partial; d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.Cout = Cout; d.in_r = in_unshuffle_r;
+  d.out_r = out_shuffle_r; d.flags = flags; d.alpha = alpha;
+  ConvPlan p;
+  if (int e = conv_plan_build(&p, d)) return e;
+  return conv_plan_launch(p, cudaStream_t(stream));
+}
+
+int rumpy_conv3x3_tail(const void* x, const void* w, const float* bias16, float* y_nchw, int N, int H, int W,
+                       int Cin, int cout_real, void* stream) {
+  if (!y_nchw) return set_error(RUMPY_ERR_ARG, "conv3x3_tail: null output");
+  ConvDesc d{};
+  d.x = x; d.w = w; d.bias = bias16; d.N = N; d.H = H; d.W = W; d.Cin = Cin; d.Cout = 16; d.out_nchw = y_nchw;
+  d.cout_real = cout_real; d.alpha = 1.f; d.in_r = 1; d.out_r = 1;
+  ConvPlan p;
+  if (int e = conv_plan_build(&p, d)) return e;
+  return conv_plan_launch(p, cudaStream_t(stream));
+}
+
+int rumpy_head_conv(const float* x, const float* w, const float* bias, float* yf, void* yb, int N, int H, int W,
+                    int Cin, int C, void* stream) {
+  if (int e = device_info(nullptr)) return e;
+  if (!x || !w || !bias || !yf || !yb) return set_error(RUMPY_ERR_ARG, "head_conv: null pointer");
+  if (Cin < 1 || Cin > 4 || C % 8 != 0 || C > 512) return set_error(RUMPY_ERR_ARG, "head_conv: Cin=%d C=%d", Cin, C);
+  const size_t smem = (size_t(Cin) * 9 * C + C) * sizeof(float);
+  const size_t items = size_t(N) * H * W * (C / 8);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(head_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  head_conv_kernel<4><<<grid_for(items, 256, 4), 256, smem, cudaStream_t(stream)>>>(
+      x, w, bias, yf, static_cast<__nv_bfloat16*>(yb), N, H, W, Cin, C);
+  return check_launch("head_conv");
+}
+
+int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const float* x_in, const float* w1,
+                   const float* b1, const float* w2, const float* b2, float* x_out, void* x_out_bf16,
+                   float* save_mean, float* save_hid, float* save_y, int N, int H, int W, int C, int Cr,
+                   void* stream) {
+  int sms = 0;
+  if (int e = device_info(&sms)) return e;
+  if (!pool_partial || !u || !x_in || !w1 || !b1 || !w2 || !b2 || !x_out || !x_out_bf16)
+    return set_error(RUMPY_ERR_ARG, "ca_apply: null pointer");
+  if (C % 4 != 0 || C > 256 || Cr < 1 || Cr > 64) return set_error(RUMPY_ERR_ARG, "ca_apply: C=%d Cr=%d", C, Cr);
+  if (save_y && (!save_mean || !save_hid)) return set_error(RUMPY_ERR_ARG, "ca_apply: save_* must come together");
+  const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const size_t vec = size_t(H) * W * (C / 4);
+  int chunks = int((vec + 256 * 4 - 1) / (256 * 4));          // ~4 vectors per thread
+  const int cap = (sms * 8 + N - 1) / N;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dim3 grid(chunks, N);
+  if (u_is_f32)
+    ca_apply_kernel<true><<<grid, 256, 0, cudaStream_t(stream)>>>(
+        pool_partial, tiles * 2, u, x_in, w1, b1, w2, b2, x_out, static_cast<__nv_bfloat16*>(x_out_bf16), save_mean,
+        save_hid, save_y, H * W, C, Cr);
+  else
+    ca_apply_kernel<false><<<grid, 256, 0, cudaStream_t(stream)>>>(
+        pool_partial, tiles * 2, u, x_in, w1, b1, w2, b2, x_out, static_cast<__nv_bfloat16*>(x_out_bf16), save_mean,
+        save_hid, save_y, H * W, C, Cr);
+  return check_launch("ca_apply");
+}
+
+}  // extern "C"

@@ -1,0 +1,381 @@
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces the reference's `common.default_conv` -> nn.Conv2d call sites on the trunk
+// (/root/reference/rumpy/SISR/models/advanced/common.py:6-9 as used by architectures.py:70-78,114-119,
+// 153-165,216-231 and common.py:30-41,60-66), forward and (with repacked weights) dgrad.
+//
+// Data layout in HBM:  activations NHWC, bf16 operand copies (64 channels = one 128-byte row = one
+// SWIZZLE_128B atom row) and an fp32 copy of the residual stream; weights packed [tap][Cout][Cin] bf16.
+//
+// GEMM view: D[128 pixels, BN out-channels] += A[128 pixels, 64 in-channels] * B[BN, 64]^T, summed over
+// K-blocks = 9 taps x (Cin/64) channel chunks.  The 128-pixel M tile is an 8x16 spatial patch of one image;
+// the A operand of tap (ky,kx) is the same patch shifted by (ky-1,kx-1), fetched by ONE 4-D TMA box
+// {64ch,16,8,1} whose out-of-bounds elements the TMA unit zero-fills -- the convolution's zero padding and
+// ragged image edges cost nothing.  Accumulators live in TMEM (double buffered, 2 x BN columns).
+//
+// Warp roles (192 threads, one persistent CTA per SM):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane)
+//   warps 2..5  epilogue: tcgen05.ld -> bias / ReLU / alpha / mask / fp32 residual -> swizzled smem staging
+//               -> TMA store (bf16 and/or fp32), plus per-tile channel sums for the channel-attention pool
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace rb {
+
+enum ConvFlags : uint32_t {
+  kConvRelu = 1u,       // v = max(v, 0)
+  kConvOutBf16 = 2u,    // store bf16 NHWC (optionally through r*r pixel-shuffle maps)
+  kConvOutF32 = 4u,     // store fp32 NHWC
+  kConvResF32 = 8u,     // v += residual (fp32 NHWC)
+  kConvMask = 16u,      // v = mask > 0 ? v : 0   (mask: bf16 NHWC; ReLU backward)
+  kConvPool = 32u,      // write per-tile channel sums (2 half-tile partials) for the CA global average pool
+};
+
+struct ConvMaps {
+  CUtensorMap a[9];   // bf16 input maps (1 normally; r*r when the input is read through a pixel-unshuffle)
+  CUtensorMap w;      // packed weights, dims {Cin, Cout, 9}
+  CUtensorMap ob[9];  // bf16 output maps (1 normally; r*r for the pixel-shuffle store)
+  CUtensorMap of;     // fp32 output
+  CUtensorMap rf;     // fp32 residual input
+  CUtensorMap mb;     // bf16 mask input
+};
+
+struct ConvArgs {
+  int N, H, W;
+  int tiles_x, tiles_y, m_tiles, n_tiles;
+  int cin_chunks;        // Cin / 64
+  int a_chunks_per_map;  // 64-channel K chunks served by each input map
+  int o_chunks_per_map;  // 64-channel output chunks served by each bf16 output map
+  int cout;              // total output channels (packed-row order)
+  int stages;            // smem pipeline depth
+  float alpha;           // scale on (acc + bias) (res_scale / gradient scale)
+  const float* bias;     // [cout] in packed-row order, or nullptr
+  float* pool_partial;   // [m_tiles][2][cout]
+  float* out_nchw;       // BN == 16 variant only: fp32 NCHW [N][cout_real][H][W]
+  int cout_real;         // BN == 16 variant only: number of real output channels (<= 16)
+  uint32_t flags;
+};
+
+constexpr int kTileH = 8, kTileW = 16, kTileM = 128;
+constexpr int kABytes = kTileM * 128;       // one A stage: 128 pixels x 64 bf16
+constexpr int kStgF32Bytes = 2 * kABytes;   // fp32 staging: two 32-channel halves
+constexpr int kStgBf16Bytes = kABytes;
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 192;
+
+__host__ __device__ constexpr int conv_b_block_bytes(int bn) { return bn * 128; }
+
+// Dynamic smem: [stg_f32 | stg_bf16 | resident B (optional) | stages x (A [+ B])], 1024-byte aligned.
+__host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, int stages) {
+  size_t s = 1024 + kStgF32Bytes + kStgBf16Bytes;
+  if (resident_b) s += size_t(9) * cin_chunks * conv_b_block_bytes(bn);
+  s += size_t(stages) * (kABytes + (resident_b ? 0 : conv_b_block_bytes(bn)));
+  return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int BN, bool RESIDENT_B>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
+  static_assert(BN == 16 || BN == 64 || BN == 128 || BN == 256, "BN must be 16, 64, 128 or 256");
+  constexpr int kBBlock = BN * 128;
+  constexpr uint32_t kTmemCols = 2 * BN;   // 32 is the minimum TMEM allocation
+  constexpr int kChunksPerTile = BN / 64;  // 0 for the thin (BN = 16) NCHW-output variant
+  constexpr uint32_t kIdesc = make_idesc_bf16(128, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t b_bar;
+  __shared__ __align__(8) uint64_t in_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[BN];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = args.stages;
+  const int kblocks = 9 * args.cin_chunks;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_f32 = smem;
+  uint8_t* stg_bf16 = smem + kStgF32Bytes;
+  uint8_t* b_res = stg_bf16 + kStgBf16Bytes;
+  uint8_t* stage0 = b_res + (RESIDENT_B ? kblocks * kBBlock : 0);
+  constexpr int kStageBytes = kABytes + (RESIDENT_B ? 0 : kBBlock);
+
+  const int n_tile = blockIdx.x % args.n_tiles;
+  const int mt_first = blockIdx.x / args.n_tiles;
+  const int mt_stride = gridDim.x / args.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 128);
+    }
+    mbar_init(&b_bar, 1);
+    mbar_init(&in_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.w);
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_s);
+  for (int i = threadIdx.x; i < BN; i += kConvThreads)
+    bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int tiles_per_img = args.tiles_x * args.tiles_y;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      if (RESIDENT_B) {
+        mbar_expect_tx(&b_bar, uint32_t(kblocks) * kBBlock);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / args.cin_chunks, chunk = kb % args.cin_chunks;
+          tma_load_3d(b_res + kb * kBBlock, &maps.w, &b_bar, chunk * 64, n_tile * BN, tap);
+        }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
+        const int n = mt / tiles_per_img;
+        const int rem = mt - n * tiles_per_img;
+        const int y0 = (rem / args.tiles_x) * kTileH;
+        const int x0 = (rem % args.tiles_x) * kTileW;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int tap = kb / args.cin_chunks, chunk = kb % args.cin_chunks;
+          const int ky = tap / 3, kx = tap % 3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = stage0 + stage * kStageBytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          const int mi = chunk / args.a_chunks_per_map;
+          const int c0 = (chunk % args.a_chunks_per_map) * 64;
+          tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c0, x0 + kx - 1, y0 + ky - 1, n);
+          if (!RESIDENT_B) tma_load_3d(sa + kABytes, &maps.w, &full_bar[stage], chunk * 64, n_tile * BN, tap);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      if (RESIDENT_B) mbar_wait(&b_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(stage0 + stage * kStageBytes);
+          const uint32_t b_addr = RESIDENT_B ? smem_u32(b_res + kb * kBBlock) : a_addr + kABytes;
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSw128);
+          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSw128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
+            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (128 threads)
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;               // pixel row of the tile == TMEM lane
+    const int et = (warp - 2) * 32 + lane;       // 0..127, et==0 is the TMA issuing thread
+    const int ly = row >> 4, lx = row & 15;
+    const uint32_t flags = args.flags;
+    const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
+    const uint32_t swz = uint32_t(row & 7);
+    uint8_t* my_f32 = stg_f32 + row * 128;
+    uint8_t* my_bf16 = stg_bf16 + row * 128;
+    uint32_t in_phase = 0;
+    int it = 0;
+    if constexpr (BN == 16) {
+      // thin tail conv (C -> out_feats <= 16): fp32 NCHW written straight from registers, no staging
+      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+        const int n = mt / tiles_per_img;
+        const int rem = mt - n * tiles_per_img;
+        const int y = (rem / args.tiles_x) * kTileH + ly;
+        const int x = (rem % args.tiles_x) * kTileW + lx;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        if (y < args.H && x < args.W) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            if (c < args.cout_real)
+              args.out_nchw[((size_t(n) * args.cout_real + c) * args.H + y) * args.W + x] =
+                  (__uint_as_float(v[c]) + bias_s[c]) * args.alpha;
+        }
+      }
+    } else
+    for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+      const int n = mt / tiles_per_img;
+      const int rem = mt - n * tiles_per_img;
+      const int y0 = (rem / args.tiles_x) * kTileH;
+      const int x0 = (rem % args.tiles_x) * kTileW;
+      const bool valid = (y0 + ly < args.H) && (x0 + lx < args.W);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      for (int j = 0; j < kChunksPerTile; ++j) {
+        const int oc = n_tile * kChunksPerTile + j;  // 64-channel output chunk index
+        // -- staging buffers become free once earlier TMA stores have finished reading them
+        if (et == 0) {
+          tma_store_wait_read0();
+          if (has_in) {
+            uint32_t bytes = 0;
+            if (flags & kConvResF32) bytes += kStgF32Bytes;
+            if (flags & kConvMask) bytes += kStgBf16Bytes;
+            mbar_expect_tx(&in_bar, bytes);
+            if (flags & kConvResF32) {
+              tma_load_4d(stg_f32, &maps.rf, &in_bar, oc * 64, x0, y0, n);
+              tma_load_4d(stg_f32 + kABytes, &maps.rf, &in_bar, oc * 64 + 32, x0, y0, n);
+            }
+            if (flags & kConvMask) tma_load_4d(stg_bf16, &maps.mb, &in_bar, oc * 64, x0, y0, n);
+          }
+        }
+        if (j == 0) {
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          tc_fence_after();
+        }
+        if (has_in) {
+          mbar_wait(&in_bar, in_phase);
+          in_phase ^= 1;
+        } else {
+          named_bar_sync(1, 128);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + j * 64 + h * 32);
+          tmem_ld32(taddr, v);
+          tmem_ld_wait();
+          if (j == kChunksPerTile - 1 && h == 1) {
+            tc_fence_before();
+            mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
+          }
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]) + bias_s[j * 64 + h * 32 + i];
+            if (flags & kConvRelu) x = fmaxf(x, 0.f);
+            f[i] = x * args.alpha;
+          }
+          if (flags & kConvMask) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 m = *reinterpret_cast<const uint4*>(my_bf16 + (((uint32_t(h * 4 + c)) ^ swz) << 4));
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t lo = mw[e] & 0xFFFFu, hi = mw[e] >> 16;
+                if (!(lo != 0 && lo < 0x8000u)) f[c * 8 + e * 2] = 0.f;
+                if (!(hi != 0 && hi < 0x8000u)) f[c * 8 + e * 2 + 1] = 0.f;
+              }
+            }
+          }
+          if (flags & kConvResF32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 r = *reinterpret_cast<const float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4));
+              f[c * 4 + 0] += r.x; f[c * 4 + 1] += r.y; f[c * 4 + 2] += r.z; f[c * 4 + 3] += r.w;
+            }
+          }
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = 0.f;
+          }
+          if (flags & kConvOutF32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4)) =
+                  make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+          }
+          if (flags & kConvOutBf16) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(my_bf16 + ((uint32_t(h * 4 + c) ^ swz) << 4)) =
+                  make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
+                             pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]));
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (et == 0) {
+          if (flags & kConvOutF32) {
+            tma_store_4d(&maps.of, stg_f32, oc * 64, x0, y0, n);
+            tma_store_4d(&maps.of, stg_f32 + kABytes, oc * 64 + 32, x0, y0, n);
+          }
+          if (flags & kConvOutBf16) {
+            const int mi = oc / args.o_chunks_per_map;
+            const int c0 = (oc % args.o_chunks_per_map) * 64;
+            tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
+          }
+          tma_store_commit();
+        }
+        if (flags & kConvPool) {
+          // channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves
+          const int c = et & 63, half = et >> 6;
+          float s = 0.f;
+          if (flags & kConvOutF32) {
+            const uint8_t* base = stg_f32 + (c >> 5) * kABytes + (c & 3) * 4;
+            const uint32_t ch = uint32_t((c & 31) >> 2);
+#pragma unroll 8
+            for (int r = half * 64; r < half * 64 + 64; ++r)
+              s += *reinterpret_cast<const float*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
+          } else {
+            const uint8_t* base = stg_bf16 + (c & 7) * 2;
+            const uint32_t ch = uint32_t(c >> 3);
+#pragma unroll 8
+            for (int r = half * 64; r < half * 64 + 64; ++r) {
+              const uint16_t b = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
+              s += __uint_as_float(uint32_t(b) << 16);
+            }
+          }
+          args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = s;
+          named_bar_sync(3, 128);  // staging may be refilled (input TMA) only after every reader is done
+        }
+      }
+    }
+    if (et == 0) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+}  // namespace rb

@@ -1,0 +1,57 @@
+// Host-side declarations shared by api.cu / net.cu.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "conv3x3_tc.cuh"
+
+namespace rb {
+
+extern thread_local std::string g_last_error;
+int set_error(int code, const char* fmt, ...);
+int device_info(int* num_sms);
+int grid_for(size_t work_items, int block, int per_sm);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(-3, "%s launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+// One convolution call, host view.
+struct ConvDesc {
+  const void* x;          // bf16 NHWC input (see in_r)
+  const void* w;          // packed bf16 weights
+  const float* bias;      // packed-row order or null
+  const float* residual;  // fp32 NHWC or null
+  const void* mask;       // bf16 NHWC or null
+  void* y_bf16;           // bf16 out or null (see out_r)
+  float* y_f32;           // fp32 out or null
+  float* pool_partial;    // CA pool partials or null
+  float* out_nchw;        // thin tail variant: fp32 NCHW output
+  int cout_real;          // thin tail variant
+  int N, H, W, Cin, Cout;
+  int in_r, out_r;        // pixel-unshuffle on load / pixel-shuffle on store
+  int force_bn;           // 0 = auto
+  unsigned flags;
+  float alpha;
+};
+
+// Everything a launch needs: tensor maps (host copy, passed by value as __grid_constant__) + args.
+struct ConvPlan {
+  ConvMaps maps;
+  ConvArgs args;
+  int bn;
+  bool resident;
+  int grid;
+  size_t smem;
+};
+
+int conv_plan_build(ConvPlan* p, const ConvDesc& d);
+int conv_plan_launch(const ConvPlan& p, cudaStream_t s);
+
+}  // namespace rb

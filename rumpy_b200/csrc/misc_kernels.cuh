@@ -1,0 +1,187 @@
+// CUDA-core kernels around the tensor-core convolution: weight packing, the thin head conv, the fused
+// channel-attention (CALayer) FC + rescale + residual pass, L1 loss and Adam.  All are memory-bound
+// streaming kernels: coalesced 16-byte accesses, grid sized in multiples of the SM count by the host.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace rb {
+
+// ------------------------------------------------------------------------------------------------
+// OIHW fp32 -> packed bf16 operand for conv3x3_tc_kernel.
+//   forward : P[tap][row][ci]            = W[o(row)][ci][ky][kx],            tap = ky*3+kx
+//   dgrad   : P[tap][ci ][col]           = W[o(col)][ci][2-ky][2-kx]   (rows = Cin, K = Cout)
+// o(row) applies the pixel-shuffle permutation when r > 1: row = q*(Cout/r^2) + c  <->  o = c*r^2 + q,
+// so that output chunk q holds the channels of sub-pixel q (nn.PixelShuffle, reference common.py:33,40).
+// Rows >= valid rows are zero filled (thin tail conv pads Cout 3 -> 16).
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ p, int cout, int cin,
+                                    int rows_padded, int r, int dgrad) {
+  const int rows = dgrad ? cin : rows_padded;   // rows of the packed [tap][rows][k] operand
+  const int kdim = dgrad ? cout : cin;
+  const size_t total = size_t(9) * rows * kdim;
+  const int rr = r * r;
+  const int cpp = cout / rr;  // channels per sub-pixel
+  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += size_t(gridDim.x) * blockDim.x) {
+    const int k = int(idx % kdim);
+    const int row = int((idx / kdim) % rows);
+    const int tap = int(idx / (size_t(kdim) * rows));
+    const int ky = tap / 3, kx = tap % 3;
+    float v = 0.f;
+    if (!dgrad) {
+      if (row < cout) {
+        const int o = (r > 1) ? (row % cpp) * rr + row / cpp : row;
+        v = w[((size_t(o) * cin + k) * 3 + ky) * 3 + kx];
+      }
+    } else {
+      const int o = (r > 1) ? (k % cpp) * rr + k / cpp : k;
+      v = w[((size_t(o) * cin + row) * 3 + (2 - ky)) * 3 + (2 - kx)];
+    }
+    p[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// bias in packed-row order (pixel-shuffle permutation), zero padded
+__global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ p, int cout, int rows_padded,
+                                 int r) {
+  const int rr = r * r, cpp = cout / rr;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < rows_padded; row += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (row < cout) v = b[(r > 1) ? (row % cpp) * rr + row / cpp : row];
+    p[row] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head conv: in_feats (3) -> C, fp32 NCHW input (the reference's tensor layout), fp32 math,
+// writes the fp32 residual stream and its bf16 operand copy in NHWC.  (architectures.py:153,172)
+// One thread = one pixel x 8 output channels; weights transposed in smem as [ci*9+tap][C].
+// ------------------------------------------------------------------------------------------------
+template <int CIN_MAX = 4>
+__global__ void head_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                 const float* __restrict__ bias, float* __restrict__ yf,
+                                 __nv_bfloat16* __restrict__ yb, int N, int H, int W, int cin, int C) {
+  extern __shared__ float wsm[];  // [cin*9][C] then bias[C]
+  const int kk = cin * 9;
+  for (int i = threadIdx.x; i < kk * C; i += blockDim.x) {
+    const int o = i % C, k = i / C;          // k = ci*9 + tap
+    wsm[i] = w[size_t(o) * kk + k];
+  }
+  float* bsm = wsm + kk * C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) bsm[i] = bias[i];
+  __syncthreads();
+  const int groups = C / 8;
+  const size_t npix = size_t(N) * H * W;
+  for (size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x; t < npix * groups;
+       t += size_t(gridDim.x) * blockDim.x) {
+    const int g = int(t % groups);
+    const size_t pix = t / groups;
+    const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bsm[g * 8 + j];
+    for (int ci = 0; ci < cin; ++ci) {
+      const float* xp = x + (size_t(n) * cin + ci) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = yh + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = xw + kx - 1;
+          if (xx < 0 || xx >= W) continue;
+          const float v = __ldg(xp + size_t(yy) * W + xx);
+          const float* wp = wsm + (ci * 9 + ky * 3 + kx) * C + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+        }
+      }
+    }
+    float4* of = reinterpret_cast<float4*>(yf + pix * C + g * 8);
+    of[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    of[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[4], acc[5]), b3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+    o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(yb + pix * C + g * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Channel attention, fused:  y = sigmoid(W2 relu(W1 mean(u) + b1) + b2);  x_out = x_in + u * y
+// (CALayer architectures.py:41-44 + the RCAB skip :83).  The global average pool arrives as per-tile
+// partial sums written by conv2's epilogue, so `u` is read exactly once here.  Every CTA recomputes
+// the tiny FC for its image (C<=256, C/r hidden) in smem -- cheaper than another launch.
+// grid = (chunks, N); block = 256.  u is fp32 or bf16 NHWC.
+// ------------------------------------------------------------------------------------------------
+template <bool U_F32>
+__global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int partials_per_img,
+                                const void* __restrict__ u_, const float* __restrict__ x_in,
+                                const float* __restrict__ w1, const float* __restrict__ b1,
+                                const float* __restrict__ w2, const float* __restrict__ b2,
+                                float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_b,
+                                float* __restrict__ save_mean, float* __restrict__ save_hid,
+                                float* __restrict__ save_y, int HW, int C, int Cr) {
+  __shared__ float mean_s[256], y_s[256], hid_s[64];
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  if (tid < C) {
+    const float* pp = pool_partial + size_t(n) * partials_per_img * C + tid;
+    float s = 0.f;
+    for (int i = 0; i < partials_per_img; ++i) s += pp[size_t(i) * C];   // fixed order: deterministic
+    mean_s[tid] = s / float(HW);
+  }
+  __syncthreads();
+  {  // hidden layer: one warp per hidden unit (strided), warp-shuffle reduction over C
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < Cr; j += nwarps) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s = fmaf(w1[j * C + c], mean_s[c], s);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) hid_s[j] = fmaxf(s + b1[j], 0.f);
+    }
+  }
+  __syncthreads();
+  if (tid < C) {
+    float s = b2[tid];
+    for (int j = 0; j < Cr; ++j) s = fmaf(w2[tid * Cr + j], hid_s[j], s);
+    y_s[tid] = 1.f / (1.f + __expf(-s));
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && save_y != nullptr) {
+    if (tid < C) { save_y[n * C + tid] = y_s[tid]; save_mean[n * C + tid] = mean_s[tid]; }
+    if (tid < Cr) save_hid[n * Cr + tid] = hid_s[tid];
+  }
+  // elementwise: 4 channels per thread
+  const int vec_per_pix = C / 4;
+  const size_t total = size_t(HW) * vec_per_pix;
+  const size_t base = size_t(n) * HW * C;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c4 = int(i % vec_per_pix) * 4;
+    const size_t off = base + i * 4;
+    float4 uu;
+    if (U_F32) {
+      uu = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(u_) + off);
+    } else {
+      const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(u_) + off);
+      uu.x = __uint_as_float(raw.x << 16); uu.y = __uint_as_float(raw.x & 0xFFFF0000u);
+      uu.z = __uint_as_float(raw.y << 16); uu.w = __uint_as_float(raw.y & 0xFFFF0000u);
+    }
+    const float4 xi = *reinterpret_cast<const float4*>(x_in + off);
+    float4 o;
+    o.x = fmaf(uu.x, y_s[c4], xi.x); o.y = fmaf(uu.y, y_s[c4 + 1], xi.y);
+    o.z = fmaf(uu.z, y_s[c4 + 2], xi.z); o.w = fmaf(uu.w, y_s[c4 + 3], xi.w);
+    *reinterpret_cast<float4*>(x_out + off) = o;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(x_out_b + off) = pk;
+  }
+}
+
+}  // namespace rb
