@@ -2,7 +2,7 @@
  *
  * This is the drop-in boundary.  The reference (um-dsrg/RUMpy) has no native code:
  * its trunk calls stock torch.nn modules.  Each entry point below replaces one of those call sites;
- * the Python mirror of the reference's block library (rumpy_b200/SISR/models/advanced/*.py) binds them
+ * the Python mirror of the reference's block library (rumpy_b200/SISR/models/advanced/ *.py) binds them
  * through ctypes (see INTEGRATION.md for the stub a RUMpy maintainer would add).
  *
  * Conventions
@@ -88,6 +88,34 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
                    const float* b1, const float* w2, const float* b2, float* x_out, void* x_out_bf16,
                    float* save_mean, float* save_hid, float* save_y, int N, int H, int W, int C, int Cr,
                    void* stream);
+
+/* Layout plumbing between the reference's fp32 NCHW tensors and the kernels' NHWC tensors (block-level use;
+ * whole networks convert inside the head / tail convs).  Either output of nchw_to_nhwc may be NULL. */
+int rumpy_nchw_to_nhwc(const float* x_nchw, float* y_f32, void* y_bf16, int N, int C, int H, int W, void* stream);
+int rumpy_nhwc_to_nchw(const void* x_nhwc, int x_is_bf16, float* y_nchw, int N, int C, int H, int W, void* stream);
+/* Per-image channel sums in pool_partial format, for a stand-alone CALayer.forward (architectures.py:41-42:
+ * nn.AdaptiveAvgPool2d(1)); inside an RCAB the sums come from rumpy_conv3x3(..., RUMPY_CONV_POOL). */
+int rumpy_pool_sum(const float* x_nhwc, float* pool_partial, int N, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Whole-network executor: one call enqueues every kernel of RCAN.forward / EDSR.forward
+ * (architectures.py:171-176, 236-241).  `params` are the module's fp32 parameters as device pointers in
+ * state_dict order; `packed` (rumpy_net_packed_bytes) and `workspace` (rumpy_net_workspace_bytes)
+ * are caller-owned device buffers.  The handle caches the per-layer launch plan (TMA descriptors) for the last
+ * (packed, workspace, N, H, W, training) it saw; a steady-state forward only launches kernels and is
+ * CUDA-graph capturable.  arch: 0 = RCAN (n_groups x n_blocks RCABs), 1 = EDSR (n_blocks ResBlocks).
+ * x: fp32 NCHW [N,in_feats,H,W] -> y: fp32 NCHW [N,out_feats,H*scale,W*scale], the reference's tensors.
+ * training != 0 keeps every activation backward needs in the workspace.
+ * ------------------------------------------------------------------------------------------------- */
+int rumpy_net_create(void** net, int arch, int n_feats, int n_groups, int n_blocks, int reduction, int scale,
+                     float res_scale, int in_feats, int out_feats, int u_f32);
+int rumpy_net_destroy(void* net);
+int rumpy_net_num_params(void* net);
+long long rumpy_net_packed_bytes(void* net);
+long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training);
+int rumpy_net_pack(void* net, const float* const* params, void* packed, void* stream);
+int rumpy_net_forward(void* net, const float* const* params, const void* packed, const float* x_nchw,
+                      float* y_nchw, void* workspace, int N, int H, int W, int training, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,19 @@ SIGNATURES = {
     'rumpy_conv3x3_tail': [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp],
     'rumpy_head_conv': [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     'rumpy_ca_apply': [_fp, _vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp],
+    'rumpy_nchw_to_nhwc': [_fp, _fp, _vp, _i, _i, _i, _i, _vp],
+    'rumpy_nhwc_to_nchw': [_vp, _i, _fp, _i, _i, _i, _i, _vp],
+    'rumpy_pool_sum': [_fp, _fp, _i, _i, _i, _i, _vp],
+    'rumpy_net_create': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i],
+    'rumpy_net_destroy': [_vp],
+    'rumpy_net_num_params': [_vp],
+    'rumpy_net_packed_bytes': [_vp],
+    'rumpy_net_workspace_bytes': [_vp, _i, _i, _i, _i],
+    'rumpy_net_pack': [_vp, _vp, _vp, _vp],
+    'rumpy_net_forward': [_vp, _vp, _vp, _fp, _fp, _vp, _i, _i, _i, _i, _vp],
 }
+
+_LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes'}
 
 _lib = None
 
@@ -47,7 +59,8 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_char_p if name == 'rumpy_last_error' else ctypes.c_int
+        fn.restype = (ctypes.c_char_p if name == 'rumpy_last_error' else
+                      ctypes.c_longlong if name in _LONGLONG else ctypes.c_int)
     _lib = lib
     return lib
 

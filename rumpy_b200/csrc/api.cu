@@ -308,4 +308,33 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
   return check_launch("ca_apply");
 }
 
+int rumpy_nchw_to_nhwc(const float* x, float* y_f32, void* y_bf16, int N, int C, int H, int W, void* stream) {
+  if (int e = device_info(nullptr)) return e;
+  if (!x || (!y_f32 && !y_bf16) || N <= 0 || C <= 0 || H <= 0 || W <= 0)
+    return set_error(RUMPY_ERR_ARG, "nchw_to_nhwc: bad args");
+  const int P = H * W;
+  dim3 grid((P + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, cudaStream_t(stream)>>>(x, y_f32, static_cast<__nv_bfloat16*>(y_bf16), C, P);
+  return check_launch("nchw_to_nhwc");
+}
+
+int rumpy_nhwc_to_nchw(const void* x, int x_is_bf16, float* y, int N, int C, int H, int W, void* stream) {
+  if (int e = device_info(nullptr)) return e;
+  if (!x || !y || N <= 0 || C <= 0 || H <= 0 || W <= 0) return set_error(RUMPY_ERR_ARG, "nhwc_to_nchw: bad args");
+  const int P = H * W;
+  dim3 grid((P + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  if (x_is_bf16) nhwc_to_nchw_kernel<true><<<grid, block, 0, cudaStream_t(stream)>>>(x, y, C, P);
+  else nhwc_to_nchw_kernel<false><<<grid, block, 0, cudaStream_t(stream)>>>(x, y, C, P);
+  return check_launch("nhwc_to_nchw");
+}
+
+int rumpy_pool_sum(const float* x_nhwc, float* pool_partial, int N, int H, int W, int C, void* stream) {
+  if (int e = device_info(nullptr)) return e;
+  if (!x_nhwc || !pool_partial || C <= 0 || C > 256) return set_error(RUMPY_ERR_ARG, "pool_sum: bad args");
+  const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const int block = (1024 / C) * C;
+  pool_sum_kernel<<<N, block, block * sizeof(float), cudaStream_t(stream)>>>(x_nhwc, pool_partial, tiles * 2, H * W, C);
+  return check_launch("pool_sum");
+}
+
 }  // extern "C"

@@ -184,4 +184,72 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Layout plumbing at block boundaries: the reference's tensors are fp32 NCHW, the kernels' are NHWC.
+// Tiled 32x32 transposes through padded smem: coalesced on both sides.   [N][C][P] <-> [N][P][C]
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ yf,
+                                    __nv_bfloat16* __restrict__ yb, int C, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + size_t(n) * C * P;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < P) ? xn[size_t(c) * P + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < P && c < C) {
+      const float v = tile[threadIdx.x][i];
+      const size_t o = (size_t(n) * P + p) * C + c;
+      if (yf) yf[o] = v;
+      if (yb) yb[o] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+template <bool X_BF16>
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x_, float* __restrict__ y, int C, int P) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < P && c < C) {
+      const size_t o = (size_t(n) * P + p) * C + c;
+      v = X_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(x_)[o]) : static_cast<const float*>(x_)[o];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < P) y[(size_t(n) * C + c) * P + p] = tile[threadIdx.x][i];
+  }
+}
+
+// Per-image channel sums of an fp32 NHWC tensor in the pool_partial format ([N][partials][C]; slot 0 gets
+// the sum, the remaining slots zero).  Only used by the stand-alone CALayer.forward; inside RCAB the sums
+// come for free from conv2's epilogue.
+__global__ void pool_sum_kernel(const float* __restrict__ x, float* __restrict__ pool_partial, int partials, int HW,
+                                int C) {
+  extern __shared__ float red[];  // [blockDim.x]
+  const int n = blockIdx.x;
+  const int lanes_per_c = blockDim.x / C;            // blockDim.x is a multiple of C
+  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  float s = 0.f;
+  if (lane < lanes_per_c)
+    for (int p = lane; p < HW; p += lanes_per_c) s += x[(size_t(n) * HW + p) * C + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int l = 0; l < lanes_per_c; ++l) t += red[l * C + threadIdx.x];
+    float* pp = pool_partial + size_t(n) * partials * C;
+    pp[threadIdx.x] = t;
+    for (int i = 1; i < partials; ++i) pp[size_t(i) * C + threadIdx.x] = 0.f;
+  }
+}
+
 }  // namespace rb

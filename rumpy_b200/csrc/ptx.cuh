@@ -51,7 +51,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef RB_WATCHDOG_CYCLES
 #define RB_WATCHDOG_CYCLES (4000000000ll)
 #endif
-__device__ __noinline__ void mbar_watchdog_fail(uint64_t* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_watchdog_fail(uint64_t* bar, uint32_t parity) {
   printf("rumpy_b200: mbarrier watchdog: block %d thread %d bar@%u parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
          smem_u32(bar), parity);
   __trap();

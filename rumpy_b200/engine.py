@@ -1,0 +1,130 @@
+"""Whole-network executor binding (rumpy_net_* in include/rumpy_b200.h).
+
+`TrunkEngine` owns, for one RCAN / EDSR module: the native net handle, the packed bf16 weight buffer, the
+activation workspace and (optionally) a captured CUDA graph of the forward.  PyTorch supplies device
+memory and streams only; every FLOP runs in librumpy_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+ARCH_RCAN, ARCH_EDSR = 0, 1
+
+
+class TrunkEngine:
+    def __init__(self, arch, params, *, n_feats, n_groups, n_blocks, reduction=16, scale=4, res_scale=1.0,
+                 in_feats=3, out_feats=3, u_f32=True):
+        self.lib = _lib.load()
+        self.arch, self.scale, self.in_feats, self.out_feats = arch, scale, in_feats, out_feats
+        self.params = list(params)
+        h = ctypes.c_void_p()
+        _lib.call('rumpy_net_create', ctypes.byref(h), arch, n_feats, n_groups, n_blocks, reduction, scale,
+                  float(res_scale), in_feats, out_feats, int(u_f32))
+        self.handle = h
+        n = self.lib.rumpy_net_num_params(h)
+        if n != len(self.params):
+            raise _lib.RumpyB200Error(f'parameter count mismatch: native {n} vs module {len(self.params)}')
+        self.device = self.params[0].device
+        if self.device.type != 'cuda':
+            raise _lib.RumpyB200Error('rumpy_b200 has no CPU path: move the model to a CUDA (sm_100) device')
+        self.packed = torch.empty(self.lib.rumpy_net_packed_bytes(h), dtype=torch.uint8, device=self.device)
+        self._ptr_array = None
+        self._ptr_sig = None
+        self._pack_sig = None
+        self._ws = {}
+        self._graphs = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None):
+                self.lib.rumpy_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameter tracking
+    def _param_ptrs(self):
+        sig = tuple(p.data_ptr() for p in self.params)
+        if sig != self._ptr_sig:
+            for p in self.params:
+                if p.dtype != torch.float32 or not p.is_contiguous() or p.device != self.device:
+                    raise _lib.RumpyB200Error('parameters must be contiguous fp32 tensors on one CUDA device')
+            self._ptr_array = (ctypes.c_void_p * len(sig))(*sig)
+            self._ptr_sig = sig
+            self._pack_sig = None
+            self._graphs.clear()
+        return self._ptr_array
+
+    def refresh_weights(self, force=False):
+        """Repacks fp32 OIHW parameters into the bf16 tensor-core operand layout when they changed."""
+        ptrs = self._param_ptrs()
+        sig = tuple(p._version for p in self.params)
+        if force or sig != self._pack_sig:
+            _lib.call('rumpy_net_pack', self.handle, ptrs, self.packed.data_ptr(),
+                      torch.cuda.current_stream().cuda_stream)
+            self._pack_sig = sig
+        return ptrs
+
+    def workspace(self, N, H, W, training):
+        key = (N, H, W, bool(training))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = self.lib.rumpy_net_workspace_bytes(self.handle, N, H, W, int(training))
+            if nbytes < 0:
+                raise _lib.RumpyB200Error('workspace query failed')
+            self._ws = {k: v for k, v in self._ws.items() if k[3] != key[3]}   # keep one per mode
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def _check_input(self, x):
+        if x.device != self.device:
+            raise _lib.RumpyB200Error(f'input on {x.device}, model on {self.device} (no CPU fallback)')
+        if x.dim() != 4 or x.shape[1] != self.in_feats:
+            raise ValueError(f'expected N x {self.in_feats} x H x W input, got {tuple(x.shape)}')
+        return x.contiguous().float()
+
+    def forward(self, x, training=False, out=None):
+        x = self._check_input(x)
+        N, _, H, W = x.shape
+        ptrs = self.refresh_weights()
+        ws = self.workspace(N, H, W, training)
+        if out is None:
+            out = torch.empty((N, self.out_feats, H * self.scale, W * self.scale), dtype=torch.float32,
+                              device=self.device)
+        _lib.call('rumpy_net_forward', self.handle, ptrs, self.packed.data_ptr(), x.data_ptr(), out.data_ptr(),
+                  ws.data_ptr(), N, H, W, int(training), torch.cuda.current_stream().cuda_stream)
+        return out
+
+    # ------------------------------------------------------------------ CUDA-graph replay (inference)
+    def forward_graphed(self, x):
+        """Forward through a captured CUDA graph (static shapes, weights assumed unchanged between calls
+        unless refresh_weights() sees new versions -- repacking happens outside the graph)."""
+        x = self._check_input(x)
+        self.refresh_weights()
+        key = tuple(x.shape)
+        g = self._graphs.get(key)
+        if g is None:
+            sx = torch.empty_like(x)
+            sy = torch.empty((x.shape[0], self.out_feats, x.shape[2] * self.scale, x.shape[3] * self.scale),
+                             dtype=torch.float32, device=self.device)
+            sx.copy_(x)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.forward(sx, out=sy)      # warm-up: builds the plan, sets kernel attributes
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.forward(sx, out=sy)
+            g = (graph, sx, sy)
+            self._graphs = {key: g}
+        graph, sx, sy = g
+        sx.copy_(x)
+        graph.replay()
+        return sy

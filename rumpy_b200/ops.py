@@ -101,3 +101,32 @@ def ca_apply(pool_partial, u, x_in, w1, b1, w2, b2, x_out, x_out_bf16, *, N, H, 
     _lib.call('rumpy_ca_apply', pool_partial.data_ptr(), u.data_ptr(), int(u_is_f32), x_in.data_ptr(),
               w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), x_out.data_ptr(), x_out_bf16.data_ptr(),
               _ptr(sm), _ptr(sh), _ptr(sy), N, H, W, C, Cr, _stream())
+
+
+def nchw_to_nhwc(x, want_f32=True, want_bf16=True):
+    """fp32 NCHW -> (fp32 NHWC | None, bf16 NHWC | None)."""
+    _chk(x, torch.float32, 'x')
+    N, C, H, W = x.shape
+    yf = torch.empty((N, H, W, C), dtype=torch.float32, device=x.device) if want_f32 else None
+    yb = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    _lib.call('rumpy_nchw_to_nhwc', x.data_ptr(), _ptr(yf), _ptr(yb), N, C, H, W, _stream())
+    return yf, yb
+
+
+def nhwc_to_nchw(x):
+    """fp32 / bf16 NHWC -> fp32 NCHW."""
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda or not x.is_contiguous():
+        raise ValueError('nhwc_to_nchw: expected contiguous CUDA fp32/bf16 tensor')
+    N, H, W, C = x.shape
+    y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    _lib.call('rumpy_nhwc_to_nchw', x.data_ptr(), int(x.dtype == torch.bfloat16), y.data_ptr(), N, C, H, W,
+              _stream())
+    return y
+
+
+def pool_sum(x_nhwc):
+    _chk(x_nhwc, torch.float32, 'x')
+    N, H, W, C = x_nhwc.shape
+    pp = torch.empty((N * tiles_per_image(H, W), 2, C), dtype=torch.float32, device=x_nhwc.device)
+    _lib.call('rumpy_pool_sum', x_nhwc.data_ptr(), pp.data_ptr(), N, H, W, C, _stream())
+    return pp

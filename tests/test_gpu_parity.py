@@ -1,0 +1,164 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  The CUDA path is called through the reference-facing
+module API (which binds the C ABI); the checker is the committed golden output of the unmodified reference
+(tests/golden/*.npz) or the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json's: output max-abs error <= 1e-2 on [0,1]-range images; PSNR within 0.02 dB;
+PixelShuffle / indexing bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import recipe
+from oracle import sr_numpy, sr_torch_cpu
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+def _build(arch, kw, sd):
+    from rumpy_b200.SISR.models.advanced.architectures import RCAN, EDSR
+    if arch == 'rcan':
+        net = RCAN(n_resblocks=kw['n_resblocks'], n_resgroups=kw['n_resgroups'], n_feats=kw['n_feats'],
+                   scale=kw['scale'])
+    else:
+        net = EDSR(net_features=kw['n_feats'], num_blocks=kw['num_blocks'], scale=kw['scale'],
+                   res_scale=kw['res_scale'])
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return net.to(_dev()).eval()
+
+
+def test_library_loaded_and_device_ok():
+    from rumpy_b200 import _lib, ops
+    _lib.load()
+    ops.device_check()
+
+
+@pytest.mark.parametrize('name', list(recipe.CASES))
+def test_network_forward_vs_reference_golden(golden_dir, name):
+    gold = np.load(os.path.join(golden_dir, name + '.npz'))
+    arch, kw, sd, x, y = recipe.case_tensors(name)
+    net = _build(arch, kw, sd)
+    with torch.no_grad():
+        out = net(torch.from_numpy(x).to(_dev())).cpu().numpy()
+    assert out.shape == gold['out'].shape
+    err = np.abs(out - gold['out']).max()
+    assert err <= TOL, f'{name}: max-abs {err}'
+
+
+def test_blocks_vs_reference_golden(golden_dir):
+    from rumpy_b200.SISR.models.advanced import architectures as A, common as Cm
+    gold = np.load(os.path.join(golden_dir, 'blocks.npz'))
+    act = torch.nn.ReLU(True)
+    mods = {
+        'calayer': A.CALayer(64, 16),
+        'rcab': A.RCAB(Cm.default_conv, 64, 3, 16, act=act),
+        'resgroup': A.ResidualGroup(Cm.default_conv, 64, 3, 16, act=act, res_scale=1, n_resblocks=2),
+        'resblock': Cm.ResBlock(Cm.default_conv, 64, 3, act=act, res_scale=0.1),
+        'upsampler2': Cm.Upsampler(Cm.default_conv, 2, 64, act=False),
+        'upsampler3': Cm.Upsampler(Cm.default_conv, 3, 64, act=False),
+        'upsampler4': Cm.Upsampler(Cm.default_conv, 4, 64, act=False),
+        'conv64': Cm.default_conv(64, 64, 3),
+    }
+    for tag, mod in mods.items():
+        spec = [(k, tuple(v.shape)) for k, v in mod.state_dict().items()]
+        assert [k for k, _ in spec] == [str(k) for k in gold[tag + '::spec_keys']], tag
+        sd = recipe.make_weights(spec, seed=sum(map(ord, tag)))
+        mod.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        mod = mod.to(_dev()).eval()
+        with torch.no_grad():
+            out = mod(torch.from_numpy(gold[tag + '::x']).to(_dev())).cpu().numpy()
+        ref = gold[tag + '::out']
+        err = np.abs(out - ref).max()
+        assert err <= 2e-2 * max(1.0, np.abs(ref).max()), f'{tag}: {err}'
+
+
+def test_pixel_shuffle_store_bit_exact():
+    """The shuffle folded into the conv store must be a pure index permutation: compare the shuffled store
+    with the un-shuffled store of the same conv, permuted by the oracle -- bit for bit."""
+    from rumpy_b200 import ops
+    dev = _dev()
+    for r in (2, 3):
+        N, H, W, C = 2, 11, 19, 64
+        g = torch.Generator(device='cuda').manual_seed(r)
+        x = (torch.rand((N, H, W, C), generator=g, device=dev) - 0.5).to(torch.bfloat16)
+        w = (torch.rand((C * r * r, C, 3, 3), generator=g, device=dev) - 0.5) / 24
+        b = torch.rand((C * r * r,), generator=g, device=dev)
+        plain = torch.empty((N, H, W, C * r * r), dtype=torch.bfloat16, device=dev)
+        ops.conv3x3(x, ops.pack_conv3x3(w), b, out_bf16=plain, N=N, H=H, W=W, Cin=C, Cout=C * r * r)
+        shuf = torch.empty((N, H * r, W * r, C), dtype=torch.bfloat16, device=dev)
+        ops.conv3x3(x, ops.pack_conv3x3(w, shuffle_r=r), ops.pack_bias(b, shuffle_r=r), out_bf16=shuf, N=N, H=H,
+                    W=W, Cin=C, Cout=C * r * r, out_shuffle_r=r)
+        torch.cuda.synchronize()
+        nchw = plain.float().permute(0, 3, 1, 2).cpu().numpy()
+        want = sr_numpy.pixel_shuffle(nchw, r)
+        got = shuf.float().permute(0, 3, 1, 2).cpu().numpy()
+        assert np.array_equal(got, want)
+
+
+def test_set5_config1_edsr_baseline(golden_dir):
+    """BASELINE.json configs[0]: EDSR-baseline x4 on the Set5 LR images; PSNR(Y) within 0.02 dB of the reference."""
+    from rumpy_b200.SISR.models.advanced.architectures import EDSR
+    gold = np.load(os.path.join(golden_dir, 'set5_edsr_baseline.npz'))
+    sd = recipe.make_weights(recipe.edsr_spec(16, 64, 4), seed=5)
+    net = EDSR()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    net = net.to(_dev()).eval()
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for f in [str(n) for n in gold['names']]:
+        x = (gold[f + '::lr_u8'].astype(np.float32) / 255.0).transpose(2, 0, 1)[None]
+        hr = (gold[f + '::hr_u8'].astype(np.float32) / 255.0).transpose(2, 0, 1)[None]
+        with torch.no_grad():
+            out = net(torch.from_numpy(x).to(_dev())).cpu().numpy()
+            ref = sr_torch_cpu.edsr_forward(tsd, torch.from_numpy(x), 16, 0.1, 4).numpy()
+        assert np.abs(out[:, :, :32, :32] - gold[f + '::out_crop']).max() <= TOL
+        assert np.abs(out[:, :, ::8, ::8] - gold[f + '::out_ds8']).max() <= TOL
+        assert np.abs(out - ref).max() <= TOL
+        p_ref = sr_numpy.psnr(sr_numpy.rgb_to_y(np.clip(ref, 0, 1)), sr_numpy.rgb_to_y(hr))
+        p_got = sr_numpy.psnr(sr_numpy.rgb_to_y(np.clip(out, 0, 1)), sr_numpy.rgb_to_y(hr))
+        assert abs(p_ref - p_got) <= 0.02, (f, p_ref, p_got)
+
+
+def test_rcan_full_config2_vs_oracle():
+    """BASELINE.json configs[1]: RCAN x4 (10 groups x 20 RCAB, 64 ch), 16 x 3 x 48 x 48, vs the CPU oracle."""
+    spec = recipe.rcan_spec(10, 20, 64, 16, 4)
+    sd = recipe.make_weights(spec, seed=8)
+    x = recipe.make_input((16, 3, 48, 48), seed=8)
+    net = _build('rcan', dict(n_resblocks=20, n_resgroups=10, n_feats=64, scale=4), sd)
+    with torch.no_grad():
+        out = net(torch.from_numpy(x).to(_dev())).cpu().numpy()
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref = sr_torch_cpu.rcan_forward({k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(x)).numpy()
+    err = np.abs(out - ref).max()
+    assert err <= TOL, f'max-abs {err}'
+    p = sr_numpy.psnr(out, ref)
+    assert p > 50, p
+
+
+def test_forward_is_deterministic_and_graph_replay_matches():
+    arch, kw, sd, x, y = recipe.case_tensors('rcan_small')
+    net = _build(arch, kw, sd)
+    xt = torch.from_numpy(x).to(_dev())
+    with torch.no_grad():
+        a = net(xt).clone()
+        b = net(xt).clone()
+        c = net.native_engine().forward_graphed(xt).clone()
+        d = net.native_engine().forward_graphed(xt).clone()
+    assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(c, d)
+
+
+def test_cpu_tensor_fails_loudly():
+    from rumpy_b200._lib import RumpyB200Error
+    arch, kw, sd, x, y = recipe.case_tensors('rcan_x2')
+    net = _build(arch, kw, sd)
+    with pytest.raises(RumpyB200Error):
+        net(torch.from_numpy(x))
