@@ -1,0 +1,318 @@
+"""Benchmark of the hot path: RCAN x4 (10 groups x 20 RCAB, 64 ch) forward on synthetic 48x48 LR patches,
+batch 16 per GPU (BASELINE.json configs[1]); metric = output Mpix/s.
+
+    python bench.py --gpus 1 --steps 50 --warmup 5                 # this repo's sm_100a path
+    python bench.py --impl reference --steps 5 --warmup 1          # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N ...                                      # weak scaling: 16 patches per GPU, no collective
+
+One JSON line on stdout (rank 0).  `value` = whole-job throughput with inputs resident in HBM (CUDA-event
+device time per step, L2 flushed between steps, max over ranks); `e2e` = the same metric through the
+reference-facing handler call `RCANHandler.run_eval` with pinned HOST buffers (H2D + D2H inside the timed
+region); `roofline` = the dominant kernel (tcgen05 conv 64->64) timed alone with CUDA events against the
+measured bf16 peak; `cpu_baseline` = the oracle port (torch-CPU restatement of the reference) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import recipe  # noqa: E402
+
+WORKLOAD = 'RCAN x4 (10 groups x 20 RCAB, 64 ch) forward, synthetic 48x48 LR patches, batch 16 per GPU'
+BATCH, LR_HW, SCALE, CH = 16, 48, 4, 64
+FLOP_PER_LR_PIXEL = 31835520          # 2*MAC over all convs of RCAN x4
+CONV64_FLOP_PER_PIXEL = 2 * 64 * 64 * 9
+OUT_MPIX_PER_STEP = BATCH * (LR_HW * SCALE) ** 2 / 1e6
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=p['bf16_tflops'], tflops_sustained=p['bf16_tflops_sustained'], hbm=p['hbm_gbs'],
+                    source='MEASURED_PEAKS.json (measured)')
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source='B200_PROFILING.md fallback')
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x2: 'applications_clocks_setting', 0x10: 'sync_boost',
+               0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop_flag and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                break
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['unavailable']}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------- workload
+def make_state_dict():
+    return recipe.make_weights(recipe.rcan_spec(10, 20, CH, 16, SCALE), seed=8)
+
+
+def cpu_forward_fn(threads):
+    """Oracle port = torch-CPU functional restatement of the reference's RCAN.forward (oracle/sr_torch_cpu.py)."""
+    from oracle import sr_torch_cpu
+    torch.set_num_threads(threads)
+    sd = {k: torch.from_numpy(v) for k, v in make_state_dict().items()}
+
+    def fwd(x):
+        with torch.no_grad():
+            return sr_torch_cpu.rcan_forward(sd, x, 10, 20, SCALE)
+    return fwd
+
+
+def time_cpu(fwd, batch, min_seconds, max_iters):
+    x = torch.from_numpy(recipe.make_input((batch, 3, LR_HW, LR_HW), seed=8))
+    fwd(x)  # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_iters and (time.perf_counter() - t_start < min_seconds or len(times) < 2):
+        t0 = time.perf_counter()
+        fwd(x)
+        times.append(time.perf_counter() - t0)
+    return float(np.median(times)), len(times)
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port), all host threads."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    fwd = cpu_forward_fn(cores)
+    x16 = torch.from_numpy(recipe.make_input((BATCH, 3, LR_HW, LR_HW), seed=8))
+    t0 = time.perf_counter()
+    fwd(x16)
+    est = time.perf_counter() - t0
+    # bound the whole run to a few minutes: shrink the per-step sample if one full batch is slow
+    budget = 150.0
+    batch = BATCH
+    while batch > 1 and est * (batch / BATCH) * (args.steps + args.warmup) > budget:
+        batch //= 2
+    x = x16[:batch].contiguous()
+    for _ in range(args.warmup):
+        fwd(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd(x)
+    dt = (time.perf_counter() - t0) / args.steps
+    mpix_s = batch * (LR_HW * SCALE) ** 2 / 1e6 / dt
+    sample = f'{batch} of {BATCH} patches per step x {args.steps} steps, fp32, torch-CPU (oneDNN)'
+    line = {
+        'impl': 'reference', 'metric': 'RCAN x4 output Mpix/s (infer)', 'value': mpix_s, 'unit': 'Mpix/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3 * (BATCH / batch),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'lr_patch': LR_HW, 'scale': SCALE},
+        'cpu_baseline': {'value': mpix_s, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': mpix_s, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def conv_kernel_roofline(device, pk):
+    """Dominant kernel alone: tcgen05 conv 64->64 (+bias+ReLU) at the workload's activation shape, 20 launches in a
+    CUDA graph, timed with CUDA events on the launching stream."""
+    from rumpy_b200 import ops
+    N, H, W, C = BATCH, LR_HW, LR_HW, CH
+    x = torch.rand((N, H, W, C), device=device).to(torch.bfloat16)
+    w = (torch.rand((C, C, 3, 3), device=device) - 0.5) / 24
+    b = torch.rand((C,), device=device)
+    wp = ops.pack_conv3x3(w)
+    y = torch.empty_like(x)
+    reps = 20
+    s = torch.cuda.Stream(device=device)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            ops.conv3x3(x, wp, b, out_bf16=y, N=N, H=H, W=W, Cin=C, Cout=C, relu=True)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            ops.conv3x3(x, wp, b, out_bf16=y, N=N, H=H, W=W, Cin=C, Cout=C, relu=True)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = None
+    for _ in range(5):
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        t = e0.elapsed_time(e1) * 1e-3 / reps
+        best = t if best is None else min(best, t)
+    flops = CONV64_FLOP_PER_PIXEL * N * H * W
+    achieved = flops / best * 1e-12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('conv64_dram_bytes_per_launch')
+    return {'bound': 'tensor', 'kernel': 'conv3x3_tc_kernel<64,resident-B> (64->64, bias+ReLU, 16x48x48)',
+            'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+            'traffic': traffic, 'us_per_launch': best * 1e6, 'flops_per_launch': flops,
+            'peak_source': pk['source'] + ', burst figure (kernel timed alone)'}
+
+
+def run_b200(args, rank, world):
+    import torch.distributed as dist
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    from rumpy_b200.shared_framework.models import define_model
+
+    tmp = tempfile.mkdtemp()
+    handler = define_model('rcan', device=local_rank, model_save_dir=tmp, eval_mode=True, scale=SCALE)
+    handler.net.load_state_dict({k: torch.from_numpy(v) for k, v in make_state_dict().items()}, strict=True)
+    handler.net.eval()
+    eng = handler.net.native_engine()
+
+    x_host = torch.from_numpy(recipe.make_input((BATCH, 3, LR_HW, LR_HW), seed=8 + rank)).pin_memory()
+    x_dev = x_host.to(device)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident steps (value)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            eng.forward_graphed(x_dev)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    evs = []
+    with torch.no_grad():
+        for _ in range(args.steps):
+            flush.zero_()                                    # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.forward_graphed(x_dev)
+            e1.record()
+            evs.append((e0, e1))
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    # ---- end-to-end through the reference-facing handler call, HOST buffers in and out
+    with torch.no_grad():
+        for _ in range(3):
+            handler.run_eval(x_host)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_cpu, _, _ = handler.run_eval(x_host)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    clocks = sampler.result()
+    launches = eng.lib.rumpy_net_num_launches(eng.handle)
+
+    t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_per_step = total_ms / args.steps
+    value = world * OUT_MPIX_PER_STEP / (ms_per_step * 1e-3)
+    e2e_value = world * OUT_MPIX_PER_STEP / (e2e_s / args.steps)
+    pk = peaks()
+    roof = conv_kernel_roofline(device, pk)
+    trunk_tflops = FLOP_PER_LR_PIXEL * BATCH * LR_HW * LR_HW / (ms_per_step * 1e-3) * 1e-12
+    cores = os.cpu_count() or 1
+    fwd = cpu_forward_fn(cores)
+    cpu_s, cpu_iters = time_cpu(fwd, BATCH, min_seconds=10.0, max_iters=30)
+    line = {
+        'metric': 'RCAN x4 output Mpix/s (infer)', 'value': value, 'unit': 'Mpix/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': BATCH, 'lr_patch': LR_HW, 'scale': SCALE,
+                   'parallelism': f'independent patch batches per GPU x{world}, no collective',
+                   'l2': 'flushed between timed steps (256 MB memset, untimed)',
+                   'weights': 'random init (numpy recipe seed 8)', 'compute': 'bf16 operands, fp32 accumulate, '
+                   'fp32 residual stream'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'Mpix/s', 'h2d_bytes_per_step': int(x_host.numel() * 4),
+                'd2h_bytes_per_step': int(out_cpu.numel() * 4), 'api': 'RCANHandler.run_eval(x_cpu) -> out_cpu'},
+        'gpu_launches': int(launches) * args.steps,
+        'launches_per_step': int(launches),
+        'whole_step_tflops': trunk_tflops, 'whole_step_frac_of_sustained_peak': trunk_tflops / pk['tflops_sustained'],
+        'roofline': roof,
+        'cpu_baseline': {'value': OUT_MPIX_PER_STEP / cpu_s, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
+                         'sample': f'full batch of {BATCH} patches, median of {cpu_iters} forwards, fp32 torch-CPU'},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback '
+                         '(use --impl reference for the CPU baseline)')
+    run_b200(args, rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -111,6 +111,7 @@ int rumpy_net_create(void** net, int arch, int n_feats, int n_groups, int n_bloc
                      float res_scale, int in_feats, int out_feats, int u_f32);
 int rumpy_net_destroy(void* net);
 int rumpy_net_num_params(void* net);
+int rumpy_net_num_launches(void* net); /* kernels per forward of the cached plan */
 long long rumpy_net_packed_bytes(void* net);
 long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training);
 int rumpy_net_pack(void* net, const float* const* params, void* packed, void* stream);

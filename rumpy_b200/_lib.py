@@ -31,6 +31,7 @@ SIGNATURES = {
     'rumpy_net_create': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i],
     'rumpy_net_destroy': [_vp],
     'rumpy_net_num_params': [_vp],
+    'rumpy_net_num_launches': [_vp],
     'rumpy_net_packed_bytes': [_vp],
     'rumpy_net_workspace_bytes': [_vp, _i, _i, _i, _i],
     'rumpy_net_pack': [_vp, _vp, _vp, _vp],

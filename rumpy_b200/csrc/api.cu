@@ -7,6 +7,7 @@
 namespace rb {
 
 thread_local std::string g_last_error;
+long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
 
 int set_error(int code, const char* fmt, ...) {
   char buf[512];
@@ -57,10 +58,10 @@ int device_info(int* num_sms) {
 
 // 4-D NHWC map {C, W, H, N} with explicit strides (bytes) and box {box_c, 16, 8, 1}, 128B swizzle, zero OOB fill.
 int make_map_nhwc(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, uint64_t stride_w,
-                  uint64_t stride_h, uint64_t stride_n) {
+                  uint64_t stride_h, uint64_t stride_n, int box_h) {
   const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
   const cuuint64_t strides[3] = {stride_w, stride_h, stride_n};
-  const cuuint32_t box[4] = {cuuint32_t(f32 ? 32 : 64), kTileW, kTileH, 1};
+  const cuuint32_t box[4] = {cuuint32_t(f32 ? 32 : 64), kTileW, cuuint32_t(box_h), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "tensor base not 16B aligned");
   CUresult r = get_encode_fn()(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
@@ -73,19 +74,21 @@ int make_map_nhwc(CUtensorMap* m, bool f32, const void* base, int C, int W, int 
 
 // Dense NHWC tensor, optionally viewed through a pixel (un)shuffle of factor r: sub-pixel q=(i,j) of the
 // [N, H*r, W*r, C] tensor is the strided [N,H,W,C] view starting at (i, j).
-int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q) {
+int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
+                      int box_h = kTileH) {
   const uint64_t es = f32 ? 4 : 2;
   const int i = q / r, j = q % r;
   const uint64_t Wf = uint64_t(W) * r, Hf = uint64_t(H) * r;
   const char* b = static_cast<const char*>(base) + (uint64_t(i) * Wf + j) * C * es;
-  return make_map_nhwc(m, f32, b, C, W, H, N, uint64_t(r) * C * es, uint64_t(r) * Wf * C * es, Hf * Wf * C * es);
+  return make_map_nhwc(m, f32, b, C, W, H, N, uint64_t(r) * C * es, uint64_t(r) * Wf * C * es, Hf * Wf * C * es,
+                       box_h);
 }
 
-// packed weights [9][rows][k] bf16 -> 3-D map {k, rows, 9}, box {64, bn, 1}
-int make_map_weights(CUtensorMap* m, const void* base, int k, int rows, int bn) {
+// packed weights [9][rows][k] bf16 -> 3-D map {k, rows, 9}, box {64, bn, taps} (9 taps resident, 3 streaming)
+int make_map_weights(CUtensorMap* m, const void* base, int k, int rows, int bn, int box_taps) {
   const cuuint64_t dims[3] = {cuuint64_t(k), cuuint64_t(rows), 9};
   const cuuint64_t strides[2] = {cuuint64_t(k) * 2, cuuint64_t(k) * 2 * rows};
-  const cuuint32_t box[3] = {64, cuuint32_t(bn), 1};
+  const cuuint32_t box[3] = {64, cuuint32_t(bn), cuuint32_t(box_taps)};
   const cuuint32_t estr[3] = {1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "weights not 16B aligned");
   CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
@@ -116,7 +119,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
       return set_error(RUMPY_ERR_ARG, "conv3x3: Cout=%d must be a multiple of 64", d.Cout);
     if (d.Cin % (64 * rin * rin) != 0 || d.Cout % (64 * rout * rout) != 0)
       return set_error(RUMPY_ERR_ARG, "conv3x3: channels/shuffle mismatch");
-    bn = (d.Cin > 64 && d.Cout % 128 == 0) ? 128 : 64;
+    bn = 64;
     if (d.force_bn) bn = d.force_bn;
     if (d.Cout % bn != 0) return set_error(RUMPY_ERR_ARG, "conv3x3: Cout %% BN != 0");
   }
@@ -138,6 +141,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.pool_partial = d.pool_partial;
   a.out_nchw = d.out_nchw;
   a.cout_real = d.cout_real;
+  a.dbg = g_debug_timeline;
   uint32_t flags = d.flags & (kConvRelu | kConvPool);
   if (d.y_bf16) flags |= kConvOutBf16;
   if (d.y_f32) flags |= kConvOutF32;
@@ -149,13 +153,13 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
     return set_error(RUMPY_ERR_ARG, "conv3x3: shuffle store supports bf16 output only");
   a.flags = flags;
   // pipeline depth from the 227 KB budget
-  const size_t budget = 227 * 1024 - 3072;
+  const size_t budget = kConvSmemBudget;
   int stages = kMaxStages;
-  while (stages > 2 && conv_smem_bytes(bn, resident, cin_chunks, stages) > budget) --stages;
-  if (conv_smem_bytes(bn, resident, cin_chunks, stages) > budget)
+  while (stages > 2 && conv_smem_bytes(bn, resident, cin_chunks, stages, flags) > budget) --stages;
+  if (conv_smem_bytes(bn, resident, cin_chunks, stages, flags) > budget)
     return set_error(RUMPY_ERR_ARG, "conv3x3: configuration does not fit shared memory");
   a.stages = stages;
-  p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages);
+  p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages, flags);
   int grid = sms < a.m_tiles * a.n_tiles ? sms : a.m_tiles * a.n_tiles;
   grid -= grid % a.n_tiles;
   if (grid < a.n_tiles) grid = a.n_tiles;
@@ -163,8 +167,8 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   // tensor maps
   const int cin_sub = d.Cin / (rin * rin);
   for (int q = 0; q < rin * rin; ++q)
-    if (int e = make_map_nhwc_sub(&p->maps.a[q], false, d.x, cin_sub, d.W, d.H, d.N, rin, q)) return e;
-  if (int e = make_map_weights(&p->maps.w, d.w, d.Cin, thin ? 16 : d.Cout, bn)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.a[q], false, d.x, cin_sub, d.W, d.H, d.N, rin, q, kABoxH)) return e;
+  if (int e = make_map_weights(&p->maps.w, d.w, d.Cin, thin ? 16 : d.Cout, bn, resident ? 9 : 3)) return e;
   if (d.y_bf16) {
     const int cout_sub = d.Cout / (rout * rout);
     for (int q = 0; q < rout * rout; ++q)
@@ -184,7 +188,7 @@ static int launch_conv_t(const ConvPlan& p, cudaStream_t s) {
   auto kern = conv3x3_tc_kernel<BN, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 3072) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kConvSmemBudget)) != cudaSuccess)
       return set_error(RUMPY_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
@@ -219,6 +223,8 @@ using namespace rb;
 extern "C" {
 
 int rumpy_version(void) { return RUMPY_B200_VERSION; }
+/* debug hook, not part of the public header: per-CTA clock64 timeline (16 slots per CTA) for conv kernels */
+int rumpy_debug_set_timeline(void* buf) { g_debug_timeline = static_cast<long long*>(buf); return 0; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }
 int rumpy_device_check(void) { return device_info(nullptr); }
 

@@ -55,25 +55,46 @@ struct ConvArgs {
   float* pool_partial;   // [m_tiles][2][cout]
   float* out_nchw;       // BN == 16 variant only: fp32 NCHW [N][cout_real][H][W]
   int cout_real;         // BN == 16 variant only: number of real output channels (<= 16)
+  long long* dbg;        // optional per-CTA timeline (16 clock64 slots per CTA); nullptr in production
   uint32_t flags;
 };
 
 constexpr int kTileH = 8, kTileW = 16, kTileM = 128;
-constexpr int kABytes = kTileM * 128;       // one A stage: 128 pixels x 64 bf16
-constexpr int kStgF32Bytes = 2 * kABytes;   // fp32 staging: two 32-channel halves
+constexpr int kABoxH = kTileH + 2;                 // A box rows: the tile plus one halo row above and below
+constexpr int kABytes = kTileM * 128;              // one 128-pixel x 64-channel bf16 operand / staging tile
+constexpr int kAStageBytes = kABoxH * kTileW * 128;  // 20 KB: serves the three ky taps of one (kx, chunk)
+constexpr int kStgF32Bytes = 2 * kABytes;          // fp32 staging: two 32-channel halves
 constexpr int kStgBf16Bytes = kABytes;
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;
+constexpr size_t kConvSmemBudget = 227 * 1024 - 3072;
 
 __host__ __device__ constexpr int conv_b_block_bytes(int bn) { return bn * 128; }
 
-// Dynamic smem: [stg_f32 | stg_bf16 | resident B (optional) | stages x (A [+ B])], 1024-byte aligned.
-__host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, int stages) {
-  size_t s = 1024 + kStgF32Bytes + kStgBf16Bytes;
+// Epilogue staging: fp32 tile (32 KB) if any fp32 input/output, bf16 tile (16 KB) if any bf16 input/output;
+// double buffered unless the epilogue has TMA inputs (residual / mask), which are consumed in place.
+__host__ __device__ inline int conv_stg_buf_bytes(uint32_t flags) {
+  return ((flags & (kConvOutF32 | kConvResF32)) ? kStgF32Bytes : 0) +
+         ((flags & (kConvOutBf16 | kConvMask)) ? kStgBf16Bytes : 0);
+}
+__host__ __device__ inline int conv_stg_bufs(uint32_t flags) { return (flags & (kConvResF32 | kConvMask)) ? 1 : 2; }
+
+// Dynamic smem: [staging | resident B (optional) | stages x (A box [+ 3 B taps])], 1024-byte aligned.
+__host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, int stages, uint32_t flags) {
+  size_t s = 1024;
+  if (bn != 16) s += size_t(conv_stg_bufs(flags)) * conv_stg_buf_bytes(flags);
   if (resident_b) s += size_t(9) * cin_chunks * conv_b_block_bytes(bn);
-  s += size_t(stages) * (kABytes + (resident_b ? 0 : conv_b_block_bytes(bn)));
+  s += size_t(stages) * (kAStageBytes + (resident_b ? 0 : 3 * conv_b_block_bytes(bn)));
   return s;
 }
+
+#define RB_STAMP(slot) do { if (args.dbg) args.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define RB_STAMP_NS(slot) do { if (args.dbg) args.dbg[blockIdx.x * 16 + (slot)] = global_timer_ns(); } while (0)
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -88,6 +109,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   constexpr uint32_t kTmemCols = 2 * BN;   // 32 is the minimum TMEM allocation
   constexpr int kChunksPerTile = BN / 64;  // 0 for the thin (BN = 16) NCHW-output variant
   constexpr uint32_t kIdesc = make_idesc_bf16(128, BN);
+  constexpr int kStageBytes = kAStageBytes + (RESIDENT_B ? 0 : 3 * kBBlock);
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -101,15 +123,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { RB_STAMP(0); RB_STAMP_NS(14); }
   const int stages = args.stages;
-  const int kblocks = 9 * args.cin_chunks;
+  const int cin_chunks = args.cin_chunks;
+  const uint32_t flags = args.flags;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg_f32 = smem;
-  uint8_t* stg_bf16 = smem + kStgF32Bytes;
-  uint8_t* b_res = stg_bf16 + kStgBf16Bytes;
-  uint8_t* stage0 = b_res + (RESIDENT_B ? kblocks * kBBlock : 0);
-  constexpr int kStageBytes = kABytes + (RESIDENT_B ? 0 : kBBlock);
+  const int stg_buf_bytes = (BN == 16) ? 0 : conv_stg_buf_bytes(flags);
+  const int stg_bufs = conv_stg_bufs(flags);
+  uint8_t* b_res = smem + stg_bufs * stg_buf_bytes;
+  uint8_t* stage0 = b_res + (RESIDENT_B ? 9 * cin_chunks * kBBlock : 0);
 
   const int n_tile = blockIdx.x % args.n_tiles;
   const int mt_first = blockIdx.x / args.n_tiles;
@@ -127,78 +150,97 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     mbar_init(&b_bar, 1);
     mbar_init(&in_bar, 1);
     fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.w);
   }
   if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_s);
-  for (int i = threadIdx.x; i < BN; i += kConvThreads)
-    bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) RB_STAMP(1);
 
   const int tiles_per_img = args.tiles_x * args.tiles_y;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      if (RESIDENT_B) {
-        mbar_expect_tx(&b_bar, uint32_t(kblocks) * kBBlock);
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / args.cin_chunks, chunk = kb % args.cin_chunks;
-          tma_load_3d(b_res + kb * kBBlock, &maps.w, &b_bar, chunk * 64, n_tile * BN, tap);
-        }
+    // The whole warp walks the loop (warp-uniform control flow, uniform registers); one elected lane issues.
+    if (RESIDENT_B) {
+      if (elect_one()) {
+        mbar_expect_tx(&b_bar, uint32_t(9 * cin_chunks) * kBBlock);
+        for (int chunk = 0; chunk < cin_chunks; ++chunk)   // one box {64, BN, 9 taps} per 64-channel chunk
+          tma_load_3d(b_res + chunk * 9 * kBBlock, &maps.w, &b_bar, chunk * 64, n_tile * BN, 0);
+        RB_STAMP(2);
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
-        const int n = mt / tiles_per_img;
-        const int rem = mt - n * tiles_per_img;
-        const int y0 = (rem / args.tiles_x) * kTileH;
-        const int x0 = (rem % args.tiles_x) * kTileW;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int tap = kb / args.cin_chunks, chunk = kb % args.cin_chunks;
-          const int ky = tap / 3, kx = tap % 3;
+      __syncwarp();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
+      const int n = mt / tiles_per_img;
+      const int rem = mt - n * tiles_per_img;
+      const int y0 = (rem / args.tiles_x) * kTileH;
+      const int x0 = (rem % args.tiles_x) * kTileW;
+      int mi = 0, cc = 0;  // input map index / 64-channel chunk inside that map
+      for (int chunk = 0; chunk < cin_chunks; ++chunk) {
+        for (int kx = 0; kx < 3; ++kx) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = stage0 + stage * kStageBytes;
-          mbar_expect_tx(&full_bar[stage], kStageBytes);
-          const int mi = chunk / args.a_chunks_per_map;
-          const int c0 = (chunk % args.a_chunks_per_map) * 64;
-          tma_load_4d(sa, &maps.a[mi], &full_bar[stage], c0, x0 + kx - 1, y0 + ky - 1, n);
-          if (!RESIDENT_B) tma_load_3d(sa + kABytes, &maps.w, &full_bar[stage], chunk * 64, n_tile * BN, tap);
+          if (elect_one()) {
+            uint8_t* sa = stage0 + stage * kStageBytes;
+            mbar_expect_tx(&full_bar[stage], kStageBytes);
+            // box {64 ch, 16 px, 10 rows}: rows y0-1 .. y0+8 at column offset kx-1 serve ky = 0, 1, 2
+            tma_load_4d(sa, &maps.a[mi], &full_bar[stage], cc * 64, x0 + kx - 1, y0 - 1, n);
+            if (!RESIDENT_B) tma_load_3d(sa + kAStageBytes, &maps.w, &full_bar[stage], chunk * 64, n_tile * BN, kx * 3);
+          }
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
+        if (++cc == args.a_chunks_per_map) { cc = 0; ++mi; }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      if (RESIDENT_B) mbar_wait(&b_bar, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < kblocks; ++kb) {
+    // ===================================================================== MMA issuer (one elected lane)
+    if (RESIDENT_B) mbar_wait(&b_bar, 0);
+    if (lane == 0) RB_STAMP(3);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+      for (int chunk = 0; chunk < cin_chunks; ++chunk) {
+        for (int kx = 0; kx < 3; ++kx) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage0 + stage * kStageBytes);
-          const uint32_t b_addr = RESIDENT_B ? smem_u32(b_res + kb * kBBlock) : a_addr + kABytes;
-          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSw128);
-          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSw128);
+          if (it == 0 && chunk == 0 && kx == 0 && lane == 0) RB_STAMP(4);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(stage0 + stage * kStageBytes);
+            const uint32_t b_addr = RESIDENT_B ? smem_u32(b_res + (chunk * 9 + kx * 3) * kBBlock)
+                                               : a_addr + kAStageBytes;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
-            umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (kb | k) != 0);
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+            for (int ky = 0; ky < 3; ++ky) {
+              // tap (ky,kx): rows [16*ky, 16*ky+128) of the box -- a 2 KB (two swizzle atoms) shift
+              const uint64_t adesc = make_smem_desc(a_addr + ky * (kTileW * 128), 16, 1024, kLayoutSw128);
+              const uint64_t bdesc = make_smem_desc(b_addr + ky * kBBlock, 16, 1024, kLayoutSw128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle row
+                umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc,
+                          (chunk | kx | ky | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          }
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (it == 0 && lane == 0) RB_STAMP(5);
     }
   } else {
     // ===================================================================== epilogue (128 threads)
@@ -206,12 +248,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     const int row = q * 32 + lane;               // pixel row of the tile == TMEM lane
     const int et = (warp - 2) * 32 + lane;       // 0..127, et==0 is the TMA issuing thread
     const int ly = row >> 4, lx = row & 15;
-    const uint32_t flags = args.flags;
-    const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
-    const uint32_t swz = uint32_t(row & 7);
-    uint8_t* my_f32 = stg_f32 + row * 128;
-    uint8_t* my_bf16 = stg_bf16 + row * 128;
-    uint32_t in_phase = 0;
+    for (int i = et; i < BN; i += 128) bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
+    named_bar_sync(1, 128);
     int it = 0;
     if constexpr (BN == 16) {
       // thin tail conv (C -> out_feats <= 16): fp32 NCHW written straight from registers, no staging
@@ -237,144 +275,164 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                   (__uint_as_float(v[c]) + bias_s[c]) * args.alpha;
         }
       }
-    } else
-    for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
-      const int n = mt / tiles_per_img;
-      const int rem = mt - n * tiles_per_img;
-      const int y0 = (rem / args.tiles_x) * kTileH;
-      const int x0 = (rem % args.tiles_x) * kTileW;
-      const bool valid = (y0 + ly < args.H) && (x0 + lx < args.W);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      for (int j = 0; j < kChunksPerTile; ++j) {
-        const int oc = n_tile * kChunksPerTile + j;  // 64-channel output chunk index
-        // -- staging buffers become free once earlier TMA stores have finished reading them
-        if (et == 0) {
-          tma_store_wait_read0();
+    } else {
+      const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
+      const bool use_f32 = (flags & (kConvOutF32 | kConvResF32)) != 0;
+      const uint32_t swz = uint32_t(row & 7);
+      uint32_t in_phase = 0;
+      int cc = 0;  // running chunk counter -> staging buffer parity
+      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+        const int n = mt / tiles_per_img;
+        const int rem = mt - n * tiles_per_img;
+        const int y0 = (rem / args.tiles_x) * kTileH;
+        const int x0 = (rem % args.tiles_x) * kTileW;
+        const bool valid = (y0 + ly < args.H) && (x0 + lx < args.W);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        for (int j = 0; j < kChunksPerTile; ++j, ++cc) {
+          const int oc = n_tile * kChunksPerTile + j;  // 64-channel output chunk index
+          uint8_t* stg = smem + ((stg_bufs == 2) ? (cc & 1) * stg_buf_bytes : 0);
+          uint8_t* stg_f32 = stg;
+          uint8_t* stg_bf16 = stg + (use_f32 ? kStgF32Bytes : 0);
+          uint8_t* my_f32 = stg_f32 + row * 128;
+          uint8_t* my_bf16 = stg_bf16 + row * 128;
           if (has_in) {
-            uint32_t bytes = 0;
-            if (flags & kConvResF32) bytes += kStgF32Bytes;
-            if (flags & kConvMask) bytes += kStgBf16Bytes;
-            mbar_expect_tx(&in_bar, bytes);
-            if (flags & kConvResF32) {
-              tma_load_4d(stg_f32, &maps.rf, &in_bar, oc * 64, x0, y0, n);
-              tma_load_4d(stg_f32 + kABytes, &maps.rf, &in_bar, oc * 64 + 32, x0, y0, n);
+            // single staging buffer consumed in place: wait until earlier stores have read it, then TMA the
+            // residual / mask tiles of this chunk into it
+            if (et == 0) {
+              tma_store_wait_read0();
+              uint32_t bytes = 0;
+              if (flags & kConvResF32) bytes += kStgF32Bytes;
+              if (flags & kConvMask) bytes += kStgBf16Bytes;
+              mbar_expect_tx(&in_bar, bytes);
+              if (flags & kConvResF32) {
+                tma_load_4d(stg_f32, &maps.rf, &in_bar, oc * 64, x0, y0, n);
+                tma_load_4d(stg_f32 + kABytes, &maps.rf, &in_bar, oc * 64 + 32, x0, y0, n);
+              }
+              if (flags & kConvMask) tma_load_4d(stg_bf16, &maps.mb, &in_bar, oc * 64, x0, y0, n);
             }
-            if (flags & kConvMask) tma_load_4d(stg_bf16, &maps.mb, &in_bar, oc * 64, x0, y0, n);
           }
-        }
-        if (j == 0) {
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
-          tc_fence_after();
-        }
-        if (has_in) {
-          mbar_wait(&in_bar, in_phase);
-          in_phase ^= 1;
-        } else {
-          named_bar_sync(1, 128);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + j * 64 + h * 32);
-          tmem_ld32(taddr, v);
-          tmem_ld_wait();
-          if (j == kChunksPerTile - 1 && h == 1) {
+          if (j == 0) {
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            if (et == 0) RB_STAMP(it == 0 ? 6 : 9);
+          }
+          uint32_t v[64];
+          {
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + j * 64);
+            tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            tmem_ld_wait();
+          }
+          if (j == kChunksPerTile - 1) {
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
           }
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]) + bias_s[j * 64 + h * 32 + i];
-            if (flags & kConvRelu) x = fmaxf(x, 0.f);
-            f[i] = x * args.alpha;
+          if (has_in) {
+            mbar_wait(&in_bar, in_phase);
+            in_phase ^= 1;
           }
-          if (flags & kConvMask) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint4 m = *reinterpret_cast<const uint4*>(my_bf16 + (((uint32_t(h * 4 + c)) ^ swz) << 4));
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+          for (int h = 0; h < 2; ++h) {
+            float f[32];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t lo = mw[e] & 0xFFFFu, hi = mw[e] >> 16;
-                if (!(lo != 0 && lo < 0x8000u)) f[c * 8 + e * 2] = 0.f;
-                if (!(hi != 0 && hi < 0x8000u)) f[c * 8 + e * 2 + 1] = 0.f;
+            for (int i = 0; i < 32; ++i) {
+              float x = __uint_as_float(v[h * 32 + i]) + bias_s[j * 64 + h * 32 + i];
+              if (flags & kConvRelu) x = fmaxf(x, 0.f);
+              f[i] = x * args.alpha;
+            }
+            if (flags & kConvMask) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint4 m = *reinterpret_cast<const uint4*>(my_bf16 + (((uint32_t(h * 4 + c)) ^ swz) << 4));
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  const uint32_t lo = mw[e] & 0xFFFFu, hi = mw[e] >> 16;
+                  if (!(lo != 0 && lo < 0x8000u)) f[c * 8 + e * 2] = 0.f;
+                  if (!(hi != 0 && hi < 0x8000u)) f[c * 8 + e * 2 + 1] = 0.f;
+                }
               }
             }
-          }
-          if (flags & kConvResF32) {
+            if (flags & kConvResF32) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float4 r = *reinterpret_cast<const float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4));
-              f[c * 4 + 0] += r.x; f[c * 4 + 1] += r.y; f[c * 4 + 2] += r.z; f[c * 4 + 3] += r.w;
+              for (int c = 0; c < 8; ++c) {
+                const float4 r = *reinterpret_cast<const float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4));
+                f[c * 4 + 0] += r.x; f[c * 4 + 1] += r.y; f[c * 4 + 2] += r.z; f[c * 4 + 3] += r.w;
+              }
+            }
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = 0.f;
+            }
+            if (flags & kConvOutF32) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4)) =
+                    make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+            }
+            if (flags & kConvOutBf16) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(my_bf16 + ((uint32_t(h * 4 + c) ^ swz) << 4)) =
+                    make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
+                               pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]));
             }
           }
-          if (!valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = 0.f;
-          }
-          if (flags & kConvOutF32) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              *reinterpret_cast<float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4)) =
-                  make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
-          }
-          if (flags & kConvOutBf16) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<uint4*>(my_bf16 + ((uint32_t(h * 4 + c) ^ swz) << 4)) =
-                  make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
-                             pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]));
-          }
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (et == 0) {
-          if (flags & kConvOutF32) {
-            tma_store_4d(&maps.of, stg_f32, oc * 64, x0, y0, n);
-            tma_store_4d(&maps.of, stg_f32 + kABytes, oc * 64 + 32, x0, y0, n);
-          }
-          if (flags & kConvOutBf16) {
-            const int mi = oc / args.o_chunks_per_map;
-            const int c0 = (oc % args.o_chunks_per_map) * 64;
-            tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
-          }
-          tma_store_commit();
-        }
-        if (flags & kConvPool) {
-          // channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves
-          const int c = et & 63, half = et >> 6;
-          float s = 0.f;
-          if (flags & kConvOutF32) {
-            const uint8_t* base = stg_f32 + (c >> 5) * kABytes + (c & 3) * 4;
-            const uint32_t ch = uint32_t((c & 31) >> 2);
-#pragma unroll 8
-            for (int r = half * 64; r < half * 64 + 64; ++r)
-              s += *reinterpret_cast<const float*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
-          } else {
-            const uint8_t* base = stg_bf16 + (c & 7) * 2;
-            const uint32_t ch = uint32_t(c >> 3);
-#pragma unroll 8
-            for (int r = half * 64; r < half * 64 + 64; ++r) {
-              const uint16_t b = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
-              s += __uint_as_float(uint32_t(b) << 16);
+          fence_proxy_async_smem();
+          // double-buffered staging: the store issued one chunk ago must have finished READING the other
+          // buffer before anyone refills it in the next chunk -- checked here, a whole chunk later
+          if (!has_in && et == 0) tma_store_wait_read0();
+          named_bar_sync(2, 128);
+          if (et == 0) {
+            RB_STAMP(it == 0 ? 8 : 10);
+            if (flags & kConvOutF32) {
+              tma_store_4d(&maps.of, stg_f32, oc * 64, x0, y0, n);
+              tma_store_4d(&maps.of, stg_f32 + kABytes, oc * 64 + 32, x0, y0, n);
             }
+            if (flags & kConvOutBf16) {
+              const int mi = oc / args.o_chunks_per_map;
+              const int c0 = (oc % args.o_chunks_per_map) * 64;
+              tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
+            }
+            tma_store_commit();
           }
-          args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = s;
-          named_bar_sync(3, 128);  // staging may be refilled (input TMA) only after every reader is done
+          if (flags & kConvPool) {
+            // channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves
+            const int c = et & 63, half = et >> 6;
+            float s = 0.f;
+            if (flags & kConvOutF32) {
+              const uint8_t* base = stg_f32 + (c >> 5) * kABytes + (c & 3) * 4;
+              const uint32_t ch = uint32_t((c & 31) >> 2);
+#pragma unroll 8
+              for (int r = half * 64; r < half * 64 + 64; ++r)
+                s += *reinterpret_cast<const float*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
+            } else {
+              const uint8_t* base = stg_bf16 + (c & 7) * 2;
+              const uint32_t ch = uint32_t(c >> 3);
+#pragma unroll 8
+              for (int r = half * 64; r < half * 64 + 64; ++r) {
+                const uint16_t b = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
+                s += __uint_as_float(uint32_t(b) << 16);
+              }
+            }
+            args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = s;
+            if (has_in) named_bar_sync(3, 128);  // single buffer: readers must finish before the next input TMA
+          }
         }
       }
+      if (et == 0) { RB_STAMP(11); tma_store_wait_all0(); RB_STAMP(12); }
     }
-    if (et == 0) tma_store_wait_all0();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) RB_STAMP(13);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+    if (lane == 0) RB_STAMP_NS(15);
   }
 }
 

@@ -10,7 +10,8 @@ namespace rb {
 
 // ------------------------------------------------------------------------------------------------
 // OIHW fp32 -> packed bf16 operand for conv3x3_tc_kernel.
-//   forward : P[tap][row][ci]            = W[o(row)][ci][ky][kx],            tap = ky*3+kx
+//   forward : P[tap][row][ci]            = W[o(row)][ci][ky][kx],            tap = kx*3+ky (kx-major: the
+//             three ky taps of one kx are contiguous -- they share one A halo box in the conv kernel)
 //   dgrad   : P[tap][ci ][col]           = W[o(col)][ci][2-ky][2-kx]   (rows = Cin, K = Cout)
 // o(row) applies the pixel-shuffle permutation when r > 1: row = q*(Cout/r^2) + c  <->  o = c*r^2 + q,
 // so that output chunk q holds the channels of sub-pixel q (nn.PixelShuffle, reference common.py:33,40).
@@ -28,7 +29,7 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
     const int k = int(idx % kdim);
     const int row = int((idx / kdim) % rows);
     const int tap = int(idx / (size_t(kdim) * rows));
-    const int ky = tap / 3, kx = tap % 3;
+    const int kx = tap / 3, ky = tap % 3;   // packed tap order is kx-major: tap' = kx*3 + ky
     float v = 0.f;
     if (!dgrad) {
       if (row < cout) {
@@ -126,14 +127,32 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
                                 float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_b,
                                 float* __restrict__ save_mean, float* __restrict__ save_hid,
                                 float* __restrict__ save_y, int HW, int C, int Cr) {
-  __shared__ float mean_s[256], y_s[256], hid_s[64];
+  __shared__ float mean_s[256], y_s[256], hid_s[64], red_s[256];
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
-  if (tid < C) {
-    const float* pp = pool_partial + size_t(n) * partials_per_img * C + tid;
-    float s = 0.f;
-    for (int i = 0; i < partials_per_img; ++i) s += pp[size_t(i) * C];   // fixed order: deterministic
-    mean_s[tid] = s / float(HW);
+  {
+    // per-image channel sums from the conv epilogue's per-tile partials: blockDim/C thread groups split the
+    // partial list, 4 independent loads in flight each (a serial chain of L2 round trips was 11 us here);
+    // fixed summation order -> deterministic
+    const int groups = blockDim.x / C;
+    const int g = tid / C, c = tid % C;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (g < groups) {
+      const float* pp = pool_partial + size_t(n) * partials_per_img * C + c;
+      int i = g;
+      for (; i + 3 * groups < partials_per_img; i += 4 * groups) {
+        s0 += pp[size_t(i) * C]; s1 += pp[size_t(i + groups) * C];
+        s2 += pp[size_t(i + 2 * groups) * C]; s3 += pp[size_t(i + 3 * groups) * C];
+      }
+      for (; i < partials_per_img; i += groups) s0 += pp[size_t(i) * C];
+    }
+    red_s[tid] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < C) {
+      float s = 0.f;
+      for (int k = 0; k < groups; ++k) s += red_s[k * C + tid];
+      mean_s[tid] = s / float(HW);
+    }
   }
   __syncthreads();
   {  // hidden layer: one warp per hidden unit (strided), warp-shuffle reduction over C

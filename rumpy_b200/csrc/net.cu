@@ -269,6 +269,9 @@ int rumpy_net_destroy(void* net) {
   return RUMPY_OK;
 }
 
+/* kernels enqueued by one forward of the cached plan (0 before the first forward) */
+int rumpy_net_num_launches(void* net) { return net ? int(static_cast<Net*>(net)->ops.size()) : -1; }
+
 int rumpy_net_num_params(void* net) { return net ? static_cast<Net*>(net)->n_params : -1; }
 
 long long rumpy_net_packed_bytes(void* net) { return net ? (long long)static_cast<Net*>(net)->packed_bytes : -1; }

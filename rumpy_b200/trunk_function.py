@@ -24,5 +24,5 @@ class _TrunkFn(torch.autograd.Function):
 def trunk_apply(module, x):
     needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters())
     if not needs_grad:
-        return module.native_engine().forward(x, training=False)
+        return module.native_engine().forward_inference(x)
     return _TrunkFn.apply(module, x, *module.parameters())
