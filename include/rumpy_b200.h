@@ -70,6 +70,17 @@ int rumpy_conv3x3(const void* x_bf16, const void* w_packed, const float* bias, c
                   int Cin, int Cout, int in_unshuffle_r, int out_shuffle_r, unsigned flags, float alpha,
                   void* stream);
 
+/* Weight gradient of the 3x3 conv on tensor cores:
+ *     dW[co][ci][ky][kx] (=|+=) alpha * sum_{n,y,x} g[n,y,x,co] * x[n,y+ky-1,x+kx-1,ci]      (OIHW fp32)
+ *   g_bf16 [N,H,W,Cout] bf16 (or [N,H*r,W*r,Cout/r^2] read through a pixel-unshuffle when g_unshuffle_r = r > 1,
+ *   i.e. the gradient of conv + PixelShuffle), x_bf16 [N,H,W,Cin] bf16; Cin, Cout multiples of 64.
+ *   workspace: rumpy_conv3x3_wgrad_workspace(...) bytes of device memory (job descriptors + K-split partials).
+ * Replaces: the weight half of autograd's convolution_backward for common.default_conv (common.py:6-9;
+ * base_architecture.py:432).  Deterministic: K splits are summed in a fixed order. */
+long long rumpy_conv3x3_wgrad_workspace(int N, int H, int W, int Cin, int Cout);
+int rumpy_conv3x3_wgrad(const void* g_bf16, const void* x_bf16, float* dw_oihw, void* workspace, int N, int H, int W,
+                        int Cin, int Cout, int g_unshuffle_r, float alpha, int accumulate, void* stream);
+
 /* Thin tail conv C -> cout_real (<=16) on tensor cores; w_packed has 16 (zero padded) rows; output is the
  * reference's fp32 NCHW tensor.  Replaces: tail.1 = default_conv(n_feats, out_feats, 3) (architectures.py:165). */
 int rumpy_conv3x3_tail(const void* x_bf16, const void* w_packed, const float* bias16, float* y_nchw, int N, int H,

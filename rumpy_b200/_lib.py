@@ -22,6 +22,8 @@ SIGNATURES = {
     'rumpy_pack_conv3x3': [_fp, _vp, _i, _i, _i, _i, _i, _vp],
     'rumpy_pack_bias': [_fp, _fp, _i, _i, _i, _vp],
     'rumpy_conv3x3': [_vp, _vp, _fp, _fp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _u, _f, _vp],
+    'rumpy_conv3x3_wgrad_workspace': [_i, _i, _i, _i, _i],
+    'rumpy_conv3x3_wgrad': [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
     'rumpy_conv3x3_tail': [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp],
     'rumpy_head_conv': [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     'rumpy_ca_apply': [_fp, _vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _vp],
@@ -38,7 +40,7 @@ SIGNATURES = {
     'rumpy_net_forward': [_vp, _vp, _vp, _fp, _fp, _vp, _i, _i, _i, _i, _vp],
 }
 
-_LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes'}
+_LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace'}
 
 _lib = None
 

@@ -75,7 +75,7 @@ int make_map_nhwc(CUtensorMap* m, bool f32, const void* base, int C, int W, int 
 // Dense NHWC tensor, optionally viewed through a pixel (un)shuffle of factor r: sub-pixel q=(i,j) of the
 // [N, H*r, W*r, C] tensor is the strided [N,H,W,C] view starting at (i, j).
 int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
-                      int box_h = kTileH) {
+                      int box_h) {
   const uint64_t es = f32 ? 4 : 2;
   const int i = q / r, j = q % r;
   const uint64_t Wf = uint64_t(W) * r, Hf = uint64_t(H) * r;
@@ -172,14 +172,14 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   if (d.y_bf16) {
     const int cout_sub = d.Cout / (rout * rout);
     for (int q = 0; q < rout * rout; ++q)
-      if (int e = make_map_nhwc_sub(&p->maps.ob[q], false, d.y_bf16, cout_sub, d.W, d.H, d.N, rout, q)) return e;
+      if (int e = make_map_nhwc_sub(&p->maps.ob[q], false, d.y_bf16, cout_sub, d.W, d.H, d.N, rout, q, kTileH)) return e;
   }
   if (d.y_f32)
-    if (int e = make_map_nhwc_sub(&p->maps.of, true, d.y_f32, d.Cout, d.W, d.H, d.N, 1, 0)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.of, true, d.y_f32, d.Cout, d.W, d.H, d.N, 1, 0, kTileH)) return e;
   if (d.residual)
-    if (int e = make_map_nhwc_sub(&p->maps.rf, true, d.residual, d.Cout, d.W, d.H, d.N, 1, 0)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.rf, true, d.residual, d.Cout, d.W, d.H, d.N, 1, 0, kTileH)) return e;
   if (d.mask)
-    if (int e = make_map_nhwc_sub(&p->maps.mb, false, d.mask, d.Cout, d.W, d.H, d.N, 1, 0)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.mb, false, d.mask, d.Cout, d.W, d.H, d.N, 1, 0, kTileH)) return e;
   return RUMPY_OK;
 }
 

@@ -51,6 +51,8 @@ struct ConvPlan {
   size_t smem;
 };
 
+int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
+                      int box_h);
 int conv_plan_build(ConvPlan* p, const ConvDesc& d);
 int conv_plan_launch(const ConvPlan& p, cudaStream_t s);
 

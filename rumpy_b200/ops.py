@@ -130,3 +130,15 @@ def pool_sum(x_nhwc):
     pp = torch.empty((N * tiles_per_image(H, W), 2, C), dtype=torch.float32, device=x_nhwc.device)
     _lib.call('rumpy_pool_sum', x_nhwc.data_ptr(), pp.data_ptr(), N, H, W, C, _stream())
     return pp
+
+
+def conv3x3_wgrad(g, x, dw, *, N, H, W, Cin, Cout, g_unshuffle_r=1, alpha=1.0, accumulate=False):
+    """dW (OIHW fp32) of the 3x3 conv from bf16 NHWC gradient / activation operands (rumpy_conv3x3_wgrad)."""
+    _chk(g, torch.bfloat16, 'g'); _chk(x, torch.bfloat16, 'x'); _chk(dw, torch.float32, 'dw')
+    nbytes = _lib.load().rumpy_conv3x3_wgrad_workspace(N, H, W, Cin, Cout)
+    if nbytes < 0:
+        raise _lib.RumpyB200Error('wgrad workspace query failed')
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
+    _lib.call('rumpy_conv3x3_wgrad', g.data_ptr(), x.data_ptr(), dw.data_ptr(), ws.data_ptr(), N, H, W, Cin, Cout,
+              g_unshuffle_r, float(alpha), int(accumulate), _stream())
+    return dw

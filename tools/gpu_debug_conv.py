@@ -302,6 +302,76 @@ def c32_ca_apply():
     return ok
 
 
+def _wgrad_case(N, H, W, Cin, Cout, r=1, alpha=1.0, accumulate=False, seed=0):
+    torch, F, ops = _imports()
+    gen = torch.Generator(device='cuda').manual_seed(seed)
+    x = torch.rand((N, Cin, H, W), generator=gen, device='cuda') * 2 - 1
+    xb = nhwc(x).to(torch.bfloat16)
+    gout = torch.rand((N, Cout // (r * r), H * r, W * r), generator=gen, device='cuda') * 2 - 1
+    gb = nhwc(gout).to(torch.bfloat16)
+    dw = torch.full((Cout, Cin, 3, 3), 0.5 if accumulate else float('nan'), device='cuda')
+    ops.conv3x3_wgrad(gb, xb, dw, N=N, H=H, W=W, Cin=Cin, Cout=Cout, g_unshuffle_r=r, alpha=alpha,
+                      accumulate=accumulate)
+    torch.cuda.synchronize()
+    w = torch.zeros((Cout, Cin, 3, 3), device='cuda', requires_grad=True)
+    xin = nchw(xb.float())
+    y = F.conv2d(xin, w, None, padding=1)
+    if r > 1:
+        y = F.pixel_shuffle(y, r)
+    y.backward(nchw(gb.float()))
+    ref = w.grad * alpha + (0.5 if accumulate else 0.0)
+    return report(f'wgrad N{N} {H}x{W} {Cin}->{Cout} r={r}', dw, ref, 2e-4 * max(1.0, ref.abs().max().item()))
+
+
+@case
+def w01_wgrad_single_tile():
+    return _wgrad_case(1, 8, 16, 64, 64)
+
+
+@case
+def w02_wgrad_ragged():
+    return _wgrad_case(2, 13, 21, 64, 64, alpha=0.5, accumulate=True)
+
+
+@case
+def w03_wgrad_many_tiles():
+    return _wgrad_case(16, 48, 48, 64, 64)
+
+
+@case
+def w04_wgrad_256():
+    return _wgrad_case(1, 11, 19, 256, 128)
+
+
+@case
+def w05_wgrad_unshuffle():
+    ok = _wgrad_case(2, 7, 10, 64, 256, r=2)
+    ok &= _wgrad_case(1, 5, 9, 64, 576, r=3)
+    return ok
+
+
+@case
+def p02_perf_wgrad():
+    torch, F, ops = _imports()
+    for (N, H, W) in ((16, 48, 48), (16, 64, 64)):
+        C = 64
+        x = torch.rand((N, H, W, C), device='cuda').to(torch.bfloat16)
+        g = torch.rand((N, H, W, C), device='cuda').to(torch.bfloat16)
+        dw = torch.empty((C, C, 3, 3), device='cuda')
+        for _ in range(3):
+            ops.conv3x3_wgrad(g, x, dw, N=N, H=H, W=W, Cin=C, Cout=C)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ops.conv3x3_wgrad(g, x, dw, N=N, H=H, W=W, Cin=C, Cout=C)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 20
+        print(f'[PERF] wgrad64 N{N} {H}x{W}: {us:.2f} us/call (op-level, incl. host job upload + sync)', flush=True)
+    return True
+
+
 @case
 def p01_perf_conv64():
     """Quick device-time numbers (CUDA events), conv 64->64 + ReLU, config #2 / #3 / big shapes."""
