@@ -122,12 +122,35 @@ int rumpy_net_create(void** net, int arch, int n_feats, int n_groups, int n_bloc
                      float res_scale, int in_feats, int out_feats, int u_f32);
 int rumpy_net_destroy(void* net);
 int rumpy_net_num_params(void* net);
-int rumpy_net_num_launches(void* net); /* kernels per forward of the cached plan */
-long long rumpy_net_packed_bytes(void* net);
+int rumpy_net_num_launches(void* net);          /* kernels per forward of the cached plan */
+int rumpy_net_num_launches_backward(void* net); /* kernels per backward of the cached plan */
+long long rumpy_net_packed_bytes(void* net, int training);
 long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training);
-int rumpy_net_pack(void* net, const float* const* params, void* packed, void* stream);
+int rumpy_net_pack(void* net, const float* const* params, void* packed, int training, void* stream);
 int rumpy_net_forward(void* net, const float* const* params, const void* packed, const float* x_nchw,
                       float* y_nchw, void* workspace, int N, int H, int W, int training, void* stream);
+/* Backward of the last training forward on the same (packed, workspace, N, H, W): every gradient the reference
+ * gets from `loss.backward()` (base_architecture.py:432).  dy: upstream gradient, fp32 NCHW like the output;
+ * grads[i] (device pointers, state_dict order, fp32, same shapes as params[i]) are overwritten.
+ * dgrad and wgrad of every 3x3 conv run on tensor cores; K-split / per-block partial sums are reduced in a fixed
+ * order, so gradients are bit-reproducible run to run. */
+int rumpy_net_backward(void* net, const float* const* params, const void* packed, const float* x_nchw,
+                       const float* dy_nchw, float* const* grads, void* workspace, int N, int H, int W, void* stream);
+
+/* ---- train-step kernels (base_architecture.py:40, 93-95, 425-440) -------------------------------------- */
+/* loss = mean|out - y| (nn.L1Loss) into *loss_out (device float) and dy = gscale * sign(out - y) / numel
+ * (dy may be NULL).  ws: rumpy_l1_workspace_floats() device floats. */
+long long rumpy_l1_workspace_floats(void);
+int rumpy_l1_loss_grad(const float* out, const float* y, float* dy, float* loss_out, float* ws, long long numel,
+                       float gscale, void* stream);
+/* nn.utils.clip_grad_norm_ coefficient over a flat gradient buffer: coef_out[0] = min(1, max_norm/(norm+1e-6)),
+ * coef_out[1] = norm.  ws: 1024 device floats. */
+int rumpy_grad_clip_coef(const float* grad_flat, long long n, float max_norm, float* coef_out, float* ws,
+                         void* stream);
+/* Fused Adam (torch.optim.Adam defaults: no weight decay / amsgrad) over flat fp32 buffers; step is 1-based;
+ * the gradient is multiplied by grad_scale and, when non-NULL, by *grad_scale_dev (clip coefficient). */
+int rumpy_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, int step, const float* grad_scale_dev, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -34,13 +34,20 @@ SIGNATURES = {
     'rumpy_net_destroy': [_vp],
     'rumpy_net_num_params': [_vp],
     'rumpy_net_num_launches': [_vp],
-    'rumpy_net_packed_bytes': [_vp],
+    'rumpy_net_num_launches_backward': [_vp],
+    'rumpy_net_packed_bytes': [_vp, _i],
     'rumpy_net_workspace_bytes': [_vp, _i, _i, _i, _i],
-    'rumpy_net_pack': [_vp, _vp, _vp, _vp],
+    'rumpy_net_pack': [_vp, _vp, _vp, _i, _vp],
     'rumpy_net_forward': [_vp, _vp, _vp, _fp, _fp, _vp, _i, _i, _i, _i, _vp],
+    'rumpy_net_backward': [_vp, _vp, _vp, _fp, _fp, _vp, _vp, _i, _i, _i, _vp],
+    'rumpy_l1_workspace_floats': [],
+    'rumpy_l1_loss_grad': [_fp, _fp, _fp, _fp, _fp, _c.c_longlong, _f, _vp],
+    'rumpy_grad_clip_coef': [_fp, _c.c_longlong, _f, _fp, _fp, _vp],
+    'rumpy_adam_step': [_fp, _fp, _fp, _fp, _c.c_longlong, _f, _f, _f, _f, _i, _fp, _f, _vp],
 }
 
-_LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace'}
+_LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace',
+             'rumpy_l1_workspace_floats'}
 
 _lib = None
 

@@ -1,0 +1,447 @@
+// CUDA-core kernels of the backward pass / train step around the tensor-core dgrad + wgrad kernels:
+// L1 loss + gradient, thin tail/head conv gradients, CALayer backward, bias gradients, gradient-stream
+// adds, fused Adam.  Memory-bound streaming kernels; reductions write per-block partials that a second
+// kernel sums in a fixed order (deterministic gradients).
+// Reference semantics: SURVEY.md 8(a') table; base_architecture.py:40 (nn.L1Loss), :93-95 (Adam), :425-440.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace rb {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1 loss (mean) + its gradient: dy = sign(out - y) / numel.   partial[b] = sum |d| of block b.
+// ------------------------------------------------------------------------------------------------
+__global__ void l1_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ y,
+                                    float* __restrict__ dy, float* __restrict__ partial, size_t numel, float gscale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  const float inv = gscale / float(numel);
+  for (size_t i = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) * 4; i < numel;
+       i += size_t(gridDim.x) * blockDim.x * 4) {
+    if (i + 3 < numel) {
+      const float4 a = *reinterpret_cast<const float4*>(out + i), b = *reinterpret_cast<const float4*>(y + i);
+      const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+      s += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+      if (dy) {
+        float4 g;
+        g.x = d0 > 0.f ? inv : (d0 < 0.f ? -inv : 0.f); g.y = d1 > 0.f ? inv : (d1 < 0.f ? -inv : 0.f);
+        g.z = d2 > 0.f ? inv : (d2 < 0.f ? -inv : 0.f); g.w = d3 > 0.f ? inv : (d3 < 0.f ? -inv : 0.f);
+        *reinterpret_cast<float4*>(dy + i) = g;
+      }
+    } else {
+      for (size_t k = i; k < numel; ++k) {
+        const float d = out[k] - y[k];
+        s += fabsf(d);
+        if (dy) dy[k] = d > 0.f ? inv : (d < 0.f ? -inv : 0.f);
+      }
+    }
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void l1_loss_finalize_kernel(const float* __restrict__ partial, int n, float* __restrict__ loss,
+                                        size_t numel) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += double(partial[i]);
+    *loss = float(s / double(numel));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thin tail conv backward (C -> out_feats <= 4), upstream gradient dy in the reference's fp32 NCHW.
+//   dgrad:  dX[p,ci] = sum_{co,ky,kx} dy[co, p - (ky-1,kx-1)] * W[co][ci][ky][kx]     -> bf16 NHWC
+// One thread = one pixel x 8 input channels; weights transposed in smem [co*9+tap][C].
+// ------------------------------------------------------------------------------------------------
+__global__ void tail_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                  __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int cout) {
+  extern __shared__ float wsm[];  // [cout*9][C]
+  for (int i = threadIdx.x; i < cout * 9 * C; i += blockDim.x) {
+    const int ci = i % C, k = i / C;       // k = co*9 + tap
+    const int co = k / 9, tap = k % 9;
+    wsm[i] = w[(size_t(co) * C + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const int groups = C / 8;
+  const size_t npix = size_t(N) * H * W;
+  for (size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x; t < npix * groups;
+       t += size_t(gridDim.x) * blockDim.x) {
+    const int g = int(t % groups);
+    const size_t pix = t / groups;
+    const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int co = 0; co < cout; ++co) {
+      const float* gp = dy + (size_t(n) * cout + co) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = yh - (ky - 1);
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int xx = xw - (kx - 1);
+          if (xx < 0 || xx >= W) continue;
+          const float v = __ldg(gp + size_t(yy) * W + xx);
+          const float* wp = wsm + (co * 9 + ky * 3 + kx) * C + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+        }
+      }
+    }
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[4], acc[5]), b3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+    o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+    *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thin conv weight gradient, shared by the tail conv (C -> few) and the head conv (few -> C):
+//   S[m][tap][c] = sum_p thin[m, p - or + off(tap)] * wide[p, c]      m < M <= 4, c < C
+//   tail: thin = dy (NCHW), wide = X bf16 NHWC, dW[m][c][ky][kx] = sum_p dy[m,p] X[p+off,c]
+//         -> iterate wide pixel q = p+off: dy index q - off            (sign = -1)
+//   head: thin = x (NCHW input), wide = G fp32 NHWC, dW[c][m][ky][kx] = sum_p G[p,c] x[m,p+off]   (sign = +1)
+// plus SB[m] = sum_p thin[m,p] (tail bias grad) or SB'[c] = sum_p wide[p,c] (head bias grad).
+// Thread = (channel c, pixel lane); each block writes a partial [M*9 + 1][C] (last row: wide column sums).
+// ------------------------------------------------------------------------------------------------
+template <bool WIDE_BF16>
+__global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __restrict__ wide_,
+                                  const float* __restrict__ wide2 /* optional second fp32 wide tensor, added */,
+                                  float* __restrict__ partial, int N, int H, int W, int C, int M, int sign) {
+  extern __shared__ float red[];  // [lanes][M*9+1][C] reduce buffer
+  const int lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  float acc[37];
+#pragma unroll
+  for (int i = 0; i < 37; ++i) acc[i] = 0.f;
+  const size_t npix = size_t(N) * H * W;
+  const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
+  const size_t p_begin = blockIdx.x * per_block;
+  const size_t p_end = (p_begin + per_block < npix) ? p_begin + per_block : npix;
+  for (size_t pix = p_begin + lane; pix < p_end; pix += lanes) {
+    const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
+    float v;
+    if (WIDE_BF16) v = __bfloat162float(static_cast<const __nv_bfloat16*>(wide_)[pix * C + c]);
+    else {
+      v = static_cast<const float*>(wide_)[pix * C + c];
+      if (wide2) v += wide2[pix * C + c];
+    }
+    acc[36] += v;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (m < M) {
+        const float* tp = thin + (size_t(n) * M + m) * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int yy = yh + sign * (ky - 1);
+          if (yy < 0 || yy >= H) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int xx = xw + sign * (kx - 1);
+            if (xx < 0 || xx >= W) continue;
+            acc[m * 9 + ky * 3 + kx] = fmaf(__ldg(tp + size_t(yy) * W + xx), v, acc[m * 9 + ky * 3 + kx]);
+          }
+        }
+      }
+    }
+  }
+  const int rows = M * 9 + 1;
+#pragma unroll
+  for (int i = 0; i < 36; ++i)
+    if (i < M * 9) red[(lane * rows + i) * C + c] = acc[i];
+  red[(lane * rows + M * 9) * C + c] = acc[36];
+  __syncthreads();
+  for (int i = threadIdx.x; i < rows * C; i += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * rows * C + i];
+    partial[size_t(blockIdx.x) * rows * C + i] = s;
+  }
+}
+
+// partial [blocks][M*9+1][C] -> tail: dW[m][c][tap] (+ thin-sum bias comes from thin_sum_kernel)
+//                               head: dW[c][m][tap], db[c] = column sums (row M*9)
+__global__ void thin_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ dw,
+                                         float* __restrict__ db_wide, int C, int M, int is_head) {
+  const int rows = M * 9 + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * C; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < blocks; ++b) s += partial[size_t(b) * rows * C + i];
+    const int c = i % C, row = i / C;
+    if (row == M * 9) { if (db_wide) db_wide[c] = s; continue; }
+    const int m = row / 9, tap = row % 9;
+    if (is_head) dw[(size_t(c) * M + m) * 9 + tap] = s;
+    else dw[(size_t(m) * C + c) * 9 + tap] = s;
+  }
+}
+
+// per-plane sums of an NCHW tensor: out[m] = sum_{n,p} t[n,m,p]   (tail bias gradient; M <= 4 planes)
+__global__ void plane_sum_kernel(const float* __restrict__ t, float* __restrict__ out, int N, int M, int P) {
+  __shared__ float red[32];
+  const int m = blockIdx.x;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = t + (size_t(n) * M + m) * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s += p[i];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[m] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bias gradients of the tensor-core convs: phase-aware column sums of a bf16 NHWC gradient operand.
+// g viewed as [outer = N*H][r (i)][inner = W][vec = r*C (j,c)]; db[c*r*r + i*r + j] = alpha * sum.
+// Job list -> one launch for every layer; per-(job, slice) partials, fixed-order reduce.
+// ------------------------------------------------------------------------------------------------
+struct ColsumJob {
+  const __nv_bfloat16* g;
+  float* db;
+  float* partial;   // [slices][r][r*C]
+  int outer, r, inner, C;
+  float alpha;
+};
+constexpr int kColsumSlices = 8;
+
+__global__ void colsum_kernel(const ColsumJob* __restrict__ jobs) {
+  extern __shared__ float red[];  // [blockDim.x]
+  const ColsumJob jb = jobs[blockIdx.y];
+  const int vec = jb.r * jb.C;          // <= 768; blockDim.x = 768 covers every case (3 * 256)
+  const int slice = blockIdx.x;
+  const int o_begin = int((long long)jb.outer * slice / kColsumSlices);
+  const int o_end = int((long long)jb.outer * (slice + 1) / kColsumSlices);
+  const int lanes = blockDim.x / vec;   // row lanes per element
+  const int e = threadIdx.x % vec, lane = threadIdx.x / vec;
+  for (int i = 0; i < jb.r; ++i) {
+    float s0 = 0.f, s1 = 0.f;
+    if (lane < lanes) {
+      for (int o = o_begin + lane; o < o_end; o += lanes) {
+        const __nv_bfloat16* row = jb.g + ((size_t(o) * jb.r + i) * jb.inner) * vec + e;
+        int w = 0;
+        for (; w + 1 < jb.inner; w += 2) {
+          s0 += __bfloat162float(row[size_t(w) * vec]);
+          s1 += __bfloat162float(row[size_t(w + 1) * vec]);
+        }
+        if (w < jb.inner) s0 += __bfloat162float(row[size_t(w) * vec]);
+      }
+    }
+    red[threadIdx.x] = s0 + s1;
+    __syncthreads();
+    if (threadIdx.x < vec) {
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[l * vec + threadIdx.x];
+      jb.partial[(size_t(slice) * jb.r + i) * vec + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void colsum_reduce_kernel(const ColsumJob* __restrict__ jobs) {
+  const ColsumJob jb = jobs[blockIdx.x];
+  const int vec = jb.r * jb.C, total = jb.r * vec;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < kColsumSlices; ++k) s += jb.partial[size_t(k) * total + idx];
+    const int i = idx / vec, e = idx % vec, j = e / jb.C, c = e % jb.C;
+    jb.db[c * jb.r * jb.r + i * jb.r + j] = s * jb.alpha;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CALayer backward (SURVEY 8a'):  out = u*y, y = sigmoid(W2 relu(W1 mean(u)+b1)+b2)
+//   s[n,c]  = sum_hw G*u            (ca_bwd_reduce_kernel -> per-(image, chunk) partials)
+//   dz2 = s*y*(1-y); dh = (W2^T dz2) * 1[hid>0]; dmean = W1^T dh
+//   du = G*y + dmean/HW  -> bf16 operand of conv2's dgrad / wgrad      (ca_bwd_apply_kernel)
+//   dW2 += dz2 (x) hid; db2 += dz2; dW1 += dh (x) mean; db1 += dh       (block (0,0), images in fixed order)
+// ------------------------------------------------------------------------------------------------
+template <bool U_F32>
+__global__ void ca_bwd_reduce_kernel(const float* __restrict__ G, const void* __restrict__ u_,
+                                     float* __restrict__ s_partial, int HW, int C) {
+  extern __shared__ float red[];
+  const int n = blockIdx.y, chunks = gridDim.x;
+  const int lanes = blockDim.x / C, c = threadIdx.x % C, lane = threadIdx.x / C;
+  const int p_begin = int((long long)HW * blockIdx.x / chunks), p_end = int((long long)HW * (blockIdx.x + 1) / chunks);
+  float s0 = 0.f, s1 = 0.f;
+  int p = p_begin + lane;
+  for (; p + lanes < p_end; p += 2 * lanes) {
+    const size_t o0 = (size_t(n) * HW + p) * C + c, o1 = o0 + size_t(lanes) * C;
+    const float u0 = U_F32 ? static_cast<const float*>(u_)[o0] : __bfloat162float(static_cast<const __nv_bfloat16*>(u_)[o0]);
+    const float u1 = U_F32 ? static_cast<const float*>(u_)[o1] : __bfloat162float(static_cast<const __nv_bfloat16*>(u_)[o1]);
+    s0 = fmaf(G[o0], u0, s0);
+    s1 = fmaf(G[o1], u1, s1);
+  }
+  if (p < p_end) {
+    const size_t o0 = (size_t(n) * HW + p) * C + c;
+    const float u0 = U_F32 ? static_cast<const float*>(u_)[o0] : __bfloat162float(static_cast<const __nv_bfloat16*>(u_)[o0]);
+    s0 = fmaf(G[o0], u0, s0);
+  }
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + threadIdx.x];
+    s_partial[(size_t(n) * chunks + blockIdx.x) * C + threadIdx.x] = s;
+  }
+}
+
+__global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ s_partial, int s_chunks,
+                                    const float* __restrict__ save_mean, const float* __restrict__ save_hid,
+                                    const float* __restrict__ save_y, const float* __restrict__ w1,
+                                    const float* __restrict__ w2, __nv_bfloat16* __restrict__ du,
+                                    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                                    float* __restrict__ db2, int N, int HW, int C, int Cr) {
+  __shared__ float y_s[256], coef_s[256], dz2_s[256], dh_s[64];
+  const int tid = threadIdx.x;
+  const int n = blockIdx.y;
+  auto per_image = [&](int img) {   // fills y_s, dz2_s, dh_s, coef_s for image `img`
+    if (tid < C) {
+      float s = 0.f;
+      for (int k = 0; k < s_chunks; ++k) s += s_partial[(size_t(img) * s_chunks + k) * C + tid];
+      const float y = save_y[img * C + tid];
+      y_s[tid] = y;
+      dz2_s[tid] = s * y * (1.f - y);
+    }
+    __syncthreads();
+    {
+      const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+      for (int j = warp; j < Cr; j += nwarps) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(w2[c * Cr + j], dz2_s[c], a);
+        a = warp_sum(a);
+        if (lane == 0) dh_s[j] = save_hid[img * Cr + j] > 0.f ? a : 0.f;
+      }
+    }
+    __syncthreads();
+    if (tid < C) {
+      float a = 0.f;
+      for (int j = 0; j < Cr; ++j) a = fmaf(w1[j * C + tid], dh_s[j], a);
+      coef_s[tid] = a / float(HW);
+    }
+    __syncthreads();
+  };
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    // parameter gradients: every image in order, accumulated in registers by fixed owner threads
+    float aw2[16], aw1[16];   // thread tid owns dW2[tid][0..Cr) and dW1[0..Cr)[tid]  (Cr <= 16 on this path)
+    float ab2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { aw2[j] = 0.f; aw1[j] = 0.f; }
+    float ab1 = 0.f;
+    for (int img = 0; img < N; ++img) {
+      per_image(img);
+      if (tid < C) {
+        const float dz = dz2_s[tid], mean = save_mean[img * C + tid];
+        ab2 += dz;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < Cr) { aw2[j] = fmaf(dz, save_hid[img * Cr + j], aw2[j]); aw1[j] = fmaf(dh_s[j], mean, aw1[j]); }
+      }
+      if (tid < Cr) ab1 += dh_s[tid];
+      __syncthreads();
+    }
+    if (tid < C) {
+      db2[tid] = ab2;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < Cr) { dw2[tid * Cr + j] = aw2[j]; dw1[j * C + tid] = aw1[j]; }
+    }
+    if (tid < Cr) db1[tid] = ab1;
+  }
+  per_image(n);
+  const int vec_per_pix = C / 4;
+  const size_t total = size_t(HW) * vec_per_pix;
+  const size_t base = size_t(n) * HW * C;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int c4 = int(i % vec_per_pix) * 4;
+    const size_t off = base + i * 4;
+    const float4 g = *reinterpret_cast<const float4*>(G + off);
+    const float a = fmaf(g.x, y_s[c4], coef_s[c4]), b = fmaf(g.y, y_s[c4 + 1], coef_s[c4 + 1]);
+    const float c = fmaf(g.z, y_s[c4 + 2], coef_s[c4 + 2]), d = fmaf(g.w, y_s[c4 + 3], coef_s[c4 + 3]);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(du + off) = pk;
+  }
+}
+
+// dst_f = a + b (fp32 NHWC), dst_b = bf16(dst_f): joins of the fp32 gradient stream at group boundaries
+__global__ void add_f32_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ dst_f,
+                                    __nv_bfloat16* __restrict__ dst_b, size_t n4) {
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n4; i += size_t(gridDim.x) * blockDim.x) {
+    const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+    const float4 o = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    if (dst_f) reinterpret_cast<float4*>(dst_f)[i] = o;
+    if (dst_b) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      reinterpret_cast<uint2*>(dst_b)[i] = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused Adam over flat fp32 buffers (torch.optim.Adam defaults: no weight decay, no amsgrad;
+// base_architecture.py:93-95).  grad_scale folds gradient clipping (clip_coef) / DDP averaging.
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float beta1, float beta2, float eps,
+                            float bc1, float bc2_sqrt, const float* __restrict__ grad_scale_dev, float grad_scale) {
+  const float gs = grad_scale_dev ? grad_scale * (*grad_scale_dev) : grad_scale;
+  const float step = lr / bc1;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+// sum of squares of a flat buffer -> partial[b]; finalize writes clip_coef = min(1, max_norm/(norm+1e-6))
+__global__ void sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    s = fmaf(g[i], g[i], s);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  }
+}
+__global__ void clip_coef_kernel(const float* __restrict__ partial, int n, float max_norm, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += double(partial[i]);
+    const float norm = float(sqrt(s));
+    out[0] = fminf(1.f, max_norm / (norm + 1e-6f));
+    out[1] = norm;
+  }
+}
+
+}  // namespace rb

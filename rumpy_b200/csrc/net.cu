@@ -1,15 +1,23 @@
-// Whole-network executor for the RCAN / EDSR trunk: one C call enqueues every kernel of a forward pass.
+// Whole-network executor for the RCAN / EDSR trunk: one C call enqueues every kernel of a forward pass, one
+// more enqueues the whole backward pass.
 //
 // Mirrors the reference's module graph (/root/reference/rumpy/SISR/models/advanced/architectures.py):
 //   RCAN.forward :171-176, ResidualGroup.forward :121-124, RCAB.forward :81-84, CALayer.forward :41-44,
-//   EDSR.forward :236-241, ResBlock.forward common.py:71-75, Upsampler common.py:29-44.
-// The layer program is built once per (shape, workspace, packed-weights) and cached: building encodes every
-// TMA tensor map on the host, so a steady-state forward is just kernel launches (CUDA-graph capturable).
+//   EDSR.forward :236-241, ResBlock.forward common.py:71-75, Upsampler common.py:29-44,
+// and, for backward, what autograd derives from them (`loss.backward()`, base_architecture.py:432; SURVEY 8a').
+// The layer program is built once per (shape, workspace, packed-weights, gradient buffers) and cached: building
+// encodes every TMA tensor map on the host, so a steady-state step is just kernel launches (graph capturable).
 #include "../../include/rumpy_b200.h"
 #include "host_util.cuh"
+#include "wgrad_tc.cuh"
+#include "bwd_kernels.cuh"
+#include <cmath>
 #include <vector>
 
 namespace rb {
+
+// implemented in wgrad.cu
+int wgrad_launch(const WgradJob* jobs_dev, int njobs, const WgradReduceJob* rjobs_dev, int nrjobs, cudaStream_t s);
 
 struct ConvW {            // one 3x3 conv of the network
   int w_idx, b_idx;       // indices into the state_dict-ordered parameter list
@@ -18,11 +26,12 @@ struct ConvW {            // one 3x3 conv of the network
   int r;                  // pixel-shuffle factor folded into the packing (1 = none)
   size_t off_fwd;         // byte offsets into the packed buffer
   size_t off_bias;        // packed bias (only when r > 1 or padded), else SIZE_MAX
+  size_t off_dgrad;       // dgrad-packed weights (training), else SIZE_MAX
 };
 
 struct CAW { int w1, b1, w2, b2; };
 
-enum OpType { OP_HEAD, OP_CONV, OP_CA };
+enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
 
 struct Op {
   OpType type;
@@ -32,11 +41,19 @@ struct Op {
   // OP_HEAD
   int head_w, head_b;
   float* yf; void* yb;
-  // OP_CA
+  // OP_CA / OP_CA_BWD
   CAW ca;
   const float* pool; const void* u; const float* x_in; float* x_out; void* x_out_b;
   float *save_mean, *save_hid, *save_y;
+  float* s_partial; void* du;
+  // OP_ADD / OP_HEAD_WGRAD / OP_TAIL_BWD
+  const float *a, *b; float* dst_f; void* dst_b; size_t n4;
+  const void* tail_in; void* g_hr; float* thin_partial;
+  int h, w;
 };
+
+struct BlockRec { const void* in_b; void* t; void* u; float* sv; int conv1, conv2, ca; };
+struct GroupRec { std::vector<BlockRec> blocks; const void* tail_in_b; int conv_tail; };
 
 struct Net {
   int arch, C, n_groups, n_blocks, reduction, scale;
@@ -45,12 +62,23 @@ struct Net {
   std::vector<ConvW> convs;   // network order
   std::vector<CAW> cas;
   int n_params = 0;
-  size_t packed_bytes = 0;
+  size_t packed_bytes = 0, packed_bytes_train = 0;
+  int conv_body = 0, conv_up0 = 0, conv_tail = 0;
   // cached plan
-  std::vector<Op> ops;
+  std::vector<Op> ops, bops;
   const void* plan_packed = nullptr;
   void* plan_ws = nullptr;
   int pN = 0, pH = 0, pW = 0, p_training = -1;
+  // backward job lists (host copies; device copies live in the workspace)
+  std::vector<float*> plan_grads;
+  std::vector<WgradJob> wg_jobs;
+  std::vector<WgradReduceJob> wg_rjobs;   // .accumulate temporarily carries the weight's param index
+  std::vector<ColsumJob> cs_jobs;
+  std::vector<int> cs_bias_param;
+  WgradJob* wg_jobs_dev = nullptr;
+  WgradReduceJob* wg_rjobs_dev = nullptr;
+  ColsumJob* cs_jobs_dev = nullptr;
+  bool jobs_uploaded = false;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -69,6 +97,7 @@ static void add_conv(Net* n, int cout, int cin, int r = 1, int rows_padded = 0) 
   } else {
     c.off_bias = SIZE_MAX;
   }
+  c.off_dgrad = SIZE_MAX;
   n->convs.push_back(c);
 }
 
@@ -98,12 +127,21 @@ static int net_init(Net* n) {
   } else {
     for (int b = 0; b < n->n_blocks; ++b) { add_conv(n, C, C); add_conv(n, C, C); }
   }
+  n->conv_body = int(n->convs.size());
   add_conv(n, C, C);  // body tail
   int r = 0;
   const int st = upsampler_stages(n->scale, &r);
   if (st < 0) return set_error(RUMPY_ERR_ARG, "scale %d unsupported (2^n or 3)", n->scale);
+  n->conv_up0 = int(n->convs.size());
   for (int s = 0; s < st; ++s) add_conv(n, C * r * r, C, r);
+  n->conv_tail = int(n->convs.size());
   add_conv(n, n->out_feats, C, 1, 16);  // thin tail
+  // dgrad operands (training): every tensor-core conv except the head (no dX needed) and the thin tail
+  n->packed_bytes_train = n->packed_bytes;
+  for (int i = 1; i < n->conv_tail; ++i) {
+    n->convs[i].off_dgrad = n->packed_bytes_train;
+    n->packed_bytes_train = align_up(n->packed_bytes_train + size_t(9) * n->convs[i].cout * n->convs[i].cin * 2, 256);
+  }
   return RUMPY_OK;
 }
 
@@ -112,7 +150,18 @@ struct Bump {
   void* take(size_t bytes) { void* p = base ? base + off : nullptr; off = align_up(off + bytes, 1024); return p; }
 };
 
-// Lays out the workspace and (when ws != nullptr) builds the op list.  Returns bytes needed.
+static int wgrad_splits(int m_tiles) {
+  int s = (m_tiles + 31) / 32;
+  if (s > 64) s = 64;
+  if (s < 1) s = 1;
+  return s;
+}
+
+constexpr int kThinBlocks = 296;
+constexpr int kCaBwdChunks = 16;
+
+// Lays out the workspace and (when build) builds the op lists.  Forward buffers first, then (training) the
+// backward buffers, so `bytes_out` covers a whole train step.
 static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W, int training, size_t* bytes_out,
                       bool build) {
   const int C = n->C;
@@ -120,23 +169,30 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   Bump bp{static_cast<char*>(ws)};
   const char* pk = static_cast<const char*>(packed);
   std::vector<Op> ops;
-  int ci = 0;  // conv cursor
-  auto conv_op = [&](const ConvW& cw, ConvDesc d, int* err) {
+  int err = 0;
+  auto conv_op = [&](std::vector<Op>& list, const ConvW& cw, ConvDesc d, bool dgrad) {
     Op op{};
     op.type = OP_CONV;
-    d.w = pk + cw.off_fwd;
-    if (cw.off_bias != SIZE_MAX) { d.bias = reinterpret_cast<const float*>(pk + cw.off_bias); op.bias_param = -1; }
-    else { d.bias = reinterpret_cast<const float*>(16); op.bias_param = cw.b_idx; }  // patched per call
-    if (build) { if (int e = conv_plan_build(&op.conv, d)) *err = e; }
-    ops.push_back(op);
+    if (dgrad) {
+      d.w = pk + cw.off_dgrad;
+      d.bias = nullptr;
+      op.bias_param = -1;
+    } else {
+      d.w = pk + cw.off_fwd;
+      if (cw.off_bias != SIZE_MAX) { d.bias = reinterpret_cast<const float*>(pk + cw.off_bias); op.bias_param = -1; }
+      else { d.bias = reinterpret_cast<const float*>(16); op.bias_param = cw.b_idx; }  // patched per call
+    }
+    if (build) { if (int e = conv_plan_build(&op.conv, d)) err = e; }
+    list.push_back(op);
   };
-  int err = 0;
+  std::vector<GroupRec> groups;
   // ---- buffers
   float* head_f = static_cast<float*>(bp.take(px * C * 4));
   void* head_b = bp.take(px * C * 2);
   float* S_f = static_cast<float*>(bp.take(px * C * 4));
   float* G_f[2] = {static_cast<float*>(bp.take(px * C * 4)), static_cast<float*>(bp.take(px * C * 4))};
   const int tiles = ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW);
+  int ci = 0;  // conv cursor
   // ---- head
   {
     Op op{};
@@ -148,8 +204,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   }
   const void* cur_b = head_b;     // bf16 operand of the running activation
   const float* cur_f = head_f;    // its fp32 residual-stream copy
+  const int Cr = C / n->reduction;
   if (n->arch == 0) {
-    const int Cr = C / n->reduction;
     const size_t u_bytes = px * C * (n->u_f32 ? 4 : 2);
     void* xb_shared = training ? nullptr : bp.take(px * C * 2);
     void* t_shared = training ? nullptr : bp.take(px * C * 2);
@@ -158,6 +214,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     void* gb[2] = {bp.take(px * C * 2), bp.take(px * C * 2)};
     int cai = 0;
     for (int g = 0; g < n->n_groups; ++g) {
+      GroupRec gr;
       const float* gin_f = cur_f;
       for (int b = 0; b < n->n_blocks; ++b) {
         void* t = training ? bp.take(px * C * 2) : t_shared;
@@ -165,79 +222,286 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         void* xb = training ? bp.take(px * C * 2) : xb_shared;
         float* pool = training ? static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4)) : pool_shared;
         float* sv = training ? static_cast<float*>(bp.take(size_t(N) * (2 * C + Cr) * 4)) : nullptr;
+        BlockRec br{cur_b, t, u, sv, ci, ci + 1, cai};
         ConvDesc d1{};
         d1.x = cur_b; d1.y_bf16 = t; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C; d1.Cout = C; d1.flags = kConvRelu;
         d1.alpha = 1.f;
-        conv_op(n->convs[ci++], d1, &err);
+        conv_op(ops, n->convs[ci++], d1, false);
         ConvDesc d2{};
         d2.x = t; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C; d2.flags = kConvPool; d2.alpha = 1.f;
         if (n->u_f32) d2.y_f32 = static_cast<float*>(u); else d2.y_bf16 = u;
         d2.pool_partial = pool;
-        conv_op(n->convs[ci++], d2, &err);
+        conv_op(ops, n->convs[ci++], d2, false);
         Op ca{};
         ca.type = OP_CA;
         ca.ca = n->cas[cai++];
         ca.pool = pool; ca.u = u; ca.x_in = (b == 0) ? gin_f : S_f; ca.x_out = S_f; ca.x_out_b = xb;
         if (sv) { ca.save_mean = sv; ca.save_y = sv + size_t(N) * C; ca.save_hid = sv + size_t(N) * 2 * C; }
         ops.push_back(ca);
+        gr.blocks.push_back(br);
         cur_b = xb; cur_f = S_f;
       }
       ConvDesc dg{};
       dg.x = cur_b; dg.residual = gin_f; dg.y_f32 = G_f[g & 1]; dg.y_bf16 = training ? bp.take(px * C * 2) : gb[g & 1];
       dg.N = N; dg.H = H; dg.W = W; dg.Cin = C; dg.Cout = C; dg.alpha = 1.f;
       void* gout_b = dg.y_bf16;
-      conv_op(n->convs[ci++], dg, &err);
+      gr.tail_in_b = cur_b; gr.conv_tail = ci;
+      conv_op(ops, n->convs[ci++], dg, false);
+      groups.push_back(gr);
       cur_b = gout_b; cur_f = G_f[g & 1];
     }
   } else {
     void* t_shared = training ? nullptr : bp.take(px * C * 2);
     void* xb_shared = training ? nullptr : bp.take(px * C * 2);
+    GroupRec gr;
     for (int b = 0; b < n->n_blocks; ++b) {
       void* t = training ? bp.take(px * C * 2) : t_shared;
       void* xb = training ? bp.take(px * C * 2) : xb_shared;
+      BlockRec br{cur_b, t, nullptr, nullptr, ci, ci + 1, -1};
       ConvDesc d1{};
       d1.x = cur_b; d1.y_bf16 = t; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C; d1.Cout = C; d1.flags = kConvRelu;
       d1.alpha = 1.f;
-      conv_op(n->convs[ci++], d1, &err);
+      conv_op(ops, n->convs[ci++], d1, false);
       ConvDesc d2{};
       d2.x = t; d2.residual = cur_f; d2.y_f32 = S_f; d2.y_bf16 = xb; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C;
       d2.Cout = C; d2.alpha = n->res_scale;   // conv2(.)*res_scale + x   (common.py:72-73)
-      conv_op(n->convs[ci++], d2, &err);
+      conv_op(ops, n->convs[ci++], d2, false);
+      gr.blocks.push_back(br);
       cur_b = xb; cur_f = S_f;
     }
+    groups.push_back(gr);
   }
   // ---- body tail conv + global skip (architectures.py:173-174 / :238-239): operand for the upsampler only
+  const void* body_in_b = cur_b;
   void* body_b = bp.take(px * C * 2);
   {
     ConvDesc d{};
     d.x = cur_b; d.residual = head_f; d.y_bf16 = body_b; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C;
     d.alpha = 1.f;
-    conv_op(n->convs[ci++], d, &err);
+    conv_op(ops, n->convs[ci++], d, false);
     cur_b = body_b;
   }
   // ---- upsampler: conv C -> C*r*r with the PixelShuffle folded into the store
   int r = 0;
   const int st = upsampler_stages(n->scale, &r);
   int h = H, w = W;
+  std::vector<const void*> up_in;
   for (int s = 0; s < st; ++s) {
     void* up = bp.take(size_t(N) * (h * r) * (w * r) * C * 2);
     ConvDesc d{};
     d.x = cur_b; d.y_bf16 = up; d.N = N; d.H = h; d.W = w; d.Cin = C; d.Cout = C * r * r; d.out_r = r; d.alpha = 1.f;
-    conv_op(n->convs[ci++], d, &err);
+    up_in.push_back(cur_b);
+    conv_op(ops, n->convs[ci++], d, false);
     cur_b = up; h *= r; w *= r;
   }
   // ---- thin tail conv -> caller's fp32 NCHW output
+  const void* tail_in_b = cur_b;
   {
     ConvDesc d{};
     d.x = cur_b; d.N = N; d.H = h; d.W = w; d.Cin = C; d.Cout = 16; d.cout_real = n->out_feats; d.alpha = 1.f;
     d.out_nchw = reinterpret_cast<float*>(16);  // patched per call
-    conv_op(n->convs[ci++], d, &err);
+    conv_op(ops, n->convs[ci++], d, false);
     ops.back().writes_output = true;
+  }
+
+  // =========================================================================================== backward
+  std::vector<Op> bops;
+  std::vector<WgradJob> wg_jobs;
+  std::vector<WgradReduceJob> wg_rjobs;
+  std::vector<ColsumJob> cs_jobs;
+  std::vector<int> cs_bias_param;
+  struct Site { int conv; const void* g; const void* x; int h, w; float alpha; };
+  std::vector<Site> sites;
+  WgradJob* jobs_dev = nullptr;
+  WgradReduceJob* rjobs_dev = nullptr;
+  ColsumJob* cs_dev = nullptr;
+  if (training) {
+    const int Hh = h, Wh = w;  // final resolution
+    // ---- tail conv (thin): dgrad on CUDA cores from the fp32 NCHW upstream gradient; wgrad + bias on CUDA cores
+    void* g_hr = bp.take(size_t(N) * Hh * Wh * C * 2);
+    float* thin_partial = static_cast<float*>(bp.take(size_t(kThinBlocks) * 37 * C * 4));
+    {
+      Op op{};
+      op.type = OP_TAIL_BWD;
+      op.g_hr = g_hr; op.tail_in = tail_in_b; op.thin_partial = thin_partial; op.h = Hh; op.w = Wh;
+      bops.push_back(op);
+    }
+    // ---- upsampler stages reversed
+    const void* g_cur = g_hr;
+    float* GF_body = nullptr;
+    void* GB_body = nullptr;
+    int hs = Hh, wsz = Wh;
+    for (int s = st - 1; s >= 0; --s) {
+      hs /= r; wsz /= r;
+      const ConvW& cw = n->convs[n->conv_up0 + s];
+      ConvDesc d{};
+      d.x = g_cur; d.in_r = r; d.N = N; d.H = hs; d.W = wsz; d.Cin = C * r * r; d.Cout = C; d.alpha = 1.f;
+      void* g_prev = bp.take(size_t(N) * hs * wsz * C * 2);
+      d.y_bf16 = g_prev;
+      if (s == 0) { GF_body = static_cast<float*>(bp.take(px * C * 4)); d.y_f32 = GF_body; GB_body = g_prev; }
+      conv_op(bops, cw, d, true);
+      sites.push_back({n->conv_up0 + s, g_cur, up_in[s], hs, wsz, 1.f});
+      g_cur = g_prev;
+    }
+    // ---- body tail conv
+    float* P = static_cast<float*>(bp.take(px * C * 4));
+    float* Q = static_cast<float*>(bp.take(px * C * 4));
+    void* GB_cur = bp.take(px * C * 2);
+    {
+      ConvDesc d{};
+      d.x = GB_body; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.y_f32 = P; d.y_bf16 = GB_cur;
+      conv_op(bops, n->convs[n->conv_body], d, true);
+      sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f});
+    }
+    if (n->arch == 0) {
+      for (int g = n->n_groups - 1; g >= 0; --g) {
+        const GroupRec& gr = groups[g];
+        {  // group tail conv: grad wrt the last block's output, fp32 only
+          ConvDesc d{};
+          d.x = GB_cur; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.y_f32 = Q;
+          conv_op(bops, n->convs[gr.conv_tail], d, true);
+          sites.push_back({gr.conv_tail, GB_cur, gr.tail_in_b, H, W, 1.f});
+        }
+        for (int b = n->n_blocks - 1; b >= 0; --b) {
+          const BlockRec& br = gr.blocks[b];
+          float* s_partial = static_cast<float*>(bp.take(size_t(N) * kCaBwdChunks * C * 4));
+          void* du = bp.take(px * C * 2);
+          void* dt = bp.take(px * C * 2);
+          Op cb{};
+          cb.type = OP_CA_BWD;
+          cb.ca = n->cas[br.ca];
+          cb.a = Q; cb.u = br.u; cb.s_partial = s_partial; cb.du = du;
+          cb.save_mean = br.sv; cb.save_y = br.sv + size_t(N) * C; cb.save_hid = br.sv + size_t(N) * 2 * C;
+          bops.push_back(cb);
+          ConvDesc d2{};
+          d2.x = du; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C; d2.alpha = 1.f;
+          conv_op(bops, n->convs[br.conv2], d2, true);
+          ConvDesc d1{};
+          d1.x = dt; d1.residual = Q; d1.y_f32 = Q; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C; d1.Cout = C; d1.alpha = 1.f;
+          conv_op(bops, n->convs[br.conv1], d1, true);
+          sites.push_back({br.conv2, du, br.t, H, W, 1.f});
+          sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f});
+        }
+        void* GB_new = bp.take(px * C * 2);
+        Op add{};
+        add.type = OP_ADD;
+        add.a = P; add.b = Q; add.dst_f = P; add.dst_b = GB_new; add.n4 = px * C / 4;
+        bops.push_back(add);
+        GB_cur = GB_new;
+      }
+    } else {
+      const GroupRec& gr = groups[0];
+      for (int b = n->n_blocks - 1; b >= 0; --b) {
+        const BlockRec& br = gr.blocks[b];
+        void* dt = bp.take(px * C * 2);
+        void* GB_new = bp.take(px * C * 2);
+        ConvDesc d2{};
+        d2.x = GB_cur; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C;
+        d2.alpha = n->res_scale;
+        conv_op(bops, n->convs[br.conv2], d2, true);
+        ConvDesc d1{};
+        d1.x = dt; d1.residual = P; d1.y_f32 = P; d1.y_bf16 = GB_new; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C;
+        d1.Cout = C; d1.alpha = 1.f;
+        conv_op(bops, n->convs[br.conv1], d1, true);
+        sites.push_back({br.conv2, GB_cur, br.t, H, W, n->res_scale});
+        sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f});
+        GB_cur = GB_new;
+      }
+    }
+    {  // head conv: weight / bias gradient only (no dX), upstream = trunk gradient + global skip
+      Op op{};
+      op.type = OP_HEAD_WGRAD;
+      op.a = P; op.b = GF_body; op.thin_partial = thin_partial;
+      bops.push_back(op);
+    }
+    // ---- batched tensor-core wgrad + bias gradients over every recorded site
+    size_t njobs = 0, nrjobs = 0, cs_floats = 0;
+    for (const Site& s : sites) {
+      const ConvW& cw = n->convs[s.conv];
+      const int mt = N * ((s.h + kTileH - 1) / kTileH) * ((s.w + kTileW - 1) / kTileW);
+      const int blocks = (cw.cout / 64) * (cw.cin / 64);
+      njobs += size_t(blocks) * wgrad_splits(mt);
+      nrjobs += blocks;
+      cs_floats += size_t(kColsumSlices) * cw.r * cw.cout;
+    }
+    jobs_dev = static_cast<WgradJob*>(bp.take(njobs * sizeof(WgradJob)));
+    rjobs_dev = static_cast<WgradReduceJob*>(bp.take(nrjobs * sizeof(WgradReduceJob)));
+    cs_dev = static_cast<ColsumJob*>(bp.take(sites.size() * sizeof(ColsumJob)));
+    float* partials = static_cast<float*>(bp.take(njobs * 9 * 64 * 64 * sizeof(float)));
+    float* cs_partials = static_cast<float*>(bp.take(cs_floats * sizeof(float)));
+    if (build) {
+      size_t job_cursor = 0, cs_cursor = 0;
+      for (const Site& s : sites) {
+        const ConvW& cw = n->convs[s.conv];
+        const int rr = cw.r * cw.r, cout_sub = cw.cout / rr, chunks_per_q = cout_sub / 64;
+        const int tiles_x = (s.w + kTileW - 1) / kTileW, tiles_y = (s.h + kTileH - 1) / kTileH;
+        const int mt = N * tiles_x * tiles_y;
+        const int splits = wgrad_splits(mt);
+        std::vector<CUtensorMap> gmaps(rr);
+        for (int q = 0; q < rr; ++q)
+          if (int e = make_map_nhwc_sub(&gmaps[q], false, s.g, cout_sub, s.w, s.h, N, cw.r, q, kABoxH)) err = e;
+        CUtensorMap xmap;
+        if (int e = make_map_nhwc_sub(&xmap, false, s.x, cw.cin, s.w, s.h, N, 1, 0, kTileH)) err = e;
+        for (int cb = 0; cb < cw.cout / 64; ++cb) {
+          for (int ib = 0; ib < cw.cin / 64; ++ib) {
+            float* pbase = partials + job_cursor * 9 * 64 * 64;
+            for (int k = 0; k < splits; ++k) {
+              WgradJob j{};
+              j.g = gmaps[cb / chunks_per_q]; j.x = xmap;
+              j.gc0 = (cb % chunks_per_q) * 64; j.xc0 = ib * 64;
+              j.tile_begin = int((long long)mt * k / splits); j.tile_end = int((long long)mt * (k + 1) / splits);
+              j.tiles_x = tiles_x; j.tiles_y = tiles_y;
+              j.out = pbase + size_t(k) * 9 * 64 * 64;
+              wg_jobs.push_back(j);
+            }
+            job_cursor += splits;
+            WgradReduceJob rj{};
+            rj.partial = pbase; rj.dw = nullptr; rj.splits = splits; rj.cout = cw.cout; rj.cin = cw.cin;
+            rj.co0 = cb * 64; rj.ci0 = ib * 64; rj.r = cw.r; rj.alpha = s.alpha;
+            rj.accumulate = cw.w_idx;  // carries the param index until net_backward binds the gradient pointer
+            wg_rjobs.push_back(rj);
+          }
+        }
+        ColsumJob cj{};
+        cj.g = static_cast<const __nv_bfloat16*>(s.g); cj.db = nullptr; cj.partial = cs_partials + cs_cursor;
+        cj.outer = N * s.h; cj.r = cw.r; cj.inner = s.w; cj.C = cout_sub; cj.alpha = s.alpha;
+        cs_cursor += size_t(kColsumSlices) * cw.r * cw.cout;
+        cs_jobs.push_back(cj);
+        cs_bias_param.push_back(cw.b_idx);
+      }
+    }
   }
   *bytes_out = bp.off;
   if (err) return err;
-  if (build) n->ops.swap(ops);
+  if (build) {
+    n->ops.swap(ops);
+    n->bops.swap(bops);
+    n->wg_jobs.swap(wg_jobs);
+    n->wg_rjobs.swap(wg_rjobs);
+    n->cs_jobs.swap(cs_jobs);
+    n->cs_bias_param.swap(cs_bias_param);
+    n->wg_jobs_dev = jobs_dev; n->wg_rjobs_dev = rjobs_dev; n->cs_jobs_dev = cs_dev;
+    n->plan_grads.clear();
+    n->jobs_uploaded = false;
+  }
   return RUMPY_OK;
+}
+
+static int ensure_plan(Net* n, const void* packed, void* workspace, int N, int H, int W, int training) {
+  if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
+      n->p_training != training) {
+    size_t bytes = 0;
+    n->plan_packed = nullptr;
+    if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
+    n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
+  }
+  return RUMPY_OK;
+}
+
+static int launch_conv_op(Op& op, const float* const* params, float* y_nchw, cudaStream_t stream) {
+  if (op.bias_param >= 0) op.conv.args.bias = params[op.bias_param];
+  if (op.writes_output) op.conv.args.out_nchw = y_nchw;
+  return conv_plan_launch(op.conv, stream);
 }
 
 }  // namespace rb
@@ -252,10 +516,10 @@ int rumpy_net_create(void** out, int arch, int n_feats, int n_groups, int n_bloc
   if (arch != 0 && arch != 1) return set_error(RUMPY_ERR_ARG, "net_create: arch %d", arch);
   if (n_feats % 64 != 0 || n_feats <= 0 || n_feats > 256)
     return set_error(RUMPY_ERR_ARG, "net_create: n_feats=%d must be 64, 128, 192 or 256", n_feats);
-  if (in_feats < 1 || in_feats > 4 || out_feats < 1 || out_feats > 16)
-    return set_error(RUMPY_ERR_ARG, "net_create: in_feats=%d out_feats=%d", in_feats, out_feats);
-  if (arch == 0 && (reduction < 1 || n_feats % reduction != 0 || n_feats / reduction > 64))
-    return set_error(RUMPY_ERR_ARG, "net_create: reduction=%d", reduction);
+  if (in_feats < 1 || in_feats > 4 || out_feats < 1 || out_feats > 4)
+    return set_error(RUMPY_ERR_ARG, "net_create: in_feats=%d out_feats=%d (1..4 supported)", in_feats, out_feats);
+  if (arch == 0 && (reduction < 1 || n_feats % reduction != 0 || n_feats / reduction > 16))
+    return set_error(RUMPY_ERR_ARG, "net_create: reduction=%d (n_feats/reduction must be 1..16)", reduction);
   Net* n = new Net();
   n->arch = arch; n->C = n_feats; n->n_groups = n_groups; n->n_blocks = n_blocks; n->reduction = reduction;
   n->scale = scale; n->res_scale = res_scale; n->in_feats = in_feats; n->out_feats = out_feats; n->u_f32 = u_f32;
@@ -272,9 +536,30 @@ int rumpy_net_destroy(void* net) {
 /* kernels enqueued by one forward of the cached plan (0 before the first forward) */
 int rumpy_net_num_launches(void* net) { return net ? int(static_cast<Net*>(net)->ops.size()) : -1; }
 
+/* kernels enqueued by one backward of the cached plan (0 when the plan is inference-only) */
+int rumpy_net_num_launches_backward(void* net) {
+  if (!net) return -1;
+  Net* n = static_cast<Net*>(net);
+  if (n->bops.empty()) return 0;
+  int c = 4;                                  // batched wgrad, its reduce, colsum, colsum reduce
+  for (const Op& op : n->bops) {
+    switch (op.type) {
+      case OP_TAIL_BWD: c += 4; break;        // dgrad, wgrad, reduce, plane sums
+      case OP_CA_BWD: c += 2; break;
+      case OP_HEAD_WGRAD: c += 2; break;
+      default: c += 1;
+    }
+  }
+  return c;
+}
+
 int rumpy_net_num_params(void* net) { return net ? static_cast<Net*>(net)->n_params : -1; }
 
-long long rumpy_net_packed_bytes(void* net) { return net ? (long long)static_cast<Net*>(net)->packed_bytes : -1; }
+long long rumpy_net_packed_bytes(void* net, int training) {
+  if (!net) return -1;
+  Net* n = static_cast<Net*>(net);
+  return (long long)(training ? n->packed_bytes_train : n->packed_bytes);
+}
 
 long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training) {
   if (!net) return -1;
@@ -284,8 +569,8 @@ long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training
 }
 
 // fp32 OIHW parameters (device pointers, state_dict order) -> packed bf16 operands.  Call after every
-// optimiser step (weights changed) and before the first forward.
-int rumpy_net_pack(void* net_, const float* const* params, void* packed, void* stream) {
+// optimiser step (weights changed) and before the first forward.  training != 0 also packs the dgrad operands.
+int rumpy_net_pack(void* net_, const float* const* params, void* packed, int training, void* stream) {
   Net* n = static_cast<Net*>(net_);
   if (!n || !params || !packed) return set_error(RUMPY_ERR_ARG, "net_pack: null");
   char* pk = static_cast<char*>(packed);
@@ -296,6 +581,9 @@ int rumpy_net_pack(void* net_, const float* const* params, void* packed, void* s
     if (c.off_bias != SIZE_MAX)
       if (int e = rumpy_pack_bias(params[c.b_idx], reinterpret_cast<float*>(pk + c.off_bias), c.cout, c.rows_padded,
                                   c.r, stream))
+        return e;
+    if (training && c.off_dgrad != SIZE_MAX)
+      if (int e = rumpy_pack_conv3x3(params[c.w_idx], pk + c.off_dgrad, c.cout, c.cin, c.cout, c.r, 1, stream))
         return e;
   }
   return RUMPY_OK;
@@ -308,13 +596,7 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
     return set_error(RUMPY_ERR_ARG, "net_forward: null pointer");
   if (int e = device_info(nullptr)) return e;
   cudaStream_t stream = cudaStream_t(stream_);
-  if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
-      n->p_training != training) {
-    size_t bytes = 0;
-    n->plan_packed = nullptr;
-    if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
-    n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
-  }
+  if (int e = ensure_plan(n, packed, workspace, N, H, W, training)) return e;
   for (Op& op : n->ops) {
     switch (op.type) {
       case OP_HEAD:
@@ -323,9 +605,7 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
           return e;
         break;
       case OP_CONV:
-        if (op.bias_param >= 0) op.conv.args.bias = params[op.bias_param];
-        if (op.writes_output) op.conv.args.out_nchw = y_nchw;
-        if (int e = conv_plan_launch(op.conv, stream)) return e;
+        if (int e = launch_conv_op(op, params, y_nchw, stream)) return e;
         break;
       case OP_CA:
         if (int e = rumpy_ca_apply(op.pool, op.u, n->u_f32, op.x_in, params[op.ca.w1], params[op.ca.b1],
@@ -333,9 +613,161 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
                                    op.save_hid, op.save_y, N, H, W, n->C, n->C / n->reduction, stream))
           return e;
         break;
+      default:
+        return set_error(RUMPY_ERR_ARG, "net_forward: unexpected op");
     }
   }
   return RUMPY_OK;
+}
+
+// Backward of the last training forward on the same (packed, workspace, shape): dy is the upstream gradient in
+// the reference's fp32 NCHW layout; grads[i] receives d(loss)/d(params[i]) (overwritten, not accumulated).
+int rumpy_net_backward(void* net_, const float* const* params, const void* packed, const float* x_nchw,
+                       const float* dy_nchw, float* const* grads, void* workspace, int N, int H, int W,
+                       void* stream_) {
+  Net* n = static_cast<Net*>(net_);
+  if (!n || !params || !packed || !x_nchw || !dy_nchw || !grads || !workspace)
+    return set_error(RUMPY_ERR_ARG, "net_backward: null pointer");
+  int sms = 0;
+  if (int e = device_info(&sms)) return e;
+  cudaStream_t stream = cudaStream_t(stream_);
+  if (int e = ensure_plan(n, packed, workspace, N, H, W, 1)) return e;
+  const int C = n->C, Cr = C / n->reduction;
+  // (re)bind gradient pointers into the reduce / colsum job lists and upload them when anything changed
+  bool rebind = !n->jobs_uploaded || n->plan_grads.size() != size_t(n->n_params);
+  if (!rebind)
+    for (int i = 0; i < n->n_params; ++i)
+      if (n->plan_grads[i] != grads[i]) { rebind = true; break; }
+  if (rebind) {
+    n->plan_grads.assign(grads, grads + n->n_params);
+    std::vector<WgradReduceJob> rj = n->wg_rjobs;
+    for (WgradReduceJob& j : rj) { j.dw = grads[j.accumulate]; j.accumulate = 0; }
+    std::vector<ColsumJob> cj = n->cs_jobs;
+    for (size_t i = 0; i < cj.size(); ++i) cj[i].db = grads[n->cs_bias_param[i]];
+    cudaError_t e1 = cudaMemcpyAsync(n->wg_jobs_dev, n->wg_jobs.data(), n->wg_jobs.size() * sizeof(WgradJob),
+                                     cudaMemcpyHostToDevice, stream);
+    cudaError_t e2 = cudaMemcpyAsync(n->wg_rjobs_dev, rj.data(), rj.size() * sizeof(WgradReduceJob),
+                                     cudaMemcpyHostToDevice, stream);
+    cudaError_t e3 = cudaMemcpyAsync(n->cs_jobs_dev, cj.data(), cj.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice,
+                                     stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "net_backward: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(stream);  // the temporaries above die at scope exit; happens once per plan
+    n->jobs_uploaded = true;
+  }
+  const ConvW& tail = n->convs[n->conv_tail];
+  const ConvW& head = n->convs[0];
+  const int thin_block = (256 / C > 0 ? 256 / C : 1) * C, thin_lanes = thin_block / C;
+  for (Op& op : n->bops) {
+    switch (op.type) {
+      case OP_TAIL_BWD: {
+        const int Hh = op.h, Wh = op.w, M = n->out_feats, rows = M * 9 + 1;
+        const size_t items = size_t(N) * Hh * Wh * (C / 8);
+        tail_dgrad_kernel<<<grid_for(items, 256, 8), 256, size_t(M) * 9 * C * sizeof(float), stream>>>(
+            dy_nchw, params[tail.w_idx], static_cast<__nv_bfloat16*>(op.g_hr), N, Hh, Wh, C, M);
+        if (int e = check_launch("tail_dgrad")) return e;
+        thin_wgrad_kernel<true><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
+            dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
+        if (int e = check_launch("tail_wgrad")) return e;
+        thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[tail.w_idx], nullptr, C, M, 0);
+        if (int e = check_launch("tail_wgrad_reduce")) return e;
+        plane_sum_kernel<<<M, 1024, 0, stream>>>(dy_nchw, grads[tail.b_idx], N, M, Hh * Wh);
+        if (int e = check_launch("tail_bias_grad")) return e;
+        break;
+      }
+      case OP_CONV:
+        if (int e = launch_conv_op(op, params, nullptr, stream)) return e;
+        break;
+      case OP_CA_BWD: {
+        const int HW = H * W;
+        dim3 g1(kCaBwdChunks, N);
+        if (n->u_f32)
+          ca_bwd_reduce_kernel<true><<<g1, thin_block, thin_block * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
+        else
+          ca_bwd_reduce_kernel<false><<<g1, thin_block, thin_block * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
+        if (int e = check_launch("ca_bwd_reduce")) return e;
+        const size_t vec = size_t(HW) * (C / 4);
+        int chunks = int((vec + 1023) / 1024);
+        const int cap = (sms * 8 + N - 1) / N;
+        if (chunks > cap) chunks = cap;
+        if (chunks < 1) chunks = 1;
+        ca_bwd_apply_kernel<<<dim3(chunks, N), 256, 0, stream>>>(
+            op.a, op.s_partial, kCaBwdChunks, op.save_mean, op.save_hid, op.save_y, params[op.ca.w1], params[op.ca.w2],
+            static_cast<__nv_bfloat16*>(op.du), grads[op.ca.w1], grads[op.ca.b1], grads[op.ca.w2], grads[op.ca.b2], N,
+            HW, C, Cr);
+        if (int e = check_launch("ca_bwd_apply")) return e;
+        break;
+      }
+      case OP_ADD:
+        add_f32_bf16_kernel<<<grid_for(op.n4, 256, 8), 256, 0, stream>>>(op.a, op.b, op.dst_f,
+                                                                        static_cast<__nv_bfloat16*>(op.dst_b), op.n4);
+        if (int e = check_launch("add_f32_bf16")) return e;
+        break;
+      case OP_HEAD_WGRAD: {
+        const int M = n->in_feats, rows = M * 9 + 1;
+        thin_wgrad_kernel<false><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
+            x_nchw, op.a, op.b, op.thin_partial, N, H, W, C, M, +1);
+        if (int e = check_launch("head_wgrad")) return e;
+        thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[head.w_idx],
+                                                        grads[head.b_idx], C, M, 1);
+        if (int e = check_launch("head_wgrad_reduce")) return e;
+        break;
+      }
+      default:
+        return set_error(RUMPY_ERR_ARG, "net_backward: unexpected op");
+    }
+  }
+  if (int e = wgrad_launch(n->wg_jobs_dev, int(n->wg_jobs.size()), n->wg_rjobs_dev, int(n->wg_rjobs.size()), stream))
+    return e;
+  const int ncs = int(n->cs_jobs.size());
+  colsum_kernel<<<dim3(kColsumSlices, ncs), 768, 768 * sizeof(float), stream>>>(n->cs_jobs_dev);
+  if (int e = check_launch("colsum")) return e;
+  colsum_reduce_kernel<<<ncs, 256, 0, stream>>>(n->cs_jobs_dev);
+  return check_launch("colsum_reduce");
+}
+
+// ------------------------------------------------------------------ loss / optimiser kernels
+long long rumpy_l1_workspace_floats(void) { return 1024 + 4; }
+
+// loss = mean |out - y| (nn.L1Loss, base_architecture.py:40) and dy = gscale * sign(out - y) / numel.
+// ws: rumpy_l1_workspace_floats() floats.  loss_out: one float (device).  dy may be NULL (loss only).
+int rumpy_l1_loss_grad(const float* out, const float* y, float* dy, float* loss_out, float* ws, long long numel,
+                       float gscale, void* stream_) {
+  if (int e = device_info(nullptr)) return e;
+  if (!out || !y || !loss_out || !ws || numel <= 0) return set_error(RUMPY_ERR_ARG, "l1_loss_grad: bad args");
+  cudaStream_t stream = cudaStream_t(stream_);
+  size_t blocks = (size_t(numel) / 4 + 255) / 256;
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  l1_loss_grad_kernel<<<int(blocks), 256, 0, stream>>>(out, y, dy, ws, size_t(numel), gscale);
+  if (int e = check_launch("l1_loss_grad")) return e;
+  l1_loss_finalize_kernel<<<1, 32, 0, stream>>>(ws, int(blocks), loss_out, size_t(numel));
+  return check_launch("l1_loss_finalize");
+}
+
+// clip_grad_norm_ coefficient (base_architecture.py:434-435): coef_out[0] = min(1, max_norm / (||g|| + 1e-6)),
+// coef_out[1] = ||g||.  ws: 1024 floats.
+int rumpy_grad_clip_coef(const float* grad_flat, long long n, float max_norm, float* coef_out, float* ws,
+                         void* stream_) {
+  if (int e = device_info(nullptr)) return e;
+  if (!grad_flat || !coef_out || !ws || n <= 0) return set_error(RUMPY_ERR_ARG, "grad_clip_coef: bad args");
+  cudaStream_t stream = cudaStream_t(stream_);
+  sumsq_kernel<<<1024, 256, 0, stream>>>(grad_flat, size_t(n), ws);
+  if (int e = check_launch("sumsq")) return e;
+  clip_coef_kernel<<<1, 32, 0, stream>>>(ws, 1024, max_norm, coef_out);
+  return check_launch("clip_coef");
+}
+
+// One fused Adam step over flat fp32 buffers (torch.optim.Adam defaults, base_architecture.py:93-95).
+// step is 1-based.  grad_scale_dev (device float, may be NULL) and grad_scale multiply the gradient first.
+int rumpy_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, int step, const float* grad_scale_dev, float grad_scale, void* stream_) {
+  if (int e = device_info(nullptr)) return e;
+  if (!p || !g || !m || !v || n <= 0 || step < 1) return set_error(RUMPY_ERR_ARG, "adam_step: bad args");
+  const double bc1 = 1.0 - pow(double(beta1), step), bc2 = 1.0 - pow(double(beta2), step);
+  adam_kernel<<<grid_for(size_t(n), 256, 8), 256, 0, cudaStream_t(stream_)>>>(
+      p, g, m, v, size_t(n), lr, beta1, beta2, eps, float(bc1), float(sqrt(bc2)), grad_scale_dev, grad_scale);
+  return check_launch("adam_step");
 }
 
 }  // extern "C"

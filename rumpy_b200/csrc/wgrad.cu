@@ -1,6 +1,7 @@
 // Host side of the tensor-core weight gradient: job lists (TMA descriptors in device memory) + launches.
 #include "../../include/rumpy_b200.h"
 #include "host_util.cuh"
+#define RB_WGRAD_KERNELS_IMPL
 #include "wgrad_tc.cuh"
 #include <vector>
 

@@ -38,6 +38,7 @@ constexpr int kWgStages = 2;
 constexpr int kWgSmemBytes = 1024 + kWgStages * kWgStageBytes + 4096;  // + pad for the dummy 10th tap window
 constexpr int kWgThreads = 192;
 
+#ifdef RB_WGRAD_KERNELS_IMPL   // kernels are compiled in wgrad.cu only; other units use the job structs
 __device__ __forceinline__ uint32_t wg_tap_offset(int t) {  // byte offset of tap t's window inside the g boxes
   return uint32_t(t / 3) * kAStageBytes + uint32_t(t % 3) * (kTileW * 128);
 }
@@ -153,6 +154,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const WgradJob*
   }
 }
 
+#endif  // RB_WGRAD_KERNELS_IMPL
+
 // Sums the K-split partials of one 64x64 channel block (fixed order) and scatters into the OIHW gradient:
 //   dW[o(co0+co)][ci0+ci][ky][kx] (=|+=) alpha * sum_s partial[s][t][co][ci],  t = kx*3 + (2-ky)
 // o() undoes the pixel-shuffle row permutation of the packed weights (row = q*cpp + c  <->  o = c*r^2 + q).
@@ -163,6 +166,7 @@ struct WgradReduceJob {
   float alpha;
 };
 
+#ifdef RB_WGRAD_KERNELS_IMPL
 __global__ void wgrad_reduce_kernel(const WgradReduceJob* __restrict__ jobs) {
   const WgradReduceJob jb = jobs[blockIdx.y];
   const int rr = jb.r * jb.r, cpp = jb.cout / rr;
@@ -178,5 +182,6 @@ __global__ void wgrad_reduce_kernel(const WgradReduceJob* __restrict__ jobs) {
     *d = jb.accumulate ? *d + v : v;
   }
 }
+#endif  // RB_WGRAD_KERNELS_IMPL
 
 }  // namespace rb

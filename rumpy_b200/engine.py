@@ -31,7 +31,12 @@ class TrunkEngine:
         self.device = self.params[0].device
         if self.device.type != 'cuda':
             raise _lib.RumpyB200Error('rumpy_b200 has no CPU path: move the model to a CUDA (sm_100) device')
-        self.packed = torch.empty(self.lib.rumpy_net_packed_bytes(h), dtype=torch.uint8, device=self.device)
+        self.packed = torch.empty(self.lib.rumpy_net_packed_bytes(h, 1), dtype=torch.uint8, device=self.device)
+        self._packed_training = False
+        self.flat_params = None      # set by FusedAdam.attach: all parameters are views of one flat buffer
+        self.flat_grads = None
+        self._grad_views = None
+        self._grad_ptr_array = None
         self._ptr_array = None
         self._ptr_sig = None
         self._pack_sig = None
@@ -48,6 +53,9 @@ class TrunkEngine:
 
     # ------------------------------------------------------------------ parameter tracking
     def _param_ptrs(self):
+        if self.flat_params is not None and self._ptr_sig is not None and \
+                self._flat_sig == (self.flat_params.data_ptr(), self.params[0].data_ptr(), self.params[-1].data_ptr()):
+            return self._ptr_array            # O(1): parameters are views of one flat buffer
         sig = tuple(p.data_ptr() for p in self.params)
         if sig != self._ptr_sig:
             for p in self.params:
@@ -57,16 +65,31 @@ class TrunkEngine:
             self._ptr_sig = sig
             self._pack_sig = None
             self._graphs.clear()
+        if self.flat_params is not None:
+            self._flat_sig = (self.flat_params.data_ptr(), self.params[0].data_ptr(), self.params[-1].data_ptr())
         return self._ptr_array
 
-    def refresh_weights(self, force=False):
+    def attach_flat(self, flat_params, flat_grads):
+        """Called by FusedAdam: parameters (and .grad) are views into these flat fp32 buffers."""
+        self.flat_params, self.flat_grads = flat_params, flat_grads
+        self._ptr_sig = None
+        self._flat_sig = None
+        self._grad_views = None
+
+    def _version_sig(self):
+        if self.flat_params is not None:
+            return (self.flat_params._version,)     # views share the base tensor's version counter
+        return tuple(p._version for p in self.params)
+
+    def refresh_weights(self, force=False, training=False):
         """Repacks fp32 OIHW parameters into the bf16 tensor-core operand layout when they changed."""
         ptrs = self._param_ptrs()
-        sig = tuple(p._version for p in self.params)
-        if force or sig != self._pack_sig:
-            _lib.call('rumpy_net_pack', self.handle, ptrs, self.packed.data_ptr(),
+        sig = self._version_sig()
+        if force or sig != self._pack_sig or (training and not self._packed_training):
+            _lib.call('rumpy_net_pack', self.handle, ptrs, self.packed.data_ptr(), int(training),
                       torch.cuda.current_stream().cuda_stream)
             self._pack_sig = sig
+            self._packed_training = bool(training)
         return ptrs
 
     def workspace(self, N, H, W, training):
@@ -92,7 +115,7 @@ class TrunkEngine:
     def forward(self, x, training=False, out=None):
         x = self._check_input(x)
         N, _, H, W = x.shape
-        ptrs = self.refresh_weights()
+        ptrs = self.refresh_weights(training=training)
         ws = self.workspace(N, H, W, training)
         if out is None:
             out = torch.empty((N, self.out_feats, H * self.scale, W * self.scale), dtype=torch.float32,
@@ -100,6 +123,35 @@ class TrunkEngine:
         _lib.call('rumpy_net_forward', self.handle, ptrs, self.packed.data_ptr(), x.data_ptr(), out.data_ptr(),
                   ws.data_ptr(), N, H, W, int(training), torch.cuda.current_stream().cuda_stream)
         return out
+
+    # ------------------------------------------------------------------ backward (after forward(training=True))
+    def grad_views(self):
+        """Per-parameter gradient tensors (views of one flat fp32 buffer), state_dict order."""
+        if self._grad_views is None:
+            if self.flat_grads is None:
+                self.flat_grads = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32,
+                                              device=self.device)
+            views, off = [], 0
+            for p in self.params:
+                views.append(self.flat_grads[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            self._grad_views = views
+            self._grad_ptr_array = (ctypes.c_void_p * len(views))(*[v.data_ptr() for v in views])
+        return self._grad_views
+
+    def backward(self, x, dy):
+        """d(loss)/d(params) for the last forward(x, training=True); dy = upstream gradient (fp32 NCHW)."""
+        x = self._check_input(x)
+        N, _, H, W = x.shape
+        dy = dy.contiguous().float()
+        if tuple(dy.shape) != (N, self.out_feats, H * self.scale, W * self.scale) or dy.device != self.device:
+            raise ValueError(f'bad upstream gradient {tuple(dy.shape)} on {dy.device}')
+        grads = self.grad_views()
+        ptrs = self._param_ptrs()
+        ws = self.workspace(N, H, W, True)
+        _lib.call('rumpy_net_backward', self.handle, ptrs, self.packed.data_ptr(), x.data_ptr(), dy.data_ptr(),
+                  self._grad_ptr_array, ws.data_ptr(), N, H, W, torch.cuda.current_stream().cuda_stream)
+        return grads
 
     def forward_inference(self, x):
         """Module-level inference entry: the first call with a shape launches eagerly; repeated calls with the same

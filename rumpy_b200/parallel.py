@@ -1,0 +1,56 @@
+"""Data parallelism for the native trunk: one process per GPU (torchrun), identical replicas, gradient
+all-reduce over NCCL / NVLink.  Replaces the reference's single-process nn.DataParallel
+(base_architecture.py:70-77): there the batch is scattered / outputs gathered every step; here every rank
+trains on its own LR/HR patch batch and only the 62 MB (RCAN) flat fp32 gradient crosses NVLink, in buckets.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def broadcast_parameters(module, src=0):
+    """Identical replicas at step 0 (the reference replicates the module every step instead)."""
+    if not is_distributed():
+        return
+    for p in module.parameters():
+        dist.broadcast(p.data, src=src)
+
+
+class GradAllReduce:
+    """Sums a flat gradient buffer across ranks in fixed-size buckets on a side stream, so the NCCL kernels of
+    bucket k overlap whatever the compute stream enqueues next.  The 1/world factor is folded into Adam."""
+
+    def __init__(self, params=None, bucket_bytes=16 << 20):
+        self.world_size = dist.get_world_size() if is_distributed() else 1
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self._stream = None
+
+    def __call__(self, flat):
+        if self.world_size == 1:
+            return flat
+        if flat.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=flat.device)
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                for off in range(0, flat.numel(), self.bucket_elems):
+                    dist.all_reduce(flat[off:off + self.bucket_elems], op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().wait_stream(self._stream)
+        else:  # gloo (CPU tests of the host logic)
+            for off in range(0, flat.numel(), self.bucket_elems):
+                dist.all_reduce(flat[off:off + self.bucket_elems], op=dist.ReduceOp.SUM)
+        return flat
+
+
+def shard_round_robin(items, rank=None, world=None):
+    """Inference sharding: whole images / frames round-robin over ranks, no collective."""
+    if rank is None:
+        rank = dist.get_rank() if is_distributed() else 0
+    if world is None:
+        world = dist.get_world_size() if is_distributed() else 1
+    return list(items)[rank::world]
