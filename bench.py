@@ -198,6 +198,50 @@ def conv_kernel_roofline(device, pk):
             'peak_source': pk['source'] + ', burst figure (kernel timed alone)'}
 
 
+def train_bench(handler_factory, device, rank, world, steps, warmup, barrier):
+    """BASELINE.json configs[2]: RCAN x4 training fwd/bwd, L1 loss, Adam 1e-4, 64x64 LR patches, batch 16 per GPU,
+    data parallel (NCCL gradient all-reduce).  Returns (ms_per_step max-over-ranks, e2e ms, first loss, last loss)."""
+    import torch.distributed as dist
+    from rumpy_b200 import train_native
+    handler = handler_factory()
+    if world > 1:
+        handler.set_multi_gpu()
+    eng = handler.net.native_engine()
+    TB, THW = 16, 64
+    xh = torch.from_numpy(recipe.make_input((TB, 3, THW, THW), seed=80 + rank)).pin_memory()
+    yh = torch.from_numpy(recipe.make_input((TB, 3, THW * SCALE, THW * SCALE), seed=180 + rank)).pin_memory()
+    xd, yd = xh.to(device), yh.to(device)
+    losses = []
+    for _ in range(max(warmup, 3)):
+        losses.append(train_native.train_step(handler.net, handler.optimizer, xd, yd, allreduce=handler._ddp)[0])
+    barrier()
+    evs = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        losses.append(train_native.train_step(handler.net, handler.optimizer, xd, yd, allreduce=handler._ddp)[0])
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+    # end to end through the reference-facing call: host batch in, loss (numpy) + SR batch on host out
+    for _ in range(2):
+        handler.run_train(x=xh, y=yh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss_np, out_cpu = handler.run_train(x=xh, y=yh)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    launches = eng.lib.rumpy_net_num_launches(eng.handle) + eng.lib.rumpy_net_num_launches_backward(eng.handle) + 4
+    return dict(dev_ms=float(t[0]), e2e_ms=float(t[1]), loss_first=float(losses[0]), loss_last=float(losses[-1]),
+                launches=int(launches), h2d=int(xh.numel() * 4 + yh.numel() * 4), d2h=int(out_cpu.numel() * 4 + 4),
+                batch=TB, hw=THW)
+
+
 def run_b200(args, rank, world):
     import torch.distributed as dist
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -252,8 +296,18 @@ def run_b200(args, rank, world):
             out_cpu, _, _ = handler.run_eval(x_host)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-    clocks = sampler.result()
     launches = eng.lib.rumpy_net_num_launches(eng.handle)
+    # ---- training (configs[2]) in the same run, same clocks record
+    def handler_factory():
+        h = define_model('rcan', device=local_rank, model_save_dir=tmp, eval_mode=False, lr=1e-4, scale=SCALE)
+        h.net.load_state_dict({k: torch.from_numpy(v) for k, v in make_state_dict().items()}, strict=True)
+        return h
+    tr = None
+    if not args.no_train:
+        del handler
+        torch.cuda.empty_cache()
+        tr = train_bench(handler_factory, device, rank, world, max(3, min(args.steps, 10)), args.warmup, barrier)
+    clocks = sampler.result()
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=device)
     if world > 1:
@@ -291,6 +345,20 @@ def run_b200(args, rank, world):
         'cpu_baseline': {'value': OUT_MPIX_PER_STEP / cpu_s, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
                          'sample': f'full batch of {BATCH} patches, median of {cpu_iters} forwards, fp32 torch-CPU'},
     }
+    if tr is not None:
+        train_flop = 3 * FLOP_PER_LR_PIXEL * tr['batch'] * tr['hw'] * tr['hw']
+        line['train'] = {
+            'metric': 'RCAN x4 train patches/s', 'value': world * tr['batch'] / (tr['dev_ms'] * 1e-3),
+            'unit': 'patches/s', 'ms_per_step': tr['dev_ms'], 'n_gpus': world, 'scaling': 'weak',
+            'config': {'workload': 'RCAN x4 train step (fwd + L1 + bwd + Adam), 64x64 LR patches, batch 16 per GPU, '
+                                   'data parallel with bucketed NCCL gradient all-reduce', 'lr': 1e-4},
+            'tflops_per_gpu': train_flop / (tr['dev_ms'] * 1e-3) * 1e-12,
+            'frac_of_sustained_peak': train_flop / (tr['dev_ms'] * 1e-3) * 1e-12 / pk['tflops_sustained'],
+            'e2e': {'value': world * tr['batch'] / (tr['e2e_ms'] * 1e-3), 'unit': 'patches/s',
+                    'h2d_bytes_per_step': tr['h2d'], 'd2h_bytes_per_step': tr['d2h'],
+                    'api': 'RCANHandler.run_train(x_cpu, y_cpu) -> (loss numpy, SR batch cpu)'},
+            'gpu_launches_per_step': tr['launches'], 'loss_first': tr['loss_first'], 'loss_last': tr['loss_last'],
+        }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -302,6 +370,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-train', action='store_true', help='skip the training (configs[2]) section')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
