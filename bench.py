@@ -38,6 +38,15 @@ CONV64_FLOP_PER_PIXEL = 2 * 64 * 64 * 9
 OUT_MPIX_PER_STEP = BATCH * (LR_HW * SCALE) ** 2 / 1e6
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -150,7 +159,7 @@ def run_reference(args, rank):
         'e2e': {'value': mpix_s, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def conv_kernel_roofline(device, pk):
@@ -359,12 +368,18 @@ def run_b200(args, rank, world):
                     'api': 'RCANHandler.run_train(x_cpu, y_cpu) -> (loss numpy, SR batch cpu)'},
             'gpu_launches_per_step': tr['launches'], 'loss_first': tr['loss_first'], 'loss_last': tr['loss_last'],
         }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # NCCL / torch print banners on stdout; the contract is ONE JSON line there -> park fd 1 on stderr and keep
+    # the real stdout for the final line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)

@@ -208,6 +208,13 @@ int conv_plan_launch(const ConvPlan& p, cudaStream_t s) {
   return set_error(RUMPY_ERR_ARG, "conv3x3: unsupported BN %d", p.bn);
 }
 
+static_assert(sizeof(PackJobHost) == sizeof(PackJob), "PackJobHost / PackJob layout mismatch");
+int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s) {
+  if (njobs <= 0) return RUMPY_OK;
+  pack_conv3x3_batched_kernel<<<dim3(8, njobs), 256, 0, s>>>(reinterpret_cast<const PackJob*>(jobs_dev));
+  return check_launch("pack_conv3x3_batched");
+}
+
 int grid_for(size_t work_items, int block, int per_sm = 8) {
   int sms = 148;
   device_info(&sms);

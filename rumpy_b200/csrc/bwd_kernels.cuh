@@ -136,28 +136,38 @@ __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __
   const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
   const size_t p_begin = blockIdx.x * per_block;
   const size_t p_end = (p_begin + per_block < npix) ? p_begin + per_block : npix;
-  for (size_t pix = p_begin + lane; pix < p_end; pix += lanes) {
-    const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
-    float v;
-    if (WIDE_BF16) v = __bfloat162float(static_cast<const __nv_bfloat16*>(wide_)[pix * C + c]);
-    else {
-      v = static_cast<const float*>(wide_)[pix * C + c];
-      if (wide2) v += wide2[pix * C + c];
-    }
-    acc[36] += v;
+  auto load_wide = [&](size_t pix) -> float {
+    if (pix >= p_end) return 0.f;
+    if (WIDE_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(wide_)[pix * C + c]);
+    float v = static_cast<const float*>(wide_)[pix * C + c];
+    if (wide2) v += wide2[pix * C + c];
+    return v;
+  };
+  for (size_t pix0 = p_begin + lane; pix0 < p_end; pix0 += size_t(lanes) * 4) {
+    float vv[4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m < M) {
-        const float* tp = thin + (size_t(n) * M + m) * H * W;
+    for (int u = 0; u < 4; ++u) vv[u] = load_wide(pix0 + size_t(u) * lanes);
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const int yy = yh + sign * (ky - 1);
-          if (yy < 0 || yy >= H) continue;
+    for (int u = 0; u < 4; ++u) {
+      const size_t pix = pix0 + size_t(u) * lanes;
+      if (pix >= p_end) break;
+      const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
+      const float v = vv[u];
+      acc[36] += v;
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const int xx = xw + sign * (kx - 1);
-            if (xx < 0 || xx >= W) continue;
-            acc[m * 9 + ky * 3 + kx] = fmaf(__ldg(tp + size_t(yy) * W + xx), v, acc[m * 9 + ky * 3 + kx]);
+      for (int m = 0; m < 4; ++m) {
+        if (m < M) {
+          const float* tp = thin + (size_t(n) * M + m) * H * W;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int yy = yh + sign * (ky - 1);
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const int xx = xw + sign * (kx - 1);
+              if (xx < 0 || xx >= W) continue;
+              acc[m * 9 + ky * 3 + kx] = fmaf(__ldg(tp + size_t(yy) * W + xx), v, acc[m * 9 + ky * 3 + kx]);
+            }
           }
         }
       }
@@ -193,13 +203,16 @@ __global__ void thin_wgrad_reduce_kernel(const float* __restrict__ partial, int 
 }
 
 // per-plane sums of an NCHW tensor: out[m] = sum_{n,p} t[n,m,p]   (tail bias gradient; M <= 4 planes)
-__global__ void plane_sum_kernel(const float* __restrict__ t, float* __restrict__ out, int N, int M, int P) {
+// grid (slices, M): partial[m][slice]; plane_sum_finalize_kernel adds the slices in order.
+__global__ void plane_sum_kernel(const float* __restrict__ t, float* __restrict__ partial, int N, int M, int P) {
   __shared__ float red[32];
-  const int m = blockIdx.x;
+  const int m = blockIdx.y, slices = gridDim.x;
+  const size_t total = size_t(N) * P;
+  const size_t begin = total * blockIdx.x / slices, end = total * (blockIdx.x + 1) / slices;
   float s = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* p = t + (size_t(n) * M + m) * P;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s += p[i];
+  for (size_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const size_t n = i / P, p = i - n * P;
+    s += t[(n * M + m) * P + p];
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -207,7 +220,15 @@ __global__ void plane_sum_kernel(const float* __restrict__ t, float* __restrict_
   if (threadIdx.x < 32) {
     float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     v = warp_sum(v);
-    if (threadIdx.x == 0) out[m] = v;
+    if (threadIdx.x == 0) partial[m * slices + blockIdx.x] = v;
+  }
+}
+__global__ void plane_sum_finalize_kernel(const float* __restrict__ partial, int slices, float* __restrict__ out,
+                                          int M) {
+  if (threadIdx.x < M) {
+    float s = 0.f;
+    for (int i = 0; i < slices; ++i) s += partial[threadIdx.x * slices + i];
+    out[threadIdx.x] = s;
   }
 }
 
@@ -223,7 +244,7 @@ struct ColsumJob {
   int outer, r, inner, C;
   float alpha;
 };
-constexpr int kColsumSlices = 8;
+constexpr int kColsumSlices = 32;
 
 __global__ void colsum_kernel(const ColsumJob* __restrict__ jobs) {
   extern __shared__ float red[];  // [blockDim.x]
@@ -279,25 +300,33 @@ __global__ void colsum_reduce_kernel(const ColsumJob* __restrict__ jobs) {
 template <bool U_F32>
 __global__ void ca_bwd_reduce_kernel(const float* __restrict__ G, const void* __restrict__ u_,
                                      float* __restrict__ s_partial, int HW, int C) {
-  extern __shared__ float red[];
+  extern __shared__ float red[];   // [lanes][C]
   const int n = blockIdx.y, chunks = gridDim.x;
-  const int lanes = blockDim.x / C, c = threadIdx.x % C, lane = threadIdx.x / C;
+  const int vpp = C / 4;                      // float4 vectors per pixel
+  const int lanes = blockDim.x / vpp, c4 = (threadIdx.x % vpp) * 4, lane = threadIdx.x / vpp;
   const int p_begin = int((long long)HW * blockIdx.x / chunks), p_end = int((long long)HW * (blockIdx.x + 1) / chunks);
-  float s0 = 0.f, s1 = 0.f;
+  auto ldu = [&](size_t o) -> float4 {
+    if (U_F32) return *reinterpret_cast<const float4*>(static_cast<const float*>(u_) + o);
+    const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(u_) + o);
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+  };
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
   int p = p_begin + lane;
   for (; p + lanes < p_end; p += 2 * lanes) {
-    const size_t o0 = (size_t(n) * HW + p) * C + c, o1 = o0 + size_t(lanes) * C;
-    const float u0 = U_F32 ? static_cast<const float*>(u_)[o0] : __bfloat162float(static_cast<const __nv_bfloat16*>(u_)[o0]);
-    const float u1 = U_F32 ? static_cast<const float*>(u_)[o1] : __bfloat162float(static_cast<const __nv_bfloat16*>(u_)[o1]);
-    s0 = fmaf(G[o0], u0, s0);
-    s1 = fmaf(G[o1], u1, s1);
+    const size_t o0 = (size_t(n) * HW + p) * C + c4, o1 = o0 + size_t(lanes) * C;
+    const float4 g0 = *reinterpret_cast<const float4*>(G + o0), g1 = *reinterpret_cast<const float4*>(G + o1);
+    const float4 u0 = ldu(o0), u1 = ldu(o1);
+    a0.x = fmaf(g0.x, u0.x, a0.x); a0.y = fmaf(g0.y, u0.y, a0.y); a0.z = fmaf(g0.z, u0.z, a0.z); a0.w = fmaf(g0.w, u0.w, a0.w);
+    a1.x = fmaf(g1.x, u1.x, a1.x); a1.y = fmaf(g1.y, u1.y, a1.y); a1.z = fmaf(g1.z, u1.z, a1.z); a1.w = fmaf(g1.w, u1.w, a1.w);
   }
   if (p < p_end) {
-    const size_t o0 = (size_t(n) * HW + p) * C + c;
-    const float u0 = U_F32 ? static_cast<const float*>(u_)[o0] : __bfloat162float(static_cast<const __nv_bfloat16*>(u_)[o0]);
-    s0 = fmaf(G[o0], u0, s0);
+    const size_t o0 = (size_t(n) * HW + p) * C + c4;
+    const float4 g0 = *reinterpret_cast<const float4*>(G + o0), u0 = ldu(o0);
+    a0.x = fmaf(g0.x, u0.x, a0.x); a0.y = fmaf(g0.y, u0.y, a0.y); a0.z = fmaf(g0.z, u0.z, a0.z); a0.w = fmaf(g0.w, u0.w, a0.w);
   }
-  red[threadIdx.x] = s0 + s1;
+  float* r = red + lane * C + c4;
+  r[0] = a0.x + a1.x; r[1] = a0.y + a1.y; r[2] = a0.z + a1.z; r[3] = a0.w + a1.w;
   __syncthreads();
   if (threadIdx.x < C) {
     float s = 0.f;
@@ -311,7 +340,8 @@ __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __
                                     const float* __restrict__ save_y, const float* __restrict__ w1,
                                     const float* __restrict__ w2, __nv_bfloat16* __restrict__ du,
                                     float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
-                                    float* __restrict__ db2, int N, int HW, int C, int Cr) {
+                                    float* __restrict__ db2, float* __restrict__ pg_scratch,
+                                    int* __restrict__ pg_counter, int N, int HW, int C, int Cr) {
   __shared__ float y_s[256], coef_s[256], dz2_s[256], dh_s[64];
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
@@ -341,47 +371,65 @@ __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __
     }
     __syncthreads();
   };
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
-    // parameter gradients: every image in order, accumulated in registers by fixed owner threads
-    float aw2[16], aw1[16];   // thread tid owns dW2[tid][0..Cr) and dW1[0..Cr)[tid]  (Cr <= 16 on this path)
-    float ab2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { aw2[j] = 0.f; aw1[j] = 0.f; }
-    float ab1 = 0.f;
-    for (int img = 0; img < N; ++img) {
-      per_image(img);
-      if (tid < C) {
-        const float dz = dz2_s[tid], mean = save_mean[img * C + tid];
-        ab2 += dz;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < Cr) { aw2[j] = fmaf(dz, save_hid[img * Cr + j], aw2[j]); aw1[j] = fmaf(dh_s[j], mean, aw1[j]); }
-      }
-      if (tid < Cr) ab1 += dh_s[tid];
-      __syncthreads();
-    }
-    if (tid < C) {
-      db2[tid] = ab2;
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < Cr) { dw2[tid * Cr + j] = aw2[j]; dw1[j * C + tid] = aw1[j]; }
-    }
-    if (tid < Cr) db1[tid] = ab1;
-  }
   per_image(n);
+  if (blockIdx.x == 0) {
+    // parameter gradients: block (0, n) writes image n's contribution; the LAST of the N blocks to finish sums
+    // all images in index order (deterministic) -- no serial chain through one CTA, no extra launch.
+    float* mine = pg_scratch + size_t(n) * (2 * C * Cr + C + Cr);
+    if (tid < C) {
+      const float dz = dz2_s[tid], mean = save_mean[n * C + tid];
+      for (int j = 0; j < Cr; ++j) {
+        mine[tid * Cr + j] = dz * save_hid[n * Cr + j];            // dW2[c][j]
+        mine[C * Cr + j * C + tid] = dh_s[j] * mean;               // dW1[j][c]
+      }
+      mine[2 * C * Cr + tid] = dz;                                 // db2[c]
+    }
+    if (tid < Cr) mine[2 * C * Cr + C + tid] = dh_s[tid];          // db1[j]
+    __threadfence();
+    __syncthreads();
+    __shared__ int last_s;
+    if (tid == 0) last_s = (atomicAdd(pg_counter, 1) == N - 1);
+    __syncthreads();
+    if (last_s) {
+      __threadfence();
+      const int per = 2 * C * Cr + C + Cr;
+      for (int i = tid; i < per; i += blockDim.x) {
+        float s = 0.f;
+        for (int img = 0; img < N; ++img) s += pg_scratch[size_t(img) * per + i];
+        if (i < C * Cr) dw2[i] = s;
+        else if (i < 2 * C * Cr) dw1[i - C * Cr] = s;
+        else if (i < 2 * C * Cr + C) db2[i - 2 * C * Cr] = s;
+        else db1[i - 2 * C * Cr - C] = s;
+      }
+      if (tid == 0) *pg_counter = 0;   // re-arm for the next launch
+    }
+  }
   const int vec_per_pix = C / 4;
   const size_t total = size_t(HW) * vec_per_pix;
   const size_t base = size_t(n) * HW * C;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
-    const int c4 = int(i % vec_per_pix) * 4;
-    const size_t off = base + i * 4;
-    const float4 g = *reinterpret_cast<const float4*>(G + off);
-    const float a = fmaf(g.x, y_s[c4], coef_s[c4]), b = fmaf(g.y, y_s[c4 + 1], coef_s[c4 + 1]);
-    const float c = fmaf(g.z, y_s[c4 + 2], coef_s[c4 + 2]), d = fmaf(g.w, y_s[c4 + 3], coef_s[c4 + 3]);
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(du + off) = pk;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += 2 * stride) {
+    const size_t i1 = i + stride;
+    const bool has1 = i1 < total;
+    const float4 g0 = *reinterpret_cast<const float4*>(G + base + i * 4);
+    float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has1) g1 = *reinterpret_cast<const float4*>(G + base + i1 * 4);
+    {
+      const int c4 = int(i % vec_per_pix) * 4;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(g0.x, y_s[c4], coef_s[c4]), fmaf(g0.y, y_s[c4 + 1], coef_s[c4 + 1]));
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(g0.z, y_s[c4 + 2], coef_s[c4 + 2]), fmaf(g0.w, y_s[c4 + 3], coef_s[c4 + 3]));
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(du + base + i * 4) = pk;
+    }
+    if (has1) {
+      const int c4 = int(i1 % vec_per_pix) * 4;
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(g1.x, y_s[c4], coef_s[c4]), fmaf(g1.y, y_s[c4 + 1], coef_s[c4 + 1]));
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(g1.z, y_s[c4 + 2], coef_s[c4 + 2]), fmaf(g1.w, y_s[c4 + 3], coef_s[c4 + 3]));
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(du + base + i1 * 4) = pk;
+    }
   }
 }
 

@@ -54,6 +54,13 @@ struct ConvPlan {
 int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
                       int box_h);
 int conv_plan_build(ConvPlan* p, const ConvDesc& d);
+
+// one conv's packing job for the batched pack kernel (misc_kernels.cuh: PackJob has the same layout)
+struct PackJobHost {
+  const float* w; void* p; const float* b; float* bp;
+  int cout, cin, rows_padded, r, dgrad;
+};
+int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s);
 int conv_plan_launch(const ConvPlan& p, cudaStream_t s);
 
 }  // namespace rb

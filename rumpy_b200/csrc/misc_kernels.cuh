@@ -44,6 +44,44 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// Whole-network variant: one launch packs every conv (job list in device memory).
+struct PackJob {
+  const float* w; __nv_bfloat16* p; const float* b; float* bp;   // bp == nullptr: no packed bias
+  int cout, cin, rows_padded, r, dgrad;
+};
+__global__ void pack_conv3x3_batched_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob jb = jobs[blockIdx.y];
+  const int rows = jb.dgrad ? jb.cin : jb.rows_padded;
+  const int kdim = jb.dgrad ? jb.cout : jb.cin;
+  const size_t total = size_t(9) * rows * kdim;
+  const int rr = jb.r * jb.r, cpp = jb.cout / rr;
+  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += size_t(gridDim.x) * blockDim.x) {
+    const int k = int(idx % kdim);
+    const int row = int((idx / kdim) % rows);
+    const int tap = int(idx / (size_t(kdim) * rows));
+    const int kx = tap / 3, ky = tap % 3;
+    float v = 0.f;
+    if (!jb.dgrad) {
+      if (row < jb.cout) {
+        const int o = (jb.r > 1) ? (row % cpp) * rr + row / cpp : row;
+        v = jb.w[((size_t(o) * jb.cin + k) * 3 + ky) * 3 + kx];
+      }
+    } else {
+      const int o = (jb.r > 1) ? (k % cpp) * rr + k / cpp : k;
+      v = jb.w[((size_t(o) * jb.cin + row) * 3 + (2 - ky)) * 3 + (2 - kx)];
+    }
+    jb.p[idx] = __float2bfloat16_rn(v);
+  }
+  if (jb.bp != nullptr && blockIdx.x == 0) {
+    for (int row = threadIdx.x; row < jb.rows_padded; row += blockDim.x) {
+      float v = 0.f;
+      if (row < jb.cout) v = jb.b[(jb.r > 1) ? (row % cpp) * rr + row / cpp : row];
+      jb.bp[row] = v;
+    }
+  }
+}
+
 // bias in packed-row order (pixel-shuffle permutation), zero padded
 __global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ p, int cout, int rows_padded,
                                  int r) {
@@ -180,18 +218,15 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
   const int vec_per_pix = C / 4;
   const size_t total = size_t(HW) * vec_per_pix;
   const size_t base = size_t(n) * HW * C;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += size_t(gridDim.x) * blockDim.x) {
+  auto load_u = [&](size_t off) -> float4 {
+    if (U_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(u_) + off);
+    const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(u_) + off);
+    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
+                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
+  };
+  auto emit = [&](size_t i, const float4& uu, const float4& xi) {
     const int c4 = int(i % vec_per_pix) * 4;
     const size_t off = base + i * 4;
-    float4 uu;
-    if (U_F32) {
-      uu = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(u_) + off);
-    } else {
-      const uint2 raw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(u_) + off);
-      uu.x = __uint_as_float(raw.x << 16); uu.y = __uint_as_float(raw.x & 0xFFFF0000u);
-      uu.z = __uint_as_float(raw.y << 16); uu.w = __uint_as_float(raw.y & 0xFFFF0000u);
-    }
-    const float4 xi = *reinterpret_cast<const float4*>(x_in + off);
     float4 o;
     o.x = fmaf(uu.x, y_s[c4], xi.x); o.y = fmaf(uu.y, y_s[c4 + 1], xi.y);
     o.z = fmaf(uu.z, y_s[c4 + 2], xi.z); o.w = fmaf(uu.w, y_s[c4 + 3], xi.w);
@@ -200,6 +235,18 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(x_out_b + off) = pk;
+  };
+  // two vectors (4 independent 16-byte loads) in flight per thread
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += 2 * stride) {
+    const size_t i1 = i + stride;
+    const bool has1 = i1 < total;
+    const float4 u0 = load_u(base + i * 4);
+    const float4 x0 = *reinterpret_cast<const float4*>(x_in + base + i * 4);
+    float4 u1 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = u1;
+    if (has1) { u1 = load_u(base + i1 * 4); x1 = *reinterpret_cast<const float4*>(x_in + base + i1 * 4); }
+    emit(i, u0, x0);
+    if (has1) emit(i1, u1, x1);
   }
 }
 

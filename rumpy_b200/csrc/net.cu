@@ -79,6 +79,14 @@ struct Net {
   WgradReduceJob* wg_rjobs_dev = nullptr;
   ColsumJob* cs_jobs_dev = nullptr;
   bool jobs_uploaded = false;
+  float* pg_scratch = nullptr;
+  int* pg_counter = nullptr;
+  // batched weight packing
+  size_t pack_jobs_bytes = 0;
+  std::vector<PackJobHost> pack_jobs;
+  const void* pack_sig_packed = nullptr;
+  const float* pack_sig_p0 = nullptr;
+  int pack_sig_training = -1;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -142,6 +150,9 @@ static int net_init(Net* n) {
     n->convs[i].off_dgrad = n->packed_bytes_train;
     n->packed_bytes_train = align_up(n->packed_bytes_train + size_t(9) * n->convs[i].cout * n->convs[i].cin * 2, 256);
   }
+  n->pack_jobs_bytes = align_up(2 * n->convs.size() * sizeof(PackJobHost), 256);
+  n->packed_bytes += n->pack_jobs_bytes;
+  n->packed_bytes_train += n->pack_jobs_bytes;
   return RUMPY_OK;
 }
 
@@ -157,8 +168,9 @@ static int wgrad_splits(int m_tiles) {
   return s;
 }
 
-constexpr int kThinBlocks = 296;
-constexpr int kCaBwdChunks = 16;
+constexpr int kThinBlocks = 1184;
+constexpr int kPlaneSlices = 64;
+constexpr int kCaBwdChunks = 32;
 
 // Lays out the workspace and (when build) builds the op lists.  Forward buffers first, then (training) the
 // backward buffers, so `bytes_out` covers a whole train step.
@@ -429,6 +441,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     cs_dev = static_cast<ColsumJob*>(bp.take(sites.size() * sizeof(ColsumJob)));
     float* partials = static_cast<float*>(bp.take(njobs * 9 * 64 * 64 * sizeof(float)));
     float* cs_partials = static_cast<float*>(bp.take(cs_floats * sizeof(float)));
+    float* pg_scratch = static_cast<float*>(bp.take(size_t(N) * (2 * C * Cr + C + Cr) * sizeof(float)));
+    int* pg_counter = static_cast<int*>(bp.take(256));
+    if (build) { n->pg_scratch = pg_scratch; n->pg_counter = pg_counter; }
     if (build) {
       size_t job_cursor = 0, cs_cursor = 0;
       for (const Site& s : sites) {
@@ -544,7 +559,7 @@ int rumpy_net_num_launches_backward(void* net) {
   int c = 4;                                  // batched wgrad, its reduce, colsum, colsum reduce
   for (const Op& op : n->bops) {
     switch (op.type) {
-      case OP_TAIL_BWD: c += 4; break;        // dgrad, wgrad, reduce, plane sums
+      case OP_TAIL_BWD: c += 5; break;        // dgrad, wgrad, reduce, plane sums (2)
       case OP_CA_BWD: c += 2; break;
       case OP_HEAD_WGRAD: c += 2; break;
       default: c += 1;
@@ -573,20 +588,34 @@ long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training
 int rumpy_net_pack(void* net_, const float* const* params, void* packed, int training, void* stream) {
   Net* n = static_cast<Net*>(net_);
   if (!n || !params || !packed) return set_error(RUMPY_ERR_ARG, "net_pack: null");
+  if (int e = device_info(nullptr)) return e;
   char* pk = static_cast<char*>(packed);
-  for (size_t i = 1; i < n->convs.size(); ++i) {  // conv 0 is the fp32 head
-    const ConvW& c = n->convs[i];
-    if (int e = rumpy_pack_conv3x3(params[c.w_idx], pk + c.off_fwd, c.cout, c.cin, c.rows_padded, c.r, 0, stream))
-      return e;
-    if (c.off_bias != SIZE_MAX)
-      if (int e = rumpy_pack_bias(params[c.b_idx], reinterpret_cast<float*>(pk + c.off_bias), c.cout, c.rows_padded,
-                                  c.r, stream))
-        return e;
-    if (training && c.off_dgrad != SIZE_MAX)
-      if (int e = rumpy_pack_conv3x3(params[c.w_idx], pk + c.off_dgrad, c.cout, c.cin, c.cout, c.r, 1, stream))
-        return e;
+  const size_t total = training ? n->packed_bytes_train : n->packed_bytes;
+  PackJobHost* jobs_dev = reinterpret_cast<PackJobHost*>(pk + total - n->pack_jobs_bytes);
+  // the job list (pointers into params / packed) is rebuilt and re-uploaded only when those pointers change
+  if (n->pack_sig_packed != packed || n->pack_sig_p0 != params[0] || n->pack_sig_training != training ||
+      n->pack_jobs.empty()) {
+    n->pack_jobs.clear();
+    for (size_t i = 1; i < n->convs.size(); ++i) {  // conv 0 is the fp32 head
+      const ConvW& c = n->convs[i];
+      PackJobHost j{};
+      j.w = params[c.w_idx]; j.p = pk + c.off_fwd; j.cout = c.cout; j.cin = c.cin; j.rows_padded = c.rows_padded;
+      j.r = c.r; j.dgrad = 0;
+      if (c.off_bias != SIZE_MAX) { j.b = params[c.b_idx]; j.bp = reinterpret_cast<float*>(pk + c.off_bias); }
+      n->pack_jobs.push_back(j);
+      if (training && c.off_dgrad != SIZE_MAX) {
+        PackJobHost d{};
+        d.w = params[c.w_idx]; d.p = pk + c.off_dgrad; d.cout = c.cout; d.cin = c.cin; d.rows_padded = c.cout;
+        d.r = c.r; d.dgrad = 1;
+        n->pack_jobs.push_back(d);
+      }
+    }
+    if (cudaMemcpyAsync(jobs_dev, n->pack_jobs.data(), n->pack_jobs.size() * sizeof(PackJobHost),
+                        cudaMemcpyHostToDevice, cudaStream_t(stream)) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "net_pack: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    n->pack_sig_packed = packed; n->pack_sig_p0 = params[0]; n->pack_sig_training = training;
   }
-  return RUMPY_OK;
+  return pack_batched_launch(jobs_dev, int(n->pack_jobs.size()), cudaStream_t(stream));
 }
 
 int rumpy_net_forward(void* net_, const float* const* params, const void* packed, const float* x_nchw,
@@ -652,6 +681,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
                                      stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
       return set_error(RUMPY_ERR_CUDA, "net_backward: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (n->pg_counter) cudaMemsetAsync(n->pg_counter, 0, 256, stream);
     cudaStreamSynchronize(stream);  // the temporaries above die at scope exit; happens once per plan
     n->jobs_uploaded = true;
   }
@@ -671,8 +701,10 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         if (int e = check_launch("tail_wgrad")) return e;
         thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[tail.w_idx], nullptr, C, M, 0);
         if (int e = check_launch("tail_wgrad_reduce")) return e;
-        plane_sum_kernel<<<M, 1024, 0, stream>>>(dy_nchw, grads[tail.b_idx], N, M, Hh * Wh);
+        plane_sum_kernel<<<dim3(kPlaneSlices, M), 512, 0, stream>>>(dy_nchw, op.thin_partial, N, M, Hh * Wh);
         if (int e = check_launch("tail_bias_grad")) return e;
+        plane_sum_finalize_kernel<<<1, 32, 0, stream>>>(op.thin_partial, kPlaneSlices, grads[tail.b_idx], M);
+        if (int e = check_launch("tail_bias_grad_finalize")) return e;
         break;
       }
       case OP_CONV:
@@ -682,9 +714,9 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         const int HW = H * W;
         dim3 g1(kCaBwdChunks, N);
         if (n->u_f32)
-          ca_bwd_reduce_kernel<true><<<g1, thin_block, thin_block * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
+          ca_bwd_reduce_kernel<true><<<g1, 256, (256 / (C / 4)) * C * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
         else
-          ca_bwd_reduce_kernel<false><<<g1, thin_block, thin_block * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
+          ca_bwd_reduce_kernel<false><<<g1, 256, (256 / (C / 4)) * C * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
         if (int e = check_launch("ca_bwd_reduce")) return e;
         const size_t vec = size_t(HW) * (C / 4);
         int chunks = int((vec + 1023) / 1024);
@@ -693,8 +725,8 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         if (chunks < 1) chunks = 1;
         ca_bwd_apply_kernel<<<dim3(chunks, N), 256, 0, stream>>>(
             op.a, op.s_partial, kCaBwdChunks, op.save_mean, op.save_hid, op.save_y, params[op.ca.w1], params[op.ca.w2],
-            static_cast<__nv_bfloat16*>(op.du), grads[op.ca.w1], grads[op.ca.b1], grads[op.ca.w2], grads[op.ca.b2], N,
-            HW, C, Cr);
+            static_cast<__nv_bfloat16*>(op.du), grads[op.ca.w1], grads[op.ca.b1], grads[op.ca.w2], grads[op.ca.b2],
+            n->pg_scratch, n->pg_counter, N, HW, C, Cr);
         if (int e = check_launch("ca_bwd_apply")) return e;
         break;
       }
