@@ -71,6 +71,8 @@ def load():
         fn.argtypes = argtypes
         fn.restype = (ctypes.c_char_p if name == 'rumpy_last_error' else
                       ctypes.c_longlong if name in _LONGLONG else ctypes.c_int)
+    if os.environ.get('RUMPY_B200_PDL') == '0':      # debug switch: disable programmatic dependent launch
+        lib.rumpy_debug_set_pdl(0)
     _lib = lib
     return lib
 

@@ -8,6 +8,7 @@ namespace rb {
 
 thread_local std::string g_last_error;
 long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
+int g_use_pdl = 1;                       // programmatic dependent launch between layers (rumpy_debug_set_pdl)
 
 int set_error(int code, const char* fmt, ...) {
   char buf[512];
@@ -192,8 +193,13 @@ static int launch_conv_t(const ConvPlan& p, cudaStream_t s) {
       return set_error(RUMPY_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
-  kern<<<p.grid, kConvThreads, p.smem, s>>>(p.maps, p.args);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p.maps, p.args);
   if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "conv3x3 launch: %s", cudaGetErrorString(e));
   return RUMPY_OK;
 }
@@ -232,6 +238,7 @@ extern "C" {
 int rumpy_version(void) { return RUMPY_B200_VERSION; }
 /* debug hook, not part of the public header: per-CTA clock64 timeline (16 slots per CTA) for conv kernels */
 int rumpy_debug_set_timeline(void* buf) { g_debug_timeline = static_cast<long long*>(buf); return 0; }
+int rumpy_debug_set_pdl(int on) { g_use_pdl = on; return 0; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }
 int rumpy_device_check(void) { return device_info(nullptr); }
 
@@ -309,15 +316,22 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
   const int cap = (sms * 8 + N - 1) / N;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
-  dim3 grid(chunks, N);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(chunks, N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = cudaStream_t(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  const int partials = tiles * 2, HW = H * W;
+  __nv_bfloat16* xob = static_cast<__nv_bfloat16*>(x_out_bf16);
+  cudaError_t le;
   if (u_is_f32)
-    ca_apply_kernel<true><<<grid, 256, 0, cudaStream_t(stream)>>>(
-        pool_partial, tiles * 2, u, x_in, w1, b1, w2, b2, x_out, static_cast<__nv_bfloat16*>(x_out_bf16), save_mean,
-        save_hid, save_y, H * W, C, Cr);
+    le = cudaLaunchKernelEx(&cfg, ca_apply_kernel<true>, pool_partial, partials, u, x_in, w1, b1, w2, b2, x_out, xob,
+                            save_mean, save_hid, save_y, HW, C, Cr);
   else
-    ca_apply_kernel<false><<<grid, 256, 0, cudaStream_t(stream)>>>(
-        pool_partial, tiles * 2, u, x_in, w1, b1, w2, b2, x_out, static_cast<__nv_bfloat16*>(x_out_bf16), save_mean,
-        save_hid, save_y, H * W, C, Cr);
+    le = cudaLaunchKernelEx(&cfg, ca_apply_kernel<false>, pool_partial, partials, u, x_in, w1, b1, w2, b2, x_out, xob,
+                            save_mean, save_hid, save_y, HW, C, Cr);
+  if (le != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "ca_apply launch: %s", cudaGetErrorString(le));
   return check_launch("ca_apply");
 }
 

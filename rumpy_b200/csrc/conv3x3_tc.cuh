@@ -123,6 +123,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  grid_dep_launch_dependents();   // PDL: let the next layer's CTAs start their prologue as SMs free up
   if (threadIdx.x == 0) { RB_STAMP(0); RB_STAMP_NS(14); }
   const int stages = args.stages;
   const int cin_chunks = args.cin_chunks;
@@ -176,6 +177,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       }
       __syncwarp();
     }
+    grid_dep_wait();   // weights are static; activations come from the previous kernel
     int stage = 0;
     uint32_t phase = 0;
     for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
@@ -250,6 +252,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     const int ly = row >> 4, lx = row & 15;
     for (int i = et; i < BN; i += 128) bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
     named_bar_sync(1, 128);
+    grid_dep_wait();   // residual / mask inputs and every global write must follow the previous kernel
     int it = 0;
     if constexpr (BN == 16) {
       // thin tail conv (C -> out_feats <= 16): fp32 NCHW written straight from registers, no staging

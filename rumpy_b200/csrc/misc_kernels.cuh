@@ -168,6 +168,8 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
   __shared__ float mean_s[256], y_s[256], hid_s[64], red_s[256];
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: pool partials / u come from the previous kernel
   {
     // per-image channel sums from the conv epilogue's per-tile partials: blockDim/C thread groups split the
     // partial list, 4 independent loads in flight each (a serial chain of L2 round trips was 11 us here);

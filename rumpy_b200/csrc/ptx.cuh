@@ -65,6 +65,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may
+// start its prologue now; grid_dep_wait: block until the previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void grid_dep_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ proxies / named barriers
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
