@@ -80,14 +80,19 @@ class _NativeTrunk(nn.Module):
         raise NotImplementedError
 
     def native_engine(self):
-        params = list(self.parameters())
         eng = self._engine_obj
-        if eng is None or eng.device != params[0].device or len(eng.params) != len(params) or \
-                any(a is not b for a, b in zip(eng.params, params)):
+        if eng is None:
+            params = list(self.parameters())
             arch, kw = self._engine_kwargs()
             eng = _engine.TrunkEngine(arch, params, **kw)
             object.__setattr__(self, '_engine_obj', eng)   # not a submodule / not in state_dict
         return eng
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() re-create parameter storage: the cached engine (flat views, packed weights,
+        # launch plans) is rebuilt on next use
+        object.__setattr__(self, '_engine_obj', None)
+        return super()._apply(fn, *args, **kwargs)
 
     def forward(self, x):
         return trunk_apply(self, x)

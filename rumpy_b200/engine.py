@@ -14,6 +14,38 @@ from . import _lib
 
 ARCH_RCAN, ARCH_EDSR = 0, 1
 
+_FLAT = {}   # id(first parameter) -> (flat fp32 buffer, weakref to first parameter): shared by engine and FusedAdam
+
+
+def flatten_parameters(params):
+    """Makes every parameter a view of ONE flat fp32 buffer (state_dict / load_state_dict keep working: they copy
+    in place).  Gives O(1) change detection (views share the base tensor's version counter), one-kernel Adam and a
+    single all-reduce buffer.  Idempotent."""
+    import weakref
+    params = list(params)
+    ent = _FLAT.get(id(params[0]))
+    if ent is not None and ent[1]() is params[0]:
+        flat, off, ok = ent[0], 0, True
+        for p in params:
+            if p.data_ptr() != flat.data_ptr() + off * 4:
+                ok = False
+                break
+            off += p.numel()
+        if ok and off == flat.numel():
+            return flat
+    dev = params[0].device
+    n = sum(p.numel() for p in params)
+    flat = torch.empty(n, dtype=torch.float32, device=dev)
+    off = 0
+    with torch.no_grad():
+        for p in params:
+            k = p.numel()
+            flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + k].view(p.shape)
+            off += k
+    _FLAT[id(params[0])] = (flat, weakref.ref(params[0]))
+    return flat
+
 
 class TrunkEngine:
     def __init__(self, arch, params, *, n_feats, n_groups, n_blocks, reduction=16, scale=4, res_scale=1.0,
@@ -33,7 +65,8 @@ class TrunkEngine:
             raise _lib.RumpyB200Error('rumpy_b200 has no CPU path: move the model to a CUDA (sm_100) device')
         self.packed = torch.empty(self.lib.rumpy_net_packed_bytes(h, 1), dtype=torch.uint8, device=self.device)
         self._packed_training = False
-        self.flat_params = None      # set by FusedAdam.attach: all parameters are views of one flat buffer
+        self.flat_params = flatten_parameters(self.params)   # all parameters are views of one flat buffer
+        self._flat_sig = None
         self.flat_grads = None
         self._grad_views = None
         self._grad_ptr_array = None
@@ -71,6 +104,8 @@ class TrunkEngine:
 
     def attach_flat(self, flat_params, flat_grads):
         """Called by FusedAdam: parameters (and .grad) are views into these flat fp32 buffers."""
+        if flat_params.data_ptr() != self.flat_params.data_ptr():
+            raise _lib.RumpyB200Error('optimizer and engine disagree on the flat parameter buffer')
         self.flat_params, self.flat_grads = flat_params, flat_grads
         self._ptr_sig = None
         self._flat_sig = None

@@ -22,9 +22,10 @@ class FusedAdam(torch.optim.Optimizer):
         self._params = list(self.param_groups[0]['params'])
         if not self._params or any(p.device.type != 'cuda' or p.dtype != torch.float32 for p in self._params):
             raise _lib.RumpyB200Error('FusedAdam needs fp32 CUDA parameters (no CPU fallback)')
+        from .engine import flatten_parameters
         dev = self._params[0].device
-        n = sum(p.numel() for p in self._params)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_p = flatten_parameters(self._params)               # parameters become views of flat_p
+        n = self.flat_p.numel()
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -33,8 +34,6 @@ class FusedAdam(torch.optim.Optimizer):
         self._slices = []
         for p in self._params:
             k = p.numel()
-            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
-            p.data = self.flat_p[off:off + k].view(p.shape)          # parameters become views of flat_p
             p.grad = self.flat_g[off:off + k].view(p.shape)
             self._slices.append((off, k))
             off += k

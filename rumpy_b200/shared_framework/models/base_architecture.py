@@ -206,7 +206,8 @@ class BaseModel(nn.Module):
         if self.loss_masking:
             raise NotImplementedError('rumpy_b200: loss masking is outside the EDSR/RCAN trunk path')
         from rumpy_b200 import train_native
-        self.net.train()
+        if not self.net.training:
+            self.net.train()
         dev = self._torch_device()
         x, y = x.to(device=dev, non_blocking=True), y.to(device=dev, non_blocking=True)
         loss, out = train_native.train_step(self.net, self.optimizer, x, y, grad_clip=self.grad_clip,
@@ -218,7 +219,8 @@ class BaseModel(nn.Module):
         return loss.detach().cpu().numpy(), out.detach().cpu()
 
     def run_eval(self, x, y=None, request_loss=False, tag=None, timing=False, keep_on_device=False, *args, **kwargs):
-        self.net.eval()
+        if self.net.training:
+            self.net.eval()          # nn.Module.eval() walks ~2000 submodules: only when the mode changes
         with torch.no_grad():
             x = x.to(device=self._torch_device(), non_blocking=True)
             if timing:

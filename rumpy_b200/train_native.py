@@ -38,8 +38,8 @@ def l1_loss(out, y, want_grad=False, gscale=1.0):
 def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None):
     """One optimiser step on batch (x, y); returns (loss 0-dim device tensor, SR output on device)."""
     eng = net.native_engine()
-    if getattr(optimizer, 'flat_p', None) is not None and eng.flat_params is not optimizer.flat_p:
-        optimizer.attach_engine(eng)
+    if getattr(optimizer, 'flat_g', None) is not None and eng.flat_grads is not optimizer.flat_g:
+        optimizer.attach_engine(eng)       # engine writes gradients straight into the optimiser's flat buffer
     out = eng.forward(x, training=True)
     loss, dy = l1_loss(out, y, want_grad=True)
     eng.backward(x, dy)
