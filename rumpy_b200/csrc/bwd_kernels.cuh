@@ -342,13 +342,28 @@ __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __
                                     float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
                                     float* __restrict__ db2, float* __restrict__ pg_scratch,
                                     int* __restrict__ pg_counter, int N, int HW, int C, int Cr) {
-  __shared__ float y_s[256], coef_s[256], dz2_s[256], dh_s[64];
+  __shared__ float y_s[256], coef_s[256], dz2_s[256], dh_s[64], red_s[256];
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
   auto per_image = [&](int img) {   // fills y_s, dz2_s, dh_s, coef_s for image `img`
+    {
+      // s[c] = sum of the reduce kernel's chunk partials: thread groups split the list (independent loads in
+      // flight instead of a serial chain of L2 round trips), fixed order
+      const int groups = blockDim.x / C, g = tid / C, c = tid % C;
+      float a0 = 0.f, a1 = 0.f;
+      if (g < groups) {
+        const float* pp = s_partial + size_t(img) * s_chunks * C + c;
+        int k = g;
+        for (; k + groups < s_chunks; k += 2 * groups) { a0 += pp[size_t(k) * C]; a1 += pp[size_t(k + groups) * C]; }
+        if (k < s_chunks) a0 += pp[size_t(k) * C];
+      }
+      red_s[tid] = a0 + a1;
+    }
+    __syncthreads();
     if (tid < C) {
+      const int groups = blockDim.x / C;
       float s = 0.f;
-      for (int k = 0; k < s_chunks; ++k) s += s_partial[(size_t(img) * s_chunks + k) * C + tid];
+      for (int g = 0; g < groups; ++g) s += red_s[g * C + tid];
       const float y = save_y[img * C + tid];
       y_s[tid] = y;
       dz2_s[tid] = s * y * (1.f - y);

@@ -1,0 +1,90 @@
+"""`eval_sisr` mirror (reference: rumpy/shared_framework/net_eval.py:19-132, evaluation/standard_eval.py:342-556) for
+the options the EDSR/RCAN path uses.  Images are sharded round-robin over ranks under torchrun (no collective);
+rank 0 writes <out_loc>/<results_name>/standard_metrics/{individual,average}_metrics.csv.
+
+    python -m rumpy_b200.shared_framework.net_eval --config eval.toml
+"""
+import csv
+import os
+
+import click
+
+
+@click.command()
+@click.option('--config', default=None, help='TOML file providing any of the options below')
+@click.option('--model_and_epoch', '-me', multiple=True, nargs=2, help='experiment name and epoch')
+@click.option('--model_loc', default=None, help='directory holding the experiment folders')
+@click.option('--hr_dir', default=None)
+@click.option('--lr_dir', default=None)
+@click.option('--results_name', default='eval')
+@click.option('--out_loc', default='.')
+@click.option('--metrics', '-m', multiple=True, default=('PSNR',))
+@click.option('--scale', default=4)
+@click.option('--batch_size', default=1)
+@click.option('--gpu/--no-gpu', default=True)
+@click.option('--sp_gpu', default=0)
+@click.option('--save_im', is_flag=True, default=False)
+def eval_run(config, **kw):
+    import numpy as np
+    import toml
+    import torch
+    import torch.distributed as dist
+    from rumpy_b200 import parallel
+    from rumpy_b200.shared_framework.data import PairSet, psnr_y
+    from rumpy_b200.shared_framework.models import define_model
+
+    if config:
+        for k, v in toml.load(config).items():
+            if k in kw:
+                kw[k] = v
+    if not kw['gpu']:
+        raise RuntimeError('rumpy_b200 eval needs a CUDA (sm_100) device: gpu=false has no fallback path')
+    local = int(kw['sp_gpu'])
+    if 'RANK' in os.environ and int(os.environ.get('WORLD_SIZE', 1)) > 1:
+        local = int(os.environ.get('LOCAL_RANK', 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    out_dir = os.path.join(kw['out_loc'], kw['results_name'], 'standard_metrics')
+    if rank == 0:
+        os.makedirs(out_dir, exist_ok=True)
+    ds = PairSet({'lr': kw['lr_dir'], 'hr': kw['hr_dir']}, int(kw['scale']))
+    rows = []
+    for exp, epoch in [tuple(me) for me in kw['model_and_epoch']]:
+        cfg = toml.load(os.path.join(kw['model_loc'], exp, 'config.toml'))
+        internal = dict(cfg['model'].get('internal_params', {}))
+        internal.setdefault('scale', int(kw['scale']))
+        internal.pop('lr', None)
+        model = define_model(cfg['model']['name'], model_save_dir=os.path.join(kw['model_loc'], exp, 'saved_models'),
+                             device=local, eval_mode=True, **internal)
+        model.load_model('train_model', epoch, legacy=model.legacy_load)
+        for idx in parallel.shard_round_robin(range(len(ds))):
+            name, lr, hr = ds.sample(idx)
+            out, _, secs = model.run_eval(lr[None], timing=True)
+            rows.append({'image': name, 'model': exp, 'runtime': secs, 'PSNR': psnr_y(out, hr[None])})
+            if kw['save_im']:
+                from PIL import Image
+                im = np.clip(out[0].permute(1, 2, 0).numpy() * 255, 0, 255).astype(np.uint8)   # truncation,
+                Image.fromarray(im).save(os.path.join(out_dir, f'{exp}_{name}'))                # visualization.py:56
+    if dist.is_initialized():
+        gathered = [None] * dist.get_world_size()
+        dist.all_gather_object(gathered, rows)      # host-side result collection only; no data-path collective
+        rows = [r for part in gathered for r in part]
+    if rank == 0:
+        with open(os.path.join(out_dir, 'individual_metrics.csv'), 'w', newline='') as f:
+            w = csv.DictWriter(f, fieldnames=['image', 'model', 'runtime', 'PSNR'])
+            w.writeheader()
+            w.writerows(sorted(rows, key=lambda r: (r['model'], r['image'])))
+        with open(os.path.join(out_dir, 'average_metrics.csv'), 'w', newline='') as f:
+            w = csv.writer(f)
+            w.writerow(['model', 'runtime', 'PSNR'])
+            for exp in sorted({r['model'] for r in rows}):
+                sel = [r for r in rows if r['model'] == exp]
+                w.writerow([exp, np.mean([r['runtime'] for r in sel]), np.mean([r['PSNR'] for r in sel])])
+        print(f'wrote {out_dir}')
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    eval_run()

@@ -179,3 +179,40 @@ def test_handler_api_train_and_eval(tmp_path):
     assert torch.allclose(out2, out_e, atol=1e-6)
     with pytest.raises(RuntimeError):
         h2.run_train(x=torch.from_numpy(x), y=torch.from_numpy(y))
+
+
+def test_cli_train_then_eval(tmp_path):
+    """train_sisr / eval_sisr mirrors: TOML in, reference on-disk layout out."""
+    import toml
+    from click.testing import CliRunner
+    from rumpy_b200.shared_framework.net_eval import eval_run
+    from rumpy_b200.shared_framework.net_train import experiment_setup
+    from PIL import Image
+    rs = np.random.RandomState(0)
+    lr_dir, hr_dir = tmp_path / 'lr', tmp_path / 'hr'
+    lr_dir.mkdir(); hr_dir.mkdir()
+    for i in range(3):
+        Image.fromarray(rs.randint(0, 256, (24, 36, 3), dtype=np.uint8)).save(lr_dir / f'im{i}.png')
+        Image.fromarray(rs.randint(0, 256, (96, 144, 3), dtype=np.uint8)).save(hr_dir / f'im{i}.png')
+    cfg = {'experiment': 'probe_rcan', 'experiment_save_loc': str(tmp_path / 'exp'),
+           'data': {'batch_size': 2, 'dataloader_threads': 0,
+                    'training_sets': {'data_1': {'lr': str(lr_dir), 'hr': str(hr_dir), 'crop': 16, 'random_augment': True}},
+                    'eval_sets': {'data_1': {'lr': str(lr_dir), 'hr': str(hr_dir)}}},
+           'model': {'name': 'rcan', 'internal_params': {
+               'scale': 4, 'lr': 1e-4, 'n_resgroups': 1, 'n_resblocks': 2, 'scheduler': 'cosine_annealing_warm_restarts',
+               'scheduler_params': {'t_mult': 1, 'restart_period': 40000, 'lr_min': 1e-7}}},
+           'training': {'seed': 8, 'num_epochs': 2, 'metrics': ['PSNR'], 'gpu': 'single', 'sp_gpu': 0}}
+    cfg_path = tmp_path / 'cfg.toml'
+    cfg_path.write_text(toml.dumps(cfg))
+    res = CliRunner().invoke(experiment_setup, ['--parameters', str(cfg_path)])
+    assert res.exit_code == 0, res.output + repr(res.exception)
+    base = tmp_path / 'exp' / 'probe_rcan'
+    assert (base / 'config.toml').exists() and (base / 'saved_models' / 'train_model_1').exists()
+    lines = (base / 'result_outputs' / 'summary.csv').read_text().strip().splitlines()
+    assert lines[0] == 'epoch,train-loss,learning-rate,val-loss,val-PSNR' and len(lines) == 3
+    res = CliRunner().invoke(eval_run, ['-me', 'probe_rcan', '1', '--model_loc', str(tmp_path / 'exp'), '--hr_dir',
+                                        str(hr_dir), '--lr_dir', str(lr_dir), '--out_loc', str(tmp_path / 'out'),
+                                        '--results_name', 'probe'])
+    assert res.exit_code == 0, res.output + repr(res.exception)
+    rows = (tmp_path / 'out' / 'probe' / 'standard_metrics' / 'individual_metrics.csv').read_text().splitlines()
+    assert rows[0] == 'image,model,runtime,PSNR' and len(rows) == 4
