@@ -341,7 +341,8 @@ __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __
                                     const float* __restrict__ w2, __nv_bfloat16* __restrict__ du,
                                     float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
                                     float* __restrict__ db2, float* __restrict__ pg_scratch,
-                                    int* __restrict__ pg_counter, int N, int HW, int C, int Cr) {
+                                    int* __restrict__ pg_counter, float* __restrict__ du_colsum /* [N][gridDim.x][C] */,
+                                    int N, int HW, int C, int Cr) {
   __shared__ float y_s[256], coef_s[256], dz2_s[256], dh_s[64], red_s[256];
   const int tid = threadIdx.x;
   const int n = blockIdx.y;
@@ -422,29 +423,66 @@ __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __
   const int vec_per_pix = C / 4;
   const size_t total = size_t(HW) * vec_per_pix;
   const size_t base = size_t(n) * HW * C;
+  // every thread keeps the same 4 channels across iterations (the stride is a multiple of C/4), so the bias
+  // gradient of conv2 (column sums of du) accumulates in registers and leaves as one partial row per block
   const size_t stride = size_t(gridDim.x) * blockDim.x;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto emit = [&](size_t i, const float4& g) {
+    const int c4 = int(i % vec_per_pix) * 4;
+    const float a = fmaf(g.x, y_s[c4], coef_s[c4]), b = fmaf(g.y, y_s[c4 + 1], coef_s[c4 + 1]);
+    const float c = fmaf(g.z, y_s[c4 + 2], coef_s[c4 + 2]), d = fmaf(g.w, y_s[c4 + 3], coef_s[c4 + 3]);
+    cs.x += a; cs.y += b; cs.z += c; cs.w += d;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(du + base + i * 4) = pk;
+  };
   for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += 2 * stride) {
     const size_t i1 = i + stride;
     const bool has1 = i1 < total;
     const float4 g0 = *reinterpret_cast<const float4*>(G + base + i * 4);
     float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (has1) g1 = *reinterpret_cast<const float4*>(G + base + i1 * 4);
-    {
-      const int c4 = int(i % vec_per_pix) * 4;
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(g0.x, y_s[c4], coef_s[c4]), fmaf(g0.y, y_s[c4 + 1], coef_s[c4 + 1]));
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(g0.z, y_s[c4 + 2], coef_s[c4 + 2]), fmaf(g0.w, y_s[c4 + 3], coef_s[c4 + 3]));
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(du + base + i * 4) = pk;
+    emit(i, g0);
+    if (has1) emit(i1, g1);
+  }
+  if (du_colsum != nullptr) {
+    __shared__ float4 cs_s[256];
+    cs_s[tid] = cs;
+    __syncthreads();
+    if (tid < vec_per_pix) {      // threads tid, tid + vpp, tid + 2 vpp ... share the channel quad
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = tid; k < int(blockDim.x); k += vec_per_pix) {
+        t.x += cs_s[k].x; t.y += cs_s[k].y; t.z += cs_s[k].z; t.w += cs_s[k].w;
+      }
+      *reinterpret_cast<float4*>(du_colsum + (size_t(n) * gridDim.x + blockIdx.x) * C + tid * 4) = t;
     }
-    if (has1) {
-      const int c4 = int(i1 % vec_per_pix) * 4;
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf(g1.x, y_s[c4], coef_s[c4]), fmaf(g1.y, y_s[c4 + 1], coef_s[c4 + 1]));
-      __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf(g1.z, y_s[c4 + 2], coef_s[c4 + 2]), fmaf(g1.w, y_s[c4 + 3], coef_s[c4 + 3]));
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(du + base + i1 * 4) = pk;
+  }
+}
+
+// db[c] = alpha * sum_i partial[i][c]  -- bias gradients from per-tile (conv epilogue POOL) / per-block partial rows
+struct PartialSumJob {
+  const float* partial; float* db; int count, C; float alpha;
+};
+__global__ void partial_sum_kernel(const PartialSumJob* __restrict__ jobs) {
+  extern __shared__ float red[];
+  const PartialSumJob jb = jobs[blockIdx.x];
+  const int lanes = blockDim.x / jb.C, c = threadIdx.x % jb.C, lane = threadIdx.x / jb.C;
+  float s0 = 0.f, s1 = 0.f;
+  if (lane < lanes) {
+    int i = lane;
+    for (; i + lanes < jb.count; i += 2 * lanes) {
+      s0 += jb.partial[size_t(i) * jb.C + c];
+      s1 += jb.partial[size_t(i + lanes) * jb.C + c];
     }
+    if (i < jb.count) s0 += jb.partial[size_t(i) * jb.C + c];
+  }
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.x < jb.C) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * jb.C + threadIdx.x];
+    jb.db[threadIdx.x] = s * jb.alpha;
   }
 }
 

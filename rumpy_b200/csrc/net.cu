@@ -45,7 +45,7 @@ struct Op {
   CAW ca;
   const float* pool; const void* u; const float* x_in; float* x_out; void* x_out_b;
   float *save_mean, *save_hid, *save_y;
-  float* s_partial; void* du;
+  float* s_partial; void* du; float* du_colsum; int ca_chunks;
   // OP_ADD / OP_HEAD_WGRAD / OP_TAIL_BWD
   const float *a, *b; float* dst_f; void* dst_b; size_t n4;
   const void* tail_in; void* g_hr; float* thin_partial;
@@ -75,6 +75,9 @@ struct Net {
   std::vector<WgradReduceJob> wg_rjobs;   // .accumulate temporarily carries the weight's param index
   std::vector<ColsumJob> cs_jobs;
   std::vector<int> cs_bias_param;
+  std::vector<PartialSumJob> ps_jobs;
+  std::vector<int> ps_bias_param;
+  PartialSumJob* ps_jobs_dev = nullptr;
   WgradJob* wg_jobs_dev = nullptr;
   WgradReduceJob* wg_rjobs_dev = nullptr;
   ColsumJob* cs_jobs_dev = nullptr;
@@ -322,7 +325,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   std::vector<WgradReduceJob> wg_rjobs;
   std::vector<ColsumJob> cs_jobs;
   std::vector<int> cs_bias_param;
-  struct Site { int conv; const void* g; const void* x; int h, w; float alpha; };
+  std::vector<PartialSumJob> ps_jobs;
+  std::vector<int> ps_bias_param;
+  PartialSumJob* ps_jobs_dev = nullptr;
+  struct Site { int conv; const void* g; const void* x; int h, w; float alpha; const float* part; int part_count; };
   std::vector<Site> sites;
   WgradJob* jobs_dev = nullptr;
   WgradReduceJob* rjobs_dev = nullptr;
@@ -352,7 +358,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       d.y_bf16 = g_prev;
       if (s == 0) { GF_body = static_cast<float*>(bp.take(px * C * 4)); d.y_f32 = GF_body; GB_body = g_prev; }
       conv_op(bops, cw, d, true);
-      sites.push_back({n->conv_up0 + s, g_cur, up_in[s], hs, wsz, 1.f});
+      sites.push_back({n->conv_up0 + s, g_cur, up_in[s], hs, wsz, 1.f, nullptr, 0});
       g_cur = g_prev;
     }
     // ---- body tail conv
@@ -363,7 +369,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       ConvDesc d{};
       d.x = GB_body; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.y_f32 = P; d.y_bf16 = GB_cur;
       conv_op(bops, n->convs[n->conv_body], d, true);
-      sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f});
+      sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f, nullptr, 0});
     }
     if (n->arch == 0) {
       for (int g = n->n_groups - 1; g >= 0; --g) {
@@ -372,27 +378,33 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           ConvDesc d{};
           d.x = GB_cur; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.y_f32 = Q;
           conv_op(bops, n->convs[gr.conv_tail], d, true);
-          sites.push_back({gr.conv_tail, GB_cur, gr.tail_in_b, H, W, 1.f});
+          sites.push_back({gr.conv_tail, GB_cur, gr.tail_in_b, H, W, 1.f, nullptr, 0});
         }
         for (int b = n->n_blocks - 1; b >= 0; --b) {
           const BlockRec& br = gr.blocks[b];
           float* s_partial = static_cast<float*>(bp.take(size_t(N) * kCaBwdChunks * C * 4));
           void* du = bp.take(px * C * 2);
           void* dt = bp.take(px * C * 2);
+          const size_t vec = size_t(H) * W * (C / 4);
+          int ca_chunks = int((vec + 1023) / 1024);
+          { const int cap = (148 * 8 + N - 1) / N; if (ca_chunks > cap) ca_chunks = cap; if (ca_chunks < 1) ca_chunks = 1; }
+          float* du_cs = static_cast<float*>(bp.take(size_t(N) * ca_chunks * C * 4));
+          float* dt_pool = static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
           Op cb{};
           cb.type = OP_CA_BWD;
           cb.ca = n->cas[br.ca];
-          cb.a = Q; cb.u = br.u; cb.s_partial = s_partial; cb.du = du;
+          cb.a = Q; cb.u = br.u; cb.s_partial = s_partial; cb.du = du; cb.du_colsum = du_cs; cb.ca_chunks = ca_chunks;
           cb.save_mean = br.sv; cb.save_y = br.sv + size_t(N) * C; cb.save_hid = br.sv + size_t(N) * 2 * C;
           bops.push_back(cb);
           ConvDesc d2{};
           d2.x = du; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C; d2.alpha = 1.f;
+          d2.flags = kConvPool; d2.pool_partial = dt_pool;   // per-tile column sums of dt = conv1's bias gradient
           conv_op(bops, n->convs[br.conv2], d2, true);
           ConvDesc d1{};
           d1.x = dt; d1.residual = Q; d1.y_f32 = Q; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C; d1.Cout = C; d1.alpha = 1.f;
           conv_op(bops, n->convs[br.conv1], d1, true);
-          sites.push_back({br.conv2, du, br.t, H, W, 1.f});
-          sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f});
+          sites.push_back({br.conv2, du, br.t, H, W, 1.f, du_cs, N * ca_chunks});
+          sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * tiles * 2});
         }
         void* GB_new = bp.take(px * C * 2);
         Op add{};
@@ -410,13 +422,15 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         ConvDesc d2{};
         d2.x = GB_cur; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C;
         d2.alpha = n->res_scale;
+        float* dt_pool = static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
+        d2.flags = kConvPool; d2.pool_partial = dt_pool;
         conv_op(bops, n->convs[br.conv2], d2, true);
         ConvDesc d1{};
         d1.x = dt; d1.residual = P; d1.y_f32 = P; d1.y_bf16 = GB_new; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C;
         d1.Cout = C; d1.alpha = 1.f;
         conv_op(bops, n->convs[br.conv1], d1, true);
-        sites.push_back({br.conv2, GB_cur, br.t, H, W, n->res_scale});
-        sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f});
+        sites.push_back({br.conv2, GB_cur, br.t, H, W, n->res_scale, nullptr, 0});
+        sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * tiles * 2});
         GB_cur = GB_new;
       }
     }
@@ -434,11 +448,13 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       const int blocks = (cw.cout / 64) * (cw.cin / 64);
       njobs += size_t(blocks) * wgrad_splits(mt);
       nrjobs += blocks;
-      cs_floats += size_t(kColsumSlices) * cw.r * cw.cout;
+      if (!s.part) cs_floats += size_t(kColsumSlices) * cw.r * cw.cout;
     }
     jobs_dev = static_cast<WgradJob*>(bp.take(njobs * sizeof(WgradJob)));
     rjobs_dev = static_cast<WgradReduceJob*>(bp.take(nrjobs * sizeof(WgradReduceJob)));
     cs_dev = static_cast<ColsumJob*>(bp.take(sites.size() * sizeof(ColsumJob)));
+    PartialSumJob* ps_dev = static_cast<PartialSumJob*>(bp.take(sites.size() * sizeof(PartialSumJob)));
+    if (build) n->ps_jobs_dev = ps_dev;
     float* partials = static_cast<float*>(bp.take(njobs * 9 * 64 * 64 * sizeof(float)));
     float* cs_partials = static_cast<float*>(bp.take(cs_floats * sizeof(float)));
     float* pg_scratch = static_cast<float*>(bp.take(size_t(N) * (2 * C * Cr + C + Cr) * sizeof(float)));
@@ -477,12 +493,19 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
             wg_rjobs.push_back(rj);
           }
         }
-        ColsumJob cj{};
-        cj.g = static_cast<const __nv_bfloat16*>(s.g); cj.db = nullptr; cj.partial = cs_partials + cs_cursor;
-        cj.outer = N * s.h; cj.r = cw.r; cj.inner = s.w; cj.C = cout_sub; cj.alpha = s.alpha;
-        cs_cursor += size_t(kColsumSlices) * cw.r * cw.cout;
-        cs_jobs.push_back(cj);
-        cs_bias_param.push_back(cw.b_idx);
+        if (s.part) {
+          PartialSumJob pj{};
+          pj.partial = s.part; pj.db = nullptr; pj.count = s.part_count; pj.C = cw.cout; pj.alpha = s.alpha;
+          ps_jobs.push_back(pj);
+          ps_bias_param.push_back(cw.b_idx);
+        } else {
+          ColsumJob cj{};
+          cj.g = static_cast<const __nv_bfloat16*>(s.g); cj.db = nullptr; cj.partial = cs_partials + cs_cursor;
+          cj.outer = N * s.h; cj.r = cw.r; cj.inner = s.w; cj.C = cout_sub; cj.alpha = s.alpha;
+          cs_cursor += size_t(kColsumSlices) * cw.r * cw.cout;
+          cs_jobs.push_back(cj);
+          cs_bias_param.push_back(cw.b_idx);
+        }
       }
     }
   }
@@ -495,6 +518,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     n->wg_rjobs.swap(wg_rjobs);
     n->cs_jobs.swap(cs_jobs);
     n->cs_bias_param.swap(cs_bias_param);
+    n->ps_jobs.swap(ps_jobs);
+    n->ps_bias_param.swap(ps_bias_param);
     n->wg_jobs_dev = jobs_dev; n->wg_rjobs_dev = rjobs_dev; n->cs_jobs_dev = cs_dev;
     n->plan_grads.clear();
     n->jobs_uploaded = false;
@@ -556,7 +581,7 @@ int rumpy_net_num_launches_backward(void* net) {
   if (!net) return -1;
   Net* n = static_cast<Net*>(net);
   if (n->bops.empty()) return 0;
-  int c = 4;                                  // batched wgrad, its reduce, colsum, colsum reduce
+  int c = 5;                                  // batched wgrad, its reduce, colsum, colsum reduce, partial sums
   for (const Op& op : n->bops) {
     switch (op.type) {
       case OP_TAIL_BWD: c += 5; break;        // dgrad, wgrad, reduce, plane sums (2)
@@ -679,7 +704,10 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
                                      cudaMemcpyHostToDevice, stream);
     cudaError_t e3 = cudaMemcpyAsync(n->cs_jobs_dev, cj.data(), cj.size() * sizeof(ColsumJob), cudaMemcpyHostToDevice,
                                      stream);
-    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    std::vector<PartialSumJob> pj = n->ps_jobs;
+    for (size_t i = 0; i < pj.size(); ++i) pj[i].db = grads[n->ps_bias_param[i]];
+    cudaError_t e4 = pj.empty() ? cudaSuccess : cudaMemcpyAsync(n->ps_jobs_dev, pj.data(), pj.size() * sizeof(PartialSumJob), cudaMemcpyHostToDevice, stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
       return set_error(RUMPY_ERR_CUDA, "net_backward: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (n->pg_counter) cudaMemsetAsync(n->pg_counter, 0, 256, stream);
     cudaStreamSynchronize(stream);  // the temporaries above die at scope exit; happens once per plan
@@ -719,14 +747,12 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
           ca_bwd_reduce_kernel<false><<<g1, 256, (256 / (C / 4)) * C * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
         if (int e = check_launch("ca_bwd_reduce")) return e;
         const size_t vec = size_t(HW) * (C / 4);
-        int chunks = int((vec + 1023) / 1024);
-        const int cap = (sms * 8 + N - 1) / N;
-        if (chunks > cap) chunks = cap;
-        if (chunks < 1) chunks = 1;
+        (void)vec;
+        const int chunks = op.ca_chunks;
         ca_bwd_apply_kernel<<<dim3(chunks, N), 256, 0, stream>>>(
             op.a, op.s_partial, kCaBwdChunks, op.save_mean, op.save_hid, op.save_y, params[op.ca.w1], params[op.ca.w2],
             static_cast<__nv_bfloat16*>(op.du), grads[op.ca.w1], grads[op.ca.b1], grads[op.ca.w2], grads[op.ca.b2],
-            n->pg_scratch, n->pg_counter, N, HW, C, Cr);
+            n->pg_scratch, n->pg_counter, op.du_colsum, N, HW, C, Cr);
         if (int e = check_launch("ca_bwd_apply")) return e;
         break;
       }
@@ -752,10 +778,18 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
   if (int e = wgrad_launch(n->wg_jobs_dev, int(n->wg_jobs.size()), n->wg_rjobs_dev, int(n->wg_rjobs.size()), stream))
     return e;
   const int ncs = int(n->cs_jobs.size());
-  colsum_kernel<<<dim3(kColsumSlices, ncs), 768, 768 * sizeof(float), stream>>>(n->cs_jobs_dev);
-  if (int e = check_launch("colsum")) return e;
-  colsum_reduce_kernel<<<ncs, 256, 0, stream>>>(n->cs_jobs_dev);
-  return check_launch("colsum_reduce");
+  if (ncs > 0) {
+    colsum_kernel<<<dim3(kColsumSlices, ncs), 768, 768 * sizeof(float), stream>>>(n->cs_jobs_dev);
+    if (int e = check_launch("colsum")) return e;
+    colsum_reduce_kernel<<<ncs, 256, 0, stream>>>(n->cs_jobs_dev);
+    if (int e = check_launch("colsum_reduce")) return e;
+  }
+  if (!n->ps_jobs.empty()) {
+    const int block = (256 / C > 0 ? 256 / C : 1) * C;
+    partial_sum_kernel<<<int(n->ps_jobs.size()), block, block * sizeof(float), stream>>>(n->ps_jobs_dev);
+    if (int e = check_launch("partial_sum")) return e;
+  }
+  return RUMPY_OK;
 }
 
 // ------------------------------------------------------------------ loss / optimiser kernels
