@@ -297,17 +297,33 @@ __global__ void colsum_reduce_kernel(const ColsumJob* __restrict__ jobs) {
 //   du = G*y + dmean/HW  -> bf16 operand of conv2's dgrad / wgrad      (ca_bwd_apply_kernel)
 //   dW2 += dz2 (x) hid; db2 += dz2; dW1 += dh (x) mean; db1 += dh       (block (0,0), images in fixed order)
 // ------------------------------------------------------------------------------------------------
+// Scratch/argument block of the CALayer backward pair (one per plan; counters self-reset every launch).
+struct CaBwdArgs {
+  const float* G; const void* u;               // upstream gradient (fp32 NHWC), saved conv2 output
+  const float *save_mean, *save_hid, *save_y;  // forward CA vectors [N][C] / [N][Cr]
+  const float *w1, *w2;                        // FC weights [Cr][C], [C][Cr]
+  float *dw1, *db1, *dw2, *db2;                // parameter gradients (overwritten)
+  float* s_partial;                            // [N][chunks][C]
+  float* coef;                                 // [N][C]: dmean/HW, consumed by ca_bwd_apply_kernel
+  float* pg_scratch;                           // [N][2*C*Cr + C + Cr] per-image parameter-gradient terms
+  int* counters;                               // [N + 1] zero-initialised
+  int N, HW, C, Cr;
+};
+
 template <bool U_F32>
-__global__ void ca_bwd_reduce_kernel(const float* __restrict__ G, const void* __restrict__ u_,
-                                     float* __restrict__ s_partial, int HW, int C) {
+__global__ void ca_bwd_reduce_kernel(const CaBwdArgs a) {
   extern __shared__ float red[];   // [lanes][C]
-  const int n = blockIdx.y, chunks = gridDim.x;
+  __shared__ float dz2_s[256], dh_s[64];
+  __shared__ int last_s;
+  const int C = a.C, HW = a.HW, Cr = a.Cr;
+  const int n = blockIdx.y, chunks = gridDim.x, tid = threadIdx.x;
   const int vpp = C / 4;                      // float4 vectors per pixel
-  const int lanes = blockDim.x / vpp, c4 = (threadIdx.x % vpp) * 4, lane = threadIdx.x / vpp;
+  const int lanes = blockDim.x / vpp, c4 = (tid % vpp) * 4, lane = tid / vpp;
   const int p_begin = int((long long)HW * blockIdx.x / chunks), p_end = int((long long)HW * (blockIdx.x + 1) / chunks);
+  const float* G = a.G;
   auto ldu = [&](size_t o) -> float4 {
-    if (U_F32) return *reinterpret_cast<const float4*>(static_cast<const float*>(u_) + o);
-    const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(u_) + o);
+    if (U_F32) return *reinterpret_cast<const float4*>(static_cast<const float*>(a.u) + o);
+    const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(a.u) + o);
     return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xFFFF0000u),
                        __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xFFFF0000u));
   };
@@ -328,124 +344,101 @@ __global__ void ca_bwd_reduce_kernel(const float* __restrict__ G, const void* __
   float* r = red + lane * C + c4;
   r[0] = a0.x + a1.x; r[1] = a0.y + a1.y; r[2] = a0.z + a1.z; r[3] = a0.w + a1.w;
   __syncthreads();
-  if (threadIdx.x < C) {
+  if (tid < C) {
     float s = 0.f;
-    for (int l = 0; l < lanes; ++l) s += red[l * C + threadIdx.x];
-    s_partial[(size_t(n) * chunks + blockIdx.x) * C + threadIdx.x] = s;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + tid];
+    a.s_partial[(size_t(n) * chunks + blockIdx.x) * C + tid] = s;
   }
+  // ---- the last chunk-block of image n finishes the tiny FC backward once per image (not once per CTA of
+  // the apply kernel): s -> dz2 -> dh -> dmean/HW, plus this image's parameter-gradient terms
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = (atomicAdd(a.counters + n, 1) == chunks - 1);
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  if (tid < C) {
+    float s = 0.f;
+    for (int k = 0; k < chunks; ++k) s += a.s_partial[(size_t(n) * chunks + k) * C + tid];   // fixed order
+    const float y = a.save_y[n * C + tid];
+    dz2_s[tid] = s * y * (1.f - y);
+  }
+  __syncthreads();
+  {
+    const int warp = tid >> 5, wl = tid & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < Cr; j += nwarps) {
+      float v = 0.f;
+      for (int c = wl; c < C; c += 32) v = fmaf(a.w2[c * Cr + j], dz2_s[c], v);
+      v = warp_sum(v);
+      if (wl == 0) dh_s[j] = a.save_hid[n * Cr + j] > 0.f ? v : 0.f;
+    }
+  }
+  __syncthreads();
+  const int per = 2 * C * Cr + C + Cr;
+  float* mine = a.pg_scratch + size_t(n) * per;
+  if (tid < C) {
+    float v = 0.f;
+    for (int j = 0; j < Cr; ++j) v = fmaf(a.w1[j * C + tid], dh_s[j], v);
+    a.coef[n * C + tid] = v / float(HW);
+    const float dz = dz2_s[tid], mean = a.save_mean[n * C + tid];
+    for (int j = 0; j < Cr; ++j) {
+      mine[tid * Cr + j] = dz * a.save_hid[n * Cr + j];            // dW2[c][j]
+      mine[C * Cr + j * C + tid] = dh_s[j] * mean;                 // dW1[j][c]
+    }
+    mine[2 * C * Cr + tid] = dz;                                   // db2[c]
+  }
+  if (tid < Cr) mine[2 * C * Cr + C + tid] = dh_s[tid];            // db1[j]
+  a.counters[n] = 0;                                               // re-arm (all chunk blocks of n have arrived)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = (atomicAdd(a.counters + a.N, 1) == a.N - 1);
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
+  for (int i = tid; i < per; i += blockDim.x) {      // parameter gradients: images summed in index order
+    float s = 0.f;
+    for (int img = 0; img < a.N; ++img) s += a.pg_scratch[size_t(img) * per + i];
+    if (i < C * Cr) a.dw2[i] = s;
+    else if (i < 2 * C * Cr) a.dw1[i - C * Cr] = s;
+    else if (i < 2 * C * Cr + C) a.db2[i - 2 * C * Cr] = s;
+    else a.db1[i - 2 * C * Cr - C] = s;
+  }
+  if (tid == 0) a.counters[a.N] = 0;
 }
 
-__global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ s_partial, int s_chunks,
-                                    const float* __restrict__ save_mean, const float* __restrict__ save_hid,
-                                    const float* __restrict__ save_y, const float* __restrict__ w1,
-                                    const float* __restrict__ w2, __nv_bfloat16* __restrict__ du,
-                                    float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
-                                    float* __restrict__ db2, float* __restrict__ pg_scratch,
-                                    int* __restrict__ pg_counter, float* __restrict__ du_colsum /* [N][gridDim.x][C] */,
-                                    int N, int HW, int C, int Cr) {
-  __shared__ float y_s[256], coef_s[256], dz2_s[256], dh_s[64], red_s[256];
-  const int tid = threadIdx.x;
-  const int n = blockIdx.y;
-  auto per_image = [&](int img) {   // fills y_s, dz2_s, dh_s, coef_s for image `img`
-    {
-      // s[c] = sum of the reduce kernel's chunk partials: thread groups split the list (independent loads in
-      // flight instead of a serial chain of L2 round trips), fixed order
-      const int groups = blockDim.x / C, g = tid / C, c = tid % C;
-      float a0 = 0.f, a1 = 0.f;
-      if (g < groups) {
-        const float* pp = s_partial + size_t(img) * s_chunks * C + c;
-        int k = g;
-        for (; k + groups < s_chunks; k += 2 * groups) { a0 += pp[size_t(k) * C]; a1 += pp[size_t(k + groups) * C]; }
-        if (k < s_chunks) a0 += pp[size_t(k) * C];
-      }
-      red_s[tid] = a0 + a1;
-    }
-    __syncthreads();
-    if (tid < C) {
-      const int groups = blockDim.x / C;
-      float s = 0.f;
-      for (int g = 0; g < groups; ++g) s += red_s[g * C + tid];
-      const float y = save_y[img * C + tid];
-      y_s[tid] = y;
-      dz2_s[tid] = s * y * (1.f - y);
-    }
-    __syncthreads();
-    {
-      const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-      for (int j = warp; j < Cr; j += nwarps) {
-        float a = 0.f;
-        for (int c = lane; c < C; c += 32) a = fmaf(w2[c * Cr + j], dz2_s[c], a);
-        a = warp_sum(a);
-        if (lane == 0) dh_s[j] = save_hid[img * Cr + j] > 0.f ? a : 0.f;
-      }
-    }
-    __syncthreads();
-    if (tid < C) {
-      float a = 0.f;
-      for (int j = 0; j < Cr; ++j) a = fmaf(w1[j * C + tid], dh_s[j], a);
-      coef_s[tid] = a / float(HW);
-    }
-    __syncthreads();
-  };
-  per_image(n);
-  if (blockIdx.x == 0) {
-    // parameter gradients: block (0, n) writes image n's contribution; the LAST of the N blocks to finish sums
-    // all images in index order (deterministic) -- no serial chain through one CTA, no extra launch.
-    float* mine = pg_scratch + size_t(n) * (2 * C * Cr + C + Cr);
-    if (tid < C) {
-      const float dz = dz2_s[tid], mean = save_mean[n * C + tid];
-      for (int j = 0; j < Cr; ++j) {
-        mine[tid * Cr + j] = dz * save_hid[n * Cr + j];            // dW2[c][j]
-        mine[C * Cr + j * C + tid] = dh_s[j] * mean;               // dW1[j][c]
-      }
-      mine[2 * C * Cr + tid] = dz;                                 // db2[c]
-    }
-    if (tid < Cr) mine[2 * C * Cr + C + tid] = dh_s[tid];          // db1[j]
-    __threadfence();
-    __syncthreads();
-    __shared__ int last_s;
-    if (tid == 0) last_s = (atomicAdd(pg_counter, 1) == N - 1);
-    __syncthreads();
-    if (last_s) {
-      __threadfence();
-      const int per = 2 * C * Cr + C + Cr;
-      for (int i = tid; i < per; i += blockDim.x) {
-        float s = 0.f;
-        for (int img = 0; img < N; ++img) s += pg_scratch[size_t(img) * per + i];
-        if (i < C * Cr) dw2[i] = s;
-        else if (i < 2 * C * Cr) dw1[i - C * Cr] = s;
-        else if (i < 2 * C * Cr + C) db2[i - 2 * C * Cr] = s;
-        else db1[i - 2 * C * Cr - C] = s;
-      }
-      if (tid == 0) *pg_counter = 0;   // re-arm for the next launch
-    }
-  }
+// du = G*y + coef  -> bf16 operand of conv2's dgrad / wgrad; pure streaming (y / coef come from the reduce
+// kernel's per-image epilogue).  Also emits per-block column sums of du (conv2's bias gradient).
+__global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ save_y,
+                                    const float* __restrict__ coef, __nv_bfloat16* __restrict__ du,
+                                    float* __restrict__ du_colsum /* [N][gridDim.x][C] */, int HW, int C) {
+  const int tid = threadIdx.x, n = blockIdx.y;
   const int vec_per_pix = C / 4;
   const size_t total = size_t(HW) * vec_per_pix;
   const size_t base = size_t(n) * HW * C;
-  // every thread keeps the same 4 channels across iterations (the stride is a multiple of C/4), so the bias
-  // gradient of conv2 (column sums of du) accumulates in registers and leaves as one partial row per block
-  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;     // multiple of C/4: each thread keeps its 4 channels
+  const size_t i0 = blockIdx.x * size_t(blockDim.x) + tid;
+  const int c4 = int(i0 % vec_per_pix) * 4;
+  const float4 y4 = *reinterpret_cast<const float4*>(save_y + n * C + c4);
+  const float4 k4 = *reinterpret_cast<const float4*>(coef + n * C + c4);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   auto emit = [&](size_t i, const float4& g) {
-    const int c4 = int(i % vec_per_pix) * 4;
-    const float a = fmaf(g.x, y_s[c4], coef_s[c4]), b = fmaf(g.y, y_s[c4 + 1], coef_s[c4 + 1]);
-    const float c = fmaf(g.z, y_s[c4 + 2], coef_s[c4 + 2]), d = fmaf(g.w, y_s[c4 + 3], coef_s[c4 + 3]);
+    const float a = fmaf(g.x, y4.x, k4.x), b = fmaf(g.y, y4.y, k4.y);
+    const float c = fmaf(g.z, y4.z, k4.z), d = fmaf(g.w, y4.w, k4.w);
     cs.x += a; cs.y += b; cs.z += c; cs.w += d;
     __nv_bfloat162 p0 = __floats2bfloat162_rn(a, b), p1 = __floats2bfloat162_rn(c, d);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(du + base + i * 4) = pk;
   };
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += 2 * stride) {
-    const size_t i1 = i + stride;
-    const bool has1 = i1 < total;
+  size_t i = i0;
+  for (; i + 3 * stride < total; i += 4 * stride) {        // four independent 16-byte loads in flight
     const float4 g0 = *reinterpret_cast<const float4*>(G + base + i * 4);
-    float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has1) g1 = *reinterpret_cast<const float4*>(G + base + i1 * 4);
-    emit(i, g0);
-    if (has1) emit(i1, g1);
+    const float4 g1 = *reinterpret_cast<const float4*>(G + base + (i + stride) * 4);
+    const float4 g2 = *reinterpret_cast<const float4*>(G + base + (i + 2 * stride) * 4);
+    const float4 g3 = *reinterpret_cast<const float4*>(G + base + (i + 3 * stride) * 4);
+    emit(i, g0); emit(i + stride, g1); emit(i + 2 * stride, g2); emit(i + 3 * stride, g3);
   }
+  for (; i < total; i += stride) emit(i, *reinterpret_cast<const float4*>(G + base + i * 4));
   if (du_colsum != nullptr) {
     __shared__ float4 cs_s[256];
     cs_s[tid] = cs;

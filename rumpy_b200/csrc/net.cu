@@ -84,6 +84,7 @@ struct Net {
   bool jobs_uploaded = false;
   float* pg_scratch = nullptr;
   int* pg_counter = nullptr;
+  float* ca_coef = nullptr;
   // batched weight packing
   size_t pack_jobs_bytes = 0;
   std::vector<PackJobHost> pack_jobs;
@@ -386,8 +387,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           void* du = bp.take(px * C * 2);
           void* dt = bp.take(px * C * 2);
           const size_t vec = size_t(H) * W * (C / 4);
-          int ca_chunks = int((vec + 1023) / 1024);
-          { const int cap = (148 * 8 + N - 1) / N; if (ca_chunks > cap) ca_chunks = cap; if (ca_chunks < 1) ca_chunks = 1; }
+          int ca_chunks = int((vec + 4095) / 4096);     // >= 16 vectors per thread: pure streaming kernel
+          { const int cap = (148 * 4 + N - 1) / N; if (ca_chunks > cap) ca_chunks = cap; if (ca_chunks < 1) ca_chunks = 1; }
           float* du_cs = static_cast<float*>(bp.take(size_t(N) * ca_chunks * C * 4));
           float* dt_pool = static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
           Op cb{};
@@ -458,8 +459,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     float* partials = static_cast<float*>(bp.take(njobs * 9 * 64 * 64 * sizeof(float)));
     float* cs_partials = static_cast<float*>(bp.take(cs_floats * sizeof(float)));
     float* pg_scratch = static_cast<float*>(bp.take(size_t(N) * (2 * C * Cr + C + Cr) * sizeof(float)));
-    int* pg_counter = static_cast<int*>(bp.take(256));
-    if (build) { n->pg_scratch = pg_scratch; n->pg_counter = pg_counter; }
+    int* pg_counter = static_cast<int*>(bp.take(size_t(N + 1) * sizeof(int)));
+    float* ca_coef = static_cast<float*>(bp.take(size_t(N) * C * sizeof(float)));
+    if (build) { n->pg_scratch = pg_scratch; n->pg_counter = pg_counter; n->ca_coef = ca_coef; }
     if (build) {
       size_t job_cursor = 0, cs_cursor = 0;
       for (const Site& s : sites) {
@@ -709,7 +711,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
     cudaError_t e4 = pj.empty() ? cudaSuccess : cudaMemcpyAsync(n->ps_jobs_dev, pj.data(), pj.size() * sizeof(PartialSumJob), cudaMemcpyHostToDevice, stream);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
       return set_error(RUMPY_ERR_CUDA, "net_backward: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (n->pg_counter) cudaMemsetAsync(n->pg_counter, 0, 256, stream);
+    if (n->pg_counter) cudaMemsetAsync(n->pg_counter, 0, size_t(N + 1) * sizeof(int), stream);
     cudaStreamSynchronize(stream);  // the temporaries above die at scope exit; happens once per plan
     n->jobs_uploaded = true;
   }
@@ -740,19 +742,19 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         break;
       case OP_CA_BWD: {
         const int HW = H * W;
+        CaBwdArgs a{};
+        a.G = op.a; a.u = op.u; a.save_mean = op.save_mean; a.save_hid = op.save_hid; a.save_y = op.save_y;
+        a.w1 = params[op.ca.w1]; a.w2 = params[op.ca.w2];
+        a.dw1 = grads[op.ca.w1]; a.db1 = grads[op.ca.b1]; a.dw2 = grads[op.ca.w2]; a.db2 = grads[op.ca.b2];
+        a.s_partial = op.s_partial; a.coef = n->ca_coef; a.pg_scratch = n->pg_scratch; a.counters = n->pg_counter;
+        a.N = N; a.HW = HW; a.C = C; a.Cr = Cr;
         dim3 g1(kCaBwdChunks, N);
-        if (n->u_f32)
-          ca_bwd_reduce_kernel<true><<<g1, 256, (256 / (C / 4)) * C * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
-        else
-          ca_bwd_reduce_kernel<false><<<g1, 256, (256 / (C / 4)) * C * sizeof(float), stream>>>(op.a, op.u, op.s_partial, HW, C);
+        const size_t smem = size_t(256 / (C / 4)) * C * sizeof(float);
+        if (n->u_f32) ca_bwd_reduce_kernel<true><<<g1, 256, smem, stream>>>(a);
+        else ca_bwd_reduce_kernel<false><<<g1, 256, smem, stream>>>(a);
         if (int e = check_launch("ca_bwd_reduce")) return e;
-        const size_t vec = size_t(HW) * (C / 4);
-        (void)vec;
-        const int chunks = op.ca_chunks;
-        ca_bwd_apply_kernel<<<dim3(chunks, N), 256, 0, stream>>>(
-            op.a, op.s_partial, kCaBwdChunks, op.save_mean, op.save_hid, op.save_y, params[op.ca.w1], params[op.ca.w2],
-            static_cast<__nv_bfloat16*>(op.du), grads[op.ca.w1], grads[op.ca.b1], grads[op.ca.w2], grads[op.ca.b2],
-            n->pg_scratch, n->pg_counter, op.du_colsum, N, HW, C, Cr);
+        ca_bwd_apply_kernel<<<dim3(op.ca_chunks, N), 256, 0, stream>>>(
+            op.a, op.save_y, n->ca_coef, static_cast<__nv_bfloat16*>(op.du), op.du_colsum, HW, C);
         if (int e = check_launch("ca_bwd_apply")) return e;
         break;
       }
