@@ -153,14 +153,25 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   if (rout > 1 && (flags & (kConvOutF32 | kConvResF32 | kConvMask | kConvPool)))
     return set_error(RUMPY_ERR_ARG, "conv3x3: shuffle store supports bf16 output only");
   a.flags = flags;
-  // pipeline depth from the 227 KB budget
+  // pipeline depth / staging slots from the 227 KB budget: two staging slots when >= 4 stages still fit
   const size_t budget = kConvSmemBudget;
-  int stages = kMaxStages;
-  while (stages > 2 && conv_smem_bytes(bn, resident, cin_chunks, stages, flags) > budget) --stages;
-  if (conv_smem_bytes(bn, resident, cin_chunks, stages, flags) > budget)
+  const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
+  int bufs = 2, stages = kMaxStages;
+  auto fit = [&](int b) {
+    int st = kMaxStages;
+    while (st > 2 && conv_smem_bytes(bn, resident, cin_chunks, st, flags, b) > budget) --st;
+    return st;
+  };
+  stages = fit(2);
+  if (conv_smem_bytes(bn, resident, cin_chunks, stages, flags, 2) > budget || (has_in && stages < 4)) {
+    bufs = has_in ? 1 : 2;
+    stages = fit(bufs);
+  }
+  if (conv_smem_bytes(bn, resident, cin_chunks, stages, flags, bufs) > budget)
     return set_error(RUMPY_ERR_ARG, "conv3x3: configuration does not fit shared memory");
   a.stages = stages;
-  p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages, flags);
+  a.stg_bufs = bufs;
+  p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages, flags, bufs);
   int grid = sms < a.m_tiles * a.n_tiles ? sms : a.m_tiles * a.n_tiles;
   grid -= grid % a.n_tiles;
   if (grid < a.n_tiles) grid = a.n_tiles;

@@ -50,6 +50,7 @@ struct ConvArgs {
   int o_chunks_per_map;  // 64-channel output chunks served by each bf16 output map
   int cout;              // total output channels (packed-row order)
   int stages;            // smem pipeline depth
+  int stg_bufs;          // epilogue staging slots (1 or 2)
   float alpha;           // scale on (acc + bias) (res_scale / gradient scale)
   const float* bias;     // [cout] in packed-row order, or nullptr
   float* pool_partial;   // [m_tiles][2][cout]
@@ -72,17 +73,19 @@ constexpr size_t kConvSmemBudget = 227 * 1024 - 3072;
 __host__ __device__ constexpr int conv_b_block_bytes(int bn) { return bn * 128; }
 
 // Epilogue staging: fp32 tile (32 KB) if any fp32 input/output, bf16 tile (16 KB) if any bf16 input/output;
-// double buffered unless the epilogue has TMA inputs (residual / mask), which are consumed in place.
+// double buffered (args.stg_bufs = 2) whenever shared memory allows: with TMA inputs (residual / mask) the second
+// slot lets the next tile's inputs be prefetched while the current tile is processed in place.
 __host__ __device__ inline int conv_stg_buf_bytes(uint32_t flags) {
   return ((flags & (kConvOutF32 | kConvResF32)) ? kStgF32Bytes : 0) +
          ((flags & (kConvOutBf16 | kConvMask)) ? kStgBf16Bytes : 0);
 }
-__host__ __device__ inline int conv_stg_bufs(uint32_t flags) { return (flags & (kConvResF32 | kConvMask)) ? 1 : 2; }
+
 
 // Dynamic smem: [staging | resident B (optional) | stages x (A box [+ 3 B taps])], 1024-byte aligned.
-__host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, int stages, uint32_t flags) {
+__host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, int stages, uint32_t flags,
+                                       int stg_bufs) {
   size_t s = 1024;
-  if (bn != 16) s += size_t(conv_stg_bufs(flags)) * conv_stg_buf_bytes(flags);
+  if (bn != 16) s += size_t(stg_bufs) * conv_stg_buf_bytes(flags);
   if (resident_b) s += size_t(9) * cin_chunks * conv_b_block_bytes(bn);
   s += size_t(stages) * (kAStageBytes + (resident_b ? 0 : 3 * conv_b_block_bytes(bn)));
   return s;
@@ -117,7 +120,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t b_bar;
-  __shared__ __align__(8) uint64_t in_bar;
+  __shared__ __align__(8) uint64_t in_bar[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float bias_s[BN];
 
@@ -131,7 +134,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stg_buf_bytes = (BN == 16) ? 0 : conv_stg_buf_bytes(flags);
-  const int stg_bufs = conv_stg_bufs(flags);
+  const int stg_bufs = args.stg_bufs;
   uint8_t* b_res = smem + stg_bufs * stg_buf_bytes;
   uint8_t* stage0 = b_res + (RESIDENT_B ? 9 * cin_chunks * kBBlock : 0);
 
@@ -149,7 +152,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       mbar_init(&tmem_empty_bar[i], 128);
     }
     mbar_init(&b_bar, 1);
-    mbar_init(&in_bar, 1);
+    mbar_init(&in_bar[0], 1);
+    mbar_init(&in_bar[1], 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -282,8 +286,30 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
       const bool use_f32 = (flags & (kConvOutF32 | kConvResF32)) != 0;
       const uint32_t swz = uint32_t(row & 7);
-      uint32_t in_phase = 0;
-      int cc = 0;  // running chunk counter -> staging buffer parity
+      int cc = 0;  // running chunk counter -> staging slot
+      const int my_tiles = (mt_first < args.m_tiles) ? (args.m_tiles - 1 - mt_first) / mt_stride + 1 : 0;
+      const int total_chunks = my_tiles * kChunksPerTile;
+      // TMA the residual / mask tiles of chunk `cidx` into its staging slot (consumed in place by the epilogue)
+      auto issue_inputs = [&](int cidx) {
+        const int t_mt = mt_first + (cidx / kChunksPerTile) * mt_stride;
+        const int t_oc = n_tile * kChunksPerTile + (cidx % kChunksPerTile);
+        const int t_n = t_mt / tiles_per_img;
+        const int t_rem = t_mt - t_n * tiles_per_img;
+        const int t_y0 = (t_rem / args.tiles_x) * kTileH, t_x0 = (t_rem % args.tiles_x) * kTileW;
+        const int slot = (stg_bufs == 2) ? (cidx & 1) : 0;
+        uint8_t* sf = smem + slot * stg_buf_bytes;
+        uint8_t* sb = sf + (use_f32 ? kStgF32Bytes : 0);
+        uint32_t bytes = 0;
+        if (flags & kConvResF32) bytes += kStgF32Bytes;
+        if (flags & kConvMask) bytes += kStgBf16Bytes;
+        mbar_expect_tx(&in_bar[slot], bytes);
+        if (flags & kConvResF32) {
+          tma_load_4d(sf, &maps.rf, &in_bar[slot], t_oc * 64, t_x0, t_y0, t_n);
+          tma_load_4d(sf + kABytes, &maps.rf, &in_bar[slot], t_oc * 64 + 32, t_x0, t_y0, t_n);
+        }
+        if (flags & kConvMask) tma_load_4d(sb, &maps.mb, &in_bar[slot], t_oc * 64, t_x0, t_y0, t_n);
+      };
+      if (has_in && stg_bufs == 2 && et == 0 && total_chunks > 0) issue_inputs(0);
       for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
         const int n = mt / tiles_per_img;
         const int rem = mt - n * tiles_per_img;
@@ -294,26 +320,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
         const uint32_t acc_phase = (it >> 1) & 1;
         for (int j = 0; j < kChunksPerTile; ++j, ++cc) {
           const int oc = n_tile * kChunksPerTile + j;  // 64-channel output chunk index
-          uint8_t* stg = smem + ((stg_bufs == 2) ? (cc & 1) * stg_buf_bytes : 0);
+          const int slot = (stg_bufs == 2) ? (cc & 1) : 0;
+          uint8_t* stg = smem + slot * stg_buf_bytes;
           uint8_t* stg_f32 = stg;
           uint8_t* stg_bf16 = stg + (use_f32 ? kStgF32Bytes : 0);
           uint8_t* my_f32 = stg_f32 + row * 128;
           uint8_t* my_bf16 = stg_bf16 + row * 128;
-          if (has_in) {
-            // single staging buffer consumed in place: wait until earlier stores have read it, then TMA the
-            // residual / mask tiles of this chunk into it
-            if (et == 0) {
-              tma_store_wait_read0();
-              uint32_t bytes = 0;
-              if (flags & kConvResF32) bytes += kStgF32Bytes;
-              if (flags & kConvMask) bytes += kStgBf16Bytes;
-              mbar_expect_tx(&in_bar, bytes);
-              if (flags & kConvResF32) {
-                tma_load_4d(stg_f32, &maps.rf, &in_bar, oc * 64, x0, y0, n);
-                tma_load_4d(stg_f32 + kABytes, &maps.rf, &in_bar, oc * 64 + 32, x0, y0, n);
-              }
-              if (flags & kConvMask) tma_load_4d(stg_bf16, &maps.mb, &in_bar, oc * 64, x0, y0, n);
-            }
+          if (has_in && stg_bufs == 1 && et == 0) {
+            // single slot: wait until the previous chunk's stores have read it, then fetch this chunk's inputs
+            tma_store_wait_read0();
+            issue_inputs(cc);
           }
           if (j == 0) {
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -331,10 +347,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
           }
-          if (has_in) {
-            mbar_wait(&in_bar, in_phase);
-            in_phase ^= 1;
-          }
+          if (has_in) mbar_wait(&in_bar[slot], uint32_t(cc / stg_bufs) & 1u);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float f[32];
@@ -400,6 +413,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
               tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
             }
             tma_store_commit();
+            if (has_in && stg_bufs == 2 && cc + 1 < total_chunks) {
+              // prefetch the next chunk's inputs into the other slot once its previous store (chunk cc-1) has
+              // been read out; the store just committed (this chunk) may stay in flight
+              tma_store_wait_read1();
+              issue_inputs(cc + 1);
+            }
           }
           if (flags & kConvPool) {
             // channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves
@@ -421,7 +440,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
               }
             }
             args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = s;
-            if (has_in) named_bar_sync(3, 128);  // single buffer: readers must finish before the next input TMA
+            if (has_in && stg_bufs == 1) named_bar_sync(3, 128);  // single slot: readers finish before the next input TMA
           }
         }
       }
