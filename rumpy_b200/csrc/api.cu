@@ -323,7 +323,10 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
   if (save_y && (!save_mean || !save_hid)) return set_error(RUMPY_ERR_ARG, "ca_apply: save_* must come together");
   const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
   const size_t vec = size_t(H) * W * (C / 4);
-  int chunks = int((vec + 256 * 4 - 1) / (256 * 4));          // ~4 vectors per thread
+  // 4 vectors per thread (all in flight) for small images, 8 once an image is >= 64K vectors: the per-CTA FC
+  // prologue is amortised over more streaming work
+  const int per_thread = vec >= 60000 ? 8 : 4;
+  int chunks = int((vec + 256 * per_thread - 1) / (256 * per_thread));
   const int cap = (sms * 8 + N - 1) / N;
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;

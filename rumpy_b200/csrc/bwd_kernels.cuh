@@ -126,58 +126,75 @@ template <bool WIDE_BF16>
 __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __restrict__ wide_,
                                   const float* __restrict__ wide2 /* optional second fp32 wide tensor, added */,
                                   float* __restrict__ partial, int N, int H, int W, int C, int M, int sign) {
+  // One (lane, row) walks along x with a sliding 3-column window of the thin tensor in registers: per pixel one
+  // coalesced wide load, 3*M broadcast thin loads (instead of 9*M) and 9*M FMAs; no div/mod in the loop.
   extern __shared__ float red[];  // [lanes][M*9+1][C] reduce buffer
   const int lanes = blockDim.x / C;
   const int c = threadIdx.x % C, lane = threadIdx.x / C;
   float acc[37];
 #pragma unroll
   for (int i = 0; i < 37; ++i) acc[i] = 0.f;
-  const size_t npix = size_t(N) * H * W;
-  const size_t per_block = (npix + gridDim.x - 1) / gridDim.x;
-  const size_t p_begin = blockIdx.x * per_block;
-  const size_t p_end = (p_begin + per_block < npix) ? p_begin + per_block : npix;
-  auto load_wide = [&](size_t pix) -> float {
-    if (pix >= p_end) return 0.f;
-    if (WIDE_BF16) return __bfloat162float(static_cast<const __nv_bfloat16*>(wide_)[pix * C + c]);
-    float v = static_cast<const float*>(wide_)[pix * C + c];
-    if (wide2) v += wide2[pix * C + c];
-    return v;
-  };
-  for (size_t pix0 = p_begin + lane; pix0 < p_end; pix0 += size_t(lanes) * 4) {
-    float vv[4];
+  const int rows_total = N * H;
+  for (int rowi = blockIdx.x * lanes + lane; rowi < rows_total && lane < lanes; rowi += gridDim.x * lanes) {
+    const int n = rowi / H, yh = rowi - n * H;
+    const float* rp[4][3];   // thin rows for (m, ky): row yh + sign*(ky-1), nullptr when outside the image
 #pragma unroll
-    for (int u = 0; u < 4; ++u) vv[u] = load_wide(pix0 + size_t(u) * lanes);
+    for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const size_t pix = pix0 + size_t(u) * lanes;
-      if (pix >= p_end) break;
-      const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
-      const float v = vv[u];
+      for (int ky = 0; ky < 3; ++ky) {
+        const int yy = yh + sign * (ky - 1);
+        rp[m][ky] = (m < M && yy >= 0 && yy < H) ? thin + ((size_t(n) * M + m) * H + yy) * W : nullptr;
+      }
+    float win[4][3][3];      // [m][ky][column offset -1, 0, +1]
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        win[m][ky][0] = 0.f;                                           // column -1 is outside
+        win[m][ky][1] = rp[m][ky] ? __ldg(rp[m][ky]) : 0.f;            // column 0
+        win[m][ky][2] = (rp[m][ky] && W > 1) ? __ldg(rp[m][ky] + 1) : 0.f;
+      }
+    const size_t wbase = (size_t(n) * H + yh) * W;
+    for (int xw = 0; xw < W; ++xw) {
+      float v;
+      if (WIDE_BF16) v = __bfloat162float(static_cast<const __nv_bfloat16*>(wide_)[(wbase + xw) * C + c]);
+      else {
+        v = static_cast<const float*>(wide_)[(wbase + xw) * C + c];
+        if (wide2) v += wide2[(wbase + xw) * C + c];
+      }
       acc[36] += v;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
+      for (int m = 0; m < 4; ++m)
         if (m < M) {
-          const float* tp = thin + (size_t(n) * M + m) * H * W;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {  // thin column xw + sign*(kx-1)  ->  window slot 1 + sign*(kx-1)
+              const float tv = (sign > 0) ? win[m][ky][kx] : win[m][ky][2 - kx];
+              acc[m * 9 + ky * 3 + kx] = fmaf(tv, v, acc[m * 9 + ky * 3 + kx]);
+            }
+        }
+      // slide the window one column to the right
+      const bool more = xw + 2 < W;
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+        if (m < M) {
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const int yy = yh + sign * (ky - 1);
-            if (yy < 0 || yy >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const int xx = xw + sign * (kx - 1);
-              if (xx < 0 || xx >= W) continue;
-              acc[m * 9 + ky * 3 + kx] = fmaf(__ldg(tp + size_t(yy) * W + xx), v, acc[m * 9 + ky * 3 + kx]);
-            }
+            win[m][ky][0] = win[m][ky][1];
+            win[m][ky][1] = win[m][ky][2];
+            win[m][ky][2] = (more && rp[m][ky]) ? __ldg(rp[m][ky] + xw + 2) : 0.f;
           }
         }
-      }
     }
   }
   const int rows = M * 9 + 1;
+  if (lane < lanes) {
 #pragma unroll
-  for (int i = 0; i < 36; ++i)
-    if (i < M * 9) red[(lane * rows + i) * C + c] = acc[i];
-  red[(lane * rows + M * 9) * C + c] = acc[36];
+    for (int i = 0; i < 36; ++i)
+      if (i < M * 9) red[(lane * rows + i) * C + c] = acc[i];
+    red[(lane * rows + M * 9) * C + c] = acc[36];
+  }
   __syncthreads();
   for (int i = threadIdx.x; i < rows * C; i += blockDim.x) {
     float s = 0.f;
@@ -357,11 +374,29 @@ __global__ void ca_bwd_reduce_kernel(const CaBwdArgs a) {
   __syncthreads();
   if (!last_s) return;
   __threadfence();
-  if (tid < C) {
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += a.s_partial[(size_t(n) * chunks + k) * C + tid];   // fixed order
-    const float y = a.save_y[n * C + tid];
-    dz2_s[tid] = s * y * (1.f - y);
+  {
+    // s[c] over the chunk partials: thread groups take interleaved chunks, 4 independent loads in flight each
+    // (a serial 32-deep chain of L2 round trips cost ~5 us here), combined in a fixed order
+    const int groups = blockDim.x / C, g = tid / C, c = tid % C;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (g < groups) {
+      const float* pp = a.s_partial + size_t(n) * chunks * C + c;
+      int k = g;
+      for (; k + 3 * groups < chunks; k += 4 * groups) {
+        s0 += pp[size_t(k) * C]; s1 += pp[size_t(k + groups) * C];
+        s2 += pp[size_t(k + 2 * groups) * C]; s3 += pp[size_t(k + 3 * groups) * C];
+      }
+      for (; k < chunks; k += groups) s0 += pp[size_t(k) * C];
+    }
+    __syncthreads();                 // `red` is being reused
+    red[tid] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < C) {
+      float s = 0.f;
+      for (int k = 0; k < groups; ++k) s += red[k * C + tid];
+      const float y = a.save_y[n * C + tid];
+      dz2_s[tid] = s * y * (1.f - y);
+    }
   }
   __syncthreads();
   {

@@ -238,18 +238,20 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
     pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(x_out_b + off) = pk;
   };
-  // two vectors (4 independent 16-byte loads) in flight per thread
+  // four vectors (8 independent 16-byte loads) in flight per thread
   const size_t stride = size_t(gridDim.x) * blockDim.x;
-  for (size_t i = blockIdx.x * size_t(blockDim.x) + tid; i < total; i += 2 * stride) {
-    const size_t i1 = i + stride;
-    const bool has1 = i1 < total;
-    const float4 u0 = load_u(base + i * 4);
+  size_t i = blockIdx.x * size_t(blockDim.x) + tid;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    const float4 u0 = load_u(base + i * 4), u1 = load_u(base + (i + stride) * 4);
+    const float4 u2 = load_u(base + (i + 2 * stride) * 4), u3 = load_u(base + (i + 3 * stride) * 4);
     const float4 x0 = *reinterpret_cast<const float4*>(x_in + base + i * 4);
-    float4 u1 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = u1;
-    if (has1) { u1 = load_u(base + i1 * 4); x1 = *reinterpret_cast<const float4*>(x_in + base + i1 * 4); }
-    emit(i, u0, x0);
-    if (has1) emit(i1, u1, x1);
+    const float4 x1 = *reinterpret_cast<const float4*>(x_in + base + (i + stride) * 4);
+    const float4 x2 = *reinterpret_cast<const float4*>(x_in + base + (i + 2 * stride) * 4);
+    const float4 x3 = *reinterpret_cast<const float4*>(x_in + base + (i + 3 * stride) * 4);
+    emit(i, u0, x0); emit(i + stride, u1, x1); emit(i + 2 * stride, u2, x2); emit(i + 3 * stride, u3, x3);
   }
+  for (; i < total; i += stride)
+    emit(i, load_u(base + i * 4), *reinterpret_cast<const float4*>(x_in + base + i * 4));
 }
 
 // ------------------------------------------------------------------------------------------------
