@@ -311,17 +311,30 @@ int rumpy_head_conv(const float* x, const float* w, const float* bias, float* yf
   return check_launch("head_conv");
 }
 
-int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const float* x_in, const float* w1,
-                   const float* b1, const float* w2, const float* b2, float* x_out, void* x_out_bf16,
-                   float* save_mean, float* save_hid, float* save_y, int N, int H, int W, int C, int Cr,
-                   void* stream) {
+}  // extern "C"
+
+namespace rb {
+// pool_partial: [N][partials_per_img][C].  compact_scratch (N*64*C floats, may be NULL): when an image has more
+// than 256 partial rows they are first compacted to 64 rows per image.
+int ca_apply_launch(const float* pool_partial, int partials_per_img, float* compact_scratch, const void* u,
+                    int u_is_f32, const float* x_in, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* x_out, void* x_out_bf16, float* save_mean, float* save_hid,
+                    float* save_y, int N, int H, int W, int C, int Cr, cudaStream_t stream) {
   int sms = 0;
   if (int e = device_info(&sms)) return e;
   if (!pool_partial || !u || !x_in || !w1 || !b1 || !w2 || !b2 || !x_out || !x_out_bf16)
     return set_error(RUMPY_ERR_ARG, "ca_apply: null pointer");
   if (C % 4 != 0 || C > 256 || Cr < 1 || Cr > 64) return set_error(RUMPY_ERR_ARG, "ca_apply: C=%d Cr=%d", C, Cr);
   if (save_y && (!save_mean || !save_hid)) return set_error(RUMPY_ERR_ARG, "ca_apply: save_* must come together");
-  const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  int partials = partials_per_img;
+  if (compact_scratch && partials > 256) {
+    const int block = (256 / C > 0 ? 256 / C : 1) * C;
+    pool_compact_kernel<<<dim3(64, N), block, block * sizeof(float), stream>>>(pool_partial, partials,
+                                                                               compact_scratch, C);
+    if (int e = check_launch("pool_compact")) return e;
+    pool_partial = compact_scratch;
+    partials = 64;
+  }
   const size_t vec = size_t(H) * W * (C / 4);
   // 4 vectors per thread (all in flight) for small images, 8 once an image is >= 64K vectors: the per-CTA FC
   // prologue is amortised over more streaming work
@@ -331,12 +344,12 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(chunks, N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = cudaStream_t(stream);
+  cfg.gridDim = dim3(chunks, N); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
-  const int partials = tiles * 2, HW = H * W;
+  const int HW = H * W;
   __nv_bfloat16* xob = static_cast<__nv_bfloat16*>(x_out_bf16);
   cudaError_t le;
   if (u_is_f32)
@@ -346,7 +359,19 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
     le = cudaLaunchKernelEx(&cfg, ca_apply_kernel<false>, pool_partial, partials, u, x_in, w1, b1, w2, b2, x_out, xob,
                             save_mean, save_hid, save_y, HW, C, Cr);
   if (le != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "ca_apply launch: %s", cudaGetErrorString(le));
-  return check_launch("ca_apply");
+  return RUMPY_OK;
+}
+}  // namespace rb
+
+extern "C" {
+
+int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const float* x_in, const float* w1,
+                   const float* b1, const float* w2, const float* b2, float* x_out, void* x_out_bf16,
+                   float* save_mean, float* save_hid, float* save_y, int N, int H, int W, int C, int Cr,
+                   void* stream) {
+  const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  return ca_apply_launch(pool_partial, tiles * 2, nullptr, u, u_is_f32, x_in, w1, b1, w2, b2, x_out, x_out_bf16,
+                         save_mean, save_hid, save_y, N, H, W, C, Cr, cudaStream_t(stream));
 }
 
 int rumpy_nchw_to_nhwc(const float* x, float* y_f32, void* y_bf16, int N, int C, int H, int W, void* stream) {

@@ -54,6 +54,10 @@ struct ConvPlan {
 int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
                       int box_h);
 int conv_plan_build(ConvPlan* p, const ConvDesc& d);
+int ca_apply_launch(const float* pool_partial, int partials_per_img, float* compact_scratch, const void* u,
+                    int u_is_f32, const float* x_in, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* x_out, void* x_out_bf16, float* save_mean, float* save_hid,
+                    float* save_y, int N, int H, int W, int C, int Cr, cudaStream_t stream);
 
 // one conv's packing job for the batched pack kernel (misc_kernels.cuh: PackJob has the same layout)
 struct PackJobHost {

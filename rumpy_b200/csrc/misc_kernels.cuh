@@ -150,6 +150,31 @@ __global__ void head_conv_kernel(const float* __restrict__ x, const float* __res
   }
 }
 
+// Large images: thousands of per-tile pool partials per image.  Compact them to `slices` rows per image first so
+// that every CTA of ca_apply_kernel reads a handful of rows instead of all of them.  grid (slices, N).
+__global__ void pool_compact_kernel(const float* __restrict__ pool_partial, int partials_per_img,
+                                    float* __restrict__ compact, int C) {
+  extern __shared__ float red[];
+  const int n = blockIdx.y, slices = gridDim.x;
+  const int begin = int((long long)partials_per_img * blockIdx.x / slices);
+  const int end = int((long long)partials_per_img * (blockIdx.x + 1) / slices);
+  const int lanes = blockDim.x / C, c = threadIdx.x % C, lane = threadIdx.x / C;
+  float s0 = 0.f, s1 = 0.f;
+  if (lane < lanes) {
+    const float* pp = pool_partial + size_t(n) * partials_per_img * C + c;
+    int i = begin + lane;
+    for (; i + lanes < end; i += 2 * lanes) { s0 += pp[size_t(i) * C]; s1 += pp[size_t(i + lanes) * C]; }
+    if (i < end) s0 += pp[size_t(i) * C];
+  }
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[l * C + threadIdx.x];
+    compact[(size_t(n) * slices + blockIdx.x) * C + threadIdx.x] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Channel attention, fused:  y = sigmoid(W2 relu(W1 mean(u) + b1) + b2);  x_out = x_in + u * y
 // (CALayer architectures.py:41-44 + the RCAB skip :83).  The global average pool arrives as per-tile

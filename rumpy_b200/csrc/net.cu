@@ -46,6 +46,7 @@ struct Op {
   const float* pool; const void* u; const float* x_in; float* x_out; void* x_out_b;
   float *save_mean, *save_hid, *save_y;
   float* s_partial; void* du; float* du_colsum; int ca_chunks;
+  float* pool_compact;
   // OP_ADD / OP_HEAD_WGRAD / OP_TAIL_BWD
   const float *a, *b; float* dst_f; void* dst_b; size_t n4;
   const void* tail_in; void* g_hr; float* thin_partial;
@@ -228,6 +229,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     void* u_shared = training ? nullptr : bp.take(u_bytes);
     float* pool_shared = training ? nullptr : static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
     void* gb[2] = {bp.take(px * C * 2), bp.take(px * C * 2)};
+    float* pool_compact = static_cast<float*>(bp.take(size_t(N) * 64 * C * 4));
     int cai = 0;
     for (int g = 0; g < n->n_groups; ++g) {
       GroupRec gr;
@@ -252,6 +254,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         ca.type = OP_CA;
         ca.ca = n->cas[cai++];
         ca.pool = pool; ca.u = u; ca.x_in = (b == 0) ? gin_f : S_f; ca.x_out = S_f; ca.x_out_b = xb;
+        ca.pool_compact = pool_compact;
         if (sv) { ca.save_mean = sv; ca.save_y = sv + size_t(N) * C; ca.save_hid = sv + size_t(N) * 2 * C; }
         ops.push_back(ca);
         gr.blocks.push_back(br);
@@ -664,9 +667,10 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
         if (int e = launch_conv_op(op, params, y_nchw, stream)) return e;
         break;
       case OP_CA:
-        if (int e = rumpy_ca_apply(op.pool, op.u, n->u_f32, op.x_in, params[op.ca.w1], params[op.ca.b1],
-                                   params[op.ca.w2], params[op.ca.b2], op.x_out, op.x_out_b, op.save_mean,
-                                   op.save_hid, op.save_y, N, H, W, n->C, n->C / n->reduction, stream))
+        if (int e = ca_apply_launch(op.pool, 2 * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW),
+                                    op.pool_compact, op.u, n->u_f32, op.x_in, params[op.ca.w1], params[op.ca.b1],
+                                    params[op.ca.w2], params[op.ca.b2], op.x_out, op.x_out_b, op.save_mean,
+                                    op.save_hid, op.save_y, N, H, W, n->C, n->C / n->reduction, stream))
           return e;
         break;
       default:
