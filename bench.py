@@ -251,6 +251,61 @@ def train_bench(handler_factory, device, rank, world, steps, warmup, barrier):
                 batch=TB, hw=THW)
 
 
+def extra_configs(device):
+    """BASELINE.json configs[3] and configs[4] on ONE GPU (informational; the headline stays configs[1])."""
+    from rumpy_b200 import train_native
+    from rumpy_b200.optim import FusedAdam
+    from rumpy_b200.SISR.models.advanced.architectures import EDSR, RCAN
+    out = {}
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    # configs[4]: RCAN x4 whole-frame inference 1920x1080 -> 7680x4320 (frames shard round-robin over GPUs)
+    net = RCAN()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in make_state_dict().items()}, strict=True)
+    net = net.to(device).eval()
+    eng = net.native_engine()
+    with torch.no_grad():
+        x = torch.rand((1, 3, 1080, 1920), device=device)
+        for _ in range(2):
+            eng.forward(x)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(3):
+            eng.forward(x)
+        e1.record()
+        e1.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out['rcan_x4_frame_1080p'] = {'ms_per_frame': ms, 'out_mpix_per_s': 4320 * 7680 / ms * 1e-3,
+                                  'tflops': FLOP_PER_LR_PIXEL * 1080 * 1920 / ms * 1e-9,
+                                  'note': 'whole frame, no tiling (CALayer pools the full image)'}
+    del net, eng, x
+    torch.cuda.empty_cache()
+    # configs[3]: EDSR x4 full (32 ResBlocks, 256 ch, res_scale 0.1) training step, 16 x 64x64 LR patches per GPU
+    spec = recipe.edsr_spec(32, 256, 4)
+    net = EDSR(net_features=256, num_blocks=32, res_scale=0.1)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in recipe.make_weights(spec, seed=8).items()}, strict=True)
+    net = net.to(device).train()
+    opt = FusedAdam(list(net.parameters()), lr=1e-4)
+    x = torch.rand((16, 3, 64, 64), device=device)
+    y = torch.rand((16, 3, 256, 256), device=device)
+    for _ in range(3):
+        train_native.train_step(net, opt, x, y)
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(5):
+        train_native.train_step(net, opt, x, y)
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out['edsr_full_x4_train'] = {'ms_per_step': ms, 'patches_per_s_per_gpu': 16 / ms * 1e3,
+                                 'tflops': 3 * 100505088 * 16 * 64 * 64 / ms * 1e-9,
+                                 'note': 'batch 16 x 64x64 LR patches per GPU (BASELINE gives no batch size)'}
+    del net, opt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args, rank, world):
     import torch.distributed as dist
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -316,6 +371,9 @@ def run_b200(args, rank, world):
         del handler
         torch.cuda.empty_cache()
         tr = train_bench(handler_factory, device, rank, world, max(3, min(args.steps, 10)), args.warmup, barrier)
+    extra = None
+    if world == 1 and not args.no_extra:
+        extra = extra_configs(device)
     clocks = sampler.result()
 
     t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=device)
@@ -354,6 +412,8 @@ def run_b200(args, rank, world):
         'cpu_baseline': {'value': OUT_MPIX_PER_STEP / cpu_s, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
                          'sample': f'full batch of {BATCH} patches, median of {cpu_iters} forwards, fp32 torch-CPU'},
     }
+    if extra is not None:
+        line['extra_configs'] = extra
     if tr is not None:
         train_flop = 3 * FLOP_PER_LR_PIXEL * tr['batch'] * tr['hw'] * tr['hw']
         line['train'] = {
@@ -386,6 +446,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-train', action='store_true', help='skip the training (configs[2]) section')
+    ap.add_argument('--no-extra', action='store_true', help='skip configs[3]/[4] (EDSR-full train, 1080p frame)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

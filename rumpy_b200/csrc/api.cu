@@ -1,4 +1,5 @@
 // C-ABI entry points (include/rumpy_b200.h): argument checks, TMA tensor-map encoding, kernel launches.
+#define RB_CONV_CA_KERNEL_IMPL
 #include "../../include/rumpy_b200.h"
 #include "host_util.cuh"
 #include "conv3x3_tc.cuh"
@@ -9,6 +10,8 @@ namespace rb {
 thread_local std::string g_last_error;
 long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
 int g_use_pdl = 1;                       // programmatic dependent launch between layers (rumpy_debug_set_pdl)
+int g_use_fused_ca = 0;                  // conv2 + CALayer in one kernel (TMEM-held accumulators + grid barrier):
+                                         // correct but not faster at the benchmark shapes, opt-in
 
 int set_error(int code, const char* fmt, ...) {
   char buf[512];
@@ -232,6 +235,69 @@ int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s) 
   return check_launch("pack_conv3x3_batched");
 }
 
+bool conv_ca_supported(int N, int H, int W, int Cin, int Cout) {
+  int sms = 0;
+  if (device_info(&sms)) return false;
+  const int m_tiles = N * ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  return Cin == 64 && Cout == 64 && m_tiles <= kCaMaxTiles * sms;
+}
+
+int conv_ca_plan_build(ConvPlan* p, CaFusedArgs* ca, const ConvDesc& d, float* u_store, int Cr,
+                       unsigned long long* grid_bar, float* save_mean, float* save_hid, float* save_y) {
+  int sms = 0;
+  if (int e = device_info(&sms)) return e;
+  if (!conv_ca_supported(d.N, d.H, d.W, d.Cin, d.Cout)) return set_error(RUMPY_ERR_ARG, "conv_ca: unsupported shape");
+  if (!d.x || !d.w || !d.residual || !d.y_f32 || !d.y_bf16 || !d.pool_partial || !grid_bar)
+    return set_error(RUMPY_ERR_ARG, "conv_ca: null pointer");
+  if (Cr < 1 || Cr > 16) return set_error(RUMPY_ERR_ARG, "conv_ca: Cr=%d", Cr);
+  memset(p, 0, sizeof(*p));
+  memset(ca, 0, sizeof(*ca));
+  ConvArgs& a = p->args;
+  a.N = d.N; a.H = d.H; a.W = d.W;
+  a.tiles_x = (d.W + kTileW - 1) / kTileW;
+  a.tiles_y = (d.H + kTileH - 1) / kTileH;
+  a.m_tiles = d.N * a.tiles_x * a.tiles_y;
+  a.n_tiles = 1; a.cin_chunks = 1; a.a_chunks_per_map = 1; a.o_chunks_per_map = 1; a.cout = 64;
+  a.alpha = 1.f; a.bias = d.bias; a.pool_partial = d.pool_partial; a.dbg = g_debug_timeline;
+  a.stages = 4; a.stg_bufs = 2;
+  p->bn = 64; p->resident = true;
+  p->smem = conv_ca_smem_bytes(a.stages);
+  const int T = (a.m_tiles + sms - 1) / sms;
+  p->grid = (a.m_tiles + T - 1) / T;
+  ca->tiles_per_cta = T;
+  ca->cr = Cr; ca->hw = d.H * d.W; ca->partials_per_img = 2 * a.tiles_x * a.tiles_y;
+  ca->store_u = u_store != nullptr;
+  ca->grid_bar = grid_bar;
+  ca->save_mean = save_mean; ca->save_hid = save_hid; ca->save_y = save_y;
+  if (int e = make_map_nhwc_sub(&p->maps.a[0], false, d.x, 64, d.W, d.H, d.N, 1, 0, kABoxH)) return e;
+  if (int e = make_map_weights(&p->maps.w, d.w, 64, 64, 64, 9)) return e;
+  if (int e = make_map_nhwc_sub(&p->maps.rf, true, d.residual, 64, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+  if (int e = make_map_nhwc_sub(&p->maps.of, true, d.y_f32, 64, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+  if (int e = make_map_nhwc_sub(&p->maps.ob[0], false, d.y_bf16, 64, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+  if (u_store)
+    if (int e = make_map_nhwc_sub(&p->maps.mb, true, u_store, 64, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+  return RUMPY_OK;
+}
+
+int conv_ca_launch(const ConvPlan& p, const CaFusedArgs& ca, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv3x3_ca_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kConvSmemBudget)) !=
+        cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "conv_ca cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ca_kernel, p.maps, p.args, ca);
+  if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "conv_ca launch: %s", cudaGetErrorString(e));
+  return RUMPY_OK;
+}
+
 int grid_for(size_t work_items, int block, int per_sm = 8) {
   int sms = 148;
   device_info(&sms);
@@ -250,6 +316,8 @@ int rumpy_version(void) { return RUMPY_B200_VERSION; }
 /* debug hook, not part of the public header: per-CTA clock64 timeline (16 slots per CTA) for conv kernels */
 int rumpy_debug_set_timeline(void* buf) { g_debug_timeline = static_cast<long long*>(buf); return 0; }
 int rumpy_debug_set_pdl(int on) { g_use_pdl = on; return 0; }
+int rumpy_debug_set_fused_ca(int on) { g_use_fused_ca = on; return 0; }
+int rumpy_debug_get_fused_ca(void) { return g_use_fused_ca; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }
 int rumpy_device_check(void) { return device_info(nullptr); }
 

@@ -8,6 +8,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "conv3x3_tc.cuh"
+#include "conv3x3_ca.cuh"
 
 namespace rb {
 
@@ -54,6 +55,12 @@ struct ConvPlan {
 int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
                       int box_h);
 int conv_plan_build(ConvPlan* p, const ConvDesc& d);
+// RCAB tail fused kernel (conv2 + channel attention + skip), conv3x3_ca.cuh.  d: x = conv2 input (bf16), w/bias,
+// residual = x_in (fp32), y_f32 / y_bf16 = x_out, pool_partial; u_store (fp32 NHWC) may be null (inference).
+bool conv_ca_supported(int N, int H, int W, int Cin, int Cout);
+int conv_ca_plan_build(ConvPlan* p, CaFusedArgs* ca, const ConvDesc& d, float* u_store, int Cr,
+                       unsigned long long* grid_bar, float* save_mean, float* save_hid, float* save_y);
+int conv_ca_launch(const ConvPlan& p, const CaFusedArgs& ca, cudaStream_t s);
 int ca_apply_launch(const float* pool_partial, int partials_per_img, float* compact_scratch, const void* u,
                     int u_is_f32, const float* x_in, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* x_out, void* x_out_bf16, float* save_mean, float* save_hid,

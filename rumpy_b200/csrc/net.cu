@@ -31,11 +31,14 @@ struct ConvW {            // one 3x3 conv of the network
 
 struct CAW { int w1, b1, w2, b2; };
 
-enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
+enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
+
+extern int g_use_fused_ca;
 
 struct Op {
   OpType type;
-  ConvPlan conv;          // OP_CONV
+  ConvPlan conv;          // OP_CONV / OP_CONV_CA
+  CaFusedArgs cafused;    // OP_CONV_CA
   int bias_param;         // param index whose pointer is patched into conv.args.bias (-1: packed / none)
   bool writes_output;     // thin tail conv: out_nchw patched with the caller's y
   // OP_HEAD
@@ -86,6 +89,9 @@ struct Net {
   float* pg_scratch = nullptr;
   int* pg_counter = nullptr;
   float* ca_coef = nullptr;
+  unsigned long long* ca_counters = nullptr;   // grid-barrier counters of the fused conv2+CA ops
+  size_t ca_counters_bytes = 0;
+  bool ca_counters_dirty = false;
   // batched weight packing
   size_t pack_jobs_bytes = 0;
   std::vector<PackJobHost> pack_jobs;
@@ -230,6 +236,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     float* pool_shared = training ? nullptr : static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
     void* gb[2] = {bp.take(px * C * 2), bp.take(px * C * 2)};
     float* pool_compact = static_cast<float*>(bp.take(size_t(N) * 64 * C * 4));
+    const size_t n_rcab = size_t(n->n_groups) * n->n_blocks;
+    unsigned long long* ca_counters = static_cast<unsigned long long*>(bp.take(n_rcab * sizeof(unsigned long long)));
+    const bool fuse_ca = g_use_fused_ca && n->u_f32 && build && conv_ca_supported(N, H, W, C, C);
+    if (build) { n->ca_counters = ca_counters; n->ca_counters_bytes = n_rcab * sizeof(unsigned long long); n->ca_counters_dirty = true; }
     int cai = 0;
     for (int g = 0; g < n->n_groups; ++g) {
       GroupRec gr;
@@ -245,6 +255,24 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         d1.x = cur_b; d1.y_bf16 = t; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C; d1.Cout = C; d1.flags = kConvRelu;
         d1.alpha = 1.f;
         conv_op(ops, n->convs[ci++], d1, false);
+        const float* ca_x_in = (b == 0) ? gin_f : S_f;
+        if (fuse_ca) {
+          // conv2 + CALayer + RCAB skip in one kernel: accumulators wait in TMEM across a grid barrier
+          const ConvW& cw = n->convs[ci++];
+          Op op{};
+          op.type = OP_CONV_CA;
+          op.ca = n->cas[cai];
+          op.bias_param = cw.b_idx;
+          ConvDesc d2{};
+          d2.x = t; d2.w = pk + cw.off_fwd; d2.bias = reinterpret_cast<const float*>(16); d2.residual = ca_x_in;
+          d2.y_f32 = S_f; d2.y_bf16 = xb; d2.pool_partial = pool; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C;
+          float* sm_ = sv, *sy_ = sv ? sv + size_t(N) * C : nullptr, *sh_ = sv ? sv + size_t(N) * 2 * C : nullptr;
+          if (int e = conv_ca_plan_build(&op.conv, &op.cafused, d2, training ? static_cast<float*>(u) : nullptr, Cr,
+                                         ca_counters + cai, sm_, sh_, sy_))
+            err = e;
+          ops.push_back(op);
+          ++cai;
+        } else {
         ConvDesc d2{};
         d2.x = t; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C; d2.flags = kConvPool; d2.alpha = 1.f;
         if (n->u_f32) d2.y_f32 = static_cast<float*>(u); else d2.y_bf16 = u;
@@ -253,10 +281,11 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         Op ca{};
         ca.type = OP_CA;
         ca.ca = n->cas[cai++];
-        ca.pool = pool; ca.u = u; ca.x_in = (b == 0) ? gin_f : S_f; ca.x_out = S_f; ca.x_out_b = xb;
+        ca.pool = pool; ca.u = u; ca.x_in = ca_x_in; ca.x_out = S_f; ca.x_out_b = xb;
         ca.pool_compact = pool_compact;
         if (sv) { ca.save_mean = sv; ca.save_y = sv + size_t(N) * C; ca.save_hid = sv + size_t(N) * 2 * C; }
         ops.push_back(ca);
+        }
         gr.blocks.push_back(br);
         cur_b = xb; cur_f = S_f;
       }
@@ -656,6 +685,11 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
   if (int e = device_info(nullptr)) return e;
   cudaStream_t stream = cudaStream_t(stream_);
   if (int e = ensure_plan(n, packed, workspace, N, H, W, training)) return e;
+  if (n->ca_counters_dirty && n->ca_counters) {
+    if (cudaMemsetAsync(n->ca_counters, 0, n->ca_counters_bytes, stream) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "net_forward: counter reset failed");
+    n->ca_counters_dirty = false;
+  }
   for (Op& op : n->ops) {
     switch (op.type) {
       case OP_HEAD:
@@ -665,6 +699,12 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
         break;
       case OP_CONV:
         if (int e = launch_conv_op(op, params, y_nchw, stream)) return e;
+        break;
+      case OP_CONV_CA:
+        op.conv.args.bias = params[op.bias_param];
+        op.cafused.w1 = params[op.ca.w1]; op.cafused.b1 = params[op.ca.b1];
+        op.cafused.w2 = params[op.ca.w2]; op.cafused.b2 = params[op.ca.b2];
+        if (int e = conv_ca_launch(op.conv, op.cafused, stream)) return e;
         break;
       case OP_CA:
         if (int e = ca_apply_launch(op.pool, 2 * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW),
