@@ -73,6 +73,8 @@ def load():
                       ctypes.c_longlong if name in _LONGLONG else ctypes.c_int)
     if os.environ.get('RUMPY_B200_PDL') == '0':      # debug switch: disable programmatic dependent launch
         lib.rumpy_debug_set_pdl(0)
+    if os.environ.get('RUMPY_B200_CONV2X') == '1':     # experiment: two streaming-B conv CTAs per SM
+        lib.rumpy_debug_set_conv2x(1)
     if os.environ.get('RUMPY_B200_FUSED_CA') == '1':  # opt-in: conv2 + CALayer + skip in one kernel (conv3x3_ca.cuh)
         lib.rumpy_debug_set_fused_ca(1)
     _lib = lib

@@ -10,6 +10,7 @@ namespace rb {
 thread_local std::string g_last_error;
 long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
 int g_use_pdl = 1;                       // programmatic dependent launch between layers (rumpy_debug_set_pdl)
+int g_conv_2x = 0;                       // experiment: stream B, <=113 KB smem, two CTAs per SM (rumpy_debug_set_conv2x)
 int g_use_fused_ca = 0;                  // conv2 + CALayer in one kernel (TMEM-held accumulators + grid barrier):
                                          // correct but not faster at the benchmark shapes, opt-in
 
@@ -175,7 +176,17 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.stages = stages;
   a.stg_bufs = bufs;
   p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages, flags, bufs);
-  int grid = sms < a.m_tiles * a.n_tiles ? sms : a.m_tiles * a.n_tiles;
+  int ctas_per_sm = 1;
+  if (g_conv_2x && !thin && bn == 64 && cin_chunks == 1 && !has_in &&
+      conv_smem_bytes(64, false, 1, 2, flags, 1) <= 113 * 1024) {
+    // two small CTAs per SM: weights streamed with the halo boxes, one tile's prologue/epilogue overlaps the
+    // other's MMAs, and the next layer's CTAs (PDL) can start as soon as one of the two slots frees up
+    p->resident = false;
+    a.stages = 2; a.stg_bufs = 1;
+    p->smem = conv_smem_bytes(64, false, 1, 2, flags, 1);
+    ctas_per_sm = 2;
+  }
+  int grid = sms * ctas_per_sm < a.m_tiles * a.n_tiles ? sms * ctas_per_sm : a.m_tiles * a.n_tiles;
   grid -= grid % a.n_tiles;
   if (grid < a.n_tiles) grid = a.n_tiles;
   p->grid = grid;
@@ -183,7 +194,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   const int cin_sub = d.Cin / (rin * rin);
   for (int q = 0; q < rin * rin; ++q)
     if (int e = make_map_nhwc_sub(&p->maps.a[q], false, d.x, cin_sub, d.W, d.H, d.N, rin, q, kABoxH)) return e;
-  if (int e = make_map_weights(&p->maps.w, d.w, d.Cin, thin ? 16 : d.Cout, bn, resident ? 9 : 3)) return e;
+  if (int e = make_map_weights(&p->maps.w, d.w, d.Cin, thin ? 16 : d.Cout, bn, p->resident ? 9 : 3)) return e;
   if (d.y_bf16) {
     const int cout_sub = d.Cout / (rout * rout);
     for (int q = 0; q < rout * rout; ++q)
@@ -316,6 +327,7 @@ int rumpy_version(void) { return RUMPY_B200_VERSION; }
 /* debug hook, not part of the public header: per-CTA clock64 timeline (16 slots per CTA) for conv kernels */
 int rumpy_debug_set_timeline(void* buf) { g_debug_timeline = static_cast<long long*>(buf); return 0; }
 int rumpy_debug_set_pdl(int on) { g_use_pdl = on; return 0; }
+int rumpy_debug_set_conv2x(int on) { g_conv_2x = on; return 0; }
 int rumpy_debug_set_fused_ca(int on) { g_use_fused_ca = on; return 0; }
 int rumpy_debug_get_fused_ca(void) { return g_use_fused_ca; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }

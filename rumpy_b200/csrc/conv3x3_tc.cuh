@@ -105,7 +105,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <int BN, bool RESIDENT_B>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, RESIDENT_B ? 1 : 2)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   static_assert(BN == 16 || BN == 64 || BN == 128 || BN == 256, "BN must be 16, 64, 128 or 256");
   constexpr int kBBlock = BN * 128;
@@ -331,6 +331,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             tma_store_wait_read0();
             issue_inputs(cc);
           }
+          if (!has_in && stg_bufs == 1 && cc > 0) {
+            // single slot without inputs (two-CTAs-per-SM configuration): the previous chunk's store must have
+            // read the slot before anyone overwrites it
+            if (et == 0) tma_store_wait_read0();
+            named_bar_sync(1, 128);
+          }
           if (j == 0) {
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
@@ -399,7 +405,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
           fence_proxy_async_smem();
           // double-buffered staging: the store issued one chunk ago must have finished READING the other
           // buffer before anyone refills it in the next chunk -- checked here, a whole chunk later
-          if (!has_in && et == 0) tma_store_wait_read0();
+          if (!has_in && stg_bufs == 2 && et == 0) tma_store_wait_read0();
           named_bar_sync(2, 128);
           if (et == 0) {
             RB_STAMP(it == 0 ? 8 : 10);
