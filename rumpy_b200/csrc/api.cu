@@ -11,6 +11,7 @@ thread_local std::string g_last_error;
 long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
 int g_use_pdl = 1;                       // programmatic dependent launch between layers (rumpy_debug_set_pdl)
 int g_conv_2x = 0;                       // experiment: stream B, <=113 KB smem, two CTAs per SM (rumpy_debug_set_conv2x)
+extern int g_use_trunk;                  // net.cu: persistent trunk kernel (trunk_pipe.cuh), default on
 int g_use_fused_ca = 0;                  // conv2 + CALayer in one kernel (TMEM-held accumulators + grid barrier):
                                          // correct but not faster at the benchmark shapes, opt-in
 
@@ -100,6 +101,19 @@ int make_map_weights(CUtensorMap* m, const void* base, int k, int rows, int bn, 
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(RUMPY_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", int(r));
+  return RUMPY_OK;
+}
+
+int make_map_weight_layers(CUtensorMap* m, const void* base, int n_layers) {
+  const cuuint64_t dims[4] = {64, 64, 9, cuuint64_t(n_layers)};
+  const cuuint64_t strides[3] = {128, 64 * 128, 9 * 64 * 128};
+  const cuuint32_t box[4] = {64, 64, 3, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "weights not 16B aligned");
+  CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(RUMPY_ERR_CUDA, "cuTensorMapEncodeTiled(weight layers) failed: %d", int(r));
   return RUMPY_OK;
 }
 
@@ -330,6 +344,8 @@ int rumpy_debug_set_pdl(int on) { g_use_pdl = on; return 0; }
 int rumpy_debug_set_conv2x(int on) { g_conv_2x = on; return 0; }
 int rumpy_debug_set_fused_ca(int on) { g_use_fused_ca = on; return 0; }
 int rumpy_debug_get_fused_ca(void) { return g_use_fused_ca; }
+int rumpy_debug_set_trunk(int on) { g_use_trunk = on; return 0; }
+int rumpy_debug_get_trunk(void) { return g_use_trunk; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }
 int rumpy_device_check(void) { return device_info(nullptr); }
 

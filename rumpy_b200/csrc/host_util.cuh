@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include "conv3x3_tc.cuh"
 #include "conv3x3_ca.cuh"
+#include "trunk_pipe.cuh"
+#include <vector>
 
 namespace rb {
 
@@ -73,5 +75,35 @@ struct PackJobHost {
 };
 int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s);
 int conv_plan_launch(const ConvPlan& p, cudaStream_t s);
+
+// ------------------------------------------------------------------ persistent trunk kernel (trunk_pipe.cuh)
+// packed weights of `n_layers` consecutive 64->64 convs ([layer][tap][64][64] bf16) -> 4-D map, box = one kx third
+int make_map_weight_layers(CUtensorMap* m, const void* base, int n_layers);
+
+struct TrunkLayerParams { int bias, w1, b1, w2, b2; };   // indices into the caller's parameter list (-1: none)
+
+struct TrunkPlan {
+  CUtensorMap w_map;
+  TrunkArgs args;
+  int grid = 0;
+  std::vector<TrunkLayer> layers;          // host copy; parameter pointers are patched per call
+  std::vector<TrunkLayerParams> lparams;
+  std::vector<TrunkLayer> uploaded;        // what the device table currently holds
+  std::vector<const void*> in_bufs;        // bf16 NHWC tensors read through in_maps[i]
+  std::vector<void*> out_bufs;             // bf16 NHWC tensors written through out_maps[i]
+  // device areas (carved from the caller's workspace)
+  TrunkLayer* layers_dev = nullptr;
+  CUtensorMap *in_maps_dev = nullptr, *out_maps_dev = nullptr;
+  void* flags_dev = nullptr;
+  size_t flags_bytes = 0;
+  bool maps_uploaded = false;
+};
+bool trunk_supported(int N, int H, int W, int C, int Cr);
+// device bytes needed next to the activations: layer table, tensor maps, flags, pool partials
+size_t trunk_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int n_out_maps);
+// fills args / maps from plan->layers, in_bufs, out_bufs; `dev` = trunk_device_bytes() bytes of device memory
+int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* w_base, const float* s_init,
+                      void* dev);
+int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s);
 
 }  // namespace rb

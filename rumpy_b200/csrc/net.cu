@@ -12,6 +12,7 @@
 #include "wgrad_tc.cuh"
 #include "bwd_kernels.cuh"
 #include <cmath>
+#include <memory>
 #include <vector>
 
 namespace rb {
@@ -31,9 +32,10 @@ struct ConvW {            // one 3x3 conv of the network
 
 struct CAW { int w1, b1, w2, b2; };
 
-enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
+enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
 
 extern int g_use_fused_ca;
+int g_use_trunk = 1;   // whole 64-channel body in the persistent dataflow kernel (trunk_pipe.cuh) when the shape fits
 
 struct Op {
   OpType type;
@@ -72,7 +74,7 @@ struct Net {
   std::vector<Op> ops, bops;
   const void* plan_packed = nullptr;
   void* plan_ws = nullptr;
-  int pN = 0, pH = 0, pW = 0, p_training = -1;
+  int pN = 0, pH = 0, pW = 0, p_training = -1, p_trunk = -1;
   // backward job lists (host copies; device copies live in the workspace)
   std::vector<float*> plan_grads;
   std::vector<WgradJob> wg_jobs;
@@ -89,6 +91,7 @@ struct Net {
   float* pg_scratch = nullptr;
   int* pg_counter = nullptr;
   float* ca_coef = nullptr;
+  std::unique_ptr<TrunkPlan> trunk;            // persistent trunk kernel plan (OP_TRUNK), or null
   unsigned long long* ca_counters = nullptr;   // grid-barrier counters of the fused conv2+CA ops
   size_t ca_counters_bytes = 0;
   bool ca_counters_dirty = false;
@@ -227,8 +230,63 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   }
   const void* cur_b = head_b;     // bf16 operand of the running activation
   const float* cur_f = head_f;    // its fp32 residual-stream copy
-  const int Cr = C / n->reduction;
-  if (n->arch == 0) {
+  const int Cr = n->arch == 0 ? C / n->reduction : 1;
+  // ---- the whole body (every 64->64 conv, CA, skips) as ONE persistent dataflow kernel when the shape fits
+  const bool use_trunk = g_use_trunk && !training && C == 64 && trunk_supported(N, H, W, C, Cr);
+  std::unique_ptr<TrunkPlan> trunk;
+  if (use_trunk) {
+    void* pp[2] = {bp.take(px * C * 2), bp.take(px * C * 2)};   // bf16 operand ping-pong
+    void* body_b = bp.take(px * C * 2);
+    const int n_body = n->conv_body;                            // convs 1 .. conv_body are the 64->64 body convs
+    void* dev = bp.take(trunk_device_bytes(N, H, W, n_body, 3, 3));
+    if (build) {
+      trunk.reset(new TrunkPlan());
+      trunk->in_bufs = {head_b, pp[0], pp[1]};
+      trunk->out_bufs = {pp[0], pp[1], body_b};
+      auto add_layer = [&](int kind, int conv, int ca) -> TrunkLayer& {
+        TrunkLayer l{};
+        const int L = int(trunk->layers.size());
+        l.kind = kind;
+        l.in_map = L == 0 ? 0 : 1 + ((L - 1) & 1);
+        l.out_map = L & 1;
+        l.ca_slot = -1; l.u_map = -1; l.alpha = 1.f;
+        TrunkLayerParams lp{n->convs[conv].b_idx, -1, -1, -1, -1};
+        if (ca >= 0) { const CAW& c = n->cas[ca]; lp.w1 = c.w1; lp.b1 = c.b1; lp.w2 = c.w2; lp.b2 = c.b2; l.ca_slot = ca; }
+        trunk->layers.push_back(l);
+        trunk->lparams.push_back(lp);
+        return trunk->layers.back();
+      };
+      int c2 = 1, cai = 0;
+      if (n->arch == 0) {
+        for (int g = 0; g < n->n_groups; ++g) {
+          for (int b = 0; b < n->n_blocks; ++b) {
+            add_layer(kTrunkRelu, c2++, -1);
+            add_layer(kTrunkCA, c2++, cai++);
+          }
+          TrunkLayer& gt = add_layer(kTrunkRes, c2++, -1);      // group tail conv + group skip (:121-124)
+          gt.res_f32 = g == 0 ? head_f : G_f[(g - 1) & 1];
+          gt.out_f32 = G_f[g & 1];
+          gt.update_s = 1;
+        }
+      } else {
+        for (int b = 0; b < n->n_blocks; ++b) {
+          add_layer(kTrunkRelu, c2++, -1);
+          TrunkLayer& r2 = add_layer(kTrunkRes, c2++, -1);      // conv2(.)*res_scale + x   (common.py:72-73)
+          r2.alpha = n->res_scale; r2.update_s = 1;
+        }
+      }
+      TrunkLayer& bt = add_layer(kTrunkRes, c2++, -1);          // body tail conv + global skip (:173-174 / :238-239)
+      bt.res_f32 = head_f;
+      bt.out_map = 2;
+      if (c2 != n_body + 1) err = set_error(RUMPY_ERR_ARG, "trunk: layer count mismatch");
+      if (int e = trunk_plan_finish(trunk.get(), N, H, W, Cr, pk + n->convs[1].off_fwd, head_f, dev)) err = e;
+      Op op{};
+      op.type = OP_TRUNK;
+      ops.push_back(op);
+    }
+    ci = n_body + 1;
+    cur_b = body_b;
+  } else if (n->arch == 0) {
     const size_t u_bytes = px * C * (n->u_f32 ? 4 : 2);
     void* xb_shared = training ? nullptr : bp.take(px * C * 2);
     void* t_shared = training ? nullptr : bp.take(px * C * 2);
@@ -321,8 +379,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   }
   // ---- body tail conv + global skip (architectures.py:173-174 / :238-239): operand for the upsampler only
   const void* body_in_b = cur_b;
-  void* body_b = bp.take(px * C * 2);
-  {
+  if (!use_trunk) {
+    void* body_b = bp.take(px * C * 2);
     ConvDesc d{};
     d.x = cur_b; d.residual = head_f; d.y_bf16 = body_b; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C;
     d.alpha = 1.f;
@@ -548,6 +606,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   if (build) {
     n->ops.swap(ops);
     n->bops.swap(bops);
+    n->trunk = std::move(trunk);
     n->wg_jobs.swap(wg_jobs);
     n->wg_rjobs.swap(wg_rjobs);
     n->cs_jobs.swap(cs_jobs);
@@ -563,11 +622,12 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
 
 static int ensure_plan(Net* n, const void* packed, void* workspace, int N, int H, int W, int training) {
   if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
-      n->p_training != training) {
+      n->p_training != training || n->p_trunk != g_use_trunk) {
     size_t bytes = 0;
     n->plan_packed = nullptr;
     if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
     n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
+    n->p_trunk = g_use_trunk;
   }
   return RUMPY_OK;
 }
@@ -699,6 +759,9 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
         break;
       case OP_CONV:
         if (int e = launch_conv_op(op, params, y_nchw, stream)) return e;
+        break;
+      case OP_TRUNK:
+        if (int e = trunk_launch(n->trunk.get(), params, stream)) return e;
         break;
       case OP_CONV_CA:
         op.conv.args.bias = params[op.bias_param];

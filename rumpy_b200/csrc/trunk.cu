@@ -1,0 +1,125 @@
+// Host side of the persistent trunk kernel (trunk_pipe.cuh): plan construction, device tables, launch.
+#define RB_TRUNK_KERNEL_IMPL
+#include "../../include/rumpy_b200.h"
+#include "host_util.cuh"
+
+namespace rb {
+
+extern long long* g_debug_timeline;
+int g_trunk_store_mode = 0;
+int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
+
+static size_t al(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+bool trunk_supported(int N, int H, int W, int C, int Cr) {
+  int sms = 0;
+  if (device_info(&sms)) return false;
+  const int P = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const long long T = (long long)N * P;
+  return C == 64 && Cr >= 1 && Cr <= 16 && T <= (long long)kTrunkMaxK * sms && P <= 512;
+}
+
+size_t trunk_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int n_out_maps) {
+  const size_t P = size_t((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const size_t T = size_t(N) * P;
+  return al(size_t(n_layers) * sizeof(TrunkLayer)) + al(size_t(n_in_maps) * sizeof(CUtensorMap)) +
+         al(size_t(n_out_maps) * sizeof(CUtensorMap)) + al((T + N) * sizeof(int)) + al(2 * T * 64 * sizeof(float));
+}
+
+int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* w_base, const float* s_init,
+                      void* dev) {
+  int sms = 0;
+  if (int e = device_info(&sms)) return e;
+  if (!trunk_supported(N, H, W, 64, Cr)) return set_error(RUMPY_ERR_ARG, "trunk: unsupported shape");
+  TrunkArgs& a = plan->args;
+  memset(&a, 0, sizeof(a));
+  a.n_layers = int(plan->layers.size());
+  a.N = N; a.H = H; a.W = W;
+  a.tiles_x = (W + kTileW - 1) / kTileW;
+  a.tiles_y = (H + kTileH - 1) / kTileH;
+  a.tiles_per_img = a.tiles_x * a.tiles_y;
+  a.T = N * a.tiles_per_img;
+  a.K = (a.T + sms - 1) / sms;
+  plan->grid = (a.T + a.K - 1) / a.K;
+  // whole images per slot row => every image lives in one tile slot => pool / apply may be interleaved per tile
+  if (a.K > 1 && a.tiles_per_img <= sms) {
+    const int g = (sms / a.tiles_per_img) * a.tiles_per_img;
+    if ((a.T + g - 1) / g <= a.K) plan->grid = g;
+  }
+  a.interleave = (plan->grid % a.tiles_per_img == 0) ? 1 : 0;
+  a.w_layer0 = 0;
+  a.cr = Cr;
+  a.inv_hw = 1.f / float(H * W);
+  a.s_init = s_init;
+  char* p = static_cast<char*>(dev);
+  plan->layers_dev = reinterpret_cast<TrunkLayer*>(p); p += al(plan->layers.size() * sizeof(TrunkLayer));
+  plan->in_maps_dev = reinterpret_cast<CUtensorMap*>(p); p += al(plan->in_bufs.size() * sizeof(CUtensorMap));
+  plan->out_maps_dev = reinterpret_cast<CUtensorMap*>(p); p += al(plan->out_bufs.size() * sizeof(CUtensorMap));
+  plan->flags_dev = p;
+  plan->flags_bytes = (size_t(a.T) + N) * sizeof(int);
+  a.ready = reinterpret_cast<int*>(p);
+  a.pool_cnt = a.ready + a.T;
+  p += al(plan->flags_bytes);
+  a.pool_partial = reinterpret_cast<float*>(p);
+  a.layers = plan->layers_dev;
+  a.in_maps = plan->in_maps_dev;
+  a.out_maps = plan->out_maps_dev;
+  if (int e = make_map_weight_layers(&plan->w_map, w_base, a.n_layers)) return e;
+  plan->uploaded.clear();
+  plan->maps_uploaded = false;
+  return RUMPY_OK;
+}
+
+int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
+  TrunkArgs& a = plan->args;
+  if (!plan->maps_uploaded) {
+    std::vector<CUtensorMap> im(plan->in_bufs.size()), om(plan->out_bufs.size());
+    for (size_t i = 0; i < im.size(); ++i)
+      if (int e = make_map_nhwc_sub(&im[i], false, plan->in_bufs[i], 64, a.W, a.H, a.N, 1, 0, kABoxH)) return e;
+    for (size_t i = 0; i < om.size(); ++i)
+      if (int e = make_map_nhwc_sub(&om[i], false, plan->out_bufs[i], 64, a.W, a.H, a.N, 1, 0, kTileH)) return e;
+    if (cudaMemcpyAsync(plan->in_maps_dev, im.data(), im.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s) !=
+            cudaSuccess ||
+        cudaMemcpyAsync(plan->out_maps_dev, om.data(), om.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s) !=
+            cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk: map upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(s);   // `im` / `om` die at scope exit; once per plan
+    plan->maps_uploaded = true;
+  }
+  for (size_t i = 0; i < plan->layers.size(); ++i) {
+    TrunkLayer& l = plan->layers[i];
+    const TrunkLayerParams& lp = plan->lparams[i];
+    l.bias = params[lp.bias];
+    l.out_bf16 = plan->out_bufs[l.out_map];
+    if (lp.w1 >= 0) { l.w1 = params[lp.w1]; l.b1 = params[lp.b1]; l.w2 = params[lp.w2]; l.b2 = params[lp.b2]; }
+  }
+  if (plan->uploaded.size() != plan->layers.size() ||
+      memcmp(plan->uploaded.data(), plan->layers.data(), plan->layers.size() * sizeof(TrunkLayer)) != 0) {
+    plan->uploaded = plan->layers;   // persistent host copy: the async copy may read it after we return
+    if (cudaMemcpyAsync(plan->layers_dev, plan->uploaded.data(), plan->uploaded.size() * sizeof(TrunkLayer),
+                        cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk: layer table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(s);
+  }
+  if (cudaMemsetAsync(plan->flags_dev, 0, plan->flags_bytes, s) != cudaSuccess)
+    return set_error(RUMPY_ERR_CUDA, "trunk: flag reset failed: %s", cudaGetErrorString(cudaGetLastError()));
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(trunk_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTrunkSmemBytes)) !=
+        cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  a.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
+  a.dbg_layers = g_trunk_dbg_layers;
+  a.store_mode = g_trunk_store_mode;
+  trunk_pipe_kernel<<<plan->grid, kTrunkThreads, kTrunkSmemBytes, s>>>(plan->w_map, a);
+  return check_launch("trunk_pipe");
+}
+
+}  // namespace rb
+
+extern "C" {
+int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
+int rumpy_debug_set_trunk_store_mode(int mode) { rb::g_trunk_store_mode = mode; return 0; }
+}

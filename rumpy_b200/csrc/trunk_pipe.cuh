@@ -1,0 +1,556 @@
+// The whole 64-channel residual trunk in ONE persistent, tile-stationary dataflow kernel (sm_100a).
+//
+// Replaces, for a whole RCAN body (or an EDSR-baseline body): every `default_conv` 3x3 64->64 call
+// (/root/reference/rumpy/SISR/models/advanced/common.py:6-9), RCAB.forward (architectures.py:81-84) with its
+// CALayer (:41-44), ResidualGroup.forward (:121-124), the body-tail conv + global skip of RCAN.forward
+// (:172-174), and ResBlock.forward (common.py:71-75).
+//
+// Why: at the benchmark shapes (16 x 48x48 / 16 x 64x64 patches) one layer is only 2-4 output tiles per SM, so
+// a kernel per layer is bounded by launch, prologue and drain latency, not by the tensor cores.  Here the layer
+// loop runs INSIDE the kernel:
+//   * each CTA (one per SM, all co-resident) owns up to 4 fixed 8x16-pixel tiles, taken from different images;
+//   * layer L+1 of a tile starts as soon as the tile and its 8 spatial neighbours have published layer L
+//     (per-tile epoch flags in global memory, release/acquire) -- no grid-wide barrier anywhere;
+//   * the fp32 residual stream of the owned tiles never leaves the SM: it lives in TENSOR MEMORY (64 columns
+//     per tile) next to the accumulators (64 columns per tile) -> 4 x 128 = all 512 TMEM columns;
+//   * bf16 operand tiles travel through L2 only: TMA store -> flag -> neighbour's TMA halo-box load;
+//   * the 72 KB of weights per layer stream through one smem buffer in three `kx` thirds that are refilled by
+//     a dedicated warp as soon as the last tile's MMAs of the previous layer have consumed them;
+//   * channel attention: per-tile channel sums (warp-shuffle transpose reduction, straight from the TMEM
+//     accumulator) -> per-image arrival counter -> a dedicated warp computes y = sigmoid(W2 relu(W1 mean+b1)+b2)
+//     -> the SAME accumulator is read again and x + u*y is written to the TMEM stream and the bf16 operand.
+//
+// Warp roles (384 threads):  0 A-operand TMA producer (polls the neighbour flags) | 1 MMA issuer | 2 weight
+// producer | 3 channel-attention warp | 4-7 epilogue group 0 (tile slots 0,2) | 8-11 epilogue group 1 (slots 1,3).
+#pragma once
+#include "conv3x3_tc.cuh"
+
+namespace rb {
+
+enum TrunkKind : int { kTrunkRelu = 0, kTrunkCA = 1, kTrunkRes = 2 };
+
+struct TrunkLayer {
+  int kind;
+  int in_map, out_map;   // indices into TrunkArgs::in_maps (box 10 rows) / out_maps (box 8 rows)
+  int ca_slot;           // kTrunkCA: ordinal among the CA layers (epoch of the per-image pool counter)
+  int update_s;          // kTrunkRes: the result replaces the fp32 residual stream in TMEM
+  int u_map;             // kTrunkCA (training): out map of the saved pre-attention activation u (bf16), or -1
+  float alpha;           // kTrunkRes: out = alpha * (acc + bias) + residual
+  int pad_;
+  const float* bias;
+  const float* res_f32;  // kTrunkRes: fp32 NHWC residual in global memory; nullptr = the TMEM stream
+  float* out_f32;        // kTrunkRes: optional fp32 NHWC copy of the result (a later layer's res_f32)
+  void* out_bf16;        // the tensor behind out_map (store_mode 1 writes it with plain stores)
+  const float *w1, *b1, *w2, *b2;          // kTrunkCA: FC weights [cr][64], [cr], [64][cr], [64]
+  float *save_mean, *save_hid, *save_y;    // kTrunkCA (training): CA vectors for backward, or nullptr
+};
+
+struct TrunkArgs {
+  const TrunkLayer* layers;
+  const CUtensorMap* in_maps;
+  const CUtensorMap* out_maps;
+  const float* s_init;     // fp32 NHWC: initial residual stream (the head conv's output)
+  int* ready;              // [T]   number of layers whose bf16 output of this tile is visible
+  int* pool_cnt;           // [N]   tiles of the image that have published their pool partials (monotonic)
+  float* pool_partial;     // [2][T][64]
+  long long* dbg;          // optional timeline, [grid][dbg_layers][2][16] clock64 stamps
+  int n_layers, N, H, W, tiles_x, tiles_y, tiles_per_img, T, K, w_layer0, cr, interleave, dbg_layers;
+  float inv_hw;
+  int store_mode;          // 0: staged tile -> TMA store; 1: staged tile -> coalesced st.global by the staging warp
+};
+
+constexpr int kTrunkThreads = 384;
+constexpr int kTrunkAStages = 4;
+constexpr int kTrunkMaxK = 4;
+constexpr int kTrunkWBytes = 9 * 64 * 128;   // 72 KB: [kx*3+ky][64 rows][64 k] bf16
+constexpr int kTrunkWThird = 3 * 64 * 128;   // 24 KB: the three ky taps of one kx
+constexpr int kTrunkAccCol = 256;            // TMEM: stream S_j at column 64 j, accumulator j at 256 + 64 j
+constexpr size_t kTrunkSmemBytes = 1024 + kTrunkWBytes + size_t(kTrunkAStages) * kAStageBytes + 2 * kABytes;
+
+#ifdef RB_TRUNK_KERNEL_IMPL
+
+static __device__ __noinline__ void trunk_watchdog_fail(const int* p, int target, int what) {
+  printf("rumpy_b200: trunk watchdog: block %d thread %d waiting (%d) for %d at %p (now %d)\n", (int)blockIdx.x,
+         (int)threadIdx.x, what, target, (const void*)p, *(volatile const int*)p);
+  __trap();
+}
+__device__ __forceinline__ void poll_ge(const int* p, int target, int what) {
+  if (ld_acquire_s32(p) >= target) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (ld_acquire_s32(p) < target) {
+    __nanosleep(20);
+    if ((++spins & 255u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) trunk_watchdog_fail(p, target, what);
+  }
+}
+
+// f[i] of lane l  ->  returns sum over the 32 lanes of element f[lane] (fixed order: deterministic)
+template <int HALF>
+__device__ __forceinline__ void xpose_step(float (&f)[32], int lane) {
+  const bool up = (lane & HALF) != 0;
+#pragma unroll
+  for (int i = 0; i < HALF; ++i) {
+    const float send = up ? f[i] : f[i + HALF];
+    const float keep = up ? f[i + HALF] : f[i];
+    f[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+  }
+}
+__device__ __forceinline__ float lane_transpose_sum32(float (&f)[32], int lane) {
+  xpose_step<16>(f, lane);
+  xpose_step<8>(f, lane);
+  xpose_step<4>(f, lane);
+  xpose_step<2>(f, lane);
+  xpose_step<1>(f, lane);
+  return f[0];
+}
+
+__global__ void __launch_bounds__(kTrunkThreads, 1)
+trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full[kTrunkAStages];
+  __shared__ __align__(8) uint64_t a_empty[kTrunkAStages];
+  __shared__ __align__(8) uint64_t w_full[3];
+  __shared__ __align__(8) uint64_t w_empty[3];
+  __shared__ __align__(8) uint64_t acc_full[kTrunkMaxK];
+  __shared__ __align__(8) uint64_t y_full[kTrunkMaxK];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float mean_s[64];
+  __shared__ float bias_s[2][64], red_s[2][4][64], y_s[kTrunkMaxK][64];
+  __shared__ float fc_w1[16 * 64], fc_w2[64 * 16], fc_b1[16], fc_b2[64];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + kTrunkWBytes;
+  uint8_t* stg_s = a_s + kTrunkAStages * kAStageBytes;
+
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int T = args.T, P = args.tiles_per_img, n_layers = args.n_layers;
+  int my_k = 0;
+  for (int j = 0; j < args.K; ++j) my_k += (cta + j * G < T) ? 1 : 0;
+
+#define TR_STAMP(L_, j_, slot_)                                                                       \
+  do {                                                                                                \
+    if (args.dbg && (L_) < args.dbg_layers && (j_) < 2)                                               \
+      args.dbg[((size_t(cta) * args.dbg_layers + (L_)) * 2 + (j_)) * 16 + (slot_)] = clock64();        \
+  } while (0)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTrunkAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < kTrunkMaxK; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&y_full[i], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 2 && lane == 0) tma_prefetch_desc(&w_map);
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================================================================== A-operand producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int L = 0; L < n_layers; ++L) {
+      const CUtensorMap* im = args.in_maps + args.layers[L].in_map;
+      if (lane == 0 && L + 1 < n_layers) tma_prefetch_desc(args.in_maps + args.layers[L + 1].in_map);
+      for (int j = 0; j < my_k; ++j) {
+        const int t = cta + j * G;
+        const int n = t / P, rem = t - n * P;
+        const int ty = rem / args.tiles_x, tx = rem - ty * args.tiles_x;
+        if (L > 0) {
+          // layer L reads layer L-1's output of this tile and of its 8 neighbours (same image)
+          if (lane < 9) {
+            const int nty = ty + lane / 3 - 1, ntx = tx + lane % 3 - 1;
+            if (nty >= 0 && nty < args.tiles_y && ntx >= 0 && ntx < args.tiles_x)
+              poll_ge(args.ready + n * P + nty * args.tiles_x + ntx, L, 1);
+          }
+          __syncwarp();
+        }
+        if (lane == 0) TR_STAMP(L, j, 0);
+        for (int kx = 0; kx < 3; ++kx) {
+          mbar_wait(&a_empty[stage], phase ^ 1);
+          if (elect_one()) {
+            fence_proxy_async_all();   // acquired generic-proxy flag -> async-proxy (TMA) read
+            mbar_expect_tx(&a_full[stage], kAStageBytes);
+            tma_load_4d(a_s + stage * kAStageBytes, im, &a_full[stage], 0, tx * kTileW + kx - 1, ty * kTileH - 1, n);
+          }
+          __syncwarp();
+          if (++stage == kTrunkAStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t kIdesc = make_idesc_bf16(128, 64);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int L = 0; L < n_layers; ++L) {
+      for (int j = 0; j < my_k; ++j) {
+        const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
+        for (int kx = 0; kx < 3; ++kx) {
+          if (j == 0) mbar_wait(&w_full[kx], uint32_t(L & 1));
+          mbar_wait(&a_full[stage], phase);
+          tc_fence_after();
+          if (kx == 0 && lane == 0) TR_STAMP(L, j, 1);
+          if (elect_one()) {
+            const uint32_t a_addr = smem_u32(a_s + stage * kAStageBytes);
+            const uint32_t b_addr = smem_u32(w_s + kx * kTrunkWThird);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const uint64_t adesc = make_smem_desc(a_addr + ky * (kTileW * 128), 16, 1024, kLayoutSw128);
+              const uint64_t bdesc = make_smem_desc(b_addr + ky * 8192, 16, 1024, kLayoutSw128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (kx | ky | k) != 0);
+            }
+            umma_commit(&a_empty[stage]);
+            if (j == my_k - 1) umma_commit(&w_empty[kx]);   // this third of the weights is free for layer L+1
+          }
+          __syncwarp();
+          if (++stage == kTrunkAStages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&acc_full[j]);
+        __syncwarp();
+        if (lane == 0) TR_STAMP(L, j, 2);
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================================================== weight producer (three kx thirds)
+    for (int L = 0; L < n_layers; ++L) {
+      for (int kx = 0; kx < 3; ++kx) {
+        mbar_wait(&w_empty[kx], uint32_t(L & 1) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&w_full[kx], kTrunkWThird);
+          tma_load_4d(w_s + kx * kTrunkWThird, &w_map, &w_full[kx], 0, 0, kx * 3, args.w_layer0 + L);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================================== channel-attention warp
+    const int cr = args.cr;
+    int ca_seen = 0;
+    for (int L = 0; L < n_layers; ++L) {
+      const TrunkLayer* lay = args.layers + L;
+      if (lay->kind != kTrunkCA) continue;
+      const float *w1 = lay->w1, *w2 = lay->w2, *b1 = lay->b1, *b2 = lay->b2;
+      const int ca_slot = lay->ca_slot;
+      // every consumer of the previous CA layer's FC parameters (this warp only) is done: reload
+      for (int i = lane; i < cr * 64; i += 32) { fc_w1[i] = __ldg(w1 + i); fc_w2[i] = __ldg(w2 + i); }
+      if (lane < cr) fc_b1[lane] = __ldg(b1 + lane);
+      fc_b2[lane] = __ldg(b2 + lane);
+      fc_b2[lane + 32] = __ldg(b2 + lane + 32);
+      __syncwarp();
+      for (int j = 0; j < my_k; ++j) {
+        const int t = cta + j * G;
+        const int n = t / P, rem = t - n * P;
+        if (lane == 0) { poll_ge(args.pool_cnt + n, (ca_slot + 1) * P, 2); TR_STAMP(L, j, 13); }
+        __syncwarp();
+        // mean over the image: lanes 0-15 / 16-31 take even / odd partial rows, 4 channels each
+        const float* pp = args.pool_partial + (size_t(ca_slot & 1) * T + size_t(n) * P) * 64 + (lane & 15) * 4;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        int r = lane >> 4;
+#pragma unroll 4
+        for (; r + 2 < P; r += 4) {
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(pp + size_t(r) * 64));
+          const float4 v1 = __ldcg(reinterpret_cast<const float4*>(pp + size_t(r + 2) * 64));
+          a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+          a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        }
+        if (r < P) {
+          const float4 v0 = __ldcg(reinterpret_cast<const float4*>(pp + size_t(r) * 64));
+          a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        }
+        a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
+        a0.x += __shfl_xor_sync(0xffffffffu, a0.x, 16);
+        a0.y += __shfl_xor_sync(0xffffffffu, a0.y, 16);
+        a0.z += __shfl_xor_sync(0xffffffffu, a0.z, 16);
+        a0.w += __shfl_xor_sync(0xffffffffu, a0.w, 16);
+        if (lane < 16)
+          *reinterpret_cast<float4*>(&mean_s[lane * 4]) =
+              make_float4(a0.x * args.inv_hw, a0.y * args.inv_hw, a0.z * args.inv_hw, a0.w * args.inv_hw);
+        __syncwarp();
+        const float m0 = mean_s[lane], m1 = mean_s[lane + 32];
+        float y0 = fc_b2[lane], y1 = fc_b2[lane + 32];
+        const bool saver = lay->save_y != nullptr && rem == 0;   // the image's first tile records the CA vectors
+        for (int h = 0; h < cr; ++h) {
+          float s = fc_w1[h * 64 + lane] * m0 + fc_w1[h * 64 + 32 + lane] * m1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float hv = fmaxf(s + fc_b1[h], 0.f);
+          y0 = fmaf(fc_w2[lane * cr + h], hv, y0);
+          y1 = fmaf(fc_w2[(lane + 32) * cr + h], hv, y1);
+          if (saver && lane == 0) lay->save_hid[n * cr + h] = hv;
+        }
+        y0 = 1.f / (1.f + __expf(-y0));
+        y1 = 1.f / (1.f + __expf(-y1));
+        y_s[j][lane] = y0;
+        y_s[j][lane + 32] = y1;
+        if (saver) {
+          lay->save_y[n * 64 + lane] = y0; lay->save_y[n * 64 + 32 + lane] = y1;
+          lay->save_mean[n * 64 + lane] = m0; lay->save_mean[n * 64 + 32 + lane] = m1;
+        }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&y_full[j]); TR_STAMP(L, j, 5); }
+      }
+      ++ca_seen;
+    }
+    (void)ca_seen;
+  } else {
+    // ===================================================================== epilogue groups (2 x 128 threads)
+    const int e = (warp - 4) >> 2;
+    const int q = warp & 3;                  // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;           // pixel of the tile == TMEM lane == thread index in the group
+    const int ly = row >> 4, lx = row & 15;
+    const uint32_t swz = uint32_t(row & 7);
+    const uint32_t bar_id = 1u + uint32_t(e);
+    uint8_t* stg = stg_s + e * kABytes;
+    uint8_t* my_stg = stg + row * 128;
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    float* bias_e = bias_s[e];
+
+    // ---- residual stream of the owned tiles: global fp32 -> TMEM
+    for (int j = e; j < my_k; j += 2) {
+      const int t = cta + j * G;
+      const int n = t / P, rem = t - n * P;
+      const int ty = rem / args.tiles_x, tx = rem - ty * args.tiles_x;
+      const int y = ty * kTileH + ly, x = tx * kTileW + lx;
+      const bool valid = y < args.H && x < args.W;
+      const float4* src = reinterpret_cast<const float4*>(args.s_init + ((size_t(n) * args.H + y) * args.W + x) * 64);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) f = __ldg(src + h * 8 + c4);
+          v[c4 * 4 + 0] = __float_as_uint(f.x); v[c4 * 4 + 1] = __float_as_uint(f.y);
+          v[c4 * 4 + 2] = __float_as_uint(f.z); v[c4 * 4 + 3] = __float_as_uint(f.w);
+        }
+        tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), v);
+      }
+    }
+    tmem_st_wait();
+
+    int ca_seen = 0;
+    for (int L = 0; L < n_layers; ++L) {
+      const TrunkLayer* lay = args.layers + L;
+      const int kind = lay->kind;
+      const float* bias = lay->bias;
+      const CUtensorMap* om = args.out_maps + lay->out_map;
+
+      // the staged bf16 tile -> global memory, then publish the tile's epoch once the data is visible gpu-wide.
+      // Called by all 128 threads of the group after they have written their staging rows.
+      auto finish_tile = [&](int j, int t, int n, int ty, int tx) {
+        if (args.store_mode == 0) {
+          tc_fence_before();
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (row == 0) {
+            TR_STAMP(L, j, 10);
+            tma_store_4d(om, stg, 0, tx * kTileW, ty * kTileH, n);
+            tma_store_commit();
+            tma_store_wait_all0();
+            TR_STAMP(L, j, 11);
+            fence_proxy_async_all();
+            st_release_s32(args.ready + t, L + 1);
+            TR_STAMP(L, j, 6);
+          }
+        } else {
+          // each warp copies its own 32 staged rows: 4 pixels x 128 B = 512 contiguous bytes per instruction
+          __syncwarp();
+          __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(lay->out_bf16);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int p = q * 32 + i * 4 + (lane >> 3), ch = lane & 7;
+            const int py = ty * kTileH + (p >> 4), px = tx * kTileW + (p & 15);
+            const uint4 d = *reinterpret_cast<const uint4*>(stg + p * 128 + ((uint32_t(ch) ^ uint32_t(p & 7)) << 4));
+            if (py < args.H && px < args.W)
+              *reinterpret_cast<uint4*>(ob + ((size_t(n) * args.H + py) * args.W + px) * 64 + ch * 8) = d;
+          }
+          tc_fence_before();
+          named_bar_sync(bar_id, 128);
+          if (row == 0) {
+            TR_STAMP(L, j, 10);
+            __threadfence();
+            TR_STAMP(L, j, 11);
+            st_release_s32(args.ready + t, L + 1);
+            TR_STAMP(L, j, 6);
+          }
+        }
+      };
+      auto stage_bf16 = [&](const float (&f)[32], int h) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(my_stg + ((uint32_t(h * 4 + c) ^ swz) << 4)) =
+              make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
+                         pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]));
+      };
+
+      // ---------------------------------------------------------------- conv + bias (+ReLU | + residual)
+      auto plain = [&](int j) {
+        const int t = cta + j * G;
+        const int n = t / P, rem = t - n * P;
+        const int ty = rem / args.tiles_x, tx = rem - ty * args.tiles_x;
+        const int y = ty * kTileH + ly, x = tx * kTileW + lx;
+        const bool valid = y < args.H && x < args.W;
+        const float bv = row < 64 ? __ldg(bias + row) : 0.f;
+        const float* res = lay->res_f32;
+        float* outf = lay->out_f32;
+        const float alpha = lay->alpha;
+        const int update_s = lay->update_s;
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
+        mbar_wait(&acc_full[j], uint32_t(L & 1));
+        tc_fence_after();
+        if (row == 0) TR_STAMP(L, j, 3);
+        if (row < 64) bias_e[row] = bv;
+        named_bar_sync(bar_id, 128);
+        if (row == 0) TR_STAMP(L, j, 8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          if (kind == kTrunkRelu) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[h * 32 + i], 0.f);
+          } else {
+            if (res != nullptr) {
+              tmem_ld_wait();
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) r = *reinterpret_cast<const float4*>(res + pix + h * 32 + c4 * 4);
+                f[c4 * 4 + 0] = r.x; f[c4 * 4 + 1] = r.y; f[c4 * 4 + 2] = r.z; f[c4 * 4 + 3] = r.w;
+              }
+            } else {
+              uint32_t s[32];
+              tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[h * 32 + i]) * alpha + f[i];
+            if (update_s) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
+              tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), v);
+            }
+            if (outf != nullptr && valid) {
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                *reinterpret_cast<float4*>(outf + pix + h * 32 + c4 * 4) =
+                    make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
+            }
+          }
+          stage_bf16(f, h);
+        }
+        tmem_st_wait();
+        if (row == 0) TR_STAMP(L, j, 9);
+        finish_tile(j, t, n, ty, tx);
+      };
+
+      // ---------------------------------------------------------------- channel attention, phase 1: pool
+      auto ca_pool = [&](int j) {
+        const int t = cta + j * G;
+        const int n = t / P, rem = t - n * P;
+        const int ty = rem / args.tiles_x, tx = rem - ty * args.tiles_x;
+        const bool valid = (ty * kTileH + ly) < args.H && (tx * kTileW + lx) < args.W;
+        const float bv = row < 64 ? __ldg(bias + row) : 0.f;
+        const int u_map = lay->u_map;
+        mbar_wait(&acc_full[j], uint32_t(L & 1));
+        tc_fence_after();
+        if (row == 0) TR_STAMP(L, j, 3);
+        if (row < 64) bias_e[row] = bv;
+        if (u_map >= 0 && row == 0) tma_store_wait_read0();   // an earlier u store has read the staging tile
+        named_bar_sync(bar_id, 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[h * 32 + i] : 0.f;
+          if (u_map >= 0) stage_bf16(f, h);
+          red_s[e][q][h * 32 + lane] = lane_transpose_sum32(f, lane);
+        }
+        tc_fence_before();
+        if (u_map >= 0) fence_proxy_async_smem();
+        if (row == 0) TR_STAMP(L, j, 12);
+        named_bar_sync(bar_id, 128);
+        if (row < 64) {
+          const float s = (red_s[e][0][row] + red_s[e][1][row]) + (red_s[e][2][row] + red_s[e][3][row]);
+          args.pool_partial[(size_t(lay->ca_slot & 1) * T + t) * 64 + row] = s;
+          __threadfence();
+        }
+        if (u_map >= 0 && row == 0) {
+          tma_store_4d(args.out_maps + u_map, stg, 0, tx * kTileW, ty * kTileH, n);
+          tma_store_commit();
+        }
+        named_bar_sync(bar_id, 128);
+        if (row == 0) { red_release_add_s32(args.pool_cnt + n, 1); TR_STAMP(L, j, 4); }
+      };
+
+      // ---------------------------------------------------------------- phase 2: x + u*y from the same accumulator
+      auto ca_apply = [&](int j) {
+        const int t = cta + j * G;
+        const int n = t / P, rem = t - n * P;
+        const int ty = rem / args.tiles_x, tx = rem - ty * args.tiles_x;
+        mbar_wait(&y_full[j], uint32_t(ca_seen & 1));
+        if (row == 0) TR_STAMP(L, j, 14);
+        if (lay->u_map >= 0) {
+          if (row == 0) tma_store_wait_read0();   // the u store has read the staging tile
+          named_bar_sync(bar_id, 128);
+        }
+        const float* yv = y_s[j];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32], s[32];
+          float f[32];
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            f[i] = fmaf(__uint_as_float(v[i]) + bias_e[h * 32 + i], yv[h * 32 + i], __uint_as_float(s[i]));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
+          tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), s);
+          stage_bf16(f, h);
+        }
+        tmem_st_wait();
+        if (row == 0) TR_STAMP(L, j, 9);
+        finish_tile(j, t, n, ty, tx);
+      };
+
+      if (kind != kTrunkCA) {
+        for (int j = e; j < my_k; j += 2) plain(j);
+      } else {
+        if (args.interleave) {
+          for (int j = e; j < my_k; j += 2) { ca_pool(j); ca_apply(j); }
+        } else {
+          for (int j = e; j < my_k; j += 2) ca_pool(j);
+          for (int j = e; j < my_k; j += 2) ca_apply(j);
+        }
+        ++ca_seen;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+#undef TR_STAMP
+}
+
+#endif  // RB_TRUNK_KERNEL_IMPL
+
+}  // namespace rb
