@@ -6,7 +6,7 @@
 namespace rb {
 
 extern long long* g_debug_timeline;
-int g_trunk_store_mode = 0;
+int g_trunk_sync_mode = 8;   // release store of the tile epoch (needed: see DESIGN.md trunk protocol)
 int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
 
 static size_t al(size_t v) { return (v + 1023) / 1024 * 1024; }
@@ -23,7 +23,7 @@ size_t trunk_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int 
   const size_t P = size_t((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
   const size_t T = size_t(N) * P;
   return al(size_t(n_layers) * sizeof(TrunkLayer)) + al(size_t(n_in_maps) * sizeof(CUtensorMap)) +
-         al(size_t(n_out_maps) * sizeof(CUtensorMap)) + al((T + N) * sizeof(int)) + al(2 * T * 64 * sizeof(float));
+         al(size_t(n_out_maps) * sizeof(CUtensorMap)) + al(T * sizeof(int) + 2 * T * 64 * sizeof(unsigned long long));
 }
 
 int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* w_base, const float* s_init,
@@ -55,12 +55,11 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
   plan->layers_dev = reinterpret_cast<TrunkLayer*>(p); p += al(plan->layers.size() * sizeof(TrunkLayer));
   plan->in_maps_dev = reinterpret_cast<CUtensorMap*>(p); p += al(plan->in_bufs.size() * sizeof(CUtensorMap));
   plan->out_maps_dev = reinterpret_cast<CUtensorMap*>(p); p += al(plan->out_bufs.size() * sizeof(CUtensorMap));
-  plan->flags_dev = p;
-  plan->flags_bytes = (size_t(a.T) + N) * sizeof(int);
+  plan->flags_dev = p;   // [T] tile epochs, then the tagged pool partials: one memset per launch clears both
+  const size_t ready_bytes = (size_t(a.T) * sizeof(int) + 15) / 16 * 16;
+  plan->flags_bytes = ready_bytes + size_t(2) * a.T * 64 * sizeof(unsigned long long);
   a.ready = reinterpret_cast<int*>(p);
-  a.pool_cnt = a.ready + a.T;
-  p += al(plan->flags_bytes);
-  a.pool_partial = reinterpret_cast<float*>(p);
+  a.pool_partial = reinterpret_cast<unsigned long long*>(p + ready_bytes);
   a.layers = plan->layers_dev;
   a.in_maps = plan->in_maps_dev;
   a.out_maps = plan->out_maps_dev;
@@ -90,7 +89,6 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
     TrunkLayer& l = plan->layers[i];
     const TrunkLayerParams& lp = plan->lparams[i];
     l.bias = params[lp.bias];
-    l.out_bf16 = plan->out_bufs[l.out_map];
     if (lp.w1 >= 0) { l.w1 = params[lp.w1]; l.b1 = params[lp.b1]; l.w2 = params[lp.w2]; l.b2 = params[lp.b2]; }
   }
   if (plan->uploaded.size() != plan->layers.size() ||
@@ -112,7 +110,7 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
   }
   a.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
   a.dbg_layers = g_trunk_dbg_layers;
-  a.store_mode = g_trunk_store_mode;
+  a.sync_mode = g_trunk_sync_mode;
   trunk_pipe_kernel<<<plan->grid, kTrunkThreads, kTrunkSmemBytes, s>>>(plan->w_map, a);
   return check_launch("trunk_pipe");
 }
@@ -121,5 +119,5 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
 
 extern "C" {
 int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
-int rumpy_debug_set_trunk_store_mode(int mode) { rb::g_trunk_store_mode = mode; return 0; }
+int rumpy_debug_set_trunk_sync_mode(int mode) { rb::g_trunk_sync_mode = mode; return 0; }
 }

@@ -72,13 +72,13 @@ def timeline(net, xshape, layers=12):
     lib.rumpy_debug_set_timeline(None)
     t = buf.cpu().numpy().reshape(148, layers, 2, 16)
     names = ['deps_ok', 'mma_start', 'mma_commit', 'epi_start', 'pool_done', 'y_ready', 'published', '-', 'bias_bar', 'staged',
-             'store_go', 'store_done', 'pool_red', 'cnt_seen', 'y_seen', '-']
+             'store_go', 'store_done', 'pool_red', 'cnt_seen', 'y_seen', 'mean_ok']
     for cta in (0,):
         base = t[cta, 0, 0, 0]
         print(f'--- CTA {cta}: cycles since layer-0 tile-0 deps_ok')
         for L in range(layers):
             for j in range(2):
-                row = ' '.join(f'{names[s]}={int(t[cta, L, j, s] - base) if t[cta, L, j, s] else -1:>7}' for s in (0, 1, 2, 3, 8, 12, 4, 13, 5, 14, 9, 10, 11, 6))
+                row = ' '.join(f'{names[s]}={int(t[cta, L, j, s] - base) if t[cta, L, j, s] else -1:>7}' for s in (0, 1, 2, 3, 8, 12, 4, 13, 15, 5, 14, 9, 10, 11, 6)) + f' passes={int(t[cta, L, j, 7])}'
                 print(f'  L{L:02d} j{j}: {row}')
     per_layer = (t[:, layers - 1, 0, 1] - t[:, 1, 0, 1]) / float(layers - 2)
     print(f'median cycles per layer (mma_start to mma_start, tile 0): {np.median(per_layer[per_layer > 0]):.0f}')
@@ -102,12 +102,28 @@ if __name__ == '__main__':
         compare('RCAN 16x64x64', build('rcan'), (16, 3, 64, 64), time_it=True)
     if 'edsr' in which:
         compare('EDSR-baseline 16x48x48', build('edsr'), (16, 3, 48, 48), time_it=True, flop_per_px=3966336)
+    if 'syncmodes' in which:
+        net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
+        eng = net.native_engine()
+        lib.rumpy_debug_set_trunk(0)
+        with torch.no_grad():
+            ref = eng.forward(x).clone()
+        lib.rumpy_debug_set_trunk(1)
+        for mode in (15, 0, 8, 4, 12, 1, 2, 3, 9):
+            lib.rumpy_debug_set_trunk_sync_mode(mode)
+            with torch.no_grad():
+                outs = [eng.forward(x).clone() for _ in range(6)]
+                torch.cuda.synchronize()
+                ms = timeit(lambda: eng.forward(x), iters=10, warm=2)
+            det = all(bool((o == outs[0]).all()) for o in outs)
+            print(f'sync_mode {mode:2d}: deterministic {det}, max diff vs per-layer '
+                  f'{max((o - ref).abs().max().item() for o in outs):.3e}, eager {ms:.3f} ms', flush=True)
+        lib.rumpy_debug_set_trunk_sync_mode(8)
     for w in which:
-        if w.startswith('store'):
-            lib.rumpy_debug_set_trunk_store_mode(int(w[5:]))
-            print('store_mode', int(w[5:]))
+        if w.startswith('sync='):
+            lib.rumpy_debug_set_trunk_sync_mode(int(w[5:])); print('sync_mode', w[5:])
     if 'timeline' in which:
-        timeline(build('rcan'), (16, 3, 48, 48), layers=8)
+        timeline(build('rcan'), (16, 3, 48, 48), layers=6)
     if 'time2' in which:
         net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
         with torch.no_grad():
