@@ -10,6 +10,7 @@
 #include "conv3x3_tc.cuh"
 #include "conv3x3_ca.cuh"
 #include "trunk_pipe.cuh"
+#include "trunk_cluster.cuh"
 #include <vector>
 
 namespace rb {
@@ -97,6 +98,11 @@ struct TrunkPlan {
   void* flags_dev = nullptr;
   size_t flags_bytes = 0;
   bool maps_uploaded = false;
+  // one-cluster-per-image variant (trunk_cluster.cuh), chosen when the image fits a cluster's shared memory
+  bool cluster = false;
+  ClusterArgs cargs;
+  int cluster_size = 0;
+  size_t cluster_smem = 0;
 };
 bool trunk_supported(int N, int H, int W, int C, int Cr);
 // device bytes needed next to the activations: layer table, tensor maps, flags, pool partials

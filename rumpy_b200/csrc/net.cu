@@ -35,6 +35,7 @@ struct CAW { int w1, b1, w2, b2; };
 enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
 
 extern int g_use_fused_ca;
+extern int g_use_cluster;
 int g_use_trunk = 1;   // whole 64-channel body in the persistent dataflow kernel (trunk_pipe.cuh) when the shape fits
 
 struct Op {
@@ -622,12 +623,12 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
 
 static int ensure_plan(Net* n, const void* packed, void* workspace, int N, int H, int W, int training) {
   if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
-      n->p_training != training || n->p_trunk != g_use_trunk) {
+      n->p_training != training || n->p_trunk != g_use_trunk + 2 * g_use_cluster) {
     size_t bytes = 0;
     n->plan_packed = nullptr;
     if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
     n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
-    n->p_trunk = g_use_trunk;
+    n->p_trunk = g_use_trunk + 2 * g_use_cluster;
   }
   return RUMPY_OK;
 }

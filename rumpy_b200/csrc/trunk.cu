@@ -6,6 +6,7 @@
 namespace rb {
 
 extern long long* g_debug_timeline;
+int g_use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
 int g_trunk_sync_mode = 8;   // release store of the tile epoch (needed: see DESIGN.md trunk protocol)
 int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
 
@@ -64,6 +65,53 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
   a.in_maps = plan->in_maps_dev;
   a.out_maps = plan->out_maps_dev;
   if (int e = make_map_weight_layers(&plan->w_map, w_base, a.n_layers)) return e;
+  // ---- one cluster per image?  pick the decomposition with the fewest tiles per CTA that keeps all N clusters
+  // co-resident (clusters are independent, so this is a performance condition, not a correctness one)
+  plan->cluster = false;
+  if (g_use_cluster) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(trunk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+      attr_set = true;
+    }
+    int best_tiles = 99, best_perim = 1 << 30;
+    for (int th = 1; th <= 4; ++th)
+      for (int tw = 1; th * tw <= kTrunkMaxK; ++tw) {
+        const int cy = (H + kClusterTileH * th - 1) / (kClusterTileH * th);
+        const int cx = (W + kClusterTileW * tw - 1) / (kClusterTileW * tw);
+        const int C = cx * cy;
+        if (C > 8) continue;
+        const size_t smem = cluster_smem_bytes(th, tw, C);
+        if (smem > 227 * 1024 - 4096) continue;
+        const int perim = kClusterTileH * th + kClusterTileW * tw;
+        if (th * tw > best_tiles || (th * tw == best_tiles && perim >= best_perim)) continue;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int active = 0;
+        if (cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel, &cfg) != cudaSuccess) {
+          (void)cudaGetLastError();
+          continue;
+        }
+        if (active < N) continue;
+        best_tiles = th * tw; best_perim = perim;
+        plan->cluster = true;
+        plan->cluster_size = C;
+        plan->cluster_smem = smem;
+        ClusterArgs& c = plan->cargs;
+        memset(&c, 0, sizeof(c));
+        c.layers = plan->layers_dev;
+        c.s_init = s_init;
+        c.x_init = static_cast<const __nv_bfloat16*>(plan->in_bufs.front());
+        c.out_bf16 = static_cast<__nv_bfloat16*>(plan->out_bufs.back());
+        c.n_layers = a.n_layers; c.N = N; c.H = H; c.W = W; c.cx = cx; c.cy = cy; c.th = th; c.tw = tw; c.cr = Cr;
+        c.inv_hw = a.inv_hw;
+        for (const TrunkLayer& l : plan->layers) c.n_ca += l.kind == kTrunkCA ? 1 : 0;
+      }
+  }
   plan->uploaded.clear();
   plan->maps_uploaded = false;
   return RUMPY_OK;
@@ -99,6 +147,21 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
       return set_error(RUMPY_ERR_CUDA, "trunk: layer table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaStreamSynchronize(s);
   }
+  if (plan->cluster) {
+    ClusterArgs& c = plan->cargs;
+    c.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
+    c.dbg_layers = g_trunk_dbg_layers;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c.N * plan->cluster_size); cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = plan->cluster_smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = plan->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, trunk_cluster_kernel, plan->w_map, c);
+    if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "trunk_cluster launch: %s", cudaGetErrorString(e));
+    return RUMPY_OK;
+  }
   if (cudaMemsetAsync(plan->flags_dev, 0, plan->flags_bytes, s) != cudaSuccess)
     return set_error(RUMPY_ERR_CUDA, "trunk: flag reset failed: %s", cudaGetErrorString(cudaGetLastError()));
   static bool attr_set = false;
@@ -120,4 +183,5 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
 extern "C" {
 int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
 int rumpy_debug_set_trunk_sync_mode(int mode) { rb::g_trunk_sync_mode = mode; return 0; }
+int rumpy_debug_set_trunk_cluster(int on) { rb::g_use_cluster = on; return 0; }
 }

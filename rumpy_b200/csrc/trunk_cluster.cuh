@@ -1,0 +1,462 @@
+// The 64-channel residual trunk with ONE THREAD-BLOCK CLUSTER PER IMAGE: activations never leave shared memory.
+//
+// Same layer program and same arithmetic as trunk_pipe.cuh (it replaces the same reference call sites:
+// common.py:6-9, architectures.py:41-44 / 81-84 / 121-124 / 172-174, common.py:71-75), different machine mapping,
+// used when a whole image fits the shared memory of one cluster (e.g. BASELINE configs[1]: 48x48 -> 6 CTAs):
+//   * CTA `rank` of the cluster owns a fixed rectangle of the image (th x tw tiles of 16 rows x 8 pixels) and keeps
+//     its bf16 activations -- plus a one-pixel halo -- in shared memory, in a channel-planar, UNSWIZZLED layout:
+//     8 planes (16 bytes = 8 channels each) of [rows+2][cols+2] pixels.  In that layout the tcgen05 A operand of
+//     tap (ky,kx) is the SAME descriptor with its start address moved by (ky*pitch + kx)*16 bytes (SBO = row pitch,
+//     LBO = plane stride): no TMA load, no im2col, no per-tap copy -- the conv reads the resident tensor in place;
+//   * an epilogue thread owns one pixel: it writes the pixel's 8 chunks into the CTA's own output buffer and, for
+//     pixels on the rectangle's edge, straight into the halo cells of the neighbouring CTAs through distributed
+//     shared memory (st.shared::cluster), then arrives (release.cluster) on the neighbour's mbarrier.  A CTA starts
+//     layer L+1 when its own tiles and every halo pixel it is owed have arrived: no global memory, no fences;
+//   * the channel-attention pool is exchanged the same way: per-tile channel sums are pushed into every CTA of the
+//     cluster, each CTA reduces them in a fixed order and computes y itself;
+//   * fp32 residual stream + accumulators live in TMEM, weights stream through one 72 KB buffer in kx thirds (as
+//     in trunk_pipe.cuh).
+// Warp roles (320 threads): 0-3 epilogue group 0 | 4-7 epilogue group 1 | 8 MMA issuer | 9 weight producer.
+#pragma once
+#include "trunk_pipe.cuh"
+
+namespace rb {
+
+struct ClusterArgs {
+  const TrunkLayer* layers;
+  const float* s_init;             // fp32 NHWC: initial residual stream (head conv output)
+  const __nv_bfloat16* x_init;     // bf16 NHWC: operand of layer 0 (head conv output)
+  __nv_bfloat16* out_bf16;         // bf16 NHWC: output of the last layer
+  long long* dbg;                  // optional timeline [grid][dbg_layers][16]
+  int n_layers, n_ca, N, H, W, cx, cy, th, tw, cr, dbg_layers;   // n_ca = number of kTrunkCA layers
+  float inv_hw;
+};
+
+constexpr int kClusterThreads = 320;
+constexpr int kClusterTileH = 16, kClusterTileW = 8;
+
+__host__ __device__ inline size_t cluster_buf_bytes(int th, int tw) {
+  return size_t(8) * (kClusterTileH * th + 2) * (kClusterTileW * tw + 2) * 16;
+}
+// dynamic smem: [weights 72 KB | buffer 0 | buffer 1 | pool slots 2 x (C * tiles) x 64 floats]
+__host__ __device__ inline size_t cluster_smem_bytes(int th, int tw, int C) {
+  return 1024 + kTrunkWBytes + 2 * cluster_buf_bytes(th, tw) + size_t(2) * C * th * tw * 64 * sizeof(float);
+}
+
+#ifdef RB_TRUNK_KERNEL_IMPL
+
+__global__ void __launch_bounds__(kClusterThreads, 1)
+trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t w_full[3];
+  __shared__ __align__(8) uint64_t w_empty[3];
+  __shared__ __align__(8) uint64_t acc_full[kTrunkMaxK];
+  __shared__ __align__(8) uint64_t in_full[2];
+  __shared__ __align__(8) uint64_t pool_full[2];
+  __shared__ uint32_t tmem_base_s, halo_bytes_s;
+  __shared__ __align__(16) float y_s[kTrunkMaxK][64];
+  __shared__ float bias_s[2][64], red_s[2][4][64];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarpMma = 8, kWarpW = 9;
+  const int n_layers = args.n_layers;
+  const int th = args.th, tw = args.tw, n_tiles = th * tw;
+  const int C = args.cx * args.cy;
+  const int rank = int(cluster_ctarank());
+  const int n = blockIdx.x / C;                     // image of this cluster
+  const int ry = rank / args.cx, rx = rank - ry * args.cx;
+  const int RH = kClusterTileH * th, RW = kClusterTileW * tw;
+  const int PR = RH + 2, PP = RW + 2;
+  const uint32_t plane = uint32_t(PR) * PP * 16;    // bytes per 8-channel plane
+  const uint32_t buf_bytes = 8 * plane;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* buf0 = smem + kTrunkWBytes;
+  float* pool_s = reinterpret_cast<float*>(buf0 + 2 * buf_bytes);   // [2][C * n_tiles][64]
+  const int pool_slots = C * n_tiles;
+
+#define CL_STAMP(L_, slot_)                                                                              \
+  do {                                                                                                   \
+    if (args.dbg && (L_) < args.dbg_layers)                                                              \
+      args.dbg[(size_t(blockIdx.x) * args.dbg_layers + (L_)) * 16 + (slot_)] = clock64();                \
+  } while (0)
+
+  // ---- zero both activation buffers (halo cells outside the image must read as the conv's zero padding)
+  for (uint32_t i = threadIdx.x * 16; i < 2 * buf_bytes; i += kClusterThreads * 16)
+    *reinterpret_cast<uint4*>(buf0 + i) = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    // halo pixels this CTA is owed per layer: the halo cells that lie inside the image (each has one owner)
+    int halo = 0;
+    for (int hy = 0; hy < PR; ++hy)
+      for (int hx = 0; hx < PP; ++hx) {
+        if (hy != 0 && hy != PR - 1 && hx != 0 && hx != PP - 1) continue;
+        const int y = ry * RH + hy - 1, x = rx * RW + hx - 1;
+        halo += (y >= 0 && y < args.H && x >= 0 && x < args.W) ? 1 : 0;
+      }
+    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < kTrunkMaxK; ++i) mbar_init(&acc_full[i], 1);
+    // in_full: one arrival per own tile + the arming arrival; the halo pixels complete transaction bytes.
+    // Both parities are armed here for layers 0 / 1 (CA layers 0 / 1); later phases are re-armed by their consumer.
+    halo_bytes_s = uint32_t(halo) * 128u;
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_full[i], uint32_t(n_tiles + 1));
+      mbar_init(&pool_full[i], 1);
+    }
+    fence_mbar_init();
+    for (int i = 0; i < 2; ++i) {
+      mbar_expect_tx(&in_full[i], uint32_t(halo) * 128u);
+      mbar_expect_tx(&pool_full[i], uint32_t(pool_slots) * 64u * 4u);
+    }
+  }
+  if (warp == kWarpW && lane == 0) tma_prefetch_desc(&w_map);
+  if (warp == kWarpMma) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();   // every CTA's buffers are zeroed and its barriers initialised before any remote access
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == kWarpMma) {
+    // ===================================================================== MMA issuer
+    constexpr uint32_t kIdesc = make_idesc_bf16(128, 64);
+    const uint32_t halo_bytes = halo_bytes_s;
+    // descriptors: everything but the 14-bit start-address field (16-byte units) is constant for the whole kernel
+    const uint64_t adesc0 = make_smem_desc(0, plane, uint32_t(PP) * 16, 0);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(w_s), 16, 1024, kLayoutSw128);
+    const uint32_t kstep = (2 * plane) >> 4;   // K = 16 channels = two planes
+    for (int L = 0; L < n_layers; ++L) {
+      // own tiles of layer L-1 and every halo pixel owed by the neighbours have landed in buffer L&1
+      mbar_wait_cluster(&in_full[L & 1], uint32_t(L >> 1) & 1u);
+      if (lane == 0 && L + 2 < n_layers) mbar_expect_tx(&in_full[L & 1], halo_bytes);   // arm layer L+2's phase
+      fence_proxy_async_smem();   // generic-proxy writes of the epilogue threads -> async-proxy (tensor core) reads
+      tc_fence_after();
+      if (lane == 0) CL_STAMP(L, 0);
+      const uint32_t abuf16 = (smem_u32(buf0 + (L & 1) * buf_bytes) & 0x3FFFF) >> 4;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int ta = j / tw, tb = j - ta * tw;
+        const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
+        const uint32_t tile16 = abuf16 + uint32_t(kClusterTileH * ta * PP + kClusterTileW * tb);
+        for (int kx = 0; kx < 3; ++kx) {
+          if (j == 0) { mbar_wait(&w_full[kx], uint32_t(L & 1)); tc_fence_after(); }
+          if (elect_one()) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              // tap (ky,kx) of tile (ta,tb): the resident plane, start moved by whole pixels
+              const uint64_t adesc = adesc0 + uint64_t(tile16 + uint32_t(ky * PP + kx));
+              const uint64_t bdesc = bdesc0 + uint64_t(((kx * 3 + ky) * 8192) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)   // K = 16 channels = planes 2k, 2k+1 (LBO = plane stride)
+                umma_bf16(d_tmem, adesc + uint64_t(k * kstep), bdesc + uint64_t(2 * k), kIdesc, (kx | ky | k) != 0);
+            }
+            if (j == n_tiles - 1) umma_commit(&w_empty[kx]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit(&acc_full[j]);
+        __syncwarp();
+      }
+      if (lane == 0) CL_STAMP(L, 1);
+    }
+  } else if (warp == kWarpW) {
+    // ===================================================================== weight producer (three kx thirds)
+    for (int L = 0; L < n_layers; ++L) {
+      for (int kx = 0; kx < 3; ++kx) {
+        mbar_wait(&w_empty[kx], uint32_t(L & 1) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&w_full[kx], kTrunkWThird);
+          tma_load_4d(w_s + kx * kTrunkWThird, &w_map, &w_full[kx], 0, 0, kx * 3, L);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================== epilogue groups (2 x 128 threads)
+    const int e = warp >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;           // pixel of the tile == TMEM lane == thread index in the group
+    const int ly = row >> 3, lx = row & 7;   // 16 rows x 8 pixels
+    const uint32_t bar_id = 1u + uint32_t(e);
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+    float* bias_e = bias_s[e];
+
+    // One pixel's 64 bf16 channels (8 chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
+    // `par` selects the destination buffer AND the mbarrier the destination CTA waits on.
+    auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[8]) {
+      uint8_t* ob = buf0 + par * buf_bytes;
+      const uint32_t cell = uint32_t((qy + 1) * PP + qx + 1) * 16;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
+      if (!valid) return;
+      const int dyv = qy == 0 ? -1 : (qy == RH - 1 ? 1 : 0);
+      const int dxv = qx == 0 ? -1 : (qx == RW - 1 ? 1 : 0);
+      if (dyv == 0 && dxv == 0) return;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int dy = k == 1 ? 0 : dyv, dx = k == 0 ? 0 : dxv;   // (dy,0), (0,dx), (dy,dx)
+        if ((k == 0 && dyv == 0) || (k == 1 && dxv == 0) || (k == 2 && (dyv == 0 || dxv == 0))) continue;
+        const int nry = ry + dy, nrx = rx + dx;
+        if (nry < 0 || nry >= args.cy || nrx < 0 || nrx >= args.cx) continue;
+        const uint32_t drank = uint32_t(nry * args.cx + nrx);
+        const uint32_t rcell = uint32_t((qy + 1 - dy * RH) * PP + (qx + 1 - dx * RW)) * 16;
+        const uint32_t raddr = mapa_u32(smem_u32(ob) + rcell, drank);
+        const uint32_t rbar = mapa_u32(smem_u32(&in_full[par]), drank);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st_async_v4(raddr + c * plane, ch[c], rbar);   // 8 x 16 B = the pixel's 128 B
+      }
+    };
+    // every thread of the group has written its pixel of tile j: one local arrival for the tile
+    auto tile_done = [&](int par) {
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 128);
+      if (row == 0) mbar_arrive(&in_full[par]);
+    };
+
+    // ---- residual stream (fp32 -> TMEM) and the layer-0 operand (bf16 -> buffer 0 + neighbours' halos)
+    for (int j = e; j < n_tiles; j += 2) {
+      const int ta = j / tw, tb = j - ta * tw;
+      const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
+      const int y = ry * RH + qy, x = rx * RW + qx;
+      const bool valid = y < args.H && x < args.W;
+      const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) f = __ldg(reinterpret_cast<const float4*>(args.s_init + pix) + h * 8 + c4);
+          v[c4 * 4 + 0] = __float_as_uint(f.x); v[c4 * 4 + 1] = __float_as_uint(f.y);
+          v[c4 * 4 + 2] = __float_as_uint(f.z); v[c4 * 4 + 3] = __float_as_uint(f.w);
+        }
+        tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), v);
+      }
+      uint4 ch[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        ch[c] = valid ? __ldg(reinterpret_cast<const uint4*>(args.x_init + pix) + c) : make_uint4(0, 0, 0, 0);
+      write_pixel(0, qy, qx, valid, ch);
+      tile_done(0);
+    }
+    tmem_st_wait();
+
+    int ca_seen = 0;
+    for (int L = 0; L < n_layers; ++L) {
+      const TrunkLayer* lay = args.layers + L;
+      const int kind = lay->kind;
+      const float* bias = lay->bias;
+      const int par_out = (L + 1) & 1;
+      const bool last = L == n_layers - 1;
+
+      // 64 fp32 results of this thread's pixel (two halves) -> bf16 chunks -> buffer / halos (or global, last layer)
+      auto emit = [&](int qy, int qx, bool valid, size_t pix, const uint4 (&ch)[8]) {
+        if (last) {
+          if (valid) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *(reinterpret_cast<uint4*>(args.out_bf16 + pix) + c) = ch[c];
+          }
+        } else {
+          write_pixel(par_out, qy, qx, valid, ch);
+        }
+      };
+      auto pack_half = [&](const float (&f)[32], uint4 (&ch)[8], int h, bool valid) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          ch[h * 4 + c] = valid ? make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
+                                             pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]))
+                                : make_uint4(0, 0, 0, 0);
+      };
+
+      // ---------------------------------------------------------------- conv + bias (+ReLU | + residual)
+      auto plain = [&](int j) {
+        const int ta = j / tw, tb = j - ta * tw;
+        const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
+        const int y = ry * RH + qy, x = rx * RW + qx;
+        const bool valid = y < args.H && x < args.W;
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
+        const float bv = row < 64 ? __ldg(bias + row) : 0.f;
+        const float* res = lay->res_f32;
+        float* outf = lay->out_f32;
+        const float alpha = lay->alpha;
+        const int update_s = lay->update_s;
+        mbar_wait(&acc_full[j], uint32_t(L & 1));
+        tc_fence_after();
+        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
+        if (row < 64) bias_e[row] = bv;
+        named_bar_sync(bar_id, 128);
+        uint4 ch[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          if (kind == kTrunkRelu) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[h * 32 + i], 0.f);
+          } else {
+            if (res != nullptr) {
+              tmem_ld_wait();
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4) {
+                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) r = *reinterpret_cast<const float4*>(res + pix + h * 32 + c4 * 4);
+                f[c4 * 4 + 0] = r.x; f[c4 * 4 + 1] = r.y; f[c4 * 4 + 2] = r.z; f[c4 * 4 + 3] = r.w;
+              }
+            } else {
+              uint32_t s[32];
+              tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[h * 32 + i]) * alpha + f[i];
+            if (update_s) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
+              tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), v);
+            }
+            if (outf != nullptr && valid) {
+#pragma unroll
+              for (int c4 = 0; c4 < 8; ++c4)
+                *reinterpret_cast<float4*>(outf + pix + h * 32 + c4 * 4) =
+                    make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
+            }
+          }
+          pack_half(f, ch, h, valid);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        emit(qy, qx, valid, pix, ch);
+        if (!last) tile_done(par_out); else named_bar_sync(bar_id, 128);
+        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
+      };
+
+      // ---------------------------------------------------------------- channel attention, phase 1: pool
+      const int cpar = ca_seen & 1;
+      auto ca_pool = [&](int j) {
+        const int ta = j / tw, tb = j - ta * tw;
+        const int y = ry * RH + kClusterTileH * ta + ly, x = rx * RW + kClusterTileW * tb + lx;
+        const bool valid = y < args.H && x < args.W;
+        const float bv = row < 64 ? __ldg(bias + row) : 0.f;
+        mbar_wait(&acc_full[j], uint32_t(L & 1));
+        tc_fence_after();
+        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
+        if (row < 64) bias_e[row] = bv;
+        named_bar_sync(bar_id, 128);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          float f[32];
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[h * 32 + i] : 0.f;
+          red_s[e][q][h * 32 + lane] = lane_transpose_sum32(f, lane);
+        }
+        tc_fence_before();
+        named_bar_sync(bar_id, 128);
+        if (row < 64) {
+          // this tile's channel sum -> slot (rank, j) of EVERY CTA of the cluster (fixed slot => fixed sum order)
+          const float s = (red_s[e][0][row] + red_s[e][1][row]) + (red_s[e][2][row] + red_s[e][3][row]);
+          const uint32_t slot = smem_u32(pool_s + (size_t(cpar) * pool_slots + rank * n_tiles + j) * 64 + row);
+          const uint32_t pbar = smem_u32(&pool_full[cpar]);
+          for (int d = 0; d < C; ++d) st_async_b32(mapa_u32(slot, uint32_t(d)), __float_as_uint(s), mapa_u32(pbar, uint32_t(d)));
+        }
+        named_bar_sync(bar_id, 128);   // red_s is free for the group's next tile
+      };
+
+      // ---------------------------------------------------------------- phase 2: y, then x + u*y from the same accumulator
+      auto ca_apply = [&](int j) {
+        const int ta = j / tw, tb = j - ta * tw;
+        const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
+        const int y = ry * RH + qy, x = rx * RW + qx;
+        const bool valid = y < args.H && x < args.W;
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
+        const int cr = args.cr;
+        const int c = row & 63, hsel = row >> 6;
+        const float *w1 = lay->w1, *b1 = lay->b1, *w2 = lay->w2;
+        float w1a[4], w1b[4], w2r[4], b1r[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const bool on = h < cr;
+          w1a[h] = on ? __ldg(w1 + h * 64 + lane) : 0.f;
+          w1b[h] = on ? __ldg(w1 + h * 64 + 32 + lane) : 0.f;
+          w2r[h] = on ? __ldg(w2 + c * cr + h) : 0.f;
+          b1r[h] = on ? __ldg(b1 + h) : 0.f;
+        }
+        float yacc = __ldg(lay->b2 + c);
+        mbar_wait_cluster(&pool_full[cpar], uint32_t(ca_seen >> 1) & 1u);   // every tile of the image has pushed
+        if (row == 0 && j == 0 && ca_seen + 2 < args.n_ca)                  // arm this barrier for CA layer +2
+          mbar_expect_tx(&pool_full[cpar], uint32_t(pool_slots) * 64u * 4u);
+        if (row == 0 && j == e) CL_STAMP(L, 4);
+        float ssum = 0.f;
+        const float* ps = pool_s + size_t(cpar) * pool_slots * 64 + c;
+        for (int sl = hsel; sl < pool_slots; sl += 2) ssum += ps[sl * 64];
+        red_s[e][hsel][c] = ssum;
+        named_bar_sync(bar_id, 128);
+        const float m0 = (red_s[e][0][lane] + red_s[e][1][lane]) * args.inv_hw;
+        const float m1 = (red_s[e][0][lane + 32] + red_s[e][1][lane + 32]) * args.inv_hw;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float sdot = w1a[h] * m0 + w1b[h] * m1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+          yacc = fmaf(w2r[h], fmaxf(sdot + b1r[h], 0.f), yacc);
+        }
+        for (int h = 4; h < cr; ++h) {
+          float sdot = __ldg(w1 + h * 64 + lane) * m0 + __ldg(w1 + h * 64 + 32 + lane) * m1;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+          yacc = fmaf(__ldg(w2 + c * cr + h), fmaxf(sdot + __ldg(b1 + h), 0.f), yacc);
+        }
+        if (hsel == 0) y_s[j][c] = 1.f / (1.f + __expf(-yacc));
+        named_bar_sync(bar_id, 128);
+        const float* yv = y_s[j];
+        uint4 ch[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32], s[32];
+          float f[32];
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            f[i] = fmaf(__uint_as_float(v[i]) + bias_e[h * 32 + i], yv[h * 32 + i], __uint_as_float(s[i]));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
+          tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), s);
+          pack_half(f, ch, h, valid);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        emit(qy, qx, valid, pix, ch);
+        if (!last) tile_done(par_out); else named_bar_sync(bar_id, 128);
+        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
+      };
+
+      if (kind != kTrunkCA) {
+        for (int j = e; j < n_tiles; j += 2) plain(j);
+      } else {
+        for (int j = e; j < n_tiles; j += 2) ca_pool(j);
+        for (int j = e; j < n_tiles; j += 2) ca_apply(j);
+        ++ca_seen;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer may still write into its shared memory
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+#undef CL_STAMP
+}
+
+#endif  // RB_TRUNK_KERNEL_IMPL
+
+}  // namespace rb

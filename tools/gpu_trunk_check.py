@@ -33,8 +33,9 @@ def build(kind, **kw):
 def compare(name, net, xshape, time_it=False, flop_per_px=31835520):
     x = torch.from_numpy(recipe.make_input(xshape, seed=8)).to(dev)
     outs = {}
-    for mode in (0, 1):
-        lib.rumpy_debug_set_trunk(mode)
+    for mode, (trunk, cluster) in (('per-layer', (0, 0)), ('trunk-flags', (1, 0)), ('trunk-cluster', (1, 1))):
+        lib.rumpy_debug_set_trunk(trunk)
+        lib.rumpy_debug_set_trunk_cluster(cluster)
         eng = net.native_engine()
         eng._ws.clear(); eng._graphs.clear()
         with torch.no_grad():
@@ -44,16 +45,17 @@ def compare(name, net, xshape, time_it=False, flop_per_px=31835520):
             outs[mode] = o1
             det = bool((o1 == o2).all())
             launches = lib.rumpy_net_num_launches(eng.handle)
-            msg = f'[{name}] trunk={mode}: launches/forward {launches}, deterministic {det}'
+            msg = f'[{name}] {mode}: launches/forward {launches}, deterministic {det}'
             if time_it:
                 ms = timeit(lambda: eng.forward_graphed(x))
                 px = xshape[0] * xshape[2] * xshape[3]
                 msg += f', graph {ms:.3f} ms -> {flop_per_px * px / ms * 1e-9:.1f} TFLOP/s, {px * 16 / ms * 1e-3:.1f} Mpix/s out'
             print(msg, flush=True)
-    d = (outs[0] - outs[1]).abs().max().item()
-    print(f'[{name}] max |trunk - per-layer| = {d:.3e} (out absmax {outs[0].abs().max().item():.3f})', flush=True)
+    for mode in ('trunk-flags', 'trunk-cluster'):
+        d = (outs['per-layer'] - outs[mode]).abs().max().item()
+        print(f'[{name}] max |{mode} - per-layer| = {d:.3e} (out absmax {outs["per-layer"].abs().max().item():.3f})', flush=True)
     lib.rumpy_debug_set_trunk(1)
-    return d
+    lib.rumpy_debug_set_trunk_cluster(1)
 
 
 def timeline(net, xshape, layers=12):
@@ -87,6 +89,7 @@ def timeline(net, xshape, layers=12):
 if __name__ == '__main__':
     which = sys.argv[1:] or ['small', 'rcan2']
     lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
     lib.rumpy_debug_set_trunk_timeline.argtypes = [ctypes.c_int]
     lib.rumpy_debug_set_timeline.argtypes = [ctypes.c_void_p]
     if 'small' in which:
@@ -122,6 +125,27 @@ if __name__ == '__main__':
     for w in which:
         if w.startswith('sync='):
             lib.rumpy_debug_set_trunk_sync_mode(int(w[5:])); print('sync_mode', w[5:])
+    if 'ctimeline' in which:
+        net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
+        eng = net.native_engine()
+        with torch.no_grad():
+            eng.forward(x)
+        layers = 10
+        buf = torch.zeros(148 * layers * 16, dtype=torch.int64, device=dev)
+        lib.rumpy_debug_set_timeline(ctypes.c_void_p(buf.data_ptr()))
+        lib.rumpy_debug_set_trunk_timeline(layers)
+        with torch.no_grad():
+            eng.forward(x)
+        torch.cuda.synchronize()
+        lib.rumpy_debug_set_trunk_timeline(0)
+        lib.rumpy_debug_set_timeline(None)
+        t = buf.cpu().numpy().reshape(148, layers, 16)
+        names = ['in_full', 'mma_issued', 'last_acc', 'last_tile_done', 'pool_full']
+        for cta in (0, 1, 5):
+            base = t[cta, 0, 0]
+            print(f'--- cluster CTA {cta}: cycles since layer-0 in_full')
+            for L in range(layers):
+                print(f'  L{L:02d}: ' + ' '.join(f'{names[s]}={int(t[cta, L, s] - base) if t[cta, L, s] else -1:>7}' for s in range(5)))
     if 'timeline' in which:
         timeline(build('rcan'), (16, 3, 48, 48), layers=6)
     if 'time2' in which:
