@@ -54,8 +54,8 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
   __shared__ __align__(8) uint64_t in_full[2];
   __shared__ __align__(8) uint64_t pool_full[2];
   __shared__ uint32_t tmem_base_s, halo_bytes_s;
-  __shared__ __align__(16) float y_s[kTrunkMaxK][64];
-  __shared__ float bias_s[2][64], red_s[2][4][64];
+  __shared__ __align__(16) float y_s[2][64];
+  __shared__ float bias_s[2][32], red_s[2][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpMma = 8, kWarpW = 9;
@@ -96,11 +96,11 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
       }
     for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < kTrunkMaxK; ++i) mbar_init(&acc_full[i], 1);
-    // in_full: one arrival per own tile + the arming arrival; the halo pixels complete transaction bytes.
+    // in_full: one arrival per epilogue group + the arming arrival; the halo pixels complete transaction bytes.
     // Both parities are armed here for layers 0 / 1 (CA layers 0 / 1); later phases are re-armed by their consumer.
     halo_bytes_s = uint32_t(halo) * 128u;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&in_full[i], uint32_t(n_tiles + 1));
+      mbar_init(&in_full[i], 3);
       mbar_init(&pool_full[i], 1);
     }
     fence_mbar_init();
@@ -171,22 +171,26 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
       }
     }
   } else {
-    // ===================================================================== epilogue groups (2 x 128 threads)
+    // ===================================================================== epilogue: 2 groups x 128 threads
+    // Both groups work on EVERY tile: group e owns channels [32e, 32e+32) of each pixel (balanced for any tile
+    // count, and the exposed epilogue of a layer's last tile is half as long).
     const int e = warp >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;           // pixel of the tile == TMEM lane == thread index in the group
     const int ly = row >> 3, lx = row & 7;   // 16 rows x 8 pixels
     const uint32_t bar_id = 1u + uint32_t(e);
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
-    float* bias_e = bias_s[e];
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(32 * e);
+    const uint32_t plane0 = uint32_t(4 * e) * plane;   // this group's four channel planes
+    float* bias_e = bias_s[e];                // 32 values: channels 32e ..
+    float* y_e = y_s[e];
 
-    // One pixel's 64 bf16 channels (8 chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
-    // `par` selects the destination buffer AND the mbarrier the destination CTA waits on.
-    auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[8]) {
-      uint8_t* ob = buf0 + par * buf_bytes;
+    // One pixel's 32 bf16 channels (4 chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
+    // `par` selects the destination buffer AND the mbarrier whose transaction count the remote bytes complete.
+    auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[4]) {
+      uint8_t* ob = buf0 + par * buf_bytes + plane0;
       const uint32_t cell = uint32_t((qy + 1) * PP + qx + 1) * 16;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
+      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
       if (!valid) return;
       const int dyv = qy == 0 ? -1 : (qy == RH - 1 ? 1 : 0);
       const int dxv = qx == 0 ? -1 : (qx == RW - 1 ? 1 : 0);
@@ -202,69 +206,67 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const uint32_t raddr = mapa_u32(smem_u32(ob) + rcell, drank);
         const uint32_t rbar = mapa_u32(smem_u32(&in_full[par]), drank);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) st_async_v4(raddr + c * plane, ch[c], rbar);   // 8 x 16 B = the pixel's 128 B
+        for (int c = 0; c < 4; ++c) st_async_v4(raddr + c * plane, ch[c], rbar);   // 4 x 16 B = this half pixel
       }
     };
-    // every thread of the group has written its pixel of tile j: one local arrival for the tile
-    auto tile_done = [&](int par) {
+    // every thread of the group has written its half pixels of ALL tiles: one local arrival per group and layer
+    auto group_done = [&](int par) {
       fence_proxy_async_smem();
       named_bar_sync(bar_id, 128);
       if (row == 0) mbar_arrive(&in_full[par]);
     };
 
     // ---- residual stream (fp32 -> TMEM) and the layer-0 operand (bf16 -> buffer 0 + neighbours' halos)
-    for (int j = e; j < n_tiles; j += 2) {
+    for (int j = 0; j < n_tiles; ++j) {
       const int ta = j / tw, tb = j - ta * tw;
       const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
       const int y = ry * RH + qy, x = rx * RW + qx;
       const bool valid = y < args.H && x < args.W;
-      const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
+      const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
+      uint32_t v[32];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) f = __ldg(reinterpret_cast<const float4*>(args.s_init + pix) + h * 8 + c4);
-          v[c4 * 4 + 0] = __float_as_uint(f.x); v[c4 * 4 + 1] = __float_as_uint(f.y);
-          v[c4 * 4 + 2] = __float_as_uint(f.z); v[c4 * 4 + 3] = __float_as_uint(f.w);
-        }
-        tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), v);
+      for (int c4 = 0; c4 < 8; ++c4) {
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) f = __ldg(reinterpret_cast<const float4*>(args.s_init + pix) + c4);
+        v[c4 * 4 + 0] = __float_as_uint(f.x); v[c4 * 4 + 1] = __float_as_uint(f.y);
+        v[c4 * 4 + 2] = __float_as_uint(f.z); v[c4 * 4 + 3] = __float_as_uint(f.w);
       }
-      uint4 ch[8];
+      tmem_st32(lane_addr + uint32_t(j * 64), v);
+      uint4 ch[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
+      for (int c = 0; c < 4; ++c)
         ch[c] = valid ? __ldg(reinterpret_cast<const uint4*>(args.x_init + pix) + c) : make_uint4(0, 0, 0, 0);
       write_pixel(0, qy, qx, valid, ch);
-      tile_done(0);
     }
+    group_done(0);
     tmem_st_wait();
 
     int ca_seen = 0;
     for (int L = 0; L < n_layers; ++L) {
       const TrunkLayer* lay = args.layers + L;
       const int kind = lay->kind;
-      const float* bias = lay->bias;
+      const float* bias = lay->bias + 32 * e;
       const int par_out = (L + 1) & 1;
       const bool last = L == n_layers - 1;
+      if (row < 32) bias_e[row] = __ldg(bias + row);   // the previous layer ended with a group barrier
+      named_bar_sync(bar_id, 128);
 
-      // 64 fp32 results of this thread's pixel (two halves) -> bf16 chunks -> buffer / halos (or global, last layer)
-      auto emit = [&](int qy, int qx, bool valid, size_t pix, const uint4 (&ch)[8]) {
+      // 32 fp32 results of this thread's half pixel -> bf16 chunks -> buffer / halos (or global, last layer)
+      auto emit = [&](int qy, int qx, bool valid, size_t pix, const float (&f)[32]) {
+        uint4 ch[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          ch[c] = valid ? make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
+                                     pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]))
+                        : make_uint4(0, 0, 0, 0);
         if (last) {
           if (valid) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) *(reinterpret_cast<uint4*>(args.out_bf16 + pix) + c) = ch[c];
+            for (int c = 0; c < 4; ++c) *(reinterpret_cast<uint4*>(args.out_bf16 + pix) + c) = ch[c];
           }
         } else {
           write_pixel(par_out, qy, qx, valid, ch);
         }
-      };
-      auto pack_half = [&](const float (&f)[32], uint4 (&ch)[8], int h, bool valid) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          ch[h * 4 + c] = valid ? make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
-                                             pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]))
-                                : make_uint4(0, 0, 0, 0);
       };
 
       // ---------------------------------------------------------------- conv + bias (+ReLU | + residual)
@@ -273,64 +275,55 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
         const int y = ry * RH + qy, x = rx * RW + qx;
         const bool valid = y < args.H && x < args.W;
-        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
-        const float bv = row < 64 ? __ldg(bias + row) : 0.f;
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
         const float* res = lay->res_f32;
         float* outf = lay->out_f32;
         const float alpha = lay->alpha;
         const int update_s = lay->update_s;
         mbar_wait(&acc_full[j], uint32_t(L & 1));
         tc_fence_after();
-        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
-        if (row < 64) bias_e[row] = bv;
-        named_bar_sync(bar_id, 128);
-        uint4 ch[8];
+        if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+        if (kind == kTrunkRelu) {
+          tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          float f[32];
-          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
-          if (kind == kTrunkRelu) {
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[i], 0.f);
+        } else {
+          if (res != nullptr) {
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[h * 32 + i], 0.f);
+            for (int c4 = 0; c4 < 8; ++c4) {
+              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid) r = *reinterpret_cast<const float4*>(res + pix + c4 * 4);
+              f[c4 * 4 + 0] = r.x; f[c4 * 4 + 1] = r.y; f[c4 * 4 + 2] = r.z; f[c4 * 4 + 3] = r.w;
+            }
           } else {
-            if (res != nullptr) {
-              tmem_ld_wait();
+            uint32_t s[32];
+            tmem_ld32(lane_addr + uint32_t(j * 64), s);
+            tmem_ld_wait();
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) r = *reinterpret_cast<const float4*>(res + pix + h * 32 + c4 * 4);
-                f[c4 * 4 + 0] = r.x; f[c4 * 4 + 1] = r.y; f[c4 * 4 + 2] = r.z; f[c4 * 4 + 3] = r.w;
-              }
-            } else {
-              uint32_t s[32];
-              tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[h * 32 + i]) * alpha + f[i];
-            if (update_s) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
-              tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), v);
-            }
-            if (outf != nullptr && valid) {
-#pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4)
-                *reinterpret_cast<float4*>(outf + pix + h * 32 + c4 * 4) =
-                    make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
-            }
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
           }
-          pack_half(f, ch, h, valid);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[i]) * alpha + f[i];
+          if (update_s) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
+            tmem_st32(lane_addr + uint32_t(j * 64), v);
+          }
+          if (outf != nullptr && valid) {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4)
+              *reinterpret_cast<float4*>(outf + pix + c4 * 4) =
+                  make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
+          }
         }
         tmem_st_wait();
         tc_fence_before();
-        emit(qy, qx, valid, pix, ch);
-        if (!last) tile_done(par_out); else named_bar_sync(bar_id, 128);
-        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
+        emit(qy, qx, valid, pix, f);
+        if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
       };
 
       // ---------------------------------------------------------------- channel attention, phase 1: pool
@@ -339,41 +332,34 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const int ta = j / tw, tb = j - ta * tw;
         const int y = ry * RH + kClusterTileH * ta + ly, x = rx * RW + kClusterTileW * tb + lx;
         const bool valid = y < args.H && x < args.W;
-        const float bv = row < 64 ? __ldg(bias + row) : 0.f;
         mbar_wait(&acc_full[j], uint32_t(L & 1));
         tc_fence_after();
-        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
-        if (row < 64) bias_e[row] = bv;
-        named_bar_sync(bar_id, 128);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
+        {
           uint32_t v[32];
           float f[32];
-          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[h * 32 + i] : 0.f;
-          red_s[e][q][h * 32 + lane] = lane_transpose_sum32(f, lane);
+          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[i] : 0.f;
+          red_s[e][q][lane] = lane_transpose_sum32(f, lane);
         }
         tc_fence_before();
         named_bar_sync(bar_id, 128);
-        if (row < 64) {
+        if (row < 32) {
           // this tile's channel sum -> slot (rank, j) of EVERY CTA of the cluster (fixed slot => fixed sum order)
           const float s = (red_s[e][0][row] + red_s[e][1][row]) + (red_s[e][2][row] + red_s[e][3][row]);
-          const uint32_t slot = smem_u32(pool_s + (size_t(cpar) * pool_slots + rank * n_tiles + j) * 64 + row);
+          const uint32_t slot =
+              smem_u32(pool_s + (size_t(cpar) * pool_slots + rank * n_tiles + j) * 64 + 32 * e + row);
           const uint32_t pbar = smem_u32(&pool_full[cpar]);
-          for (int d = 0; d < C; ++d) st_async_b32(mapa_u32(slot, uint32_t(d)), __float_as_uint(s), mapa_u32(pbar, uint32_t(d)));
+          for (int d = 0; d < C; ++d)
+            st_async_b32(mapa_u32(slot, uint32_t(d)), __float_as_uint(s), mapa_u32(pbar, uint32_t(d)));
         }
-        named_bar_sync(bar_id, 128);   // red_s is free for the group's next tile
+        named_bar_sync(bar_id, 128);   // red_s is free for the next tile
       };
 
-      // ---------------------------------------------------------------- phase 2: y, then x + u*y from the same accumulator
-      auto ca_apply = [&](int j) {
-        const int ta = j / tw, tb = j - ta * tw;
-        const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
-        const int y = ry * RH + qy, x = rx * RW + qx;
-        const bool valid = y < args.H && x < args.W;
-        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64;
+      // ---------------------------------------------------------------- y for the image (once per CA layer and group)
+      auto ca_y = [&]() {
         const int cr = args.cr;
         const int c = row & 63, hsel = row >> 6;
         const float *w1 = lay->w1, *b1 = lay->b1, *w2 = lay->w2;
@@ -388,9 +374,11 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         }
         float yacc = __ldg(lay->b2 + c);
         mbar_wait_cluster(&pool_full[cpar], uint32_t(ca_seen >> 1) & 1u);   // every tile of the image has pushed
-        if (row == 0 && j == 0 && ca_seen + 2 < args.n_ca)                  // arm this barrier for CA layer +2
-          mbar_expect_tx(&pool_full[cpar], uint32_t(pool_slots) * 64u * 4u);
-        if (row == 0 && j == e) CL_STAMP(L, 4);
+        if (row == 0 && e == 0) {
+          CL_STAMP(L, 4);
+          if (ca_seen + 2 < args.n_ca)                                     // arm this barrier for CA layer +2
+            mbar_expect_tx(&pool_full[cpar], uint32_t(pool_slots) * 64u * 4u);
+        }
         float ssum = 0.f;
         const float* ps = pool_s + size_t(cpar) * pool_slots * 64 + c;
         for (int sl = hsel; sl < pool_slots; sl += 2) ssum += ps[sl * 64];
@@ -411,39 +399,43 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
           for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
           yacc = fmaf(__ldg(w2 + c * cr + h), fmaxf(sdot + __ldg(b1 + h), 0.f), yacc);
         }
-        if (hsel == 0) y_s[j][c] = 1.f / (1.f + __expf(-yacc));
+        if (hsel == 0) y_e[c] = 1.f / (1.f + __expf(-yacc));
         named_bar_sync(bar_id, 128);
-        const float* yv = y_s[j];
-        uint4 ch[8];
+      };
+
+      // ---------------------------------------------------------------- phase 2: x + u*y from the same accumulator
+      auto ca_apply = [&](int j) {
+        const int ta = j / tw, tb = j - ta * tw;
+        const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
+        const int y = ry * RH + qy, x = rx * RW + qx;
+        const bool valid = y < args.H && x < args.W;
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
+        const float* yv = y_e + 32 * e;
+        uint32_t v[32], s[32];
+        float f[32];
+        tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+        tmem_ld32(lane_addr + uint32_t(j * 64), s);
+        tmem_ld_wait();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32], s[32];
-          float f[32];
-          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
-          tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
-          tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]) + bias_e[i], yv[i], __uint_as_float(s[i]));
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            f[i] = fmaf(__uint_as_float(v[i]) + bias_e[h * 32 + i], yv[h * 32 + i], __uint_as_float(s[i]));
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
-          tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), s);
-          pack_half(f, ch, h, valid);
-        }
+        for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
+        tmem_st32(lane_addr + uint32_t(j * 64), s);
         tmem_st_wait();
         tc_fence_before();
-        emit(qy, qx, valid, pix, ch);
-        if (!last) tile_done(par_out); else named_bar_sync(bar_id, 128);
-        if (row == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
+        emit(qy, qx, valid, pix, f);
+        if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
       };
 
       if (kind != kTrunkCA) {
-        for (int j = e; j < n_tiles; j += 2) plain(j);
+        for (int j = 0; j < n_tiles; ++j) plain(j);
       } else {
-        for (int j = e; j < n_tiles; j += 2) ca_pool(j);
-        for (int j = e; j < n_tiles; j += 2) ca_apply(j);
+        for (int j = 0; j < n_tiles; ++j) ca_pool(j);
+        ca_y();
+        for (int j = 0; j < n_tiles; ++j) ca_apply(j);
         ++ca_seen;
       }
+      if (!last) group_done(par_out); else named_bar_sync(bar_id, 128);
     }
   }
 
