@@ -207,6 +207,44 @@ def conv_kernel_roofline(device, pk):
             'peak_source': pk['source'] + ', burst figure (kernel timed alone)'}
 
 
+def trunk_kernel_roofline(eng, x_dev, flush, pk):
+    """Dominant kernel of the headline forward: the trunk kernel that runs all 411 body convs (64->64, 3x3) with
+    their epilogues.  Timed live with CUDA events recorded by the library right before / after the kernel on the
+    launching stream (eager forwards, L2 flushed before each), best of 5."""
+    lib = eng.lib
+    mode = lib.rumpy_net_trunk_mode(eng.handle)
+    if mode <= 0:
+        return None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); e1.record()
+    torch.cuda.synchronize()
+    lib.rumpy_debug_set_trunk_events(e0.cuda_event, e1.cuda_event)
+    best = None
+    try:
+        with torch.no_grad():
+            for _ in range(5):
+                flush.zero_()
+                eng.forward(x_dev)
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1) * 1e-3
+                best = t if best is None else min(best, t)
+    finally:
+        lib.rumpy_debug_set_trunk_events(None, None)
+    n_convs = 10 * (2 * 20 + 1) + 1
+    flops = n_convs * CONV64_FLOP_PER_PIXEL * BATCH * LR_HW * LR_HW
+    achieved = flops / best * 1e-12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get('trunk_dram_bytes_per_launch')
+    name = {1: 'trunk_pipe_kernel (persistent dataflow, epoch flags)',
+            2: 'trunk_cluster_kernel (one 6-CTA cluster per image, DSMEM halo exchange)'}[mode]
+    return {'bound': 'tensor', 'kernel': name + f': {n_convs} fused conv3x3 64->64 layers + CA + skips, 16x48x48',
+            'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+            'traffic': traffic, 'us_per_launch': best * 1e6, 'flops_per_launch': flops,
+            'peak_source': pk['source'] + ', burst figure (one ~2.5 ms kernel)'}
+
+
 def train_bench(handler_factory, device, rank, world, steps, warmup, barrier):
     """BASELINE.json configs[2]: RCAN x4 training fwd/bwd, L1 loss, Adam 1e-4, 64x64 LR patches, batch 16 per GPU,
     data parallel (NCCL gradient all-reduce).  Returns (ms_per_step max-over-ranks, e2e ms, first loss, last loss)."""
@@ -388,7 +426,10 @@ def run_b200(args, rank, world):
     value = world * OUT_MPIX_PER_STEP / (ms_per_step * 1e-3)
     e2e_value = world * OUT_MPIX_PER_STEP / (e2e_s / args.steps)
     pk = peaks()
-    roof = conv_kernel_roofline(device, pk)
+    roof_conv = conv_kernel_roofline(device, pk)
+    roof = trunk_kernel_roofline(eng, x_dev, flush, pk) if eng is not None else None
+    if roof is None:
+        roof, roof_conv = roof_conv, None
     trunk_tflops = FLOP_PER_LR_PIXEL * BATCH * LR_HW * LR_HW / (ms_per_step * 1e-3) * 1e-12
     cores = os.cpu_count() or 1
     fwd = cpu_forward_fn(cores)
@@ -412,6 +453,8 @@ def run_b200(args, rank, world):
         'cpu_baseline': {'value': OUT_MPIX_PER_STEP / cpu_s, 'unit': 'Mpix/s', 'cores': cores, 'kind': 'port',
                          'sample': f'full batch of {BATCH} patches, median of {cpu_iters} forwards, fp32 torch-CPU'},
     }
+    if roof_conv is not None:
+        line['roofline_per_layer_conv'] = roof_conv    # the stand-alone conv kernel (used for shapes the trunk kernels skip)
     if extra is not None:
         line['extra_configs'] = extra
     if tr is not None:

@@ -124,6 +124,15 @@ int rumpy_net_destroy(void* net);
 int rumpy_net_num_params(void* net);
 int rumpy_net_num_launches(void* net);          /* kernels per forward of the cached plan */
 int rumpy_net_num_launches_backward(void* net); /* kernels per backward of the cached plan */
+/* How the 64-channel body (every default_conv 64->64, CALayer, RCAB / group / global skips:
+ * architectures.py:81-84, 121-124, 172-174; common.py:71-75) of the cached plan is executed:
+ *   0  one kernel per layer (any shape);
+ *   1  ONE persistent tile-stationary dataflow kernel for the whole body (<= 4 tiles per SM): neighbour tiles
+ *      hand over through per-tile epochs in global memory, fp32 residual stream in tensor memory;
+ *   2  one thread-block CLUSTER per image: activations stay in (distributed) shared memory across all layers,
+ *      halos and the channel-attention pool travel by st.async between the CTAs of the cluster.
+ * The mode is picked per (N,H,W) when the plan is built; all three compute the same layer program. */
+int rumpy_net_trunk_mode(void* net);
 long long rumpy_net_packed_bytes(void* net, int training);
 long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training);
 int rumpy_net_pack(void* net, const float* const* params, void* packed, int training, void* stream);

@@ -35,6 +35,7 @@ SIGNATURES = {
     'rumpy_net_num_params': [_vp],
     'rumpy_net_num_launches': [_vp],
     'rumpy_net_num_launches_backward': [_vp],
+    'rumpy_net_trunk_mode': [_vp],
     'rumpy_net_packed_bytes': [_vp, _i],
     'rumpy_net_workspace_bytes': [_vp, _i, _i, _i, _i],
     'rumpy_net_pack': [_vp, _vp, _vp, _i, _vp],
@@ -75,6 +76,11 @@ def load():
         lib.rumpy_debug_set_pdl(0)
     if os.environ.get('RUMPY_B200_CONV2X') == '1':     # experiment: two streaming-B conv CTAs per SM
         lib.rumpy_debug_set_conv2x(1)
+    lib.rumpy_debug_set_trunk_events.argtypes = [_vp, _vp]
+    if os.environ.get('RUMPY_B200_TRUNK') == '0':     # debug switch: one kernel per layer instead of the trunk kernels
+        lib.rumpy_debug_set_trunk(0)
+    if os.environ.get('RUMPY_B200_CLUSTER') == '0':   # debug switch: no cluster-per-image kernel (dataflow kernel only)
+        lib.rumpy_debug_set_trunk_cluster(0)
     if os.environ.get('RUMPY_B200_FUSED_CA') == '1':  # opt-in: conv2 + CALayer + skip in one kernel (conv3x3_ca.cuh)
         lib.rumpy_debug_set_fused_ca(1)
     _lib = lib

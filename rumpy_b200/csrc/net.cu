@@ -671,6 +671,14 @@ int rumpy_net_destroy(void* net) {
 /* kernels enqueued by one forward of the cached plan (0 before the first forward) */
 int rumpy_net_num_launches(void* net) { return net ? int(static_cast<Net*>(net)->ops.size()) : -1; }
 
+/* how the 64-channel body of the cached plan runs: 0 one kernel per layer, 1 persistent dataflow kernel
+ * (trunk_pipe.cuh), 2 one thread-block cluster per image (trunk_cluster.cuh) */
+int rumpy_net_trunk_mode(void* net) {
+  if (!net) return -1;
+  Net* n = static_cast<Net*>(net);
+  return n->trunk ? (n->trunk->cluster ? 2 : 1) : 0;
+}
+
 /* kernels enqueued by one backward of the cached plan (0 when the plan is inference-only) */
 int rumpy_net_num_launches_backward(void* net) {
   if (!net) return -1;

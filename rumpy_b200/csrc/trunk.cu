@@ -8,6 +8,7 @@ namespace rb {
 extern long long* g_debug_timeline;
 int g_use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
 int g_trunk_sync_mode = 8;   // release store of the tile epoch (needed: see DESIGN.md trunk protocol)
+cudaEvent_t g_trunk_ev0 = nullptr, g_trunk_ev1 = nullptr;   // optional: recorded around the trunk kernel (bench)
 int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
 
 static size_t al(size_t v) { return (v + 1023) / 1024 * 1024; }
@@ -158,8 +159,10 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = plan->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
     cudaError_t e = cudaLaunchKernelEx(&cfg, trunk_cluster_kernel, plan->w_map, c);
     if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "trunk_cluster launch: %s", cudaGetErrorString(e));
+    if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
     return RUMPY_OK;
   }
   if (cudaMemsetAsync(plan->flags_dev, 0, plan->flags_bytes, s) != cudaSuccess)
@@ -174,8 +177,11 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
   a.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
   a.dbg_layers = g_trunk_dbg_layers;
   a.sync_mode = g_trunk_sync_mode;
+  if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
   trunk_pipe_kernel<<<plan->grid, kTrunkThreads, kTrunkSmemBytes, s>>>(plan->w_map, a);
-  return check_launch("trunk_pipe");
+  if (int e = check_launch("trunk_pipe")) return e;
+  if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
+  return RUMPY_OK;
 }
 
 }  // namespace rb
@@ -184,4 +190,10 @@ extern "C" {
 int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
 int rumpy_debug_set_trunk_sync_mode(int mode) { rb::g_trunk_sync_mode = mode; return 0; }
 int rumpy_debug_set_trunk_cluster(int on) { rb::g_use_cluster = on; return 0; }
+/* bench hook: CUDA events (cudaEvent_t) recorded right before / after the trunk kernel of every forward; NULL = off */
+int rumpy_debug_set_trunk_events(void* ev_start, void* ev_stop) {
+  rb::g_trunk_ev0 = static_cast<cudaEvent_t>(ev_start);
+  rb::g_trunk_ev1 = static_cast<cudaEvent_t>(ev_stop);
+  return 0;
+}
 }

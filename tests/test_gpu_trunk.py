@@ -1,0 +1,112 @@
+"""GPU tests of the two whole-body kernels (csrc/trunk_pipe.cuh: persistent dataflow kernel; csrc/trunk_cluster.cuh:
+one thread-block cluster per image).  Both must reproduce the per-layer path (same layer program, same arithmetic
+up to fp32 summation order of the channel-attention pool) and stay inside BASELINE.json's tolerance against the
+CPU oracle; both must be bit-reproducible run to run.  Called through the reference-facing module API.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import recipe
+from oracle import sr_torch_cpu
+
+pytestmark = pytest.mark.gpu
+
+MODES = {'per-layer': (0, 0), 'dataflow': (1, 0), 'cluster': (1, 1)}
+
+
+def _dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+def _lib():
+    from rumpy_b200 import _lib
+    lib = _lib.load()
+    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
+    return lib
+
+
+def _net(kind, **kw):
+    from rumpy_b200.SISR.models.advanced.architectures import RCAN, EDSR
+    net = RCAN(**kw) if kind == 'rcan' else EDSR(**kw)
+    spec = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    sd = recipe.make_weights(spec, seed=8)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return net.to(_dev()).eval(), sd
+
+
+def _run_modes(net, x):
+    lib = _lib()
+    outs, modes = {}, {}
+    try:
+        for name, (trunk, cluster) in MODES.items():
+            lib.rumpy_debug_set_trunk(trunk)
+            lib.rumpy_debug_set_trunk_cluster(cluster)
+            eng = net.native_engine()
+            eng._ws.clear()
+            eng._graphs.clear()
+            with torch.no_grad():
+                a = eng.forward(x).clone()
+                b = eng.forward(x).clone()
+            torch.cuda.synchronize()
+            assert bool((a == b).all()), f'{name}: forward is not bit-reproducible'
+            outs[name] = a
+            modes[name] = lib.rumpy_net_trunk_mode(eng.handle)
+    finally:
+        lib.rumpy_debug_set_trunk(1)
+        lib.rumpy_debug_set_trunk_cluster(1)
+    return outs, modes
+
+
+CASES = [
+    # name, kind, ctor kwargs, input shape, expected mode with the cluster kernel allowed
+    ('rcan_2x16x16', 'rcan', dict(n_resgroups=1, n_resblocks=2), (2, 3, 16, 16), 2),
+    ('rcan_ragged_3x20x37', 'rcan', dict(n_resgroups=2, n_resblocks=3), (3, 3, 20, 37), 2),
+    ('rcan_5x64x96_two_slots', 'rcan', dict(n_resgroups=2, n_resblocks=2), (5, 3, 64, 96), None),
+    ('rcan_1x100x200_image_spans_slots', 'rcan', dict(n_resgroups=1, n_resblocks=2), (1, 3, 100, 200), 1),
+    ('rcan_16x48x48_cfg2_shape', 'rcan', dict(n_resgroups=1, n_resblocks=3), (16, 3, 48, 48), 2),
+    ('rcan_16x64x64_cfg3_shape', 'rcan', dict(n_resgroups=1, n_resblocks=2), (16, 3, 64, 64), 1),
+    ('edsr_2x24x24', 'edsr', dict(num_blocks=4), (2, 3, 24, 24), 2),
+]
+
+
+@pytest.mark.parametrize('name,kind,kw,shape,want_mode', CASES, ids=[c[0] for c in CASES])
+def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, want_mode):
+    net, sd = _net(kind, **kw)
+    x = recipe.make_input(shape, seed=8)
+    outs, modes = _run_modes(net, torch.from_numpy(x).to(_dev()))
+    assert modes['per-layer'] == 0 and modes['dataflow'] == 1
+    if want_mode is not None:
+        assert modes['cluster'] == want_mode, f'cluster-allowed plan picked mode {modes["cluster"]}'
+    sdt = {k: torch.from_numpy(v) for k, v in sd.items()}
+    arch, akw = sr_torch_cpu.infer_arch(sdt)
+    ref = sr_torch_cpu.forward(sdt, torch.from_numpy(x), arch, res_scale=0.1, **akw).numpy()
+    scale = max(1.0, float(np.abs(ref).max()))
+    for mode, out in outs.items():
+        err = float(np.abs(out.cpu().numpy() - ref).max())
+        assert err <= 1e-2 * scale, f'{name} [{mode}]: max-abs {err} vs CPU oracle'
+    base = outs['per-layer']
+    for mode in ('dataflow', 'cluster'):
+        d = float((outs[mode] - base).abs().max())
+        assert d <= 5e-3 * scale, f'{name}: {mode} differs from the per-layer path by {d}'
+
+
+def test_full_rcan_cfg2_uses_cluster_kernel_and_matches_oracle():
+    """BASELINE configs[1] (RCAN 10x20x64, 16 x 48x48): the plan must pick the cluster kernel and stay within 1e-2
+    of the CPU oracle on the same seeded input."""
+    net, sd = _net('rcan')
+    x = recipe.make_input((16, 3, 48, 48), seed=8)
+    with torch.no_grad():
+        out = net(torch.from_numpy(x).to(_dev())).cpu().numpy()
+    eng = net.native_engine()
+    assert _lib().rumpy_net_trunk_mode(eng.handle) == 2
+    assert _lib().rumpy_net_num_launches(eng.handle) == 5      # head, trunk, 2 upsampler convs, tail
+    sdt = {k: torch.from_numpy(v) for k, v in sd.items()}
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = sr_torch_cpu.rcan_forward(sdt, torch.from_numpy(x), 10, 20, 4).numpy()
+    err = float(np.abs(out - ref).max())
+    assert err <= 1e-2, f'RCAN cfg2 through the cluster kernel: max-abs {err}'
