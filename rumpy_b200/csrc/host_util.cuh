@@ -108,8 +108,9 @@ bool trunk_supported(int N, int H, int W, int C, int Cr);
 // device bytes needed next to the activations: layer table, tensor maps, flags, pool partials
 size_t trunk_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int n_out_maps);
 // fills args / maps from plan->layers, in_bufs, out_bufs; `dev` = trunk_device_bytes() bytes of device memory
+// allow_cluster: the cluster-per-image kernel ping-pongs two resident buffers, so it serves inference plans only
 int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* w_base, const float* s_init,
-                      void* dev);
+                      void* dev, bool allow_cluster);
 int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s);
 
 }  // namespace rb

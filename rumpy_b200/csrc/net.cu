@@ -66,6 +66,7 @@ struct Net {
   int arch, C, n_groups, n_blocks, reduction, scale;
   float res_scale;
   int in_feats, out_feats, u_f32;
+  int plan_u_f32 = 1;         // dtype of the saved pre-attention activation of the cached plan (bf16 with OP_TRUNK)
   std::vector<ConvW> convs;   // network order
   std::vector<CAW> cas;
   int n_params = 0;
@@ -212,7 +213,6 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     if (build) { if (int e = conv_plan_build(&op.conv, d)) err = e; }
     list.push_back(op);
   };
-  std::vector<GroupRec> groups;
   // ---- buffers
   float* head_f = static_cast<float*>(bp.take(px * C * 4));
   void* head_b = bp.take(px * C * 2);
@@ -233,54 +233,96 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   const float* cur_f = head_f;    // its fp32 residual-stream copy
   const int Cr = n->arch == 0 ? C / n->reduction : 1;
   // ---- the whole body (every 64->64 conv, CA, skips) as ONE persistent dataflow kernel when the shape fits
-  const bool use_trunk = g_use_trunk && !training && C == 64 && trunk_supported(N, H, W, C, Cr);
+  const bool use_trunk = g_use_trunk && C == 64 && trunk_supported(N, H, W, C, Cr);
   std::unique_ptr<TrunkPlan> trunk;
+  std::vector<GroupRec> groups;
+  const void* trunk_body_in = nullptr;
   if (use_trunk) {
-    void* pp[2] = {bp.take(px * C * 2), bp.take(px * C * 2)};   // bf16 operand ping-pong
-    void* body_b = bp.take(px * C * 2);
+    // Inference: two ping-pong operand buffers.  Training: every layer writes its own buffer (backward needs the
+    // RCAB inputs, the post-ReLU t, the pre-attention u (kept in bf16) and the CA vectors).
     const int n_body = n->conv_body;                            // convs 1 .. conv_body are the 64->64 body convs
-    void* dev = bp.take(trunk_device_bytes(N, H, W, n_body, 3, 3));
-    if (build) {
-      trunk.reset(new TrunkPlan());
-      trunk->in_bufs = {head_b, pp[0], pp[1]};
-      trunk->out_bufs = {pp[0], pp[1], body_b};
-      auto add_layer = [&](int kind, int conv, int ca) -> TrunkLayer& {
-        TrunkLayer l{};
-        const int L = int(trunk->layers.size());
-        l.kind = kind;
-        l.in_map = L == 0 ? 0 : 1 + ((L - 1) & 1);
-        l.out_map = L & 1;
-        l.ca_slot = -1; l.u_map = -1; l.alpha = 1.f;
-        TrunkLayerParams lp{n->convs[conv].b_idx, -1, -1, -1, -1};
-        if (ca >= 0) { const CAW& c = n->cas[ca]; lp.w1 = c.w1; lp.b1 = c.b1; lp.w2 = c.w2; lp.b2 = c.b2; l.ca_slot = ca; }
-        trunk->layers.push_back(l);
-        trunk->lparams.push_back(lp);
-        return trunk->layers.back();
-      };
-      int c2 = 1, cai = 0;
-      if (n->arch == 0) {
-        for (int g = 0; g < n->n_groups; ++g) {
-          for (int b = 0; b < n->n_blocks; ++b) {
-            add_layer(kTrunkRelu, c2++, -1);
-            add_layer(kTrunkCA, c2++, cai++);
-          }
-          TrunkLayer& gt = add_layer(kTrunkRes, c2++, -1);      // group tail conv + group skip (:121-124)
-          gt.res_f32 = g == 0 ? head_f : G_f[(g - 1) & 1];
-          gt.out_f32 = G_f[g & 1];
-          gt.update_s = 1;
-        }
-      } else {
+    void* pp[2] = {nullptr, nullptr};
+    if (!training) { pp[0] = bp.take(px * C * 2); pp[1] = bp.take(px * C * 2); }
+    void* dev = bp.take(trunk_device_bytes(N, H, W, n_body, 2 * n_body + 2, 2 * n_body + 2));
+    if (build) trunk.reset(new TrunkPlan());
+    int L = 0;
+    auto in_of = [&](const void* p) {
+      for (size_t i = 0; i < trunk->in_bufs.size(); ++i) if (trunk->in_bufs[i] == p) return int(i);
+      trunk->in_bufs.push_back(p);
+      return int(trunk->in_bufs.size()) - 1;
+    };
+    auto out_of = [&](void* p) {
+      for (size_t i = 0; i < trunk->out_bufs.size(); ++i) if (trunk->out_bufs[i] == p) return int(i);
+      trunk->out_bufs.push_back(p);
+      return int(trunk->out_bufs.size()) - 1;
+    };
+    auto next_out = [&]() -> void* { return training ? bp.take(px * C * 2) : pp[L & 1]; };
+    auto add_layer = [&](int kind, int conv, int ca, const void* in, void* out) -> TrunkLayer* {
+      ++L;
+      if (!build) return nullptr;
+      TrunkLayer l{};
+      l.kind = kind;
+      l.in_map = in_of(in);
+      l.out_map = out_of(out);
+      l.ca_slot = -1; l.u_map = -1; l.alpha = 1.f;
+      TrunkLayerParams lp{n->convs[conv].b_idx, -1, -1, -1, -1};
+      if (ca >= 0) { const CAW& c = n->cas[ca]; lp.w1 = c.w1; lp.b1 = c.b1; lp.w2 = c.w2; lp.b2 = c.b2; l.ca_slot = ca; }
+      trunk->layers.push_back(l);
+      trunk->lparams.push_back(lp);
+      return &trunk->layers.back();
+    };
+    int c2 = 1, cai = 0;
+    if (n->arch == 0) {
+      for (int g = 0; g < n->n_groups; ++g) {
+        GroupRec gr;
         for (int b = 0; b < n->n_blocks; ++b) {
-          add_layer(kTrunkRelu, c2++, -1);
-          TrunkLayer& r2 = add_layer(kTrunkRes, c2++, -1);      // conv2(.)*res_scale + x   (common.py:72-73)
-          r2.alpha = n->res_scale; r2.update_s = 1;
+          void* t = next_out();
+          add_layer(kTrunkRelu, c2, -1, cur_b, t);
+          void* xb = next_out();
+          void* u = training ? bp.take(px * C * 2) : nullptr;
+          float* sv = training ? static_cast<float*>(bp.take(size_t(N) * (2 * C + Cr) * 4)) : nullptr;
+          if (TrunkLayer* l = add_layer(kTrunkCA, c2 + 1, cai, t, xb)) {
+            if (training) {
+              l->u_map = out_of(u);
+              l->save_mean = sv; l->save_y = sv + size_t(N) * C; l->save_hid = sv + size_t(N) * 2 * C;
+            }
+          }
+          gr.blocks.push_back(BlockRec{cur_b, t, u, sv, c2, c2 + 1, cai});
+          c2 += 2; ++cai;
+          cur_b = xb;
         }
+        void* gout = next_out();
+        gr.tail_in_b = cur_b; gr.conv_tail = c2;
+        if (TrunkLayer* l = add_layer(kTrunkRes, c2++, -1, cur_b, gout)) {   // group tail conv + group skip (:121-124)
+          l->res_f32 = g == 0 ? head_f : G_f[(g - 1) & 1];
+          l->out_f32 = G_f[g & 1];
+          l->update_s = 1;
+        }
+        groups.push_back(gr);
+        cur_b = gout;
       }
-      TrunkLayer& bt = add_layer(kTrunkRes, c2++, -1);          // body tail conv + global skip (:173-174 / :238-239)
-      bt.res_f32 = head_f;
-      bt.out_map = 2;
+    } else {
+      GroupRec gr;
+      for (int b = 0; b < n->n_blocks; ++b) {
+        void* t = next_out();
+        add_layer(kTrunkRelu, c2, -1, cur_b, t);
+        void* xb = next_out();
+        if (TrunkLayer* l = add_layer(kTrunkRes, c2 + 1, -1, t, xb)) {       // conv2(.)*res_scale + x (common.py:72-73)
+          l->alpha = n->res_scale; l->update_s = 1;
+        }
+        gr.blocks.push_back(BlockRec{cur_b, t, nullptr, nullptr, c2, c2 + 1, -1});
+        c2 += 2;
+        cur_b = xb;
+      }
+      groups.push_back(gr);
+    }
+    trunk_body_in = cur_b;
+    void* body_b = bp.take(px * C * 2);
+    if (TrunkLayer* l = add_layer(kTrunkRes, c2++, -1, cur_b, body_b))       // body tail conv + global skip
+      l->res_f32 = head_f;
+    if (build) {
       if (c2 != n_body + 1) err = set_error(RUMPY_ERR_ARG, "trunk: layer count mismatch");
-      if (int e = trunk_plan_finish(trunk.get(), N, H, W, Cr, pk + n->convs[1].off_fwd, head_f, dev)) err = e;
+      if (int e = trunk_plan_finish(trunk.get(), N, H, W, Cr, pk + n->convs[1].off_fwd, head_f, dev, !training)) err = e;
       Op op{};
       op.type = OP_TRUNK;
       ops.push_back(op);
@@ -379,7 +421,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     groups.push_back(gr);
   }
   // ---- body tail conv + global skip (architectures.py:173-174 / :238-239): operand for the upsampler only
-  const void* body_in_b = cur_b;
+  const void* body_in_b = use_trunk ? trunk_body_in : cur_b;
   if (!use_trunk) {
     void* body_b = bp.take(px * C * 2);
     ConvDesc d{};
@@ -608,6 +650,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     n->ops.swap(ops);
     n->bops.swap(bops);
     n->trunk = std::move(trunk);
+    n->plan_u_f32 = use_trunk ? 0 : n->u_f32;
     n->wg_jobs.swap(wg_jobs);
     n->wg_rjobs.swap(wg_rjobs);
     n->cs_jobs.swap(cs_jobs);
@@ -866,7 +909,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         a.N = N; a.HW = HW; a.C = C; a.Cr = Cr;
         dim3 g1(kCaBwdChunks, N);
         const size_t smem = size_t(256 / (C / 4)) * C * sizeof(float);
-        if (n->u_f32) ca_bwd_reduce_kernel<true><<<g1, 256, smem, stream>>>(a);
+        if (n->plan_u_f32) ca_bwd_reduce_kernel<true><<<g1, 256, smem, stream>>>(a);
         else ca_bwd_reduce_kernel<false><<<g1, 256, smem, stream>>>(a);
         if (int e = check_launch("ca_bwd_reduce")) return e;
         ca_bwd_apply_kernel<<<dim3(op.ca_chunks, N), 256, 0, stream>>>(

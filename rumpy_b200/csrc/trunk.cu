@@ -29,7 +29,7 @@ size_t trunk_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int 
 }
 
 int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* w_base, const float* s_init,
-                      void* dev) {
+                      void* dev, bool allow_cluster) {
   int sms = 0;
   if (int e = device_info(&sms)) return e;
   if (!trunk_supported(N, H, W, 64, Cr)) return set_error(RUMPY_ERR_ARG, "trunk: unsupported shape");
@@ -69,7 +69,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
   // ---- one cluster per image?  pick the decomposition with the fewest tiles per CTA that keeps all N clusters
   // co-resident (clusters are independent, so this is a performance condition, not a correctness one)
   plan->cluster = false;
-  if (g_use_cluster) {
+  if (g_use_cluster && allow_cluster) {
     static bool attr_set = false;
     if (!attr_set) {
       cudaFuncSetAttribute(trunk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);

@@ -152,7 +152,11 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
     uint32_t phase = 0;
     for (int L = 0; L < n_layers; ++L) {
       const CUtensorMap* im = args.in_maps + args.layers[L].in_map;
-      if (lane == 0 && L + 1 < n_layers) tma_prefetch_desc(args.in_maps + args.layers[L + 1].in_map);
+      if (lane == 0 && L + 1 < n_layers) {   // descriptors of the next layer (training plans use one map per layer)
+        tma_prefetch_desc(args.in_maps + args.layers[L + 1].in_map);
+        tma_prefetch_desc(args.out_maps + args.layers[L + 1].out_map);
+        if (args.layers[L + 1].u_map >= 0) tma_prefetch_desc(args.out_maps + args.layers[L + 1].u_map);
+      }
       for (int j = 0; j < my_k; ++j) {
         const int t = cta + j * G;
         const int n = t / P, rem = t - n * P;
