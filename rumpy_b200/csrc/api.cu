@@ -11,6 +11,7 @@ thread_local std::string g_last_error;
 long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
 int g_use_pdl = 1;                       // programmatic dependent launch between layers (rumpy_debug_set_pdl)
 int g_conv_2x = 0;                       // experiment: stream B, <=113 KB smem, two CTAs per SM (rumpy_debug_set_conv2x)
+extern int g_use_trunk_bwd;
 extern int g_use_trunk;                  // net.cu: persistent trunk kernel (trunk_pipe.cuh), default on
 int g_use_fused_ca = 0;                  // conv2 + CALayer in one kernel (TMEM-held accumulators + grid barrier):
                                          // correct but not faster at the benchmark shapes, opt-in
@@ -346,6 +347,7 @@ int rumpy_debug_set_fused_ca(int on) { g_use_fused_ca = on; return 0; }
 int rumpy_debug_get_fused_ca(void) { return g_use_fused_ca; }
 int rumpy_debug_set_trunk(int on) { g_use_trunk = on; return 0; }
 int rumpy_debug_get_trunk(void) { return g_use_trunk; }
+int rumpy_debug_set_trunk_bwd(int on) { g_use_trunk_bwd = on; return 0; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }
 int rumpy_device_check(void) { return device_info(nullptr); }
 

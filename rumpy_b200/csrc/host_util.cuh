@@ -11,6 +11,7 @@
 #include "conv3x3_ca.cuh"
 #include "trunk_pipe.cuh"
 #include "trunk_cluster.cuh"
+#include "trunk_bwd.cuh"
 #include <vector>
 
 namespace rb {
@@ -104,6 +105,32 @@ struct TrunkPlan {
   int cluster_size = 0;
   size_t cluster_smem = 0;
 };
+// backward program of the body (trunk_bwd.cuh)
+struct TrunkBwdLayerParams { int w1, w2; };              // parameter indices of a kBwdCA layer (-1: none)
+struct TrunkBwdPgBind { int layer, dw1, db1, dw2, db2; };   // kBwdCA layer -> gradient parameter indices
+struct CaPgJobHost { const float* pg; float *dw1, *db1, *dw2, *db2; };
+struct TrunkBwdPlan {
+  CUtensorMap w_map;
+  TrunkBwdArgs args;
+  int grid = 0;
+  std::vector<TrunkBwdLayer> layers, uploaded;
+  std::vector<TrunkBwdLayerParams> lparams;
+  std::vector<TrunkBwdPgBind> pg_binds;
+  std::vector<const void*> in_bufs;
+  std::vector<void*> out_bufs;
+  TrunkBwdLayer* layers_dev = nullptr;
+  CUtensorMap *in_maps_dev = nullptr, *out_maps_dev = nullptr;
+  void* flags_dev = nullptr;
+  size_t flags_bytes = 0;
+  CaPgJobHost* pg_jobs_dev = nullptr;
+  std::vector<CaPgJobHost> pg_jobs_uploaded;
+  bool maps_uploaded = false;
+};
+size_t trunk_bwd_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int n_out_maps, int n_ca);
+int trunk_bwd_plan_finish(TrunkBwdPlan* plan, int N, int H, int W, int Cr, const void* w_base, int n_w_layers,
+                          void* dev);
+int trunk_bwd_launch(TrunkBwdPlan* plan, const float* const* params, float* const* grads, cudaStream_t s);
+
 bool trunk_supported(int N, int H, int W, int C, int Cr);
 // device bytes needed next to the activations: layer table, tensor maps, flags, pool partials
 size_t trunk_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int n_out_maps);

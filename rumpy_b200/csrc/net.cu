@@ -32,10 +32,11 @@ struct ConvW {            // one 3x3 conv of the network
 
 struct CAW { int w1, b1, w2, b2; };
 
-enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
+enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
 
 extern int g_use_fused_ca;
 extern int g_use_cluster;
+int g_use_trunk_bwd = 1;   // backward of the RCAN body in the persistent dataflow kernel (trunk_bwd.cuh)
 int g_use_trunk = 1;   // whole 64-channel body in the persistent dataflow kernel (trunk_pipe.cuh) when the shape fits
 
 struct Op {
@@ -94,6 +95,7 @@ struct Net {
   int* pg_counter = nullptr;
   float* ca_coef = nullptr;
   std::unique_ptr<TrunkPlan> trunk;            // persistent trunk kernel plan (OP_TRUNK), or null
+  std::unique_ptr<TrunkBwdPlan> trunk_bwd;     // backward program of the body (OP_TRUNK_BWD), or null
   unsigned long long* ca_counters = nullptr;   // grid-barrier counters of the fused conv2+CA ops
   size_t ca_counters_bytes = 0;
   bool ca_counters_dirty = false;
@@ -455,6 +457,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
 
   // =========================================================================================== backward
   std::vector<Op> bops;
+  std::unique_ptr<TrunkBwdPlan> trunk_bwd;
   std::vector<WgradJob> wg_jobs;
   std::vector<WgradReduceJob> wg_rjobs;
   std::vector<ColsumJob> cs_jobs;
@@ -505,7 +508,96 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       conv_op(bops, n->convs[n->conv_body], d, true);
       sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f, nullptr, 0});
     }
-    if (n->arch == 0) {
+    const bool use_trunk_bwd = g_use_trunk_bwd && use_trunk && n->arch == 0;
+    if (use_trunk_bwd) {
+      // ---- the whole backward body as ONE persistent dataflow kernel (trunk_bwd.cuh); the gradient stream Q lives
+      // in tensor memory, P (gradient w.r.t. the group input) is updated in place once per group
+      const int T_tiles = N * tiles;
+      const int n_ca = n->n_groups * n->n_blocks;
+      const int n_lay = n->n_groups * (1 + 3 * n->n_blocks);
+      const size_t per = size_t(2) * C * Cr + C + Cr;
+      void* dev = bp.take(trunk_bwd_device_bytes(N, H, W, n_lay, n_lay + 2, n_lay + 2, n_ca));
+      float* pg_all = static_cast<float*>(bp.take(size_t(n_ca) * N * per * 4));
+      if (build) trunk_bwd.reset(new TrunkBwdPlan());
+      auto in_of = [&](const void* p) {
+        for (size_t i = 0; i < trunk_bwd->in_bufs.size(); ++i) if (trunk_bwd->in_bufs[i] == p) return int(i);
+        trunk_bwd->in_bufs.push_back(p);
+        return int(trunk_bwd->in_bufs.size()) - 1;
+      };
+      auto out_of = [&](void* p) {
+        for (size_t i = 0; i < trunk_bwd->out_bufs.size(); ++i) if (trunk_bwd->out_bufs[i] == p) return int(i);
+        trunk_bwd->out_bufs.push_back(p);
+        return int(trunk_bwd->out_bufs.size()) - 1;
+      };
+      int L = 0, ca_ord = 0;
+      const void* gb = GB_cur;   // bf16 gradient w.r.t. the current group's output ...
+      int gb_epoch = 0;          // ... complete at this tile epoch (0: written before the kernel)
+      auto push = [&](const TrunkBwdLayer& l, int w1 = -1, int w2 = -1) {
+        if (build) { trunk_bwd->layers.push_back(l); trunk_bwd->lparams.push_back(TrunkBwdLayerParams{w1, w2}); }
+        ++L;
+      };
+      for (int g = n->n_groups - 1; g >= 0; --g) {
+        const GroupRec& gr = groups[g];
+        {
+          TrunkBwdLayer l{};
+          l.kind = kBwdFresh; l.out_map = -1; l.ca_slot = -1;
+          l.w_idx = gr.conv_tail - 1; l.wait_epoch = gb_epoch;
+          if (build) l.in_map = in_of(gb);
+          push(l);
+          sites.push_back({gr.conv_tail, gb, gr.tail_in_b, H, W, 1.f, nullptr, 0});
+        }
+        for (int b = n->n_blocks - 1; b >= 0; --b) {
+          const BlockRec& br = gr.blocks[b];
+          void* du = bp.take(px * C * 2);
+          void* dt = bp.take(px * C * 2);
+          float* du_cs = static_cast<float*>(bp.take(size_t(T_tiles) * C * 4));
+          float* dt_pool = static_cast<float*>(bp.take(size_t(T_tiles) * C * 4));
+          const int L_ca = L;
+          {
+            TrunkBwdLayer l{};
+            l.kind = kBwdCA; l.in_map = -1; l.w_idx = -1; l.ca_slot = ca_ord;
+            l.aux = static_cast<const __nv_bfloat16*>(br.u); l.colsum = du_cs;
+            l.save_mean = br.sv; l.save_y = br.sv + size_t(N) * C; l.save_hid = br.sv + size_t(N) * 2 * C;
+            l.pg = pg_all + size_t(ca_ord) * N * per;
+            if (build) {
+              l.out_map = out_of(du);
+              const CAW& cw = n->cas[br.ca];
+              trunk_bwd->pg_binds.push_back(TrunkBwdPgBind{L, cw.w1, cw.b1, cw.w2, cw.b2});
+              push(l, cw.w1, cw.w2);
+            } else {
+              push(l);
+            }
+            ++ca_ord;
+          }
+          const int L_mask = L;
+          {
+            TrunkBwdLayer l{};
+            l.kind = kBwdMask; l.ca_slot = -1; l.w_idx = br.conv2 - 1; l.wait_epoch = L_ca + 1;
+            l.aux = static_cast<const __nv_bfloat16*>(br.t); l.colsum = dt_pool;
+            if (build) { l.in_map = in_of(du); l.out_map = out_of(dt); }
+            push(l);
+          }
+          {
+            TrunkBwdLayer l{};
+            l.kind = kBwdAcc; l.ca_slot = -1; l.out_map = -1; l.w_idx = br.conv1 - 1; l.wait_epoch = L_mask + 1;
+            void* GB_new = b == 0 ? bp.take(px * C * 2) : nullptr;
+            if (b == 0) { l.res_f32 = P; l.out_f32 = P; }
+            if (build) { l.in_map = in_of(dt); if (b == 0) l.out_map = out_of(GB_new); }
+            if (b == 0) { gb = GB_new; gb_epoch = L + 1; }
+            push(l);
+          }
+          sites.push_back({br.conv2, du, br.t, H, W, 1.f, du_cs, T_tiles});
+          sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, T_tiles});
+        }
+      }
+      if (build) {
+        if (int e = trunk_bwd_plan_finish(trunk_bwd.get(), N, H, W, Cr, pk + n->convs[1].off_dgrad, n->conv_body, dev))
+          err = e;
+        Op op{};
+        op.type = OP_TRUNK_BWD;
+        bops.push_back(op);
+      }
+    } else if (n->arch == 0) {
       for (int g = n->n_groups - 1; g >= 0; --g) {
         const GroupRec& gr = groups[g];
         {  // group tail conv: grad wrt the last block's output, fp32 only
@@ -650,6 +742,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     n->ops.swap(ops);
     n->bops.swap(bops);
     n->trunk = std::move(trunk);
+    n->trunk_bwd = std::move(trunk_bwd);
     n->plan_u_f32 = use_trunk ? 0 : n->u_f32;
     n->wg_jobs.swap(wg_jobs);
     n->wg_rjobs.swap(wg_rjobs);
@@ -666,12 +759,12 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
 
 static int ensure_plan(Net* n, const void* packed, void* workspace, int N, int H, int W, int training) {
   if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
-      n->p_training != training || n->p_trunk != g_use_trunk + 2 * g_use_cluster) {
+      n->p_training != training || n->p_trunk != g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd) {
     size_t bytes = 0;
     n->plan_packed = nullptr;
     if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
     n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
-    n->p_trunk = g_use_trunk + 2 * g_use_cluster;
+    n->p_trunk = g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd;
   }
   return RUMPY_OK;
 }
@@ -732,6 +825,7 @@ int rumpy_net_num_launches_backward(void* net) {
     switch (op.type) {
       case OP_TAIL_BWD: c += 5; break;        // dgrad, wgrad, reduce, plane sums (2)
       case OP_CA_BWD: c += 2; break;
+      case OP_TRUNK_BWD: c += 2; break;       // the dataflow kernel + the CA parameter-gradient finalize
       case OP_HEAD_WGRAD: c += 2; break;
       default: c += 1;
     }
@@ -898,6 +992,9 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
       }
       case OP_CONV:
         if (int e = launch_conv_op(op, params, nullptr, stream)) return e;
+        break;
+      case OP_TRUNK_BWD:
+        if (int e = trunk_bwd_launch(n->trunk_bwd.get(), params, grads, stream)) return e;
         break;
       case OP_CA_BWD: {
         const int HW = H * W;

@@ -184,6 +184,116 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
   return RUMPY_OK;
 }
 
+// ------------------------------------------------------------------ backward program (trunk_bwd.cuh)
+size_t trunk_bwd_device_bytes(int N, int H, int W, int n_layers, int n_in_maps, int n_out_maps, int n_ca) {
+  const size_t P = size_t((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  const size_t T = size_t(N) * P;
+  return al(size_t(n_layers) * sizeof(TrunkBwdLayer)) + al(size_t(n_in_maps) * sizeof(CUtensorMap)) +
+         al(size_t(n_out_maps) * sizeof(CUtensorMap)) + al(T * sizeof(int) + 2 * T * 64 * sizeof(unsigned long long)) +
+         al(size_t(n_ca) * sizeof(CaPgJobHost));
+}
+
+int trunk_bwd_plan_finish(TrunkBwdPlan* plan, int N, int H, int W, int Cr, const void* w_base, int n_w_layers,
+                          void* dev) {
+  int sms = 0;
+  if (int e = device_info(&sms)) return e;
+  if (!trunk_supported(N, H, W, 64, Cr)) return set_error(RUMPY_ERR_ARG, "trunk_bwd: unsupported shape");
+  TrunkBwdArgs& a = plan->args;
+  memset(&a, 0, sizeof(a));
+  a.n_layers = int(plan->layers.size());
+  a.N = N; a.H = H; a.W = W;
+  a.tiles_x = (W + kTileW - 1) / kTileW;
+  a.tiles_y = (H + kTileH - 1) / kTileH;
+  a.tiles_per_img = a.tiles_x * a.tiles_y;
+  a.T = N * a.tiles_per_img;
+  a.K = (a.T + sms - 1) / sms;
+  plan->grid = (a.T + a.K - 1) / a.K;
+  if (a.K > 1 && a.tiles_per_img <= sms) {
+    const int g = (sms / a.tiles_per_img) * a.tiles_per_img;
+    if ((a.T + g - 1) / g <= a.K) plan->grid = g;
+  }
+  a.cr = Cr;
+  a.inv_hw = 1.f / float(H * W);
+  char* p = static_cast<char*>(dev);
+  plan->layers_dev = reinterpret_cast<TrunkBwdLayer*>(p); p += al(plan->layers.size() * sizeof(TrunkBwdLayer));
+  plan->in_maps_dev = reinterpret_cast<CUtensorMap*>(p); p += al(plan->in_bufs.size() * sizeof(CUtensorMap));
+  plan->out_maps_dev = reinterpret_cast<CUtensorMap*>(p); p += al(plan->out_bufs.size() * sizeof(CUtensorMap));
+  plan->flags_dev = p;
+  const size_t ready_bytes = (size_t(a.T) * sizeof(int) + 15) / 16 * 16;
+  plan->flags_bytes = ready_bytes + size_t(2) * a.T * 64 * sizeof(unsigned long long);
+  a.ready = reinterpret_cast<int*>(p);
+  a.pool_partial = reinterpret_cast<unsigned long long*>(p + ready_bytes);
+  p += al(size_t(a.T) * sizeof(int) + 2 * size_t(a.T) * 64 * sizeof(unsigned long long));
+  plan->pg_jobs_dev = reinterpret_cast<CaPgJobHost*>(p);
+  a.layers = plan->layers_dev;
+  a.in_maps = plan->in_maps_dev;
+  a.out_maps = plan->out_maps_dev;
+  if (int e = make_map_weight_layers(&plan->w_map, w_base, n_w_layers)) return e;
+  plan->uploaded.clear();
+  plan->pg_jobs_uploaded.clear();
+  plan->maps_uploaded = false;
+  return RUMPY_OK;
+}
+
+static_assert(sizeof(CaPgJobHost) == sizeof(CaPgJob), "CaPgJobHost / CaPgJob layout mismatch");
+
+int trunk_bwd_launch(TrunkBwdPlan* plan, const float* const* params, float* const* grads, cudaStream_t s) {
+  TrunkBwdArgs& a = plan->args;
+  if (!plan->maps_uploaded) {
+    std::vector<CUtensorMap> im(plan->in_bufs.size()), om(plan->out_bufs.size());
+    for (size_t i = 0; i < im.size(); ++i)
+      if (int e = make_map_nhwc_sub(&im[i], false, plan->in_bufs[i], 64, a.W, a.H, a.N, 1, 0, kABoxH)) return e;
+    for (size_t i = 0; i < om.size(); ++i)
+      if (int e = make_map_nhwc_sub(&om[i], false, plan->out_bufs[i], 64, a.W, a.H, a.N, 1, 0, kTileH)) return e;
+    if (cudaMemcpyAsync(plan->in_maps_dev, im.data(), im.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s) !=
+            cudaSuccess ||
+        cudaMemcpyAsync(plan->out_maps_dev, om.data(), om.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, s) !=
+            cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk_bwd: map upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(s);
+    plan->maps_uploaded = true;
+  }
+  for (size_t i = 0; i < plan->layers.size(); ++i) {
+    const TrunkBwdLayerParams& lp = plan->lparams[i];
+    if (lp.w1 >= 0) { plan->layers[i].w1 = params[lp.w1]; plan->layers[i].w2 = params[lp.w2]; }
+  }
+  if (plan->uploaded.size() != plan->layers.size() ||
+      memcmp(plan->uploaded.data(), plan->layers.data(), plan->layers.size() * sizeof(TrunkBwdLayer)) != 0) {
+    plan->uploaded = plan->layers;
+    if (cudaMemcpyAsync(plan->layers_dev, plan->uploaded.data(), plan->uploaded.size() * sizeof(TrunkBwdLayer),
+                        cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk_bwd: layer table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(s);
+  }
+  std::vector<CaPgJobHost> jobs;
+  for (const TrunkBwdPgBind& b : plan->pg_binds)
+    jobs.push_back(CaPgJobHost{plan->layers[b.layer].pg, grads[b.dw1], grads[b.db1], grads[b.dw2], grads[b.db2]});
+  if (!jobs.empty() && (jobs.size() != plan->pg_jobs_uploaded.size() ||
+                        memcmp(jobs.data(), plan->pg_jobs_uploaded.data(), jobs.size() * sizeof(CaPgJobHost)) != 0)) {
+    plan->pg_jobs_uploaded = jobs;
+    if (cudaMemcpyAsync(plan->pg_jobs_dev, plan->pg_jobs_uploaded.data(), jobs.size() * sizeof(CaPgJobHost),
+                        cudaMemcpyHostToDevice, s) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk_bwd: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(s);
+  }
+  if (cudaMemsetAsync(plan->flags_dev, 0, plan->flags_bytes, s) != cudaSuccess)
+    return set_error(RUMPY_ERR_CUDA, "trunk_bwd: flag reset failed: %s", cudaGetErrorString(cudaGetLastError()));
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(trunk_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTrunkSmemBytes)) !=
+        cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "trunk_bwd cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    attr_set = true;
+  }
+  trunk_bwd_kernel<<<plan->grid, kTrunkThreads, kTrunkSmemBytes, s>>>(plan->w_map, a);
+  if (int e = check_launch("trunk_bwd")) return e;
+  if (!jobs.empty()) {
+    ca_pg_finalize_kernel<<<int(jobs.size()), 256, 0, s>>>(reinterpret_cast<const CaPgJob*>(plan->pg_jobs_dev), a.N, a.cr);
+    if (int e = check_launch("ca_pg_finalize")) return e;
+  }
+  return RUMPY_OK;
+}
+
 }  // namespace rb
 
 extern "C" {
