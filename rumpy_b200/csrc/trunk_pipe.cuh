@@ -509,10 +509,16 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
       if (kind != kTrunkCA) {
         for (int j = e; j < my_k; j += 2) plain(j);
       } else {
-        // all pools first, then the applies: no tile's pool ever waits on another CTA (deadlock-free for any
-        // tile-to-slot assignment), and a group with two tiles hides one image's pool exchange behind the other
-        for (int j = e; j < my_k; j += 2) ca_pool(j);
-        for (int j = e; j < my_k; j += 2) ca_apply(j);
+        if (args.interleave) {
+          // every image lives in ONE tile slot (the grid is a whole number of images): slot j's exchange only needs
+          // slot-j pools, which never wait on anything => pool(j), apply(j) back to back is deadlock-free, and the
+          // first tile of the next layer does not have to wait for this group's last MMA
+          for (int j = e; j < my_k; j += 2) { ca_pool(j); ca_apply(j); }
+        } else {
+          // any tile-to-slot assignment: all pools first (no pool ever waits on another CTA), then the applies
+          for (int j = e; j < my_k; j += 2) ca_pool(j);
+          for (int j = e; j < my_k; j += 2) ca_apply(j);
+        }
         ++ca_seen;
       }
     }
