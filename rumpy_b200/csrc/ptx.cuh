@@ -220,6 +220,13 @@ __device__ __forceinline__ void ld_relaxed_u64x2(const unsigned long long* p, un
 // orders generic-proxy and async-proxy (TMA) accesses of this thread, all state spaces
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// ------------------------------------------------------------------ cp.async (LDGSTS): 16-byte global -> shared copies that bypass L1
+__device__ __forceinline__ void cp_async_cg16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------ thread-block clusters / distributed shared memory
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -185,6 +185,7 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
     const uint32_t bar_id = 1u + uint32_t(e);
     uint8_t* stg = stg_s + e * kABytes;
     uint8_t* my_stg = stg + row * 128;
+    unsigned long long* pool_scr = reinterpret_cast<unsigned long long*>(stg_s + 2 * kABytes + e * kTrunkPoolBytes);
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     const int cr = args.cr;
 
@@ -370,29 +371,7 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
             w1c[h] = on ? __ldg(lay->w1 + h * 64 + c) : 0.f;
             hid[h] = on ? __ldg(lay->save_hid + n * cr + h) : 0.f;
           }
-          float ssum = 0.f;
-          {
-            const long long t0 = clock64();
-            for (int r0 = hsel; r0 < P; r0 += 32) {
-              unsigned long long v[16];
-              unsigned pending = 0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (r0 + 2 * i < P) { v[i] = ld_relaxed_u64(pp + size_t(r0 + 2 * i) * 64 + c); pending |= 1u << i; }
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (pending & (1u << i)) {
-                  uint32_t spins = 0;
-                  while (unsigned(v[i] >> 32) != epoch) {
-                    __nanosleep(20);
-                    v[i] = ld_relaxed_u64(pp + size_t(r0 + 2 * i) * 64 + c);
-                    if ((++spins & 255u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES)
-                      trunk_watchdog_fail(reinterpret_cast<const int*>(pp + size_t(r0 + 2 * i) * 64 + c) + 1, int(epoch), 3);
-                  }
-                  ssum += __uint_as_float(unsigned(v[i]));
-                }
-            }
-          }
+          const float ssum = pool_column_sum(pp, P, epoch, pool_scr, row, bar_id);
           named_bar_sync(bar_id, 128);   // previous readers of red_s / y_s / coef_s are done; staging is free
           red_s[e][hsel][c] = ssum;
           named_bar_sync(bar_id, 128);

@@ -64,7 +64,10 @@ constexpr int kTrunkMaxK = 4;
 constexpr int kTrunkWBytes = 9 * 64 * 128;   // 72 KB: [kx*3+ky][64 rows][64 k] bf16
 constexpr int kTrunkWThird = 3 * 64 * 128;   // 24 KB: the three ky taps of one kx
 constexpr int kTrunkAccCol = 256;            // TMEM: stream S_j at column 64 j, accumulator j at 256 + 64 j
-constexpr size_t kTrunkSmemBytes = 1024 + kTrunkWBytes + size_t(kTrunkAStages) * kAStageBytes + 2 * kABytes;
+constexpr int kTrunkPoolRows = 32;             // rows of (value, epoch) pairs fetched per cp.async round
+constexpr int kTrunkPoolBytes = kTrunkPoolRows * 64 * 8;   // 16 KB per epilogue group
+constexpr size_t kTrunkSmemBytes =
+    1024 + kTrunkWBytes + size_t(kTrunkAStages) * kAStageBytes + 2 * kABytes + 2 * kTrunkPoolBytes;
 
 #ifdef RB_TRUNK_KERNEL_IMPL
 
@@ -81,6 +84,39 @@ __device__ __forceinline__ void poll_ge(const int* p, int target, int what, bool
     __nanosleep(20);
     if ((++spins & 255u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) trunk_watchdog_fail(p, target, what);
   }
+}
+
+// Column sum of one image's (value, epoch) partial rows for channel c = row & 63 over the rows of parity row >> 6
+// (fixed order: deterministic).  The rows are fetched with cp.async.cg -- 16-byte copies that bypass L1 and stay
+// in flight together; gpu-scope relaxed / .cg loads are issued one at a time by the hardware (16 of them cost
+// ~4 000 cycles here).  A stale entry (epoch mismatch) falls back to a polling reload of that entry.
+// Called by all 128 threads of an epilogue group; `scratch` = the group's kTrunkPoolBytes of shared memory.
+__device__ __forceinline__ float pool_column_sum(const unsigned long long* pp, int P, unsigned epoch,
+                                                 unsigned long long* scratch, int row, uint32_t bar_id) {
+  const int c = row & 63, hsel = row >> 6;
+  float ssum = 0.f;
+  const long long t0 = clock64();
+  for (int r0 = 0; r0 < P; r0 += kTrunkPoolRows) {
+    const int rows = P - r0 < kTrunkPoolRows ? P - r0 : kTrunkPoolRows;
+    for (int r = row >> 5; r < rows; r += 4)
+      cp_async_cg16(smem_u32(scratch + r * 64 + (row & 31) * 2), pp + size_t(r0 + r) * 64 + (row & 31) * 2);
+    cp_async_commit();
+    cp_async_wait_all();
+    named_bar_sync(bar_id, 128);
+    for (int r = hsel; r < rows; r += 2) {
+      unsigned long long v = scratch[r * 64 + c];
+      uint32_t spins = 0;
+      while (unsigned(v >> 32) != epoch) {
+        __nanosleep(20);
+        v = ld_relaxed_u64(pp + size_t(r0 + r) * 64 + c);
+        if ((++spins & 255u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES)
+          trunk_watchdog_fail(reinterpret_cast<const int*>(pp + size_t(r0 + r) * 64 + c) + 1, int(epoch), 2);
+      }
+      ssum += __uint_as_float(unsigned(v));
+    }
+    if (r0 + kTrunkPoolRows < P) named_bar_sync(bar_id, 128);   // scratch is refilled by the next round
+  }
+  return ssum;
 }
 
 // f[i] of lane l  ->  returns sum over the 32 lanes of element f[lane] (fixed order: deterministic)
@@ -240,6 +276,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
     const uint32_t bar_id = 1u + uint32_t(e);
     uint8_t* stg = stg_s + e * kABytes;
     uint8_t* my_stg = stg + row * 128;
+    unsigned long long* pool_scr = reinterpret_cast<unsigned long long*>(stg_s + 2 * kABytes + e * kTrunkPoolBytes);
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     float* bias_e = bias_s[e];
 
@@ -429,30 +466,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
           b1r[h] = on ? __ldg(b1 + h) : 0.f;
         }
         float yacc = __ldg(lay->b2 + c);
-        // this thread's share: channel c, rows hsel, hsel+2, ... (fixed order: deterministic); stale entries are re-read
-        float ssum = 0.f;
-        {
-          const long long t0 = clock64();
-          for (int r0 = hsel; r0 < P; r0 += 32) {
-            unsigned long long v[16];
-            unsigned pending = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (r0 + 2 * i < P) { v[i] = ld_relaxed_u64(pp + size_t(r0 + 2 * i) * 64 + c); pending |= 1u << i; }
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (pending & (1u << i)) {
-                uint32_t spins = 0;
-                while (unsigned(v[i] >> 32) != epoch) {
-                  __nanosleep(20);
-                  v[i] = ld_relaxed_u64(pp + size_t(r0 + 2 * i) * 64 + c);
-                  if ((++spins & 255u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES)
-                    trunk_watchdog_fail(reinterpret_cast<const int*>(pp + size_t(r0 + 2 * i) * 64 + c) + 1, int(epoch), 2);
-                }
-                ssum += __uint_as_float(unsigned(v[i]));
-              }
-          }
-        }
+        const float ssum = pool_column_sum(pp, P, epoch, pool_scr, row, bar_id);
         if (row == 0) TR_STAMP(L, j, 13);
         if (lay->u_map >= 0 && row == 0) tma_store_wait_read0();   // the u store has read the staging tile
         red_s[e][hsel][c] = ssum;

@@ -148,6 +148,9 @@ if __name__ == '__main__':
                 print(f'  L{L:02d}: ' + ' '.join(f'{names[s]}={int(t[cta, L, s] - base) if t[cta, L, s] else -1:>7}' for s in range(5)))
     if 'timeline' in which:
         timeline(build('rcan'), (16, 3, 48, 48), layers=6)
+    if 'timeline3' in which:
+        lib.rumpy_debug_set_trunk_cluster(0)
+        timeline(build('rcan'), (16, 3, 64, 64), layers=8)
     if 'time2' in which:
         net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
         with torch.no_grad():
