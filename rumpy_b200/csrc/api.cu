@@ -261,13 +261,6 @@ int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s) 
   return check_launch("pack_conv3x3_batched");
 }
 
-static_assert(sizeof(CaStatJob) == sizeof(CaStatJobDev), "CaStatJob layout mismatch");
-int pack_ca_stat_launch(const CaStatJob* jobs_dev, int njobs, cudaStream_t s) {
-  if (njobs <= 0) return RUMPY_OK;
-  pack_ca_stat_kernel<<<njobs, 256, 0, s>>>(reinterpret_cast<const CaStatJobDev*>(jobs_dev));
-  return check_launch("pack_ca_stat");
-}
-
 bool conv_ca_supported(int N, int H, int W, int Cin, int Cout) {
   int sms = 0;
   if (device_info(&sms)) return false;

@@ -76,10 +76,6 @@ struct PackJobHost {
   int cout, cin, rows_padded, r, dgrad;
 };
 int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s);
-// channel-attention statistics matrices of one conv2 (trunk_cluster.cuh): out[9][64 ci][64 co] fp32 from OIHW fp32
-struct CaStatJob { const float* w; float* out; };
-constexpr size_t kCaStatBytes = size_t(9) * 64 * 64 * sizeof(float);
-int pack_ca_stat_launch(const CaStatJob* jobs_dev, int njobs, cudaStream_t s);
 int conv_plan_launch(const ConvPlan& p, cudaStream_t s);
 
 // ------------------------------------------------------------------ persistent trunk kernel (trunk_pipe.cuh)

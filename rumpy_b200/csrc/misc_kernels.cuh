@@ -82,36 +82,6 @@ __global__ void pack_conv3x3_batched_kernel(const PackJob* __restrict__ jobs) {
   }
 }
 
-// mean_hw(conv2(t)) is linear in t: with F = sum of t over the image, R0/R1 = sums over the first/last image row,
-// C0/C1 = first/last column, K.. = the four corner pixels (all per input channel),
-//   sum_o conv2(t)(o)[co] = Wsum.F - A_R0.R0 - A_R1.R1 - A_C0.C0 - A_C1.C1 + W22.K00 + W20.K0L + W02.KL0 + W00.KLL
-// where the matrices below are sums of the bf16-ROUNDED taps (what the tensor cores multiply).  Layout
-// out[k][ci][co], k = {Wsum, A_R0 = sum_kx W[2][kx], A_R1 = sum_kx W[0][kx], A_C0 = sum_ky W[ky][2],
-// A_C1 = sum_ky W[ky][0], W[2][2], W[2][0], W[0][2], W[0][0]}.  One block per conv2.
-struct CaStatJobDev { const float* w; float* out; };
-__global__ void pack_ca_stat_kernel(const CaStatJobDev* __restrict__ jobs) {
-  const CaStatJobDev jb = jobs[blockIdx.x];
-  for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
-    const int ci = idx >> 6, co = idx & 63;
-    float w[3][3];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-        w[ky][kx] = __bfloat162float(__float2bfloat16_rn(jb.w[((size_t(co) * 64 + ci) * 3 + ky) * 3 + kx]));
-    float* o = jb.out + idx;
-    o[0 * 4096] = ((w[0][0] + w[0][1]) + (w[0][2] + w[1][0])) + ((w[1][1] + w[1][2]) + (w[2][0] + w[2][1])) + w[2][2];
-    o[1 * 4096] = w[2][0] + w[2][1] + w[2][2];
-    o[2 * 4096] = w[0][0] + w[0][1] + w[0][2];
-    o[3 * 4096] = w[0][2] + w[1][2] + w[2][2];
-    o[4 * 4096] = w[0][0] + w[1][0] + w[2][0];
-    o[5 * 4096] = w[2][2];
-    o[6 * 4096] = w[2][0];
-    o[7 * 4096] = w[0][2];
-    o[8 * 4096] = w[0][0];
-  }
-}
-
 // bias in packed-row order (pixel-shuffle permutation), zero padded
 __global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ p, int cout, int rows_padded,
                                  int r) {

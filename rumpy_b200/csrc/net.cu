@@ -101,8 +101,6 @@ struct Net {
   bool ca_counters_dirty = false;
   // batched weight packing
   size_t pack_jobs_bytes = 0;
-  size_t castat_off = SIZE_MAX, castat_jobs_off = SIZE_MAX;   // CA statistics matrices + their pack job list
-  std::vector<CaStatJob> castat_jobs;
   std::vector<PackJobHost> pack_jobs;
   const void* pack_sig_packed = nullptr;
   const float* pack_sig_p0 = nullptr;
@@ -165,14 +163,6 @@ static int net_init(Net* n) {
   n->conv_tail = int(n->convs.size());
   add_conv(n, n->out_feats, C, 1, 16);  // thin tail
   // dgrad operands (training): every tensor-core conv except the head (no dX needed) and the thin tail
-  // channel-attention statistics matrices (trunk_cluster.cuh: mean(conv2(t)) from sums of t): 9 x [64][64] fp32 per
-  // RCAB, at the same offset for inference and training packings
-  if (n->arch == 0 && C == 64) {
-    n->castat_off = n->packed_bytes;
-    n->packed_bytes = align_up(n->packed_bytes + n->cas.size() * kCaStatBytes, 256);
-    n->castat_jobs_off = n->packed_bytes;
-    n->packed_bytes = align_up(n->packed_bytes + n->cas.size() * sizeof(CaStatJob), 256);
-  }
   n->packed_bytes_train = n->packed_bytes;
   for (int i = 1; i < n->conv_tail; ++i) {
     n->convs[i].off_dgrad = n->packed_bytes_train;
@@ -890,27 +880,7 @@ int rumpy_net_pack(void* net_, const float* const* params, void* packed, int tra
       return set_error(RUMPY_ERR_CUDA, "net_pack: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     n->pack_sig_packed = packed; n->pack_sig_p0 = params[0]; n->pack_sig_training = training;
   }
-  if (int e = pack_batched_launch(jobs_dev, int(n->pack_jobs.size()), cudaStream_t(stream))) return e;
-  if (n->castat_off != SIZE_MAX && !n->cas.empty()) {
-    // conv2 of RCAB i is conv 2 + i + (i / n_blocks)  (head, then per group: n_blocks x (conv1, conv2), group tail)
-    std::vector<CaStatJob> jobs;
-    for (size_t i = 0; i < n->cas.size(); ++i) {
-      const int g = int(i) / n->n_blocks, b = int(i) % n->n_blocks;
-      const int conv2 = 1 + g * (2 * n->n_blocks + 1) + 2 * b + 1;
-      jobs.push_back(CaStatJob{params[n->convs[conv2].w_idx],
-                               reinterpret_cast<float*>(pk + n->castat_off + i * kCaStatBytes)});
-    }
-    CaStatJob* cj_dev = reinterpret_cast<CaStatJob*>(pk + n->castat_jobs_off);
-    if (jobs.size() != n->castat_jobs.size() ||
-        memcmp(jobs.data(), n->castat_jobs.data(), jobs.size() * sizeof(CaStatJob)) != 0) {
-      n->castat_jobs = jobs;
-      if (cudaMemcpyAsync(cj_dev, n->castat_jobs.data(), jobs.size() * sizeof(CaStatJob), cudaMemcpyHostToDevice,
-                          cudaStream_t(stream)) != cudaSuccess)
-        return set_error(RUMPY_ERR_CUDA, "net_pack: CA-stat job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    if (int e = pack_ca_stat_launch(cj_dev, int(jobs.size()), cudaStream_t(stream))) return e;
-  }
-  return RUMPY_OK;
+  return pack_batched_launch(jobs_dev, int(n->pack_jobs.size()), cudaStream_t(stream));
 }
 
 int rumpy_net_forward(void* net_, const float* const* params, const void* packed, const float* x_nchw,
