@@ -70,6 +70,9 @@ __global__ void l1_loss_finalize_kernel(const float* __restrict__ partial, int n
 // ------------------------------------------------------------------------------------------------
 __global__ void tail_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w,
                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int cout) {
+  // One thread = FOUR consecutive pixels of a row x 8 input channels: every weight vector fetched from shared
+  // memory feeds 32 FMAs (the one-pixel version was bound by the shared-memory reads of the weights), and the
+  // 3 x 6 window of dy per output channel is loaded once for the four pixels.
   extern __shared__ float wsm[];  // [cout*9][C]
   for (int i = threadIdx.x; i < cout * 9 * C; i += blockDim.x) {
     const int ci = i % C, k = i / C;       // k = co*9 + tap
@@ -78,38 +81,54 @@ __global__ void tail_dgrad_kernel(const float* __restrict__ dy, const float* __r
   }
   __syncthreads();
   const int groups = C / 8;
-  const size_t npix = size_t(N) * H * W;
-  for (size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x; t < npix * groups;
-       t += size_t(gridDim.x) * blockDim.x) {
+  const int quads = (W + 3) / 4;
+  const size_t items = size_t(N) * H * quads * groups;
+  for (size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x; t < items; t += size_t(gridDim.x) * blockDim.x) {
     const int g = int(t % groups);
-    const size_t pix = t / groups;
-    const int xw = int(pix % W), yh = int((pix / W) % H), n = int(pix / (size_t(W) * H));
-    float acc[8];
+    const size_t qi = t / groups;
+    const int x0 = int(qi % quads) * 4, yh = int((qi / quads) % H), n = int(qi / (size_t(quads) * H));
+    float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
     for (int co = 0; co < cout; ++co) {
       const float* gp = dy + (size_t(n) * cout + co) * H * W;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = yh - (ky - 1);
         if (yy < 0 || yy >= H) continue;
+        float win[6];                       // dy[yy][x0 - 1 .. x0 + 4]
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int xx = x0 - 1 + i;
+          win[i] = (xx >= 0 && xx < W) ? __ldg(gp + size_t(yy) * W + xx) : 0.f;
+        }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const int xx = xw - (kx - 1);
-          if (xx < 0 || xx >= W) continue;
-          const float v = __ldg(gp + size_t(yy) * W + xx);
-          const float* wp = wsm + (co * 9 + ky * 3 + kx) * C + g * 8;
+          const float4 w0 = *reinterpret_cast<const float4*>(wsm + (co * 9 + ky * 3 + kx) * C + g * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wsm + (co * 9 + ky * 3 + kx) * C + g * 8 + 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wp[j], acc[j]);
+          for (int p = 0; p < 4; ++p) {
+            const float v = win[p + 2 - kx];   // dy at x0 + p - (kx - 1)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(v, wv[j], acc[p][j]);
+          }
         }
       }
     }
-    __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[0], acc[1]), b1 = __floats2bfloat162_rn(acc[2], acc[3]);
-    __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[4], acc[5]), b3 = __floats2bfloat162_rn(acc[6], acc[7]);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
-    o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
-    *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = o;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      if (x0 + p >= W) break;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(acc[p][0], acc[p][1]), b1 = __floats2bfloat162_rn(acc[p][2], acc[p][3]);
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(acc[p][4], acc[p][5]), b3 = __floats2bfloat162_rn(acc[p][6], acc[p][7]);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&b0); o.y = *reinterpret_cast<uint32_t*>(&b1);
+      o.z = *reinterpret_cast<uint32_t*>(&b2); o.w = *reinterpret_cast<uint32_t*>(&b3);
+      const size_t pix = (size_t(n) * H + yh) * W + x0 + p;
+      *reinterpret_cast<uint4*>(dx + pix * C + g * 8) = o;
+    }
   }
 }
 
@@ -122,7 +141,9 @@ __global__ void tail_dgrad_kernel(const float* __restrict__ dy, const float* __r
 // plus SB[m] = sum_p thin[m,p] (tail bias grad) or SB'[c] = sum_p wide[p,c] (head bias grad).
 // Thread = (channel c, pixel lane); each block writes a partial [M*9 + 1][C] (last row: wide column sums).
 // ------------------------------------------------------------------------------------------------
-template <bool WIDE_BF16>
+// MM = compile-time bound on M (3 for RGB: the accumulators and the window stay in ~130 registers, two blocks per
+// SM instead of one at MM = 4).
+template <bool WIDE_BF16, int MM = 4>
 __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __restrict__ wide_,
                                   const float* __restrict__ wide2 /* optional second fp32 wide tensor, added */,
                                   float* __restrict__ partial, int N, int H, int W, int C, int M, int sign) {
@@ -131,23 +152,23 @@ __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __
   extern __shared__ float red[];  // [lanes][M*9+1][C] reduce buffer
   const int lanes = blockDim.x / C;
   const int c = threadIdx.x % C, lane = threadIdx.x / C;
-  float acc[37];
+  float acc[MM * 9 + 1];
 #pragma unroll
-  for (int i = 0; i < 37; ++i) acc[i] = 0.f;
+  for (int i = 0; i < MM * 9 + 1; ++i) acc[i] = 0.f;
   const int rows_total = N * H;
   for (int rowi = blockIdx.x * lanes + lane; rowi < rows_total && lane < lanes; rowi += gridDim.x * lanes) {
     const int n = rowi / H, yh = rowi - n * H;
-    const float* rp[4][3];   // thin rows for (m, ky): row yh + sign*(ky-1), nullptr when outside the image
+    const float* rp[MM][3];   // thin rows for (m, ky): row yh + sign*(ky-1), nullptr when outside the image
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < MM; ++m)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = yh + sign * (ky - 1);
         rp[m][ky] = (m < M && yy >= 0 && yy < H) ? thin + ((size_t(n) * M + m) * H + yy) * W : nullptr;
       }
-    float win[4][3][3];      // [m][ky][column offset -1, 0, +1]
+    float win[MM][3][3];      // [m][ky][column offset -1, 0, +1]
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+    for (int m = 0; m < MM; ++m)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         win[m][ky][0] = 0.f;                                           // column -1 is outside
@@ -162,9 +183,9 @@ __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __
         v = static_cast<const float*>(wide_)[(wbase + xw) * C + c];
         if (wide2) v += wide2[(wbase + xw) * C + c];
       }
-      acc[36] += v;
+      acc[MM * 9] += v;
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < MM; ++m)
         if (m < M) {
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
@@ -177,7 +198,7 @@ __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __
       // slide the window one column to the right
       const bool more = xw + 2 < W;
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < MM; ++m)
         if (m < M) {
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
@@ -191,9 +212,9 @@ __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __
   const int rows = M * 9 + 1;
   if (lane < lanes) {
 #pragma unroll
-    for (int i = 0; i < 36; ++i)
+    for (int i = 0; i < MM * 9; ++i)
       if (i < M * 9) red[(lane * rows + i) * C + c] = acc[i];
-    red[(lane * rows + M * 9) * C + c] = acc[36];
+    red[(lane * rows + M * 9) * C + c] = acc[MM * 9];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < rows * C; i += blockDim.x) {
@@ -261,7 +282,7 @@ struct ColsumJob {
   int outer, r, inner, C;
   float alpha;
 };
-constexpr int kColsumSlices = 32;
+constexpr int kColsumSlices = 128;   // per-job parallelism: the HR upsampler gradients are 134 MB / 33 MB tensors
 
 __global__ void colsum_kernel(const ColsumJob* __restrict__ jobs) {
   extern __shared__ float red[];  // [blockDim.x]
@@ -278,11 +299,15 @@ __global__ void colsum_kernel(const ColsumJob* __restrict__ jobs) {
       for (int o = o_begin + lane; o < o_end; o += lanes) {
         const __nv_bfloat16* row = jb.g + ((size_t(o) * jb.r + i) * jb.inner) * vec + e;
         int w = 0;
-        for (; w + 1 < jb.inner; w += 2) {
-          s0 += __bfloat162float(row[size_t(w) * vec]);
-          s1 += __bfloat162float(row[size_t(w + 1) * vec]);
+        for (; w + 7 < jb.inner; w += 8) {   // eight independent 2-byte loads in flight per thread
+          const float v0 = __bfloat162float(row[size_t(w) * vec]), v1 = __bfloat162float(row[size_t(w + 1) * vec]);
+          const float v2 = __bfloat162float(row[size_t(w + 2) * vec]), v3 = __bfloat162float(row[size_t(w + 3) * vec]);
+          const float v4 = __bfloat162float(row[size_t(w + 4) * vec]), v5 = __bfloat162float(row[size_t(w + 5) * vec]);
+          const float v6 = __bfloat162float(row[size_t(w + 6) * vec]), v7 = __bfloat162float(row[size_t(w + 7) * vec]);
+          s0 += (v0 + v2) + (v4 + v6);
+          s1 += (v1 + v3) + (v5 + v7);
         }
-        if (w < jb.inner) s0 += __bfloat162float(row[size_t(w) * vec]);
+        for (; w < jb.inner; ++w) s0 += __bfloat162float(row[size_t(w) * vec]);
       }
     }
     red[threadIdx.x] = s0 + s1;

@@ -975,12 +975,16 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
     switch (op.type) {
       case OP_TAIL_BWD: {
         const int Hh = op.h, Wh = op.w, M = n->out_feats, rows = M * 9 + 1;
-        const size_t items = size_t(N) * Hh * Wh * (C / 8);
+        const size_t items = size_t(N) * Hh * ((Wh + 3) / 4) * (C / 8);
         tail_dgrad_kernel<<<grid_for(items, 256, 8), 256, size_t(M) * 9 * C * sizeof(float), stream>>>(
             dy_nchw, params[tail.w_idx], static_cast<__nv_bfloat16*>(op.g_hr), N, Hh, Wh, C, M);
         if (int e = check_launch("tail_dgrad")) return e;
-        thin_wgrad_kernel<true><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
-            dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
+        if (M <= 3)
+          thin_wgrad_kernel<true, 3><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
+              dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
+        else
+          thin_wgrad_kernel<true, 4><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
+              dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
         if (int e = check_launch("tail_wgrad")) return e;
         thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[tail.w_idx], nullptr, C, M, 0);
         if (int e = check_launch("tail_wgrad_reduce")) return e;
@@ -1021,8 +1025,12 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         break;
       case OP_HEAD_WGRAD: {
         const int M = n->in_feats, rows = M * 9 + 1;
-        thin_wgrad_kernel<false><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
-            x_nchw, op.a, op.b, op.thin_partial, N, H, W, C, M, +1);
+        if (M <= 3)
+          thin_wgrad_kernel<false, 3><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
+              x_nchw, op.a, op.b, op.thin_partial, N, H, W, C, M, +1);
+        else
+          thin_wgrad_kernel<false, 4><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
+              x_nchw, op.a, op.b, op.thin_partial, N, H, W, C, M, +1);
         if (int e = check_launch("head_wgrad")) return e;
         thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[head.w_idx],
                                                         grads[head.b_idx], C, M, 1);
