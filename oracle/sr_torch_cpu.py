@@ -15,6 +15,7 @@ Reference lines restated (relative to /root/reference):
   RCAN.forward  rumpy/SISR/models/advanced/architectures.py:171-176
   ResidualGroup :121-124   RCAB :81-84   CALayer :41-44
   EDSR.forward  :236-241   ResBlock common.py:71-75   Upsampler common.py:29-44
+  QRCAN.forward rumpy/SISR/models/attention_manipulators/architectures.py:438-446 (qrcan_forward below)
   train step    rumpy/shared_framework/models/base_architecture.py:425-440,457-485
 """
 from __future__ import annotations
@@ -69,6 +70,34 @@ def edsr_forward(sd, x, num_blocks=16, res_scale=0.1, scale=4):
         t = F.relu(_conv(sd, f'body.{b}.body.0', res))
         res = _conv(sd, f'body.{b}.body.2', t).mul(res_scale) + res
     res = _conv(sd, f'body.{num_blocks}', res) + x
+    return _tail(sd, res, scale)
+
+
+def qrcan_forward(sd, x, attributes, n_resgroups, n_resblocks, scale=4, style='standard'):
+    """Q-RCAN forward (reference SISR/models/attention_manipulators/architectures.py: QRCAN.forward :438-446,
+    QResidualGroup.forward :296-300, QRCAB.forward :198-219 with QCALayer.forward :110-130 styles 'standard' /
+    'modulate' and ParaCALayer.forward q_layer.py:42-45).  attributes: [N, M, 1, 1]; RCABs whose state_dict
+    holds `q_node.attribute_integrator.*` are multiplied by the meta-attention vector."""
+    x = _conv(sd, 'head.0', x)
+    res = x
+    for g in range(n_resgroups):
+        gin = res
+        for b in range(n_resblocks):
+            p = f'body.{g}.body.{b}'
+            u = _conv(sd, p + '.body.2', F.relu(_conv(sd, p + '.body.0', res)))
+            y = F.adaptive_avg_pool2d(u, 1)
+            y = F.relu(_conv(sd, p + '.final_body.conv_du.0', y))
+            y = torch.sigmoid(_conv(sd, p + '.final_body.conv_du.2', y))
+            if style == 'modulate':
+                y = y * attributes
+            u = u * y
+            if p + '.q_node.attribute_integrator.0.weight' in sd:
+                q = F.relu(_conv(sd, p + '.q_node.attribute_integrator.0', attributes))
+                q = torch.sigmoid(_conv(sd, p + '.q_node.attribute_integrator.2', q))
+                u = u * q
+            res = u + res
+        res = _conv(sd, f'body.{g}.final_body', res) + gin
+    res = _conv(sd, 'final_body', res) + x
     return _tail(sd, res, scale)
 
 

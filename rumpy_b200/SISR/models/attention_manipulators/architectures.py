@@ -1,0 +1,186 @@
+"""B200-native mirror of the reference's Q-RCAN (meta-attention RCAN)
+(/root/reference/rumpy/SISR/models/attention_manipulators/architectures.py:46-462).
+
+Same class names, constructor signatures, module tree, registration order and state_dict keys as the reference
+for the configurations the native trunk implements:
+  * QCALayer style 'standard' (plain channel attention, :127-128) or 'modulate' (attention x attributes, :113-114);
+  * optional q-nodes (`include_q_layer`, `selective_meta_blocks`, `num_q_layers_inner_residual`) with the
+    reference's 2-layer ParaCALayer (q_layer.py:5-45).
+Everything else the reference's QRCAN can be configured with (pixel attention, SFT / DGFMB / DA-conv layers, the
+concat styles, staggered encodings, outer metadata reduction) is outside SURVEY.md section 8 and raises
+NotImplementedError at construction.  Inference only (training the meta-attention is a 'next' row).
+
+`QRCAN.forward(x, metadata)` hands the parameter list and the metadata to the native executor: the metadata
+multipliers q[rcab][n][c] are computed by one kernel, and the whole body runs in the same trunk kernel as RCAN
+with q multiplied into the channel-attention vector.
+"""
+import torch
+from torch import nn
+
+from rumpy_b200 import _lib
+from rumpy_b200 import engine as _engine
+from rumpy_b200.SISR.models.advanced import common
+from rumpy_b200.SISR.models.advanced.architectures import _NativeTrunk
+from rumpy_b200.SISR.models.attention_manipulators.q_layer import ParaCALayer
+
+_NATIVE_ONLY = 'runs inside the native QRCAN trunk only (no standalone / CPU path)'
+
+
+class QCALayer(nn.Module):
+    """reference architectures.py:46-130"""
+
+    def __init__(self, channel, style, reduction=16, num_metadata=1):
+        super(QCALayer, self).__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        if reduction < 16:
+            raise RuntimeError('Using an extreme channel attention reduction value')
+        if style not in ('standard', 'modulate'):
+            raise NotImplementedError(f"rumpy_b200 QCALayer: style '{style}' (native: 'standard', 'modulate')")
+        self.conv_du = nn.Sequential(
+            nn.Conv2d(channel, channel // reduction, 1, padding=0, bias=True),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(channel // reduction, channel, 1, padding=0, bias=True),
+            nn.Sigmoid()
+        )
+        self.style = style
+
+    def forward(self, x, attributes):
+        raise _lib.RumpyB200Error('QCALayer ' + _NATIVE_ONLY)
+
+
+class QRCAB(nn.Module):
+    """reference architectures.py:152-219.  Registration order: final_body (channel attention), q_node, body."""
+
+    def __init__(self, conv, n_feat, kernel_size, reduction, style='modulate', pa=False, q_layer=False,
+                 dgfmb_layer=False, sft_layer=False, da_conv_layer=False, bias=True, bn=False, act=nn.ReLU(True),
+                 res_scale=1, num_metadata=1, num_layers_in_q_layer=2, num_layers_in_dgfmb_layer=2,
+                 use_dgfmb_reduction=True):
+        super(QRCAB, self).__init__()
+        if bn or pa or dgfmb_layer or sft_layer or da_conv_layer:
+            raise NotImplementedError('rumpy_b200 QRCAB: bn / pixel attention / DGFMB / SFT / DA-conv variants')
+        if q_layer and num_layers_in_q_layer != 2:
+            raise NotImplementedError('rumpy_b200 QRCAB: q-layers with 2 fully-connected layers only')
+        modules_body = []
+        for i in range(2):
+            modules_body.append(conv(n_feat, n_feat, kernel_size, bias=bias))
+            if i == 0:
+                modules_body.append(act)
+        self.final_body = QCALayer(channel=n_feat, reduction=reduction, style=style, num_metadata=num_metadata)
+        self.pa = pa
+        self.q_layer = q_layer
+        self.dgfmb_layer = dgfmb_layer
+        self.da_conv_layer = da_conv_layer
+        self.sft_layer = sft_layer
+        if q_layer:
+            self.q_node = ParaCALayer(network_channels=n_feat, num_metadata=num_metadata, nonlinearity=True,
+                                      num_layers=num_layers_in_q_layer)
+        self.body = nn.Sequential(*modules_body)
+        self.res_scale = res_scale
+
+    def forward(self, x):
+        raise _lib.RumpyB200Error('QRCAB ' + _NATIVE_ONLY)
+
+
+class QResidualGroup(nn.Module):
+    """reference architectures.py:247-300"""
+
+    def __init__(self, conv, n_feat, kernel_size, reduction, act, res_scale, n_resblocks, style, num_metadata,
+                 pa, q_layer, dgfmb_layer, da_conv_layer,
+                 num_q_layers, num_layers_in_q_layer,
+                 sft_layer, num_sft_layers,
+                 num_dgfmb_layers, num_layers_in_dgfmb_layer, use_dgfmb_reduction,
+                 num_da_conv_layers):
+        super(QResidualGroup, self).__init__()
+        modules_body = []
+        for index in range(n_resblocks):
+            q_in = q_layer if (num_q_layers is None or index < num_q_layers) else False
+            dgfmb_in = dgfmb_layer if (num_dgfmb_layers is None or index < num_dgfmb_layers) else False
+            da_conv_in = da_conv_layer if (num_da_conv_layers is None or index < num_da_conv_layers) else False
+            sft_in = sft_layer if (num_sft_layers is None or index < num_sft_layers) else False
+            modules_body.append(QRCAB(conv, n_feat, kernel_size, reduction, bias=True, bn=False,
+                                      act=act, res_scale=res_scale, style=style,
+                                      pa=pa, q_layer=q_in, dgfmb_layer=dgfmb_in, da_conv_layer=da_conv_in,
+                                      num_metadata=num_metadata,
+                                      num_layers_in_q_layer=num_layers_in_q_layer,
+                                      sft_layer=sft_in,
+                                      num_layers_in_dgfmb_layer=num_layers_in_dgfmb_layer,
+                                      use_dgfmb_reduction=use_dgfmb_reduction))
+        self.final_body = conv(n_feat, n_feat, kernel_size)
+        self.body = nn.Sequential(*modules_body)
+
+    def forward(self, x):
+        raise _lib.RumpyB200Error('QResidualGroup ' + _NATIVE_ONLY)
+
+
+class QRCAN(_NativeTrunk):
+    """reference architectures.py:313-446"""
+
+    def __init__(self, n_resblocks=20, n_resgroups=10, n_feats=64, in_feats=3, out_feats=3, scale=4, reduction=16,
+                 res_scale=1.0, style='modulate', num_metadata=1, include_pixel_attention=False,
+                 selective_meta_blocks=None,
+                 include_q_layer=False, num_q_layers_inner_residual=None, num_layers_in_q_layer=2,
+                 include_sft_layer=False, num_sft_layers_inner_residual=None,
+                 include_dgfmb_layer=False, num_dgfmb_layers_inner_residual=None, num_layers_in_dgfmb_layer=2,
+                 use_dgfmb_reduction=True, use_dgfmb_outer_reduction=False,
+                 include_da_conv_layer=False, num_da_conv_layers_inner_residual=None, staggered_encoding=False,
+                 **kwargs):
+        super(QRCAN, self).__init__()
+        kernel_size = 3
+        act = nn.ReLU(True)
+        if style != 'standard' and staggered_encoding:
+            raise RuntimeError('QRCAN must be set to standard for staggered encoding to work.')
+        if staggered_encoding or use_dgfmb_outer_reduction:
+            raise NotImplementedError('rumpy_b200 QRCAN: staggered encodings / outer metadata reduction')
+        self.style = style
+        self.staggered_encoding = staggered_encoding
+        self.metadata_reduction = nn.Sequential(nn.Identity())
+
+        modules_head = [common.default_conv(in_feats, n_feats, kernel_size)]
+        modules_body = []
+        for index in range(n_resgroups):
+            on = selective_meta_blocks is None or bool(selective_meta_blocks[index])
+            modules_body.append(
+                QResidualGroup(common.default_conv, n_feats, kernel_size, reduction, style=style,
+                               num_metadata=num_metadata, pa=include_pixel_attention,
+                               q_layer=include_q_layer if on else False,
+                               dgfmb_layer=include_dgfmb_layer if on else False,
+                               da_conv_layer=include_da_conv_layer if on else False,
+                               sft_layer=include_sft_layer if on else False,
+                               act=act, res_scale=res_scale, n_resblocks=n_resblocks,
+                               num_q_layers=num_q_layers_inner_residual,
+                               num_layers_in_q_layer=num_layers_in_q_layer,
+                               num_dgfmb_layers=num_dgfmb_layers_inner_residual,
+                               num_layers_in_dgfmb_layer=num_layers_in_dgfmb_layer,
+                               num_sft_layers=num_sft_layers_inner_residual,
+                               use_dgfmb_reduction=use_dgfmb_reduction,
+                               num_da_conv_layers=num_da_conv_layers_inner_residual))
+        self.final_body = common.default_conv(n_feats, n_feats, kernel_size)
+        modules_tail = [
+            common.Upsampler(common.default_conv, scale, n_feats, act=False),
+            common.default_conv(n_feats, out_feats, kernel_size)]
+        self.head = nn.Sequential(*modules_head)
+        self.body = nn.Sequential(*modules_body)
+        self.tail = nn.Sequential(*modules_tail)
+
+        has_q = [bool(blk.q_layer) for grp in self.body for blk in grp.body]
+        q_hidden = 0
+        for grp in self.body:
+            for blk in grp.body:
+                if blk.q_layer:
+                    q_hidden = blk.q_node.layer_sizes[1]
+        self._cfg = dict(n_feats=n_feats, n_groups=n_resgroups, n_blocks=n_resblocks, reduction=reduction,
+                         scale=scale, in_feats=in_feats, out_feats=out_feats, num_metadata=num_metadata,
+                         q_hidden=max(q_hidden, 1), rcab_has_q=has_q, modulate=(style == 'modulate'))
+
+    def _engine_kwargs(self):
+        return _engine.ARCH_QRCAN, dict(self._cfg)
+
+    def forward(self, x, metadata):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError('rumpy_b200 QRCAN: inference only (call under torch.no_grad())')
+        eng = self.native_engine()
+        eng.set_metadata(metadata, x.shape[0])
+        return eng.forward_inference(x)
+
+    def forensic(self, x, qpi, *args, **kwargs):
+        raise NotImplementedError('rumpy_b200: forensic() diagnostics are not part of the native trunk')

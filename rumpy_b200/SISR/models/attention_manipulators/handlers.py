@@ -1,0 +1,46 @@
+"""Mirror of the reference's Q-RCAN handler
+(/root/reference/rumpy/SISR/models/attention_manipulators/handlers.py:11-79): registry name 'qrcan', same
+constructor arguments and attributes; `scale_qpi` reproduces the 'modulate' style's Gaussian channel scalers."""
+import numpy as np
+import torch
+
+from rumpy_b200.SISR.models.attention_manipulators import QModel
+from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+
+
+class QRCANHandler(QModel):
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, scheduler=None,
+                 scheduler_params=None, style='modulate', perceptual=None, clamp=False, min_mu=-0.2,
+                 max_mu=0.8, n_feats=64, srmd_mode=False, **kwargs):
+        super(QRCANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                           **kwargs)
+        if srmd_mode or kwargs.get('include_sft_layer'):
+            raise NotImplementedError('rumpy_b200 QRCANHandler: SRMD / SFT channel-tiled metadata')
+        self.srmd_channel_mode = False
+        self.net = QRCAN(scale=scale, in_feats=in_features, num_metadata=self.num_metadata,
+                         n_feats=n_feats, style=style, **kwargs)
+        self.colorspace = 'augmented_rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.model_name = 'qrcan'
+        self.min_mu = min_mu
+        self.max_mu = max_mu
+        self.base_scaler = np.linspace(0, 1, n_feats)
+        self.clamp = clamp
+        self.style = style
+
+    @staticmethod
+    def gaussian(x, mu, sig=0.2):
+        return torch.from_numpy(
+            (1 / (np.sqrt(2 * np.pi) * sig)) * np.exp(-np.power(x - mu, 2.) / (2 * np.power(sig, 2.)))).type(
+            torch.float32)
+
+    def scale_qpi(self, qpi):
+        """[N,1,1,1] quality index -> [N,n_feats,1,1] Gaussian bump centred on the scaled index (reference :65-73)."""
+        scaled_qpi = (qpi * (self.max_mu - self.min_mu)) + self.min_mu
+        scalers = [self.gaussian(self.base_scaler, scaled_qpi[i].squeeze().numpy()) for i in range(scaled_qpi.size(0))]
+        full_scalers = torch.stack(scalers)
+        if self.clamp:
+            full_scalers = torch.clamp(full_scalers, 0, 1)
+        return full_scalers.unsqueeze(2).unsqueeze(3)

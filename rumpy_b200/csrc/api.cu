@@ -261,6 +261,15 @@ int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s) 
   return check_launch("pack_conv3x3_batched");
 }
 
+static_assert(sizeof(QScaleJobHost) == sizeof(QScaleJobDev), "QScaleJobHost layout mismatch");
+int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int modulate,
+                   cudaStream_t s) {
+  if (njobs <= 0) return RUMPY_OK;
+  q_scale_kernel<<<dim3(njobs, N), 64, size_t(M + hidden) * sizeof(float), s>>>(
+      reinterpret_cast<const QScaleJobDev*>(jobs_dev), meta, M, hidden, modulate);
+  return check_launch("q_scale");
+}
+
 bool conv_ca_supported(int N, int H, int W, int Cin, int Cout) {
   int sms = 0;
   if (device_info(&sms)) return false;
@@ -417,7 +426,8 @@ namespace rb {
 int ca_apply_launch(const float* pool_partial, int partials_per_img, float* compact_scratch, const void* u,
                     int u_is_f32, const float* x_in, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* x_out, void* x_out_bf16, float* save_mean, float* save_hid,
-                    float* save_y, int N, int H, int W, int C, int Cr, cudaStream_t stream) {
+                    float* save_y, int N, int H, int W, int C, int Cr, cudaStream_t stream,
+                    const float* q_scale) {
   int sms = 0;
   if (int e = device_info(&sms)) return e;
   if (!pool_partial || !u || !x_in || !w1 || !b1 || !w2 || !b2 || !x_out || !x_out_bf16)
@@ -452,10 +462,10 @@ int ca_apply_launch(const float* pool_partial, int partials_per_img, float* comp
   cudaError_t le;
   if (u_is_f32)
     le = cudaLaunchKernelEx(&cfg, ca_apply_kernel<true>, pool_partial, partials, u, x_in, w1, b1, w2, b2, x_out, xob,
-                            save_mean, save_hid, save_y, HW, C, Cr);
+                            save_mean, save_hid, save_y, HW, C, Cr, q_scale);
   else
     le = cudaLaunchKernelEx(&cfg, ca_apply_kernel<false>, pool_partial, partials, u, x_in, w1, b1, w2, b2, x_out, xob,
-                            save_mean, save_hid, save_y, HW, C, Cr);
+                            save_mean, save_hid, save_y, HW, C, Cr, q_scale);
   if (le != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "ca_apply launch: %s", cudaGetErrorString(le));
   return RUMPY_OK;
 }
@@ -469,7 +479,7 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
                    void* stream) {
   const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
   return ca_apply_launch(pool_partial, tiles * 2, nullptr, u, u_is_f32, x_in, w1, b1, w2, b2, x_out, x_out_bf16,
-                         save_mean, save_hid, save_y, N, H, W, C, Cr, cudaStream_t(stream));
+                         save_mean, save_hid, save_y, N, H, W, C, Cr, cudaStream_t(stream), nullptr);
 }
 
 int rumpy_nchw_to_nhwc(const float* x, float* y_f32, void* y_bf16, int N, int C, int H, int W, void* stream) {

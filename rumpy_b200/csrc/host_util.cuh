@@ -68,7 +68,12 @@ int conv_ca_launch(const ConvPlan& p, const CaFusedArgs& ca, cudaStream_t s);
 int ca_apply_launch(const float* pool_partial, int partials_per_img, float* compact_scratch, const void* u,
                     int u_is_f32, const float* x_in, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* x_out, void* x_out_bf16, float* save_mean, float* save_hid,
-                    float* save_y, int N, int H, int W, int C, int Cr, cudaStream_t stream);
+                    float* save_y, int N, int H, int W, int C, int Cr, cudaStream_t stream,
+                    const float* q_scale = nullptr);
+// Q-RCAN meta-attention multipliers (misc_kernels.cuh q_scale_kernel): one job per RCAB
+struct QScaleJobHost { const float *w1, *b1, *w2, *b2; float* out; };
+int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int modulate,
+                   cudaStream_t s);
 
 // one conv's packing job for the batched pack kernel (misc_kernels.cuh: PackJob has the same layout)
 struct PackJobHost {

@@ -82,6 +82,40 @@ __global__ void pack_conv3x3_batched_kernel(const PackJob* __restrict__ jobs) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Q-RCAN meta-attention (reference attention_manipulators/q_layer.py:5-45 `ParaCALayer`, used by QRCAB.forward
+// architectures.py:198-219; QCALayer style 'modulate' :113-116): per (image, channel) multipliers of the channel-
+// attention vector that depend on the metadata only, so all RCABs are evaluated up front in one launch:
+//   q[n][c] = sigmoid(W2 relu(W1 meta[n] + b1) + b2)[c]          (RCABs with a q-layer; 2-layer integrator)
+//   q[n][c] *= meta[n][c or 0]                                   (style 'modulate')
+// grid (jobs, N), block 64.
+// ------------------------------------------------------------------------------------------------
+struct QScaleJobDev { const float *w1, *b1, *w2, *b2; float* out; };
+__global__ void q_scale_kernel(const QScaleJobDev* __restrict__ jobs, const float* __restrict__ meta, int M, int hidden,
+                               int modulate) {
+  extern __shared__ float qs_smem[];   // [M] metadata, [hidden] hidden units
+  float* meta_s = qs_smem;
+  float* hid_s = qs_smem + M;
+  const QScaleJobDev jb = jobs[blockIdx.x];
+  const int n = blockIdx.y, c = threadIdx.x;
+  for (int m = c; m < M; m += 64) meta_s[m] = meta[size_t(n) * M + m];
+  __syncthreads();
+  float q = 1.f;
+  if (jb.w1 != nullptr) {
+    for (int t = c; t < hidden; t += 64) {
+      float a = jb.b1[t];
+      for (int m = 0; m < M; ++m) a = fmaf(jb.w1[size_t(t) * M + m], meta_s[m], a);
+      hid_s[t] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    float a = jb.b2[c];
+    for (int t = 0; t < hidden; ++t) a = fmaf(jb.w2[size_t(c) * hidden + t], hid_s[t], a);
+    q = 1.f / (1.f + __expf(-a));
+  }
+  if (modulate) q *= meta_s[M == 1 ? 0 : c];
+  jb.out[size_t(n) * 64 + c] = q;
+}
+
 // bias in packed-row order (pixel-shuffle permutation), zero padded
 __global__ void pack_bias_kernel(const float* __restrict__ b, float* __restrict__ p, int cout, int rows_padded,
                                  int r) {
@@ -189,7 +223,8 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
                                 const float* __restrict__ w2, const float* __restrict__ b2,
                                 float* __restrict__ x_out, __nv_bfloat16* __restrict__ x_out_b,
                                 float* __restrict__ save_mean, float* __restrict__ save_hid,
-                                float* __restrict__ save_y, int HW, int C, int Cr) {
+                                float* __restrict__ save_y, int HW, int C, int Cr,
+                                const float* __restrict__ q_scale /* [N][C] or nullptr (Q-RCAN) */) {
   __shared__ float mean_s[256], y_s[256], hid_s[64], red_s[256];
   const int n = blockIdx.y;
   const int tid = threadIdx.x;
@@ -235,6 +270,7 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
     float s = b2[tid];
     for (int j = 0; j < Cr; ++j) s = fmaf(w2[tid * Cr + j], hid_s[j], s);
     y_s[tid] = 1.f / (1.f + __expf(-s));
+    if (q_scale != nullptr) y_s[tid] *= q_scale[size_t(n) * C + tid];
   }
   __syncthreads();
   if (blockIdx.x == 0 && save_y != nullptr) {

@@ -31,8 +31,9 @@ struct ConvW {            // one 3x3 conv of the network
 };
 
 struct CAW { int w1, b1, w2, b2; };
+using QScaleJob = QScaleJobHost;   // q_scale_kernel job (w1 == nullptr: no q-layer)
 
-enum OpType { OP_HEAD, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
+enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
 
 extern int g_use_fused_ca;
 extern int g_use_cluster;
@@ -54,6 +55,7 @@ struct Op {
   float *save_mean, *save_hid, *save_y;
   float* s_partial; void* du; float* du_colsum; int ca_chunks;
   float* pool_compact;
+  const float* q_scale;   // OP_CA (Q-RCAN): [N][C] multipliers of the CA vector, or nullptr
   // OP_ADD / OP_HEAD_WGRAD / OP_TAIL_BWD
   const float *a, *b; float* dst_f; void* dst_b; size_t n4;
   const void* tail_in; void* g_hr; float* thin_partial;
@@ -70,6 +72,16 @@ struct Net {
   int plan_u_f32 = 1;         // dtype of the saved pre-attention activation of the cached plan (bf16 with OP_TRUNK)
   std::vector<ConvW> convs;   // network order
   std::vector<CAW> cas;
+  // Q-RCAN (meta-attention, attention_manipulators/architectures.py:154-246, q_layer.py:5-45): per-RCAB q-layer
+  // parameters (w1 < 0: the RCAB has none), metadata vector length, q-layer hidden width, 'modulate' style flag
+  bool qrcan = false;
+  std::vector<CAW> qs;
+  int num_meta = 0, q_hidden = 0, modulate = 0;
+  const float* meta_dev = nullptr;
+  int meta_n = 0, meta_m = 0;
+  float* q_scale = nullptr;                 // [n_rcab][N][64] per-(image, channel) multipliers of the CA vector
+  QScaleJob* q_jobs_dev = nullptr;
+  std::vector<QScaleJob> q_jobs_uploaded;
   int n_params = 0;
   size_t packed_bytes = 0, packed_bytes_train = 0;
   int conv_body = 0, conv_up0 = 0, conv_tail = 0;
@@ -162,6 +174,29 @@ static int net_init(Net* n) {
   for (int s = 0; s < st; ++s) add_conv(n, C * r * r, C, r);
   n->conv_tail = int(n->convs.size());
   add_conv(n, n->out_feats, C, 1, 16);  // thin tail
+  if (n->qrcan) {
+    // QRCAN registers its modules in a different order than RCAN (attention_manipulators/architectures.py:313-433,
+    // 154-196, 249-294): final_body | head | per group: final_body, per block: QCALayer, [q_node], conv1, conv2 | tail
+    int p = 0;
+    auto set = [&](int ci) { n->convs[ci].w_idx = p++; n->convs[ci].b_idx = p++; };
+    set(n->conv_body);
+    set(0);
+    const int B = n->n_blocks;
+    for (int g = 0; g < n->n_groups; ++g) {
+      set(1 + g * (2 * B + 1) + 2 * B);
+      for (int b = 0; b < B; ++b) {
+        const int rc = g * B + b;
+        n->cas[rc] = CAW{p, p + 1, p + 2, p + 3};
+        p += 4;
+        if (n->qs[rc].w1 >= 0) { n->qs[rc] = CAW{p, p + 1, p + 2, p + 3}; p += 4; }
+        set(1 + g * (2 * B + 1) + 2 * b);
+        set(1 + g * (2 * B + 1) + 2 * b + 1);
+      }
+    }
+    for (int s2 = 0; s2 < st; ++s2) set(n->conv_up0 + s2);
+    set(n->conv_tail);
+    n->n_params = p;
+  }
   // dgrad operands (training): every tensor-core conv except the head (no dX needed) and the thin tail
   n->packed_bytes_train = n->packed_bytes;
   for (int i = 1; i < n->conv_tail; ++i) {
@@ -231,6 +266,23 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     ops.push_back(op);
     ci = 1;
   }
+  // ---- Q-RCAN: per-(RCAB, image, channel) meta-attention multipliers, evaluated once per forward
+  float* q_scale = nullptr;
+  if (n->qrcan) {
+    if (training) return set_error(RUMPY_ERR_ARG, "Q-RCAN: training is not implemented (inference only)");
+    q_scale = static_cast<float*>(bp.take(n->cas.size() * size_t(N) * 64 * sizeof(float)));
+    QScaleJob* qj = static_cast<QScaleJob*>(bp.take(n->cas.size() * sizeof(QScaleJob)));
+    if (build) {
+      n->q_scale = q_scale; n->q_jobs_dev = qj; n->q_jobs_uploaded.clear();
+      Op op{};
+      op.type = OP_QSCALE;
+      ops.push_back(op);
+    }
+  }
+  auto q_of = [&](int cai) -> const float* {
+    if (!n->qrcan || (n->qs[cai].w1 < 0 && !n->modulate)) return nullptr;
+    return q_scale + size_t(cai) * N * 64;
+  };
   const void* cur_b = head_b;     // bf16 operand of the running activation
   const float* cur_f = head_f;    // its fp32 residual-stream copy
   const int Cr = n->arch == 0 ? C / n->reduction : 1;
@@ -284,6 +336,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           void* u = training ? bp.take(px * C * 2) : nullptr;
           float* sv = training ? static_cast<float*>(bp.take(size_t(N) * (2 * C + Cr) * 4)) : nullptr;
           if (TrunkLayer* l = add_layer(kTrunkCA, c2 + 1, cai, t, xb)) {
+            l->q_scale = q_of(cai);
             if (training) {
               l->u_map = out_of(u);
               l->save_mean = sv; l->save_y = sv + size_t(N) * C; l->save_hid = sv + size_t(N) * 2 * C;
@@ -341,7 +394,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     float* pool_compact = static_cast<float*>(bp.take(size_t(N) * 64 * C * 4));
     const size_t n_rcab = size_t(n->n_groups) * n->n_blocks;
     unsigned long long* ca_counters = static_cast<unsigned long long*>(bp.take(n_rcab * sizeof(unsigned long long)));
-    const bool fuse_ca = g_use_fused_ca && n->u_f32 && build && conv_ca_supported(N, H, W, C, C);
+    const bool fuse_ca = g_use_fused_ca && !n->qrcan && n->u_f32 && build && conv_ca_supported(N, H, W, C, C);
     if (build) { n->ca_counters = ca_counters; n->ca_counters_bytes = n_rcab * sizeof(unsigned long long); n->ca_counters_dirty = true; }
     int cai = 0;
     for (int g = 0; g < n->n_groups; ++g) {
@@ -386,6 +439,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         ca.ca = n->cas[cai++];
         ca.pool = pool; ca.u = u; ca.x_in = ca_x_in; ca.x_out = S_f; ca.x_out_b = xb;
         ca.pool_compact = pool_compact;
+        ca.q_scale = q_of(cai - 1);
         if (sv) { ca.save_mean = sv; ca.save_y = sv + size_t(N) * C; ca.save_hid = sv + size_t(N) * 2 * C; }
         ops.push_back(ca);
         }
@@ -799,6 +853,50 @@ int rumpy_net_create(void** out, int arch, int n_feats, int n_groups, int n_bloc
   return RUMPY_OK;
 }
 
+/* Q-RCAN (meta-attention RCAN, reference attention_manipulators/architectures.py:313-462 with style 'standard' or
+ * 'modulate' and optional q-layers, q_layer.py:5-45).  rcab_has_q[g*n_blocks+b] != 0: that RCAB carries a 2-layer
+ * ParaCALayer (num_metadata -> q_hidden -> n_feats).  Parameter order = the reference's state_dict order. */
+int rumpy_net_create_q(void** out, int n_feats, int n_groups, int n_blocks, int reduction, int scale, int in_feats,
+                       int out_feats, int num_metadata, int q_hidden, const unsigned char* rcab_has_q, int modulate) {
+  if (!out || !rcab_has_q) return set_error(RUMPY_ERR_ARG, "net_create_q: null pointer");
+  if (n_feats != 64) return set_error(RUMPY_ERR_ARG, "net_create_q: n_feats=%d (64 supported)", n_feats);
+  if (in_feats < 1 || in_feats > 4 || out_feats < 1 || out_feats > 4)
+    return set_error(RUMPY_ERR_ARG, "net_create_q: in_feats=%d out_feats=%d (1..4 supported)", in_feats, out_feats);
+  if (reduction < 1 || n_feats % reduction != 0 || n_feats / reduction > 16)
+    return set_error(RUMPY_ERR_ARG, "net_create_q: reduction=%d", reduction);
+  if (num_metadata < 1 || num_metadata > 1024 || q_hidden < 1 || q_hidden > 1024)
+    return set_error(RUMPY_ERR_ARG, "net_create_q: num_metadata=%d q_hidden=%d", num_metadata, q_hidden);
+  Net* n = new Net();
+  n->arch = 0; n->qrcan = true;
+  n->C = n_feats; n->n_groups = n_groups; n->n_blocks = n_blocks; n->reduction = reduction;
+  n->scale = scale; n->res_scale = 1.f; n->in_feats = in_feats; n->out_feats = out_feats; n->u_f32 = 1;
+  n->num_meta = num_metadata; n->q_hidden = q_hidden; n->modulate = modulate;
+  n->qs.resize(size_t(n_groups) * n_blocks);
+  for (size_t i = 0; i < n->qs.size(); ++i) n->qs[i] = CAW{rcab_has_q[i] ? 0 : -1, -1, -1, -1};
+  if (int e = net_init(n)) { delete n; return e; }
+  *out = n;
+  return RUMPY_OK;
+}
+
+/* metadata: device fp32 [N][num_metadata] (what QRCAN.forward receives as `metadata`, squeezed); read by the next
+ * rumpy_net_forward of a Q-RCAN handle on its stream.  M = num_metadata; style 'modulate' without q-layers
+ * also takes M = n_feats (the handler's scale_qpi vector, reference attention_manipulators/handlers.py:65-73). */
+int rumpy_net_set_metadata(void* net, const float* metadata, int N, int M) {
+  Net* n = static_cast<Net*>(net);
+  if (!n || !n->qrcan) return set_error(RUMPY_ERR_ARG, "net_set_metadata: not a Q-RCAN handle");
+  bool any_q = false;
+  for (const CAW& q : n->qs) any_q |= q.w1 >= 0;
+  if (any_q && M != n->num_meta)
+    return set_error(RUMPY_ERR_ARG, "net_set_metadata: %d attributes per image, the q-layers take %d", M, n->num_meta);
+  if (n->modulate && M != 1 && M != n->C)
+    return set_error(RUMPY_ERR_ARG, "net_set_metadata: style 'modulate' takes 1 or %d attributes per image, got %d", n->C, M);
+  if (M < 1 || M > 1024) return set_error(RUMPY_ERR_ARG, "net_set_metadata: M=%d", M);
+  n->meta_dev = metadata;
+  n->meta_n = N;
+  n->meta_m = M;
+  return RUMPY_OK;
+}
+
 int rumpy_net_destroy(void* net) {
   delete static_cast<Net*>(net);
   return RUMPY_OK;
@@ -903,6 +1001,30 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
                                     n->C, stream))
           return e;
         break;
+      case OP_QSCALE: {
+        if (!n->meta_dev || n->meta_n != N)
+          return set_error(RUMPY_ERR_ARG, "Q-RCAN forward: call rumpy_net_set_metadata with a [%d][%d] tensor first", N,
+                           n->num_meta);
+        std::vector<QScaleJob> jobs(n->cas.size());
+        for (size_t i = 0; i < jobs.size(); ++i) {
+          const CAW& q = n->qs[i];
+          jobs[i] = q.w1 >= 0 ? QScaleJob{params[q.w1], params[q.b1], params[q.w2], params[q.b2], nullptr}
+                              : QScaleJob{nullptr, nullptr, nullptr, nullptr, nullptr};
+          jobs[i].out = n->q_scale + i * size_t(N) * 64;
+        }
+        if (jobs.size() != n->q_jobs_uploaded.size() ||
+            memcmp(jobs.data(), n->q_jobs_uploaded.data(), jobs.size() * sizeof(QScaleJob)) != 0) {
+          n->q_jobs_uploaded = jobs;
+          if (cudaMemcpyAsync(n->q_jobs_dev, n->q_jobs_uploaded.data(), jobs.size() * sizeof(QScaleJob),
+                              cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            return set_error(RUMPY_ERR_CUDA, "Q-RCAN: job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+          cudaStreamSynchronize(stream);
+        }
+        if (int e = q_scale_launch(n->q_jobs_dev, int(jobs.size()), n->meta_dev,
+                                   N, n->meta_m, n->q_hidden, n->modulate, stream))
+          return e;
+        break;
+      }
       case OP_CONV:
         if (int e = launch_conv_op(op, params, y_nchw, stream)) return e;
         break;
@@ -919,7 +1041,7 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
         if (int e = ca_apply_launch(op.pool, 2 * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW),
                                     op.pool_compact, op.u, n->u_f32, op.x_in, params[op.ca.w1], params[op.ca.b1],
                                     params[op.ca.w2], params[op.ca.b2], op.x_out, op.x_out_b, op.save_mean,
-                                    op.save_hid, op.save_y, N, H, W, n->C, n->C / n->reduction, stream))
+                                    op.save_hid, op.save_y, N, H, W, n->C, n->C / n->reduction, stream, op.q_scale))
           return e;
         break;
       default:

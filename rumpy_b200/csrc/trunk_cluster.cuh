@@ -399,7 +399,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
           for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
           yacc = fmaf(__ldg(w2 + c * cr + h), fmaxf(sdot + __ldg(b1 + h), 0.f), yacc);
         }
-        if (hsel == 0) y_e[c] = 1.f / (1.f + __expf(-yacc));
+        if (hsel == 0) y_e[c] = (1.f / (1.f + __expf(-yacc))) * (lay->q_scale ? __ldg(lay->q_scale + n * 64 + c) : 1.f);
         named_bar_sync(bar_id, 128);
       };
 

@@ -43,6 +43,7 @@ struct TrunkLayer {
   float* out_f32;        // kTrunkRes: optional fp32 NHWC copy of the result (a later layer's res_f32)
   const float *w1, *b1, *w2, *b2;          // kTrunkCA: FC weights [cr][64], [cr], [64][cr], [64]
   float *save_mean, *save_hid, *save_y;    // kTrunkCA (training): CA vectors for backward, or nullptr
+  const float* q_scale;  // kTrunkCA, Q-RCAN: [N][64] meta-attention multipliers of the CA vector, or nullptr
 };
 
 struct TrunkArgs {
@@ -491,7 +492,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
           yacc = fmaf(__ldg(w2 + c * cr + h), hv, yacc);
           if (saver && lane == 0) lay->save_hid[n * cr + h] = hv;
         }
-        if (hsel == 0) y_s[j][c] = 1.f / (1.f + __expf(-yacc));
+        if (hsel == 0) y_s[j][c] = (1.f / (1.f + __expf(-yacc))) * (lay->q_scale ? __ldg(lay->q_scale + n * 64 + c) : 1.f);
         if (saver) {
           lay->save_mean[n * 64 + lane] = m0;
           lay->save_mean[n * 64 + 32 + lane] = m1;

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-ARCH_RCAN, ARCH_EDSR = 0, 1
+ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN = 0, 1, 2
 
 _FLAT = {}   # id(first parameter) -> (flat fp32 buffer, weakref to first parameter): shared by engine and FusedAdam
 
@@ -49,13 +49,21 @@ def flatten_parameters(params):
 
 class TrunkEngine:
     def __init__(self, arch, params, *, n_feats, n_groups, n_blocks, reduction=16, scale=4, res_scale=1.0,
-                 in_feats=3, out_feats=3, u_f32=True):
+                 in_feats=3, out_feats=3, u_f32=True, num_metadata=0, q_hidden=0, rcab_has_q=None, modulate=False):
         self.lib = _lib.load()
         self.arch, self.scale, self.in_feats, self.out_feats = arch, scale, in_feats, out_feats
         self.params = list(params)
         h = ctypes.c_void_p()
-        _lib.call('rumpy_net_create', ctypes.byref(h), arch, n_feats, n_groups, n_blocks, reduction, scale,
-                  float(res_scale), in_feats, out_feats, int(u_f32))
+        self._meta = None
+        if arch == ARCH_QRCAN:
+            flags = bytes(bytearray(int(bool(f)) for f in rcab_has_q))
+            if len(flags) != n_groups * n_blocks:
+                raise ValueError('rcab_has_q needs one flag per RCAB')
+            _lib.call('rumpy_net_create_q', ctypes.byref(h), n_feats, n_groups, n_blocks, reduction, scale, in_feats,
+                      out_feats, int(num_metadata), int(q_hidden), flags, int(bool(modulate)))
+        else:
+            _lib.call('rumpy_net_create', ctypes.byref(h), arch, n_feats, n_groups, n_blocks, reduction, scale,
+                      float(res_scale), in_feats, out_feats, int(u_f32))
         self.handle = h
         n = self.lib.rumpy_net_num_params(h)
         if n != len(self.params):
@@ -138,6 +146,23 @@ class TrunkEngine:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
+
+    # ------------------------------------------------------------------ Q-RCAN metadata
+    def set_metadata(self, metadata, N):
+        """metadata: [N, M, 1, 1] or [N, M] tensor (what QRCAN.forward receives).  It is copied into a buffer the
+        engine owns (static address: CUDA-graph replays see the new values)."""
+        if self.arch != ARCH_QRCAN:
+            raise _lib.RumpyB200Error('set_metadata: not a Q-RCAN engine')
+        if metadata is None:
+            raise RuntimeError('Metadata needs to be specified for this network to run properly.')
+        m = metadata.reshape(metadata.shape[0], -1).to(device=self.device, dtype=torch.float32)
+        if m.shape[0] != N:
+            raise ValueError(f'metadata for {m.shape[0]} images, batch has {N}')
+        if self._meta is None or self._meta.shape != m.shape:
+            self._meta = torch.empty_like(m)
+            self._graphs.clear()
+        self._meta.copy_(m)
+        _lib.call('rumpy_net_set_metadata', self.handle, self._meta.data_ptr(), int(N), int(m.shape[1]))
 
     # ------------------------------------------------------------------ forward
     def _check_input(self, x):

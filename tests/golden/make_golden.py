@@ -188,6 +188,35 @@ def set5_case(arch_mod):
     return rec
 
 
+def qrcan_cases():
+    """Q-RCAN (meta-attention) forward through the reference's QRCAN module; 'modulate' attributes through the
+    reference handler's own scale_qpi arithmetic (attention_manipulators/handlers.py:59-73)."""
+    from rumpy.SISR.models.attention_manipulators import architectures as qarch
+    rec = {}
+    for name in recipe.QCASES:
+        kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
+        net = qarch.QRCAN(**kw)
+        assert list(net.state_dict().keys()) == list(sd.keys()), 'Q-RCAN key order mismatch vs reference'
+        net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+        net.eval()
+        attrs = t(meta).unsqueeze(2).unsqueeze(3)
+        if kw['style'] == 'modulate':
+            base = np.linspace(0, 1, 64)
+            scaled = attrs * (0.8 - (-0.2)) + (-0.2)
+            rows = []
+            for i in range(scaled.size(0)):
+                mu = scaled[i].squeeze().numpy()
+                rows.append(torch.from_numpy((1 / (np.sqrt(2 * np.pi) * 0.2)) *
+                                             np.exp(-np.power(base - mu, 2.) / (2 * np.power(0.2, 2.)))).type(torch.float32))
+            attrs = torch.stack(rows).unsqueeze(2).unsqueeze(3)
+        with torch.no_grad():
+            out = net(t(x), attrs)
+        rec[name + '::attributes'] = attrs.numpy()
+        rec[name + '::out'] = out.numpy()
+        print(name, 'out', out.shape, float(out.abs().max()))
+    return rec
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     arch_mod, common = import_reference()
@@ -197,6 +226,7 @@ def main():
         print(name, 'loss', rec['loss'], 'train', rec['train_losses'], 'out', rec['out'].shape)
     np.savez_compressed(os.path.join(HERE, 'blocks.npz'), **block_cases(arch_mod, common))
     np.savez_compressed(os.path.join(HERE, 'set5_edsr_baseline.npz'), **set5_case(arch_mod))
+    np.savez_compressed(os.path.join(HERE, 'qrcan.npz'), **qrcan_cases())
     print('done')
 
 

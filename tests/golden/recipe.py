@@ -104,3 +104,71 @@ def case_tensors(name):
     s = kw['scale']
     y = make_input((shape[0], 3, shape[2] * s, shape[3] * s), xseed + 1000)
     return arch, kw, sd, x, y
+
+
+# ---------------------------------------------------------------------------- Q-RCAN (meta-attention)
+def q_layer_sizes(num_metadata, n_feats=64):
+    """ParaCALayer's two layer widths (reference attention_manipulators/q_layer.py:24-31, num_layers=2)."""
+    if num_metadata > 15:
+        return (n_feats - num_metadata) // 2 + num_metadata, (n_feats - num_metadata) // 1 + num_metadata
+    return n_feats // 2, n_feats
+
+
+def qrcan_has_q(n_resgroups, n_resblocks, include_q_layer, selective_meta_blocks=None,
+                num_q_layers_inner_residual=None):
+    """Which RCABs own a q-node (reference attention_manipulators/architectures.py:262-266, 384-425)."""
+    flags = []
+    for g in range(n_resgroups):
+        on = include_q_layer and (selective_meta_blocks is None or bool(selective_meta_blocks[g]))
+        for b in range(n_resblocks):
+            flags.append(bool(on and (num_q_layers_inner_residual is None or b < num_q_layers_inner_residual)))
+    return flags
+
+
+def qrcan_spec(n_resgroups, n_resblocks, num_metadata, has_q, n_feats=64, reduction=16, scale=4, in_feats=3,
+               out_feats=3):
+    """state_dict layout of the reference's QRCAN (module REGISTRATION order: final_body before head/body/tail,
+    and inside a QRCAB the attention and the q-node before the convolutions)."""
+    spec = []
+    _conv_spec(spec, 'final_body', n_feats, n_feats, 3)
+    _conv_spec(spec, 'head.0', n_feats, in_feats, 3)
+    h1, h2 = q_layer_sizes(num_metadata, n_feats)
+    for g in range(n_resgroups):
+        _conv_spec(spec, f'body.{g}.final_body', n_feats, n_feats, 3)
+        for b in range(n_resblocks):
+            p = f'body.{g}.body.{b}'
+            _conv_spec(spec, p + '.final_body.conv_du.0', n_feats // reduction, n_feats, 1)
+            _conv_spec(spec, p + '.final_body.conv_du.2', n_feats, n_feats // reduction, 1)
+            if has_q[g * n_resblocks + b]:
+                _conv_spec(spec, p + '.q_node.attribute_integrator.0', h1, num_metadata, 1)
+                _conv_spec(spec, p + '.q_node.attribute_integrator.2', h2, h1, 1)
+            _conv_spec(spec, p + '.body.0', n_feats, n_feats, 3)
+            _conv_spec(spec, p + '.body.2', n_feats, n_feats, 3)
+    _tail_spec(spec, n_feats, out_feats, scale)
+    return spec
+
+
+# name -> (QRCAN ctor kwargs, lr-input shape, weight seed, input seed).  'modulate' cases feed the [N,1] quality
+# index through QRCANHandler.scale_qpi (min_mu=-0.2, max_mu=0.8) to get the [N,64] attributes, as the handler does.
+QCASES = OrderedDict(
+    qrcan_blur_q=(dict(n_resgroups=2, n_resblocks=2, scale=4, style='standard', num_metadata=10,
+                       include_q_layer=True), (2, 3, 12, 20), 61, 62),
+    qrcan_selective=(dict(n_resgroups=2, n_resblocks=3, scale=2, style='standard', num_metadata=3,
+                          include_q_layer=True, selective_meta_blocks=[True, False],
+                          num_q_layers_inner_residual=2), (3, 3, 9, 14), 63, 64),
+    qrcan_wide_meta=(dict(n_resgroups=1, n_resblocks=2, scale=4, style='standard', num_metadata=40,
+                          include_q_layer=True), (2, 3, 10, 10), 65, 66),
+    qrcan_modulate=(dict(n_resgroups=1, n_resblocks=2, scale=3, style='modulate', num_metadata=1),
+                    (2, 3, 8, 11), 67, 68),
+)
+
+
+def qcase_tensors(name):
+    kw, shape, wseed, xseed = QCASES[name]
+    has_q = qrcan_has_q(kw['n_resgroups'], kw['n_resblocks'], kw.get('include_q_layer', False),
+                        kw.get('selective_meta_blocks'), kw.get('num_q_layers_inner_residual'))
+    spec = qrcan_spec(kw['n_resgroups'], kw['n_resblocks'], kw['num_metadata'], has_q, scale=kw['scale'])
+    sd = make_weights(spec, wseed)
+    x = make_input(shape, xseed)
+    meta = make_input((shape[0], kw['num_metadata']), xseed + 500)
+    return kw, has_q, sd, x, meta

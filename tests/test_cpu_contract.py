@@ -63,10 +63,29 @@ def test_state_dict_layout_matches_reference_spec():
             [k for k, _ in recipe.rcan_spec(1, 1, scale=scale)]
 
 
+def test_qrcan_state_dict_layout_matches_reference_spec():
+    """Q-RCAN mirrors keep the reference's REGISTRATION order (final_body first; attention and q-node before the
+    convolutions inside a block): tests/golden/make_golden.py asserted recipe.qrcan_spec against the reference."""
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+    for name in recipe.QCASES:
+        kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
+        m = QRCAN(**kw)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, v.shape) for k, v in sd.items()], name
+        assert m._cfg['rcab_has_q'] == has_q
+    full = QRCAN(style='standard', num_metadata=10, include_q_layer=True)     # sample q-rcan.toml configuration
+    assert sum(p.numel() for p in full.parameters()) == 15592355 + 200 * (10 * 32 + 32 + 32 * 64 + 64)
+    with pytest.raises(NotImplementedError):
+        QRCAN(style='max_concat')
+    with pytest.raises(NotImplementedError):
+        QRCAN(style='standard', include_sft_layer=True)
+    with pytest.raises(RuntimeError):
+        QRCAN(style='standard', reduction=8)
+
+
 def test_registry_and_legacy_switch():
     from rumpy_b200.shared_framework.models import available_models
     from rumpy_b200.shared_framework.models.base_architecture import BaseModel
-    assert set(available_models) == {'rcan', 'edsr'}
+    assert set(available_models) == {'rcan', 'edsr', 'qrcan'}
     sd = {'model.module.head.0.weight': 1, 'model.body.0.bias': 2, 'tail.1.bias': 3}
     assert list(BaseModel.legacy_switch(sd)) == ['head.0.weight', 'body.0.bias', 'tail.1.bias']
     with pytest.raises(RuntimeError):

@@ -1,0 +1,129 @@
+"""GPU parity of the Q-RCAN (meta-attention) widening: the native QRCAN module / QRCANHandler against outputs of
+the unmodified reference (tests/golden/qrcan.npz) and the CPU oracle, in all three trunk modes."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import recipe
+from oracle import sr_torch_cpu
+
+pytestmark = pytest.mark.gpu
+
+MODES = {'per-layer': (0, 0), 'dataflow': (1, 0), 'cluster': (1, 1)}
+
+
+def _dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+def _lib():
+    from rumpy_b200 import _lib
+    lib = _lib.load()
+    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
+    return lib
+
+
+def _qrcan(kw, sd):
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+    net = QRCAN(**kw)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return net.to(_dev()).eval()
+
+
+@pytest.mark.parametrize('name', list(recipe.QCASES))
+def test_qrcan_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
+    gold = np.load(os.path.join(golden_dir, 'qrcan.npz'))
+    kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
+    net = _qrcan(kw, sd)
+    attrs = torch.from_numpy(gold[name + '::attributes']).to(_dev())
+    xt = torch.from_numpy(x).to(_dev())
+    ref = gold[name + '::out']
+    lib = _lib()
+    outs = {}
+    try:
+        for mode, (trunk, cluster) in MODES.items():
+            lib.rumpy_debug_set_trunk(trunk)
+            lib.rumpy_debug_set_trunk_cluster(cluster)
+            eng = net.native_engine()
+            eng._ws.clear()
+            eng._graphs.clear()
+            eng._last_infer_shape = None
+            with torch.no_grad():
+                a = net(xt, attrs).clone()       # eager launch
+                b = net(xt, attrs).clone()       # CUDA-graph replay of the same shape
+            assert bool((a == b).all()), f'{mode}: graph replay differs from the eager forward'
+            outs[mode] = a.cpu().numpy()
+            err = float(np.abs(outs[mode] - ref).max())
+            assert err <= 1e-2, f'{name} [{mode}]: max-abs {err} vs the reference output'
+    finally:
+        lib.rumpy_debug_set_trunk(1)
+        lib.rumpy_debug_set_trunk_cluster(1)
+    for mode in ('dataflow', 'cluster'):
+        assert float(np.abs(outs[mode] - outs['per-layer']).max()) <= 5e-3
+
+
+def test_qrcan_metadata_changes_output_through_graph_replay():
+    """New metadata with the same batch shape must reach the replayed CUDA graph (static metadata buffer)."""
+    kw, has_q, sd, x, meta = recipe.qcase_tensors('qrcan_blur_q')
+    net = _qrcan(kw, sd)
+    xt = torch.from_numpy(x).to(_dev())
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    for seed in (1, 2, 3):
+        m = recipe.make_input(meta.shape, seed)
+        attrs = torch.from_numpy(m).unsqueeze(2).unsqueeze(3)
+        with torch.no_grad():
+            out = net(xt, attrs.to(_dev())).cpu().numpy()
+        ref = sr_torch_cpu.qrcan_forward(tsd, torch.from_numpy(x), attrs, kw['n_resgroups'], kw['n_resblocks'],
+                                         kw['scale'], kw['style']).numpy()
+        assert float(np.abs(out - ref).max()) <= 1e-2, f'metadata seed {seed}'
+
+
+def test_qrcan_handler_run_eval_with_metadata_keys(tmp_path):
+    """QRCANHandler.run_eval(x, metadata=..., metadata_keys=...) selects the handler's metadata columns, builds
+    the [N,M,1,1] vector (reference attention_manipulators/__init__.py:87-108) and runs the native trunk."""
+    from rumpy_b200.shared_framework.models import define_model
+    h = define_model('qrcan', device=0, model_save_dir=str(tmp_path), eval_mode=True, scale=4, style='standard',
+                     metadata=['blur_sigma', 'noise'], include_q_layer=True, n_resgroups=1, n_resblocks=2)
+    assert h.model_name == 'qrcan' and h.num_metadata == 2 and h.colorspace == 'augmented_rgb'
+    spec = [(k, tuple(v.shape)) for k, v in h.net.state_dict().items()]
+    sd = recipe.make_weights(spec, seed=70)
+    h.net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    x = recipe.make_input((2, 3, 16, 12), 71)
+    table = torch.from_numpy(recipe.make_input((2, 3), 72))      # columns: blur_sigma, jpeg (unused), noise
+    keys = [('blur_sigma',), ('jpeg_quality',), ('noise',)]
+    out, loss, _ = h.run_eval(torch.from_numpy(x), metadata=table, metadata_keys=keys)
+    assert tuple(out.shape) == (2, 3, 64, 48) and out.device.type == 'cpu' and loss is None
+    attrs = table[:, [0, 2]].unsqueeze(2).unsqueeze(3)
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ref = sr_torch_cpu.qrcan_forward(tsd, torch.from_numpy(x), attrs, 1, 2, 4, 'standard').numpy()
+    assert float(np.abs(out.numpy() - ref).max()) <= 1e-2
+    assert h.metadata_keys_used_in_training == ['blur_sigma', 'jpeg_quality', 'noise']
+    with pytest.raises(NotImplementedError):
+        h.eval_mode = False
+        h.run_train(torch.from_numpy(x), torch.zeros(2, 3, 64, 48), metadata=table, metadata_keys=keys)
+
+
+def test_qrcan_full_size_uses_cluster_kernel():
+    """Sample q-rcan.toml configuration (10 groups x 20 blocks, blur-kernel metadata M=10, q-node in every RCAB)
+    at BASELINE configs[1]'s batch: same launch structure as RCAN plus one metadata kernel; oracle parity."""
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+    net = QRCAN(style='standard', num_metadata=10, include_q_layer=True)
+    spec = [(k, tuple(v.shape)) for k, v in net.state_dict().items()]
+    sd = recipe.make_weights(spec, seed=80)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    net = net.to(_dev()).eval()
+    x = recipe.make_input((16, 3, 48, 48), 81)
+    attrs = torch.from_numpy(recipe.make_input((16, 10), 82)).unsqueeze(2).unsqueeze(3)
+    with torch.no_grad():
+        out = net(torch.from_numpy(x).to(_dev()), attrs.to(_dev())).cpu().numpy()
+    eng = net.native_engine()
+    assert _lib().rumpy_net_trunk_mode(eng.handle) == 2
+    assert _lib().rumpy_net_num_launches(eng.handle) == 6      # head, metadata, trunk, 2 upsampler convs, tail
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ref = sr_torch_cpu.qrcan_forward(tsd, torch.from_numpy(x), attrs, 10, 20, 4, 'standard').numpy()
+    assert float(np.abs(out - ref).max()) <= 1e-2
