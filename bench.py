@@ -341,7 +341,90 @@ def extra_configs(device):
                                  'note': 'batch 16 x 64x64 LR patches per GPU (BASELINE gives no batch size)'}
     del net, opt
     torch.cuda.empty_cache()
+    # Q-RCAN (meta-attention; sample q-rcan.toml: blur-kernel metadata M=10, q-node in every
+    # RCAB) at configs[1]'s batch, through QRCAN.forward(x, metadata)
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+    qnet = QRCAN(style='standard', num_metadata=10, include_q_layer=True)
+    qspec = [(k, tuple(v.shape)) for k, v in qnet.state_dict().items()]
+    qnet.load_state_dict({k: torch.from_numpy(v) for k, v in recipe.make_weights(qspec, seed=8).items()}, strict=True)
+    qnet = qnet.to(device).eval()
+    x = torch.rand((BATCH, 3, LR_HW, LR_HW), device=device)
+    meta = torch.rand((BATCH, 10, 1, 1), device=device)
+    with torch.no_grad():
+        for _ in range(3):
+            qnet(x, meta)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(10):
+            qnet(x, meta)
+        e1.record()
+        e1.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    out['qrcan_x4_infer'] = {'ms_per_step': ms, 'out_mpix_per_s': OUT_MPIX_PER_STEP / (ms * 1e-3),
+                             'launches': int(qnet.native_engine().lib.rumpy_net_num_launches(qnet.native_engine().handle)),
+                             'note': f'{BATCH} x {LR_HW}x{LR_HW}, metadata copy + graph replay + output clone per call'}
+    del qnet
+    torch.cuda.empty_cache()
+    out['torch_eager_gpu_baseline'] = eager_gpu_baseline(device)
     return out
+
+
+def eager_gpu_baseline(device):
+    """Like-for-like GPU baseline: the reference's arithmetic as PyTorch eager (cuDNN) on the SAME B200 --
+    the oracle's functional restatement of RCAN.forward / run_train moved to the device, in fp32, TF32 and
+    bf16-autocast.  Baseline leg only (reported beside cpu_baseline, never the measured product)."""
+    from oracle import sr_torch_cpu
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    sd = {k: torch.from_numpy(v).to(device) for k, v in make_state_dict().items()}
+    x = torch.rand((BATCH, 3, LR_HW, LR_HW), device=device)
+    res = {}
+
+    def timed(fn, iters):
+        for _ in range(2):
+            fn()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / iters
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for mode in ('fp32', 'tf32', 'bf16_autocast'):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (mode == 'tf32')
+
+            def fwd():
+                with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=(mode == 'bf16_autocast')):
+                    return sr_torch_cpu.rcan_forward(sd, x, 10, 20, SCALE)
+            ms = timed(fwd, 5)
+            res['infer_' + mode] = {'ms_per_step': ms, 'out_mpix_per_s': OUT_MPIX_PER_STEP / (ms * 1e-3)}
+        xt = torch.rand((16, 3, 64, 64), device=device)
+        yt = torch.rand((16, 3, 256, 256), device=device)
+        for mode in ('fp32', 'tf32', 'bf16_autocast'):
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = (mode == 'tf32')
+            params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+            opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+
+            def step():
+                with torch.autocast('cuda', dtype=torch.bfloat16, enabled=(mode == 'bf16_autocast')):
+                    o = sr_torch_cpu.rcan_forward(params, xt, 10, 20, SCALE)
+                loss = torch.nn.functional.l1_loss(o.float(), yt)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            ms = timed(step, 3)
+            res['train_' + mode] = {'ms_per_step': ms, 'patches_per_s': 16 / (ms * 1e-3)}
+            del params, opt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    res['note'] = ('torch %s eager, cuDNN, same weights and shapes as configs[1] / configs[2]; bf16_autocast fails the '
+                   '1e-2 output tolerance (BASELINE.md bf16 risk probe) and is listed for speed only' % torch.__version__)
+    return res
 
 
 def run_b200(args, rank, world):

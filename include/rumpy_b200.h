@@ -134,18 +134,23 @@ int rumpy_net_num_launches_backward(void* net); /* kernels per backward of the c
  * The mode is picked per (N,H,W) when the plan is built; all three compute the same layer program. */
 int rumpy_net_trunk_mode(void* net);
 
-/* Q-RCAN: RCAN whose RCABs are modulated by per-image metadata ("meta-attention").
- * Replaces QRCAN.__init__ / QRCAN.forward (reference SISR/models/attention_manipulators/architectures.py:313-462)
- * for QCALayer style 'standard' or 'modulate' (:113-116, :127-128) with optional 2-layer ParaCALayer q-nodes
- * (q_layer.py:5-45, used at architectures.py:198-219):
- *     RCAB(x) = x + conv2(relu(conv1(x))) * CA(.) * [attributes] * [sigmoid(FC2 relu(FC1 metadata))]
- * rcab_has_q[g * n_blocks + b] != 0: that RCAB owns a q-node (num_metadata -> q_hidden -> n_feats).  params are in
- * the reference's state_dict order (final_body | head | per group: final_body, per block: final_body.conv_du,
- * [q_node.attribute_integrator], body.0, body.2 | tail).  Inference only: rumpy_net_forward with training != 0 and
- * rumpy_net_backward return RUMPY_ERR_ARG.  The metadata multipliers are evaluated by one small kernel per forward
- * and applied inside the trunk kernels' channel-attention step. */
-int rumpy_net_create_q(void** net, int n_feats, int n_groups, int n_blocks, int reduction, int scale, int in_feats,
-                       int out_feats, int num_metadata, int q_hidden, const unsigned char* rcab_has_q, int modulate);
+/* Meta-attention networks: the same trunks modulated by per-image metadata.
+ *   arch 0  Q-RCAN: replaces QRCAN.__init__/forward (reference SISR/models/attention_manipulators/architectures.py
+ *           :313-462) for QCALayer style 'standard' or 'modulate' (:113-116, :127-128) with optional q-nodes:
+ *               RCAB(x) = x + conv2(relu(conv1(x))) * CA(.) * [attributes] * [q]
+ *           params: final_body | head | per group: final_body, per block: final_body.conv_du, [q_node], body.0,
+ *           body.2 | tail   (the reference's registration order);
+ *   arch 1  Q-EDSR: replaces QEDSR (:496-556) / ParamResBlock (:463-493):
+ *               ResBlock(x) = x + res_scale * conv2(relu(conv1(x))) * [q]
+ *           params: head | final_body | per block: body.0, body.2, [attention_layer] | tail;  n_groups ignored.
+ * q = sigmoid(FC2 act(FC1 metadata)) is the reference's 2-layer ParaCALayer (q_layer.py:5-45): num_metadata ->
+ * q_hidden -> n_feats, act = ReLU iff q_relu.  block_has_q[i] != 0: block i owns one.  Inference only:
+ * rumpy_net_forward with training != 0 and rumpy_net_backward return RUMPY_ERR_ARG.  All multipliers are evaluated
+ * by ONE small kernel per forward and applied inside the trunk kernels (channel-attention step / residual epilogue)
+ * or, for shapes outside the trunk kernels' envelope, in the per-layer kernels' epilogues. */
+int rumpy_net_create_q(void** net, int arch, int n_feats, int n_groups, int n_blocks, int reduction, int scale,
+                       float res_scale, int in_feats, int out_feats, int num_metadata, int q_hidden,
+                       const unsigned char* block_has_q, int modulate, int q_relu);
 /* metadata: device fp32 [N][M] (the `metadata` tensor of QRCAN.forward, [N,M,1,1] squeezed); it is read by every
  * following rumpy_net_forward on that call's stream, so it must stay allocated. */
 int rumpy_net_set_metadata(void* net, const float* metadata, int N, int M);

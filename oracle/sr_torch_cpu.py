@@ -101,6 +101,27 @@ def qrcan_forward(sd, x, attributes, n_resgroups, n_resblocks, scale=4, style='s
     return _tail(sd, res, scale)
 
 
+def qedsr_forward(sd, x, attributes, num_blocks, res_scale=0.1, scale=4):
+    """Q-EDSR forward (reference attention_manipulators/architectures.py: QEDSR.forward :549-555,
+    ParamResBlock.forward :484-493).  The integrator's second conv is `.2` when a ReLU separates the two
+    fully-connected layers (q_layer_nonlinearity) and `.1` when it does not."""
+    def conv(key, v):
+        w = sd[key + '.weight']
+        return F.conv2d(v, w, sd[key + '.bias'], padding=w.shape[-1] // 2)
+    x = conv('head', x)
+    res = x
+    for b in range(num_blocks):
+        r = conv(f'body.{b}.body.2', F.relu(conv(f'body.{b}.body.0', res))).mul(res_scale)
+        p = f'body.{b}.attention_layer.attribute_integrator'
+        if p + '.0.weight' in sd:
+            q = conv(p + '.0', attributes)
+            q = conv(p + '.2', F.relu(q)) if p + '.2.weight' in sd else conv(p + '.1', q)
+            r = r * torch.sigmoid(q)
+        res = r + res
+    res = conv('final_body', res) + x
+    return _tail(sd, res, scale)
+
+
 def infer_arch(sd):
     """Recover (arch, kwargs) from a reference-layout state_dict."""
     keys = list(sd.keys())

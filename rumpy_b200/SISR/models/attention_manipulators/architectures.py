@@ -1,5 +1,5 @@
-"""B200-native mirror of the reference's Q-RCAN (meta-attention RCAN)
-(/root/reference/rumpy/SISR/models/attention_manipulators/architectures.py:46-462).
+"""B200-native mirror of the reference's Q-RCAN and Q-EDSR (meta-attention RCAN / EDSR)
+(/root/reference/rumpy/SISR/models/attention_manipulators/architectures.py:46-556).
 
 Same class names, constructor signatures, module tree, registration order and state_dict keys as the reference
 for the configurations the native trunk implements:
@@ -10,7 +10,10 @@ Everything else the reference's QRCAN can be configured with (pixel attention, S
 concat styles, staggered encodings, outer metadata reduction) is outside SURVEY.md section 8 and raises
 NotImplementedError at construction.  Inference only (training the meta-attention is a 'next' row).
 
-`QRCAN.forward(x, metadata)` hands the parameter list and the metadata to the native executor: the metadata
+`QEDSR` (ParamResBlocks: res_scale * conv2(relu(conv1 x)) * q + x) keeps the reference's ctor and key layout too
+(`head.weight` without a Sequential index, `final_body` registered before `body`).
+
+`QRCAN.forward(x, metadata)` / `QEDSR.forward(x, metadata)` hand the parameter list and the metadata to the native executor: the metadata
 multipliers q[rcab][n][c] are computed by one kernel, and the whole body runs in the same trunk kernel as RCAN
 with q multiplied into the channel-attention vector.
 """
@@ -170,7 +173,7 @@ class QRCAN(_NativeTrunk):
                     q_hidden = blk.q_node.layer_sizes[1]
         self._cfg = dict(n_feats=n_feats, n_groups=n_resgroups, n_blocks=n_resblocks, reduction=reduction,
                          scale=scale, in_feats=in_feats, out_feats=out_feats, num_metadata=num_metadata,
-                         q_hidden=max(q_hidden, 1), rcab_has_q=has_q, modulate=(style == 'modulate'))
+                         q_hidden=max(q_hidden, 1), block_has_q=has_q, modulate=(style == 'modulate'))
 
     def _engine_kwargs(self):
         return _engine.ARCH_QRCAN, dict(self._cfg)
@@ -184,3 +187,60 @@ class QRCAN(_NativeTrunk):
 
     def forensic(self, x, qpi, *args, **kwargs):
         raise NotImplementedError('rumpy_b200: forensic() diagnostics are not part of the native trunk')
+
+
+class ParamResBlock(nn.Module):
+    """reference architectures.py:463-493.  Registration order: body, attention_layer."""
+
+    def __init__(self, conv, n_feats, n_params, kernel_size, act=nn.ReLU(True), bias=True, res_scale=1.0,
+                 q_layer_nonlinearity=False, add_q_layer=None, num_layers=2):
+        super(ParamResBlock, self).__init__()
+        if add_q_layer and num_layers != 2:
+            raise NotImplementedError('rumpy_b200 ParamResBlock: q-layers with 2 fully-connected layers only')
+        m = []
+        for i in range(2):
+            m.append(conv(n_feats, n_feats, kernel_size, bias=bias))
+            if i == 0:
+                m.append(act)
+        self.body = nn.Sequential(*m)
+        self.add_q_layer = add_q_layer
+        if self.add_q_layer:
+            self.attention_layer = ParaCALayer(n_feats, n_params, nonlinearity=q_layer_nonlinearity,
+                                               num_layers=num_layers)
+        self.res_scale = res_scale
+
+    def forward(self, x):
+        raise _lib.RumpyB200Error('ParamResBlock ' + _NATIVE_ONLY)
+
+
+class QEDSR(_NativeTrunk):
+    """reference architectures.py:496-556"""
+
+    def __init__(self, in_features=3, out_features=3, num_features=64, input_para=1, num_blocks=16, scale=4,
+                 res_scale=0.1, q_layer_nonlinearity=False, selective_meta_blocks=None, num_layers=2, **kwargs):
+        super(QEDSR, self).__init__()
+        n_feats = num_features
+        kernel_size = 3
+        if selective_meta_blocks == 'front_only':
+            selective_meta_blocks = [True] + [False] * (num_blocks - 1)
+        self.head = common.default_conv(in_features, n_feats, kernel_size)
+        m_body = [
+            ParamResBlock(common.default_conv, n_feats, input_para, kernel_size, res_scale=res_scale,
+                          q_layer_nonlinearity=q_layer_nonlinearity,
+                          add_q_layer=True if selective_meta_blocks is None else selective_meta_blocks[i],
+                          num_layers=num_layers) for i in range(num_blocks)]
+        self.final_body = common.default_conv(n_feats, n_feats, kernel_size)
+        m_tail = [common.Upsampler(common.default_conv, scale, n_feats),
+                  common.default_conv(n_feats, out_features, kernel_size)]
+        self.body = nn.Sequential(*m_body)
+        self.tail = nn.Sequential(*m_tail)
+        has_q = [bool(blk.add_q_layer) for blk in self.body]
+        q_hidden = max([blk.attention_layer.layer_sizes[1] for blk in self.body if blk.add_q_layer] + [1])
+        self._cfg = dict(n_feats=n_feats, n_groups=1, n_blocks=num_blocks, scale=scale, res_scale=res_scale,
+                         in_feats=in_features, out_feats=out_features, num_metadata=input_para, q_hidden=q_hidden,
+                         block_has_q=has_q, q_relu=bool(q_layer_nonlinearity))
+
+    def _engine_kwargs(self):
+        return _engine.ARCH_QEDSR, dict(self._cfg)
+
+    forward = QRCAN.forward

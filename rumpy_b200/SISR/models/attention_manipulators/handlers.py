@@ -1,11 +1,11 @@
-"""Mirror of the reference's Q-RCAN handler
-(/root/reference/rumpy/SISR/models/attention_manipulators/handlers.py:11-79): registry name 'qrcan', same
-constructor arguments and attributes; `scale_qpi` reproduces the 'modulate' style's Gaussian channel scalers."""
+"""Mirror of the reference's Q-RCAN / Q-EDSR handlers
+(/root/reference/rumpy/SISR/models/attention_manipulators/handlers.py:11-103): registry names 'qrcan' / 'qedsr',
+same constructor arguments and attributes; `scale_qpi` reproduces the 'modulate' style's Gaussian channel scalers."""
 import numpy as np
 import torch
 
 from rumpy_b200.SISR.models.attention_manipulators import QModel
-from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+from rumpy_b200.SISR.models.attention_manipulators.architectures import QEDSR, QRCAN
 
 
 class QRCANHandler(QModel):
@@ -44,3 +44,17 @@ class QRCANHandler(QModel):
         if self.clamp:
             full_scalers = torch.clamp(full_scalers, 0, 1)
         return full_scalers.unsqueeze(2).unsqueeze(3)
+
+
+class QEDSRHandler(QModel):
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, in_features=3, num_blocks=16,
+                 num_features=64, res_scale=0.1, scheduler=None, scheduler_params=None, perceptual=None, **kwargs):
+        super(QEDSRHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                           **kwargs)
+        self.net = QEDSR(scale=scale, in_features=in_features, num_features=num_features, num_blocks=num_blocks,
+                         res_scale=res_scale, input_para=self.num_metadata, **kwargs)
+        self.colorspace = 'augmented_rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.model_name = 'qedsr'
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)

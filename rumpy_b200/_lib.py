@@ -31,7 +31,7 @@ SIGNATURES = {
     'rumpy_nhwc_to_nchw': [_vp, _i, _fp, _i, _i, _i, _i, _vp],
     'rumpy_pool_sum': [_fp, _fp, _i, _i, _i, _i, _vp],
     'rumpy_net_create': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i],
-    'rumpy_net_create_q': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _i, _i, _i, _c.c_char_p, _i],
+    'rumpy_net_create_q': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _c.c_char_p, _i, _i],
     'rumpy_net_set_metadata': [_vp, _fp, _i, _i],
     'rumpy_net_destroy': [_vp],
     'rumpy_net_num_params': [_vp],

@@ -157,6 +157,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.o_chunks_per_map = thin ? 1 : (d.Cout / 64) / (rout * rout);
   a.cout = thin ? 16 : d.Cout;
   a.alpha = d.alpha;
+  a.ch_scale = d.ch_scale;
   a.bias = d.bias;
   a.pool_partial = d.pool_partial;
   a.out_nchw = d.out_nchw;
@@ -262,11 +263,11 @@ int pack_batched_launch(const PackJobHost* jobs_dev, int njobs, cudaStream_t s) 
 }
 
 static_assert(sizeof(QScaleJobHost) == sizeof(QScaleJobDev), "QScaleJobHost layout mismatch");
-int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int modulate,
-                   cudaStream_t s) {
+int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C,
+                   int modulate, int relu, cudaStream_t s) {
   if (njobs <= 0) return RUMPY_OK;
-  q_scale_kernel<<<dim3(njobs, N), 64, size_t(M + hidden) * sizeof(float), s>>>(
-      reinterpret_cast<const QScaleJobDev*>(jobs_dev), meta, M, hidden, modulate);
+  q_scale_kernel<<<dim3(njobs, N), C, size_t(M + hidden) * sizeof(float), s>>>(
+      reinterpret_cast<const QScaleJobDev*>(jobs_dev), meta, M, hidden, modulate, relu);
   return check_launch("q_scale");
 }
 

@@ -52,6 +52,7 @@ struct ConvArgs {
   int stages;            // smem pipeline depth
   int stg_bufs;          // epilogue staging slots (1 or 2)
   float alpha;           // scale on (acc + bias) (res_scale / gradient scale)
+  const float* ch_scale; // [N][cout] extra per-(image, channel) scale on the same term (meta-attention), or nullptr
   const float* bias;     // [cout] in packed-row order, or nullptr
   float* pool_partial;   // [m_tiles][2][cout]
   float* out_nchw;       // BN == 16 variant only: fp32 NCHW [N][cout_real][H][W]
@@ -362,6 +363,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
               float x = __uint_as_float(v[h * 32 + i]) + bias_s[j * 64 + h * 32 + i];
               if (flags & kConvRelu) x = fmaxf(x, 0.f);
               f[i] = x * args.alpha;
+            }
+            if (args.ch_scale != nullptr) {
+              const float* cs = args.ch_scale + size_t(n) * args.cout + oc * 64 + h * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= __ldg(cs + i);
             }
             if (flags & kConvMask) {
 #pragma unroll

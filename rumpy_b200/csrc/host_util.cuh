@@ -44,6 +44,7 @@ struct ConvDesc {
   int force_bn;           // 0 = auto
   unsigned flags;
   float alpha;
+  const float* ch_scale;  // [N][Cout] per-(image, channel) multiplier of alpha * (acc + bias) (Q-EDSR), or null
 };
 
 // Everything a launch needs: tensor maps (host copy, passed by value as __grid_constant__) + args.
@@ -72,8 +73,8 @@ int ca_apply_launch(const float* pool_partial, int partials_per_img, float* comp
                     const float* q_scale = nullptr);
 // Q-RCAN meta-attention multipliers (misc_kernels.cuh q_scale_kernel): one job per RCAB
 struct QScaleJobHost { const float *w1, *b1, *w2, *b2; float* out; };
-int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int modulate,
-                   cudaStream_t s);
+int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C,
+                   int modulate, int relu, cudaStream_t s);
 
 // one conv's packing job for the batched pack kernel (misc_kernels.cuh: PackJob has the same layout)
 struct PackJobHost {

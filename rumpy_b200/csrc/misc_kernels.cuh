@@ -83,29 +83,29 @@ __global__ void pack_conv3x3_batched_kernel(const PackJob* __restrict__ jobs) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Q-RCAN meta-attention (reference attention_manipulators/q_layer.py:5-45 `ParaCALayer`, used by QRCAB.forward
-// architectures.py:198-219; QCALayer style 'modulate' :113-116): per (image, channel) multipliers of the channel-
-// attention vector that depend on the metadata only, so all RCABs are evaluated up front in one launch:
-//   q[n][c] = sigmoid(W2 relu(W1 meta[n] + b1) + b2)[c]          (RCABs with a q-layer; 2-layer integrator)
-//   q[n][c] *= meta[n][c or 0]                                   (style 'modulate')
-// grid (jobs, N), block 64.
+// Meta-attention (reference attention_manipulators/q_layer.py:5-45 `ParaCALayer`; used by QRCAB.forward
+// architectures.py:198-219 and ParamResBlock.forward :484-493; QCALayer style 'modulate' :113-116): per
+// (image, channel) multipliers that depend on the metadata only, so all blocks are evaluated up front in one launch:
+//   q[n][c] = sigmoid(W2 act(W1 meta[n] + b1) + b2)[c]     (blocks with a q-layer; act = ReLU or identity)
+//   q[n][c] *= meta[n][c or 0]                             (style 'modulate')
+// grid (jobs, N), block C (= n_feats, 64..256).
 // ------------------------------------------------------------------------------------------------
 struct QScaleJobDev { const float *w1, *b1, *w2, *b2; float* out; };
 __global__ void q_scale_kernel(const QScaleJobDev* __restrict__ jobs, const float* __restrict__ meta, int M, int hidden,
-                               int modulate) {
+                               int modulate, int relu) {
   extern __shared__ float qs_smem[];   // [M] metadata, [hidden] hidden units
   float* meta_s = qs_smem;
   float* hid_s = qs_smem + M;
   const QScaleJobDev jb = jobs[blockIdx.x];
-  const int n = blockIdx.y, c = threadIdx.x;
-  for (int m = c; m < M; m += 64) meta_s[m] = meta[size_t(n) * M + m];
+  const int n = blockIdx.y, c = threadIdx.x, C = blockDim.x;
+  for (int m = c; m < M; m += C) meta_s[m] = meta[size_t(n) * M + m];
   __syncthreads();
   float q = 1.f;
   if (jb.w1 != nullptr) {
-    for (int t = c; t < hidden; t += 64) {
+    for (int t = c; t < hidden; t += C) {
       float a = jb.b1[t];
       for (int m = 0; m < M; ++m) a = fmaf(jb.w1[size_t(t) * M + m], meta_s[m], a);
-      hid_s[t] = fmaxf(a, 0.f);
+      hid_s[t] = relu ? fmaxf(a, 0.f) : a;
     }
     __syncthreads();
     float a = jb.b2[c];
@@ -113,7 +113,7 @@ __global__ void q_scale_kernel(const QScaleJobDev* __restrict__ jobs, const floa
     q = 1.f / (1.f + __expf(-a));
   }
   if (modulate) q *= meta_s[M == 1 ? 0 : c];
-  jb.out[size_t(n) * 64 + c] = q;
+  jb.out[size_t(n) * C + c] = q;
 }
 
 // bias in packed-row order (pixel-shuffle permutation), zero padded

@@ -76,7 +76,7 @@ struct Net {
   // parameters (w1 < 0: the RCAB has none), metadata vector length, q-layer hidden width, 'modulate' style flag
   bool qrcan = false;
   std::vector<CAW> qs;
-  int num_meta = 0, q_hidden = 0, modulate = 0;
+  int num_meta = 0, q_hidden = 0, modulate = 0, q_relu = 1;
   const float* meta_dev = nullptr;
   int meta_n = 0, meta_m = 0;
   float* q_scale = nullptr;                 // [n_rcab][N][64] per-(image, channel) multipliers of the CA vector
@@ -174,7 +174,7 @@ static int net_init(Net* n) {
   for (int s = 0; s < st; ++s) add_conv(n, C * r * r, C, r);
   n->conv_tail = int(n->convs.size());
   add_conv(n, n->out_feats, C, 1, 16);  // thin tail
-  if (n->qrcan) {
+  if (n->qrcan && n->arch == 0) {
     // QRCAN registers its modules in a different order than RCAN (attention_manipulators/architectures.py:313-433,
     // 154-196, 249-294): final_body | head | per group: final_body, per block: QCALayer, [q_node], conv1, conv2 | tail
     int p = 0;
@@ -192,6 +192,22 @@ static int net_init(Net* n) {
         set(1 + g * (2 * B + 1) + 2 * b);
         set(1 + g * (2 * B + 1) + 2 * b + 1);
       }
+    }
+    for (int s2 = 0; s2 < st; ++s2) set(n->conv_up0 + s2);
+    set(n->conv_tail);
+    n->n_params = p;
+  }
+  if (n->qrcan && n->arch == 1) {
+    // QEDSR registration order (attention_manipulators/architectures.py:501-548, 463-482):
+    // head | final_body | per block: body.0, body.2, [attention_layer] | tail
+    int p = 0;
+    auto set = [&](int ci) { n->convs[ci].w_idx = p++; n->convs[ci].b_idx = p++; };
+    set(0);
+    set(n->conv_body);
+    for (int b = 0; b < n->n_blocks; ++b) {
+      set(1 + 2 * b);
+      set(2 + 2 * b);
+      if (n->qs[b].w1 >= 0) { n->qs[b] = CAW{p, p + 1, p + 2, p + 3}; p += 4; }
     }
     for (int s2 = 0; s2 < st; ++s2) set(n->conv_up0 + s2);
     set(n->conv_tail);
@@ -269,9 +285,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   // ---- Q-RCAN: per-(RCAB, image, channel) meta-attention multipliers, evaluated once per forward
   float* q_scale = nullptr;
   if (n->qrcan) {
-    if (training) return set_error(RUMPY_ERR_ARG, "Q-RCAN: training is not implemented (inference only)");
-    q_scale = static_cast<float*>(bp.take(n->cas.size() * size_t(N) * 64 * sizeof(float)));
-    QScaleJob* qj = static_cast<QScaleJob*>(bp.take(n->cas.size() * sizeof(QScaleJob)));
+    if (training) return set_error(RUMPY_ERR_ARG, "meta-attention networks: training is not implemented (inference only)");
+    q_scale = static_cast<float*>(bp.take(n->qs.size() * size_t(N) * C * sizeof(float)));
+    QScaleJob* qj = static_cast<QScaleJob*>(bp.take(n->qs.size() * sizeof(QScaleJob)));
     if (build) {
       n->q_scale = q_scale; n->q_jobs_dev = qj; n->q_jobs_uploaded.clear();
       Op op{};
@@ -281,7 +297,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   }
   auto q_of = [&](int cai) -> const float* {
     if (!n->qrcan || (n->qs[cai].w1 < 0 && !n->modulate)) return nullptr;
-    return q_scale + size_t(cai) * N * 64;
+    return q_scale + size_t(cai) * N * C;
   };
   const void* cur_b = head_b;     // bf16 operand of the running activation
   const float* cur_f = head_f;    // its fp32 residual-stream copy
@@ -364,6 +380,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         void* xb = next_out();
         if (TrunkLayer* l = add_layer(kTrunkRes, c2 + 1, -1, t, xb)) {       // conv2(.)*res_scale + x (common.py:72-73)
           l->alpha = n->res_scale; l->update_s = 1;
+          l->q_scale = q_of(b);          // Q-EDSR: (conv2(.)*res_scale) * q + x   (ParamResBlock.forward :484-493)
         }
         gr.blocks.push_back(BlockRec{cur_b, t, nullptr, nullptr, c2, c2 + 1, -1});
         c2 += 2;
@@ -470,6 +487,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       ConvDesc d2{};
       d2.x = t; d2.residual = cur_f; d2.y_f32 = S_f; d2.y_bf16 = xb; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C;
       d2.Cout = C; d2.alpha = n->res_scale;   // conv2(.)*res_scale + x   (common.py:72-73)
+      d2.ch_scale = q_of(b);
       conv_op(ops, n->convs[ci++], d2, false);
       gr.blocks.push_back(br);
       cur_b = xb; cur_f = S_f;
@@ -853,26 +871,34 @@ int rumpy_net_create(void** out, int arch, int n_feats, int n_groups, int n_bloc
   return RUMPY_OK;
 }
 
-/* Q-RCAN (meta-attention RCAN, reference attention_manipulators/architectures.py:313-462 with style 'standard' or
- * 'modulate' and optional q-layers, q_layer.py:5-45).  rcab_has_q[g*n_blocks+b] != 0: that RCAB carries a 2-layer
- * ParaCALayer (num_metadata -> q_hidden -> n_feats).  Parameter order = the reference's state_dict order. */
-int rumpy_net_create_q(void** out, int n_feats, int n_groups, int n_blocks, int reduction, int scale, int in_feats,
-                       int out_feats, int num_metadata, int q_hidden, const unsigned char* rcab_has_q, int modulate) {
-  if (!out || !rcab_has_q) return set_error(RUMPY_ERR_ARG, "net_create_q: null pointer");
-  if (n_feats != 64) return set_error(RUMPY_ERR_ARG, "net_create_q: n_feats=%d (64 supported)", n_feats);
+/* Meta-attention networks (reference SISR/models/attention_manipulators/architectures.py):
+ *   arch 0  Q-RCAN (:313-462), QCALayer style 'standard' or 'modulate', optional q-nodes in the RCABs;
+ *   arch 1  Q-EDSR (:496-556), ParamResBlocks with optional q-layers (n_groups ignored).
+ * block_has_q[i] != 0: block i (RCAB g*n_blocks+b / ResBlock b) owns a 2-layer ParaCALayer (q_layer.py:5-45:
+ * num_metadata -> q_hidden -> n_feats, ReLU in between iff q_relu).  Parameter order = the reference's state_dict. */
+int rumpy_net_create_q(void** out, int arch, int n_feats, int n_groups, int n_blocks, int reduction, int scale,
+                       float res_scale, int in_feats, int out_feats, int num_metadata, int q_hidden,
+                       const unsigned char* block_has_q, int modulate, int q_relu) {
+  if (!out || !block_has_q) return set_error(RUMPY_ERR_ARG, "net_create_q: null pointer");
+  if (arch != 0 && arch != 1) return set_error(RUMPY_ERR_ARG, "net_create_q: arch %d", arch);
+  if (arch == 0 && n_feats != 64) return set_error(RUMPY_ERR_ARG, "net_create_q: Q-RCAN n_feats=%d (64 supported)", n_feats);
+  if (n_feats % 64 != 0 || n_feats <= 0 || n_feats > 256)
+    return set_error(RUMPY_ERR_ARG, "net_create_q: n_feats=%d must be 64, 128, 192 or 256", n_feats);
   if (in_feats < 1 || in_feats > 4 || out_feats < 1 || out_feats > 4)
     return set_error(RUMPY_ERR_ARG, "net_create_q: in_feats=%d out_feats=%d (1..4 supported)", in_feats, out_feats);
-  if (reduction < 1 || n_feats % reduction != 0 || n_feats / reduction > 16)
+  if (arch == 0 && (reduction < 1 || n_feats % reduction != 0 || n_feats / reduction > 16))
     return set_error(RUMPY_ERR_ARG, "net_create_q: reduction=%d", reduction);
   if (num_metadata < 1 || num_metadata > 1024 || q_hidden < 1 || q_hidden > 1024)
     return set_error(RUMPY_ERR_ARG, "net_create_q: num_metadata=%d q_hidden=%d", num_metadata, q_hidden);
+  if (arch == 1 && modulate) return set_error(RUMPY_ERR_ARG, "net_create_q: 'modulate' is a Q-RCAN style");
   Net* n = new Net();
-  n->arch = 0; n->qrcan = true;
-  n->C = n_feats; n->n_groups = n_groups; n->n_blocks = n_blocks; n->reduction = reduction;
-  n->scale = scale; n->res_scale = 1.f; n->in_feats = in_feats; n->out_feats = out_feats; n->u_f32 = 1;
-  n->num_meta = num_metadata; n->q_hidden = q_hidden; n->modulate = modulate;
-  n->qs.resize(size_t(n_groups) * n_blocks);
-  for (size_t i = 0; i < n->qs.size(); ++i) n->qs[i] = CAW{rcab_has_q[i] ? 0 : -1, -1, -1, -1};
+  n->arch = arch; n->qrcan = true;
+  n->C = n_feats; n->n_groups = arch == 0 ? n_groups : 1; n->n_blocks = n_blocks; n->reduction = reduction;
+  n->scale = scale; n->res_scale = arch == 0 ? 1.f : res_scale; n->in_feats = in_feats; n->out_feats = out_feats;
+  n->u_f32 = 1;
+  n->num_meta = num_metadata; n->q_hidden = q_hidden; n->modulate = modulate; n->q_relu = q_relu;
+  n->qs.resize(size_t(n->n_groups) * n_blocks);
+  for (size_t i = 0; i < n->qs.size(); ++i) n->qs[i] = CAW{block_has_q[i] ? 0 : -1, -1, -1, -1};
   if (int e = net_init(n)) { delete n; return e; }
   *out = n;
   return RUMPY_OK;
@@ -883,7 +909,7 @@ int rumpy_net_create_q(void** out, int n_feats, int n_groups, int n_blocks, int 
  * also takes M = n_feats (the handler's scale_qpi vector, reference attention_manipulators/handlers.py:65-73). */
 int rumpy_net_set_metadata(void* net, const float* metadata, int N, int M) {
   Net* n = static_cast<Net*>(net);
-  if (!n || !n->qrcan) return set_error(RUMPY_ERR_ARG, "net_set_metadata: not a Q-RCAN handle");
+  if (!n || !n->qrcan) return set_error(RUMPY_ERR_ARG, "net_set_metadata: not a meta-attention (rumpy_net_create_q) handle");
   bool any_q = false;
   for (const CAW& q : n->qs) any_q |= q.w1 >= 0;
   if (any_q && M != n->num_meta)
@@ -1003,14 +1029,14 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
         break;
       case OP_QSCALE: {
         if (!n->meta_dev || n->meta_n != N)
-          return set_error(RUMPY_ERR_ARG, "Q-RCAN forward: call rumpy_net_set_metadata with a [%d][%d] tensor first", N,
+          return set_error(RUMPY_ERR_ARG, "meta-attention forward: call rumpy_net_set_metadata with a [%d][%d] tensor first", N,
                            n->num_meta);
-        std::vector<QScaleJob> jobs(n->cas.size());
+        std::vector<QScaleJob> jobs(n->qs.size());
         for (size_t i = 0; i < jobs.size(); ++i) {
           const CAW& q = n->qs[i];
           jobs[i] = q.w1 >= 0 ? QScaleJob{params[q.w1], params[q.b1], params[q.w2], params[q.b2], nullptr}
                               : QScaleJob{nullptr, nullptr, nullptr, nullptr, nullptr};
-          jobs[i].out = n->q_scale + i * size_t(N) * 64;
+          jobs[i].out = n->q_scale + i * size_t(N) * n->C;
         }
         if (jobs.size() != n->q_jobs_uploaded.size() ||
             memcmp(jobs.data(), n->q_jobs_uploaded.data(), jobs.size() * sizeof(QScaleJob)) != 0) {
@@ -1021,7 +1047,7 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
           cudaStreamSynchronize(stream);
         }
         if (int e = q_scale_launch(n->q_jobs_dev, int(jobs.size()), n->meta_dev,
-                                   N, n->meta_m, n->q_hidden, n->modulate, stream))
+                                   N, n->meta_m, n->q_hidden, n->C, n->modulate, n->q_relu, stream))
           return e;
         break;
       }

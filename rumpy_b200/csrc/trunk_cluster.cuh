@@ -55,7 +55,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
   __shared__ __align__(8) uint64_t pool_full[2];
   __shared__ uint32_t tmem_base_s, halo_bytes_s;
   __shared__ __align__(16) float y_s[2][64];
-  __shared__ float bias_s[2][32], red_s[2][4][64];
+  __shared__ float bias_s[2][32], alpha_s[2][32], red_s[2][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpMma = 8, kWarpW = 9;
@@ -182,6 +182,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(32 * e);
     const uint32_t plane0 = uint32_t(4 * e) * plane;   // this group's four channel planes
     float* bias_e = bias_s[e];                // 32 values: channels 32e ..
+    float* alpha_e = alpha_s[e];              // kTrunkRes: alpha (x the Q-EDSR multiplier of this image's channel)
     float* y_e = y_s[e];
 
     // One pixel's 32 bf16 channels (4 chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
@@ -248,7 +249,11 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
       const float* bias = lay->bias + 32 * e;
       const int par_out = (L + 1) & 1;
       const bool last = L == n_layers - 1;
-      if (row < 32) bias_e[row] = __ldg(bias + row);   // the previous layer ended with a group barrier
+      if (row < 32) {   // the previous layer ended with a group barrier
+        bias_e[row] = __ldg(bias + row);
+        alpha_e[row] = (kind == kTrunkRes && lay->q_scale != nullptr)
+                           ? lay->alpha * __ldg(lay->q_scale + n * 64 + 32 * e + row) : lay->alpha;
+      }
       named_bar_sync(bar_id, 128);
 
       // 32 fp32 results of this thread's half pixel -> bf16 chunks -> buffer / halos (or global, last layer)
@@ -278,7 +283,6 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
         const float* res = lay->res_f32;
         float* outf = lay->out_f32;
-        const float alpha = lay->alpha;
         const int update_s = lay->update_s;
         mbar_wait(&acc_full[j], uint32_t(L & 1));
         tc_fence_after();
@@ -307,7 +311,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
             for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[i]) * alpha + f[i];
+          for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[i]) * alpha_e[i] + f[i];
           if (update_s) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);

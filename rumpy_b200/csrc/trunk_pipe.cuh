@@ -43,7 +43,8 @@ struct TrunkLayer {
   float* out_f32;        // kTrunkRes: optional fp32 NHWC copy of the result (a later layer's res_f32)
   const float *w1, *b1, *w2, *b2;          // kTrunkCA: FC weights [cr][64], [cr], [64][cr], [64]
   float *save_mean, *save_hid, *save_y;    // kTrunkCA (training): CA vectors for backward, or nullptr
-  const float* q_scale;  // kTrunkCA, Q-RCAN: [N][64] meta-attention multipliers of the CA vector, or nullptr
+  const float* q_scale;  // [N][64] meta-attention multipliers or nullptr: of the CA vector (kTrunkCA, Q-RCAN) /
+                         // of the scaled branch alpha * (acc + bias) (kTrunkRes, Q-EDSR)
 };
 
 struct TrunkArgs {
@@ -150,7 +151,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
   __shared__ __align__(8) uint64_t acc_full[kTrunkMaxK];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float y_s[kTrunkMaxK][64];
-  __shared__ float bias_s[2][64], red_s[2][4][64];
+  __shared__ float bias_s[2][64], alpha_s[2][64], red_s[2][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpA = 8, kWarpMma = 9, kWarpW = 10;
@@ -280,6 +281,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
     unsigned long long* pool_scr = reinterpret_cast<unsigned long long*>(stg_s + 2 * kABytes + e * kTrunkPoolBytes);
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
     float* bias_e = bias_s[e];
+    float* alpha_e = alpha_s[e];   // kTrunkRes: alpha (x the Q-EDSR meta-attention multiplier of this image's channel)
 
     // ---- residual stream of the owned tiles: global fp32 -> TMEM
     for (int j = e; j < my_k; j += 2) {
@@ -353,7 +355,10 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
         mbar_wait(&acc_full[j], uint32_t(L & 1));
         tc_fence_after();
         if (row == 0) TR_STAMP(L, j, 3);
-        if (row < 64) bias_e[row] = bv;
+        if (row < 64) {
+          bias_e[row] = bv;
+          alpha_e[row] = lay->q_scale != nullptr ? alpha * __ldg(lay->q_scale + n * 64 + row) : alpha;
+        }
         named_bar_sync(bar_id, 128);
         if (row == 0) TR_STAMP(L, j, 8);
 #pragma unroll
@@ -382,7 +387,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[h * 32 + i]) * alpha + f[i];
+            for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[h * 32 + i]) * alpha_e[h * 32 + i] + f[i];
             if (update_s) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN = 0, 1, 2
+ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN, ARCH_QEDSR = 0, 1, 2, 3
 
 _FLAT = {}   # id(first parameter) -> (flat fp32 buffer, weakref to first parameter): shared by engine and FusedAdam
 
@@ -49,18 +49,20 @@ def flatten_parameters(params):
 
 class TrunkEngine:
     def __init__(self, arch, params, *, n_feats, n_groups, n_blocks, reduction=16, scale=4, res_scale=1.0,
-                 in_feats=3, out_feats=3, u_f32=True, num_metadata=0, q_hidden=0, rcab_has_q=None, modulate=False):
+                 in_feats=3, out_feats=3, u_f32=True, num_metadata=0, q_hidden=0, block_has_q=None, modulate=False,
+                 q_relu=True):
         self.lib = _lib.load()
         self.arch, self.scale, self.in_feats, self.out_feats = arch, scale, in_feats, out_feats
         self.params = list(params)
         h = ctypes.c_void_p()
         self._meta = None
-        if arch == ARCH_QRCAN:
-            flags = bytes(bytearray(int(bool(f)) for f in rcab_has_q))
-            if len(flags) != n_groups * n_blocks:
-                raise ValueError('rcab_has_q needs one flag per RCAB')
-            _lib.call('rumpy_net_create_q', ctypes.byref(h), n_feats, n_groups, n_blocks, reduction, scale, in_feats,
-                      out_feats, int(num_metadata), int(q_hidden), flags, int(bool(modulate)))
+        if arch in (ARCH_QRCAN, ARCH_QEDSR):
+            flags = bytes(bytearray(int(bool(f)) for f in block_has_q))
+            if len(flags) != (n_groups * n_blocks if arch == ARCH_QRCAN else n_blocks):
+                raise ValueError('block_has_q needs one flag per RCAB / ResBlock')
+            _lib.call('rumpy_net_create_q', ctypes.byref(h), arch - ARCH_QRCAN, n_feats, n_groups, n_blocks, reduction,
+                      scale, float(res_scale), in_feats, out_feats, int(num_metadata), int(q_hidden), flags,
+                      int(bool(modulate)), int(bool(q_relu)))
         else:
             _lib.call('rumpy_net_create', ctypes.byref(h), arch, n_feats, n_groups, n_blocks, reduction, scale,
                       float(res_scale), in_feats, out_feats, int(u_f32))
@@ -151,8 +153,8 @@ class TrunkEngine:
     def set_metadata(self, metadata, N):
         """metadata: [N, M, 1, 1] or [N, M] tensor (what QRCAN.forward receives).  It is copied into a buffer the
         engine owns (static address: CUDA-graph replays see the new values)."""
-        if self.arch != ARCH_QRCAN:
-            raise _lib.RumpyB200Error('set_metadata: not a Q-RCAN engine')
+        if self.arch not in (ARCH_QRCAN, ARCH_QEDSR):
+            raise _lib.RumpyB200Error('set_metadata: not a meta-attention engine')
         if metadata is None:
             raise RuntimeError('Metadata needs to be specified for this network to run properly.')
         m = metadata.reshape(metadata.shape[0], -1).to(device=self.device, dtype=torch.float32)

@@ -214,6 +214,18 @@ def qrcan_cases():
         rec[name + '::attributes'] = attrs.numpy()
         rec[name + '::out'] = out.numpy()
         print(name, 'out', out.shape, float(out.abs().max()))
+    for name in recipe.QECASES:
+        kw, has_q, sd, x, meta = recipe.qecase_tensors(name)
+        net = qarch.QEDSR(**kw)
+        assert list(net.state_dict().keys()) == list(sd.keys()), 'Q-EDSR key order mismatch vs reference'
+        net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+        net.eval()
+        attrs = t(meta).unsqueeze(2).unsqueeze(3)
+        with torch.no_grad():
+            out = net(t(x), attrs)
+        rec[name + '::attributes'] = attrs.numpy()
+        rec[name + '::out'] = out.numpy()
+        print(name, 'out', out.shape, float(out.abs().max()))
     return rec
 
 

@@ -172,3 +172,43 @@ def qcase_tensors(name):
     x = make_input(shape, xseed)
     meta = make_input((shape[0], kw['num_metadata']), xseed + 500)
     return kw, has_q, sd, x, meta
+
+
+def qedsr_spec(num_blocks, num_metadata, has_q, n_feats=64, scale=4, q_relu=False, in_feats=3, out_feats=3):
+    """state_dict layout of the reference's QEDSR (head is a bare conv; final_body registered before body; the
+    integrator's second conv sits at Sequential index 2 only when a ReLU separates the two)."""
+    spec = []
+    _conv_spec(spec, 'head', n_feats, in_feats, 3)
+    _conv_spec(spec, 'final_body', n_feats, n_feats, 3)
+    h1, h2 = q_layer_sizes(num_metadata, n_feats)
+    for b in range(num_blocks):
+        _conv_spec(spec, f'body.{b}.body.0', n_feats, n_feats, 3)
+        _conv_spec(spec, f'body.{b}.body.2', n_feats, n_feats, 3)
+        if has_q[b]:
+            _conv_spec(spec, f'body.{b}.attention_layer.attribute_integrator.0', h1, num_metadata, 1)
+            _conv_spec(spec, f'body.{b}.attention_layer.attribute_integrator.{2 if q_relu else 1}', h2, h1, 1)
+    _tail_spec(spec, n_feats, out_feats, scale)
+    return spec
+
+
+# name -> (QEDSR ctor kwargs, lr-input shape, weight seed, input seed)
+QECASES = OrderedDict(
+    qedsr_blur=(dict(num_blocks=3, num_features=64, scale=4, res_scale=0.1, input_para=10,
+                     q_layer_nonlinearity=True), (2, 3, 11, 15), 71, 72),
+    qedsr_linear_front=(dict(num_blocks=3, num_features=64, scale=2, res_scale=0.1, input_para=2,
+                             q_layer_nonlinearity=False, selective_meta_blocks='front_only'), (3, 3, 8, 8), 73, 74),
+    qedsr_wide=(dict(num_blocks=1, num_features=256, scale=2, res_scale=0.1, input_para=10,
+                     q_layer_nonlinearity=True), (2, 3, 8, 16), 75, 76),
+)
+
+
+def qecase_tensors(name):
+    kw, shape, wseed, xseed = QECASES[name]
+    sel = kw.get('selective_meta_blocks')
+    nb = kw['num_blocks']
+    has_q = [True] * nb if sel is None else ([True] + [False] * (nb - 1) if sel == 'front_only' else list(sel))
+    spec = qedsr_spec(nb, kw['input_para'], has_q, kw['num_features'], kw['scale'], kw['q_layer_nonlinearity'])
+    sd = make_weights(spec, wseed)
+    x = make_input(shape, xseed)
+    meta = make_input((shape[0], kw['input_para']), xseed + 500)
+    return kw, has_q, sd, x, meta

@@ -71,9 +71,15 @@ def test_qrcan_state_dict_layout_matches_reference_spec():
         kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
         m = QRCAN(**kw)
         assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, v.shape) for k, v in sd.items()], name
-        assert m._cfg['rcab_has_q'] == has_q
+        assert m._cfg['block_has_q'] == has_q
     full = QRCAN(style='standard', num_metadata=10, include_q_layer=True)     # sample q-rcan.toml configuration
     assert sum(p.numel() for p in full.parameters()) == 15592355 + 200 * (10 * 32 + 32 + 32 * 64 + 64)
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QEDSR
+    for name in recipe.QECASES:
+        kw, has_q, sd, x, meta = recipe.qecase_tensors(name)
+        m = QEDSR(**kw)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, v.shape) for k, v in sd.items()], name
+        assert m._cfg['block_has_q'] == has_q
     with pytest.raises(NotImplementedError):
         QRCAN(style='max_concat')
     with pytest.raises(NotImplementedError):
@@ -85,7 +91,7 @@ def test_qrcan_state_dict_layout_matches_reference_spec():
 def test_registry_and_legacy_switch():
     from rumpy_b200.shared_framework.models import available_models
     from rumpy_b200.shared_framework.models.base_architecture import BaseModel
-    assert set(available_models) == {'rcan', 'edsr', 'qrcan'}
+    assert set(available_models) == {'rcan', 'edsr', 'qrcan', 'qedsr'}
     sd = {'model.module.head.0.weight': 1, 'model.body.0.bias': 2, 'tail.1.bias': 3}
     assert list(BaseModel.legacy_switch(sd)) == ['head.0.weight', 'body.0.bias', 'tail.1.bias']
     with pytest.raises(RuntimeError):

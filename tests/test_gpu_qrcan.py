@@ -1,5 +1,5 @@
-"""GPU parity of the Q-RCAN (meta-attention) widening: the native QRCAN module / QRCANHandler against outputs of
-the unmodified reference (tests/golden/qrcan.npz) and the CPU oracle, in all three trunk modes."""
+"""GPU parity of the meta-attention widening (Q-RCAN, Q-EDSR): the native QRCAN / QEDSR modules and their handlers
+against outputs of the unmodified reference (tests/golden/qrcan.npz) and the CPU oracle, in all three trunk modes."""
 import ctypes
 import os
 
@@ -28,18 +28,22 @@ def _lib():
     return lib
 
 
-def _qrcan(kw, sd):
-    from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
-    net = QRCAN(**kw)
+def _qrcan(kw, sd, cls='QRCAN'):
+    from rumpy_b200.SISR.models.attention_manipulators import architectures
+    net = getattr(architectures, cls)(**kw)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
     return net.to(_dev()).eval()
 
 
-@pytest.mark.parametrize('name', list(recipe.QCASES))
+@pytest.mark.parametrize('name', list(recipe.QCASES) + list(recipe.QECASES))
 def test_qrcan_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
     gold = np.load(os.path.join(golden_dir, 'qrcan.npz'))
-    kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
-    net = _qrcan(kw, sd)
+    if name in recipe.QCASES:
+        kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
+        net = _qrcan(kw, sd)
+    else:
+        kw, has_q, sd, x, meta = recipe.qecase_tensors(name)
+        net = _qrcan(kw, sd, 'QEDSR')
     attrs = torch.from_numpy(gold[name + '::attributes']).to(_dev())
     xt = torch.from_numpy(x).to(_dev())
     ref = gold[name + '::out']
@@ -127,3 +131,23 @@ def test_qrcan_full_size_uses_cluster_kernel():
     tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
     ref = sr_torch_cpu.qrcan_forward(tsd, torch.from_numpy(x), attrs, 10, 20, 4, 'standard').numpy()
     assert float(np.abs(out - ref).max()) <= 1e-2
+
+
+def test_qedsr_handler_full_width_per_layer_path(tmp_path):
+    """Sample q-edsr.toml configuration (256 features, blur-kernel metadata M=10, ReLU q-layers) with 2 blocks:
+    the 256-channel trunk runs on the per-layer kernels, the multiplier rides in the conv epilogue."""
+    from rumpy_b200.shared_framework.models import define_model
+    h = define_model('qedsr', device=0, model_save_dir=str(tmp_path), eval_mode=True, scale=4, num_blocks=2,
+                     num_features=256, res_scale=0.1, metadata=['blur_kernel'], q_layer_nonlinearity=True)
+    assert h.model_name == 'qedsr' and h.num_metadata == 10
+    spec = [(k, tuple(v.shape)) for k, v in h.net.state_dict().items()]
+    assert spec[4][0] == 'body.0.body.0.weight' and spec[8] == ('body.0.attention_layer.attribute_integrator.0.weight',
+                                                                (128, 10, 1, 1))
+    sd = recipe.make_weights(spec, seed=90)
+    h.net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    x = recipe.make_input((2, 3, 24, 20), 91)
+    attrs = torch.from_numpy(recipe.make_input((2, 10), 92)).unsqueeze(2).unsqueeze(3)
+    out, _, _ = h.run_eval(torch.from_numpy(x), extra_channels=attrs)
+    tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    ref = sr_torch_cpu.qedsr_forward(tsd, torch.from_numpy(x), attrs, 2, 0.1, 4).numpy()
+    assert float(np.abs(out.numpy() - ref).max()) <= 1e-2
