@@ -139,6 +139,9 @@ def infer_arch(sd):
 
 
 def forward(sd, x, arch, **kw):
+    if arch == 'qrcan':
+        return qrcan_forward(sd, x, kw['attributes'], kw['n_resgroups'], kw['n_resblocks'], kw.get('scale', 4),
+                             kw.get('style', 'standard'))
     if arch == 'rcan':
         return rcan_forward(sd, x, kw['n_resgroups'], kw['n_resblocks'], kw.get('scale', 4))
     return edsr_forward(sd, x, kw['num_blocks'], kw.get('res_scale', 0.1), kw.get('scale', 4))

@@ -87,8 +87,8 @@ class QModel(BaseModel):
                                                    '{}_{}'.format(model_save_name, self.curr_epoch)))
 
     def run_train(self, x, y, metadata=None, extra_channels=None, metadata_keys=None, *args, **kwargs):
-        raise NotImplementedError('rumpy_b200: training the meta-attention networks is not implemented (the native '
-                                  'Q-RCAN trunk is inference only); train with RCANHandler / EDSRHandler')
+        input_data, extra_channels = self.channel_concat_logic(x, extra_channels, metadata, metadata_keys)
+        return super().run_train(input_data, y, extra_channels=extra_channels, **kwargs)
 
     def run_eval(self, x, y=None, request_loss=False, metadata=None, metadata_keys=None,
                  extra_channels=None, *args, **kwargs):

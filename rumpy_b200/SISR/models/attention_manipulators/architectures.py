@@ -8,7 +8,8 @@ for the configurations the native trunk implements:
     reference's 2-layer ParaCALayer (q_layer.py:5-45).
 Everything else the reference's QRCAN can be configured with (pixel attention, SFT / DGFMB / DA-conv layers, the
 concat styles, staggered encodings, outer metadata reduction) is outside SURVEY.md section 8 and raises
-NotImplementedError at construction.  Inference only (training the meta-attention is a 'next' row).
+NotImplementedError at construction.  Q-RCAN style 'standard' trains natively (the q-layer parameters get their
+gradients from the backward dataflow kernel's per-channel sums); Q-EDSR and style 'modulate' are inference only.
 
 `QEDSR` (ParamResBlocks: res_scale * conv2(relu(conv1 x)) * q + x) keeps the reference's ctor and key layout too
 (`head.weight` without a Sequential index, `final_body` registered before `body`).
@@ -25,6 +26,7 @@ from rumpy_b200 import engine as _engine
 from rumpy_b200.SISR.models.advanced import common
 from rumpy_b200.SISR.models.advanced.architectures import _NativeTrunk
 from rumpy_b200.SISR.models.attention_manipulators.q_layer import ParaCALayer
+from rumpy_b200.trunk_function import trunk_apply
 
 _NATIVE_ONLY = 'runs inside the native QRCAN trunk only (no standalone / CPU path)'
 
@@ -179,11 +181,9 @@ class QRCAN(_NativeTrunk):
         return _engine.ARCH_QRCAN, dict(self._cfg)
 
     def forward(self, x, metadata):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError('rumpy_b200 QRCAN: inference only (call under torch.no_grad())')
         eng = self.native_engine()
         eng.set_metadata(metadata, x.shape[0])
-        return eng.forward_inference(x)
+        return trunk_apply(self, x)       # autograd boundary: native backward incl. the q-layer parameters
 
     def forensic(self, x, qpi, *args, **kwargs):
         raise NotImplementedError('rumpy_b200: forensic() diagnostics are not part of the native trunk')

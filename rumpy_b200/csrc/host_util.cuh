@@ -76,6 +76,11 @@ struct QScaleJobHost { const float *w1, *b1, *w2, *b2; float* out; };
 int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C,
                    int modulate, int relu, cudaStream_t s);
 
+// one q-layer's parameter-gradient job (trunk_bwd.cuh: QGradJob has the same layout)
+struct QGradJobHost { const float *w1, *b1, *w2, *b2, *q, *dq; float *dw1, *db1, *dw2, *db2; };
+int q_grad_launch(const QGradJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C, int relu,
+                  cudaStream_t s);
+
 // one conv's packing job for the batched pack kernel (misc_kernels.cuh: PackJob has the same layout)
 struct PackJobHost {
   const float* w; void* p; const float* b; float* bp;

@@ -269,12 +269,13 @@ __global__ void ca_apply_kernel(const float* __restrict__ pool_partial, int part
   if (tid < C) {
     float s = b2[tid];
     for (int j = 0; j < Cr; ++j) s = fmaf(w2[tid * Cr + j], hid_s[j], s);
-    y_s[tid] = 1.f / (1.f + __expf(-s));
-    if (q_scale != nullptr) y_s[tid] *= q_scale[size_t(n) * C + tid];
+    const float yr = 1.f / (1.f + __expf(-s));
+    y_s[tid] = q_scale != nullptr ? yr * q_scale[size_t(n) * C + tid] : yr;
+    if (blockIdx.x == 0 && save_y != nullptr) save_y[n * C + tid] = yr;   // backward wants the raw sigmoid
   }
   __syncthreads();
   if (blockIdx.x == 0 && save_y != nullptr) {
-    if (tid < C) { save_y[n * C + tid] = y_s[tid]; save_mean[n * C + tid] = mean_s[tid]; }
+    if (tid < C) save_mean[n * C + tid] = mean_s[tid];
     if (tid < Cr) save_hid[n * Cr + tid] = hid_s[tid];
   }
   // elementwise: 4 channels per thread

@@ -79,6 +79,9 @@ struct Net {
   int num_meta = 0, q_hidden = 0, modulate = 0, q_relu = 1;
   const float* meta_dev = nullptr;
   int meta_n = 0, meta_m = 0;
+  float* q_dq = nullptr;                    // training: [n_rcab][N][64] d(loss)/dq from the backward kernel
+  QGradJobHost* qg_jobs_dev = nullptr;
+  std::vector<QGradJobHost> qg_jobs_uploaded;
   float* q_scale = nullptr;                 // [n_rcab][N][64] per-(image, channel) multipliers of the CA vector
   QScaleJob* q_jobs_dev = nullptr;
   std::vector<QScaleJob> q_jobs_uploaded;
@@ -285,7 +288,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   // ---- Q-RCAN: per-(RCAB, image, channel) meta-attention multipliers, evaluated once per forward
   float* q_scale = nullptr;
   if (n->qrcan) {
-    if (training) return set_error(RUMPY_ERR_ARG, "meta-attention networks: training is not implemented (inference only)");
+    if (training && n->arch != 0)
+      return set_error(RUMPY_ERR_ARG, "Q-EDSR: training is not implemented (inference only)");
+    if (training && n->modulate)
+      return set_error(RUMPY_ERR_ARG, "Q-RCAN style 'modulate': training is not implemented (inference only)");
     q_scale = static_cast<float*>(bp.take(n->qs.size() * size_t(N) * C * sizeof(float)));
     QScaleJob* qj = static_cast<QScaleJob*>(bp.take(n->qs.size() * sizeof(QScaleJob)));
     if (build) {
@@ -590,6 +596,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       const size_t per = size_t(2) * C * Cr + C + Cr;
       void* dev = bp.take(trunk_bwd_device_bytes(N, H, W, n_lay, n_lay + 2, n_lay + 2, n_ca));
       float* pg_all = static_cast<float*>(bp.take(size_t(n_ca) * N * per * 4));
+      float* dq_all = n->qrcan ? static_cast<float*>(bp.take(size_t(n_ca) * N * C * 4)) : nullptr;
+      QGradJobHost* qgj = n->qrcan ? static_cast<QGradJobHost*>(bp.take(size_t(n_ca) * sizeof(QGradJobHost))) : nullptr;
+      if (build) { n->q_dq = dq_all; n->qg_jobs_dev = qgj; n->qg_jobs_uploaded.clear(); }
       if (build) trunk_bwd.reset(new TrunkBwdPlan());
       auto in_of = [&](const void* p) {
         for (size_t i = 0; i < trunk_bwd->in_bufs.size(); ++i) if (trunk_bwd->in_bufs[i] == p) return int(i);
@@ -631,6 +640,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
             l.aux = static_cast<const __nv_bfloat16*>(br.u); l.colsum = du_cs;
             l.save_mean = br.sv; l.save_y = br.sv + size_t(N) * C; l.save_hid = br.sv + size_t(N) * 2 * C;
             l.pg = pg_all + size_t(ca_ord) * N * per;
+            if (n->qrcan && n->qs[br.ca].w1 >= 0) {
+              l.q_scale = q_of(br.ca);
+              l.dq = dq_all + size_t(br.ca) * N * C;
+            }
             if (build) {
               l.out_map = out_of(du);
               const CAW& cw = n->cas[br.ca];
@@ -670,6 +683,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         bops.push_back(op);
       }
     } else if (n->arch == 0) {
+      if (n->qrcan)
+        return set_error(RUMPY_ERR_ARG, "Q-RCAN training needs the dataflow kernels: batch %d x %d x %d exceeds 4 tiles "
+                         "(8x16 px) per SM", N, H, W);
       for (int g = n->n_groups - 1; g >= 0; --g) {
         const GroupRec& gr = groups[g];
         {  // group tail conv: grad wrt the last block's output, fp32 only
@@ -949,7 +965,7 @@ int rumpy_net_num_launches_backward(void* net) {
     switch (op.type) {
       case OP_TAIL_BWD: c += 5; break;        // dgrad, wgrad, reduce, plane sums (2)
       case OP_CA_BWD: c += 2; break;
-      case OP_TRUNK_BWD: c += 2; break;       // the dataflow kernel + the CA parameter-gradient finalize
+      case OP_TRUNK_BWD: c += n->qrcan ? 3 : 2; break;   // dataflow kernel + CA parameter-gradient finalize [+ q-layer grads]
       case OP_HEAD_WGRAD: c += 2; break;
       default: c += 1;
     }
@@ -1147,6 +1163,27 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         break;
       case OP_TRUNK_BWD:
         if (int e = trunk_bwd_launch(n->trunk_bwd.get(), params, grads, stream)) return e;
+        if (n->qrcan) {   // q-layer parameter gradients from the dq = s*y terms the kernel left behind
+          std::vector<QGradJobHost> jobs;
+          for (size_t i = 0; i < n->qs.size(); ++i) {
+            const CAW& q = n->qs[i];
+            if (q.w1 < 0) continue;
+            jobs.push_back(QGradJobHost{params[q.w1], params[q.b1], params[q.w2], params[q.b2],
+                                        n->q_scale + i * size_t(N) * C, n->q_dq + i * size_t(N) * C,
+                                        grads[q.w1], grads[q.b1], grads[q.w2], grads[q.b2]});
+          }
+          if (!jobs.empty() && (jobs.size() != n->qg_jobs_uploaded.size() ||
+                                memcmp(jobs.data(), n->qg_jobs_uploaded.data(), jobs.size() * sizeof(QGradJobHost)) != 0)) {
+            n->qg_jobs_uploaded = jobs;
+            if (cudaMemcpyAsync(n->qg_jobs_dev, n->qg_jobs_uploaded.data(), jobs.size() * sizeof(QGradJobHost),
+                                cudaMemcpyHostToDevice, stream) != cudaSuccess)
+              return set_error(RUMPY_ERR_CUDA, "Q-RCAN: gradient job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaStreamSynchronize(stream);
+          }
+          if (int e = q_grad_launch(n->qg_jobs_dev, int(jobs.size()), n->meta_dev, N, n->meta_m, n->q_hidden, C, n->q_relu,
+                                    stream))
+            return e;
+        }
         break;
       case OP_CA_BWD: {
         const int HW = H * W;

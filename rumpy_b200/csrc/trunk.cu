@@ -297,6 +297,18 @@ int trunk_bwd_launch(TrunkBwdPlan* plan, const float* const* params, float* cons
   return RUMPY_OK;
 }
 
+static_assert(sizeof(QGradJobHost) == sizeof(QGradJob), "QGradJobHost layout mismatch");
+int q_grad_launch(const QGradJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C, int relu,
+                  cudaStream_t s) {
+  if (njobs <= 0) return RUMPY_OK;
+  const size_t smem = size_t(N) * (M + 2 * hidden + C) * sizeof(float);
+  if (smem > 48 * 1024)
+    return set_error(RUMPY_ERR_ARG, "q_grad: batch %d x (metadata %d + hidden %d) does not fit 48 KB of shared memory", N, M,
+                     hidden);
+  q_grad_kernel<<<njobs, 256, smem, s>>>(reinterpret_cast<const QGradJob*>(jobs_dev), meta, N, M, hidden, C, relu);
+  return check_launch("q_grad");
+}
+
 }  // namespace rb
 
 extern "C" {

@@ -34,6 +34,8 @@ struct TrunkBwdLayer {
   const float *w1, *w2;         // kBwdCA: FC weights [cr][64], [64][cr]
   const float *save_mean, *save_hid, *save_y;   // kBwdCA: forward CA vectors [N][64], [N][cr], [N][64]
   float* pg;                    // kBwdCA: per-image parameter-gradient terms [N][2*64*cr + 64 + cr]
+  const float* q_scale;         // kBwdCA, Q-RCAN: forward meta-attention multipliers [N][64] (out = x + u*y*q), or nullptr
+  float* dq;                    // kBwdCA, Q-RCAN: d(loss)/dq = s*y per (image, channel) [N][64], or nullptr
   const float* res_f32;         // kBwdAcc with emit: P (fp32 NHWC) read ...
   float* out_f32;               // ... and P + Q written (may alias res_f32); nullptr = no emit
 };
@@ -362,6 +364,9 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
           // CA vectors / FC weights of this image into registers while the partials are in flight
           const float y0 = __ldg(lay->save_y + n * 64 + lane), y1 = __ldg(lay->save_y + n * 64 + 32 + lane);
           const float yc = __ldg(lay->save_y + n * 64 + c);
+          const float* qs = lay->q_scale;   // Q-RCAN: out = x + u*y*q  =>  du = Q*y*q + coef, dy = s*q, dq = s*y
+          const float q0 = qs ? __ldg(qs + n * 64 + lane) : 1.f, q1 = qs ? __ldg(qs + n * 64 + 32 + lane) : 1.f;
+          const float qc = qs ? __ldg(qs + n * 64 + c) : 1.f;
           float w2a[4], w2b[4], w1c[4], hid[4];
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -376,8 +381,8 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
           red_s[e][hsel][c] = ssum;
           named_bar_sync(bar_id, 128);
           // dz2 = s*y*(1-y) for channels lane, lane+32; dh_j = (W2^T dz2)_j * 1[hid_j > 0]; dmean_c = (W1^T dh)_c
-          const float dz0 = (red_s[e][0][lane] + red_s[e][1][lane]) * y0 * (1.f - y0);
-          const float dz1 = (red_s[e][0][lane + 32] + red_s[e][1][lane + 32]) * y1 * (1.f - y1);
+          const float dz0 = (red_s[e][0][lane] + red_s[e][1][lane]) * q0 * y0 * (1.f - y0);
+          const float dz1 = (red_s[e][0][lane + 32] + red_s[e][1][lane + 32]) * q1 * y1 * (1.f - y1);
           float dmean = 0.f;
           float dh[4];
 #pragma unroll
@@ -401,6 +406,7 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
                 if (c == 0) mine[2 * 64 * cr + 64 + h] = dh[h];    // db1[h]
               }
             mine[2 * 64 * cr + c] = my_dz;                         // db2[c]
+            if (lay->dq != nullptr) lay->dq[n * 64 + c] = (red_s[e][0][c] + red_s[e][1][c]) * yc;
           }
           for (int h = 4; h < cr; ++h) {   // generic tail (cr > 4)
             float sdot = __ldg(lay->w2 + lane * cr + h) * dz0 + __ldg(lay->w2 + (lane + 32) * cr + h) * dz1;
@@ -415,7 +421,7 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
               if (c == 0) mine[2 * 64 * cr + 64 + h] = dhh;
             }
           }
-          if (hsel == 0) { y_s[e][c] = yc; coef_s[e][c] = dmean * args.inv_hw; }
+          if (hsel == 0) { y_s[e][c] = yc * qc; coef_s[e][c] = dmean * args.inv_hw; }
           named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -457,6 +463,60 @@ __global__ void ca_pg_finalize_kernel(const CaPgJob* __restrict__ jobs, int N, i
     else if (i < 2 * 64 * cr) jb.dw1[i - 64 * cr] = s;
     else if (i < 2 * 64 * cr + 64) jb.db2[i - 2 * 64 * cr] = s;
     else jb.db1[i - 2 * 64 * cr - 64] = s;
+  }
+}
+
+// d(loss)/d(q-layer parameters) of one block (reference q_layer.py:5-45, 2-layer ParaCALayer): q = sigmoid(a),
+// a = W2 act(W1 meta + b1) + b2.  dq[n][c] = sum_hw g*u*y comes from trunk_bwd_kernel.  One CTA per block; the sums
+// over the images run in a fixed order (deterministic).
+struct QGradJob { const float *w1, *b1, *w2, *b2, *q, *dq; float *dw1, *db1, *dw2, *db2; };
+__global__ void q_grad_kernel(const QGradJob* __restrict__ jobs, const float* __restrict__ meta, int N, int M,
+                              int hidden, int C, int relu) {
+  extern __shared__ float qg_smem[];
+  float* meta_s = qg_smem;                 // [N][M]
+  float* hid_s = meta_s + N * M;           // [N][hidden]  act(W1 meta + b1)
+  float* da_s = hid_s + N * hidden;        // [N][C]       dq * q * (1 - q)
+  float* dh_s = da_s + N * C;              // [N][hidden]
+  const QGradJob jb = jobs[blockIdx.x];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < N * M; i += nt) meta_s[i] = meta[i];
+  for (int i = tid; i < N * C; i += nt) { const float q = jb.q[i]; da_s[i] = jb.dq[i] * q * (1.f - q); }
+  __syncthreads();
+  for (int i = tid; i < N * hidden; i += nt) {
+    const int n = i / hidden, t = i - n * hidden;
+    float a = jb.b1[t];
+    for (int m = 0; m < M; ++m) a = fmaf(jb.w1[size_t(t) * M + m], meta_s[n * M + m], a);
+    hid_s[i] = relu ? fmaxf(a, 0.f) : a;
+  }
+  __syncthreads();
+  for (int i = tid; i < C * hidden; i += nt) {   // dW2[c][t]
+    const int c = i / hidden, t = i - c * hidden;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(da_s[n * C + c], hid_s[n * hidden + t], s);
+    jb.dw2[i] = s;
+  }
+  for (int c = tid; c < C; c += nt) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += da_s[n * C + c];
+    jb.db2[c] = s;
+  }
+  for (int i = tid; i < N * hidden; i += nt) {
+    const int n = i / hidden, t = i - n * hidden;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(jb.w2[size_t(c) * hidden + t], da_s[n * C + c], s);
+    dh_s[i] = (relu && hid_s[i] <= 0.f) ? 0.f : s;
+  }
+  __syncthreads();
+  for (int i = tid; i < hidden * M; i += nt) {   // dW1[t][m]
+    const int t = i / M, m = i - t * M;
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(dh_s[n * hidden + t], meta_s[n * M + m], s);
+    jb.dw1[i] = s;
+  }
+  for (int t = tid; t < hidden; t += nt) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += dh_s[n * hidden + t];
+    jb.db1[t] = s;
   }
 }
 

@@ -497,13 +497,16 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
           yacc = fmaf(__ldg(w2 + c * cr + h), hv, yacc);
           if (saver && lane == 0) lay->save_hid[n * cr + h] = hv;
         }
-        if (hsel == 0) y_s[j][c] = (1.f / (1.f + __expf(-yacc))) * (lay->q_scale ? __ldg(lay->q_scale + n * 64 + c) : 1.f);
+        if (hsel == 0) {
+          const float yr = 1.f / (1.f + __expf(-yacc));
+          y_s[j][c] = yr * (lay->q_scale ? __ldg(lay->q_scale + n * 64 + c) : 1.f);
+          if (lay->save_y != nullptr && rem == 0) lay->save_y[n * 64 + c] = yr;   // backward wants the raw sigmoid
+        }
         if (saver) {
           lay->save_mean[n * 64 + lane] = m0;
           lay->save_mean[n * 64 + 32 + lane] = m1;
         }
         named_bar_sync(bar_id, 128);
-        if (saver) { lay->save_y[n * 64 + lane] = y_s[j][lane]; lay->save_y[n * 64 + 32 + lane] = y_s[j][lane + 32]; }
         if (row == 0) TR_STAMP(L, j, 14);
         const float* yv = y_s[j];
 #pragma unroll

@@ -143,7 +143,8 @@ class TrunkEngine:
         if ws is None:
             nbytes = self.lib.rumpy_net_workspace_bytes(self.handle, N, H, W, int(training))
             if nbytes < 0:
-                raise _lib.RumpyB200Error('workspace query failed')
+                msg = self.lib.rumpy_last_error()
+                raise _lib.RumpyB200Error('workspace query failed: ' + (msg.decode() if msg else '?'))
             self._ws = {k: v for k, v in self._ws.items() if k[3] != key[3]}   # keep one per mode
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws

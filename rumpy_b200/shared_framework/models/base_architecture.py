@@ -220,7 +220,7 @@ class BaseModel(nn.Module):
         dev = self._torch_device()
         x, y = x.to(device=dev, non_blocking=True), y.to(device=dev, non_blocking=True)
         loss, out = train_native.train_step(self.net, self.optimizer, x, y, grad_clip=self.grad_clip,
-                                            allreduce=self._ddp)
+                                            allreduce=self._ddp, metadata=kwargs.get('extra_channels'))
         if self.learning_rate_scheduler is not None and not scheduler_skip:
             self.learning_rate_scheduler.step()
         if keep_on_device:

@@ -35,9 +35,12 @@ def l1_loss(out, y, want_grad=False, gscale=1.0):
     return (loss, dy) if want_grad else loss
 
 
-def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None):
-    """One optimiser step on batch (x, y); returns (loss 0-dim device tensor, SR output on device)."""
+def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None, metadata=None):
+    """One optimiser step on batch (x, y); returns (loss 0-dim device tensor, SR output on device).
+    metadata: the [N, M, 1, 1] vector of the meta-attention networks (QRCAN), else None."""
     eng = net.native_engine()
+    if metadata is not None:
+        eng.set_metadata(metadata, x.shape[0])
     if getattr(optimizer, 'flat_g', None) is not None and eng.flat_grads is not optimizer.flat_g:
         optimizer.attach_engine(eng)       # engine writes gradients straight into the optimiser's flat buffer
     out = eng.forward(x, training=True)

@@ -107,9 +107,6 @@ def test_qrcan_handler_run_eval_with_metadata_keys(tmp_path):
     ref = sr_torch_cpu.qrcan_forward(tsd, torch.from_numpy(x), attrs, 1, 2, 4, 'standard').numpy()
     assert float(np.abs(out.numpy() - ref).max()) <= 1e-2
     assert h.metadata_keys_used_in_training == ['blur_sigma', 'jpeg_quality', 'noise']
-    with pytest.raises(NotImplementedError):
-        h.eval_mode = False
-        h.run_train(torch.from_numpy(x), torch.zeros(2, 3, 64, 48), metadata=table, metadata_keys=keys)
 
 
 def test_qrcan_full_size_uses_cluster_kernel():
@@ -151,3 +148,100 @@ def test_qedsr_handler_full_width_per_layer_path(tmp_path):
     tsd = {k: torch.from_numpy(v) for k, v in sd.items()}
     ref = sr_torch_cpu.qedsr_forward(tsd, torch.from_numpy(x), attrs, 2, 0.1, 4).numpy()
     assert float(np.abs(out.numpy() - ref).max()) <= 1e-2
+
+
+# ----------------------------------------------------------------------------- training (Q-RCAN style 'standard')
+def _ytrain(name, kw, x):
+    return recipe.make_input((x.shape[0], 3, x.shape[2] * kw['scale'], x.shape[3] * kw['scale']),
+                             recipe.QCASES[name][3] + 1000)
+
+
+@pytest.mark.parametrize('name', ['qrcan_blur_q', 'qrcan_selective', 'qrcan_wide_meta'])
+def test_qrcan_gradients_vs_reference_golden(golden_dir, name):
+    """Every parameter gradient (convs, channel attention, q-layers) of the native backward against the reference's
+    autograd: <= 3 % of the tensor's max magnitude and cosine >= 0.999 (bf16 operands, fp32 accumulate)."""
+    from rumpy_b200 import train_native
+    gold = np.load(os.path.join(golden_dir, 'qrcan.npz'))
+    kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
+    net = _qrcan(kw, sd).train()
+    eng = net.native_engine()
+    xt = torch.from_numpy(x).to(_dev())
+    yt = torch.from_numpy(_ytrain(name, kw, x)).to(_dev())
+    eng.set_metadata(torch.from_numpy(gold[name + '::attributes']), x.shape[0])
+    out = eng.forward(xt, training=True)
+    loss, dy = train_native.l1_loss(out, yt, want_grad=True)
+    grads = eng.backward(xt, dy)
+    assert abs(loss.item() - float(gold[name + '::loss'])) <= 0.01 * float(gold[name + '::loss'])
+    n_q = 0
+    for (k, _), g in zip(net.named_parameters(), grads):
+        ref = gold[name + '::gradsub::' + k]
+        got = recipe.subsample(g.cpu().numpy())
+        scale = max(float(np.abs(ref).max()), 1e-12)
+        assert np.abs(got - ref).max() <= 0.03 * scale, k
+        cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
+        assert cos >= 0.999, (k, cos)
+        n_q += 'q_node' in k
+    assert n_q == 4 * sum(has_q)
+
+
+def test_qrcan_three_adam_steps_and_autograd_path(golden_dir):
+    from rumpy_b200 import train_native
+    from rumpy_b200.optim import FusedAdam
+    name = 'qrcan_blur_q'
+    gold = np.load(os.path.join(golden_dir, 'qrcan.npz'))
+    kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
+    attrs = torch.from_numpy(gold[name + '::attributes']).to(_dev())
+    xt = torch.from_numpy(x).to(_dev())
+    yt = torch.from_numpy(_ytrain(name, kw, x)).to(_dev())
+    # autograd.Function path: net(x, metadata) under grad + a torch-side loss
+    net = _qrcan(kw, sd).train()
+    out = net(xt, attrs)
+    assert out.requires_grad
+    (out - yt).abs().mean().backward()
+    for k, p in net.named_parameters():
+        ref = gold[name + '::gradsub::' + k]
+        assert np.abs(recipe.subsample(p.grad.cpu().numpy()) - ref).max() <= 0.03 * max(float(np.abs(ref).max()), 1e-12), k
+    # native train step x3 against the reference's Adam losses
+    net = _qrcan(kw, sd).train()
+    opt = FusedAdam(list(net.parameters()), lr=1e-4)
+    losses = [train_native.train_step(net, opt, xt, yt, metadata=attrs)[0].item() for _ in range(3)]
+    np.testing.assert_allclose(losses, gold[name + '::train_losses'], rtol=0.01)
+    net.eval()
+    with torch.no_grad():
+        o = net(xt, attrs).cpu().numpy()
+    assert np.abs(o - gold[name + '::out_after3']).max() <= 1e-2
+
+
+def test_qrcan_handler_run_train_loss_curve_vs_oracle(tmp_path):
+    """QRCANHandler.run_train(x, y, metadata, metadata_keys) for 60 steps against the CPU oracle's Adam on the same
+    batches: per-step loss within 1 %."""
+    from rumpy_b200.shared_framework.models import define_model
+    h = define_model('qrcan', device=0, model_save_dir=str(tmp_path), eval_mode=False, scale=4, style='standard',
+                     metadata=['blur_kernel'], include_q_layer=True, n_resgroups=1, n_resblocks=2, lr=1e-4)
+    spec = [(k, tuple(v.shape)) for k, v in h.net.state_dict().items()]
+    sd = recipe.make_weights(spec, seed=95)
+    h.net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    keys = [('blur_kernel',)]
+    batches = [(recipe.make_input((2, 3, 16, 16), 300 + i), recipe.make_input((2, 3, 64, 64), 400 + i),
+                recipe.make_input((2, 10), 500 + i)) for i in range(4)]
+    tr = None
+    for step in range(60):
+        x, y, m = batches[step % 4]
+        attrs = torch.from_numpy(m).unsqueeze(2).unsqueeze(3)
+        if tr is None:
+            tr = sr_torch_cpu.Trainer({k: torch.from_numpy(v) for k, v in sd.items()}, 'qrcan', lr=1e-4,
+                                      attributes=attrs, n_resgroups=1, n_resblocks=2, scale=4)
+        tr.kw['attributes'] = attrs
+        l_cpu, _ = tr.step(torch.from_numpy(x), torch.from_numpy(y))
+        l_gpu, out = h.run_train(torch.from_numpy(x), torch.from_numpy(y), metadata=torch.from_numpy(m),
+                                 metadata_keys=keys)
+        assert abs(float(l_gpu) - l_cpu) <= 0.01 * l_cpu, (step, float(l_gpu), l_cpu)
+    assert tuple(out.shape) == (2, 3, 64, 64)
+
+
+def test_qedsr_and_modulate_training_is_rejected():
+    from rumpy_b200 import _lib
+    kw, has_q, sd, x, meta = recipe.qecase_tensors('qedsr_blur')
+    net = _qrcan(kw, sd, 'QEDSR').train()
+    with pytest.raises(_lib.RumpyB200Error, match='inference only'):
+        net(torch.from_numpy(x).to(_dev()), torch.from_numpy(meta).to(_dev()))
