@@ -366,7 +366,76 @@ def extra_configs(device):
     del qnet
     torch.cuda.empty_cache()
     out['torch_eager_gpu_baseline'] = eager_gpu_baseline(device)
+    out['glue'] = glue_bench(device)
     return out
+
+
+def glue_bench(device):
+    """SURVEY 8(f) ranks 3 and 4 (csrc/glue.cu): eval glue (PSNR(Y), uint8 quantise) and the training-patch pipeline
+    on the device, each against its HBM roofline and against the host (numpy) path it replaces."""
+    import time as _t
+    from rumpy_b200.shared_framework.data import (DevicePairSet, PairSet, psnr_y, psnr_y_device, quantize_u8_device)
+    pk = peaks()
+    res = {}
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / iters
+    hw = LR_HW * SCALE
+    sr = torch.rand((BATCH, 3, hw, hw), device=device) * 1.2 - 0.1
+    hr = torch.rand((BATCH, 3, hw, hw), device=device)
+    ms = timed(lambda: psnr_y_device(sr, hr))
+    nbytes = 2 * sr.numel() * 4
+    res['psnr_y'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6, 'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'],
+                     'algorithmic_bytes': nbytes}
+    ms = timed(lambda: quantize_u8_device(sr))
+    nbytes = sr.numel() * 5
+    res['quantize_u8'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6, 'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'],
+                          'algorithmic_bytes': nbytes}
+    # a whole x4 frame (configs[4]'s output, 4320 x 7680): large enough to be bound by HBM rather than by launches
+    fsr = torch.rand((1, 3, 4320, 7680), device=device)
+    fhr = torch.rand((1, 3, 4320, 7680), device=device)
+    ms = timed(lambda: psnr_y_device(fsr, fhr), 10)
+    nbytes = 2 * fsr.numel() * 4
+    res['psnr_y_frame_4320x7680'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6,
+                                     'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'], 'algorithmic_bytes': nbytes}
+    ms = timed(lambda: quantize_u8_device(fsr), 10)
+    nbytes = fsr.numel() * 5
+    res['quantize_u8_frame_4320x7680'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6,
+                                          'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'], 'algorithmic_bytes': nbytes}
+    del fsr, fhr
+    torch.cuda.empty_cache()
+    t0 = _t.perf_counter()
+    src, hrc = sr.cpu(), hr.cpu()
+    for n in range(BATCH):
+        psnr_y(src[n:n + 1], hrc[n:n + 1])
+    (src.permute(0, 2, 3, 1).numpy() * 255).clip(0, 255).astype(np.uint8)
+    res['host_path_ms'] = (_t.perf_counter() - t0) * 1e3     # D2H fp32 + numpy PSNR + numpy quantise (reference flow)
+    cfg = {'synthetic': 64, 'crop': 64, 'random_augment': True}
+    host, dev = PairSet(cfg, SCALE, seed=8), DevicePairSet(cfg, SCALE, seed=8, device=device.index or 0)
+    t0 = _t.perf_counter()
+    nb = sum(1 for _ in host.batches(16))
+    host_s = _t.perf_counter() - t0
+    torch.cuda.synchronize()
+    e0, e1 = ev(), ev()
+    e0.record()
+    nbd = sum(1 for _ in dev.batches(16))
+    e1.record()
+    e1.synchronize()
+    res['patch_pipeline'] = {'host_patches_per_s': nb * 16 / host_s, 'device_patches_per_s': nbd * 16 / (e0.elapsed_time(e1) * 1e-3),
+                             'note': '16 x (64x64 LR + 256x256 HR) patches per batch: crop + flips + transpose + ToTensor; '
+                                     'host = numpy on one core, device = one kernel per batch from uint8 images in HBM'}
+    return res
 
 
 def eager_gpu_baseline(device):

@@ -182,6 +182,26 @@ int rumpy_grad_clip_coef(const float* grad_flat, long long n, float max_norm, fl
 int rumpy_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, int step, const float* grad_scale_dev, float grad_scale, void* stream);
 
+/* ---- eval glue and training-patch pipeline on the device (csrc/glue.cu) ------------------
+ * rumpy_psnr_y: per-image PSNR on the Y channel of jpg-style YCbCr after clipping both images to [0,1]
+ *   (replaces the numpy chain ImageModelInterface.colorspace_convert base_interface.py:208-222 -> ycbcr_convert
+ *   image_functions.py:72-88 -> psnr sr_tools/metrics.py:33-44).  sr, hr: device fp32 NCHW [N][3][H][W];
+ *   psnr: device fp32 [N]; workspace: rumpy_psnr_y_workspace(N) bytes.  Identical images give 100 (metrics.py:41-42).
+ * rumpy_quantize_u8: dst[n][y][x][c] = uint8(clip(src[n][c][y][x] * 255, 0, 255)) with numpy's truncation
+ *   (the uint8 image the reference saves, sr_tools/visualization.py:31-61); bit-exact.
+ * rumpy_patch_batch: one training batch of LR/HR patches from uint8 HWC images resident on the device: crop at
+ *   (y, x) [LR coordinates; HR = * scale], hflip, vflip, transpose (in that order), ToTensor (u8 / 255 -> fp32 CHW)
+ *   (replaces image_functions.py:287-362 random_matched_crop / random_flip_rotate + torchvision ToTensor per sample
+ *   in data_handler.py:570-645).  lr_imgs / hr_imgs: DEVICE arrays of device pointers; geom: device int32 [N][6] =
+ *   {image index, y, x, flags (1 hflip | 2 vflip | 4 transpose), lr_h, lr_w}; outputs fp32 [N][3][crop][crop] and
+ *   [N][3][crop*scale][crop*scale]; bit-exact. */
+long long rumpy_psnr_y_workspace(int N);
+int rumpy_psnr_y(const float* sr, const float* hr, float* psnr, void* workspace, int N, int H, int W, float max_value,
+                 void* stream);
+int rumpy_quantize_u8(const float* src_nchw, unsigned char* dst_nhwc, int N, int C, int H, int W, void* stream);
+int rumpy_patch_batch(const unsigned char* const* lr_imgs, const unsigned char* const* hr_imgs, const int* geom,
+                      float* lr_out, float* hr_out, int N, int crop, int scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

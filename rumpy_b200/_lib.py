@@ -33,6 +33,10 @@ SIGNATURES = {
     'rumpy_net_create': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i],
     'rumpy_net_create_q': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _c.c_char_p, _i, _i],
     'rumpy_net_set_metadata': [_vp, _fp, _i, _i],
+    'rumpy_psnr_y_workspace': [_i],
+    'rumpy_psnr_y': [_fp, _fp, _fp, _vp, _i, _i, _i, _f, _vp],
+    'rumpy_quantize_u8': [_fp, _vp, _i, _i, _i, _i, _vp],
+    'rumpy_patch_batch': [_vp, _vp, _vp, _fp, _fp, _i, _i, _i, _vp],
     'rumpy_net_destroy': [_vp],
     'rumpy_net_num_params': [_vp],
     'rumpy_net_num_launches': [_vp],
@@ -50,7 +54,7 @@ SIGNATURES = {
 }
 
 _LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace',
-             'rumpy_l1_workspace_floats'}
+             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace'}
 
 _lib = None
 

@@ -78,3 +78,82 @@ def psnr_y(sr, hr, max_value=1.0):
     if mse == 0:
         return 100.0
     return float(20 * np.log10(max_value / np.sqrt(mse)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Device-side versions (csrc/glue.cu): same results as the host functions above, computed where the batch already is
+# ----------------------------------------------------------------------------------------------------------------
+def psnr_y_device(sr, hr, max_value=1.0):
+    """Per-image PSNR(Y) of NCHW fp32 CUDA tensors -> fp32 CUDA tensor [N] (no host sync).  Same definition as
+    `psnr_y`, evaluated per image (what EvalHub records in individual_metrics.csv)."""
+    from rumpy_b200 import _lib
+    if not (sr.is_cuda and hr.is_cuda):
+        raise _lib.RumpyB200Error('psnr_y_device: CUDA tensors only (no CPU fallback)')
+    sr, hr = sr.contiguous().float(), hr.contiguous().float()
+    if sr.shape != hr.shape or sr.dim() != 4 or sr.shape[1] != 3:
+        raise ValueError(f'psnr_y_device: expected matching N x 3 x H x W tensors, got {tuple(sr.shape)} / {tuple(hr.shape)}')
+    n, _, h, w = sr.shape
+    lib = _lib.load()
+    ws = torch.empty(lib.rumpy_psnr_y_workspace(n), dtype=torch.uint8, device=sr.device)
+    out = torch.empty(n, dtype=torch.float32, device=sr.device)
+    _lib.call('rumpy_psnr_y', sr.data_ptr(), hr.data_ptr(), out.data_ptr(), ws.data_ptr(), n, h, w, float(max_value),
+              torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def quantize_u8_device(img):
+    """NCHW fp32 CUDA tensor -> NHWC uint8 CUDA tensor, `np.clip(x * 255, 0, 255).astype(np.uint8)` (truncation)."""
+    from rumpy_b200 import _lib
+    if not img.is_cuda:
+        raise _lib.RumpyB200Error('quantize_u8_device: CUDA tensors only (no CPU fallback)')
+    img = img.contiguous().float()
+    n, c, h, w = img.shape
+    out = torch.empty((n, h, w, c), dtype=torch.uint8, device=img.device)
+    _lib.call('rumpy_quantize_u8', img.data_ptr(), out.data_ptr(), n, c, h, w, torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+class DevicePairSet(PairSet):
+    """PairSet whose uint8 images live in HBM and whose training batches (crop + flips + transpose + ToTensor) are
+    produced by ONE kernel per batch (`rumpy_patch_batch`).  Draws the same random numbers in the same order as
+    PairSet, so for one seed both yield bit-identical batches; only 24 B of geometry per sample cross PCIe."""
+
+    def __init__(self, cfg, scale, seed=8, device=0):
+        super().__init__(cfg, scale, seed)
+        if not self.crop:
+            raise ValueError('DevicePairSet needs `crop` (training patches); use PairSet for whole images')
+        self.device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
+        self._lr = [torch.from_numpy(np.ascontiguousarray(lr)).to(self.device) for _, lr, _ in self.items]
+        self._hr = [torch.from_numpy(np.ascontiguousarray(hr)).to(self.device) for _, _, hr in self.items]
+        self._lr_tab = torch.tensor([t.data_ptr() for t in self._lr], dtype=torch.int64, device=self.device)
+        self._hr_tab = torch.tensor([t.data_ptr() for t in self._hr], dtype=torch.int64, device=self.device)
+
+    def geometry(self, idx):
+        """The random draws of PairSet.sample, without touching pixels."""
+        _, lr, _ = self.items[idx]
+        c = self.crop
+        y = self.rng.randint(0, lr.shape[0] - c)
+        x = self.rng.randint(0, lr.shape[1] - c)
+        flags = 0
+        if self.augment:
+            flags |= 1 if self.rng.random() < 0.5 else 0
+            flags |= 2 if self.rng.random() < 0.5 else 0
+            flags |= 4 if self.rng.random() < 0.5 else 0
+        return [idx, y, x, flags, lr.shape[0], lr.shape[1]]
+
+    def batches(self, batch_size, shuffle=True, rank=0, world=1):
+        from rumpy_b200 import _lib
+        order = list(range(len(self.items)))
+        if shuffle:
+            self.rng.shuffle(order)
+        order = order[rank::world]
+        c, s = self.crop, self.scale
+        for i in range(0, len(order) - batch_size + 1, batch_size):
+            picks = order[i:i + batch_size]
+            geom = torch.tensor([self.geometry(j) for j in picks], dtype=torch.int32).pin_memory()
+            geom = geom.to(self.device, non_blocking=True)
+            lr = torch.empty((batch_size, 3, c, c), dtype=torch.float32, device=self.device)
+            hr = torch.empty((batch_size, 3, c * s, c * s), dtype=torch.float32, device=self.device)
+            _lib.call('rumpy_patch_batch', self._lr_tab.data_ptr(), self._hr_tab.data_ptr(), geom.data_ptr(),
+                      lr.data_ptr(), hr.data_ptr(), batch_size, c, s, torch.cuda.current_stream().cuda_stream)
+            yield {'tag': [self.items[j][0] for j in picks], 'lr': lr, 'hr': hr}

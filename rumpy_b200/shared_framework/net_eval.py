@@ -30,7 +30,7 @@ def eval_run(config, **kw):
     import torch
     import torch.distributed as dist
     from rumpy_b200 import parallel
-    from rumpy_b200.shared_framework.data import PairSet, psnr_y
+    from rumpy_b200.shared_framework.data import PairSet, psnr_y_device, quantize_u8_device
     from rumpy_b200.shared_framework.models import define_model
 
     if config:
@@ -60,11 +60,14 @@ def eval_run(config, **kw):
         model.load_model('train_model', epoch, legacy=model.legacy_load)
         for idx in parallel.shard_round_robin(range(len(ds))):
             name, lr, hr = ds.sample(idx)
-            out, _, secs = model.run_eval(lr[None], timing=True)
-            rows.append({'image': name, 'model': exp, 'runtime': secs, 'PSNR': psnr_y(out, hr[None])})
+            # eval glue on the device (csrc/glue.cu): the SR image never crosses PCIe as fp32 -- PSNR(Y) is reduced
+            # next to it and only the uint8 image (when saved) and one float come back
+            out, _, secs = model.run_eval(lr[None], timing=True, keep_on_device=True)
+            hr_dev = hr[None].to(out.device, non_blocking=True)
+            rows.append({'image': name, 'model': exp, 'runtime': secs, 'PSNR': float(psnr_y_device(out, hr_dev)[0])})
             if kw['save_im']:
                 from PIL import Image
-                im = np.clip(out[0].permute(1, 2, 0).numpy() * 255, 0, 255).astype(np.uint8)   # truncation,
+                im = quantize_u8_device(out)[0].cpu().numpy()      # clip(x*255).astype(uint8): truncation,
                 Image.fromarray(im).save(os.path.join(out_dir, f'{exp}_{name}'))                # visualization.py:56
     if dist.is_initialized():
         gathered = [None] * dist.get_world_size()

@@ -25,7 +25,7 @@ def experiment_setup(parameters, experiment_name, **kwargs):
     import toml
     import torch
     import torch.distributed as dist
-    from rumpy_b200.shared_framework.data import PairSet, psnr_y
+    from rumpy_b200.shared_framework.data import DevicePairSet, PairSet, psnr_y_device
     from rumpy_b200.shared_framework.models import define_model
 
     params = toml.load(parameters)
@@ -61,7 +61,9 @@ def experiment_setup(parameters, experiment_name, **kwargs):
         model.set_multi_gpu()
     scale = int(internal.get('scale', 4))
     data = params['data']
-    train_sets = [PairSet(v, scale, seed + rank) for v in data['training_sets'].values()]
+    # training patches are cut / flipped / converted on the GPU from uint8 images resident in HBM (csrc/glue.cu)
+    train_sets = [DevicePairSet(v, scale, seed + rank, device=local) if v.get('crop') else PairSet(v, scale, seed + rank)
+                  for v in data['training_sets'].values()]
     eval_sets = [PairSet({**v, 'crop': None, 'random_augment': False}, scale, seed)
                  for v in data.get('eval_sets', {}).values()]
     summary = os.path.join(out_dir, 'summary.csv')
@@ -80,9 +82,10 @@ def experiment_setup(parameters, experiment_name, **kwargs):
             for ds in eval_sets:
                 for i in range(len(ds)):
                     _, lr, hr = ds.sample(i)
-                    out, vloss, _ = model.run_eval(lr[None], hr[None], request_loss=True)
+                    hr_dev = hr[None].to(torch.device('cuda', local), non_blocking=True)
+                    out, vloss, _ = model.run_eval(lr[None], hr_dev, request_loss=True, keep_on_device=True)
                     val_losses.append(float(vloss))
-                    val_psnr.append(psnr_y(out, hr[None]))
+                    val_psnr.append(float(psnr_y_device(out, hr_dev)[0]))     # clip -> Y -> PSNR on the device
             model.save_model('train_model')
             with open(summary, 'a', newline='') as f:
                 csv.writer(f).writerow([epoch, np.mean(losses) if losses else float('nan'), model.get_learning_rate(),

@@ -1,0 +1,100 @@
+"""GPU tests of the eval glue and the device-side patch pipeline (csrc/glue.cu).
+Integer / byte work: bit-exact against the numpy expressions the reference uses; PSNR within 1e-3 dB."""
+import numpy as np
+import pytest
+import torch
+
+import recipe
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 1, 1), (2, 3, 17, 31), (3, 1, 64, 64), (1, 3, 231, 517), (2, 4, 9, 5)])
+def test_quantize_u8_bit_exact_vs_numpy(shape):
+    """`np.clip(x * 255, 0, 255).astype(np.uint8)` (truncation; reference sr_tools/visualization.py:31-61), including
+    out-of-range values, exact k/255 grid points and values one ulp either side of them."""
+    from rumpy_b200.shared_framework.data import quantize_u8_device
+    rs = np.random.RandomState(5)
+    x = rs.uniform(-0.2, 1.2, size=shape).astype(np.float32)
+    flat = x.reshape(-1)
+    grid = (np.arange(256, dtype=np.float32) / np.float32(255.0))
+    k = min(flat.size // 3, 256)
+    flat[:k] = grid[:k]
+    flat[k:2 * k] = np.nextafter(grid[:k], np.float32(2.0))
+    flat[2 * k:3 * k] = np.nextafter(grid[:k], np.float32(-1.0))
+    want = np.clip(x * 255, 0, 255).astype(np.uint8).transpose(0, 2, 3, 1)
+    got = quantize_u8_device(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    assert got.dtype == np.uint8 and got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 8, 8), (3, 3, 57, 86), (2, 3, 512, 384)])
+def test_psnr_y_matches_host_definition(shape):
+    from rumpy_b200.shared_framework.data import psnr_y, psnr_y_device
+    rs = np.random.RandomState(6)
+    hr = rs.uniform(0, 1, size=shape).astype(np.float32)
+    sr = (hr + rs.normal(0, 0.05, size=shape)).astype(np.float32)        # leaves [0,1]: exercises the clip
+    got = psnr_y_device(torch.from_numpy(sr).to(DEV), torch.from_numpy(hr).to(DEV)).cpu().numpy()
+    for n in range(shape[0]):
+        want = psnr_y(torch.from_numpy(sr[n:n + 1]), torch.from_numpy(hr[n:n + 1]))
+        assert abs(float(got[n]) - want) <= 1e-3, (n, float(got[n]), want)
+    same = psnr_y_device(torch.from_numpy(hr).to(DEV), torch.from_numpy(hr).to(DEV)).cpu().numpy()
+    assert np.all(same == 100.0)                                          # metrics.py:41-42
+    a = psnr_y_device(torch.from_numpy(sr).to(DEV), torch.from_numpy(hr).to(DEV))
+    assert torch.equal(a, psnr_y_device(torch.from_numpy(sr).to(DEV), torch.from_numpy(hr).to(DEV)))   # deterministic
+
+
+def test_psnr_y_set5_golden_within_tolerance(golden_dir):
+    """PSNR(Y) of the reference's own Set5 outputs (golden crops) computed on the device equals the numpy oracle's."""
+    import os
+    from oracle import sr_numpy
+    from rumpy_b200.shared_framework.data import psnr_y_device
+    gold = np.load(os.path.join(golden_dir, 'set5_edsr_baseline.npz'))
+    for f in [str(n) for n in gold['names']]:
+        crop = gold[f + '::out_crop']                                     # 1 x 3 x 32 x 32 of the reference output
+        hr = (gold[f + '::hr_u8'][:32, :32].astype(np.float32) / 255.0).transpose(2, 0, 1)[None]
+        want = sr_numpy.psnr(sr_numpy.rgb_to_y(np.clip(crop, 0, 1)), sr_numpy.rgb_to_y(hr))
+        got = float(psnr_y_device(torch.from_numpy(crop).to(DEV), torch.from_numpy(hr).to(DEV))[0])
+        assert abs(got - want) <= 1e-3, (f, got, want)
+
+
+@pytest.mark.parametrize('crop,scale,augment', [(16, 4, True), (7, 3, True), (24, 2, False), (48, 4, True)])
+def test_device_patch_pipeline_bit_exact_vs_host_pipeline(crop, scale, augment):
+    """DevicePairSet (one kernel per batch, images resident in HBM) against PairSet (numpy crop / flips / transpose +
+    ToTensor on the host) with the same seed: identical tags and bit-identical fp32 batches."""
+    from rumpy_b200.shared_framework.data import DevicePairSet, PairSet
+    cfg = {'synthetic': 11, 'crop': crop, 'random_augment': augment}
+    host, dev = PairSet(cfg, scale, seed=8), DevicePairSet(cfg, scale, seed=8, device=0)
+    # ragged, non-square sources: replace the synthetic squares by rectangles of different sizes
+    rs = np.random.RandomState(3)
+    items = []
+    for i in range(11):
+        h, w = crop + rs.randint(0, 40), crop + rs.randint(0, 40)
+        items.append((f'img_{i}', rs.randint(0, 256, (h, w, 3), dtype=np.uint8),
+                      rs.randint(0, 256, (h * scale, w * scale, 3), dtype=np.uint8)))
+    host.items = items
+    dev2 = DevicePairSet.__new__(DevicePairSet)
+    dev2.__dict__.update(dev.__dict__)
+    dev2.items = items
+    dev2._lr = [torch.from_numpy(a).to(DEV) for _, a, _ in items]
+    dev2._hr = [torch.from_numpy(a).to(DEV) for _, _, a in items]
+    dev2._lr_tab = torch.tensor([t.data_ptr() for t in dev2._lr], dtype=torch.int64, device=DEV)
+    dev2._hr_tab = torch.tensor([t.data_ptr() for t in dev2._hr], dtype=torch.int64, device=DEV)
+    n_batches = 0
+    for _ in range(3):                                                    # three epochs: the RNG streams stay in step
+        for hb, db in zip(host.batches(4), dev2.batches(4)):
+            assert hb['tag'] == db['tag']
+            assert torch.equal(hb['lr'], db['lr'].cpu()), 'LR patch batch differs'
+            assert torch.equal(hb['hr'], db['hr'].cpu()), 'HR patch batch differs'
+            n_batches += 1
+    assert n_batches == 6
+
+
+def test_glue_rejects_cpu_tensors():
+    from rumpy_b200 import _lib
+    from rumpy_b200.shared_framework.data import psnr_y_device, quantize_u8_device
+    with pytest.raises(_lib.RumpyB200Error):
+        quantize_u8_device(torch.rand(1, 3, 4, 4))
+    with pytest.raises(_lib.RumpyB200Error):
+        psnr_y_device(torch.rand(1, 3, 4, 4), torch.rand(1, 3, 4, 4))
