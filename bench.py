@@ -423,6 +423,9 @@ def glue_bench(device):
     res['host_path_ms'] = (_t.perf_counter() - t0) * 1e3     # D2H fp32 + numpy PSNR + numpy quantise (reference flow)
     cfg = {'synthetic': 64, 'crop': 64, 'random_augment': True}
     host, dev = PairSet(cfg, SCALE, seed=8), DevicePairSet(cfg, SCALE, seed=8, device=device.index or 0)
+    for _ in dev.batches(16):      # warm-up epoch (allocator, pinned staging)
+        pass
+    torch.cuda.synchronize()
     t0 = _t.perf_counter()
     nb = sum(1 for _ in host.batches(16))
     host_s = _t.perf_counter() - t0
