@@ -365,6 +365,31 @@ def extra_configs(device):
                              'note': f'{BATCH} x {LR_HW}x{LR_HW}, metadata copy + graph replay + output clone per call'}
     del qnet
     torch.cuda.empty_cache()
+    # HAN (10 x 20 RCAN groups + layer attention + channel-spatial attention) at configs[1]'s batch
+    from rumpy_b200.SISR.models.advanced.architectures import HAN
+    hnet = HAN()
+    hsd = recipe.make_weights(recipe.han_spec(20), seed=8)
+    hsd['la.gamma'] = np.array([0.3], dtype=np.float32)
+    hsd['csa.gamma'] = np.array([0.5], dtype=np.float32)
+    hnet.load_state_dict({k: torch.from_numpy(v) for k, v in hsd.items()}, strict=True)
+    hnet = hnet.to(device).eval()
+    x = torch.rand((BATCH, 3, LR_HW, LR_HW), device=device)
+    with torch.no_grad():
+        for _ in range(3):
+            hnet(x)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(10):
+            hnet(x)
+        e1.record()
+        e1.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    out['han_x4_infer'] = {'ms_per_step': ms, 'out_mpix_per_s': OUT_MPIX_PER_STEP / (ms * 1e-3),
+                           'launches': int(hnet.native_engine().lib.rumpy_net_num_launches(hnet.native_engine().handle)),
+                           'note': f'{BATCH} x {LR_HW}x{LR_HW}; ops: head, trunk, LAM (3 kernels), last_conv, CSAM+cat, '
+                                   'last, 2 upsampler convs, tail'}
+    del hnet
+    torch.cuda.empty_cache()
     out['torch_eager_gpu_baseline'] = eager_gpu_baseline(device)
     out['glue'] = glue_bench(device)
     return out

@@ -114,7 +114,12 @@ int rumpy_pool_sum(const float* x_nhwc, float* pool_partial, int N, int H, int W
  * state_dict order; `packed` (rumpy_net_packed_bytes) and `workspace` (rumpy_net_workspace_bytes)
  * are caller-owned device buffers.  The handle caches the per-layer launch plan (TMA descriptors) for the last
  * (packed, workspace, N, H, W, training) it saw; a steady-state forward only launches kernels and is
- * CUDA-graph capturable.  arch: 0 = RCAN (n_groups x n_blocks RCABs), 1 = EDSR (n_blocks ResBlocks).
+ * CUDA-graph capturable.  arch: 0 = RCAN (n_groups x n_blocks RCABs), 1 = EDSR (n_blocks ResBlocks),
+ * 2 = HAN (HAN.forward architectures.py:368-392 with LAM_Module / CSAM_Module HAN_blocks.py:8-76:
+ * RCAN's groups in the trunk kernels, then layer attention over the 11 stacked group / body outputs -> last_conv,
+ * channel-spatial attention of the body output, last(cat) + head skip; n_feats 64, n_groups 10 as the reference fixes
+ * them; params in the reference's order head | body | csa.gamma, csa.conv | la.gamma | last_conv | last | tail;
+ * inference only).
  * x: fp32 NCHW [N,in_feats,H,W] -> y: fp32 NCHW [N,out_feats,H*scale,W*scale], the reference's tensors.
  * training != 0 keeps every activation backward needs in the workspace.
  * ------------------------------------------------------------------------------------------------- */

@@ -16,6 +16,7 @@ Reference lines restated (relative to /root/reference):
   ResidualGroup :121-124   RCAB :81-84   CALayer :41-44
   EDSR.forward  :236-241   ResBlock common.py:71-75   Upsampler common.py:29-44
   QRCAN.forward rumpy/SISR/models/attention_manipulators/architectures.py:438-446 (qrcan_forward below)
+  HAN.forward   rumpy/SISR/models/advanced/architectures.py:368-392, HAN_blocks.py:17-76 (han_forward below)
   train step    rumpy/shared_framework/models/base_architecture.py:425-440,457-485
 """
 from __future__ import annotations
@@ -119,6 +120,37 @@ def qedsr_forward(sd, x, attributes, num_blocks, res_scale=0.1, scale=4):
             r = r * torch.sigmoid(q)
         res = r + res
     res = conv('final_body', res) + x
+    return _tail(sd, res, scale)
+
+
+def han_forward(sd, x, n_resgroups=10, n_resblocks=20, scale=4):
+    """HAN forward (reference advanced/architectures.py:368-392, HAN_blocks.py: LAM_Module.forward :17-41,
+    CSAM_Module.forward :55-76)."""
+    x = _conv(sd, 'head.0', x)
+    res = x
+    stack = []
+    for g in range(n_resgroups):
+        gin = res
+        for b in range(n_resblocks):
+            p = f'body.{g}.body.{b}.body'
+            t = F.relu(_conv(sd, p + '.0', res))
+            res = _ca(sd, p + '.3', _conv(sd, p + '.2', t)) + res
+        res = _conv(sd, f'body.{g}.body.{n_resblocks}', res) + gin
+        stack.insert(0, res)
+    res = _conv(sd, f'body.{n_resgroups}', res)
+    stack.insert(0, res)
+    out1 = res
+    s = torch.stack(stack, 1)                                     # B x L x C x H x W, newest first
+    B, L, C, H, W = s.shape
+    q = s.reshape(B, L, -1)
+    energy = torch.bmm(q, q.permute(0, 2, 1))
+    att = torch.softmax(energy.max(-1, keepdim=True)[0].expand_as(energy) - energy, dim=-1)
+    la = (sd['la.gamma'] * torch.bmm(att, q).reshape(B, L, C, H, W) + s).reshape(B, -1, H, W)
+    out2 = _conv(sd, 'last_conv', la)
+    a = torch.sigmoid(F.conv3d(out1.unsqueeze(1), sd['csa.conv.weight'], sd['csa.conv.bias'], padding=1))
+    a = (sd['csa.gamma'] * a).reshape(B, -1, H, W)
+    out1 = out1 * a + out1
+    res = _conv(sd, 'last', torch.cat([out1, out2], 1)) + x
     return _tail(sd, res, scale)
 
 

@@ -15,6 +15,7 @@ from torch import nn
 from rumpy_b200 import blocks_native as _bn
 from rumpy_b200 import engine as _engine
 from rumpy_b200.SISR.models.advanced import common
+from rumpy_b200.SISR.models.advanced.HAN_blocks import CSAM_Module, LAM_Module
 from rumpy_b200.trunk_function import trunk_apply
 
 
@@ -149,3 +150,35 @@ class EDSR(_NativeTrunk):
 
     def _engine_kwargs(self):
         return _engine.ARCH_EDSR, dict(self._cfg)
+
+
+class HAN(_NativeTrunk):
+    """reference architectures.py:331-394: RCAN's residual groups, then layer attention (LAM) over the 11 stacked
+    group / body outputs -> last_conv, channel-spatial attention (CSAM) of the body output, last(cat) + head skip.
+    The groups run in the trunk kernels; LAM / CSAM are the kernels of csrc/han.cu.  Inference only."""
+
+    def __init__(self, n_resgroups=10, n_resblocks=20, n_feats=64, reduction=16, scale=4, n_colors=3, res_scale=1.0,
+                 conv=common.default_conv):
+        super(HAN, self).__init__()
+        kernel_size = 3
+        act = nn.ReLU(True)
+        modules_head = [conv(n_colors, n_feats, kernel_size)]
+        modules_body = [
+            ResidualGroup(conv, n_feats, kernel_size, reduction, act=act, res_scale=res_scale, n_resblocks=n_resblocks)
+            for _ in range(n_resgroups)]
+        modules_body.append(conv(n_feats, n_feats, kernel_size))
+        modules_tail = [
+            common.Upsampler(conv, scale, n_feats, act=False),
+            conv(n_feats, n_colors, kernel_size)]
+        self.head = nn.Sequential(*modules_head)
+        self.body = nn.Sequential(*modules_body)
+        self.csa = CSAM_Module(n_feats)
+        self.la = LAM_Module(n_feats)
+        self.last_conv = nn.Conv2d(n_feats * 11, n_feats, 3, 1, 1)     # the reference fixes 11 = 10 groups + body conv
+        self.last = nn.Conv2d(n_feats * 2, n_feats, 3, 1, 1)
+        self.tail = nn.Sequential(*modules_tail)
+        self._cfg = dict(n_feats=n_feats, n_groups=n_resgroups, n_blocks=n_resblocks, reduction=reduction,
+                         scale=scale, res_scale=1.0, in_feats=n_colors, out_feats=n_colors)
+
+    def _engine_kwargs(self):
+        return _engine.ARCH_HAN, dict(self._cfg)

@@ -1,6 +1,6 @@
 """Mirror of the reference's EDSR / RCAN handlers (/root/reference/rumpy/SISR/models/advanced/handlers.py:8-42):
-same registry names ('edsr', 'rcan'), constructor arguments and attributes."""
-from rumpy_b200.SISR.models.advanced.architectures import EDSR, RCAN
+same registry names ('edsr', 'rcan', 'han'), constructor arguments and attributes."""
+from rumpy_b200.SISR.models.advanced.architectures import EDSR, HAN, RCAN
 from rumpy_b200.shared_framework.models.base_architecture import BaseModel
 
 
@@ -30,3 +30,18 @@ class RCANHandler(BaseModel):
         self.activate_device()
         self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
         self.model_name = 'rcan'
+
+
+class HANHandler(BaseModel):
+    """reference handlers.py:44-58 (most parameters locked, as there); inference only here."""
+
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
+                 scheduler=None, scheduler_params=None, **kwargs):
+        super(HANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                         **kwargs)
+        self.net = HAN(scale=scale)
+        self.colorspace = 'rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.model_name = 'han'

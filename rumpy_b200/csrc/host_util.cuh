@@ -76,6 +76,14 @@ struct QScaleJobHost { const float *w1, *b1, *w2, *b2; float* out; };
 int q_scale_launch(const QScaleJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C,
                    int modulate, int relu, cudaStream_t s);
 
+// HAN attention modules (han.cu): layer attention over the kLamLayers stacked fp32 NHWC feature maps -> bf16 NHWC with
+// kLamLayers*64 channels; channel-spatial attention + concat -> bf16 NHWC with 128 channels
+constexpr int kLamLayers = 11;   // the reference hard-codes n_feats*11 (10 residual groups + the body conv)
+int lam_workspace_floats(int N);
+int lam_launch(const float* const* stack, float* scratch, const float* gamma, void* out_bf16, int N, int HW, cudaStream_t s);
+int csam_cat_launch(const float* x, const float* out2, const float* w, const float* b, const float* gamma, void* cat_bf16,
+                    int N, int H, int W, cudaStream_t s);
+
 // one q-layer's parameter-gradient job (trunk_bwd.cuh: QGradJob has the same layout)
 struct QGradJobHost { const float *w1, *b1, *w2, *b2, *q, *dq; float *dw1, *db1, *dw2, *db2; };
 int q_grad_launch(const QGradJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C, int relu,

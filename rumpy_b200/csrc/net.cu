@@ -33,7 +33,7 @@ struct ConvW {            // one 3x3 conv of the network
 struct CAW { int w1, b1, w2, b2; };
 using QScaleJob = QScaleJobHost;   // q_scale_kernel job (w1 == nullptr: no q-layer)
 
-enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD };
+enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD, OP_LAM, OP_CSAM };
 
 extern int g_use_fused_ca;
 extern int g_use_cluster;
@@ -56,6 +56,8 @@ struct Op {
   float* s_partial; void* du; float* du_colsum; int ca_chunks;
   float* pool_compact;
   const float* q_scale;   // OP_CA (Q-RCAN): [N][C] multipliers of the CA vector, or nullptr
+  // OP_LAM / OP_CSAM (HAN)
+  const float* stack[kLamLayers]; float* lam_scratch; void* lam_out; const float* csam_x; const float* csam_out2; void* cat;
   // OP_ADD / OP_HEAD_WGRAD / OP_TAIL_BWD
   const float *a, *b; float* dst_f; void* dst_b; size_t n4;
   const void* tail_in; void* g_hr; float* thin_partial;
@@ -74,6 +76,10 @@ struct Net {
   std::vector<CAW> cas;
   // Q-RCAN (meta-attention, attention_manipulators/architectures.py:154-246, q_layer.py:5-45): per-RCAB q-layer
   // parameters (w1 < 0: the RCAB has none), metadata vector length, q-layer hidden width, 'modulate' style flag
+  // HAN (advanced/architectures.py:331-394): RCAN groups + layer attention + channel-spatial attention; parameter
+  // indices of csa.gamma, csa.conv.weight, csa.conv.bias, la.gamma and the two extra convs (last_conv, last)
+  bool han = false;
+  int p_csa_gamma = -1, p_csa_w = -1, p_csa_b = -1, p_la_gamma = -1, conv_lastconv = -1, conv_last = -1;
   bool qrcan = false;
   std::vector<CAW> qs;
   int num_meta = 0, q_hidden = 0, modulate = 0, q_relu = 1;
@@ -200,6 +206,22 @@ static int net_init(Net* n) {
     set(n->conv_tail);
     n->n_params = p;
   }
+  if (n->han) {
+    // registration order (architectures.py:360-366): head | body | csa.gamma, csa.conv.{weight,bias} | la.gamma |
+    // last_conv | last | tail
+    n->conv_lastconv = int(n->convs.size());
+    add_conv(n, C, C * (n->n_groups + 1));
+    n->conv_last = int(n->convs.size());
+    add_conv(n, C, 2 * C);
+    int p = n->convs[n->conv_body].b_idx + 1;
+    auto set = [&](int ci) { n->convs[ci].w_idx = p++; n->convs[ci].b_idx = p++; };
+    n->p_csa_gamma = p++; n->p_csa_w = p++; n->p_csa_b = p++; n->p_la_gamma = p++;
+    set(n->conv_lastconv);
+    set(n->conv_last);
+    for (int s2 = 0; s2 < st; ++s2) set(n->conv_up0 + s2);
+    set(n->conv_tail);
+    n->n_params = p;
+  }
   if (n->qrcan && n->arch == 1) {
     // QEDSR registration order (attention_manipulators/architectures.py:501-548, 463-482):
     // head | final_body | per block: body.0, body.2, [attention_layer] | tail
@@ -273,7 +295,13 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   float* head_f = static_cast<float*>(bp.take(px * C * 4));
   void* head_b = bp.take(px * C * 2);
   float* S_f = static_cast<float*>(bp.take(px * C * 4));
-  float* G_f[2] = {static_cast<float*>(bp.take(px * C * 4)), static_cast<float*>(bp.take(px * C * 4))};
+  // fp32 group outputs: two ping-pong buffers (RCAN) or one per group (HAN stacks them for the layer attention)
+  const bool han = n->han;
+  if (han && training) return set_error(RUMPY_ERR_ARG, "HAN: training is not implemented (inference only)");
+  std::vector<float*> G_bufs(han ? n->n_groups : 2);
+  for (auto& g : G_bufs) g = static_cast<float*>(bp.take(px * C * 4));
+  struct { std::vector<float*>* v; bool han; float* operator[](int g) const { return (*v)[han ? g : (g & 1)]; } } G_f{&G_bufs, han};
+  float* han_body_f = han ? static_cast<float*>(bp.take(px * C * 4)) : nullptr;   // body conv output (no skip in HAN)
   const int tiles = ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW);
   int ci = 0;  // conv cursor
   // ---- head
@@ -371,8 +399,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         void* gout = next_out();
         gr.tail_in_b = cur_b; gr.conv_tail = c2;
         if (TrunkLayer* l = add_layer(kTrunkRes, c2++, -1, cur_b, gout)) {   // group tail conv + group skip (:121-124)
-          l->res_f32 = g == 0 ? head_f : G_f[(g - 1) & 1];
-          l->out_f32 = G_f[g & 1];
+          l->res_f32 = g == 0 ? head_f : G_f[g - 1];
+          l->out_f32 = G_f[g];
           l->update_s = 1;
         }
         groups.push_back(gr);
@@ -396,8 +424,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     }
     trunk_body_in = cur_b;
     void* body_b = bp.take(px * C * 2);
-    if (TrunkLayer* l = add_layer(kTrunkRes, c2++, -1, cur_b, body_b))       // body tail conv + global skip
-      l->res_f32 = head_f;
+    if (TrunkLayer* l = add_layer(kTrunkRes, c2++, -1, cur_b, body_b)) {     // body tail conv + global skip
+      if (han) { l->no_res = 1; l->out_f32 = han_body_f; }                   // HAN: plain conv, fp32 copy for LAM / CSAM
+      else l->res_f32 = head_f;
+    }
     if (build) {
       if (c2 != n_body + 1) err = set_error(RUMPY_ERR_ARG, "trunk: layer count mismatch");
       if (int e = trunk_plan_finish(trunk.get(), N, H, W, Cr, pk + n->convs[1].off_fwd, head_f, dev, !training)) err = e;
@@ -470,13 +500,13 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         cur_b = xb; cur_f = S_f;
       }
       ConvDesc dg{};
-      dg.x = cur_b; dg.residual = gin_f; dg.y_f32 = G_f[g & 1]; dg.y_bf16 = training ? bp.take(px * C * 2) : gb[g & 1];
+      dg.x = cur_b; dg.residual = gin_f; dg.y_f32 = G_f[g]; dg.y_bf16 = training ? bp.take(px * C * 2) : gb[g & 1];
       dg.N = N; dg.H = H; dg.W = W; dg.Cin = C; dg.Cout = C; dg.alpha = 1.f;
       void* gout_b = dg.y_bf16;
       gr.tail_in_b = cur_b; gr.conv_tail = ci;
       conv_op(ops, n->convs[ci++], dg, false);
       groups.push_back(gr);
-      cur_b = gout_b; cur_f = G_f[g & 1];
+      cur_b = gout_b; cur_f = G_f[g];
     }
   } else {
     void* t_shared = training ? nullptr : bp.take(px * C * 2);
@@ -507,8 +537,38 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     ConvDesc d{};
     d.x = cur_b; d.residual = head_f; d.y_bf16 = body_b; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C;
     d.alpha = 1.f;
+    if (han) { d.residual = nullptr; d.y_f32 = han_body_f; }     // HAN: plain conv, fp32 copy for LAM / CSAM
     conv_op(ops, n->convs[ci++], d, false);
     cur_b = body_b;
+  }
+  // ---- HAN: layer attention over the stacked group outputs -> last_conv; channel-spatial attention of the body
+  // output; last(cat) + head skip  (architectures.py:368-392)
+  if (han) {
+    const int L = n->n_groups + 1;
+    if (L != kLamLayers) return set_error(RUMPY_ERR_ARG, "HAN: %d residual groups (the reference fixes 10)", n->n_groups);
+    void* lam_out = bp.take(px * C * L * 2);
+    float* lam_scratch = static_cast<float*>(bp.take(size_t(lam_workspace_floats(N)) * 4));
+    float* out2_f = static_cast<float*>(bp.take(px * C * 4));
+    void* cat = bp.take(px * 2 * C * 2);
+    void* last_b = bp.take(px * C * 2);
+    Op lam{};
+    lam.type = OP_LAM;
+    lam.stack[0] = han_body_f;                                   // res1 is stacked newest first (:373-378)
+    for (int k = 1; k < L; ++k) lam.stack[k] = G_f[L - 1 - k];
+    lam.lam_scratch = lam_scratch; lam.lam_out = lam_out;
+    ops.push_back(lam);
+    ConvDesc d1{};
+    d1.x = lam_out; d1.y_f32 = out2_f; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C * L; d1.Cout = C; d1.alpha = 1.f;
+    conv_op(ops, n->convs[n->conv_lastconv], d1, false);
+    Op cs{};
+    cs.type = OP_CSAM;
+    cs.csam_x = han_body_f; cs.csam_out2 = out2_f; cs.cat = cat;
+    ops.push_back(cs);
+    ConvDesc d2{};
+    d2.x = cat; d2.residual = head_f; d2.y_bf16 = last_b; d2.N = N; d2.H = H; d2.W = W; d2.Cin = 2 * C; d2.Cout = C;
+    d2.alpha = 1.f;
+    conv_op(ops, n->convs[n->conv_last], d2, false);
+    cur_b = last_b;
   }
   // ---- upsampler: conv C -> C*r*r with the PixelShuffle folded into the store
   int r = 0;
@@ -872,7 +932,13 @@ extern "C" {
 int rumpy_net_create(void** out, int arch, int n_feats, int n_groups, int n_blocks, int reduction, int scale,
                      float res_scale, int in_feats, int out_feats, int u_f32) {
   if (!out) return set_error(RUMPY_ERR_ARG, "net_create: null out");
-  if (arch != 0 && arch != 1) return set_error(RUMPY_ERR_ARG, "net_create: arch %d", arch);
+  if (arch != 0 && arch != 1 && arch != 2) return set_error(RUMPY_ERR_ARG, "net_create: arch %d", arch);
+  const bool han = arch == 2;
+  if (han) {
+    if (n_feats != 64 || n_groups != kLamLayers - 1)
+      return set_error(RUMPY_ERR_ARG, "net_create: HAN needs n_feats=64 and %d residual groups", kLamLayers - 1);
+    arch = 0;
+  }
   if (n_feats % 64 != 0 || n_feats <= 0 || n_feats > 256)
     return set_error(RUMPY_ERR_ARG, "net_create: n_feats=%d must be 64, 128, 192 or 256", n_feats);
   if (in_feats < 1 || in_feats > 4 || out_feats < 1 || out_feats > 4)
@@ -882,6 +948,7 @@ int rumpy_net_create(void** out, int arch, int n_feats, int n_groups, int n_bloc
   Net* n = new Net();
   n->arch = arch; n->C = n_feats; n->n_groups = n_groups; n->n_blocks = n_blocks; n->reduction = reduction;
   n->scale = scale; n->res_scale = res_scale; n->in_feats = in_feats; n->out_feats = out_feats; n->u_f32 = u_f32;
+  n->han = han;
   if (int e = net_init(n)) { delete n; return e; }
   *out = n;
   return RUMPY_OK;
@@ -1041,6 +1108,14 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
       case OP_HEAD:
         if (int e = rumpy_head_conv(x_nchw, params[op.head_w], params[op.head_b], op.yf, op.yb, N, H, W, n->in_feats,
                                     n->C, stream))
+          return e;
+        break;
+      case OP_LAM:
+        if (int e = lam_launch(op.stack, op.lam_scratch, params[n->p_la_gamma], op.lam_out, N, H * W, stream)) return e;
+        break;
+      case OP_CSAM:
+        if (int e = csam_cat_launch(op.csam_x, op.csam_out2, params[n->p_csa_w], params[n->p_csa_b],
+                                    params[n->p_csa_gamma], op.cat, N, H, W, stream))
           return e;
         break;
       case OP_QSCALE: {

@@ -295,7 +295,11 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[i], 0.f);
         } else {
-          if (res != nullptr) {
+          if (lay->no_res) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = 0.f;
+          } else if (res != nullptr) {
             tmem_ld_wait();
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {

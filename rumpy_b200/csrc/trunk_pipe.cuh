@@ -37,7 +37,7 @@ struct TrunkLayer {
   int update_s;          // kTrunkRes: the result replaces the fp32 residual stream in TMEM
   int u_map;             // kTrunkCA (training): out map of the saved pre-attention activation u (bf16), or -1
   float alpha;           // kTrunkRes: out = alpha * (acc + bias) + residual
-  int pad_;
+  int no_res;            // kTrunkRes: no residual term at all (out = alpha * (acc + bias)); HAN's body conv
   const float* bias;
   const float* res_f32;  // kTrunkRes: fp32 NHWC residual in global memory; nullptr = the TMEM stream
   float* out_f32;        // kTrunkRes: optional fp32 NHWC copy of the result (a later layer's res_f32)
@@ -371,7 +371,11 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[h * 32 + i], 0.f);
           } else {
-            if (res != nullptr) {
+            if (lay->no_res) {
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = 0.f;
+            } else if (res != nullptr) {
               tmem_ld_wait();
 #pragma unroll
               for (int c4 = 0; c4 < 8; ++c4) {

@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN, ARCH_QEDSR = 0, 1, 2, 3
+ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN, ARCH_QEDSR, ARCH_HAN = 0, 1, 2, 3, 4
 
 _FLAT = {}   # id(first parameter) -> (flat fp32 buffer, weakref to first parameter): shared by engine and FusedAdam
 
@@ -64,7 +64,7 @@ class TrunkEngine:
                       scale, float(res_scale), in_feats, out_feats, int(num_metadata), int(q_hidden), flags,
                       int(bool(modulate)), int(bool(q_relu)))
         else:
-            _lib.call('rumpy_net_create', ctypes.byref(h), arch, n_feats, n_groups, n_blocks, reduction, scale,
+            _lib.call('rumpy_net_create', ctypes.byref(h), 2 if arch == ARCH_HAN else arch, n_feats, n_groups, n_blocks, reduction, scale,
                       float(res_scale), in_feats, out_feats, int(u_f32))
         self.handle = h
         n = self.lib.rumpy_net_num_params(h)

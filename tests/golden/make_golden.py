@@ -253,6 +253,20 @@ def qrcan_cases():
     return rec
 
 
+def han_cases(arch_mod):
+    rec = {}
+    for name in recipe.HCASES:
+        nb, scale, sd, x = recipe.hcase_tensors(name)
+        net = arch_mod.HAN(n_resblocks=nb, scale=scale)
+        assert list(net.state_dict().keys()) == list(sd.keys()), 'HAN key order mismatch vs reference'
+        net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+        net.eval()
+        with torch.no_grad():
+            rec[name + '::out'] = net(t(x)).numpy()
+        print(name, rec[name + '::out'].shape, float(np.abs(rec[name + '::out']).max()))
+    return rec
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     arch_mod, common = import_reference()
@@ -263,6 +277,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'blocks.npz'), **block_cases(arch_mod, common))
     np.savez_compressed(os.path.join(HERE, 'set5_edsr_baseline.npz'), **set5_case(arch_mod))
     np.savez_compressed(os.path.join(HERE, 'qrcan.npz'), **qrcan_cases())
+    np.savez_compressed(os.path.join(HERE, 'han.npz'), **han_cases(arch_mod))
     print('done')
 
 

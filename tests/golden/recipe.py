@@ -212,3 +212,34 @@ def qecase_tensors(name):
     x = make_input(shape, xseed)
     meta = make_input((shape[0], kw['input_para']), xseed + 500)
     return kw, has_q, sd, x, meta
+
+
+# ---------------------------------------------------------------------------- HAN
+def han_spec(n_resblocks, n_feats=64, reduction=16, scale=4):
+    """state_dict layout of the reference's HAN (10 residual groups fixed by last_conv's n_feats*11 input)."""
+    spec = rcan_spec(10, n_resblocks, n_feats, reduction, scale)
+    cut = [i for i, (k, _) in enumerate(spec) if k.startswith('tail.')][0]
+    extra = [('csa.gamma', (1,)), ('csa.conv.weight', (1, 1, 3, 3, 3)), ('csa.conv.bias', (1,)), ('la.gamma', (1,))]
+    _conv_spec(extra, 'last_conv', n_feats, n_feats * 11, 3)
+    _conv_spec(extra, 'last', n_feats, n_feats * 2, 3)
+    return spec[:cut] + extra + spec[cut:]
+
+
+# name -> (n_resblocks, scale, lr-input shape, weight seed, input seed, la.gamma, csa.gamma)
+HCASES = OrderedDict(
+    han_b1_x4=(1, 4, (2, 3, 12, 20), 81, 82, 0.4, 0.6),
+    han_b2_x2=(2, 2, (1, 3, 9, 13), 83, 84, -0.3, 1.0),
+)
+
+
+def hcase_tensors(name):
+    nb, scale, shape, wseed, xseed, la_g, csa_g = HCASES[name]
+    spec = han_spec(nb, scale=scale)
+    rs_fix = {'csa.gamma': csa_g, 'la.gamma': la_g}
+    # conv3d fan-in: give the 27-tap kernel O(1) weights so the sigmoid moves
+    sd = make_weights([(k, (s if k not in rs_fix else (1, 1, 1, 1))) for k, s in spec], wseed)
+    for k, v in rs_fix.items():
+        sd[k] = np.full((1,), v, dtype=np.float32)
+    sd['csa.conv.weight'] = np.random.RandomState(wseed + 1).uniform(-0.5, 0.5, (1, 1, 3, 3, 3)).astype(np.float32)
+    sd['csa.conv.bias'] = np.array([0.1], dtype=np.float32)
+    return nb, scale, sd, make_input(shape, xseed)

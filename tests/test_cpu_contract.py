@@ -88,10 +88,19 @@ def test_qrcan_state_dict_layout_matches_reference_spec():
         QRCAN(style='standard', reduction=8)
 
 
+def test_han_state_dict_layout_matches_reference_spec():
+    from rumpy_b200.SISR.models.advanced.architectures import HAN
+    for name in recipe.HCASES:
+        nb, scale, sd, x = recipe.hcase_tensors(name)
+        m = HAN(n_resblocks=nb, scale=scale)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, v.shape) for k, v in sd.items()], name
+    assert sum(p.numel() for p in HAN().parameters()) == 15592355 + 3 + 27 + (64 * 704 * 9 + 64) + (64 * 128 * 9 + 64)
+
+
 def test_registry_and_legacy_switch():
     from rumpy_b200.shared_framework.models import available_models
     from rumpy_b200.shared_framework.models.base_architecture import BaseModel
-    assert set(available_models) == {'rcan', 'edsr', 'qrcan', 'qedsr'}
+    assert set(available_models) == {'rcan', 'edsr', 'han', 'qrcan', 'qedsr'}
     sd = {'model.module.head.0.weight': 1, 'model.body.0.bias': 2, 'tail.1.bias': 3}
     assert list(BaseModel.legacy_switch(sd)) == ['head.0.weight', 'body.0.bias', 'tail.1.bias']
     with pytest.raises(RuntimeError):

@@ -1,0 +1,82 @@
+"""GPU parity of the HAN widening: residual groups in the trunk kernels + the layer-attention and
+channel-spatial-attention kernels of csrc/han.cu, against outputs of the unmodified reference (tests/golden/han.npz)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import recipe
+from oracle import sr_torch_cpu
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+MODES = {'per-layer': (0, 0), 'dataflow': (1, 0), 'cluster': (1, 1)}
+
+
+def _lib():
+    from rumpy_b200 import _lib
+    lib = _lib.load()
+    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
+    return lib
+
+
+def _han(nb, scale, sd):
+    from rumpy_b200.SISR.models.advanced.architectures import HAN
+    net = HAN(n_resblocks=nb, scale=scale)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    return net.to(DEV).eval()
+
+
+@pytest.mark.parametrize('name', list(recipe.HCASES))
+def test_han_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
+    gold = np.load(os.path.join(golden_dir, 'han.npz'))
+    nb, scale, sd, x = recipe.hcase_tensors(name)
+    net = _han(nb, scale, sd)
+    xt = torch.from_numpy(x).to(DEV)
+    ref = gold[name + '::out']
+    lib = _lib()
+    outs = {}
+    try:
+        for mode, (trunk, cluster) in MODES.items():
+            lib.rumpy_debug_set_trunk(trunk)
+            lib.rumpy_debug_set_trunk_cluster(cluster)
+            eng = net.native_engine()
+            eng._ws.clear()
+            eng._graphs.clear()
+            eng._last_infer_shape = None
+            with torch.no_grad():
+                a = net(xt).clone()
+                b = net(xt).clone()      # CUDA-graph replay
+            assert bool((a == b).all()), f'{mode}: graph replay differs from the eager forward'
+            outs[mode] = a.cpu().numpy()
+            err = float(np.abs(outs[mode] - ref).max())
+            assert err <= 1e-2, f'{name} [{mode}]: max-abs {err} vs the reference output'
+    finally:
+        lib.rumpy_debug_set_trunk(1)
+        lib.rumpy_debug_set_trunk_cluster(1)
+
+
+def test_han_handler_cfg2_batch_vs_oracle(tmp_path):
+    """HANHandler (registry name 'han', 10 groups x 20 blocks as the reference locks it) at BASELINE configs[1]'s batch
+    through run_eval, against the CPU oracle."""
+    from rumpy_b200.shared_framework.models import define_model
+    h = define_model('han', device=0, model_save_dir=str(tmp_path), eval_mode=True, scale=4)
+    assert h.model_name == 'han'
+    spec = recipe.han_spec(20)
+    assert [(k, tuple(v.shape)) for k, v in h.net.state_dict().items()] == [(k, tuple(s)) for k, s in spec]
+    sd = recipe.make_weights(spec, seed=85)
+    sd['la.gamma'] = np.array([0.3], dtype=np.float32)
+    sd['csa.gamma'] = np.array([0.5], dtype=np.float32)
+    sd['csa.conv.weight'] = np.random.RandomState(86).uniform(-0.5, 0.5, (1, 1, 3, 3, 3)).astype(np.float32)
+    h.net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    x = recipe.make_input((16, 3, 48, 48), 87)
+    out, _, _ = h.run_eval(torch.from_numpy(x))
+    assert _lib().rumpy_net_trunk_mode(h.net.native_engine().handle) == 2      # cluster kernel for the groups
+    ref = sr_torch_cpu.han_forward({k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(x), 10, 20, 4).numpy()
+    assert float(np.abs(out.numpy() - ref).max()) <= 1e-2
+    with pytest.raises(Exception, match='inference only'):
+        h.net.train()
+        h.net(torch.from_numpy(x[:1]).to(DEV))
