@@ -67,15 +67,23 @@ __global__ void psnr_y_partial_kernel(const float* __restrict__ sr, const float*
   if (threadIdx.x == 0) partial[size_t(n) * gridDim.x + blockIdx.x] = red[0];
 }
 
-// one thread per image: fixed-order sum of the partials -> PSNR (100 for identical images, metrics.py:41-42)
-__global__ void psnr_y_finalize_kernel(const double* __restrict__ partial, float* __restrict__ psnr, int N, int blocks,
+// one CTA per image: fixed-order tree sum of the partials -> PSNR (100 for identical images, metrics.py:41-42)
+__global__ void psnr_y_finalize_kernel(const double* __restrict__ partial, float* __restrict__ psnr, int blocks,
                                        double inv_count, float max_value) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  const int n = blockIdx.x;
+  __shared__ double red[256];
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += partial[size_t(n) * blocks + b];
-  const double mse = s * inv_count;
-  psnr[n] = mse == 0.0 ? 100.f : float(20.0 * log10(double(max_value) / sqrt(mse)));
+  for (int b = threadIdx.x; b < blocks; b += 256) s += partial[size_t(n) * blocks + b];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mse = red[0] * inv_count;
+    psnr[n] = mse == 0.0 ? 100.f : float(20.0 * log10(double(max_value) / sqrt(mse)));
+  }
 }
 
 // out[n][y][x][c] = uint8(trunc(clip(in[n][c][y][x] * 255, 0, 255)))
@@ -165,7 +173,7 @@ int rumpy_psnr_y(const float* sr, const float* hr, float* psnr, void* workspace,
   if (vec) psnr_y_partial_kernel<true><<<dim3(blocks, N), 256, 0, s>>>(sr, hr, part, HW);
   else psnr_y_partial_kernel<false><<<dim3(blocks, N), 256, 0, s>>>(sr, hr, part, HW);
   if (int e = check_launch("psnr_y_partial")) return e;
-  psnr_y_finalize_kernel<<<(N + 63) / 64, 64, 0, s>>>(part, psnr, N, blocks, 1.0 / (double(H) * W), max_value);
+  psnr_y_finalize_kernel<<<N, 256, 0, s>>>(part, psnr, blocks, 1.0 / (double(H) * W), max_value);
   return check_launch("psnr_y_finalize");
 }
 
