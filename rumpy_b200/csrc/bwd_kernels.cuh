@@ -226,18 +226,27 @@ __global__ void thin_wgrad_kernel(const float* __restrict__ thin, const void* __
 
 // partial [blocks][M*9+1][C] -> tail: dW[m][c][tap] (+ thin-sum bias comes from thin_sum_kernel)
 //                               head: dW[c][m][tap], db[c] = column sums (row M*9)
+// 32 outputs x 8 slices per CTA of 256 threads: slice s adds partials s, s+8, ... (coalesced over the 32 outputs), the
+// eight slice sums are combined in a fixed order (deterministic).
 __global__ void thin_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ dw,
                                          float* __restrict__ db_wide, int C, int M, int is_head) {
   const int rows = M * 9 + 1;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * C; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += partial[size_t(b) * rows * C + i];
-    const int c = i % C, row = i / C;
-    if (row == M * 9) { if (db_wide) db_wide[c] = s; continue; }
-    const int m = row / 9, tap = row % 9;
-    if (is_head) dw[(size_t(c) * M + m) * 9 + tap] = s;
-    else dw[(size_t(m) * C + c) * 9 + tap] = s;
-  }
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (i < rows * C)
+    for (int b = slice; b < blocks; b += 8) s += partial[size_t(b) * rows * C + i];
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || i >= rows * C) return;
+  s = ((red[0][lane] + red[1][lane]) + (red[2][lane] + red[3][lane])) +
+      ((red[4][lane] + red[5][lane]) + (red[6][lane] + red[7][lane]));
+  const int c = i % C, row = i / C;
+  if (row == M * 9) { if (db_wide) db_wide[c] = s; return; }
+  const int m = row / 9, tap = row % 9;
+  if (is_head) dw[(size_t(c) * M + m) * 9 + tap] = s;
+  else dw[(size_t(m) * C + c) * 9 + tap] = s;
 }
 
 // per-plane sums of an NCHW tensor: out[m] = sum_{n,p} t[n,m,p]   (tail bias gradient; M <= 4 planes)

@@ -53,25 +53,34 @@ __global__ void pack_conv3x3_batched_kernel(const PackJob* __restrict__ jobs) {
   const PackJob jb = jobs[blockIdx.y];
   const int rows = jb.dgrad ? jb.cin : jb.rows_padded;
   const int kdim = jb.dgrad ? jb.cout : jb.cin;
-  const size_t total = size_t(9) * rows * kdim;
+  const size_t plane = size_t(rows) * kdim;   // elements per tap
   const int rr = jb.r * jb.r, cpp = jb.cout / rr;
-  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < total;
+  // one thread per (row, k): its 9 taps are 36 contiguous bytes of the OIHW tensor; the 9 stores are coalesced in k
+  for (size_t idx = blockIdx.x * size_t(blockDim.x) + threadIdx.x; idx < plane;
        idx += size_t(gridDim.x) * blockDim.x) {
     const int k = int(idx % kdim);
-    const int row = int((idx / kdim) % rows);
-    const int tap = int(idx / (size_t(kdim) * rows));
-    const int kx = tap / 3, ky = tap % 3;
-    float v = 0.f;
+    const int row = int(idx / kdim);
+    float v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = 0.f;
     if (!jb.dgrad) {
       if (row < jb.cout) {
         const int o = (jb.r > 1) ? (row % cpp) * rr + row / cpp : row;
-        v = jb.w[((size_t(o) * jb.cin + k) * 3 + ky) * 3 + kx];
+        const float* src = jb.w + (size_t(o) * jb.cin + k) * 9;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = src[t];            // src[ky * 3 + kx]
       }
     } else {
       const int o = (jb.r > 1) ? (k % cpp) * rr + k / cpp : k;
-      v = jb.w[((size_t(o) * jb.cin + row) * 3 + (2 - ky)) * 3 + (2 - kx)];
+      const float* src = jb.w + (size_t(o) * jb.cin + row) * 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[t] = src[8 - t];          // 180-degree rotation: (2 - ky) * 3 + (2 - kx)
     }
-    jb.p[idx] = __float2bfloat16_rn(v);
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)                          // packed tap index = kx * 3 + ky
+        jb.p[size_t(kx * 3 + ky) * plane + idx] = __float2bfloat16_rn(v[ky * 3 + kx]);
   }
   if (jb.bp != nullptr && blockIdx.x == 0) {
     for (int row = threadIdx.x; row < jb.rows_padded; row += blockDim.x) {

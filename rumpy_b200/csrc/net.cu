@@ -1225,7 +1225,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
           thin_wgrad_kernel<true, 4><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
               dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
         if (int e = check_launch("tail_wgrad")) return e;
-        thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[tail.w_idx], nullptr, C, M, 0);
+        thin_wgrad_reduce_kernel<<<((M * 9 + 1) * C + 31) / 32, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[tail.w_idx], nullptr, C, M, 0);
         if (int e = check_launch("tail_wgrad_reduce")) return e;
         plane_sum_kernel<<<dim3(kPlaneSlices, M), 512, 0, stream>>>(dy_nchw, op.thin_partial, N, M, Hh * Wh);
         if (int e = check_launch("tail_bias_grad")) return e;
@@ -1292,7 +1292,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
           thin_wgrad_kernel<false, 4><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
               x_nchw, op.a, op.b, op.thin_partial, N, H, W, C, M, +1);
         if (int e = check_launch("head_wgrad")) return e;
-        thin_wgrad_reduce_kernel<<<8, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[head.w_idx],
+        thin_wgrad_reduce_kernel<<<((M * 9 + 1) * C + 31) / 32, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[head.w_idx],
                                                         grads[head.b_idx], C, M, 1);
         if (int e = check_launch("head_wgrad_reduce")) return e;
         break;

@@ -123,8 +123,8 @@ class DevicePairSet(PairSet):
         if not self.crop:
             raise ValueError('DevicePairSet needs `crop` (training patches); use PairSet for whole images')
         self.device = torch.device('cuda', device) if isinstance(device, int) else torch.device(device)
-        self._lr = [torch.from_numpy(np.ascontiguousarray(lr)).to(self.device) for _, lr, _ in self.items]
-        self._hr = [torch.from_numpy(np.ascontiguousarray(hr)).to(self.device) for _, _, hr in self.items]
+        self._lr = [torch.from_numpy(np.array(lr, copy=True)).to(self.device) for _, lr, _ in self.items]
+        self._hr = [torch.from_numpy(np.array(hr, copy=True)).to(self.device) for _, _, hr in self.items]
         self._lr_tab = torch.tensor([t.data_ptr() for t in self._lr], dtype=torch.int64, device=self.device)
         self._hr_tab = torch.tensor([t.data_ptr() for t in self._hr], dtype=torch.int64, device=self.device)
 
