@@ -133,6 +133,31 @@ __global__ void tail_dgrad_kernel(const float* __restrict__ dy, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Upstream gradient of the thin tail conv as a tensor-core operand: dy fp32 NCHW [N][M][H][W] (M <= 4) -> bf16 NHWC
+// with 64 channels (channels >= M zero), so the tail conv's weight gradient rides in the batched tcgen05 wgrad kernel
+// as one more 64x64 block instead of a CUDA-core pass (was 0.67 ms of the 15.8 ms RCAN train step).
+// One thread = one pixel x one 16-byte chunk (8 channels); a warp writes 4 whole pixels (512 contiguous bytes).
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_thin_grad_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ out, int N, int M,
+                                     int HW) {
+  const size_t total = size_t(N) * HW * 8;
+  for (size_t t = blockIdx.x * size_t(blockDim.x) + threadIdx.x; t < total; t += size_t(gridDim.x) * blockDim.x) {
+    const int chunk = int(t & 7);
+    const size_t pix = t >> 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (chunk == 0) {
+      const size_t n = pix / HW, p = pix - n * HW;
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int m = 0; m < M; ++m) f[m] = dy[(n * M + m) * HW + p];
+      const __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+      v.x = *reinterpret_cast<const uint32_t*>(&a);
+      v.y = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    reinterpret_cast<uint4*>(out)[t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Thin conv weight gradient, shared by the tail conv (C -> few) and the head conv (few -> C):
 //   S[m][tap][c] = sum_p thin[m, p - or + off(tap)] * wide[p, c]      m < M <= 4, c < C
 //   tail: thin = dy (NCHW), wide = X bf16 NHWC, dW[m][c][ky][kx] = sum_p dy[m,p] X[p+off,c]

@@ -152,7 +152,7 @@ using namespace rb;
 
 extern "C" {
 
-long long rumpy_psnr_y_workspace(int N) { return N > 0 ? (long long)N * kPsnrMaxBlocks * sizeof(double) : -1; }
+long long rumpy_psnr_y_workspace(int N) { return N > 0 ? (long long)N * kPsnrMaxBlocks * (long long)sizeof(double) : -1LL; }
 
 int rumpy_psnr_y(const float* sr, const float* hr, float* psnr, void* workspace, int N, int H, int W, float max_value,
                  void* stream) {

@@ -603,7 +603,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   std::vector<PartialSumJob> ps_jobs;
   std::vector<int> ps_bias_param;
   PartialSumJob* ps_jobs_dev = nullptr;
-  struct Site { int conv; const void* g; const void* x; int h, w; float alpha; const float* part; int part_count; };
+  struct Site { int conv; const void* g; const void* x; int h, w; float alpha; const float* part; int part_count;
+                bool thin = false; /* tail conv: g is zero-padded to 64 channels, bias gradient handled elsewhere */ };
   std::vector<Site> sites;
   WgradJob* jobs_dev = nullptr;
   WgradReduceJob* rjobs_dev = nullptr;
@@ -617,7 +618,12 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       Op op{};
       op.type = OP_TAIL_BWD;
       op.g_hr = g_hr; op.tail_in = tail_in_b; op.thin_partial = thin_partial; op.h = Hh; op.w = Wh;
+      // weight gradient on tensor cores: dy zero-padded to a 64-channel bf16 NHWC operand of the batched wgrad kernel
+      op.dst_b = bp.take(size_t(N) * Hh * Wh * 64 * 2);
       bops.push_back(op);
+      Site ts{n->conv_tail, op.dst_b, tail_in_b, Hh, Wh, 1.f, nullptr, 0};
+      ts.thin = true;
+      sites.push_back(ts);
     }
     // ---- upsampler stages reversed
     const void* g_cur = g_hr;
@@ -819,10 +825,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     for (const Site& s : sites) {
       const ConvW& cw = n->convs[s.conv];
       const int mt = N * ((s.h + kTileH - 1) / kTileH) * ((s.w + kTileW - 1) / kTileW);
-      const int blocks = (cw.cout / 64) * (cw.cin / 64);
+      const int blocks = (s.thin ? 1 : cw.cout / 64) * (cw.cin / 64);
       njobs += size_t(blocks) * wgrad_splits(mt);
       nrjobs += blocks;
-      if (!s.part) cs_floats += size_t(kColsumSlices) * cw.r * cw.cout;
+      if (!s.part && !s.thin) cs_floats += size_t(kColsumSlices) * cw.r * cw.cout;
     }
     jobs_dev = static_cast<WgradJob*>(bp.take(njobs * sizeof(WgradJob)));
     rjobs_dev = static_cast<WgradReduceJob*>(bp.take(nrjobs * sizeof(WgradReduceJob)));
@@ -839,7 +845,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       size_t job_cursor = 0, cs_cursor = 0;
       for (const Site& s : sites) {
         const ConvW& cw = n->convs[s.conv];
-        const int rr = cw.r * cw.r, cout_sub = cw.cout / rr, chunks_per_q = cout_sub / 64;
+        const int cout_eff = s.thin ? 64 : cw.cout;
+        const int rr = cw.r * cw.r, cout_sub = cout_eff / rr, chunks_per_q = cout_sub / 64;
         const int tiles_x = (s.w + kTileW - 1) / kTileW, tiles_y = (s.h + kTileH - 1) / kTileH;
         const int mt = N * tiles_x * tiles_y;
         const int splits = wgrad_splits(mt);
@@ -848,7 +855,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           if (int e = make_map_nhwc_sub(&gmaps[q], false, s.g, cout_sub, s.w, s.h, N, cw.r, q, kABoxH)) err = e;
         CUtensorMap xmap;
         if (int e = make_map_nhwc_sub(&xmap, false, s.x, cw.cin, s.w, s.h, N, 1, 0, kTileH)) err = e;
-        for (int cb = 0; cb < cw.cout / 64; ++cb) {
+        for (int cb = 0; cb < cout_eff / 64; ++cb) {
           for (int ib = 0; ib < cw.cin / 64; ++ib) {
             float* pbase = partials + job_cursor * 9 * 64 * 64;
             for (int k = 0; k < splits; ++k) {
@@ -868,6 +875,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
             wg_rjobs.push_back(rj);
           }
         }
+        if (s.thin) continue;   // bias gradient of the tail conv: plane sums of dy (OP_TAIL_BWD)
         if (s.part) {
           PartialSumJob pj{};
           pj.partial = s.part; pj.db = nullptr; pj.count = s.part_count; pj.C = cw.cout; pj.alpha = s.alpha;
@@ -1030,7 +1038,7 @@ int rumpy_net_num_launches_backward(void* net) {
   int c = 5;                                  // batched wgrad, its reduce, colsum, colsum reduce, partial sums
   for (const Op& op : n->bops) {
     switch (op.type) {
-      case OP_TAIL_BWD: c += 5; break;        // dgrad, wgrad, reduce, plane sums (2)
+      case OP_TAIL_BWD: c += 4; break;        // dgrad, padded dy operand, plane sums (2)
       case OP_CA_BWD: c += 2; break;
       case OP_TRUNK_BWD: c += n->qrcan ? 3 : 2; break;   // dataflow kernel + CA parameter-gradient finalize [+ q-layer grads]
       case OP_HEAD_WGRAD: c += 2; break;
@@ -1213,20 +1221,14 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
   for (Op& op : n->bops) {
     switch (op.type) {
       case OP_TAIL_BWD: {
-        const int Hh = op.h, Wh = op.w, M = n->out_feats, rows = M * 9 + 1;
+        const int Hh = op.h, Wh = op.w, M = n->out_feats;
         const size_t items = size_t(N) * Hh * ((Wh + 3) / 4) * (C / 8);
         tail_dgrad_kernel<<<grid_for(items, 256, 8), 256, size_t(M) * 9 * C * sizeof(float), stream>>>(
             dy_nchw, params[tail.w_idx], static_cast<__nv_bfloat16*>(op.g_hr), N, Hh, Wh, C, M);
         if (int e = check_launch("tail_dgrad")) return e;
-        if (M <= 3)
-          thin_wgrad_kernel<true, 3><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
-              dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
-        else
-          thin_wgrad_kernel<true, 4><<<kThinBlocks, thin_block, size_t(thin_lanes) * rows * C * sizeof(float), stream>>>(
-              dy_nchw, op.tail_in, nullptr, op.thin_partial, N, Hh, Wh, C, M, -1);
-        if (int e = check_launch("tail_wgrad")) return e;
-        thin_wgrad_reduce_kernel<<<((M * 9 + 1) * C + 31) / 32, 256, 0, stream>>>(op.thin_partial, kThinBlocks, grads[tail.w_idx], nullptr, C, M, 0);
-        if (int e = check_launch("tail_wgrad_reduce")) return e;
+        pad_thin_grad_kernel<<<grid_for(size_t(N) * Hh * Wh * 8, 256, 8), 256, 0, stream>>>(
+            dy_nchw, static_cast<__nv_bfloat16*>(op.dst_b), N, M, Hh * Wh);
+        if (int e = check_launch("tail_grad_pad")) return e;
         plane_sum_kernel<<<dim3(kPlaneSlices, M), 512, 0, stream>>>(dy_nchw, op.thin_partial, N, M, Hh * Wh);
         if (int e = check_launch("tail_bias_grad")) return e;
         plane_sum_finalize_kernel<<<1, 32, 0, stream>>>(op.thin_partial, kPlaneSlices, grads[tail.b_idx], M);

@@ -176,6 +176,7 @@ __global__ void wgrad_reduce_kernel(const WgradReduceJob* __restrict__ jobs) {
     const int ci = idx & 63, co = (idx >> 6) & 63, t = idx >> 12;
     const int kx = t / 3, ky = 2 - (t % 3);
     const int row = jb.co0 + co;
+    if (row >= jb.cout) continue;   // thin tail conv: the operand is zero-padded to 64 output channels
     const int o = (jb.r > 1) ? (row % cpp) * rr + row / cpp : row;
     float* d = jb.dw + ((size_t(o) * jb.cin + jb.ci0 + ci) * 3 + ky) * 3 + kx;
     const float v = s * jb.alpha;
