@@ -255,8 +255,9 @@ struct Bump {
   void* take(size_t bytes) { void* p = base ? base + off : nullptr; off = align_up(off + bytes, 1024); return p; }
 };
 
+int g_wgrad_tiles_per_split = 64;   // pixel tiles per split-K job of the batched wgrad kernel (measured: 32 -> 14.97, 64 -> 14.76, 128 -> 14.73, 256 -> 15.12 ms per RCAN train step)
 static int wgrad_splits(int m_tiles) {
-  int s = (m_tiles + 31) / 32;
+  int s = (m_tiles + g_wgrad_tiles_per_split - 1) / g_wgrad_tiles_per_split;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
   return s;
@@ -1013,6 +1014,8 @@ int rumpy_net_set_metadata(void* net, const float* metadata, int N, int M) {
   n->meta_m = M;
   return RUMPY_OK;
 }
+
+int rumpy_debug_set_wgrad_split(int tiles) { rb::g_wgrad_tiles_per_split = tiles < 1 ? 1 : tiles; return 0; }
 
 int rumpy_net_destroy(void* net) {
   delete static_cast<Net*>(net);
