@@ -171,6 +171,8 @@ def infer_arch(sd):
 
 
 def forward(sd, x, arch, **kw):
+    if arch == 'qedsr':
+        return qedsr_forward(sd, x, kw['attributes'], kw['num_blocks'], kw.get('res_scale', 0.1), kw.get('scale', 4))
     if arch == 'qrcan':
         return qrcan_forward(sd, x, kw['attributes'], kw['n_resgroups'], kw['n_resblocks'], kw.get('scale', 4),
                              kw.get('style', 'standard'))

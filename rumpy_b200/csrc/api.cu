@@ -158,6 +158,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.cout = thin ? 16 : d.Cout;
   a.alpha = d.alpha;
   a.ch_scale = d.ch_scale;
+  a.bf16_scale = d.bf16_scale;
   a.bias = d.bias;
   a.pool_partial = d.pool_partial;
   a.out_nchw = d.out_nchw;

@@ -53,6 +53,8 @@ struct ConvArgs {
   int stg_bufs;          // epilogue staging slots (1 or 2)
   float alpha;           // scale on (acc + bias) (res_scale / gradient scale)
   const float* ch_scale; // [N][cout] extra per-(image, channel) scale on the same term (meta-attention), or nullptr
+  const float* bf16_scale;  // [N][cout] scale applied to the bf16 output ONLY (fp32 output unscaled): Q-EDSR backward,
+                            // the next dgrad / wgrad operand is g * q while the fp32 skip gradient stays g; or nullptr
   const float* bias;     // [cout] in packed-row order, or nullptr
   float* pool_partial;   // [m_tiles][2][cout]
   float* out_nchw;       // BN == 16 variant only: fp32 NCHW [N][cout_real][H][W]
@@ -399,6 +401,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
               for (int c = 0; c < 8; ++c)
                 *reinterpret_cast<float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4)) =
                     make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
+            }
+            if ((flags & kConvOutBf16) && args.bf16_scale != nullptr) {
+              const float* bs = args.bf16_scale + size_t(n) * args.cout + oc * 64 + h * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] *= __ldg(bs + i);
             }
             if (flags & kConvOutBf16) {
 #pragma unroll

@@ -45,6 +45,7 @@ struct ConvDesc {
   unsigned flags;
   float alpha;
   const float* ch_scale;  // [N][Cout] per-(image, channel) multiplier of alpha * (acc + bias) (Q-EDSR), or null
+  const float* bf16_scale;  // [N][Cout] multiplier of the bf16 output only (Q-EDSR backward), or null
 };
 
 // Everything a launch needs: tensor maps (host copy, passed by value as __grid_constant__) + args.
@@ -86,8 +87,13 @@ int csam_cat_launch(const float* x, const float* out2, const float* w, const flo
 
 // one q-layer's parameter-gradient job (trunk_bwd.cuh: QGradJob has the same layout)
 struct QGradJobHost { const float *w1, *b1, *w2, *b2, *q, *dq; float *dw1, *db1, *dw2, *db2; };
+// dq_slices > 0: dq holds [N][dq_slices][C] partial sums of dq * q (Q-EDSR); 0: dq holds [N][C] (Q-RCAN)
 int q_grad_launch(const QGradJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C, int relu,
-                  cudaStream_t s);
+                  int dq_slices, cudaStream_t s);
+// Q-EDSR: partial[n][slice][c] = sum over a pixel slice of g[n,p,c] * (out[n,p,c] - x[n,p,c])  (= dq * q)
+constexpr int kDqSlices = 32;
+int dq_reduce_launch(const float* g_f32, const void* out_bf16, const void* x_bf16, float* partial, int N, int HW, int C,
+                     cudaStream_t s);
 
 // one conv's packing job for the batched pack kernel (misc_kernels.cuh: PackJob has the same layout)
 struct PackJobHost {

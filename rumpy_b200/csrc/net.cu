@@ -33,7 +33,7 @@ struct ConvW {            // one 3x3 conv of the network
 struct CAW { int w1, b1, w2, b2; };
 using QScaleJob = QScaleJobHost;   // q_scale_kernel job (w1 == nullptr: no q-layer)
 
-enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD, OP_LAM, OP_CSAM };
+enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD, OP_LAM, OP_CSAM, OP_DQ, OP_QGRAD };
 
 extern int g_use_fused_ca;
 extern int g_use_cluster;
@@ -317,8 +317,6 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   // ---- Q-RCAN: per-(RCAB, image, channel) meta-attention multipliers, evaluated once per forward
   float* q_scale = nullptr;
   if (n->qrcan) {
-    if (training && n->arch != 0)
-      return set_error(RUMPY_ERR_ARG, "Q-EDSR: training is not implemented (inference only)");
     if (training && n->modulate)
       return set_error(RUMPY_ERR_ARG, "Q-RCAN style 'modulate': training is not implemented (inference only)");
     q_scale = static_cast<float*>(bp.take(n->qs.size() * size_t(N) * C * sizeof(float)));
@@ -650,6 +648,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     {
       ConvDesc d{};
       d.x = GB_body; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.y_f32 = P; d.y_bf16 = GB_cur;
+      // Q-EDSR: the bf16 gradient operand of block b's conv2 dgrad / wgrad is g * q_b; the fp32 skip stream P stays g
+      if (n->qrcan && n->arch == 1) d.bf16_scale = q_of(n->n_blocks - 1);
       conv_op(bops, n->convs[n->conv_body], d, true);
       sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f, nullptr, 0});
     }
@@ -796,8 +796,20 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       }
     } else {
       const GroupRec& gr = groups[0];
+      const bool qed = n->qrcan;
+      float* dq_all = qed ? static_cast<float*>(bp.take(size_t(n->n_blocks) * N * kDqSlices * C * 4)) : nullptr;
+      QGradJobHost* qgj = qed ? static_cast<QGradJobHost*>(bp.take(size_t(n->n_blocks) * sizeof(QGradJobHost))) : nullptr;
+      if (build && qed) { n->q_dq = dq_all; n->qg_jobs_dev = qgj; n->qg_jobs_uploaded.clear(); }
       for (int b = n->n_blocks - 1; b >= 0; --b) {
         const BlockRec& br = gr.blocks[b];
+        if (qed && n->qs[b].w1 >= 0) {
+          // q * dq[n][c] = sum_hw g * (out - x), taken while P still holds the gradient w.r.t. this block's output
+          Op dq{};
+          dq.type = OP_DQ;
+          dq.a = P; dq.u = b + 1 < n->n_blocks ? gr.blocks[b + 1].in_b : body_in_b; dq.tail_in = br.in_b;
+          dq.dst_f = dq_all + size_t(b) * N * kDqSlices * C;
+          bops.push_back(dq);
+        }
         void* dt = bp.take(px * C * 2);
         void* GB_new = bp.take(px * C * 2);
         ConvDesc d2{};
@@ -809,11 +821,13 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         ConvDesc d1{};
         d1.x = dt; d1.residual = P; d1.y_f32 = P; d1.y_bf16 = GB_new; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C;
         d1.Cout = C; d1.alpha = 1.f;
+        if (qed && b > 0) d1.bf16_scale = q_of(b - 1);
         conv_op(bops, n->convs[br.conv1], d1, true);
         sites.push_back({br.conv2, GB_cur, br.t, H, W, n->res_scale, nullptr, 0});
         sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * tiles * 2});
         GB_cur = GB_new;
       }
+      if (qed) { Op qg{}; qg.type = OP_QGRAD; bops.push_back(qg); }
     }
     {  // head conv: weight / bias gradient only (no dX), upstream = trunk gradient + global skip
       Op op{};
@@ -1241,6 +1255,31 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
       case OP_CONV:
         if (int e = launch_conv_op(op, params, nullptr, stream)) return e;
         break;
+      case OP_DQ:
+        if (int e = dq_reduce_launch(op.a, op.u, op.tail_in, op.dst_f, N, H * W, C, stream)) return e;
+        break;
+      case OP_QGRAD: {   // Q-EDSR q-layer parameter gradients from the q * dq partial sums of the OP_DQ passes
+        std::vector<QGradJobHost> jobs;
+        for (size_t i = 0; i < n->qs.size(); ++i) {
+          const CAW& q = n->qs[i];
+          if (q.w1 < 0) continue;
+          jobs.push_back(QGradJobHost{params[q.w1], params[q.b1], params[q.w2], params[q.b2],
+                                      n->q_scale + i * size_t(N) * C, n->q_dq + i * size_t(N) * kDqSlices * C,
+                                      grads[q.w1], grads[q.b1], grads[q.w2], grads[q.b2]});
+        }
+        if (!jobs.empty() && (jobs.size() != n->qg_jobs_uploaded.size() ||
+                              memcmp(jobs.data(), n->qg_jobs_uploaded.data(), jobs.size() * sizeof(QGradJobHost)) != 0)) {
+          n->qg_jobs_uploaded = jobs;
+          if (cudaMemcpyAsync(n->qg_jobs_dev, n->qg_jobs_uploaded.data(), jobs.size() * sizeof(QGradJobHost),
+                              cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            return set_error(RUMPY_ERR_CUDA, "Q-EDSR: gradient job upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+          cudaStreamSynchronize(stream);
+        }
+        if (int e = q_grad_launch(n->qg_jobs_dev, int(jobs.size()), n->meta_dev, N, n->meta_m, n->q_hidden, C, n->q_relu,
+                                  kDqSlices, stream))
+          return e;
+        break;
+      }
       case OP_TRUNK_BWD:
         if (int e = trunk_bwd_launch(n->trunk_bwd.get(), params, grads, stream)) return e;
         if (n->qrcan) {   // q-layer parameter gradients from the dq = s*y terms the kernel left behind
@@ -1261,7 +1300,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
             cudaStreamSynchronize(stream);
           }
           if (int e = q_grad_launch(n->qg_jobs_dev, int(jobs.size()), n->meta_dev, N, n->meta_m, n->q_hidden, C, n->q_relu,
-                                    stream))
+                                    0, stream))
             return e;
         }
         break;

@@ -299,14 +299,24 @@ int trunk_bwd_launch(TrunkBwdPlan* plan, const float* const* params, float* cons
 
 static_assert(sizeof(QGradJobHost) == sizeof(QGradJob), "QGradJobHost layout mismatch");
 int q_grad_launch(const QGradJobHost* jobs_dev, int njobs, const float* meta, int N, int M, int hidden, int C, int relu,
-                  cudaStream_t s) {
+                  int dq_slices, cudaStream_t s) {
   if (njobs <= 0) return RUMPY_OK;
   const size_t smem = size_t(N) * (M + 2 * hidden + C) * sizeof(float);
   if (smem > 48 * 1024)
     return set_error(RUMPY_ERR_ARG, "q_grad: batch %d x (metadata %d + hidden %d) does not fit 48 KB of shared memory", N, M,
                      hidden);
-  q_grad_kernel<<<njobs, 256, smem, s>>>(reinterpret_cast<const QGradJob*>(jobs_dev), meta, N, M, hidden, C, relu);
+  q_grad_kernel<<<njobs, 256, smem, s>>>(reinterpret_cast<const QGradJob*>(jobs_dev), meta, N, M, hidden, C, relu,
+                                         dq_slices);
   return check_launch("q_grad");
+}
+
+int dq_reduce_launch(const float* g_f32, const void* out_bf16, const void* x_bf16, float* partial, int N, int HW, int C,
+                     cudaStream_t s) {
+  if (C < 1 || C > 256) return set_error(RUMPY_ERR_ARG, "dq_reduce: C=%d", C);
+  const int threads = (256 / C) * C;
+  dq_reduce_kernel<<<dim3(kDqSlices, N), threads, threads * sizeof(float), s>>>(
+      g_f32, static_cast<const __nv_bfloat16*>(out_bf16), static_cast<const __nv_bfloat16*>(x_bf16), partial, HW, C);
+  return check_launch("dq_reduce");
 }
 
 }  // namespace rb

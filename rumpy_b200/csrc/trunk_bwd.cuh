@@ -470,8 +470,10 @@ __global__ void ca_pg_finalize_kernel(const CaPgJob* __restrict__ jobs, int N, i
 // a = W2 act(W1 meta + b1) + b2.  dq[n][c] = sum_hw g*u*y comes from trunk_bwd_kernel.  One CTA per block; the sums
 // over the images run in a fixed order (deterministic).
 struct QGradJob { const float *w1, *b1, *w2, *b2, *q, *dq; float *dw1, *db1, *dw2, *db2; };
+// dq_slices == 0: jb.dq = dq [N][C] (Q-RCAN).  dq_slices > 0: jb.dq = [N][dq_slices][C] partial sums of dq * q
+// (Q-EDSR: sum_hw g * (out - x) = q * dq), so da = dq * q * (1 - q) = (sum of the slices) * (1 - q).
 __global__ void q_grad_kernel(const QGradJob* __restrict__ jobs, const float* __restrict__ meta, int N, int M,
-                              int hidden, int C, int relu) {
+                              int hidden, int C, int relu, int dq_slices) {
   extern __shared__ float qg_smem[];
   float* meta_s = qg_smem;                 // [N][M]
   float* hid_s = meta_s + N * M;           // [N][hidden]  act(W1 meta + b1)
@@ -480,7 +482,17 @@ __global__ void q_grad_kernel(const QGradJob* __restrict__ jobs, const float* __
   const QGradJob jb = jobs[blockIdx.x];
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < N * M; i += nt) meta_s[i] = meta[i];
-  for (int i = tid; i < N * C; i += nt) { const float q = jb.q[i]; da_s[i] = jb.dq[i] * q * (1.f - q); }
+  for (int i = tid; i < N * C; i += nt) {
+    const float q = jb.q[i];
+    if (dq_slices == 0) {
+      da_s[i] = jb.dq[i] * q * (1.f - q);
+    } else {
+      const int n = i / C, c = i - n * C;
+      float s = 0.f;
+      for (int k = 0; k < dq_slices; ++k) s += jb.dq[(size_t(n) * dq_slices + k) * C + c];
+      da_s[i] = s * (1.f - q);
+    }
+  }
   __syncthreads();
   for (int i = tid; i < N * hidden; i += nt) {
     const int n = i / hidden, t = i - n * hidden;
@@ -517,6 +529,27 @@ __global__ void q_grad_kernel(const QGradJob* __restrict__ jobs, const float* __
     float s = 0.f;
     for (int n = 0; n < N; ++n) s += dh_s[n * hidden + t];
     jb.db1[t] = s;
+  }
+}
+
+// Q-EDSR: partial[n][slice][c] = sum over the slice's pixels of g[n,p,c] * (out[n,p,c] - x[n,p,c]); out - x = the
+// block's scaled branch r * q, so the sum over slices is q * dq.  grid (slices, N), block 256 = (256 / C) pixel lanes x C.
+__global__ void dq_reduce_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ out,
+                                 const __nv_bfloat16* __restrict__ x, float* __restrict__ partial, int HW, int C) {
+  extern __shared__ float dq_red[];   // [lanes][C]
+  const int n = blockIdx.y, lanes = blockDim.x / C;
+  const int c = threadIdx.x % C, lane = threadIdx.x / C;
+  const int begin = int((long long)HW * blockIdx.x / gridDim.x), end = int((long long)HW * (blockIdx.x + 1) / gridDim.x);
+  float s = 0.f;
+  for (int p = begin + lane; p < end; p += lanes) {
+    const size_t i = (size_t(n) * HW + p) * C + c;
+    s = fmaf(g[i], __bfloat162float(out[i]) - __bfloat162float(x[i]), s);
+  }
+  dq_red[lane * C + c] = s;
+  __syncthreads();
+  if (lane == 0) {
+    for (int l = 1; l < lanes; ++l) s += dq_red[l * C + c];
+    partial[(size_t(n) * gridDim.x + blockIdx.x) * C + c] = s;
   }
 }
 

@@ -250,6 +250,29 @@ def qrcan_cases():
         rec[name + '::attributes'] = attrs.numpy()
         rec[name + '::out'] = out.numpy()
         print(name, 'out', out.shape, float(out.abs().max()))
+        # training: L1 gradients of every parameter (q-layers included) and 3 Adam steps
+        y = recipe.make_input((x.shape[0], 3, x.shape[2] * kw['scale'], x.shape[3] * kw['scale']),
+                              recipe.QECASES[name][3] + 1000)
+        net.train()
+        o = net(t(x), attrs)
+        loss = torch.nn.L1Loss()(o, t(y))
+        loss.backward()
+        rec[name + '::loss'] = np.float32(loss.item())
+        for k, p in net.named_parameters():
+            rec[name + '::gradsub::' + k] = recipe.subsample(p.grad.numpy()).copy()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        losses = []
+        for _ in range(3):
+            o = net(t(x), attrs)
+            l = torch.nn.L1Loss()(o, t(y))
+            opt.zero_grad()
+            l.backward()
+            opt.step()
+            losses.append(l.item())
+        rec[name + '::train_losses'] = np.array(losses, dtype=np.float32)
+        net.eval()
+        with torch.no_grad():
+            rec[name + '::out_after3'] = net(t(x), attrs).numpy()
     return rec
 
 
