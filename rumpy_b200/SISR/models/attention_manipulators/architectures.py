@@ -8,8 +8,8 @@ for the configurations the native trunk implements:
     reference's 2-layer ParaCALayer (q_layer.py:5-45).
 Everything else the reference's QRCAN can be configured with (pixel attention, SFT / DGFMB / DA-conv layers, the
 concat styles, staggered encodings, outer metadata reduction) is outside SURVEY.md section 8 and raises
-NotImplementedError at construction.  Q-RCAN style 'standard' trains natively (the q-layer parameters get their
-gradients from the backward dataflow kernel's per-channel sums); Q-EDSR and style 'modulate' are inference only.
+NotImplementedError at construction.  Q-RCAN style 'standard' and Q-EDSR train natively (the q-layer parameters get
+their gradients from per-channel sums the backward kernels leave behind); style 'modulate' is inference only.
 
 `QEDSR` (ParamResBlocks: res_scale * conv2(relu(conv1 x)) * q + x) keeps the reference's ctor and key layout too
 (`head.weight` without a Sequential index, `final_body` registered before `body`).
