@@ -87,7 +87,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 break
-            time.sleep(0.02)
+            time.sleep(0.1)    # 10 Hz: NVML queries contend with the CUDA driver lock, 50 Hz slowed the host-side e2e loop
 
     def result(self):
         self.stop_flag = True
