@@ -57,6 +57,21 @@ class PairSet:
                 lr, hr = lr.transpose(1, 0, 2), hr.transpose(1, 0, 2)
         return name, to_tensor(np.ascontiguousarray(lr)), to_tensor(np.ascontiguousarray(hr))
 
+    def geometry(self, idx):
+        """The random draws of `sample` (same order, same count), without touching pixels:
+        [image index, y, x, flags (1 hflip | 2 vflip | 4 transpose, applied in that order), lr_h, lr_w] -- the row
+        `rumpy_patch_batch` consumes."""
+        _, lr, _ = self.items[idx]
+        c = self.crop
+        y = self.rng.randint(0, lr.shape[0] - c)
+        x = self.rng.randint(0, lr.shape[1] - c)
+        flags = 0
+        if self.augment:
+            flags |= 1 if self.rng.random() < 0.5 else 0
+            flags |= 2 if self.rng.random() < 0.5 else 0
+            flags |= 4 if self.rng.random() < 0.5 else 0
+        return [idx, y, x, flags, lr.shape[0], lr.shape[1]]
+
     def batches(self, batch_size, shuffle=True, rank=0, world=1):
         order = list(range(len(self.items)))
         if shuffle:
@@ -127,19 +142,6 @@ class DevicePairSet(PairSet):
         self._hr = [torch.from_numpy(np.array(hr, copy=True)).to(self.device) for _, _, hr in self.items]
         self._lr_tab = torch.tensor([t.data_ptr() for t in self._lr], dtype=torch.int64, device=self.device)
         self._hr_tab = torch.tensor([t.data_ptr() for t in self._hr], dtype=torch.int64, device=self.device)
-
-    def geometry(self, idx):
-        """The random draws of PairSet.sample, without touching pixels."""
-        _, lr, _ = self.items[idx]
-        c = self.crop
-        y = self.rng.randint(0, lr.shape[0] - c)
-        x = self.rng.randint(0, lr.shape[1] - c)
-        flags = 0
-        if self.augment:
-            flags |= 1 if self.rng.random() < 0.5 else 0
-            flags |= 2 if self.rng.random() < 0.5 else 0
-            flags |= 4 if self.rng.random() < 0.5 else 0
-        return [idx, y, x, flags, lr.shape[0], lr.shape[1]]
 
     def batches(self, batch_size, shuffle=True, rank=0, world=1):
         from rumpy_b200 import _lib

@@ -108,6 +108,32 @@ def test_registry_and_legacy_switch():
         define_model('rcan', device='cpu', model_save_dir='/tmp', eval_mode=True)
 
 
+def test_patch_geometry_reproduces_host_pipeline():
+    """`PairSet.geometry` (the 24-byte row the device patch kernel consumes) draws the same random numbers as
+    `PairSet.sample`; applying its crop offsets and flag bits (hflip, vflip, transpose in that order) with numpy
+    reproduces `sample` bit for bit -- the host-side half of the DevicePairSet contract."""
+    from rumpy_b200.shared_framework.data import PairSet, to_tensor
+    cfg = {'synthetic': 9, 'crop': 12, 'random_augment': True}
+    a, b = PairSet(cfg, 3, seed=5), PairSet(cfg, 3, seed=5)
+    seen = set()
+    for rep in range(4):
+        for i in range(len(a)):
+            _, lr, hr = a.sample(i)
+            idx, y, x, flags, lh, lw = b.geometry(i)
+            seen.add(flags)
+            _, L, H = b.items[idx]
+            assert (lh, lw) == L.shape[:2]
+            pl, ph = L[y:y + 12, x:x + 12], H[y * 3:(y + 12) * 3, x * 3:(x + 12) * 3]
+            if flags & 1:
+                pl, ph = pl[:, ::-1], ph[:, ::-1]
+            if flags & 2:
+                pl, ph = pl[::-1], ph[::-1]
+            if flags & 4:
+                pl, ph = pl.transpose(1, 0, 2), ph.transpose(1, 0, 2)
+            assert torch.equal(lr, to_tensor(np.ascontiguousarray(pl))) and torch.equal(hr, to_tensor(np.ascontiguousarray(ph)))
+    assert len(seen) >= 6            # the flag combinations actually occur
+
+
 def test_shard_round_robin():
     from rumpy_b200.parallel import shard_round_robin
     items = list(range(10))
