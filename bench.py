@@ -574,10 +574,15 @@ def run_b200(args, rank, world):
             handler.run_eval(x_host)
         barrier()
         t0 = time.perf_counter()
+        call_ms = []
         for _ in range(args.steps):
+            tc = time.perf_counter()
             out_cpu, _, _ = handler.run_eval(x_host)
+            call_ms.append((time.perf_counter() - tc) * 1e3)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        print('e2e per-call ms: min %.3f median %.3f max %.3f' % (min(call_ms), float(np.median(call_ms)), max(call_ms)),
+              file=sys.stderr)
     launches = eng.lib.rumpy_net_num_launches(eng.handle)
     # ---- training (configs[2]) in the same run, same clocks record
     def handler_factory():

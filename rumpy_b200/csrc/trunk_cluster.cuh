@@ -328,7 +328,6 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
                   make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
           }
         }
-        tmem_st_wait();
         tc_fence_before();
         emit(qy, qx, valid, pix, f);
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
@@ -429,7 +428,6 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
         tmem_st32(lane_addr + uint32_t(j * 64), s);
-        tmem_st_wait();
         tc_fence_before();
         emit(qy, qx, valid, pix, f);
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
@@ -443,6 +441,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         for (int j = 0; j < n_tiles; ++j) ca_apply(j);
         ++ca_seen;
       }
+      tmem_st_wait();   // the residual-stream updates of this layer (one wait per layer, not per tile)
       if (!last) group_done(par_out); else named_bar_sync(bar_id, 128);
     }
   }

@@ -39,3 +39,15 @@ with torch.no_grad():
     buf = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
     print('d2h into a reused buffer  %.3f ms' % T(lambda: (buf.copy_(out, non_blocking=True), torch.cuda.current_stream().synchronize())))
     print('net.training check        %.3f ms' % T(lambda: h.net.training))
+
+# effect of bench.py's NVML clock sampler thread on the host-side loop
+sys.path.insert(0, ROOT)
+import bench
+for hz_sleep in (0.1, 0.02):
+    s = bench.ClockSampler(0)
+    s.run_sleep = hz_sleep
+    s.start()
+    with torch.no_grad():
+        print('run_eval(pinned x) with the NVML sampler thread (bench.py, sleep 0.1 s)   %.3f ms' % T(lambda: h.run_eval(xp)))
+    s.result()
+    break
