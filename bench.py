@@ -570,7 +570,7 @@ def run_b200(args, rank, world):
     total_ms = float(sum(step_ms))
     # ---- end-to-end through the reference-facing handler call, HOST buffers in and out
     with torch.no_grad():
-        for _ in range(3):
+        for _ in range(max(args.warmup, 3)):
             handler.run_eval(x_host)
         barrier()
         t0 = time.perf_counter()
@@ -581,8 +581,8 @@ def run_b200(args, rank, world):
             call_ms.append((time.perf_counter() - tc) * 1e3)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        print('e2e per-call ms: min %.3f median %.3f max %.3f' % (min(call_ms), float(np.median(call_ms)), max(call_ms)),
-              file=sys.stderr)
+        print('e2e per-call ms: min %.3f median %.3f max %.3f (call %d of %d)' %
+              (min(call_ms), float(np.median(call_ms)), max(call_ms), int(np.argmax(call_ms)), len(call_ms)), file=sys.stderr)
     launches = eng.lib.rumpy_net_num_launches(eng.handle)
     # ---- training (configs[2]) in the same run, same clocks record
     def handler_factory():

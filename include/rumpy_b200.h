@@ -139,6 +139,16 @@ int rumpy_net_num_launches_backward(void* net); /* kernels per backward of the c
  * The mode is picked per (N,H,W) when the plan is built; all three compute the same layer program. */
 int rumpy_net_trunk_mode(void* net);
 
+/* Chunked weight gradients for data-parallel training: rumpy_net_backward computes the conv weight gradients last,
+ * in chunks ordered from the LAST parameters to the first.  After chunk k every gradient with parameter index
+ * >= first_param[k] is final (first_param is decreasing and ends with 0); if events were registered, event k is
+ * recorded on the backward's stream at that point, so the caller can all-reduce that range of its flat gradient
+ * buffer on another stream while the remaining chunks run (replaces nn.DataParallel's gather,
+ * base_architecture.py:70-77, with an overlapped NCCL all-reduce).  rumpy_net_backward_chunks is valid once the
+ * training plan exists (after rumpy_net_forward(training=1) for the current shape) and returns the chunk count. */
+int rumpy_net_backward_chunks(void* net, int* first_param, int max_chunks);
+int rumpy_net_set_backward_events(void* net, void* const* events /* cudaEvent_t[n_events], n_events <= 8 */, int n_events);
+
 /* Meta-attention networks: the same trunks modulated by per-image metadata.
  *   arch 0  Q-RCAN: replaces QRCAN.__init__/forward (reference SISR/models/attention_manipulators/architectures.py
  *           :313-462) for QCALayer style 'standard' or 'modulate' (:113-116, :127-128) with optional q-nodes:

@@ -37,6 +37,8 @@ SIGNATURES = {
     'rumpy_psnr_y': [_fp, _fp, _fp, _vp, _i, _i, _i, _f, _vp],
     'rumpy_quantize_u8': [_fp, _vp, _i, _i, _i, _i, _vp],
     'rumpy_patch_batch': [_vp, _vp, _vp, _fp, _fp, _i, _i, _i, _vp],
+    'rumpy_net_backward_chunks': [_vp, _vp, _i],
+    'rumpy_net_set_backward_events': [_vp, _vp, _i],
     'rumpy_net_destroy': [_vp],
     'rumpy_net_num_params': [_vp],
     'rumpy_net_num_launches': [_vp],

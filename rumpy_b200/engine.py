@@ -216,6 +216,32 @@ class TrunkEngine:
                   self._grad_ptr_array, ws.data_ptr(), N, H, W, torch.cuda.current_stream().cuda_stream)
         return grads
 
+    # ------------------------------------------------------------------ chunked backward (data parallel)
+    def backward_chunks(self):
+        """[(event, lo, hi)]: after `event` (recorded by the native backward on its stream) the flat gradient range
+        [lo, hi) is final.  Ranges run from the end of the buffer to its start and cover it exactly once."""
+        first = (ctypes.c_int * 8)()
+        k = self.lib.rumpy_net_backward_chunks(self.handle, first, 8)
+        if k <= 0:
+            raise _lib.RumpyB200Error('backward_chunks: no training plan yet (run forward(training=True) first)')
+        key = tuple(first[i] for i in range(k))
+        if getattr(self, '_chunk_key', None) != key:
+            offs = [0]
+            for p in self.params:
+                offs.append(offs[-1] + p.numel())
+            events = [torch.cuda.Event() for _ in range(k)]
+            for e in events:
+                e.record()                       # materialises the cudaEvent_t handle
+            arr = (ctypes.c_void_p * k)(*[e.cuda_event for e in events])
+            _lib.call('rumpy_net_set_backward_events', self.handle, arr, k)
+            hi, chunks = offs[-1], []
+            for i in range(k):
+                lo = offs[first[i]]
+                chunks.append((events[i], lo, hi))
+                hi = lo
+            self._chunk_key, self._chunks, self._chunk_events_arr = key, chunks, arr
+        return self._chunks
+
     def forward_inference(self, x):
         """Module-level inference entry: the first call with a shape launches eagerly; repeated calls with the same
         shape replay a captured CUDA graph (launch overhead of ~600 kernels -> one graph launch)."""

@@ -47,6 +47,31 @@ class GradAllReduce:
         return flat
 
 
+    def chunked(self, flat, chunks):
+        """All-reduce `flat` range by range as the backward finishes them: chunks = [(event | None, lo, hi)] from
+        TrunkEngine.backward_chunks(); the side stream waits for each event and reduces [lo, hi) while the compute
+        stream is still producing the earlier ranges.  Call right after the backward was enqueued."""
+        if self.world_size == 1:
+            return flat
+        covered = sorted((lo, hi) for _, lo, hi in chunks)
+        if covered[0][0] != 0 or covered[-1][1] != flat.numel() or any(a[1] != b[0] for a, b in zip(covered, covered[1:])):
+            raise ValueError('gradient chunks do not tile the flat buffer')
+        if not flat.is_cuda:     # gloo (CPU tests of the host logic)
+            for _, lo, hi in chunks:
+                for off in range(lo, hi, self.bucket_elems):
+                    dist.all_reduce(flat[off:min(hi, off + self.bucket_elems)], op=dist.ReduceOp.SUM)
+            return flat
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=flat.device)
+        with torch.cuda.stream(self._stream):
+            for event, lo, hi in chunks:
+                self._stream.wait_event(event)
+                for off in range(lo, hi, self.bucket_elems):
+                    dist.all_reduce(flat[off:min(hi, off + self.bucket_elems)], op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().wait_stream(self._stream)
+        return flat
+
+
 def shard_round_robin(items, rank=None, world=None):
     """Inference sharding: whole images / frames round-robin over ranks, no collective."""
     if rank is None:

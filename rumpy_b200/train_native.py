@@ -45,10 +45,16 @@ def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None, metadata=No
         optimizer.attach_engine(eng)       # engine writes gradients straight into the optimiser's flat buffer
     out = eng.forward(x, training=True)
     loss, dy = l1_loss(out, y, want_grad=True)
+    chunks = eng.backward_chunks() if (allreduce is not None and allreduce.world_size > 1) else None
     eng.backward(x, dy)
     flat_g = eng.flat_grads
     if allreduce is not None:
-        allreduce(flat_g)                      # NCCL sum over ranks; 1/world folded into the Adam grad scale
+        # NCCL sum over ranks, range by range while the remaining weight-gradient chunks are still running;
+        # 1/world folded into the Adam grad scale
+        if chunks is not None:
+            allreduce.chunked(flat_g, chunks)
+        else:
+            allreduce(flat_g)
         optimizer.grad_scale = 1.0 / allreduce.world_size
     if grad_clip is not None:
         coef = _buf(('clip', flat_g.device), (2,), flat_g.device)

@@ -152,6 +152,14 @@ ar = GradAllReduce(bucket_bytes=4096)
 ar(flat)
 assert ar.world_size == 2
 assert torch.equal(flat, torch.arange(10000, dtype=torch.float32) * 3), 'bucketed all-reduce mismatch'
+flat = torch.arange(10000, dtype=torch.float32) * (rank + 1)
+ar.chunked(flat, [(None, 7000, 10000), (None, 2500, 7000), (None, 0, 2500)])     # ranges as the chunked backward hands them over
+assert torch.equal(flat, torch.arange(10000, dtype=torch.float32) * 3), 'chunked all-reduce mismatch'
+try:
+    ar.chunked(flat, [(None, 7000, 10000), (None, 0, 2500)])
+    raise SystemExit('a gap in the gradient ranges must be rejected')
+except ValueError:
+    pass
 lin = torch.nn.Linear(4, 4)
 broadcast_parameters(lin)
 w = lin.weight.detach().clone(); dist.all_reduce(w); assert torch.allclose(w, lin.weight.detach() * 2)
