@@ -272,8 +272,8 @@ def train_bench(handler_factory, device, rank, world, steps, warmup, barrier):
     barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
     # end to end through the reference-facing call: host batch in, loss (numpy) + SR batch on host out
-    for _ in range(2):
-        handler.run_train(x=xh, y=yh)
+    for _ in range(3):     # keep the result like the timed loop does: both pinned output buffers exist before timing
+        loss_np, out_cpu = handler.run_train(x=xh, y=yh)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -571,7 +571,9 @@ def run_b200(args, rank, world):
     # ---- end-to-end through the reference-facing handler call, HOST buffers in and out
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
-            handler.run_eval(x_host)
+            # keep the result like the timed loop does: the pinned-memory allocator then owns both output buffers
+            # before timing starts (a cudaHostAlloc of 7 MB inside the loop cost 5 ms once)
+            out_cpu, _, _ = handler.run_eval(x_host)
         barrier()
         t0 = time.perf_counter()
         call_ms = []
