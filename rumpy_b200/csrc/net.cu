@@ -1055,6 +1055,7 @@ int rumpy_net_set_metadata(void* net, const float* metadata, int N, int M) {
   return RUMPY_OK;
 }
 
+int rumpy_debug_set_wgrad_chunks(int chunks) { rb::g_wgrad_chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks); return 0; }
 int rumpy_debug_set_wgrad_split(int tiles) { rb::g_wgrad_tiles_per_split = tiles < 1 ? 1 : tiles; return 0; }
 
 int rumpy_net_destroy(void* net) {
