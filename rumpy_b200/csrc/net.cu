@@ -609,7 +609,6 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   std::vector<int> cs_bias_param;
   std::vector<PartialSumJob> ps_jobs;
   std::vector<int> ps_bias_param;
-  PartialSumJob* ps_jobs_dev = nullptr;
   struct Site { int conv; const void* g; const void* x; int h, w; float alpha; const float* part; int part_count;
                 bool thin = false; /* tail conv: g is zero-padded to 64 channels, bias gradient handled elsewhere */ };
   std::vector<Site> sites;
