@@ -89,6 +89,8 @@ def load():
         lib.rumpy_debug_set_trunk(0)
     if os.environ.get('RUMPY_B200_CLUSTER') == '0':   # debug switch: no cluster-per-image kernel (dataflow kernel only)
         lib.rumpy_debug_set_trunk_cluster(0)
+    if os.environ.get('RUMPY_B200_CLUSTER_GROUPS') in ('2', '4'):   # epilogue groups of the cluster kernel
+        lib.rumpy_debug_set_cluster_groups(int(os.environ['RUMPY_B200_CLUSTER_GROUPS']))
     if os.environ.get('RUMPY_B200_FUSED_CA') == '1':  # opt-in: conv2 + CALayer + skip in one kernel (conv3x3_ca.cuh)
         lib.rumpy_debug_set_fused_ca(1)
     _lib = lib

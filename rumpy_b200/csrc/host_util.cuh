@@ -128,6 +128,7 @@ struct TrunkPlan {
   bool cluster = false;
   ClusterArgs cargs;
   int cluster_size = 0;
+  int cluster_groups = 2;   // epilogue groups (template parameter of the cluster kernel) the plan was built for
   size_t cluster_smem = 0;
 };
 // backward program of the body (trunk_bwd.cuh)

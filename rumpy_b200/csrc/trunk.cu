@@ -7,6 +7,8 @@ namespace rb {
 
 extern long long* g_debug_timeline;
 int g_use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
+int g_cluster_groups = 2;     // epilogue groups of the cluster kernel (2 or 4)
+constexpr int kClusterMaxDyn = 227 * 1024 - 8192;
 int g_trunk_sync_mode = 8;   // release store of the tile epoch (needed: see DESIGN.md trunk protocol)
 cudaEvent_t g_trunk_ev0 = nullptr, g_trunk_ev1 = nullptr;   // optional: recorded around the trunk kernel (bench)
 int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
@@ -75,7 +77,10 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
   if (g_use_cluster && allow_cluster) {
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(trunk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096);
+      // dynamic + static (3.2 KB with 2 epilogue groups, 5.8 KB with 4) must stay within 227 KB
+      if (cudaFuncSetAttribute(trunk_cluster_kernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClusterMaxDyn) != cudaSuccess ||
+          cudaFuncSetAttribute(trunk_cluster_kernel_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kClusterMaxDyn) != cudaSuccess)
+        return set_error(RUMPY_ERR_CUDA, "trunk_cluster cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
       attr_set = true;
     }
     int best_tiles = 99, best_perim = 1 << 30;
@@ -86,17 +91,18 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         const int C = cx * cy;
         if (C > 8) continue;
         const size_t smem = cluster_smem_bytes(th, tw, C);
-        if (smem > 227 * 1024 - 4096) continue;
+        if (smem > size_t(kClusterMaxDyn)) continue;
         const int perim = kClusterTileH * th + kClusterTileW * tw;
         if (th * tw > best_tiles || (th * tw == best_tiles && perim >= best_perim)) continue;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(cluster_threads(g_cluster_groups)); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int active = 0;
-        if (cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel, &cfg) != cudaSuccess) {
+        if ((g_cluster_groups == 4 ? cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel_t<4>, &cfg)
+                                   : cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel_t<2>, &cfg)) != cudaSuccess) {
           (void)cudaGetLastError();
           continue;
         }
@@ -104,6 +110,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         best_tiles = th * tw; best_perim = perim;
         plan->cluster = true;
         plan->cluster_size = C;
+        plan->cluster_groups = g_cluster_groups;
         plan->cluster_smem = smem;
         ClusterArgs& c = plan->cargs;
         memset(&c, 0, sizeof(c));
@@ -156,14 +163,15 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
     c.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
     c.dbg_layers = g_trunk_dbg_layers;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(c.N * plan->cluster_size); cfg.blockDim = dim3(kClusterThreads);
+    cfg.gridDim = dim3(c.N * plan->cluster_size); cfg.blockDim = dim3(cluster_threads(plan->cluster_groups));
     cfg.dynamicSmemBytes = plan->cluster_smem; cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = plan->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, trunk_cluster_kernel, plan->w_map, c);
+    cudaError_t e = plan->cluster_groups == 4 ? cudaLaunchKernelEx(&cfg, trunk_cluster_kernel_t<4>, plan->w_map, c)
+                                              : cudaLaunchKernelEx(&cfg, trunk_cluster_kernel_t<2>, plan->w_map, c);
     if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "trunk_cluster launch: %s", cudaGetErrorString(e));
     if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
     return RUMPY_OK;
@@ -325,6 +333,8 @@ extern "C" {
 int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
 int rumpy_debug_set_trunk_sync_mode(int mode) { rb::g_trunk_sync_mode = mode; return 0; }
 int rumpy_debug_set_trunk_cluster(int on) { rb::g_use_cluster = on; return 0; }
+/* epilogue groups of the cluster kernel: 2 (320 threads) or 4 (576 threads); takes effect for plans built afterwards */
+int rumpy_debug_set_cluster_groups(int groups) { rb::g_cluster_groups = groups == 4 ? 4 : 2; return 0; }
 /* bench hook: CUDA events (cudaEvent_t) recorded right before / after the trunk kernel of every forward; NULL = off */
 int rumpy_debug_set_trunk_events(void* ev_start, void* ev_stop) {
   rb::g_trunk_ev0 = static_cast<cudaEvent_t>(ev_start);

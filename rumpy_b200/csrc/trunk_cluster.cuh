@@ -16,7 +16,9 @@
 //     cluster, each CTA reduces them in a fixed order and computes y itself;
 //   * fp32 residual stream + accumulators live in TMEM, weights stream through one 72 KB buffer in kx thirds (as
 //     in trunk_pipe.cuh).
-// Warp roles (320 threads): 0-3 epilogue group 0 | 4-7 epilogue group 1 | 8 MMA issuer | 9 weight producer.
+// Warp roles, NG epilogue groups (template parameter, 2 or 4): warps 0 .. 4*NG-1 epilogue (group e = warp / 4 owns
+// channels [64/NG * e, 64/NG * (e+1)) of every tile) | 4*NG MMA issuer | 4*NG+1 weight producer.  NG = 4 (576 threads,
+// <= 112 registers) halves the exposed epilogue / channel-attention tails that NG = 2 (320 threads) leaves.
 #pragma once
 #include "trunk_pipe.cuh"
 
@@ -32,7 +34,8 @@ struct ClusterArgs {
   float inv_hw;
 };
 
-constexpr int kClusterThreads = 320;
+constexpr int kClusterThreads = 320;   // NG = 2
+__host__ __device__ constexpr int cluster_threads(int ng) { return (4 * ng + 2) * 32; }
 constexpr int kClusterTileH = 16, kClusterTileW = 8;
 
 __host__ __device__ inline size_t cluster_buf_bytes(int th, int tw) {
@@ -45,8 +48,11 @@ __host__ __device__ inline size_t cluster_smem_bytes(int th, int tw, int C) {
 
 #ifdef RB_TRUNK_KERNEL_IMPL
 
-__global__ void __launch_bounds__(kClusterThreads, 1)
-trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArgs args) {
+template <int NG>
+__global__ void __launch_bounds__(cluster_threads(NG), 1)
+trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterArgs args) {
+  constexpr int KC = 64 / NG;      // channels (TMEM columns) per epilogue group
+  constexpr int KCH = KC / 8;      // 16-byte chunks (8 channels) per pixel and group
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full[3];
   __shared__ __align__(8) uint64_t w_empty[3];
@@ -54,11 +60,11 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
   __shared__ __align__(8) uint64_t in_full[2];
   __shared__ __align__(8) uint64_t pool_full[2];
   __shared__ uint32_t tmem_base_s, halo_bytes_s;
-  __shared__ __align__(16) float y_s[2][64];
-  __shared__ float bias_s[2][32], alpha_s[2][32], red_s[2][4][64];
+  __shared__ __align__(16) float y_s[NG][64];
+  __shared__ float bias_s[NG][KC], alpha_s[NG][KC], red_s[NG][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarpMma = 8, kWarpW = 9;
+  constexpr int kWarpMma = 4 * NG, kWarpW = 4 * NG + 1;
   const int n_layers = args.n_layers;
   const int th = args.th, tw = args.tw, n_tiles = th * tw;
   const int C = args.cx * args.cy;
@@ -83,7 +89,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
   } while (0)
 
   // ---- zero both activation buffers (halo cells outside the image must read as the conv's zero padding)
-  for (uint32_t i = threadIdx.x * 16; i < 2 * buf_bytes; i += kClusterThreads * 16)
+  for (uint32_t i = threadIdx.x * 16; i < 2 * buf_bytes; i += cluster_threads(NG) * 16)
     *reinterpret_cast<uint4*>(buf0 + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     // halo pixels this CTA is owed per layer: the halo cells that lie inside the image (each has one owner)
@@ -100,7 +106,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
     // Both parities are armed here for layers 0 / 1 (CA layers 0 / 1); later phases are re-armed by their consumer.
     halo_bytes_s = uint32_t(halo) * 128u;
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&in_full[i], 3);
+      mbar_init(&in_full[i], NG + 1);
       mbar_init(&pool_full[i], 1);
     }
     fence_mbar_init();
@@ -171,27 +177,27 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
       }
     }
   } else {
-    // ===================================================================== epilogue: 2 groups x 128 threads
-    // Both groups work on EVERY tile: group e owns channels [32e, 32e+32) of each pixel (balanced for any tile
-    // count, and the exposed epilogue of a layer's last tile is half as long).
+    // ===================================================================== epilogue: NG groups x 128 threads
+    // Every group works on EVERY tile: group e owns channels [KC*e, KC*e + KC) of each pixel (balanced for any tile
+    // count, and the exposed epilogue of a layer's last tile shrinks with NG).
     const int e = warp >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;           // pixel of the tile == TMEM lane == thread index in the group
     const int ly = row >> 3, lx = row & 7;   // 16 rows x 8 pixels
     const uint32_t bar_id = 1u + uint32_t(e);
-    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(32 * e);
-    const uint32_t plane0 = uint32_t(4 * e) * plane;   // this group's four channel planes
-    float* bias_e = bias_s[e];                // 32 values: channels 32e ..
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(KC * e);
+    const uint32_t plane0 = uint32_t(KCH * e) * plane;   // this group's channel planes
+    float* bias_e = bias_s[e];                // KC values: channels KC*e ..
     float* alpha_e = alpha_s[e];              // kTrunkRes: alpha (x the Q-EDSR multiplier of this image's channel)
     float* y_e = y_s[e];
 
-    // One pixel's 32 bf16 channels (4 chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
+    // One pixel's KC bf16 channels (KCH chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
     // `par` selects the destination buffer AND the mbarrier whose transaction count the remote bytes complete.
-    auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[4]) {
+    auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[KCH]) {
       uint8_t* ob = buf0 + par * buf_bytes + plane0;
       const uint32_t cell = uint32_t((qy + 1) * PP + qx + 1) * 16;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
+      for (int c = 0; c < KCH; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
       if (!valid) return;
       const int dyv = qy == 0 ? -1 : (qy == RH - 1 ? 1 : 0);
       const int dxv = qx == 0 ? -1 : (qx == RW - 1 ? 1 : 0);
@@ -207,7 +213,7 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const uint32_t raddr = mapa_u32(smem_u32(ob) + rcell, drank);
         const uint32_t rbar = mapa_u32(smem_u32(&in_full[par]), drank);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) st_async_v4(raddr + c * plane, ch[c], rbar);   // 4 x 16 B = this half pixel
+        for (int c = 0; c < KCH; ++c) st_async_v4(raddr + c * plane, ch[c], rbar);   // KCH x 16 B of this pixel
       }
     };
     // every thread of the group has written its half pixels of ALL tiles: one local arrival per group and layer
@@ -223,19 +229,19 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
       const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
       const int y = ry * RH + qy, x = rx * RW + qx;
       const bool valid = y < args.H && x < args.W;
-      const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
-      uint32_t v[32];
+      const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + KC * e;
+      uint32_t v[KC];
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
+      for (int c4 = 0; c4 < KC / 4; ++c4) {
         float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid) f = __ldg(reinterpret_cast<const float4*>(args.s_init + pix) + c4);
         v[c4 * 4 + 0] = __float_as_uint(f.x); v[c4 * 4 + 1] = __float_as_uint(f.y);
         v[c4 * 4 + 2] = __float_as_uint(f.z); v[c4 * 4 + 3] = __float_as_uint(f.w);
       }
-      tmem_st32(lane_addr + uint32_t(j * 64), v);
-      uint4 ch[4];
+      tmem_st(lane_addr + uint32_t(j * 64), v);
+      uint4 ch[KCH];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < KCH; ++c)
         ch[c] = valid ? __ldg(reinterpret_cast<const uint4*>(args.x_init + pix) + c) : make_uint4(0, 0, 0, 0);
       write_pixel(0, qy, qx, valid, ch);
     }
@@ -246,28 +252,28 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
     for (int L = 0; L < n_layers; ++L) {
       const TrunkLayer* lay = args.layers + L;
       const int kind = lay->kind;
-      const float* bias = lay->bias + 32 * e;
+      const float* bias = lay->bias + KC * e;
       const int par_out = (L + 1) & 1;
       const bool last = L == n_layers - 1;
-      if (row < 32) {   // the previous layer ended with a group barrier
+      if (row < KC) {   // the previous layer ended with a group barrier
         bias_e[row] = __ldg(bias + row);
         alpha_e[row] = (kind == kTrunkRes && lay->q_scale != nullptr)
-                           ? lay->alpha * __ldg(lay->q_scale + n * 64 + 32 * e + row) : lay->alpha;
+                           ? lay->alpha * __ldg(lay->q_scale + n * 64 + KC * e + row) : lay->alpha;
       }
       named_bar_sync(bar_id, 128);
 
-      // 32 fp32 results of this thread's half pixel -> bf16 chunks -> buffer / halos (or global, last layer)
-      auto emit = [&](int qy, int qx, bool valid, size_t pix, const float (&f)[32]) {
-        uint4 ch[4];
+      // KC fp32 results of this thread's part of a pixel -> bf16 chunks -> buffer / halos (or global, last layer)
+      auto emit = [&](int qy, int qx, bool valid, size_t pix, const float (&f)[KC]) {
+        uint4 ch[KCH];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < KCH; ++c)
           ch[c] = valid ? make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
                                      pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]))
                         : make_uint4(0, 0, 0, 0);
         if (last) {
           if (valid) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) *(reinterpret_cast<uint4*>(args.out_bf16 + pix) + c) = ch[c];
+            for (int c = 0; c < KCH; ++c) *(reinterpret_cast<uint4*>(args.out_bf16 + pix) + c) = ch[c];
           }
         } else {
           write_pixel(par_out, qy, qx, valid, ch);
@@ -280,50 +286,50 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
         const int y = ry * RH + qy, x = rx * RW + qx;
         const bool valid = y < args.H && x < args.W;
-        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + KC * e;
         const float* res = lay->res_f32;
         float* outf = lay->out_f32;
         const int update_s = lay->update_s;
         mbar_wait(&acc_full[j], uint32_t(L & 1));
         tc_fence_after();
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
-        uint32_t v[32];
-        float f[32];
-        tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+        uint32_t v[KC];
+        float f[KC];
+        tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
         if (kind == kTrunkRelu) {
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[i], 0.f);
+          for (int i = 0; i < KC; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[i], 0.f);
         } else {
           if (lay->no_res) {
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = 0.f;
+            for (int i = 0; i < KC; ++i) f[i] = 0.f;
           } else if (res != nullptr) {
             tmem_ld_wait();
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
+            for (int c4 = 0; c4 < KC / 4; ++c4) {
               float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
               if (valid) r = *reinterpret_cast<const float4*>(res + pix + c4 * 4);
               f[c4 * 4 + 0] = r.x; f[c4 * 4 + 1] = r.y; f[c4 * 4 + 2] = r.z; f[c4 * 4 + 3] = r.w;
             }
           } else {
-            uint32_t s[32];
-            tmem_ld32(lane_addr + uint32_t(j * 64), s);
+            uint32_t s[KC];
+            tmem_ld(lane_addr + uint32_t(j * 64), s);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
+            for (int i = 0; i < KC; ++i) f[i] = __uint_as_float(s[i]);
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[i]) * alpha_e[i] + f[i];
+          for (int i = 0; i < KC; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[i]) * alpha_e[i] + f[i];
           if (update_s) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
-            tmem_st32(lane_addr + uint32_t(j * 64), v);
+            for (int i = 0; i < KC; ++i) v[i] = __float_as_uint(f[i]);
+            tmem_st(lane_addr + uint32_t(j * 64), v);
           }
           if (outf != nullptr && valid) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4)
+            for (int c4 = 0; c4 < KC / 4; ++c4)
               *reinterpret_cast<float4*>(outf + pix + c4 * 4) =
                   make_float4(f[c4 * 4], f[c4 * 4 + 1], f[c4 * 4 + 2], f[c4 * 4 + 3]);
           }
@@ -343,21 +349,26 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         tc_fence_after();
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
         {
-          uint32_t v[32];
-          float f[32];
-          tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+          uint32_t v[KC];
+          float f[KC];
+          tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[i] : 0.f;
-          red_s[e][q][lane] = lane_transpose_sum32(f, lane);
+          for (int i = 0; i < KC; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[i] : 0.f;
+          if constexpr (KC == 32) {
+            red_s[e][q][lane] = lane_transpose_sum32(f, lane);
+          } else {
+            const float cs = lane_transpose_sum16(f, lane);   // column (lane >> 1), at both lanes of the pair
+            if ((lane & 1) == 0) red_s[e][q][lane >> 1] = cs;
+          }
         }
         tc_fence_before();
         named_bar_sync(bar_id, 128);
-        if (row < 32) {
+        if (row < KC) {
           // this tile's channel sum -> slot (rank, j) of EVERY CTA of the cluster (fixed slot => fixed sum order)
           const float s = (red_s[e][0][row] + red_s[e][1][row]) + (red_s[e][2][row] + red_s[e][3][row]);
           const uint32_t slot =
-              smem_u32(pool_s + (size_t(cpar) * pool_slots + rank * n_tiles + j) * 64 + 32 * e + row);
+              smem_u32(pool_s + (size_t(cpar) * pool_slots + rank * n_tiles + j) * 64 + KC * e + row);
           const uint32_t pbar = smem_u32(&pool_full[cpar]);
           for (int d = 0; d < C; ++d)
             st_async_b32(mapa_u32(slot, uint32_t(d)), __float_as_uint(s), mapa_u32(pbar, uint32_t(d)));
@@ -416,18 +427,18 @@ trunk_cluster_kernel(const __grid_constant__ CUtensorMap w_map, const ClusterArg
         const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
         const int y = ry * RH + qy, x = rx * RW + qx;
         const bool valid = y < args.H && x < args.W;
-        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + 32 * e;
-        const float* yv = y_e + 32 * e;
-        uint32_t v[32], s[32];
-        float f[32];
-        tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
-        tmem_ld32(lane_addr + uint32_t(j * 64), s);
+        const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + KC * e;
+        const float* yv = y_e + KC * e;
+        uint32_t v[KC], s[KC];
+        float f[KC];
+        tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+        tmem_ld(lane_addr + uint32_t(j * 64), s);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]) + bias_e[i], yv[i], __uint_as_float(s[i]));
+        for (int i = 0; i < KC; ++i) f[i] = fmaf(__uint_as_float(v[i]) + bias_e[i], yv[i], __uint_as_float(s[i]));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
-        tmem_st32(lane_addr + uint32_t(j * 64), s);
+        for (int i = 0; i < KC; ++i) s[i] = __float_as_uint(f[i]);
+        tmem_st(lane_addr + uint32_t(j * 64), s);
         tc_fence_before();
         emit(qy, qx, valid, pix, f);
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);

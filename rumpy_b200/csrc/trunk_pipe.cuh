@@ -141,6 +141,24 @@ __device__ __forceinline__ float lane_transpose_sum32(float (&f)[32], int lane) 
   return f[0];
 }
 
+// 16 columns per lane: after the steps over lane bits 4..1 lane l holds column (l >> 1) summed over 16 rows; the last
+// exchange adds the other 16.  Returns the sum over the warp's 32 rows of column (lane >> 1), at every lane.
+__device__ __forceinline__ float lane_transpose_sum16(float (&f)[16], int lane) {
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const bool up = (lane & (2 * half)) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < half) {
+        const float send = up ? f[i] : f[i + half];
+        const float keep = up ? f[i + half] : f[i];
+        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * half);
+      }
+    }
+  }
+  return f[0] + __shfl_xor_sync(0xffffffffu, f[0], 1);
+}
+
 __global__ void __launch_bounds__(kTrunkThreads, 1)
 trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs args) {
   extern __shared__ uint8_t smem_raw[];

@@ -14,7 +14,8 @@ from oracle import sr_torch_cpu
 
 pytestmark = pytest.mark.gpu
 
-MODES = {'per-layer': (0, 0), 'dataflow': (1, 0), 'cluster': (1, 1)}
+DEFAULT_GROUPS = int(__import__('os').environ.get('RUMPY_B200_CLUSTER_GROUPS', 2))
+MODES = {'per-layer': (0, 0, 2), 'dataflow': (1, 0, 2), 'cluster': (1, 1, 2), 'cluster-4-groups': (1, 1, 4)}
 
 
 def _dev():
@@ -27,6 +28,7 @@ def _lib():
     lib = _lib.load()
     lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
     lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_cluster_groups.argtypes = [ctypes.c_int]
     return lib
 
 
@@ -43,9 +45,10 @@ def _run_modes(net, x):
     lib = _lib()
     outs, modes = {}, {}
     try:
-        for name, (trunk, cluster) in MODES.items():
+        for name, (trunk, cluster, groups) in MODES.items():
             lib.rumpy_debug_set_trunk(trunk)
             lib.rumpy_debug_set_trunk_cluster(cluster)
+            lib.rumpy_debug_set_cluster_groups(groups)
             eng = net.native_engine()
             eng._ws.clear()
             eng._graphs.clear()
@@ -59,6 +62,7 @@ def _run_modes(net, x):
     finally:
         lib.rumpy_debug_set_trunk(1)
         lib.rumpy_debug_set_trunk_cluster(1)
+        lib.rumpy_debug_set_cluster_groups(DEFAULT_GROUPS)
     return outs, modes
 
 
@@ -82,6 +86,7 @@ def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, wa
     assert modes['per-layer'] == 0 and modes['dataflow'] == 1
     if want_mode is not None:
         assert modes['cluster'] == want_mode, f'cluster-allowed plan picked mode {modes["cluster"]}'
+        assert modes['cluster-4-groups'] == want_mode
     sdt = {k: torch.from_numpy(v) for k, v in sd.items()}
     arch, akw = sr_torch_cpu.infer_arch(sdt)
     ref = sr_torch_cpu.forward(sdt, torch.from_numpy(x), arch, res_scale=0.1, **akw).numpy()
@@ -90,7 +95,7 @@ def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, wa
         err = float(np.abs(out.cpu().numpy() - ref).max())
         assert err <= 1e-2 * scale, f'{name} [{mode}]: max-abs {err} vs CPU oracle'
     base = outs['per-layer']
-    for mode in ('dataflow', 'cluster'):
+    for mode in ('dataflow', 'cluster', 'cluster-4-groups'):
         d = float((outs[mode] - base).abs().max())
         assert d <= 5e-3 * scale, f'{name}: {mode} differs from the per-layer path by {d}'
 
