@@ -1078,7 +1078,9 @@ int rumpy_net_num_launches_backward(void* net) {
   if (!net) return -1;
   Net* n = static_cast<Net*>(net);
   if (n->bops.empty()) return 0;
-  int c = 5;                                  // batched wgrad, its reduce, colsum, colsum reduce, partial sums
+  int chunks = 0, j0 = 0;                     // wgrad chunks that actually hold jobs: wgrad kernel + its reduce each
+  for (int j1 : n->wg_chunk_job_end) { chunks += j1 > j0; j0 = j1; }
+  int c = 2 * chunks + (n->cs_jobs.empty() ? 0 : 2) + (n->ps_jobs.empty() ? 0 : 1);   // + colsum, its reduce, partial sums
   for (const Op& op : n->bops) {
     switch (op.type) {
       case OP_TAIL_BWD: c += 4; break;        // dgrad, padded dy operand, plane sums (2)
