@@ -384,6 +384,8 @@ struct CaBwdArgs {
   float* pg_scratch;                           // [N][2*C*Cr + C + Cr] per-image parameter-gradient terms
   int* counters;                               // [N + 1] zero-initialised
   int N, HW, C, Cr;
+  const float* q_scale;                        // Q-RCAN: forward multipliers [N][C] (out = x + u*y*q), or nullptr
+  float* dq;                                   // Q-RCAN: d(loss)/dq = s*y [N][C], or nullptr
 };
 
 template <bool U_F32>
@@ -454,7 +456,9 @@ __global__ void ca_bwd_reduce_kernel(const CaBwdArgs a) {
       float s = 0.f;
       for (int k = 0; k < groups; ++k) s += red[k * C + tid];
       const float y = a.save_y[n * C + tid];
-      dz2_s[tid] = s * y * (1.f - y);
+      const float qv = a.q_scale != nullptr ? a.q_scale[n * C + tid] : 1.f;   // dy = s*q, dq = s*y
+      dz2_s[tid] = s * qv * y * (1.f - y);
+      if (a.dq != nullptr) a.dq[n * C + tid] = s * y;
     }
   }
   __syncthreads();
@@ -504,7 +508,8 @@ __global__ void ca_bwd_reduce_kernel(const CaBwdArgs a) {
 // kernel's per-image epilogue).  Also emits per-block column sums of du (conv2's bias gradient).
 __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __restrict__ save_y,
                                     const float* __restrict__ coef, __nv_bfloat16* __restrict__ du,
-                                    float* __restrict__ du_colsum /* [N][gridDim.x][C] */, int HW, int C) {
+                                    float* __restrict__ du_colsum /* [N][gridDim.x][C] */, int HW, int C,
+                                    const float* __restrict__ q_scale /* Q-RCAN: du = G*y*q + coef; or nullptr */) {
   const int tid = threadIdx.x, n = blockIdx.y;
   const int vec_per_pix = C / 4;
   const size_t total = size_t(HW) * vec_per_pix;
@@ -512,7 +517,11 @@ __global__ void ca_bwd_apply_kernel(const float* __restrict__ G, const float* __
   const size_t stride = size_t(gridDim.x) * blockDim.x;     // multiple of C/4: each thread keeps its 4 channels
   const size_t i0 = blockIdx.x * size_t(blockDim.x) + tid;
   const int c4 = int(i0 % vec_per_pix) * 4;
-  const float4 y4 = *reinterpret_cast<const float4*>(save_y + n * C + c4);
+  float4 y4 = *reinterpret_cast<const float4*>(save_y + n * C + c4);
+  if (q_scale != nullptr) {
+    const float4 q4 = *reinterpret_cast<const float4*>(q_scale + n * C + c4);
+    y4.x *= q4.x; y4.y *= q4.y; y4.z *= q4.z; y4.w *= q4.w;
+  }
   const float4 k4 = *reinterpret_cast<const float4*>(coef + n * C + c4);
   float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   auto emit = [&](size_t i, const float4& g) {

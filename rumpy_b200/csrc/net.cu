@@ -757,9 +757,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         bops.push_back(op);
       }
     } else if (n->arch == 0) {
-      if (n->qrcan)
-        return set_error(RUMPY_ERR_ARG, "Q-RCAN training needs the dataflow kernels: batch %d x %d x %d exceeds 4 tiles "
-                         "(8x16 px) per SM", N, H, W);
+      float* dq_all = n->qrcan ? static_cast<float*>(bp.take(size_t(n->cas.size()) * N * C * 4)) : nullptr;
+      QGradJobHost* qgj = n->qrcan ? static_cast<QGradJobHost*>(bp.take(n->cas.size() * sizeof(QGradJobHost))) : nullptr;
+      if (build && n->qrcan) { n->q_dq = dq_all; n->qg_jobs_dev = qgj; n->qg_jobs_uploaded.clear(); }
       for (int g = n->n_groups - 1; g >= 0; --g) {
         const GroupRec& gr = groups[g];
         {  // group tail conv: grad wrt the last block's output, fp32 only
@@ -783,6 +783,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           cb.ca = n->cas[br.ca];
           cb.a = Q; cb.u = br.u; cb.s_partial = s_partial; cb.du = du; cb.du_colsum = du_cs; cb.ca_chunks = ca_chunks;
           cb.save_mean = br.sv; cb.save_y = br.sv + size_t(N) * C; cb.save_hid = br.sv + size_t(N) * 2 * C;
+          if (n->qrcan && n->qs[br.ca].w1 >= 0) { cb.q_scale = q_of(br.ca); cb.dst_f = dq_all + size_t(br.ca) * N * C; }
           bops.push_back(cb);
           ConvDesc d2{};
           d2.x = du; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C; d2.alpha = 1.f;
@@ -801,6 +802,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         bops.push_back(add);
         GB_cur = GB_new;
       }
+      if (n->qrcan) { Op qg{}; qg.type = OP_QGRAD; qg.ca_chunks = 0; bops.push_back(qg); }   // dq [N][C] per RCAB
     } else {
       const GroupRec& gr = groups[0];
       const bool qed = n->qrcan;
@@ -834,7 +836,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * tiles * 2});
         GB_cur = GB_new;
       }
-      if (qed) { Op qg{}; qg.type = OP_QGRAD; bops.push_back(qg); }
+      if (qed) { Op qg{}; qg.type = OP_QGRAD; qg.ca_chunks = kDqSlices; bops.push_back(qg); }   // q*dq slices
     }
     {  // head conv: weight / bias gradient only (no dX), upstream = trunk gradient + global skip
       Op op{};
@@ -1286,13 +1288,15 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
       case OP_DQ:
         if (int e = dq_reduce_launch(op.a, op.u, op.tail_in, op.dst_f, N, H * W, C, stream)) return e;
         break;
-      case OP_QGRAD: {   // Q-EDSR q-layer parameter gradients from the q * dq partial sums of the OP_DQ passes
+      case OP_QGRAD: {   // q-layer parameter gradients: Q-EDSR from the q * dq slices of the OP_DQ passes, Q-RCAN
+                         // (per-layer path) from the dq the CA backward wrote
         std::vector<QGradJobHost> jobs;
         for (size_t i = 0; i < n->qs.size(); ++i) {
           const CAW& q = n->qs[i];
           if (q.w1 < 0) continue;
           jobs.push_back(QGradJobHost{params[q.w1], params[q.b1], params[q.w2], params[q.b2],
-                                      n->q_scale + i * size_t(N) * C, n->q_dq + i * size_t(N) * kDqSlices * C,
+                                      n->q_scale + i * size_t(N) * C,
+                                      n->q_dq + i * size_t(N) * (op.ca_chunks > 0 ? op.ca_chunks : 1) * C,
                                       grads[q.w1], grads[q.b1], grads[q.w2], grads[q.b2]});
         }
         if (!jobs.empty() && (jobs.size() != n->qg_jobs_uploaded.size() ||
@@ -1304,7 +1308,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
           cudaStreamSynchronize(stream);
         }
         if (int e = q_grad_launch(n->qg_jobs_dev, int(jobs.size()), n->meta_dev, N, n->meta_m, n->q_hidden, C, n->q_relu,
-                                  kDqSlices, stream))
+                                  op.ca_chunks, stream))
           return e;
         break;
       }
@@ -1340,13 +1344,14 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         a.dw1 = grads[op.ca.w1]; a.db1 = grads[op.ca.b1]; a.dw2 = grads[op.ca.w2]; a.db2 = grads[op.ca.b2];
         a.s_partial = op.s_partial; a.coef = n->ca_coef; a.pg_scratch = n->pg_scratch; a.counters = n->pg_counter;
         a.N = N; a.HW = HW; a.C = C; a.Cr = Cr;
+        a.q_scale = op.q_scale; a.dq = op.q_scale ? op.dst_f : nullptr;
         dim3 g1(kCaBwdChunks, N);
         const size_t smem = size_t(256 / (C / 4)) * C * sizeof(float);
         if (n->plan_u_f32) ca_bwd_reduce_kernel<true><<<g1, 256, smem, stream>>>(a);
         else ca_bwd_reduce_kernel<false><<<g1, 256, smem, stream>>>(a);
         if (int e = check_launch("ca_bwd_reduce")) return e;
         ca_bwd_apply_kernel<<<dim3(op.ca_chunks, N), 256, 0, stream>>>(
-            op.a, op.save_y, n->ca_coef, static_cast<__nv_bfloat16*>(op.du), op.du_colsum, HW, C);
+            op.a, op.save_y, n->ca_coef, static_cast<__nv_bfloat16*>(op.du), op.du_colsum, HW, C, op.q_scale);
         if (int e = check_launch("ca_bwd_apply")) return e;
         break;
       }

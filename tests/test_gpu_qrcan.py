@@ -156,14 +156,25 @@ def _ytrain(name, kw, x):
                              recipe.QCASES[name][3] + 1000)
 
 
+@pytest.mark.parametrize('trunk', [1, 0], ids=['dataflow-kernels', 'per-layer-kernels'])
 @pytest.mark.parametrize('name', ['qrcan_blur_q', 'qrcan_selective', 'qrcan_wide_meta'])
-def test_qrcan_gradients_vs_reference_golden(golden_dir, name):
+def test_qrcan_gradients_vs_reference_golden(golden_dir, name, trunk):
     """Every parameter gradient (convs, channel attention, q-layers) of the native backward against the reference's
-    autograd: <= 3 % of the tensor's max magnitude and cosine >= 0.999 (bf16 operands, fp32 accumulate)."""
+    autograd: <= 3 % of the tensor's max magnitude and cosine >= 0.999 (bf16 operands, fp32 accumulate).  Both
+    backward implementations: the dataflow kernels and the per-layer kernels (shapes beyond 4 tiles per SM)."""
     from rumpy_b200 import train_native
     gold = np.load(os.path.join(golden_dir, 'qrcan.npz'))
     kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
     net = _qrcan(kw, sd).train()
+    lib = _lib()
+    lib.rumpy_debug_set_trunk(trunk)
+    try:
+        _check_qrcan_gradients(net, gold, name, kw, has_q, x, train_native)
+    finally:
+        lib.rumpy_debug_set_trunk(1)
+
+
+def _check_qrcan_gradients(net, gold, name, kw, has_q, x, train_native):
     eng = net.native_engine()
     xt = torch.from_numpy(x).to(_dev())
     yt = torch.from_numpy(_ytrain(name, kw, x)).to(_dev())
