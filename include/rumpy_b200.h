@@ -160,7 +160,7 @@ int rumpy_net_set_backward_events(void* net, void* const* events /* cudaEvent_t[
  *           params: head | final_body | per block: body.0, body.2, [attention_layer] | tail;  n_groups ignored.
  * q = sigmoid(FC2 act(FC1 metadata)) is the reference's 2-layer ParaCALayer (q_layer.py:5-45): num_metadata ->
  * q_hidden -> n_feats, act = ReLU iff q_relu.  block_has_q[i] != 0: block i owns one.  rumpy_net_forward(training)
- * / rumpy_net_backward also return the q-layer gradients; style 'modulate' is inference only.  All multipliers are evaluated
+ * / rumpy_net_backward also return the q-layer gradients ('modulate' combined with q-layers: inference only).  All multipliers are evaluated
  * by ONE small kernel per forward and applied inside the trunk kernels (channel-attention step / residual epilogue)
  * or, for shapes outside the trunk kernels' envelope, in the per-layer kernels' epilogues. */
 int rumpy_net_create_q(void** net, int arch, int n_feats, int n_groups, int n_blocks, int reduction, int scale,

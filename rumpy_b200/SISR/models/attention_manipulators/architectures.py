@@ -9,7 +9,7 @@ for the configurations the native trunk implements:
 Everything else the reference's QRCAN can be configured with (pixel attention, SFT / DGFMB / DA-conv layers, the
 concat styles, staggered encodings, outer metadata reduction) is outside SURVEY.md section 8 and raises
 NotImplementedError at construction.  Q-RCAN style 'standard' and Q-EDSR train natively (the q-layer parameters get
-their gradients from per-channel sums the backward kernels leave behind); style 'modulate' is inference only.
+their gradients from per-channel sums the backward kernels leave behind), style 'modulate' included.
 
 `QEDSR` (ParamResBlocks: res_scale * conv2(relu(conv1 x)) * q + x) keeps the reference's ctor and key layout too
 (`head.weight` without a Sequential index, `final_body` registered before `body`).

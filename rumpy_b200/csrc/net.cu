@@ -325,8 +325,13 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   // ---- Q-RCAN: per-(RCAB, image, channel) meta-attention multipliers, evaluated once per forward
   float* q_scale = nullptr;
   if (n->qrcan) {
-    if (training && n->modulate)
-      return set_error(RUMPY_ERR_ARG, "Q-RCAN style 'modulate': training is not implemented (inference only)");
+    if (training && n->modulate) {
+      // attributes * sigmoid(q-layer) would need the two factors apart in the backward; the reference's handler never
+      // builds that combination (its 'modulate' attributes are n_feats wide, the q-layers take num_metadata inputs)
+      for (const CAW& q : n->qs)
+        if (q.w1 >= 0)
+          return set_error(RUMPY_ERR_ARG, "Q-RCAN style 'modulate' combined with q-layers: inference only");
+    }
     q_scale = static_cast<float*>(bp.take(n->qs.size() * size_t(N) * C * sizeof(float)));
     QScaleJob* qj = static_cast<QScaleJob*>(bp.take(n->qs.size() * sizeof(QScaleJob)));
     if (build) {
@@ -714,9 +719,9 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
             l.aux = static_cast<const __nv_bfloat16*>(br.u); l.colsum = du_cs;
             l.save_mean = br.sv; l.save_y = br.sv + size_t(N) * C; l.save_hid = br.sv + size_t(N) * 2 * C;
             l.pg = pg_all + size_t(ca_ord) * N * per;
-            if (n->qrcan && n->qs[br.ca].w1 >= 0) {
-              l.q_scale = q_of(br.ca);
-              l.dq = dq_all + size_t(br.ca) * N * C;
+            if (n->qrcan) {
+              l.q_scale = q_of(br.ca);       // q-layer output, or the 'modulate' attributes (no gradient of their own)
+              if (n->qs[br.ca].w1 >= 0) l.dq = dq_all + size_t(br.ca) * N * C;
             }
             if (build) {
               l.out_map = out_of(du);
@@ -783,7 +788,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           cb.ca = n->cas[br.ca];
           cb.a = Q; cb.u = br.u; cb.s_partial = s_partial; cb.du = du; cb.du_colsum = du_cs; cb.ca_chunks = ca_chunks;
           cb.save_mean = br.sv; cb.save_y = br.sv + size_t(N) * C; cb.save_hid = br.sv + size_t(N) * 2 * C;
-          if (n->qrcan && n->qs[br.ca].w1 >= 0) { cb.q_scale = q_of(br.ca); cb.dst_f = dq_all + size_t(br.ca) * N * C; }
+          if (n->qrcan) { cb.q_scale = q_of(br.ca); cb.dst_f = n->qs[br.ca].w1 >= 0 ? dq_all + size_t(br.ca) * N * C : nullptr; }
           bops.push_back(cb);
           ConvDesc d2{};
           d2.x = du; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C; d2.alpha = 1.f;
@@ -1344,7 +1349,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
         a.dw1 = grads[op.ca.w1]; a.db1 = grads[op.ca.b1]; a.dw2 = grads[op.ca.w2]; a.db2 = grads[op.ca.b2];
         a.s_partial = op.s_partial; a.coef = n->ca_coef; a.pg_scratch = n->pg_scratch; a.counters = n->pg_counter;
         a.N = N; a.HW = HW; a.C = C; a.Cr = Cr;
-        a.q_scale = op.q_scale; a.dq = op.q_scale ? op.dst_f : nullptr;
+        a.q_scale = op.q_scale; a.dq = op.dst_f;
         dim3 g1(kCaBwdChunks, N);
         const size_t smem = size_t(256 / (C / 4)) * C * sizeof(float);
         if (n->plan_u_f32) ca_bwd_reduce_kernel<true><<<g1, 256, smem, stream>>>(a);

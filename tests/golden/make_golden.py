@@ -214,8 +214,8 @@ def qrcan_cases():
         rec[name + '::attributes'] = attrs.numpy()
         rec[name + '::out'] = out.numpy()
         print(name, 'out', out.shape, float(out.abs().max()))
-        if kw['style'] == 'standard':
-            # training: L1 gradients of every parameter (q-layers included) and 3 Adam steps
+        if True:
+            # training ('modulate': the attributes carry no gradient, the networks' own parameters do): L1 gradients of every parameter (q-layers included) and 3 Adam steps
             y = recipe.make_input((x.shape[0], 3, x.shape[2] * kw['scale'], x.shape[3] * kw['scale']),
                                   recipe.QCASES[name][3] + 1000)
             net.train()

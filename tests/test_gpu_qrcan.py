@@ -157,7 +157,7 @@ def _ytrain(name, kw, x):
 
 
 @pytest.mark.parametrize('trunk', [1, 0], ids=['dataflow-kernels', 'per-layer-kernels'])
-@pytest.mark.parametrize('name', ['qrcan_blur_q', 'qrcan_selective', 'qrcan_wide_meta'])
+@pytest.mark.parametrize('name', ['qrcan_blur_q', 'qrcan_selective', 'qrcan_wide_meta', 'qrcan_modulate'])
 def test_qrcan_gradients_vs_reference_golden(golden_dir, name, trunk):
     """Every parameter gradient (convs, channel attention, q-layers) of the native backward against the reference's
     autograd: <= 3 % of the tensor's max magnitude and cosine >= 0.999 (bf16 operands, fp32 accumulate).  Both
@@ -250,12 +250,13 @@ def test_qrcan_handler_run_train_loss_curve_vs_oracle(tmp_path):
     assert tuple(out.shape) == (2, 3, 64, 64)
 
 
-def test_modulate_training_is_rejected():
+def test_modulate_with_q_layers_training_is_rejected():
+    """attributes * sigmoid(q-layer) is inference only (the reference's handler cannot build that combination)."""
     from rumpy_b200 import _lib
-    kw, has_q, sd, x, meta = recipe.qcase_tensors('qrcan_modulate')
-    net = _qrcan(kw, sd).train()
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QRCAN
+    net = QRCAN(n_resgroups=1, n_resblocks=1, style='modulate', num_metadata=64, include_q_layer=True).to(_dev()).train()
     with pytest.raises(_lib.RumpyB200Error, match='inference only'):
-        net(torch.from_numpy(x).to(_dev()), torch.rand(x.shape[0], 64, 1, 1, device=_dev()))
+        net(torch.rand(1, 3, 16, 16, device=_dev()), torch.rand(1, 64, 1, 1, device=_dev()))
 
 
 @pytest.mark.parametrize('name', list(recipe.QECASES))
