@@ -119,7 +119,7 @@ int rumpy_pool_sum(const float* x_nhwc, float* pool_partial, int N, int H, int W
  * RCAN's groups in the trunk kernels, then layer attention over the 11 stacked group / body outputs -> last_conv,
  * channel-spatial attention of the body output, last(cat) + head skip; n_feats 64, n_groups 10 as the reference fixes
  * them; params in the reference's order head | body | csa.gamma, csa.conv | la.gamma | last_conv | last | tail;
- * inference only).
+ * trains too: backward through the per-layer kernels with the layer-attention gradients injected between the groups).
  * x: fp32 NCHW [N,in_feats,H,W] -> y: fp32 NCHW [N,out_feats,H*scale,W*scale], the reference's tensors.
  * training != 0 keeps every activation backward needs in the workspace.
  * ------------------------------------------------------------------------------------------------- */

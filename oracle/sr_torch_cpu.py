@@ -171,6 +171,8 @@ def infer_arch(sd):
 
 
 def forward(sd, x, arch, **kw):
+    if arch == 'han':
+        return han_forward(sd, x, kw.get('n_resgroups', 10), kw['n_resblocks'], kw.get('scale', 4))
     if arch == 'qedsr':
         return qedsr_forward(sd, x, kw['attributes'], kw['num_blocks'], kw.get('res_scale', 0.1), kw.get('scale', 4))
     if arch == 'qrcan':

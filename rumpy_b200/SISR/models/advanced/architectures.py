@@ -155,7 +155,7 @@ class EDSR(_NativeTrunk):
 class HAN(_NativeTrunk):
     """reference architectures.py:331-394: RCAN's residual groups, then layer attention (LAM) over the 11 stacked
     group / body outputs -> last_conv, channel-spatial attention (CSAM) of the body output, last(cat) + head skip.
-    The groups run in the trunk kernels; LAM / CSAM are the kernels of csrc/han.cu.  Inference only."""
+    The groups run in the trunk kernels; LAM / CSAM (forward and backward) are the kernels of csrc/han.cu."""
 
     def __init__(self, n_resgroups=10, n_resblocks=20, n_feats=64, reduction=16, scale=4, n_colors=3, res_scale=1.0,
                  conv=common.default_conv):

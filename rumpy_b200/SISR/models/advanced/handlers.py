@@ -36,7 +36,7 @@ class RCANHandler(ChopMixin, BaseModel):
 
 
 class HANHandler(ChopMixin, BaseModel):
-    """reference handlers.py:44-58 (most parameters locked, as there); inference only here."""
+    """reference handlers.py:44-58 (most parameters locked, as there)."""
 
     def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
                  scheduler=None, scheduler_params=None, max_combined_im_size=None, **kwargs):

@@ -85,6 +85,17 @@ int lam_launch(const float* const* stack, float* scratch, const float* gamma, vo
 int csam_cat_launch(const float* x, const float* out2, const float* w, const float* b, const float* gamma, void* cat_bf16,
                     int N, int H, int W, cudaStream_t s);
 
+// HAN training (han.cu): backward of CSAM / LAM and their parameter gradients
+int han_csam_blocks(int N, int H, int W);
+int han_bwd_scratch_floats(int N, int csam_blocks);
+const float* lam_att_ptr(const float* lam_scratch, int N);
+int csam_bwd_launch(const float* x, const float* dcat, const float* w, const float* b, const float* gamma, float* dc,
+                    float* sig, void* d2_b, float* dx0, float* scratch, int N, int H, int W, cudaStream_t s);
+int lam_bwd_launch(const float* const* stack, const float* G, const float* att, const float* gamma, float* const* dx,
+                   void* dx0_b, float* scratch, int csam_blocks, int N, int HW, cudaStream_t s);
+int han_param_grad_launch(const float* scratch, int csam_blocks, int N, float* dw, float* db, float* dg_csa, float* dg_la,
+                          cudaStream_t s);
+
 // one q-layer's parameter-gradient job (trunk_bwd.cuh: QGradJob has the same layout)
 struct QGradJobHost { const float *w1, *b1, *w2, *b2, *q, *dq; float *dw1, *db1, *dw2, *db2; };
 // dq_slices > 0: dq holds [N][dq_slices][C] partial sums of dq * q (Q-EDSR); 0: dq holds [N][C] (Q-RCAN)

@@ -34,7 +34,7 @@ struct ConvW {            // one 3x3 conv of the network
 struct CAW { int w1, b1, w2, b2; };
 using QScaleJob = QScaleJobHost;   // q_scale_kernel job (w1 == nullptr: no q-layer)
 
-enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD, OP_LAM, OP_CSAM, OP_DQ, OP_QGRAD };
+enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD, OP_LAM, OP_CSAM, OP_DQ, OP_QGRAD, OP_CSAM_BWD, OP_LAM_BWD, OP_HAN_PG };
 
 extern int g_use_fused_ca;
 extern int g_use_cluster;
@@ -59,6 +59,7 @@ struct Op {
   const float* q_scale;   // OP_CA (Q-RCAN): [N][C] multipliers of the CA vector, or nullptr
   // OP_LAM / OP_CSAM (HAN)
   const float* stack[kLamLayers]; float* lam_scratch; void* lam_out; const float* csam_x; const float* csam_out2; void* cat;
+  float* han_dx[kLamLayers]; float* han_f[4]; void* han_v; int han_i;   // OP_CSAM_BWD / OP_LAM_BWD / OP_HAN_PG
   // OP_ADD / OP_HEAD_WGRAD / OP_TAIL_BWD
   const float *a, *b; float* dst_f; void* dst_b; size_t n4;
   const void* tail_in; void* g_hr; float* thin_partial;
@@ -251,6 +252,11 @@ static int net_init(Net* n) {
     n->convs[i].off_dgrad = n->packed_bytes_train;
     n->packed_bytes_train = align_up(n->packed_bytes_train + size_t(9) * n->convs[i].cout * n->convs[i].cin * 2, 256);
   }
+  if (n->han)
+    for (int i : {n->conv_lastconv, n->conv_last}) {
+      n->convs[i].off_dgrad = n->packed_bytes_train;
+      n->packed_bytes_train = align_up(n->packed_bytes_train + size_t(9) * n->convs[i].cout * n->convs[i].cin * 2, 256);
+    }
   n->pack_jobs_bytes = align_up(2 * n->convs.size() * sizeof(PackJobHost), 256);
   n->packed_bytes += n->pack_jobs_bytes;
   n->packed_bytes_train += n->pack_jobs_bytes;
@@ -306,7 +312,10 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   float* S_f = static_cast<float*>(bp.take(px * C * 4));
   // fp32 group outputs: two ping-pong buffers (RCAN) or one per group (HAN stacks them for the layer attention)
   const bool han = n->han;
-  if (han && training) return set_error(RUMPY_ERR_ARG, "HAN: training is not implemented (inference only)");
+  const float* han_stack[kLamLayers] = {};   // kept for the backward plan
+  float* han_lam_scratch = nullptr;
+  void* han_lam_out = nullptr;
+  void* han_cat = nullptr;
   std::vector<float*> G_bufs(han ? n->n_groups : 2);
   for (auto& g : G_bufs) g = static_cast<float*>(bp.take(px * C * 4));
   struct { std::vector<float*>* v; bool han; float* operator[](int g) const { return (*v)[han ? g : (g & 1)]; } } G_f{&G_bufs, han};
@@ -569,6 +578,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     for (int k = 1; k < L; ++k) lam.stack[k] = G_f[L - 1 - k];
     lam.lam_scratch = lam_scratch; lam.lam_out = lam_out;
     ops.push_back(lam);
+    for (int k = 0; k < L; ++k) han_stack[k] = lam.stack[k];
+    han_lam_scratch = lam_scratch; han_lam_out = lam_out; han_cat = cat;
     ConvDesc d1{};
     d1.x = lam_out; d1.y_f32 = out2_f; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C * L; d1.Cout = C; d1.alpha = 1.f;
     conv_op(ops, n->convs[n->conv_lastconv], d1, false);
@@ -657,7 +668,48 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     float* P = static_cast<float*>(bp.take(px * C * 4));
     float* Q = static_cast<float*>(bp.take(px * C * 4));
     void* GB_cur = bp.take(px * C * 2);
-    {
+    float* han_dx[kLamLayers] = {};   // HAN: gradients w.r.t. the stacked maps (body conv output, groups 9 .. 0)
+    if (han) {
+      // ---- HAN head of the backward (architectures.py:380-392 in reverse): last -> {CSAM, last_conv -> LAM}
+      const int L = kLamLayers;
+      float* dcat_f = static_cast<float*>(bp.take(px * 2 * C * 4));
+      float* dc_f = static_cast<float*>(bp.take(px * C * 4));
+      float* sig_f = static_cast<float*>(bp.take(px * C * 4));
+      void* d2_b = bp.take(px * C * 2);
+      float* glam_f = static_cast<float*>(bp.take(px * C * L * 4));
+      for (int k = 0; k < L; ++k) han_dx[k] = static_cast<float*>(bp.take(px * C * 4));
+      void* gb2 = bp.take(px * C * 2);
+      const int cblocks = han_csam_blocks(N, H, W);
+      float* hscr = static_cast<float*>(bp.take(size_t(han_bwd_scratch_floats(N, cblocks)) * 4));
+      ConvDesc dl{};
+      dl.x = GB_body; dl.N = N; dl.H = H; dl.W = W; dl.Cin = C; dl.Cout = 2 * C; dl.alpha = 1.f; dl.y_f32 = dcat_f;
+      conv_op(bops, n->convs[n->conv_last], dl, true);
+      sites.push_back({n->conv_last, GB_body, han_cat, H, W, 1.f, nullptr, 0});
+      Op cb{};
+      cb.type = OP_CSAM_BWD;
+      cb.csam_x = han_stack[0]; cb.han_f[0] = dcat_f; cb.han_f[1] = dc_f; cb.han_f[2] = sig_f; cb.han_f[3] = hscr;
+      cb.han_v = d2_b; cb.han_dx[0] = han_dx[0]; cb.han_i = cblocks;
+      bops.push_back(cb);
+      ConvDesc dlc{};
+      dlc.x = d2_b; dlc.N = N; dlc.H = H; dlc.W = W; dlc.Cin = C; dlc.Cout = C * L; dlc.alpha = 1.f; dlc.y_f32 = glam_f;
+      conv_op(bops, n->convs[n->conv_lastconv], dlc, true);
+      sites.push_back({n->conv_lastconv, d2_b, han_lam_out, H, W, 1.f, nullptr, 0});
+      Op lb{};
+      lb.type = OP_LAM_BWD;
+      for (int k = 0; k < L; ++k) { lb.stack[k] = han_stack[k]; lb.han_dx[k] = han_dx[k]; }
+      lb.han_f[0] = glam_f; lb.han_f[3] = hscr; lb.lam_scratch = han_lam_scratch; lb.han_v = gb2; lb.han_i = cblocks;
+      bops.push_back(lb);
+      Op pg{};
+      pg.type = OP_HAN_PG;
+      pg.han_f[3] = hscr; pg.han_i = cblocks;
+      bops.push_back(pg);
+      // body conv (no skip in HAN): its input gradient + the layer-attention gradient of group 9's output
+      ConvDesc d{};
+      d.x = gb2; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.residual = han_dx[1]; d.y_f32 = P;
+      d.y_bf16 = GB_cur;
+      conv_op(bops, n->convs[n->conv_body], d, true);
+      sites.push_back({n->conv_body, gb2, body_in_b, H, W, 1.f, nullptr, 0});
+    } else {
       ConvDesc d{};
       d.x = GB_body; d.N = N; d.H = H; d.W = W; d.Cin = C; d.Cout = C; d.alpha = 1.f; d.y_f32 = P; d.y_bf16 = GB_cur;
       // Q-EDSR: the bf16 gradient operand of block b's conv2 dgrad / wgrad is g * q_b; the fp32 skip stream P stays g
@@ -665,7 +717,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       conv_op(bops, n->convs[n->conv_body], d, true);
       sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f, nullptr, 0});
     }
-    const bool use_trunk_bwd = g_use_trunk_bwd && use_trunk && n->arch == 0;
+    const bool use_trunk_bwd = g_use_trunk_bwd && use_trunk && n->arch == 0 && !han;   // HAN injects the layer-attention
+                                                                                       // gradients between the groups
     if (use_trunk_bwd) {
       // ---- the whole backward body as ONE persistent dataflow kernel (trunk_bwd.cuh); the gradient stream Q lives
       // in tensor memory, P (gradient w.r.t. the group input) is updated in place once per group
@@ -805,6 +858,11 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         add.type = OP_ADD;
         add.a = P; add.b = Q; add.dst_f = P; add.dst_b = GB_new; add.n4 = px * C / 4;
         bops.push_back(add);
+        if (han && g > 0) {   // + the layer-attention gradient of group g-1's output (stack index L - g)
+          Op add2 = add;
+          add2.b = han_dx[kLamLayers - g];
+          bops.push_back(add2);
+        }
         GB_cur = GB_new;
       }
       if (n->qrcan) { Op qg{}; qg.type = OP_QGRAD; qg.ca_chunks = 0; bops.push_back(qg); }   // dq [N][C] per RCAB
@@ -1289,6 +1347,21 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
       }
       case OP_CONV:
         if (int e = launch_conv_op(op, params, nullptr, stream)) return e;
+        break;
+      case OP_CSAM_BWD:
+        if (int e = csam_bwd_launch(op.csam_x, op.han_f[0], params[n->p_csa_w], params[n->p_csa_b], params[n->p_csa_gamma],
+                                    op.han_f[1], op.han_f[2], op.han_v, op.han_dx[0], op.han_f[3], N, H, W, stream))
+          return e;
+        break;
+      case OP_LAM_BWD:
+        if (int e = lam_bwd_launch(op.stack, op.han_f[0], lam_att_ptr(op.lam_scratch, N), params[n->p_la_gamma], op.han_dx,
+                                   op.han_v, op.han_f[3], op.han_i, N, H * W, stream))
+          return e;
+        break;
+      case OP_HAN_PG:
+        if (int e = han_param_grad_launch(op.han_f[3], op.han_i, N, grads[n->p_csa_w], grads[n->p_csa_b],
+                                          grads[n->p_csa_gamma], grads[n->p_la_gamma], stream))
+          return e;
         break;
       case OP_DQ:
         if (int e = dq_reduce_launch(op.a, op.u, op.tail_in, op.dst_f, N, H * W, C, stream)) return e;

@@ -287,6 +287,23 @@ def han_cases(arch_mod):
         with torch.no_grad():
             rec[name + '::out'] = net(t(x)).numpy()
         print(name, rec[name + '::out'].shape, float(np.abs(rec[name + '::out']).max()))
+        # training: L1 gradients of every parameter (attention modules included) and 3 Adam steps
+        y = recipe.make_input((x.shape[0], 3, x.shape[2] * scale, x.shape[3] * scale), recipe.HCASES[name][4] + 1000)
+        net.train()
+        loss = torch.nn.L1Loss()(net(t(x)), t(y))
+        loss.backward()
+        rec[name + '::loss'] = np.float32(loss.item())
+        for k, p in net.named_parameters():
+            rec[name + '::gradsub::' + k] = recipe.subsample(p.grad.numpy()).copy()
+        opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+        losses = []
+        for _ in range(3):
+            l = torch.nn.L1Loss()(net(t(x)), t(y))
+            opt.zero_grad()
+            l.backward()
+            opt.step()
+            losses.append(l.item())
+        rec[name + '::train_losses'] = np.array(losses, dtype=np.float32)
     return rec
 
 
