@@ -388,6 +388,29 @@ def extra_configs(device):
                            'launches': int(hnet.native_engine().lib.rumpy_net_num_launches(hnet.native_engine().handle)),
                            'note': f'{BATCH} x {LR_HW}x{LR_HW}; ops: head, trunk, LAM (3 kernels), last_conv, CSAM+cat, '
                                    'last, 2 upsampler convs, tail'}
+    # train steps of the two widened families at configs[2]'s batch (16 x 64x64 LR patches)
+    xt = torch.rand((16, 3, 64, 64), device=device)
+    yt = torch.rand((16, 3, 256, 256), device=device)
+    mt = torch.rand((16, 10, 1, 1), device=device)
+    for key, tnet, md in (('han_x4_train', hnet, None),
+                          ('qrcan_x4_train', QRCAN(style='standard', num_metadata=10, include_q_layer=True), mt)):
+        if md is not None:
+            tnet.load_state_dict({k: torch.from_numpy(v) for k, v in recipe.make_weights(qspec, seed=8).items()}, strict=True)
+            tnet = tnet.to(device)
+        tnet.train()
+        topt = FusedAdam(list(tnet.parameters()), lr=1e-4)
+        for _ in range(3):
+            train_native.train_step(tnet, topt, xt, yt, metadata=md)
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(5):
+            train_native.train_step(tnet, topt, xt, yt, metadata=md)
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out[key] = {'ms_per_step': ms, 'patches_per_s_per_gpu': 16 / ms * 1e3}
+        del tnet, topt
+        torch.cuda.empty_cache()
     del hnet
     torch.cuda.empty_cache()
     out['torch_eager_gpu_baseline'] = eager_gpu_baseline(device)

@@ -717,8 +717,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       conv_op(bops, n->convs[n->conv_body], d, true);
       sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f, nullptr, 0});
     }
-    const bool use_trunk_bwd = g_use_trunk_bwd && use_trunk && n->arch == 0 && !han;   // HAN injects the layer-attention
-                                                                                       // gradients between the groups
+    const bool use_trunk_bwd = g_use_trunk_bwd && use_trunk && n->arch == 0;
     if (use_trunk_bwd) {
       // ---- the whole backward body as ONE persistent dataflow kernel (trunk_bwd.cuh); the gradient stream Q lives
       // in tensor memory, P (gradient w.r.t. the group input) is updated in place once per group
@@ -798,7 +797,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
             TrunkBwdLayer l{};
             l.kind = kBwdAcc; l.ca_slot = -1; l.out_map = -1; l.w_idx = br.conv1 - 1; l.wait_epoch = L_mask + 1;
             void* GB_new = b == 0 ? bp.take(px * C * 2) : nullptr;
-            if (b == 0) { l.res_f32 = P; l.out_f32 = P; }
+            if (b == 0) { l.res_f32 = P; l.out_f32 = P; if (han && g > 0) l.add_f32 = han_dx[kLamLayers - g]; }
             if (build) { l.in_map = in_of(dt); if (b == 0) l.out_map = out_of(GB_new); }
             if (b == 0) { gb = GB_new; gb_epoch = L + 1; }
             push(l);

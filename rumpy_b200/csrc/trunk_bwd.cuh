@@ -38,6 +38,7 @@ struct TrunkBwdLayer {
   float* dq;                    // kBwdCA, Q-RCAN: d(loss)/dq = s*y per (image, channel) [N][64], or nullptr
   const float* res_f32;         // kBwdAcc with emit: P (fp32 NHWC) read ...
   float* out_f32;               // ... and P + Q written (may alias res_f32); nullptr = no emit
+  const float* add_f32;         // kBwdAcc with emit, HAN: the layer-attention gradient of the same tensor, added too; or nullptr
 };
 
 struct TrunkBwdArgs {
@@ -274,6 +275,10 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
               for (int c4 = 0; c4 < 8; ++c4) {
                 float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (valid) r = *reinterpret_cast<const float4*>(res + pix + h * 32 + c4 * 4);
+                if (valid && lay->add_f32 != nullptr) {
+                  const float4 a = *reinterpret_cast<const float4*>(lay->add_f32 + pix + h * 32 + c4 * 4);
+                  r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+                }
                 f[c4 * 4 + 0] += r.x; f[c4 * 4 + 1] += r.y; f[c4 * 4 + 2] += r.z; f[c4 * 4 + 3] += r.w;
                 if (valid)
                   *reinterpret_cast<float4*>(outf + pix + h * 32 + c4 * 4) =

@@ -79,10 +79,11 @@ def test_han_handler_cfg2_batch_vs_oracle(tmp_path):
     assert float(np.abs(out.numpy() - ref).max()) <= 1e-2
 
 
+@pytest.mark.parametrize('bwd', [1, 0], ids=['dataflow-backward', 'per-layer-backward'])
 @pytest.mark.parametrize('name', list(recipe.HCASES))
-def test_han_gradients_and_adam_steps_vs_reference_golden(golden_dir, name):
-    """HAN training: trunk forward in the dataflow kernel, backward through the per-layer kernels with the layer-attention
-    gradients injected between the groups; every gradient (convs, channel attention, csa.conv, both gammas) against the
+def test_han_gradients_and_adam_steps_vs_reference_golden(golden_dir, name, bwd):
+    """HAN training: trunk forward in the dataflow kernel, backward in the dataflow kernel or through the per-layer kernels,
+    with the layer-attention gradients injected at the group boundaries; every gradient (convs, channel attention, csa.conv, both gammas) against the
     reference autograd (<= 5 % of the tensor's max magnitude -- the layer attention's softmax over 10^3-sized energies
     amplifies the bf16 rounding of the stacked features a little beyond the 3 % the plain trunk needs -- and cosine
     >= 0.999), then 3 Adam steps against the reference's losses (<= 1 %)."""
@@ -91,6 +92,16 @@ def test_han_gradients_and_adam_steps_vs_reference_golden(golden_dir, name):
     gold = np.load(os.path.join(golden_dir, 'han.npz'))
     nb, scale, sd, x = recipe.hcase_tensors(name)
     y = recipe.make_input((x.shape[0], 3, x.shape[2] * scale, x.shape[3] * scale), recipe.HCASES[name][4] + 1000)
+    lib = _lib()
+    lib.rumpy_debug_set_trunk_bwd.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_trunk_bwd(bwd)
+    try:
+        _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam)
+    finally:
+        lib.rumpy_debug_set_trunk_bwd(1)
+
+
+def _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam):
     net = _han(nb, scale, sd).train()
     eng = net.native_engine()
     xt, yt = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
