@@ -158,6 +158,8 @@ int rumpy_net_set_backward_events(void* net, void* const* events /* cudaEvent_t[
  *   arch 1  Q-EDSR: replaces QEDSR (:496-556) / ParamResBlock (:463-493):
  *               ResBlock(x) = x + res_scale * conv2(relu(conv1(x))) * [q]
  *           params: head | final_body | per block: body.0, body.2, [attention_layer] | tail;  n_groups ignored.
+ *   arch 2  Q-HAN: replaces QHAN (:643-760): HAN (rumpy_net_create arch 2) whose residual groups are Q-RCAN's;
+ *           params: head | per group: final_body, per block: ... | body conv | csa | la | last_conv | last | tail.
  * q = sigmoid(FC2 act(FC1 metadata)) is the reference's 2-layer ParaCALayer (q_layer.py:5-45): num_metadata ->
  * q_hidden -> n_feats, act = ReLU iff q_relu.  block_has_q[i] != 0: block i owns one.  rumpy_net_forward(training)
  * / rumpy_net_backward also return the q-layer gradients ('modulate' combined with q-layers: inference only).  All multipliers are evaluated

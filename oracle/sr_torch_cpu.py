@@ -123,6 +123,49 @@ def qedsr_forward(sd, x, attributes, num_blocks, res_scale=0.1, scale=4):
     return _tail(sd, res, scale)
 
 
+def qhan_forward(sd, x, attributes, n_resblocks, scale=4, style='standard'):
+    """Q-HAN forward (reference attention_manipulators/architectures.py:733-760): HAN's attention tail on a trunk of
+    QResidualGroups (qrcan_forward's block)."""
+    def block(p, res):
+        u = _conv(sd, p + '.body.2', F.relu(_conv(sd, p + '.body.0', res)))
+        yv = F.adaptive_avg_pool2d(u, 1)
+        yv = torch.sigmoid(_conv(sd, p + '.final_body.conv_du.2', F.relu(_conv(sd, p + '.final_body.conv_du.0', yv))))
+        if style == 'modulate':
+            yv = yv * attributes
+        u = u * yv
+        if p + '.q_node.attribute_integrator.0.weight' in sd:
+            q = F.relu(_conv(sd, p + '.q_node.attribute_integrator.0', attributes))
+            u = u * torch.sigmoid(_conv(sd, p + '.q_node.attribute_integrator.2', q))
+        return u + res
+    x = _conv(sd, 'head.0', x)
+    res = x
+    stack = []
+    for g in range(10):
+        gin = res
+        for b in range(n_resblocks):
+            res = block(f'body.{g}.body.{b}', res)
+        res = _conv(sd, f'body.{g}.final_body', res) + gin
+        stack.insert(0, res)
+    res = _conv(sd, 'body.10', res)
+    stack.insert(0, res)
+    return _han_tail(sd, x, res, stack, scale)
+
+
+def _han_tail(sd, x, out1, stack, scale):
+    s = torch.stack(stack, 1)
+    B, L, C, H, W = s.shape
+    q = s.reshape(B, L, -1)
+    energy = torch.bmm(q, q.permute(0, 2, 1))
+    att = torch.softmax(energy.max(-1, keepdim=True)[0].expand_as(energy) - energy, dim=-1)
+    la = (sd['la.gamma'] * torch.bmm(att, q).reshape(B, L, C, H, W) + s).reshape(B, -1, H, W)
+    out2 = _conv(sd, 'last_conv', la)
+    a = torch.sigmoid(F.conv3d(out1.unsqueeze(1), sd['csa.conv.weight'], sd['csa.conv.bias'], padding=1))
+    a = (sd['csa.gamma'] * a).reshape(B, -1, H, W)
+    out1 = out1 * a + out1
+    res = _conv(sd, 'last', torch.cat([out1, out2], 1)) + x
+    return _tail(sd, res, scale)
+
+
 def han_forward(sd, x, n_resgroups=10, n_resblocks=20, scale=4):
     """HAN forward (reference advanced/architectures.py:368-392, HAN_blocks.py: LAM_Module.forward :17-41,
     CSAM_Module.forward :55-76)."""

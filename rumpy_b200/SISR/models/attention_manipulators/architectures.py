@@ -25,6 +25,7 @@ from rumpy_b200 import _lib
 from rumpy_b200 import engine as _engine
 from rumpy_b200.SISR.models.advanced import common
 from rumpy_b200.SISR.models.advanced.architectures import _NativeTrunk
+from rumpy_b200.SISR.models.advanced.HAN_blocks import CSAM_Module, LAM_Module
 from rumpy_b200.SISR.models.attention_manipulators.q_layer import ParaCALayer
 from rumpy_b200.trunk_function import trunk_apply
 
@@ -242,5 +243,65 @@ class QEDSR(_NativeTrunk):
 
     def _engine_kwargs(self):
         return _engine.ARCH_QEDSR, dict(self._cfg)
+
+    forward = QRCAN.forward
+
+
+class QHAN(_NativeTrunk):
+    """reference architectures.py:643-760: HAN whose residual groups are QResidualGroups (meta-attention inside the
+    RCABs), i.e. the Q-RCAN trunk followed by HAN's layer / channel-spatial attention.  Same supported options as QRCAN."""
+
+    def __init__(self, n_resgroups=10, n_resblocks=20, n_feats=64, reduction=16, num_metadata=0,
+                 scale=4, n_colors=3, res_scale=1.0, style='standard', include_pixel_attention=False,
+                 selective_meta_blocks=None,
+                 include_q_layer=False, num_q_layers_inner_residual=None, num_layers_in_q_layer=2,
+                 include_sft_layer=False, num_sft_layers_inner_residual=None,
+                 include_dgfmb_layer=False, num_dgfmb_layers_inner_residual=None, num_layers_in_dgfmb_layer=2,
+                 use_dgfmb_reduction=True, use_dgfmb_outer_reduction=False,
+                 include_da_conv_layer=False, num_da_conv_layers_inner_residual=None, **kwargs):
+        super(QHAN, self).__init__()
+        kernel_size = 3
+        act = nn.ReLU(True)
+        self.style = style
+        modules_head = [common.default_conv(n_colors, n_feats, kernel_size)]
+        modules_body = []
+        for index in range(n_resgroups):
+            on = selective_meta_blocks is None or bool(selective_meta_blocks[index])
+            modules_body.append(
+                QResidualGroup(common.default_conv, n_feats, kernel_size, reduction, style=style,
+                               num_metadata=num_metadata, pa=include_pixel_attention,
+                               q_layer=include_q_layer if on else False,
+                               # the reference passes dgfmb_layer=None when no selection is given (:676)
+                               dgfmb_layer=(include_dgfmb_layer if on else False) if selective_meta_blocks is not None else None,
+                               da_conv_layer=include_da_conv_layer if on else False,
+                               sft_layer=include_sft_layer if on else False,
+                               act=act, res_scale=res_scale, n_resblocks=n_resblocks,
+                               num_q_layers=num_q_layers_inner_residual,
+                               num_layers_in_q_layer=num_layers_in_q_layer,
+                               num_dgfmb_layers=num_dgfmb_layers_inner_residual,
+                               num_layers_in_dgfmb_layer=num_layers_in_dgfmb_layer,
+                               num_sft_layers=num_sft_layers_inner_residual,
+                               use_dgfmb_reduction=use_dgfmb_reduction,
+                               num_da_conv_layers=num_da_conv_layers_inner_residual))
+        modules_body.append(common.default_conv(n_feats, n_feats, kernel_size))
+        modules_tail = [
+            common.Upsampler(common.default_conv, scale, n_feats, act=False),
+            common.default_conv(n_feats, n_colors, kernel_size)]
+        self.head = nn.Sequential(*modules_head)
+        self.body = nn.Sequential(*modules_body)
+        self.csa = CSAM_Module(n_feats)
+        self.la = LAM_Module(n_feats)
+        self.last_conv = nn.Conv2d(n_feats * 11, n_feats, 3, 1, 1)
+        self.last = nn.Conv2d(n_feats * 2, n_feats, 3, 1, 1)
+        self.tail = nn.Sequential(*modules_tail)
+        groups = [m for m in self.body if isinstance(m, QResidualGroup)]
+        has_q = [bool(blk.q_layer) for grp in groups for blk in grp.body]
+        q_hidden = max([blk.q_node.layer_sizes[1] for grp in groups for blk in grp.body if blk.q_layer] + [1])
+        self._cfg = dict(n_feats=n_feats, n_groups=n_resgroups, n_blocks=n_resblocks, reduction=reduction,
+                         scale=scale, in_feats=n_colors, out_feats=n_colors, num_metadata=max(num_metadata, 1),
+                         q_hidden=q_hidden, block_has_q=has_q, modulate=(style == 'modulate'))
+
+    def _engine_kwargs(self):
+        return _engine.ARCH_QHAN, dict(self._cfg)
 
     forward = QRCAN.forward

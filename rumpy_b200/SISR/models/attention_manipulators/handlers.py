@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 from rumpy_b200.SISR.models.attention_manipulators import QModel
-from rumpy_b200.SISR.models.attention_manipulators.architectures import QEDSR, QRCAN
+from rumpy_b200.SISR.models.attention_manipulators.architectures import QEDSR, QHAN, QRCAN
 
 
 class QRCANHandler(QModel):
@@ -58,3 +58,18 @@ class QEDSRHandler(QModel):
         self.activate_device()
         self.model_name = 'qedsr'
         self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+
+
+class QHANHandler(QModel):
+    """reference handlers.py:183-199"""
+
+    def __init__(self, device, model_save_dir, eval_mode=False, lr=1e-4, scale=4, perceptual=None,
+                 scheduler=None, scheduler_params=None, **kwargs):
+        super(QHANHandler, self).__init__(device=device, model_save_dir=model_save_dir, eval_mode=eval_mode,
+                                          **kwargs)
+        self.net = QHAN(scale=scale, num_metadata=self.num_metadata, **kwargs)
+        self.colorspace = 'rgb'
+        self.im_input = 'unmodified'
+        self.activate_device()
+        self.training_setup(lr, scheduler, scheduler_params, perceptual, device)
+        self.model_name = 'qhan'

@@ -194,9 +194,11 @@ static int net_init(Net* n) {
   if (n->qrcan && n->arch == 0) {
     // QRCAN registers its modules in a different order than RCAN (attention_manipulators/architectures.py:313-433,
     // 154-196, 249-294): final_body | head | per group: final_body, per block: QCALayer, [q_node], conv1, conv2 | tail
+    // (QHAN, :643-760: head | groups | body conv -- the body conv is the last entry of `body` there, not a separate
+    // final_body registered first)
     int p = 0;
     auto set = [&](int ci) { n->convs[ci].w_idx = p++; n->convs[ci].b_idx = p++; };
-    set(n->conv_body);
+    if (!n->han) set(n->conv_body);
     set(0);
     const int B = n->n_blocks;
     for (int g = 0; g < n->n_groups; ++g) {
@@ -210,6 +212,7 @@ static int net_init(Net* n) {
         set(1 + g * (2 * B + 1) + 2 * b + 1);
       }
     }
+    if (n->han) set(n->conv_body);
     for (int s2 = 0; s2 < st; ++s2) set(n->conv_up0 + s2);
     set(n->conv_tail);
     n->n_params = p;
@@ -1075,7 +1078,13 @@ int rumpy_net_create_q(void** out, int arch, int n_feats, int n_groups, int n_bl
                        float res_scale, int in_feats, int out_feats, int num_metadata, int q_hidden,
                        const unsigned char* block_has_q, int modulate, int q_relu) {
   if (!out || !block_has_q) return set_error(RUMPY_ERR_ARG, "net_create_q: null pointer");
-  if (arch != 0 && arch != 1) return set_error(RUMPY_ERR_ARG, "net_create_q: arch %d", arch);
+  if (arch != 0 && arch != 1 && arch != 2) return set_error(RUMPY_ERR_ARG, "net_create_q: arch %d", arch);
+  const bool han = arch == 2;
+  if (han) {
+    if (n_groups != kLamLayers - 1)
+      return set_error(RUMPY_ERR_ARG, "net_create_q: Q-HAN needs %d residual groups", kLamLayers - 1);
+    arch = 0;
+  }
   if (arch == 0 && n_feats != 64) return set_error(RUMPY_ERR_ARG, "net_create_q: Q-RCAN n_feats=%d (64 supported)", n_feats);
   if (n_feats % 64 != 0 || n_feats <= 0 || n_feats > 256)
     return set_error(RUMPY_ERR_ARG, "net_create_q: n_feats=%d must be 64, 128, 192 or 256", n_feats);
@@ -1087,7 +1096,7 @@ int rumpy_net_create_q(void** out, int arch, int n_feats, int n_groups, int n_bl
     return set_error(RUMPY_ERR_ARG, "net_create_q: num_metadata=%d q_hidden=%d", num_metadata, q_hidden);
   if (arch == 1 && modulate) return set_error(RUMPY_ERR_ARG, "net_create_q: 'modulate' is a Q-RCAN style");
   Net* n = new Net();
-  n->arch = arch; n->qrcan = true;
+  n->arch = arch; n->qrcan = true; n->han = han;
   n->C = n_feats; n->n_groups = arch == 0 ? n_groups : 1; n->n_blocks = n_blocks; n->reduction = reduction;
   n->scale = scale; n->res_scale = arch == 0 ? 1.f : res_scale; n->in_feats = in_feats; n->out_feats = out_feats;
   n->u_f32 = 1;

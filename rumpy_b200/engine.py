@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 
-ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN, ARCH_QEDSR, ARCH_HAN = 0, 1, 2, 3, 4
+ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN, ARCH_QEDSR, ARCH_HAN, ARCH_QHAN = 0, 1, 2, 3, 4, 5
 
 _FLAT = {}   # id(first parameter) -> (flat fp32 buffer, weakref to first parameter): shared by engine and FusedAdam
 
@@ -56,11 +56,11 @@ class TrunkEngine:
         self.params = list(params)
         h = ctypes.c_void_p()
         self._meta = None
-        if arch in (ARCH_QRCAN, ARCH_QEDSR):
+        if arch in (ARCH_QRCAN, ARCH_QEDSR, ARCH_QHAN):
             flags = bytes(bytearray(int(bool(f)) for f in block_has_q))
-            if len(flags) != (n_groups * n_blocks if arch == ARCH_QRCAN else n_blocks):
+            if len(flags) != (n_blocks if arch == ARCH_QEDSR else n_groups * n_blocks):
                 raise ValueError('block_has_q needs one flag per RCAB / ResBlock')
-            _lib.call('rumpy_net_create_q', ctypes.byref(h), arch - ARCH_QRCAN, n_feats, n_groups, n_blocks, reduction,
+            _lib.call('rumpy_net_create_q', ctypes.byref(h), {ARCH_QRCAN: 0, ARCH_QEDSR: 1, ARCH_QHAN: 2}[arch], n_feats, n_groups, n_blocks, reduction,
                       scale, float(res_scale), in_feats, out_feats, int(num_metadata), int(q_hidden), flags,
                       int(bool(modulate)), int(bool(q_relu)))
         else:
@@ -154,7 +154,7 @@ class TrunkEngine:
     def set_metadata(self, metadata, N):
         """metadata: [N, M, 1, 1] or [N, M] tensor (what QRCAN.forward receives).  It is copied into a buffer the
         engine owns (static address: CUDA-graph replays see the new values)."""
-        if self.arch not in (ARCH_QRCAN, ARCH_QEDSR):
+        if self.arch not in (ARCH_QRCAN, ARCH_QEDSR, ARCH_QHAN):
             raise _lib.RumpyB200Error('set_metadata: not a meta-attention engine')
         if metadata is None:
             raise RuntimeError('Metadata needs to be specified for this network to run properly.')

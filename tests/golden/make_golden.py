@@ -307,6 +307,28 @@ def han_cases(arch_mod):
     return rec
 
 
+def qhan_case():
+    from rumpy.SISR.models.attention_manipulators import architectures as qarch
+    kw, has_q, sd, x, meta = recipe.qhcase_tensors()
+    net = qarch.QHAN(**kw)
+    assert list(net.state_dict().keys()) == list(sd.keys()), 'Q-HAN key order mismatch vs reference'
+    net.load_state_dict({k: t(v) for k, v in sd.items()}, strict=True)
+    attrs = t(meta).unsqueeze(2).unsqueeze(3)
+    rec = {}
+    net.eval()
+    with torch.no_grad():
+        rec['qhan::out'] = net(t(x), attrs).numpy()
+    y = recipe.make_input((x.shape[0], 3, x.shape[2] * kw['scale'], x.shape[3] * kw['scale']), recipe.QHCASE['xseed'] + 1000)
+    net.train()
+    loss = torch.nn.L1Loss()(net(t(x), attrs), t(y))
+    loss.backward()
+    rec['qhan::loss'] = np.float32(loss.item())
+    for k, p in net.named_parameters():
+        rec['qhan::gradsub::' + k] = recipe.subsample(p.grad.numpy()).copy()
+    print('qhan', rec['qhan::out'].shape, float(rec['qhan::loss']))
+    return rec
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     arch_mod, common = import_reference()
@@ -317,7 +339,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'blocks.npz'), **block_cases(arch_mod, common))
     np.savez_compressed(os.path.join(HERE, 'set5_edsr_baseline.npz'), **set5_case(arch_mod))
     np.savez_compressed(os.path.join(HERE, 'qrcan.npz'), **qrcan_cases())
-    np.savez_compressed(os.path.join(HERE, 'han.npz'), **han_cases(arch_mod))
+    np.savez_compressed(os.path.join(HERE, 'han.npz'), **{**han_cases(arch_mod), **qhan_case()})
     print('done')
 
 

@@ -243,3 +243,48 @@ def hcase_tensors(name):
     sd['csa.conv.weight'] = np.random.RandomState(wseed + 1).uniform(-0.5, 0.5, (1, 1, 3, 3, 3)).astype(np.float32)
     sd['csa.conv.bias'] = np.array([0.1], dtype=np.float32)
     return nb, scale, sd, make_input(shape, xseed)
+
+
+# ---------------------------------------------------------------------------- Q-HAN (HAN with Q-RCAN's residual groups)
+def qhan_spec(n_resblocks, num_metadata, has_q, n_feats=64, reduction=16, scale=4):
+    """state_dict layout of the reference's QHAN: head | per group: final_body, per block: attention, [q_node], convs |
+    body conv (last entry of `body`) | csa | la | last_conv | last | tail."""
+    spec = []
+    _conv_spec(spec, 'head.0', n_feats, 3, 3)
+    h1, h2 = q_layer_sizes(num_metadata, n_feats)
+    for g in range(10):
+        _conv_spec(spec, f'body.{g}.final_body', n_feats, n_feats, 3)
+        for b in range(n_resblocks):
+            p = f'body.{g}.body.{b}'
+            _conv_spec(spec, p + '.final_body.conv_du.0', n_feats // reduction, n_feats, 1)
+            _conv_spec(spec, p + '.final_body.conv_du.2', n_feats, n_feats // reduction, 1)
+            if has_q[g * n_resblocks + b]:
+                _conv_spec(spec, p + '.q_node.attribute_integrator.0', h1, num_metadata, 1)
+                _conv_spec(spec, p + '.q_node.attribute_integrator.2', h2, h1, 1)
+            _conv_spec(spec, p + '.body.0', n_feats, n_feats, 3)
+            _conv_spec(spec, p + '.body.2', n_feats, n_feats, 3)
+    _conv_spec(spec, 'body.10', n_feats, n_feats, 3)
+    spec += [('csa.gamma', (1,)), ('csa.conv.weight', (1, 1, 3, 3, 3)), ('csa.conv.bias', (1,)), ('la.gamma', (1,))]
+    _conv_spec(spec, 'last_conv', n_feats, n_feats * 11, 3)
+    _conv_spec(spec, 'last', n_feats, n_feats * 2, 3)
+    _tail_spec(spec, n_feats, 3, scale)
+    return spec
+
+
+QHCASE = dict(kw=dict(n_resblocks=1, scale=2, style='standard', num_metadata=10, include_q_layer=True,
+                      selective_meta_blocks=[True, False] * 5), shape=(2, 3, 10, 12), wseed=91, xseed=92)
+
+
+def qhcase_tensors():
+    kw = QHCASE['kw']
+    has_q = qrcan_has_q(10, kw['n_resblocks'], True, kw['selective_meta_blocks'], None)
+    spec = qhan_spec(kw['n_resblocks'], kw['num_metadata'], has_q, scale=kw['scale'])
+    fix = {'csa.gamma': 0.6, 'la.gamma': 0.4}
+    sd = make_weights([(k, (s if k not in fix else (1, 1, 1, 1))) for k, s in spec], QHCASE['wseed'])
+    for k, v in fix.items():
+        sd[k] = np.full((1,), v, dtype=np.float32)
+    sd['csa.conv.weight'] = np.random.RandomState(QHCASE['wseed'] + 1).uniform(-0.5, 0.5, (1, 1, 3, 3, 3)).astype(np.float32)
+    sd['csa.conv.bias'] = np.array([0.1], dtype=np.float32)
+    x = make_input(QHCASE['shape'], QHCASE['xseed'])
+    meta = make_input((QHCASE['shape'][0], kw['num_metadata']), QHCASE['xseed'] + 500)
+    return kw, has_q, sd, x, meta

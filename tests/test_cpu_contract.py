@@ -97,10 +97,18 @@ def test_han_state_dict_layout_matches_reference_spec():
     assert sum(p.numel() for p in HAN().parameters()) == 15592355 + 3 + 27 + (64 * 704 * 9 + 64) + (64 * 128 * 9 + 64)
 
 
+def test_qhan_state_dict_layout_matches_reference_spec():
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QHAN
+    kw, has_q, sd, x, meta = recipe.qhcase_tensors()
+    m = QHAN(**kw)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, v.shape) for k, v in sd.items()]
+    assert m._cfg['block_has_q'] == has_q
+
+
 def test_registry_and_legacy_switch():
     from rumpy_b200.shared_framework.models import available_models
     from rumpy_b200.shared_framework.models.base_architecture import BaseModel
-    assert set(available_models) == {'rcan', 'edsr', 'han', 'qrcan', 'qedsr'}
+    assert set(available_models) == {'rcan', 'edsr', 'han', 'qrcan', 'qedsr', 'qhan'}
     sd = {'model.module.head.0.weight': 1, 'model.body.0.bias': 2, 'tail.1.bias': 3}
     assert list(BaseModel.legacy_switch(sd)) == ['head.0.weight', 'body.0.bias', 'tail.1.bias']
     with pytest.raises(RuntimeError):

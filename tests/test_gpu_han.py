@@ -123,3 +123,48 @@ def _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam
     opt = FusedAdam(list(net.parameters()), lr=1e-4)
     losses = [train_native.train_step(net, opt, xt, yt)[0].item() for _ in range(3)]
     np.testing.assert_allclose(losses, gold[name + '::train_losses'], rtol=0.01)
+
+
+def test_qhan_forward_and_gradients_vs_reference_golden(golden_dir):
+    """Q-HAN (reference attention_manipulators/architectures.py:643-760): Q-RCAN's residual groups inside HAN -- the
+    native net is the same executor with both features switched on.  Forward in all trunk modes and every gradient
+    (q-layers, attention modules, convs) against the unmodified reference."""
+    from rumpy_b200 import train_native
+    from rumpy_b200.SISR.models.attention_manipulators.architectures import QHAN
+    gold = np.load(os.path.join(golden_dir, 'han.npz'))
+    kw, has_q, sd, x, meta = recipe.qhcase_tensors()
+    net = QHAN(**kw)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    net = net.to(DEV).eval()
+    xt = torch.from_numpy(x).to(DEV)
+    attrs = torch.from_numpy(meta).unsqueeze(2).unsqueeze(3).to(DEV)
+    lib = _lib()
+    try:
+        for mode, (trunk, cluster) in MODES.items():
+            lib.rumpy_debug_set_trunk(trunk)
+            lib.rumpy_debug_set_trunk_cluster(cluster)
+            eng = net.native_engine()
+            eng._ws.clear(); eng._graphs.clear(); eng._last_infer_shape = None
+            with torch.no_grad():
+                out = net(xt, attrs).cpu().numpy()
+            assert float(np.abs(out - gold['qhan::out']).max()) <= 1e-2, mode
+    finally:
+        lib.rumpy_debug_set_trunk(1)
+        lib.rumpy_debug_set_trunk_cluster(1)
+    net.train()
+    eng = net.native_engine()
+    y = recipe.make_input((x.shape[0], 3, x.shape[2] * kw['scale'], x.shape[3] * kw['scale']), recipe.QHCASE['xseed'] + 1000)
+    eng.set_metadata(attrs, x.shape[0])
+    o = eng.forward(xt, training=True)
+    loss, dy = train_native.l1_loss(o, torch.from_numpy(y).to(DEV), want_grad=True)
+    grads = eng.backward(xt, dy)
+    assert abs(loss.item() - float(gold['qhan::loss'])) <= 0.01 * float(gold['qhan::loss'])
+    n_q = 0
+    for (k, _), g in zip(net.named_parameters(), grads):
+        ref = gold['qhan::gradsub::' + k]
+        got = recipe.subsample(g.cpu().numpy())
+        scale_ = max(float(np.abs(ref).max()), 1e-12)
+        # + a 5e-8 floor: a nearly dead channel-attention block has gradients of 1e-7, where bf16 noise dominates
+        assert np.abs(got - ref).max() <= 0.05 * scale_ + 5e-8, (k, float(np.abs(got - ref).max()), scale_)
+        n_q += 'q_node' in k
+    assert n_q == 4 * sum(has_q)
