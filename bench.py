@@ -422,7 +422,8 @@ def glue_bench(device):
     """SURVEY 8(f) ranks 3 and 4 (csrc/glue.cu): eval glue (PSNR(Y), uint8 quantise) and the training-patch pipeline
     on the device, each against its HBM roofline and against the host (numpy) path it replaces."""
     import time as _t
-    from rumpy_b200.shared_framework.data import (DevicePairSet, PairSet, psnr_y, psnr_y_device, quantize_u8_device)
+    from rumpy_b200.shared_framework.data import (DevicePairSet, PairSet, bicubic_upsample_device, psnr_y, psnr_y_device,
+                                                  quantize_u8_device)
     pk = peaks()
     res = {}
 
@@ -462,6 +463,19 @@ def glue_bench(device):
     res['quantize_u8_frame_4320x7680'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6,
                                           'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'], 'algorithmic_bytes': nbytes}
     del fsr, fhr
+    # bicubic baseline (Pillow's 8-bit resampler restated on the device): 4 B read per LR + 4 B written per output element
+    lrb = torch.rand((BATCH, 3, LR_HW, LR_HW), device=device)
+    ms = timed(lambda: bicubic_upsample_device(lrb, SCALE))
+    nbytes = lrb.numel() * 4 * (1 + SCALE * SCALE)
+    res['bicubic_upsample'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6, 'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'],
+                               'algorithmic_bytes': nbytes}
+    flr = torch.rand((1, 3, 1080, 1920), device=device)
+    ms = timed(lambda: bicubic_upsample_device(flr, 4), 10)
+    nbytes = flr.numel() * 4 * 17
+    res['bicubic_upsample_frame_1080p_x4'] = {'ms': ms, 'gb_per_s': nbytes / ms * 1e-6,
+                                              'frac_of_hbm_peak': nbytes / ms * 1e-6 / pk['hbm'],
+                                              'algorithmic_bytes': nbytes}
+    del flr
     torch.cuda.empty_cache()
     t0 = _t.perf_counter()
     src, hrc = sr.cpu(), hr.cpu()

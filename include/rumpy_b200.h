@@ -211,13 +211,23 @@ int rumpy_adam_step(float* p, const float* g, float* m, float* v, long long n, f
  *   (replaces image_functions.py:287-362 random_matched_crop / random_flip_rotate + torchvision ToTensor per sample
  *   in data_handler.py:570-645).  lr_imgs / hr_imgs: DEVICE arrays of device pointers; geom: device int32 [N][6] =
  *   {image index, y, x, flags (1 hflip | 2 vflip | 4 transpose), lr_h, lr_w}; outputs fp32 [N][3][crop][crop] and
- *   [N][3][crop*scale][crop*scale]; bit-exact. */
+ *   [N][3][crop*scale][crop*scale]; bit-exact.
+ * rumpy_bicubic_upsample: the evaluation's bicubic baseline ("LR" row of the metrics, the image saved under
+ *   `bicubic/`), replaces EvalHub._low_res_prep (shared_framework/evaluation/standard_eval.py:240-275; also
+ *   image_functions.py:38-41 `upsample`): per image torchvision ToPILImage (x * 255, truncated to uint8) ->
+ *   PIL Image.resize((W*scale, H*scale), BICUBIC) (Pillow's 8-bit two-pass fixed-point resampler) -> ToTensor
+ *   (u8 / 255).  lr_nchw: device fp32 [N][C][H][W] in [0,1] (values outside are clamped; the reference's `.byte()` is
+ *   undefined there); out_nchw: device fp32 [N][C][H*scale][W*scale]; workspace: rumpy_bicubic_workspace(H, W, scale)
+ *   bytes, 16-byte aligned (the per-column / per-row tap tables); scale 2..8, N*C <= 65535; bit-exact with Pillow.  'lanczos' (standard_eval.py:252-253) is not provided. */
 long long rumpy_psnr_y_workspace(int N);
 int rumpy_psnr_y(const float* sr, const float* hr, float* psnr, void* workspace, int N, int H, int W, float max_value,
                  void* stream);
 int rumpy_quantize_u8(const float* src_nchw, unsigned char* dst_nhwc, int N, int C, int H, int W, void* stream);
 int rumpy_patch_batch(const unsigned char* const* lr_imgs, const unsigned char* const* hr_imgs, const int* geom,
                       float* lr_out, float* hr_out, int N, int crop, int scale, void* stream);
+long long rumpy_bicubic_workspace(int H, int W, int scale);
+int rumpy_bicubic_upsample(const float* lr_nchw, float* out_nchw, void* workspace, int N, int C, int H, int W, int scale,
+                           void* stream);
 
 #ifdef __cplusplus
 }

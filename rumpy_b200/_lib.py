@@ -37,6 +37,8 @@ SIGNATURES = {
     'rumpy_psnr_y': [_fp, _fp, _fp, _vp, _i, _i, _i, _f, _vp],
     'rumpy_quantize_u8': [_fp, _vp, _i, _i, _i, _i, _vp],
     'rumpy_patch_batch': [_vp, _vp, _vp, _fp, _fp, _i, _i, _i, _vp],
+    'rumpy_bicubic_workspace': [_i, _i, _i],
+    'rumpy_bicubic_upsample': [_fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     'rumpy_net_backward_chunks': [_vp, _vp, _i],
     'rumpy_net_set_backward_events': [_vp, _vp, _i],
     'rumpy_net_destroy': [_vp],
@@ -56,7 +58,7 @@ SIGNATURES = {
 }
 
 _LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace',
-             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace'}
+             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace', 'rumpy_bicubic_workspace'}
 
 _lib = None
 

@@ -6,10 +6,12 @@
 //                      image_tools/image_manipulation/image_functions.py:72-88, base_interface.py:208-222)
 //   rumpy_quantize_u8  clip(x*255, 0, 255).astype(uint8) (truncation), NCHW fp32 -> NHWC uint8 (what gets saved:
 //                      sr_tools/visualization.py:31-61)
+//   rumpy_bicubic_upsample  the "LR" (bicubic) baseline row of the evaluation: ToPILImage -> Image.resize(BICUBIC)
+//                      -> ToTensor, bit-exact with Pillow's 8-bit resampler (evaluation/standard_eval.py:240-275)
 //   rumpy_patch_batch  random crop + hflip / vflip / transpose + ToTensor for a whole batch of LR/HR pairs from
 //                      uint8 images resident in HBM (image_functions.py:287-362, sr_tools/data_handler.py:570-645)
 //
-// All three are integer / byte work bound by HBM: one pass, coalesced along the fastest output dimension, grids sized
+// All four are integer / byte work bound by HBM: one pass, coalesced along the fastest output dimension, grids sized
 // from the element count; reductions run in a fixed order (deterministic).
 #include <cuda_runtime.h>
 
@@ -146,6 +148,146 @@ __global__ void patch_batch_kernel(const uint8_t* const* __restrict__ lr_imgs, c
   for (int c = 0; c < 3; ++c) dst[size_t(c) * side * side] = __fdiv_rn(float(src[c]), 255.f);   // ToTensor()
 }
 
+// ---- bicubic baseline (standard_eval.py:240-275: ToPILImage -> Image.resize(BICUBIC) -> ToTensor) -----------------
+// Pillow's 8-bit resampler (src/libImaging/Resample.c, restated in oracle/pil_resample.py): horizontal pass, uint8
+// intermediate, vertical pass; per output index five taps at most, double-precision Keys weights (a = -0.5) clipped
+// to the image, re-normalised and rounded to 22-bit fixed point.
+//   bicubic_coeff_kernel  one thread per output column / row: the tap table {k[5], first tap, taps} (32 B) evaluated
+//                         with explicitly rounded double arithmetic (no FMA contraction: the same bits as the C code)
+//   bicubic_up_kernel     one CTA = one 32 x 128 output tile of one plane: its 160 table entries and the LR footprint
+//                         (<= 22 x 70 pixels for scale >= 2, quantised like to_pil_image) go to shared memory, both
+//                         passes run there (intermediate kept as one int per pixel so the vertical pass reads four
+//                         columns with one 16-byte load and no byte extraction), v/255 comes from a 256-entry table
+//                         of correctly rounded quotients, and the tile is written once with 16-byte stores.
+// Algorithmic bytes: 4 B read per LR element + 4 B written per output element.  The first version (coefficients
+// recomputed per tile, runtime divisions in the index math, __fdiv_rn per output) was issue-bound at 1.2 TB/s.
+constexpr int kBicTH = 32, kBicTW = 128;
+constexpr int kBicRows = kBicTH / 2 + 10, kBicCols = kBicTW / 2 + 8;   // footprint + 4 (zero-weight taps past the end)
+constexpr int kBicPrec = 22;
+
+struct __align__(16) BicTap {
+  int k[5];
+  int lo, n, pad;
+};
+
+__device__ __forceinline__ double pil_bicubic(double x) {
+  x = fabs(x);
+  if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.5, x), 2.5), x), x), 1.0);
+  if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), -0.5);
+  return 0.0;
+}
+
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc for output index xx of an upscaling pass (filterscale = 1)
+__device__ __forceinline__ BicTap pil_coeffs(int xx, int in_size, int out_size) {
+  const double scale = __ddiv_rn(double(in_size), double(out_size));
+  const double center = __dmul_rn(__dadd_rn(double(xx), 0.5), scale);
+  int lo = __double2int_rz(__dadd_rn(__dsub_rn(center, 2.0), 0.5));
+  int hi = __double2int_rz(__dadd_rn(__dadd_rn(center, 2.0), 0.5));
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > in_size ? in_size : hi;
+  const int n = hi - lo;
+  double w[5], ww = 0.0;
+#pragma unroll
+  for (int x = 0; x < 5; ++x) {
+    w[x] = x < n ? pil_bicubic(__dadd_rn(__dsub_rn(double(x + lo), center), 0.5)) : 0.0;
+    if (x < n) ww = __dadd_rn(ww, w[x]);
+  }
+  BicTap e;
+#pragma unroll
+  for (int x = 0; x < 5; ++x) {
+    const double v = ww != 0.0 ? __ddiv_rn(w[x], ww) : w[x];
+    const double f = __dmul_rn(v, double(1 << kBicPrec));
+    e.k[x] = x < n ? __double2int_rz(v < 0.0 ? __dadd_rn(-0.5, f) : __dadd_rn(0.5, f)) : 0;
+  }
+  e.lo = lo;
+  e.n = n;
+  e.pad = 0;
+  return e;
+}
+
+// table[0 .. OW) = column taps, table[OW .. OW + OH) = row taps
+__global__ void bicubic_coeff_kernel(BicTap* __restrict__ table, int H, int W, int scale) {
+  const int OW = W * scale, OH = H * scale;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < OW) table[i] = pil_coeffs(i, W, OW);
+  else if (i < OW + OH) table[i] = pil_coeffs(i - OW, H, OH);
+}
+
+__device__ __forceinline__ int bic_clip8(int acc) { return min(max(acc >> kBicPrec, 0), 255); }
+
+// grid (ceil(OW / 128), ceil(OH / 32), N * C), block 256
+__global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         const BicTap* __restrict__ table, int H, int W, int scale,
+                                                         int vec_store) {
+  __shared__ BicTap s_cx[kBicTW], s_cy[kBicTH];
+  __shared__ float s_lut[256];
+  __shared__ __align__(16) uint8_t s_lr[kBicRows][kBicCols];
+  __shared__ __align__(16) int s_tmp[kBicRows][kBicTW];
+  const int OH = H * scale, OW = W * scale;
+  const int ox0 = blockIdx.x * kBicTW, oy0 = blockIdx.y * kBicTH;
+  const int tw = min(kBicTW, OW - ox0), th = min(kBicTH, OH - oy0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < kBicTW) {
+    if (tid < tw) s_cx[tid] = table[ox0 + tid];
+  } else if (tid - kBicTW < th) {
+    s_cy[tid - kBicTW] = table[OW + oy0 + tid - kBicTW];
+  }
+  s_lut[tid] = __fdiv_rn(float(tid), 255.f);                                 // to_tensor: .div(255)
+  __syncthreads();
+  // bounds are non-decreasing in the output index: the tile's footprint is [lo of its first, lo + n of its last]
+  const int x_lo = s_cx[0].lo, cols = s_cx[tw - 1].lo + s_cx[tw - 1].n - x_lo;
+  const int y_lo = s_cy[0].lo, rows = s_cy[th - 1].lo + s_cy[th - 1].n - y_lo;
+  const float* sp = src + size_t(blockIdx.z) * H * W + size_t(y_lo) * W + x_lo;
+  for (int r = warp; r < rows; r += 8)
+    for (int c = lane; c < cols; c += 32)
+      s_lr[r][c] = uint8_t(quant1(sp[size_t(r) * W + c]));                   // to_pil_image: pic.mul(255).byte()
+  __syncthreads();
+  {                                                                          // horizontal pass: one column per thread
+    const int x = tid & (kBicTW - 1);
+    if (x < tw) {
+      const BicTap e = s_cx[x];
+      const int lo = e.lo - x_lo;
+      for (int r = tid >> 7; r < rows; r += 2) {
+        const uint8_t* p = &s_lr[r][lo];               // taps past e.n carry k = 0 (the row buffer is padded by 4)
+        const int acc = (1 << (kBicPrec - 1)) + int(p[0]) * e.k[0] + int(p[1]) * e.k[1] + int(p[2]) * e.k[2] +
+                        int(p[3]) * e.k[3] + int(p[4]) * e.k[4];
+        s_tmp[r][x] = bic_clip8(acc);
+      }
+    }
+  }
+  __syncthreads();
+  float* dp = dst + size_t(blockIdx.z) * OH * OW;
+  const int x4 = lane * 4;
+  if (x4 < tw) {
+#pragma unroll
+    for (int j = 0; j < kBicTH / 8; ++j) {                                   // vertical pass: four columns per thread
+      const int y = warp + 8 * j;
+      if (y >= th) break;
+      const BicTap e = s_cy[y];
+      const int lo = e.lo - y_lo;
+      int a0 = 1 << (kBicPrec - 1), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll
+      for (int t = 0; t < 5; ++t) {                    // rows past e.n carry k = 0 (s_tmp is padded by 4 rows)
+        const int4 p = *reinterpret_cast<const int4*>(&s_tmp[lo + t][x4]);
+        a0 += p.x * e.k[t];
+        a1 += p.y * e.k[t];
+        a2 += p.z * e.k[t];
+        a3 += p.w * e.k[t];
+      }
+      const float4 o = make_float4(s_lut[bic_clip8(a0)], s_lut[bic_clip8(a1)], s_lut[bic_clip8(a2)], s_lut[bic_clip8(a3)]);
+      float* d = dp + size_t(oy0 + y) * OW + ox0 + x4;
+      if (vec_store && x4 + 3 < tw) {
+        *reinterpret_cast<float4*>(d) = o;
+      } else {
+        d[0] = o.x;
+        if (x4 + 1 < tw) d[1] = o.y;
+        if (x4 + 2 < tw) d[2] = o.z;
+        if (x4 + 3 < tw) d[3] = o.w;
+      }
+    }
+  }
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -205,6 +347,31 @@ int rumpy_patch_batch(const unsigned char* const* lr_imgs, const unsigned char* 
   patch_batch_kernel<<<dim3((side * side + 255) / 256, N, 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lr_imgs, hr_imgs, geom, lr_out, hr_out, crop, scale);
   return check_launch("patch_batch");
+}
+
+long long rumpy_bicubic_workspace(int H, int W, int scale) {
+  if (H < 1 || W < 1 || scale < 2 || scale > 8) return -1LL;
+  return ((long long)H + W) * scale * (long long)sizeof(BicTap);
+}
+
+int rumpy_bicubic_upsample(const float* lr_nchw, float* out_nchw, void* workspace, int N, int C, int H, int W, int scale,
+                           void* stream) {
+  if (!lr_nchw || !out_nchw || !workspace) return set_error(RUMPY_ERR_ARG, "bicubic_upsample: null pointer");
+  if (N < 1 || C < 1 || H < 1 || W < 1 || scale < 2 || scale > 8 || (long long)N * C > 65535 ||
+      (long long)H * scale > 32LL * 65535 || (long long)H * scale * W * scale > 0x7fffffffLL ||
+      reinterpret_cast<uintptr_t>(workspace) % 16 != 0)
+    return set_error(RUMPY_ERR_ARG, "bicubic_upsample: N=%d C=%d H=%d W=%d scale=%d (scale 2..8, N*C <= 65535, "
+                     "16-byte aligned workspace)", N, C, H, W, scale);
+  if (int e = device_info(nullptr)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  BicTap* table = static_cast<BicTap*>(workspace);
+  const int OH = H * scale, OW = W * scale;
+  bicubic_coeff_kernel<<<(OW + OH + 127) / 128, 128, 0, s>>>(table, H, W, scale);
+  if (int e = check_launch("bicubic_coeff")) return e;
+  const int vec = OW % 4 == 0 && reinterpret_cast<uintptr_t>(out_nchw) % 16 == 0;
+  bicubic_up_kernel<<<dim3((OW + kBicTW - 1) / kBicTW, (OH + kBicTH - 1) / kBicTH, N * C), 256, 0, s>>>(
+      lr_nchw, out_nchw, table, H, W, scale, vec);
+  return check_launch("bicubic_upsample");
 }
 
 }  // extern "C"

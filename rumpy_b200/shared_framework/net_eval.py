@@ -30,7 +30,7 @@ def eval_run(config, **kw):
     import torch
     import torch.distributed as dist
     from rumpy_b200 import parallel
-    from rumpy_b200.shared_framework.data import PairSet, psnr_y_device, quantize_u8_device
+    from rumpy_b200.shared_framework.data import PairSet, bicubic_upsample_device, psnr_y_device, quantize_u8_device
     from rumpy_b200.shared_framework.models import define_model
 
     if config:
@@ -50,6 +50,21 @@ def eval_run(config, **kw):
         os.makedirs(out_dir, exist_ok=True)
     ds = PairSet({'lr': kw['lr_dir'], 'hr': kw['hr_dir']}, int(kw['scale']))
     rows = []
+    # the 'LR' row of the reference's metrics: bicubic baseline of every image (standard_eval.py:371-402), computed on
+    # the device with Pillow's own arithmetic (rumpy_bicubic_upsample) and scored next to it
+    dev = torch.device('cuda', local)
+    for idx in parallel.shard_round_robin(range(len(ds))):
+        name, lr, hr = ds.sample(idx)
+        t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0[0].record()
+        interp = bicubic_upsample_device(lr[None].to(dev), int(kw['scale']))
+        t0[1].record()
+        score = float(psnr_y_device(interp, hr[None].to(dev))[0])
+        rows.append({'image': name, 'model': 'LR', 'runtime': t0[0].elapsed_time(t0[1]) * 1e-3, 'PSNR': score})
+        if kw['save_im']:
+            from PIL import Image
+            os.makedirs(os.path.join(out_dir, 'bicubic'), exist_ok=True)
+            Image.fromarray(quantize_u8_device(interp)[0].cpu().numpy()).save(os.path.join(out_dir, 'bicubic', name))
     for exp, epoch in [tuple(me) for me in kw['model_and_epoch']]:
         cfg = toml.load(os.path.join(kw['model_loc'], exp, 'config.toml'))
         internal = dict(cfg['model'].get('internal_params', {}))

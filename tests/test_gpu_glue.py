@@ -91,9 +91,68 @@ def test_device_patch_pipeline_bit_exact_vs_host_pipeline(crop, scale, augment):
     assert n_batches == 6
 
 
+def test_bicubic_baseline_vs_reference_golden(golden_dir):
+    """`rumpy_bicubic_upsample` against the reference's own `EvalHub._low_res_prep` outputs
+    (evaluation/standard_eval.py:240-275; tests/golden/bicubic.npz): bit-exact."""
+    import os
+    from rumpy_b200.shared_framework.data import bicubic_upsample_device
+    gold = np.load(os.path.join(golden_dir, 'bicubic.npz'))
+    for name in [str(n) for n in gold['names']]:
+        got = bicubic_upsample_device(torch.from_numpy(gold[name + '::lr']).to(DEV), int(gold[name + '::scale']))
+        want = gold[name + '::up_u8'].astype(np.float32) / np.float32(255.0)
+        assert tuple(got.shape) == want.shape and np.array_equal(got.cpu().numpy(), want), name
+
+
+@pytest.mark.parametrize('shape,scale', [((1, 3, 1, 1), 2), ((2, 3, 37, 20), 4), ((1, 1, 5, 131), 3),
+                                         ((3, 3, 48, 48), 4), ((1, 3, 65, 33), 2), ((1, 2, 17, 19), 8),
+                                         ((16, 3, 64, 64), 4), ((1, 3, 9, 70), 5)])
+def test_bicubic_baseline_bit_exact_vs_oracle(shape, scale):
+    """Ragged shapes (tile edges in both directions, images smaller than the filter support), every scale, random and
+    saturated content (over- / undershoot clamps in both passes), k/255 grid points +- 1 ulp in the quantiser."""
+    from oracle import pil_resample
+    from rumpy_b200.shared_framework.data import bicubic_upsample_device
+    rs = np.random.RandomState(7)
+    x = rs.rand(*shape).astype(np.float32)
+    x[0, 0] = (rs.rand(*shape[2:]) > 0.5).astype(np.float32)
+    flat = x[-1, -1].reshape(-1)
+    grid = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    k = min(flat.size // 2, 256)
+    flat[:k] = np.minimum(np.nextafter(grid[:k], np.float32(2.0)), np.float32(1.0))
+    flat[k:2 * k] = np.maximum(np.nextafter(grid[:k], np.float32(-1.0)), np.float32(0.0))
+    want = pil_resample.low_res_prep(x, scale)
+    dev = torch.from_numpy(x).to(DEV)
+    got = bicubic_upsample_device(dev, scale)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert torch.equal(got, bicubic_upsample_device(dev, scale))          # deterministic
+
+
+def test_bicubic_baseline_1080p_frame_vs_pillow():
+    """BASELINE configs[4]'s frame (1080 x 1920 -> 4320 x 7680) against Pillow itself, plus the size-independent
+    properties: a constant image stays constant, and the result equals its own tiles' (any crop far from the border
+    depends only on the 5 x 5 LR neighbourhood)."""
+    from PIL import Image
+    from rumpy_b200.shared_framework.data import bicubic_upsample_device
+    rs = np.random.RandomState(9)
+    img = rs.randint(0, 256, size=(1080, 1920, 3)).astype(np.uint8)
+    x = torch.from_numpy(img.transpose(2, 0, 1).astype(np.float32) / np.float32(255.0))[None].to(DEV)
+    got = bicubic_upsample_device(x, 4)
+    want = np.asarray(Image.fromarray(img).resize((7680, 4320), resample=Image.BICUBIC)).transpose(2, 0, 1)
+    got_u8 = torch.round(got[0] * 255).to(torch.uint8).cpu().numpy()
+    assert np.array_equal(got_u8, want)
+    assert torch.equal(got[0].cpu(), torch.from_numpy(want.copy()).float().div(255))      # ToTensor (true division)
+    const = bicubic_upsample_device(torch.full((1, 3, 100, 100), 77 / 255, device=DEV), 4)
+    assert torch.equal(const, torch.full_like(const, 77 / 255))
+    crop = bicubic_upsample_device(x[:, :, 500:540, 900:960].contiguous(), 4)
+    assert torch.equal(crop[:, :, 16:-16, 16:-16], got[:, :, 2016:2144, 3616:3824])
+
+
 def test_glue_rejects_cpu_tensors():
     from rumpy_b200 import _lib
-    from rumpy_b200.shared_framework.data import psnr_y_device, quantize_u8_device
+    from rumpy_b200.shared_framework.data import bicubic_upsample_device, psnr_y_device, quantize_u8_device
+    with pytest.raises(_lib.RumpyB200Error):
+        bicubic_upsample_device(torch.rand(1, 3, 4, 4), 4)
+    with pytest.raises(_lib.RumpyB200Error):
+        bicubic_upsample_device(torch.rand(1, 3, 4, 4, device=DEV), 1)    # scale 2..8 only
     with pytest.raises(_lib.RumpyB200Error):
         quantize_u8_device(torch.rand(1, 3, 4, 4))
     with pytest.raises(_lib.RumpyB200Error):

@@ -215,7 +215,13 @@ def test_cli_train_then_eval(tmp_path):
                                         '--results_name', 'probe'])
     assert res.exit_code == 0, res.output + repr(res.exception)
     rows = (tmp_path / 'out' / 'probe' / 'standard_metrics' / 'individual_metrics.csv').read_text().splitlines()
-    assert rows[0] == 'image,model,runtime,PSNR' and len(rows) == 4
+    assert rows[0] == 'image,model,runtime,PSNR' and len(rows) == 7        # 3 x 'LR' (bicubic baseline) + 3 x model
+    from rumpy_b200.shared_framework.data import psnr_y
+    for row in [r.split(',') for r in rows[1:] if r.split(',')[1] == 'LR']:  # the reference's bicubic row, host-side
+        up = np.asarray(Image.open(lr_dir / row[0]).resize((144, 96), resample=Image.BICUBIC), dtype=np.float32) / 255
+        hr = np.asarray(Image.open(hr_dir / row[0]), dtype=np.float32) / 255
+        want = psnr_y(torch.from_numpy(up.transpose(2, 0, 1))[None], torch.from_numpy(hr.transpose(2, 0, 1))[None])
+        assert abs(float(row[3]) - want) <= 1e-3, (row, want)
 
 
 def test_backward_chunks_tile_the_gradient_buffer_and_events_fire():
