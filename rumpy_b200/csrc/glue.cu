@@ -152,15 +152,19 @@ __global__ void patch_batch_kernel(const uint8_t* const* __restrict__ lr_imgs, c
 // Pillow's 8-bit resampler (src/libImaging/Resample.c, restated in oracle/pil_resample.py): horizontal pass, uint8
 // intermediate, vertical pass; per output index five taps at most, double-precision Keys weights (a = -0.5) clipped
 // to the image, re-normalised and rounded to 22-bit fixed point.
-//   bicubic_coeff_kernel  one thread per output column / row: the tap table {k[5], first tap, taps} (32 B) evaluated
-//                         with explicitly rounded double arithmetic (no FMA contraction: the same bits as the C code)
-//   bicubic_up_kernel     one CTA = one 32 x 128 output tile of one plane: its 160 table entries and the LR footprint
+//   bicubic_coeff_kernel  one thread per output column / group of four output rows: the tap tables ({k[5], first
+//                         tap, taps} per column; dense 8 x 4 tap matrix per row group) evaluated with explicitly
+//                         rounded double arithmetic (no FMA contraction: the same bits as the C code)
+//   bicubic_up_kernel     one CTA = one 32 x 128 output tile of one plane: its table entries and the LR footprint
 //                         (<= 22 x 70 pixels for scale >= 2, quantised like to_pil_image) go to shared memory, both
 //                         passes run there (intermediate kept as one int per pixel so the vertical pass reads four
-//                         columns with one 16-byte load and no byte extraction), v/255 comes from a 256-entry table
-//                         of correctly rounded quotients, and the tile is written once with 16-byte stores.
-// Algorithmic bytes: 4 B read per LR element + 4 B written per output element.  The first version (coefficients
-// recomputed per tile, runtime divisions in the index math, __fdiv_rn per output) was issue-bound at 1.2 TB/s.
+//                         columns with one 16-byte load and no byte extraction; four consecutive output rows
+//                         share their <= 8 source rows through a dense tap matrix), v/255 is a correctly rounded
+//                         multiply + Newton step, and the tile is written once with 16-byte stores.
+// Algorithmic bytes: 4 B read per LR element + 4 B written per output element.  Versions (1080p x4 frame): taps
+// recomputed per tile, runtime divisions in the index math, __fdiv_rn per output: 0.32 ms, issue-bound; tap table +
+// per-row vertical pass + quotient table in shared memory: 0.187 ms, bound by shared-memory wavefronts (95 %); grouped
+// vertical pass + division-free quotient: 0.149 ms, issue-bound (84 %), a quarter of it in the footprint load loop.
 constexpr int kBicTH = 32, kBicTW = 128;
 constexpr int kBicRows = kBicTH / 2 + 10, kBicCols = kBicTW / 2 + 8;   // footprint + 4 (zero-weight taps past the end)
 constexpr int kBicPrec = 22;
@@ -205,42 +209,83 @@ __device__ __forceinline__ BicTap pil_coeffs(int xx, int in_size, int out_size) 
   return e;
 }
 
-// table[0 .. OW) = column taps, table[OW .. OW + OH) = row taps
-__global__ void bicubic_coeff_kernel(BicTap* __restrict__ table, int H, int W, int scale) {
-  const int OW = W * scale, OH = H * scale;
+// four consecutive output rows share <= 8 source rows: their taps as a dense [source row - base][row in group] matrix
+struct __align__(16) BicGroup {
+  int k[8][4];
+  int base, span, pad0, pad1;
+};
+__host__ __device__ inline size_t bic_groups_offset(int OW) { return size_t(OW) * sizeof(BicTap); }
+
+// workspace = OW column taps (BicTap), then ceil(OH / 4) row groups (BicGroup); one thread per entry
+__global__ void bicubic_coeff_kernel(void* __restrict__ workspace, int H, int W, int scale) {
+  const int OW = W * scale, OH = H * scale, G = (OH + 3) / 4;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < OW) table[i] = pil_coeffs(i, W, OW);
-  else if (i < OW + OH) table[i] = pil_coeffs(i - OW, H, OH);
+  if (i < OW) {
+    static_cast<BicTap*>(workspace)[i] = pil_coeffs(i, W, OW);
+  } else if (i < OW + G) {
+    const int g = i - OW;
+    BicGroup* out = reinterpret_cast<BicGroup*>(static_cast<char*>(workspace) + bic_groups_offset(OW)) + g;
+    for (int u = 0; u < 8; ++u)
+      for (int j = 0; j < 4; ++j) out->k[u][j] = 0;
+    int base = 0, last_lo = 0;
+    for (int j = 0; j < 4 && 4 * g + j < OH; ++j) {
+      const BicTap e = pil_coeffs(4 * g + j, H, OH);
+      if (j == 0) base = e.lo;
+      last_lo = e.lo;
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        if (e.lo - base + t < 8) out->k[e.lo - base + t][j] = e.k[t];      // always true for scale >= 2
+    }
+    out->base = base;
+    out->span = min(8, min(last_lo + 5, H) - base);                         // rows past H only carry zero taps
+    out->pad0 = out->pad1 = 0;
+  }
 }
 
-__device__ __forceinline__ int bic_clip8(int acc) { return min(max(acc >> kBicPrec, 0), 255); }
+__device__ __forceinline__ int bic_clip8(int acc) { return __vimin_s32_relu(acc >> kBicPrec, 255); }
+
+// v / 255.f, correctly rounded, for v in 0..255 without a division: 1/255 as a two-float constant, q = fma(v, hi,
+// v * lo).  Equal to __fdiv_rn for all 256 values (checked exhaustively in exact arithmetic, and the 1080p test
+// compares every byte value with ToTensor's true division).
+__device__ __forceinline__ float bic_div255(int v) {
+  const float f = float(v);
+  return __fmaf_rn(f, 0x1.010102p-8f, __fmul_rn(f, -0x1.fdfdfep-33f));
+}
 
 // grid (ceil(OW / 128), ceil(OH / 32), N * C), block 256
 __global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                         const BicTap* __restrict__ table, int H, int W, int scale,
+                                                         const void* __restrict__ workspace, int H, int W, int scale,
                                                          int vec_store) {
-  __shared__ BicTap s_cx[kBicTW], s_cy[kBicTH];
-  __shared__ float s_lut[256];
+  __shared__ BicTap s_cx[kBicTW];
+  __shared__ BicGroup s_cg[kBicTH / 4];
   __shared__ __align__(16) uint8_t s_lr[kBicRows][kBicCols];
   __shared__ __align__(16) int s_tmp[kBicRows][kBicTW];
   const int OH = H * scale, OW = W * scale;
   const int ox0 = blockIdx.x * kBicTW, oy0 = blockIdx.y * kBicTH;
   const int tw = min(kBicTW, OW - ox0), th = min(kBicTH, OH - oy0);
+  const int groups = (th + 3) >> 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < kBicTW) {
-    if (tid < tw) s_cx[tid] = table[ox0 + tid];
-  } else if (tid - kBicTW < th) {
-    s_cy[tid - kBicTW] = table[OW + oy0 + tid - kBicTW];
+    if (tid < tw) s_cx[tid] = static_cast<const BicTap*>(workspace)[ox0 + tid];
+  } else if (tid - kBicTW < groups * int(sizeof(BicGroup) / 16)) {
+    const int4* g = reinterpret_cast<const int4*>(static_cast<const char*>(workspace) + bic_groups_offset(OW) +
+                                                  size_t(blockIdx.y) * (kBicTH / 4) * sizeof(BicGroup));
+    reinterpret_cast<int4*>(s_cg)[tid - kBicTW] = g[tid - kBicTW];
   }
-  s_lut[tid] = __fdiv_rn(float(tid), 255.f);                                 // to_tensor: .div(255)
   __syncthreads();
-  // bounds are non-decreasing in the output index: the tile's footprint is [lo of its first, lo + n of its last]
+  // bounds are non-decreasing in the output index: the tile's footprint is [first tap of its first, end of its last]
   const int x_lo = s_cx[0].lo, cols = s_cx[tw - 1].lo + s_cx[tw - 1].n - x_lo;
-  const int y_lo = s_cy[0].lo, rows = s_cy[th - 1].lo + s_cy[th - 1].n - y_lo;
+  const int y_lo = s_cg[0].base, rows = s_cg[groups - 1].base + s_cg[groups - 1].span - y_lo;
   const float* sp = src + size_t(blockIdx.z) * H * W + size_t(y_lo) * W + x_lo;
-  for (int r = warp; r < rows; r += 8)
-    for (int c = lane; c < cols; c += 32)
-      s_lr[r][c] = uint8_t(quant1(sp[size_t(r) * W + c]));                   // to_pil_image: pic.mul(255).byte()
+  {                                                                          // LR footprint, quantised like
+    const int c = tid & 63;                                                  // to_pil_image: pic.mul(255).byte()
+    if (c < cols)
+      for (int r = tid >> 6; r < rows; r += 4) s_lr[r][c] = uint8_t(quant1(sp[r * W + c]));
+    if (cols > 64) {
+      const int c2 = 64 + (tid & 7), r = tid >> 3;
+      if (c2 < cols && r < rows) s_lr[r][c2] = uint8_t(quant1(sp[r * W + c2]));
+    }
+  }
   __syncthreads();
   {                                                                          // horizontal pass: one column per thread
     const int x = tid & (kBicTW - 1);
@@ -256,33 +301,48 @@ __global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict
     }
   }
   __syncthreads();
-  float* dp = dst + size_t(blockIdx.z) * OH * OW;
+  // vertical pass: warp = four consecutive output rows, lane = four columns; the source rows those output rows share
+  // are read once (one 16-byte load each) and hit the dense tap matrix of the group
   const int x4 = lane * 4;
-  if (x4 < tw) {
+  if (warp < groups && x4 < tw) {
+    const int base = s_cg[warp].base - y_lo, span = s_cg[warp].span;
+    int acc[4][4];
 #pragma unroll
-    for (int j = 0; j < kBicTH / 8; ++j) {                                   // vertical pass: four columns per thread
-      const int y = warp + 8 * j;
-      if (y >= th) break;
-      const BicTap e = s_cy[y];
-      const int lo = e.lo - y_lo;
-      int a0 = 1 << (kBicPrec - 1), a1 = a0, a2 = a0, a3 = a0;
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int t = 0; t < 5; ++t) {                    // rows past e.n carry k = 0 (s_tmp is padded by 4 rows)
-        const int4 p = *reinterpret_cast<const int4*>(&s_tmp[lo + t][x4]);
-        a0 += p.x * e.k[t];
-        a1 += p.y * e.k[t];
-        a2 += p.z * e.k[t];
-        a3 += p.w * e.k[t];
+      for (int c = 0; c < 4; ++c) acc[j][c] = 1 << (kBicPrec - 1);
+    const int4* prow = reinterpret_cast<const int4*>(&s_tmp[base][x4]);
+    const int4* krow = reinterpret_cast<const int4*>(&s_cg[warp].k[0][0]);
+#pragma unroll 2
+    for (int u = 0; u < span; ++u) {
+      const int4 p = prow[u * (kBicTW / 4)];
+      const int4 k = krow[u];
+      const int kk[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j][0] += p.x * kk[j];
+        acc[j][1] += p.y * kk[j];
+        acc[j][2] += p.z * kk[j];
+        acc[j][3] += p.w * kk[j];
       }
-      const float4 o = make_float4(s_lut[bic_clip8(a0)], s_lut[bic_clip8(a1)], s_lut[bic_clip8(a2)], s_lut[bic_clip8(a3)]);
-      float* d = dp + size_t(oy0 + y) * OW + ox0 + x4;
-      if (vec_store && x4 + 3 < tw) {
-        *reinterpret_cast<float4*>(d) = o;
-      } else {
-        d[0] = o.x;
-        if (x4 + 1 < tw) d[1] = o.y;
-        if (x4 + 2 < tw) d[2] = o.z;
-        if (x4 + 3 < tw) d[3] = o.w;
+    }
+    float* d = dst + size_t(blockIdx.z) * OH * OW + size_t(oy0 + 4 * warp) * OW + ox0 + x4;
+    const bool vec = vec_store && x4 + 3 < tw;
+    const int nrow = min(4, th - 4 * warp);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < nrow) {
+        const float4 o = make_float4(bic_div255(bic_clip8(acc[j][0])), bic_div255(bic_clip8(acc[j][1])),
+                                     bic_div255(bic_clip8(acc[j][2])), bic_div255(bic_clip8(acc[j][3])));
+        if (vec) {
+          *reinterpret_cast<float4*>(d) = o;
+        } else {
+          d[0] = o.x;
+          if (x4 + 1 < tw) d[1] = o.y;
+          if (x4 + 2 < tw) d[2] = o.z;
+          if (x4 + 3 < tw) d[3] = o.w;
+        }
+        d += OW;
       }
     }
   }
@@ -351,7 +411,7 @@ int rumpy_patch_batch(const unsigned char* const* lr_imgs, const unsigned char* 
 
 long long rumpy_bicubic_workspace(int H, int W, int scale) {
   if (H < 1 || W < 1 || scale < 2 || scale > 8) return -1LL;
-  return ((long long)H + W) * scale * (long long)sizeof(BicTap);
+  return (long long)W * scale * (long long)sizeof(BicTap) + ((long long)H * scale + 3) / 4 * (long long)sizeof(BicGroup);
 }
 
 int rumpy_bicubic_upsample(const float* lr_nchw, float* out_nchw, void* workspace, int N, int C, int H, int W, int scale,
@@ -364,13 +424,12 @@ int rumpy_bicubic_upsample(const float* lr_nchw, float* out_nchw, void* workspac
                      "16-byte aligned workspace)", N, C, H, W, scale);
   if (int e = device_info(nullptr)) return e;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  BicTap* table = static_cast<BicTap*>(workspace);
   const int OH = H * scale, OW = W * scale;
-  bicubic_coeff_kernel<<<(OW + OH + 127) / 128, 128, 0, s>>>(table, H, W, scale);
+  bicubic_coeff_kernel<<<(OW + (OH + 3) / 4 + 127) / 128, 128, 0, s>>>(workspace, H, W, scale);
   if (int e = check_launch("bicubic_coeff")) return e;
   const int vec = OW % 4 == 0 && reinterpret_cast<uintptr_t>(out_nchw) % 16 == 0;
   bicubic_up_kernel<<<dim3((OW + kBicTW - 1) / kBicTW, (OH + kBicTH - 1) / kBicTH, N * C), 256, 0, s>>>(
-      lr_nchw, out_nchw, table, H, W, scale, vec);
+      lr_nchw, out_nchw, workspace, H, W, scale, vec);
   return check_launch("bicubic_upsample");
 }
 
