@@ -155,8 +155,8 @@ __global__ void patch_batch_kernel(const uint8_t* const* __restrict__ lr_imgs, c
 //   bicubic_coeff_kernel  one thread per output column / group of four output rows: the tap tables ({k[5], first
 //                         tap, taps} per column; dense 8 x 4 tap matrix per row group) evaluated with explicitly
 //                         rounded double arithmetic (no FMA contraction: the same bits as the C code)
-//   bicubic_up_kernel     one CTA = one 32 x 128 output tile of one plane: its table entries and the LR footprint
-//                         (<= 22 x 70 pixels for scale >= 2, quantised like to_pil_image) go to shared memory, both
+//   bicubic_up_kernel     one CTA = one 64 x 128 output tile of one plane: its table entries and the LR footprint
+//                         (<= 38 x 70 pixels for scale >= 2, quantised like to_pil_image) go to shared memory, both
 //                         passes run there (intermediate kept as one int per pixel so the vertical pass reads four
 //                         columns with one 16-byte load and no byte extraction; four consecutive output rows
 //                         share their <= 8 source rows through a dense tap matrix), v/255 is a correctly rounded
@@ -164,8 +164,9 @@ __global__ void patch_batch_kernel(const uint8_t* const* __restrict__ lr_imgs, c
 // Algorithmic bytes: 4 B read per LR element + 4 B written per output element.  Versions (1080p x4 frame): taps
 // recomputed per tile, runtime divisions in the index math, __fdiv_rn per output: 0.32 ms, issue-bound; tap table +
 // per-row vertical pass + quotient table in shared memory: 0.187 ms, bound by shared-memory wavefronts (95 %); grouped
-// vertical pass + division-free quotient: 0.149 ms, issue-bound (84 %), a quarter of it in the footprint load loop.
-constexpr int kBicTH = 32, kBicTW = 128;
+// vertical pass + division-free quotient: 0.149 ms, issue-bound (84 %); row-group table, 32-row tiles: 0.147 ms with
+// 28 % of the instructions in per-CTA set-up, hence 64-row tiles.
+constexpr int kBicTH = 64, kBicTW = 128;
 constexpr int kBicRows = kBicTH / 2 + 10, kBicCols = kBicTW / 2 + 8;   // footprint + 4 (zero-weight taps past the end)
 constexpr int kBicPrec = 22;
 
@@ -252,8 +253,8 @@ __device__ __forceinline__ float bic_div255(int v) {
   return __fmaf_rn(f, 0x1.010102p-8f, __fmul_rn(f, -0x1.fdfdfep-33f));
 }
 
-// grid (ceil(OW / 128), ceil(OH / 32), N * C), block 256
-__global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict__ src, float* __restrict__ dst,
+// grid (ceil(OW / 128), ceil(OH / 64), N * C), block 256
+__global__ void __launch_bounds__(256, 6) bicubic_up_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                          const void* __restrict__ workspace, int H, int W, int scale,
                                                          int vec_store) {
   __shared__ BicTap s_cx[kBicTW];
@@ -267,10 +268,11 @@ __global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < kBicTW) {
     if (tid < tw) s_cx[tid] = static_cast<const BicTap*>(workspace)[ox0 + tid];
-  } else if (tid - kBicTW < groups * int(sizeof(BicGroup) / 16)) {
+  } else {
     const int4* g = reinterpret_cast<const int4*>(static_cast<const char*>(workspace) + bic_groups_offset(OW) +
                                                   size_t(blockIdx.y) * (kBicTH / 4) * sizeof(BicGroup));
-    reinterpret_cast<int4*>(s_cg)[tid - kBicTW] = g[tid - kBicTW];
+    for (int i = tid - kBicTW; i < groups * int(sizeof(BicGroup) / 16); i += 256 - kBicTW)
+      reinterpret_cast<int4*>(s_cg)[i] = g[i];
   }
   __syncthreads();
   // bounds are non-decreasing in the output index: the tile's footprint is [first tap of its first, end of its last]
@@ -282,8 +284,9 @@ __global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict
     if (c < cols)
       for (int r = tid >> 6; r < rows; r += 4) s_lr[r][c] = uint8_t(quant1(sp[r * W + c]));
     if (cols > 64) {
-      const int c2 = 64 + (tid & 7), r = tid >> 3;
-      if (c2 < cols && r < rows) s_lr[r][c2] = uint8_t(quant1(sp[r * W + c2]));
+      const int c2 = 64 + (tid & 7);
+      if (c2 < cols)
+        for (int r = tid >> 3; r < rows; r += 32) s_lr[r][c2] = uint8_t(quant1(sp[r * W + c2]));
     }
   }
   __syncthreads();
@@ -304,15 +307,16 @@ __global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict
   // vertical pass: warp = four consecutive output rows, lane = four columns; the source rows those output rows share
   // are read once (one 16-byte load each) and hit the dense tap matrix of the group
   const int x4 = lane * 4;
-  if (warp < groups && x4 < tw) {
-    const int base = s_cg[warp].base - y_lo, span = s_cg[warp].span;
+  if (x4 >= tw) return;
+  for (int g = warp; g < groups; g += 8) {
+    const int base = s_cg[g].base - y_lo, span = s_cg[g].span;
     int acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[j][c] = 1 << (kBicPrec - 1);
     const int4* prow = reinterpret_cast<const int4*>(&s_tmp[base][x4]);
-    const int4* krow = reinterpret_cast<const int4*>(&s_cg[warp].k[0][0]);
+    const int4* krow = reinterpret_cast<const int4*>(&s_cg[g].k[0][0]);
 #pragma unroll 2
     for (int u = 0; u < span; ++u) {
       const int4 p = prow[u * (kBicTW / 4)];
@@ -326,9 +330,9 @@ __global__ void __launch_bounds__(256) bicubic_up_kernel(const float* __restrict
         acc[j][3] += p.w * kk[j];
       }
     }
-    float* d = dst + size_t(blockIdx.z) * OH * OW + size_t(oy0 + 4 * warp) * OW + ox0 + x4;
+    float* d = dst + size_t(blockIdx.z) * OH * OW + size_t(oy0 + 4 * g) * OW + ox0 + x4;
     const bool vec = vec_store && x4 + 3 < tw;
-    const int nrow = min(4, th - 4 * warp);
+    const int nrow = min(4, th - 4 * g);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < nrow) {
@@ -418,7 +422,7 @@ int rumpy_bicubic_upsample(const float* lr_nchw, float* out_nchw, void* workspac
                            void* stream) {
   if (!lr_nchw || !out_nchw || !workspace) return set_error(RUMPY_ERR_ARG, "bicubic_upsample: null pointer");
   if (N < 1 || C < 1 || H < 1 || W < 1 || scale < 2 || scale > 8 || (long long)N * C > 65535 ||
-      (long long)H * scale > 32LL * 65535 || (long long)H * scale * W * scale > 0x7fffffffLL ||
+      (long long)H * scale > (long long)kBicTH * 65535 || (long long)H * scale * W * scale > 0x7fffffffLL ||
       reinterpret_cast<uintptr_t>(workspace) % 16 != 0)
     return set_error(RUMPY_ERR_ARG, "bicubic_upsample: N=%d C=%d H=%d W=%d scale=%d (scale 2..8, N*C <= 65535, "
                      "16-byte aligned workspace)", N, C, H, W, scale);

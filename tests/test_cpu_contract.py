@@ -47,6 +47,31 @@ def test_no_gpu_fails_loudly():
         RCAN(n_resgroups=1, n_resblocks=1)(torch.rand(1, 3, 8, 8))
 
 
+def test_glue_host_side_argument_checks_without_a_gpu():
+    """Host-only parts of the eval-glue ABI (no kernel runs): workspace sizes, argument validation, and the loud
+    failure of the compute entry points when there is no CUDA device."""
+    import ctypes
+    from rumpy_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip('librumpy_b200.so not built (run __graft_entry__.build())')
+    lib = _lib.load()
+    # bicubic: OW column tap entries of 32 B + ceil(OH / 4) row-group entries of 144 B; scale 2..8 only
+    assert lib.rumpy_bicubic_workspace(48, 48, 4) == 192 * 32 + 48 * 144
+    assert lib.rumpy_bicubic_workspace(5, 7, 3) == 21 * 32 + 4 * 144
+    assert lib.rumpy_bicubic_workspace(48, 48, 1) < 0 and lib.rumpy_bicubic_workspace(48, 48, 9) < 0
+    assert lib.rumpy_bicubic_workspace(0, 48, 4) < 0
+    assert lib.rumpy_psnr_y_workspace(3) > 0 and lib.rumpy_psnr_y_workspace(0) < 0
+    assert lib.rumpy_bicubic_upsample(None, None, None, 1, 3, 8, 8, 4, None) != 0          # null pointers
+    assert b'bicubic_upsample' in lib.rumpy_last_error()
+    if not torch.cuda.is_available():
+        buf = (ctypes.c_float * 16)()
+        p = ctypes.cast(buf, ctypes.POINTER(ctypes.c_float))
+        assert lib.rumpy_bicubic_upsample(p, p, ctypes.cast(buf, ctypes.c_void_p), 1, 1, 2, 2, 2, None) != 0
+        from rumpy_b200.shared_framework.data import bicubic_upsample_device
+        with pytest.raises(_lib.RumpyB200Error):
+            bicubic_upsample_device(torch.rand(1, 3, 4, 4), 4)
+
+
 def test_state_dict_layout_matches_reference_spec():
     from rumpy_b200.SISR.models.advanced.architectures import RCAN, EDSR
     m = RCAN()
