@@ -286,3 +286,30 @@ class BaseModel(nn.Module):
 
     def get_learning_rate(self):
         return self.optimizer.param_groups[0]['lr']
+
+    # direction of improvement per logged metric (reference shared_framework/configuration/constants.py:26-34)
+    METRIC_BEST_VAL = {'val-loss': 'lower', 'train-loss': 'lower', 'regression-loss': 'lower',
+                       'contrastive-loss': 'lower', 'val-PSNR': 'higher', 'val-SSIM': 'higher', 'val-LPIPS': 'lower'}
+
+    @staticmethod
+    def best_model_selection_criteria(log_dir=None, log_file='summary.csv', model_metadata=None, stats=None,
+                                      stats_dir=None, base_metric='val-PSNR'):
+        """Epoch (row index of summary.csv) with the best `base_metric` (reference base_architecture.py:601-612 ->
+        sr_tools/helper_functions.py:29-40: `idxmax` / `idxmin`, i.e. the FIRST best row).  `stats` is a pandas
+        DataFrame or a dict of lists (the two forms `load_statistics` returns, sr_tools/stats.py:117-122); when only a
+        directory is given the CSV is read from it."""
+        if stats is None:
+            folder = stats_dir if stats_dir else log_dir
+            if folder is None:
+                raise RuntimeError('best_model_selection_criteria: neither stats nor a log directory given')
+            import csv
+            with open(os.path.join(folder, log_file), newline='') as f:
+                rows = list(csv.DictReader(f))
+            stats = {k: [float(r[k]) for r in rows] for k in rows[0]} if rows else {}
+        if base_metric not in BaseModel.METRIC_BEST_VAL:
+            raise KeyError(base_metric)
+        column = [float(v) for v in list(stats[base_metric])]
+        if not column:
+            raise RuntimeError(f'best_model_selection_criteria: no rows for {base_metric}')
+        arr = np.asarray(column, dtype=np.float64)
+        return int(np.nanargmax(arr) if BaseModel.METRIC_BEST_VAL[base_metric] == 'higher' else np.nanargmin(arr))

@@ -72,6 +72,13 @@ def eval_run(config, **kw):
         internal.pop('lr', None)
         model = define_model(cfg['model']['name'], model_save_dir=os.path.join(kw['model_loc'], exp, 'saved_models'),
                              device=local, eval_mode=True, **internal)
+        if epoch in ('best', 'last'):       # reference base_interface.py:86-95: resolved from the training summary
+            logs = os.path.join(kw['model_loc'], exp, 'result_outputs')
+            if epoch == 'best':
+                epoch = model.best_model_selection_criteria(log_dir=logs, base_metric='val-PSNR')
+            else:
+                with open(os.path.join(logs, 'summary.csv')) as f:
+                    epoch = sum(1 for line in f if line.strip()) - 2
         model.load_model('train_model', epoch, legacy=model.legacy_load)
         for idx in parallel.shard_round_robin(range(len(ds))):
             name, lr, hr = ds.sample(idx)

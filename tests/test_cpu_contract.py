@@ -72,6 +72,22 @@ def test_glue_host_side_argument_checks_without_a_gpu():
             bicubic_upsample_device(torch.rand(1, 3, 4, 4), 4)
 
 
+def test_best_model_selection_criteria(tmp_path):
+    """`BaseModel.best_model_selection_criteria` (reference base_architecture.py:601-612, helper_functions.py:29-40):
+    first row with the highest val-PSNR / lowest loss, from a DataFrame, a dict of lists or the summary.csv itself."""
+    import pandas as pd
+    from rumpy_b200.shared_framework.models.base_architecture import BaseModel
+    stats = {'epoch': [0, 1, 2, 3], 'train-loss': [0.5, 0.2, 0.3, 0.2], 'val-PSNR': [20.0, 27.5, 27.5, 25.0]}
+    assert BaseModel.best_model_selection_criteria(stats=stats) == 1
+    assert BaseModel.best_model_selection_criteria(stats=pd.DataFrame(stats), base_metric='train-loss') == 1
+    assert BaseModel.best_model_selection_criteria(stats=pd.DataFrame(stats)) == int(pd.DataFrame(stats)['val-PSNR'].idxmax())
+    pd.DataFrame(stats).to_csv(tmp_path / 'summary.csv', index=False)
+    assert BaseModel.best_model_selection_criteria(log_dir=str(tmp_path)) == 1
+    assert BaseModel.best_model_selection_criteria(stats_dir=str(tmp_path), base_metric='train-loss') == 1
+    with pytest.raises(KeyError):
+        BaseModel.best_model_selection_criteria(stats=stats, base_metric='nonsense')
+
+
 def test_state_dict_layout_matches_reference_spec():
     from rumpy_b200.SISR.models.advanced.architectures import RCAN, EDSR
     m = RCAN()
