@@ -218,7 +218,9 @@ int rumpy_adam_step(float* p, const float* g, float* m, float* v, long long n, f
  *   PIL Image.resize((W*scale, H*scale), BICUBIC) (Pillow's 8-bit two-pass fixed-point resampler) -> ToTensor
  *   (u8 / 255).  lr_nchw: device fp32 [N][C][H][W] in [0,1] (values outside are clamped; the reference's `.byte()` is
  *   undefined there); out_nchw: device fp32 [N][C][H*scale][W*scale]; workspace: rumpy_bicubic_workspace(H, W, scale)
- *   bytes, 16-byte aligned (the per-column / per-row tap tables); scale 2..8, N*C <= 65535; bit-exact with Pillow.  'lanczos' (standard_eval.py:252-253) is not provided. */
+ *   bytes, 16-byte aligned (tap tables: one entry per output column and per group of four output rows, written by
+ *   the call itself); scale 2..8, N*C <= 65535; bit-exact with Pillow.  'lanczos' (standard_eval.py:252-253) is not
+ *   provided. */
 long long rumpy_psnr_y_workspace(int N);
 int rumpy_psnr_y(const float* sr, const float* hr, float* psnr, void* workspace, int N, int H, int W, float max_value,
                  void* stream);
