@@ -32,12 +32,30 @@ def bicubic_filter(x):
     return np.where(x < 1.0, near, np.where(x < 2.0, far, 0.0))
 
 
-def precompute_coeffs(in_size, out_size):
+def lanczos_filter(x):
+    """Resample.c `lanczos_filter` (a = 3): sinc(x) * sinc(x / 3) on [-3, 3), libm `sin` element by element (numpy's
+    vectorised sin is not guaranteed to round like libm's)."""
+    import math
+
+    def sinc(v):
+        if v == 0.0:
+            return 1.0
+        v = v * math.pi
+        return math.sin(v) / v
+    x = np.atleast_1d(np.asarray(x, dtype=np.float64))
+    return np.array([sinc(float(v)) * sinc(float(v) / 3) if -3.0 <= v < 3.0 else 0.0 for v in x], dtype=np.float64)
+
+
+FILTERS = {'bicubic': (bicubic_filter, SUPPORT), 'lanczos': (lanczos_filter, 3.0)}
+
+
+def precompute_coeffs(in_size, out_size, resample='bicubic'):
     """Resample.c `precompute_coeffs` + `normalize_coeffs_8bpc` for the whole-image box.
     Returns (xmin[out], count[out], kk[out][ksize] int32)."""
+    filter_fn, filter_support = FILTERS[resample]
     scale = float(in_size) / out_size
     filterscale = max(scale, 1.0)
-    support = SUPPORT * filterscale
+    support = filter_support * filterscale
     ksize = int(np.ceil(support)) * 2 + 1
     ss = 1.0 / filterscale
     xmin = np.zeros(out_size, dtype=np.int64)
@@ -48,7 +66,7 @@ def precompute_coeffs(in_size, out_size):
         lo = max(int(center - support + 0.5), 0)           # C cast: truncation towards zero
         hi = min(int(center + support + 0.5), in_size)
         n = hi - lo
-        w = bicubic_filter((np.arange(n, dtype=np.float64) + lo - center + 0.5) * ss)
+        w = filter_fn((np.arange(n, dtype=np.float64) + lo - center + 0.5) * ss)
         ww = 0.0
         for v in w:                                        # running sum in tap order, like the C loop
             ww += float(v)
@@ -60,22 +78,23 @@ def precompute_coeffs(in_size, out_size):
     return xmin, count, kk
 
 
-def _pass_last_axis(img, out_size):
+def _pass_last_axis(img, out_size, resample='bicubic'):
     """One resampling pass along the last axis of a uint8 array."""
-    xmin, count, kk = precompute_coeffs(img.shape[-1], out_size)
+    xmin, count, kk = precompute_coeffs(img.shape[-1], out_size, resample)
     ksize = kk.shape[1]
     idx = np.minimum(xmin[:, None] + np.arange(ksize)[None, :], img.shape[-1] - 1)    # taps past `count` have k = 0
     acc = (img[..., idx].astype(np.int64) * kk.astype(np.int64)).sum(-1) + (1 << (PRECISION_BITS - 1))
     return np.clip(acc >> PRECISION_BITS, 0, 255).astype(np.uint8)
 
 
-def resize_u8(img, out_h, out_w):
-    """`Image.resize((out_w, out_h), Image.BICUBIC)` for uint8 arrays [..., H, W] (each band on its own)."""
+def resize_u8(img, out_h, out_w, resample='bicubic'):
+    """`Image.resize((out_w, out_h), Image.BICUBIC | Image.LANCZOS)` for uint8 arrays [..., H, W] (each band on its
+    own)."""
     img = np.asarray(img, dtype=np.uint8)
     if out_w != img.shape[-1]:
-        img = _pass_last_axis(img, out_w)                                  # horizontal pass first
+        img = _pass_last_axis(img, out_w, resample)                        # horizontal pass first
     if out_h != img.shape[-2]:
-        img = np.swapaxes(_pass_last_axis(np.swapaxes(img, -1, -2), out_h), -1, -2)
+        img = np.swapaxes(_pass_last_axis(np.swapaxes(img, -1, -2), out_h, resample), -1, -2)
     return img
 
 
@@ -84,8 +103,9 @@ def to_u8(x):
     return (np.asarray(x, dtype=np.float32) * np.float32(255.0)).astype(np.uint8)
 
 
-def low_res_prep(lr, scale):
-    """`EvalHub._low_res_prep(lr, upsample_function='bicubic')`: N x C x H x W fp32 in [0,1] -> N x C x sH x sW."""
+def low_res_prep(lr, scale, upsample_function='bicubic'):
+    """`EvalHub._low_res_prep(lr, upsample_function=...)`: N x C x H x W fp32 in [0,1] -> N x C x sH x sW.  'lanczos'
+    (standard_eval.py:252-253) is restated here ahead of a device kernel for it (the product provides bicubic only)."""
     lr = np.asarray(lr, dtype=np.float32)
-    up = resize_u8(to_u8(lr), lr.shape[-2] * scale, lr.shape[-1] * scale)
+    up = resize_u8(to_u8(lr), lr.shape[-2] * scale, lr.shape[-1] * scale, upsample_function)
     return up.astype(np.float32) / np.float32(255.0)
