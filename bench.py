@@ -238,7 +238,9 @@ def trunk_kernel_roofline(eng, x_dev, flush, pk):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get('trunk_dram_bytes_per_launch')
     name = {1: 'trunk_pipe_kernel (persistent dataflow, epoch flags)',
-            2: 'trunk_cluster_kernel (one 6-CTA cluster per image, DSMEM halo exchange)'}[mode]
+            2: 'trunk_cluster_kernel (one 6-CTA cluster per image, DSMEM halo exchange)',
+            3: 'trunk_band_kernel (role-swapped: weights in TMEM, N = 144 pixels per MMA; one 6-CTA cluster of row '
+               'bands per image, DSMEM halo rows)'}[mode]
     return {'bound': 'tensor', 'kernel': name + f': {n_convs} fused conv3x3 64->64 layers + CA + skips, 16x48x48',
             'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
             'traffic': traffic, 'us_per_launch': best * 1e6, 'flops_per_launch': flops,

@@ -89,6 +89,8 @@ def load():
     lib.rumpy_debug_set_trunk_events.argtypes = [_vp, _vp]
     if os.environ.get('RUMPY_B200_TRUNK') == '0':     # debug switch: one kernel per layer instead of the trunk kernels
         lib.rumpy_debug_set_trunk(0)
+    if os.environ.get('RUMPY_B200_BAND') == '1':      # opt-in experiment: role-swapped band kernel (trunk_band.cuh)
+        lib.rumpy_debug_set_trunk_band(1)
     if os.environ.get('RUMPY_B200_CLUSTER') == '0':   # debug switch: no cluster-per-image kernel (dataflow kernel only)
         lib.rumpy_debug_set_trunk_cluster(0)
     if os.environ.get('RUMPY_B200_CLUSTER_GROUPS') in ('2', '4'):   # epilogue groups of the cluster kernel

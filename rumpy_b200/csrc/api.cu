@@ -105,10 +105,10 @@ int make_map_weights(CUtensorMap* m, const void* base, int k, int rows, int bn, 
   return RUMPY_OK;
 }
 
-int make_map_weight_layers(CUtensorMap* m, const void* base, int n_layers) {
+int make_map_weight_layers(CUtensorMap* m, const void* base, int n_layers, int box_taps) {
   const cuuint64_t dims[4] = {64, 64, 9, cuuint64_t(n_layers)};
   const cuuint64_t strides[3] = {128, 64 * 128, 9 * 64 * 128};
-  const cuuint32_t box[4] = {64, 64, 3, 1};
+  const cuuint32_t box[4] = {64, 64, cuuint32_t(box_taps), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "weights not 16B aligned");
   CUresult r = get_encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,

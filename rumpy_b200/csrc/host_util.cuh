@@ -11,6 +11,7 @@
 #include "conv3x3_ca.cuh"
 #include "trunk_pipe.cuh"
 #include "trunk_cluster.cuh"
+#include "trunk_band.cuh"
 #include "trunk_bwd.cuh"
 #include <vector>
 
@@ -116,7 +117,7 @@ int conv_plan_launch(const ConvPlan& p, cudaStream_t s);
 
 // ------------------------------------------------------------------ persistent trunk kernel (trunk_pipe.cuh)
 // packed weights of `n_layers` consecutive 64->64 convs ([layer][tap][64][64] bf16) -> 4-D map, box = one kx third
-int make_map_weight_layers(CUtensorMap* m, const void* base, int n_layers);
+int make_map_weight_layers(CUtensorMap* m, const void* base, int n_layers, int box_taps = 3);
 
 struct TrunkLayerParams { int bias, w1, b1, w2, b2; };   // indices into the caller's parameter list (-1: none)
 
@@ -141,6 +142,11 @@ struct TrunkPlan {
   int cluster_size = 0;
   int cluster_groups = 2;   // epilogue groups (template parameter of the cluster kernel) the plan was built for
   size_t cluster_smem = 0;
+  // role-swapped band kernel (trunk_band.cuh): weights in tensor memory, one cluster of row bands per image
+  bool band = false;
+  BandArgs bargs;
+  CUtensorMap w_tap_map;    // same packed weights, box = one tap (8 KB)
+  size_t band_smem = 0;
 };
 // backward program of the body (trunk_bwd.cuh)
 struct TrunkBwdLayerParams { int w1, w2; };              // parameter indices of a kBwdCA layer (-1: none)

@@ -38,6 +38,7 @@ enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK
 
 extern int g_use_fused_ca;
 extern int g_use_cluster;
+extern int g_use_band;
 int g_use_trunk_bwd = 1;   // backward of the RCAN body in the persistent dataflow kernel (trunk_bwd.cuh)
 int g_use_trunk = 1;   // whole 64-channel body in the persistent dataflow kernel (trunk_pipe.cuh) when the shape fits
 
@@ -1022,12 +1023,12 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
 
 static int ensure_plan(Net* n, const void* packed, void* workspace, int N, int H, int W, int training) {
   if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
-      n->p_training != training || n->p_trunk != g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd) {
+      n->p_training != training || n->p_trunk != g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd + 8 * g_use_band) {
     size_t bytes = 0;
     n->plan_packed = nullptr;
     if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
     n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
-    n->p_trunk = g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd;
+    n->p_trunk = g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd + 8 * g_use_band;
   }
   return RUMPY_OK;
 }
@@ -1143,7 +1144,7 @@ int rumpy_net_num_launches(void* net) { return net ? int(static_cast<Net*>(net)-
 int rumpy_net_trunk_mode(void* net) {
   if (!net) return -1;
   Net* n = static_cast<Net*>(net);
-  return n->trunk ? (n->trunk->cluster ? 2 : 1) : 0;
+  return n->trunk ? (n->trunk->band ? 3 : (n->trunk->cluster ? 2 : 1)) : 0;
 }
 
 /* kernels enqueued by one backward of the cached plan (0 when the plan is inference-only) */

@@ -301,6 +301,13 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ register re-partitioning between warpgroups
+// (all four warps of a warpgroup must execute the same instruction; inc blocks until the registers are free)
+template <uint32_t kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <uint32_t kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor (sm_100 format, version field = 1).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4

@@ -8,7 +8,9 @@ namespace rb {
 extern long long* g_debug_timeline;
 int g_use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
 int g_cluster_groups = 2;     // epilogue groups of the cluster kernel (2 or 4)
+int g_use_band = 0;           // role-swapped band kernel (trunk_band.cuh): opt-in (RUMPY_B200_BAND=1), slower than the cluster kernel so far
 constexpr int kClusterMaxDyn = 227 * 1024 - 8192;
+constexpr int kBandMaxDyn = 227 * 1024 - 2048;   // the band kernel has < 2 KB of static shared memory
 int g_trunk_sync_mode = 8;   // release store of the tile epoch (needed: see DESIGN.md trunk protocol)
 cudaEvent_t g_trunk_ev0 = nullptr, g_trunk_ev1 = nullptr;   // optional: recorded around the trunk kernel (bench)
 int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
@@ -123,6 +125,59 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         for (const TrunkLayer& l : plan->layers) c.n_ca += l.kind == kTrunkCA ? 1 : 0;
       }
   }
+  // ---- role-swapped band kernel: one cluster of row bands per image, weights in tensor memory.  Picks the
+  // largest cluster (most SMs) whose bands fit (<= 3 chunks of <= 143 linear pixels, shared memory) with all N
+  // clusters co-resident.
+  plan->band = false;
+  if (g_use_band && allow_cluster && W + 1 >= 4) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      if (cudaFuncSetAttribute(trunk_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandMaxDyn) != cudaSuccess)
+        return set_error(RUMPY_ERR_CUDA, "trunk_band cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+      attr_set = true;
+    }
+    const int P = W + 1;
+    for (int C = kBandMaxCluster; C >= 1 && !plan->band; --C) {
+      const int R = (H + C - 1) / C;
+      if ((C - 1) * R >= H) continue;                       // every CTA owns at least one row
+      const int count = R * P - 1;                          // linear output pixels of a full band
+      const int n_chunks = (count + kBandNQMax - 1) / kBandNQMax;
+      if (n_chunks > kBandMaxChunks) continue;
+      const size_t smem = band_smem_bytes(R, P, C);
+      if (smem > size_t(kBandMaxDyn)) continue;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(kBandThreads); cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int active = 0;
+      if (cudaOccupancyMaxActiveClusters(&active, trunk_band_kernel, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        continue;
+      }
+      if (active < N) continue;
+      plan->band = true;
+      plan->band_smem = smem;
+      BandArgs& b = plan->bargs;
+      memset(&b, 0, sizeof(b));
+      b.layers = plan->layers_dev;
+      b.s_init = s_init;
+      b.out_bf16 = static_cast<__nv_bfloat16*>(plan->out_bufs.back());
+      b.n_layers = a.n_layers; b.N = N; b.H = H; b.W = W; b.C = C; b.R = R; b.P = P; b.n_chunks = n_chunks; b.cr = Cr;
+      b.inv_hw = a.inv_hw;
+      b.plane_bytes = band_plane_bytes(R, P);
+      b.pmagic = ((1u << 24) + uint32_t(P) - 1) / uint32_t(P);
+      int left = count;
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        b.nq[ch] = left < kBandNQMax ? left : kBandNQMax;
+        b.nn[ch] = (b.nq[ch] + 1 + 15) / 16 * 16;
+        left -= b.nq[ch];
+      }
+      for (const TrunkLayer& l : plan->layers) b.n_ca += l.kind == kTrunkCA ? 1 : 0;
+      if (int e = make_map_weight_layers(&plan->w_tap_map, w_base, a.n_layers, 1)) return e;
+    }
+  }
   plan->uploaded.clear();
   plan->maps_uploaded = false;
   return RUMPY_OK;
@@ -157,6 +212,23 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
                         cudaMemcpyHostToDevice, s) != cudaSuccess)
       return set_error(RUMPY_ERR_CUDA, "trunk: layer table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaStreamSynchronize(s);
+  }
+  if (plan->band) {
+    BandArgs& b = plan->bargs;
+    b.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
+    b.dbg_layers = g_trunk_dbg_layers;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(b.N * b.C); cfg.blockDim = dim3(kBandThreads);
+    cfg.dynamicSmemBytes = plan->band_smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = b.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, trunk_band_kernel, plan->w_tap_map, b);
+    if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "trunk_band launch: %s", cudaGetErrorString(e));
+    if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
+    return RUMPY_OK;
   }
   if (plan->cluster) {
     ClusterArgs& c = plan->cargs;
@@ -333,6 +405,8 @@ extern "C" {
 int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
 int rumpy_debug_set_trunk_sync_mode(int mode) { rb::g_trunk_sync_mode = mode; return 0; }
 int rumpy_debug_set_trunk_cluster(int on) { rb::g_use_cluster = on; return 0; }
+/* role-swapped band kernel (trunk_band.cuh) on / off; takes effect for plans built afterwards */
+int rumpy_debug_set_trunk_band(int on) { rb::g_use_band = on; return 0; }
 /* epilogue groups of the cluster kernel: 2 (320 threads) or 4 (576 threads); takes effect for plans built afterwards */
 int rumpy_debug_set_cluster_groups(int groups) { rb::g_cluster_groups = groups == 4 ? 4 : 2; return 0; }
 /* bench hook: CUDA events (cudaEvent_t) recorded right before / after the trunk kernel of every forward; NULL = off */

@@ -15,7 +15,12 @@ from oracle import sr_torch_cpu
 pytestmark = pytest.mark.gpu
 
 DEFAULT_GROUPS = int(__import__('os').environ.get('RUMPY_B200_CLUSTER_GROUPS', 2))
-MODES = {'per-layer': (0, 0, 2), 'dataflow': (1, 0, 2), 'cluster': (1, 1, 2), 'cluster-4-groups': (1, 1, 4)}
+MODES = {'per-layer': (0, 0, 2, 0), 'dataflow': (1, 0, 2, 0), 'cluster': (1, 1, 2, 0), 'cluster-4-groups': (1, 1, 4, 0)}
+# the role-swapped band kernel (csrc/trunk_band.cuh) is an opt-in experiment (slower than the cluster kernel and not
+# yet exact at every shape): it joins the comparison only when asked for
+TEST_BAND = __import__('os').environ.get('RUMPY_B200_TEST_BAND') == '1'
+if TEST_BAND:
+    MODES['band'] = (1, 1, 2, 1)
 
 
 def _dev():
@@ -29,6 +34,7 @@ def _lib():
     lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
     lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
     lib.rumpy_debug_set_cluster_groups.argtypes = [ctypes.c_int]
+    lib.rumpy_debug_set_trunk_band.argtypes = [ctypes.c_int]
     return lib
 
 
@@ -45,8 +51,9 @@ def _run_modes(net, x):
     lib = _lib()
     outs, modes = {}, {}
     try:
-        for name, (trunk, cluster, groups) in MODES.items():
+        for name, (trunk, cluster, groups, band) in MODES.items():
             lib.rumpy_debug_set_trunk(trunk)
+            lib.rumpy_debug_set_trunk_band(band)
             lib.rumpy_debug_set_trunk_cluster(cluster)
             lib.rumpy_debug_set_cluster_groups(groups)
             eng = net.native_engine()
@@ -63,23 +70,26 @@ def _run_modes(net, x):
         lib.rumpy_debug_set_trunk(1)
         lib.rumpy_debug_set_trunk_cluster(1)
         lib.rumpy_debug_set_cluster_groups(DEFAULT_GROUPS)
+        lib.rumpy_debug_set_trunk_band(0)
     return outs, modes
 
 
 CASES = [
-    # name, kind, ctor kwargs, input shape, expected mode with the cluster kernel allowed
-    ('rcan_2x16x16', 'rcan', dict(n_resgroups=1, n_resblocks=2), (2, 3, 16, 16), 2),
-    ('rcan_ragged_3x20x37', 'rcan', dict(n_resgroups=2, n_resblocks=3), (3, 3, 20, 37), 2),
-    ('rcan_5x64x96_two_slots', 'rcan', dict(n_resgroups=2, n_resblocks=2), (5, 3, 64, 96), None),
-    ('rcan_1x100x200_image_spans_slots', 'rcan', dict(n_resgroups=1, n_resblocks=2), (1, 3, 100, 200), 1),
-    ('rcan_16x48x48_cfg2_shape', 'rcan', dict(n_resgroups=1, n_resblocks=3), (16, 3, 48, 48), 2),
-    ('rcan_16x64x64_cfg3_shape', 'rcan', dict(n_resgroups=1, n_resblocks=2), (16, 3, 64, 64), 1),
-    ('edsr_2x24x24', 'edsr', dict(num_blocks=4), (2, 3, 24, 24), 2),
+    # name, kind, ctor kwargs, input shape, expected mode with the cluster kernel allowed, with the band kernel allowed
+    ('rcan_2x16x16', 'rcan', dict(n_resgroups=1, n_resblocks=2), (2, 3, 16, 16), 2, 3),
+    ('rcan_ragged_3x20x37', 'rcan', dict(n_resgroups=2, n_resblocks=3), (3, 3, 20, 37), 2, 3),
+    ('rcan_5x64x96_two_slots', 'rcan', dict(n_resgroups=2, n_resblocks=2), (5, 3, 64, 96), None, None),
+    ('rcan_1x100x200_image_spans_slots', 'rcan', dict(n_resgroups=1, n_resblocks=2), (1, 3, 100, 200), 1, 1),
+    ('rcan_16x48x48_cfg2_shape', 'rcan', dict(n_resgroups=1, n_resblocks=3), (16, 3, 48, 48), 2, 3),
+    ('rcan_16x64x64_cfg3_shape', 'rcan', dict(n_resgroups=1, n_resblocks=2), (16, 3, 64, 64), 1, 1),
+    ('edsr_2x24x24', 'edsr', dict(num_blocks=4), (2, 3, 24, 24), 2, 3),
+    ('rcan_1x7x5_tiny', 'rcan', dict(n_resgroups=1, n_resblocks=2), (1, 3, 7, 5), None, 3),
+    ('rcan_2x33x48_three_chunks_short_last_band', 'rcan', dict(n_resgroups=2, n_resblocks=2), (2, 3, 33, 48), None, 3),
 ]
 
 
-@pytest.mark.parametrize('name,kind,kw,shape,want_mode', CASES, ids=[c[0] for c in CASES])
-def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, want_mode):
+@pytest.mark.parametrize('name,kind,kw,shape,want_mode,want_band', CASES, ids=[c[0] for c in CASES])
+def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, want_mode, want_band):
     net, sd = _net(kind, **kw)
     x = recipe.make_input(shape, seed=8)
     outs, modes = _run_modes(net, torch.from_numpy(x).to(_dev()))
@@ -87,6 +97,8 @@ def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, wa
     if want_mode is not None:
         assert modes['cluster'] == want_mode, f'cluster-allowed plan picked mode {modes["cluster"]}'
         assert modes['cluster-4-groups'] == want_mode
+    if TEST_BAND and want_band is not None:
+        assert modes['band'] == want_band, f'band-allowed plan picked mode {modes["band"]}'
     sdt = {k: torch.from_numpy(v) for k, v in sd.items()}
     arch, akw = sr_torch_cpu.infer_arch(sdt)
     ref = sr_torch_cpu.forward(sdt, torch.from_numpy(x), arch, res_scale=0.1, **akw).numpy()
@@ -95,7 +107,7 @@ def test_trunk_kernels_match_per_layer_path_and_oracle(name, kind, kw, shape, wa
         err = float(np.abs(out.cpu().numpy() - ref).max())
         assert err <= 1e-2 * scale, f'{name} [{mode}]: max-abs {err} vs CPU oracle'
     base = outs['per-layer']
-    for mode in ('dataflow', 'cluster', 'cluster-4-groups'):
+    for mode in [m for m in MODES if m != 'per-layer']:
         d = float((outs[mode] - base).abs().max())
         assert d <= 5e-3 * scale, f'{name}: {mode} differs from the per-layer path by {d}'
 
