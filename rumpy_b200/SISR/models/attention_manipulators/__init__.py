@@ -46,54 +46,63 @@ class QModel(BaseModel):
         super(QModel, self).__init__(**kwargs)
         self.moco_encoding = False
 
-    def generate_channels(self, x, metadata, keys):
-        """Per-image metadata rows -> [N, num_metadata, 1, 1] (reference __init__.py:87-108)."""
+    def _metadata_table(self, n, metadata, keys):
+        """The per-image metadata rows as an [n, k] fp32 CPU table restricted to the keys this model was configured
+        with (`self.metadata`; 'all' keeps every column).  With a single key the row is the value itself."""
         if metadata is None:
             raise RuntimeError('Metadata needs to be specified for this network to run properly.')
-        extra_channels = torch.ones(x.size(0), self.num_metadata)
-        if 'all' in self.metadata:
-            mask = [True] * self.num_metadata
-        else:
-            mask = [True if key[0] in self.metadata else False for key in keys]
-        for index in range(extra_channels.size(0)):
-            added_info = metadata[index] if len(keys) == 1 else metadata[index][mask]
-            extra_channels[index, ...] = extra_channels[index, :] * added_info
-        extra_channels = extra_channels.unsqueeze(2).unsqueeze(3)
-        if self.style == 'modulate':
-            extra_channels = self.scale_qpi(extra_channels)
-        return extra_channels
+        rows = metadata if torch.is_tensor(metadata) else torch.as_tensor(np.asarray(metadata))
+        table = rows.detach().to('cpu', torch.float32).reshape(n, -1)
+        if len(keys) > 1:
+            if 'all' in self.metadata:
+                keep = torch.ones(self.num_metadata, dtype=torch.bool)
+            else:
+                keep = torch.tensor([key[0] in self.metadata for key in keys], dtype=torch.bool)
+            table = table[:, keep]
+        return table
+
+    def generate_channels(self, x, metadata, keys):
+        """Per-image metadata rows -> the [N, num_metadata, 1, 1] vector the q-layers take (what the reference's
+        per-image loop builds, __init__.py:87-108): one broadcast instead of a Python loop over the batch."""
+        n = x.size(0)
+        vec = self._metadata_table(n, metadata, keys).expand(n, self.num_metadata).clone()[:, :, None, None]
+        return self.scale_qpi(vec) if self.style == 'modulate' else vec
 
     def generate_sft_channels(self, x, metadata, metadata_keys):
         raise NotImplementedError('rumpy_b200 QModel: SFT / SRMD channel-tiled metadata is outside the native trunk')
 
     def channel_concat_logic(self, x, extra_channels, metadata, metadata_keys):
-        """reference __init__.py:137-165"""
-        if self.no_metadata:
-            extra_channels = None
-        else:
-            if extra_channels is None:
-                extra_channels = self.generate_channels(x, metadata, metadata_keys)
-            if self.metadata_keys_used_in_training is None and metadata_keys is not None:
-                self.metadata_keys_used_in_training = [m[0] for m in metadata_keys]
+        """(input batch, metadata vector) for the network call (reference __init__.py:137-165).  Ready-made
+        `extra_channels` pass through; the key names seen first are remembered for the checkpoint."""
         if self.channel_concat:
             raise NotImplementedError('rumpy_b200 QModel: metadata concatenated with the input image (SRMD mode)')
+        if self.no_metadata:
+            return x, None
+        if extra_channels is None:
+            extra_channels = self.generate_channels(x, metadata, metadata_keys)
+        if self.metadata_keys_used_in_training is None and metadata_keys is not None:
+            self.metadata_keys_used_in_training = [key[0] for key in metadata_keys]
         return x, extra_channels
 
     def save_model(self, model_save_name, extract_state_only=True, minimal=False):
+        """Reference __init__.py:167-175: the base class only assembles the state (extract_state_only=True by
+        default here), the file is ALWAYS written by this override, with the metadata key names when known."""
         super().save_model(model_save_name=model_save_name, extract_state_only=extract_state_only, minimal=minimal)
         if self.metadata_keys_used_in_training:
             self.state['metadata_keys_used_in_training'] = self.metadata_keys_used_in_training
-            torch.save(self.state, f=os.path.join(self.model_save_dir,
-                                                   '{}_{}'.format(model_save_name, self.curr_epoch)))
+        torch.save(self.state, f=os.path.join(self.model_save_dir, '{}_{}'.format(model_save_name, self.curr_epoch)))
+
+    def _with_metadata(self, base_call, x, y, metadata, metadata_keys, extra_channels, **kwargs):
+        data, vec = self.channel_concat_logic(x, extra_channels, metadata, metadata_keys)
+        return base_call(data, y, extra_channels=vec, **kwargs)
 
     def run_train(self, x, y, metadata=None, extra_channels=None, metadata_keys=None, *args, **kwargs):
-        input_data, extra_channels = self.channel_concat_logic(x, extra_channels, metadata, metadata_keys)
-        return super().run_train(input_data, y, extra_channels=extra_channels, **kwargs)
+        return self._with_metadata(super().run_train, x, y, metadata, metadata_keys, extra_channels, **kwargs)
 
     def run_eval(self, x, y=None, request_loss=False, metadata=None, metadata_keys=None,
                  extra_channels=None, *args, **kwargs):
-        input_data, extra_channels = self.channel_concat_logic(x, extra_channels, metadata, metadata_keys)
-        return super().run_eval(input_data, y, request_loss=request_loss, extra_channels=extra_channels, **kwargs)
+        return self._with_metadata(super().run_eval, x, y, metadata, metadata_keys, extra_channels,
+                                   request_loss=request_loss, **kwargs)
 
     def run_model(self, x, extra_channels=None, *args, **kwargs):
         return self.net.forward(x, metadata=extra_channels)

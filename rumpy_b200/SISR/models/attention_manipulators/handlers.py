@@ -32,18 +32,19 @@ class QRCANHandler(QModel):
 
     @staticmethod
     def gaussian(x, mu, sig=0.2):
-        return torch.from_numpy(
-            (1 / (np.sqrt(2 * np.pi) * sig)) * np.exp(-np.power(x - mu, 2.) / (2 * np.power(sig, 2.)))).type(
-            torch.float32)
+        """Normal density N(mu, sig) sampled at `x` (float64 numpy in, fp32 tensor out; reference handlers.py:59-63)."""
+        z = (np.asarray(x, dtype=np.float64) - np.asarray(mu, dtype=np.float64)) / sig
+        return torch.from_numpy(np.exp(-0.5 * z * z) / (sig * np.sqrt(2.0 * np.pi))).to(torch.float32)
 
     def scale_qpi(self, qpi):
-        """[N,1,1,1] quality index -> [N,n_feats,1,1] Gaussian bump centred on the scaled index (reference :65-73)."""
-        scaled_qpi = (qpi * (self.max_mu - self.min_mu)) + self.min_mu
-        scalers = [self.gaussian(self.base_scaler, scaled_qpi[i].squeeze().numpy()) for i in range(scaled_qpi.size(0))]
-        full_scalers = torch.stack(scalers)
+        """'modulate' style: the [N,1,1,1] quality index becomes an [N,n_feats,1,1] Gaussian bump over the channel
+        axis, centred on the index mapped into [min_mu, max_mu] (reference handlers.py:65-73).  One broadcast over
+        the batch; float64 density, fp32 result, like the reference."""
+        centre = (qpi * (self.max_mu - self.min_mu) + self.min_mu).reshape(-1).numpy()     # fp32, one per image
+        bumps = self.gaussian(self.base_scaler[None, :], centre[:, None])
         if self.clamp:
-            full_scalers = torch.clamp(full_scalers, 0, 1)
-        return full_scalers.unsqueeze(2).unsqueeze(3)
+            bumps = bumps.clamp(0, 1)
+        return bumps[:, :, None, None]
 
 
 class QEDSRHandler(QModel):

@@ -20,7 +20,8 @@ def _require_cuda(x):
 
 def _packed(conv, shuffle_r=1, rows_padded=0):
     """Packs (and caches on the module) the conv's bf16 operand; refreshed when the weight changes."""
-    key = (conv.weight._version, conv.weight.data_ptr(), shuffle_r, rows_padded)
+    from .engine import PARAM_EPOCH
+    key = (conv.weight._version, PARAM_EPOCH[0], conv.weight.data_ptr(), shuffle_r, rows_padded)
     if getattr(conv, '_rb_pack_key', None) != key:
         w = conv.weight.detach()
         conv._rb_w = ops.pack_conv3x3(w, rows_padded=rows_padded, shuffle_r=shuffle_r)

@@ -14,6 +14,9 @@ from . import _lib
 
 ARCH_RCAN, ARCH_EDSR, ARCH_QRCAN, ARCH_QEDSR, ARCH_HAN, ARCH_QHAN = 0, 1, 2, 3, 4, 5
 
+PARAM_EPOCH = [0]   # bumped by every native optimiser step (FusedAdam writes parameters through the flat buffer, which
+                    # leaves the per-parameter version counters alone): part of the stand-alone blocks' cache keys
+
 _FLAT = {}   # id(first parameter) -> (flat fp32 buffer, weakref to first parameter): shared by engine and FusedAdam
 
 
@@ -122,9 +125,18 @@ class TrunkEngine:
         self._grad_views = None
 
     def _version_sig(self):
-        if self.flat_params is not None:
-            return (self.flat_params._version,)     # views share the base tensor's version counter
-        return tuple(p._version for p in self.params)
+        # FusedAdam bumps the flat buffer's counter (one in-place op per step); load_state_dict, foreign optimisers
+        # and user code write through the parameters, whose counters are their own (`p.data = view` does not share
+        # the base tensor's counter) -- so both are part of the signature.
+        flat_v = self.flat_params._version if self.flat_params is not None else 0
+        return (flat_v, sum(p._version for p in self.params))
+
+    def invalidate(self):
+        """Forget everything derived from the parameter VALUES or from buffer addresses: packed bf16 weights are
+        rebuilt on the next forward, captured graphs are dropped."""
+        self._pack_sig = None
+        self._graphs.clear()
+        self._last_infer_shape = None
 
     def refresh_weights(self, force=False, training=False):
         """Repacks fp32 OIHW parameters into the bf16 tensor-core operand layout when they changed."""
@@ -145,7 +157,12 @@ class TrunkEngine:
             if nbytes < 0:
                 msg = self.lib.rumpy_last_error()
                 raise _lib.RumpyB200Error('workspace query failed: ' + (msg.decode() if msg else '?'))
-            self._ws = {k: v for k, v in self._ws.items() if k[3] != key[3]}   # keep one per mode
+            if any(k[3] == key[3] for k in self._ws):
+                # one workspace per mode: the other shape's buffer is released, and with it every CUDA graph that
+                # was captured against its address (replaying one would touch freed memory)
+                self._ws = {k: v for k, v in self._ws.items() if k[3] != key[3]}
+                self._graphs.clear()
+                self._last_infer_shape = None
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
@@ -259,6 +276,8 @@ class TrunkEngine:
         self.refresh_weights()
         key = tuple(x.shape)
         g = self._graphs.get(key)
+        if g is not None and g[3].data_ptr() != self.workspace(x.shape[0], x.shape[2], x.shape[3], False).data_ptr():
+            g = None                               # captured against a workspace that has been replaced
         if g is None:
             sx = torch.empty_like(x)
             sy = torch.empty((x.shape[0], self.out_feats, x.shape[2] * self.scale, x.shape[3] * self.scale),
@@ -272,9 +291,10 @@ class TrunkEngine:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.forward(sx, out=sy)
-            g = (graph, sx, sy)
+            # the graph keeps the workspace it was captured with alive
+            g = (graph, sx, sy, self.workspace(x.shape[0], x.shape[2], x.shape[3], False))
             self._graphs = {key: g}
-        graph, sx, sy = g
+        graph, sx, sy, _ = g
         sx.copy_(x)
         graph.replay()
         return sy

@@ -54,8 +54,10 @@ class FusedAdam(torch.optim.Optimizer):
                              'exp_avg_sq': self.flat_v[off:off + k].view(p.shape)}
 
     def zero_grad(self, set_to_none=False):
-        # the native backward overwrites every gradient; nothing to clear
-        return None
+        """Clears the flat gradient buffer (p.grad are views of it, so `set_to_none` is ignored).  The native train
+        step does not call this -- its backward overwrites every gradient -- but the module-level autograd path
+        (`net(x)`, `loss.backward()`, `opt.step()`) accumulates into .grad like any torch optimiser expects."""
+        self.flat_g.zero_()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -66,7 +68,9 @@ class FusedAdam(torch.optim.Optimizer):
                   float(g['betas'][1]), float(g['eps']), self._step,
                   0 if self.grad_scale_dev is None else self.grad_scale_dev.data_ptr(), float(self.grad_scale),
                   torch.cuda.current_stream().cuda_stream)
-        self.flat_p[:1].add_(0)  # bump the version counter shared by all parameter views -> engines repack
+        self.flat_p[:1].add_(0)  # bump the flat buffer's version counter -> engines repack
+        from . import engine
+        engine.PARAM_EPOCH[0] += 1   # ... and the stand-alone blocks' packed-weight caches (blocks_native._packed)
         self.grad_scale_dev = None
         self.grad_scale = 1.0
         for st in self.state.values():

@@ -1,7 +1,8 @@
 """Minimal LR/HR patch data source for the CLI mirrors (the reference's full pipeline, rumpy/sr_tools/data_handler.py,
 is out of scope -- SURVEY.md section 2 #12).  Same semantics for the keys the EDSR/RCAN path uses: `lr` / `hr` image
 directories matched by file name, `crop` = LR patch side (HR patch = crop*scale, image_functions.py:320-326),
-`random_augment` = hflip / vflip / transpose with p=0.5 each (:346-362).  `synthetic = N` yields N random pairs."""
+`random_augment` = hflip / vflip / transpose with p=0.5 each (:346-362), drawn and applied BEFORE the patch is cut, like
+the reference's `image_augment_crop` (sr_tools/data_handler.py:570-596; pinned by tests/golden/host_glue.npz).  `synthetic = N` yields N random pairs."""
 from __future__ import annotations
 
 import os
@@ -28,8 +29,9 @@ class PairSet:
         if cfg.get('synthetic'):
             g = np.random.RandomState(seed)
             side = (self.crop or 48) * 2
-            self.items = [(f'synthetic_{i}', g.randint(0, 256, (side, side, 3), dtype=np.uint8),
-                           g.randint(0, 256, (side * scale, side * scale, 3), dtype=np.uint8))
+            sh, sw = cfg.get('synthetic_hw', (side, side))       # LR image size (default: square, twice the crop)
+            self.items = [(f'synthetic_{i}', g.randint(0, 256, (sh, sw, 3), dtype=np.uint8),
+                           g.randint(0, 256, (sh * scale, sw * scale, 3), dtype=np.uint8))
                           for i in range(int(cfg['synthetic']))]
         else:
             names = sorted(f for f in os.listdir(cfg['lr']) if f.lower().endswith(('.png', '.jpg', '.bmp')))
@@ -40,37 +42,56 @@ class PairSet:
     def __len__(self):
         return len(self.items)
 
-    def sample(self, idx):
-        name, lr, hr = self.items[idx]
-        if self.crop:
-            c, s = self.crop, self.scale
-            y = self.rng.randint(0, lr.shape[0] - c)
-            x = self.rng.randint(0, lr.shape[1] - c)
-            lr = lr[y:y + c, x:x + c]
-            hr = hr[y * s:(y + c) * s, x * s:(x + c) * s]
-        if self.augment:
-            if self.rng.random() < 0.5:
-                lr, hr = lr[:, ::-1], hr[:, ::-1]
-            if self.rng.random() < 0.5:
-                lr, hr = lr[::-1], hr[::-1]
-            if self.rng.random() < 0.5:
-                lr, hr = lr.transpose(1, 0, 2), hr.transpose(1, 0, 2)
-        return name, to_tensor(np.ascontiguousarray(lr)), to_tensor(np.ascontiguousarray(hr))
-
-    def geometry(self, idx):
-        """The random draws of `sample` (same order, same count), without touching pixels:
-        [image index, y, x, flags (1 hflip | 2 vflip | 4 transpose, applied in that order), lr_h, lr_w] -- the row
-        `rumpy_patch_batch` consumes."""
-        _, lr, _ = self.items[idx]
-        c = self.crop
-        y = self.rng.randint(0, lr.shape[0] - c)
-        x = self.rng.randint(0, lr.shape[1] - c)
+    def _draw(self, lr_h, lr_w):
+        """The random draws of one sample, in the reference's order (sr_tools/data_handler.py:570-596): first the
+        augmentation coins of `random_flip_rotate` (image_functions.py:346-350: hflip, vflip, transpose, p = 0.5
+        each, one `random()` per coin), then the patch corner of `random_patch_selection` (:287-294: `randint` for
+        the row, then the column) ON THE AUGMENTED IMAGE -- a transposed image swaps the two ranges."""
         flags = 0
         if self.augment:
             flags |= 1 if self.rng.random() < 0.5 else 0
             flags |= 2 if self.rng.random() < 0.5 else 0
             flags |= 4 if self.rng.random() < 0.5 else 0
-        return [idx, y, x, flags, lr.shape[0], lr.shape[1]]
+        h, w = 0, 0
+        if self.crop:
+            aug_h, aug_w = (lr_w, lr_h) if flags & 4 else (lr_h, lr_w)
+            h = self.rng.randint(0, max(0, aug_h - self.crop))
+            w = self.rng.randint(0, max(0, aug_w - self.crop))
+        return flags, h, w
+
+    def sample(self, idx):
+        """One (name, LR, HR) training pair, built the way the reference builds it: augment the whole image pair,
+        then cut the patch (LR at (h, w), HR at (h, w) * scale)."""
+        name, lr, hr = self.items[idx]
+        flags, h, w = self._draw(lr.shape[0], lr.shape[1])
+        if flags & 1:
+            lr, hr = lr[:, ::-1], hr[:, ::-1]
+        if flags & 2:
+            lr, hr = lr[::-1], hr[::-1]
+        if flags & 4:
+            lr, hr = lr.transpose(1, 0, 2), hr.transpose(1, 0, 2)
+        if self.crop:
+            c, s = self.crop, self.scale
+            lr = lr[h:h + c, w:w + c]
+            hr = hr[h * s:(h + c) * s, w * s:(w + c) * s]
+        return name, to_tensor(np.ascontiguousarray(lr)), to_tensor(np.ascontiguousarray(hr))
+
+    def geometry(self, idx):
+        """The same draws as `sample` (same order, same count) without touching pixels, as the row
+        `rumpy_patch_batch` consumes: [image index, y, x, flags (1 hflip | 2 vflip | 4 transpose, applied to the
+        PATCH in that order), lr_h, lr_w] with (y, x) the patch corner in the ORIGINAL image.  Cutting at (h, w)
+        after the flips equals cutting the mirrored window before them: undo the transpose (swap), then the
+        vertical / horizontal mirror (corner -> size - crop - corner)."""
+        _, lr, _ = self.items[idx]
+        lr_h, lr_w = lr.shape[0], lr.shape[1]
+        flags, h, w = self._draw(lr_h, lr_w)
+        c = self.crop
+        y, x = (w, h) if flags & 4 else (h, w)
+        if flags & 2:
+            y = lr_h - c - y
+        if flags & 1:
+            x = lr_w - c - x
+        return [idx, y, x, flags, lr_h, lr_w]
 
     def batches(self, batch_size, shuffle=True, rank=0, world=1):
         order = list(range(len(self.items)))

@@ -65,8 +65,18 @@ def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None, metadata=No
                   ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
         optimizer.grad_scale_dev = coef
     if getattr(optimizer, 'flat_g', None) is not flat_g:
-        # foreign optimiser (e.g. RMSprop from the reference's optimizer_type switch): hand it the gradients
+        # foreign optimiser (e.g. torch's RMSprop from the reference's optimizer_type switch): it knows nothing of
+        # the fused step's grad scales, so the 1/world average and the clip coefficient are applied to the flat
+        # gradient here, then the gradients are handed over as .grad
+        if allreduce is not None and allreduce.world_size > 1:
+            flat_g.mul_(1.0 / allreduce.world_size)
+        if grad_clip is not None:
+            flat_g.mul_(optimizer.grad_scale_dev[0])
+        optimizer.grad_scale, optimizer.grad_scale_dev = 1.0, None
         for p, g in zip(eng.params, eng.grad_views()):
             p.grad = g
+        optimizer.step()
+        eng.invalidate()                   # parameters changed behind the engine's back: repack before the next use
+        return loss, out
     optimizer.step()
     return loss, out

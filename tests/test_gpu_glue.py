@@ -91,6 +91,27 @@ def test_device_patch_pipeline_bit_exact_vs_host_pipeline(crop, scale, augment):
     assert n_batches == 6
 
 
+@pytest.mark.parametrize('name', ['square_x4', 'wide_x2', 'tall_x3_noaug', 'exact_fit_x4'])
+def test_device_patch_pipeline_vs_reference_golden(name, golden_dir):
+    """`rumpy_patch_batch` against patches cut by the reference's OWN `random_flip_rotate` + `image_patch_selection`
+    (image_functions.py:287-362, called in data_handler.py:570-596's order; tests/golden/host_glue.npz written by
+    make_golden_host.py): bit-exact for every sample of three passes over the set."""
+    import os
+    import make_golden_host as mgh
+    from rumpy_b200.shared_framework.data import DevicePairSet
+    gold = np.load(os.path.join(golden_dir, 'host_glue.npz'))
+    cfg, scale, seed = mgh.PATCH_CASES[name]
+    dev = DevicePairSet(cfg, scale, seed=seed, device=0)
+    n = len(dev)
+    k = 0
+    for _ in range(mgh.PASSES):
+        got = list(dev.batches(n, shuffle=False))
+        assert len(got) == 1
+        assert np.array_equal(got[0]['lr'].cpu().numpy(), gold[f'patch::{name}::lr'][k:k + n]), 'LR patches'
+        assert np.array_equal(got[0]['hr'].cpu().numpy(), gold[f'patch::{name}::hr'][k:k + n]), 'HR patches'
+        k += n
+
+
 def test_bicubic_baseline_vs_reference_golden(golden_dir):
     """`rumpy_bicubic_upsample` against the reference's own `EvalHub._low_res_prep` outputs
     (evaluation/standard_eval.py:240-275; tests/golden/bicubic.npz): bit-exact."""
