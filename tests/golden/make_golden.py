@@ -32,34 +32,12 @@ REF = '/root/reference'
 
 
 # ---------------------------------------------------------------------------- import shims
-class _StubLoader(importlib.abc.Loader):
-    def create_module(self, spec):
-        m = mock.MagicMock(name=spec.name)
-        m.__name__ = spec.name
-        m.__path__ = []
-        m.__spec__ = spec
-        m.__loader__ = self
-        return m
-
-    def exec_module(self, module):
-        pass
-
-
-class _StubFinder(importlib.abc.MetaPathFinder):
-    ROOTS = ('timm', 'matplotlib', 'deepdiff', 'colorama', 'torchinfo', 'prefetch_generator', 'skimage',
-             'lpips', 'h5py', 'skvideo', 'moviepy', 'umap', 'click_config_file', 'imageio', 'aim', 'seaborn',
-             'facenet_pytorch', 'mtcnn', 'keras', 'tensorflow', 'onnx', 'onnxruntime')
-
-    def find_spec(self, name, path=None, target=None):
-        if name.split('.')[0] in self.ROOTS:
-            return importlib.machinery.ModuleSpec(name, _StubLoader(), is_package=True)
-        return None
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_import  # noqa: E402  (collections.Callable + stub modules for absent third-party packages)
 
 
 def import_reference():
-    collections.Callable = collections.abc.Callable
-    sys.meta_path.append(_StubFinder())
-    sys.path.insert(0, REF)
+    ref_import.import_reference(REF)           # goldens are generated from the source tree in the build container
     from rumpy.SISR.models.advanced import architectures, common  # noqa
     return architectures, common
 
