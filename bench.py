@@ -218,7 +218,7 @@ def trunk_kernel_roofline(eng, x_dev, flush, pk):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); e1.record()
     torch.cuda.synchronize()
-    lib.rumpy_debug_set_trunk_events(e0.cuda_event, e1.cuda_event)
+    eng.set_trunk_events(e0, e1)
     best = None
     try:
         with torch.no_grad():
@@ -229,7 +229,7 @@ def trunk_kernel_roofline(eng, x_dev, flush, pk):
                 t = e0.elapsed_time(e1) * 1e-3
                 best = t if best is None else min(best, t)
     finally:
-        lib.rumpy_debug_set_trunk_events(None, None)
+        eng.set_trunk_events(None, None)
     n_convs = 10 * (2 * 20 + 1) + 1
     flops = n_convs * CONV64_FLOP_PER_PIXEL * BATCH * LR_HW * LR_HW
     achieved = flops / best * 1e-12

@@ -135,9 +135,27 @@ int rumpy_net_num_launches_backward(void* net); /* kernels per backward of the c
  *   1  ONE persistent tile-stationary dataflow kernel for the whole body (<= 4 tiles per SM): neighbour tiles
  *      hand over through per-tile epochs in global memory, fp32 residual stream in tensor memory;
  *   2  one thread-block CLUSTER per image: activations stay in (distributed) shared memory across all layers,
- *      halos and the channel-attention pool travel by st.async between the CTAs of the cluster.
- * The mode is picked per (N,H,W) when the plan is built; all three compute the same layer program. */
+ *      halos and the channel-attention pool travel by st.async between the CTAs of the cluster;
+ *   3  (option "band", experiment) the cluster layout with the MMA roles swapped: weights in tensor memory as the
+ *      A operand, up to 144 pixels as N (trunk_band.cuh).
+ * The mode is picked per (N,H,W) when the plan is built; all of them compute the same layer program. */
 int rumpy_net_trunk_mode(void* net);
+
+/* Per-handle execution options.  The library has NO process-global switches: every knob lives in the net handle and
+ * applies to the calls made with that handle only (re-entrant; two handles with different options can run side by
+ * side).  An option change takes effect with the next forward (the cached launch plan is rebuilt when it depends on
+ * the option).  Names (value): "trunk" (1; 0 = one kernel per layer), "cluster" (1; 0 = dataflow kernel only),
+ * "cluster_groups" (2 | 4 epilogue groups of the cluster kernel), "band" (0; 1 = role-swapped band kernel,
+ * experiment), "trunk_bwd" (1; 0 = per-layer backward), "fused_ca" (0), "wgrad_chunks" (4; 1..8), "wgrad_tiles_per_split"
+ * (64), "pdl" (1), "conv_2x" (0), "trunk_sync_mode" (8).  Unknown names return RUMPY_ERR_ARG / -1. */
+int rumpy_net_set_option(void* net, const char* name, long long value);
+long long rumpy_net_get_option(void* net, const char* name);
+/* Measurement hook (bench.py's roofline timing): two caller-owned CUDA events (cudaEvent_t) recorded on the launching
+ * stream right before / after the trunk kernel of every forward of this handle; NULL, NULL = off. */
+int rumpy_net_set_trunk_events(void* net, void* ev_start, void* ev_stop);
+/* Diagnostics: caller-owned device buffer of int64 that this handle's kernels fill with clock64 stamps; layers > 0
+ * additionally requests a per-layer timeline of that many layers from the trunk kernels.  NULL = off. */
+int rumpy_net_set_timeline(void* net, void* buf, int layers);
 
 /* Chunked weight gradients for data-parallel training: rumpy_net_backward computes the conv weight gradients last,
  * in chunks ordered from the LAST parameters to the first.  After chunk k every gradient with parameter index

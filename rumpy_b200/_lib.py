@@ -46,6 +46,10 @@ SIGNATURES = {
     'rumpy_net_num_launches': [_vp],
     'rumpy_net_num_launches_backward': [_vp],
     'rumpy_net_trunk_mode': [_vp],
+    'rumpy_net_set_option': [_vp, _c.c_char_p, _c.c_longlong],
+    'rumpy_net_get_option': [_vp, _c.c_char_p],
+    'rumpy_net_set_trunk_events': [_vp, _vp, _vp],
+    'rumpy_net_set_timeline': [_vp, _vp, _i],
     'rumpy_net_packed_bytes': [_vp, _i],
     'rumpy_net_workspace_bytes': [_vp, _i, _i, _i, _i],
     'rumpy_net_pack': [_vp, _vp, _vp, _i, _vp],
@@ -58,9 +62,25 @@ SIGNATURES = {
 }
 
 _LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace',
-             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace', 'rumpy_bicubic_workspace'}
+             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace', 'rumpy_bicubic_workspace', 'rumpy_net_get_option'}
 
 _lib = None
+
+# developer switches, read when an engine is created and applied to ITS handle (rumpy_net_set_option): env var ->
+# (option, value when the variable holds that string)
+ENV_OPTIONS = {'RUMPY_B200_PDL': ('pdl', {'0': 0}), 'RUMPY_B200_CONV2X': ('conv_2x', {'1': 1}),
+               'RUMPY_B200_TRUNK': ('trunk', {'0': 0}), 'RUMPY_B200_BAND': ('band', {'1': 1}),
+               'RUMPY_B200_CLUSTER': ('cluster', {'0': 0}), 'RUMPY_B200_CLUSTER_GROUPS': ('cluster_groups', {'2': 2, '4': 4}),
+               'RUMPY_B200_FUSED_CA': ('fused_ca', {'1': 1})}
+
+
+def env_options():
+    out = {}
+    for var, (name, table) in ENV_OPTIONS.items():
+        v = os.environ.get(var)
+        if v in table:
+            out[name] = table[v]
+    return out
 
 
 class RumpyB200Error(RuntimeError):
@@ -82,21 +102,6 @@ def load():
         fn.argtypes = argtypes
         fn.restype = (ctypes.c_char_p if name == 'rumpy_last_error' else
                       ctypes.c_longlong if name in _LONGLONG else ctypes.c_int)
-    if os.environ.get('RUMPY_B200_PDL') == '0':      # debug switch: disable programmatic dependent launch
-        lib.rumpy_debug_set_pdl(0)
-    if os.environ.get('RUMPY_B200_CONV2X') == '1':     # experiment: two streaming-B conv CTAs per SM
-        lib.rumpy_debug_set_conv2x(1)
-    lib.rumpy_debug_set_trunk_events.argtypes = [_vp, _vp]
-    if os.environ.get('RUMPY_B200_TRUNK') == '0':     # debug switch: one kernel per layer instead of the trunk kernels
-        lib.rumpy_debug_set_trunk(0)
-    if os.environ.get('RUMPY_B200_BAND') == '1':      # opt-in experiment: role-swapped band kernel (trunk_band.cuh)
-        lib.rumpy_debug_set_trunk_band(1)
-    if os.environ.get('RUMPY_B200_CLUSTER') == '0':   # debug switch: no cluster-per-image kernel (dataflow kernel only)
-        lib.rumpy_debug_set_trunk_cluster(0)
-    if os.environ.get('RUMPY_B200_CLUSTER_GROUPS') in ('2', '4'):   # epilogue groups of the cluster kernel
-        lib.rumpy_debug_set_cluster_groups(int(os.environ['RUMPY_B200_CLUSTER_GROUPS']))
-    if os.environ.get('RUMPY_B200_FUSED_CA') == '1':  # opt-in: conv2 + CALayer + skip in one kernel (conv3x3_ca.cuh)
-        lib.rumpy_debug_set_fused_ca(1)
     _lib = lib
     return lib
 

@@ -8,13 +8,11 @@
 namespace rb {
 
 thread_local std::string g_last_error;
-long long* g_debug_timeline = nullptr;  // debug hook (rumpy_debug_set_timeline)
-int g_use_pdl = 1;                       // programmatic dependent launch between layers (rumpy_debug_set_pdl)
-int g_conv_2x = 0;                       // experiment: stream B, <=113 KB smem, two CTAs per SM (rumpy_debug_set_conv2x)
-extern int g_use_trunk_bwd;
-extern int g_use_trunk;                  // net.cu: persistent trunk kernel (trunk_pipe.cuh), default on
-int g_use_fused_ca = 0;                  // conv2 + CALayer in one kernel (TMEM-held accumulators + grid barrier):
-                                         // correct but not faster at the benchmark shapes, opt-in
+static const Options g_default_options{};
+static thread_local const Options* t_options = nullptr;   // options of the net whose entry point runs on this thread
+const Options& opt() { return t_options ? *t_options : g_default_options; }
+OptScope::OptScope(const Options* o) : prev(t_options) { t_options = o; }
+OptScope::~OptScope() { t_options = prev; }
 
 int set_error(int code, const char* fmt, ...) {
   char buf[512];
@@ -163,7 +161,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.pool_partial = d.pool_partial;
   a.out_nchw = d.out_nchw;
   a.cout_real = d.cout_real;
-  a.dbg = g_debug_timeline;
+  a.dbg = opt().timeline;
   uint32_t flags = d.flags & (kConvRelu | kConvPool);
   if (d.y_bf16) flags |= kConvOutBf16;
   if (d.y_f32) flags |= kConvOutF32;
@@ -194,7 +192,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.stg_bufs = bufs;
   p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages, flags, bufs);
   int ctas_per_sm = 1;
-  if (g_conv_2x && !thin && bn == 64 && cin_chunks == 1 && !has_in &&
+  if (opt().conv_2x && !thin && bn == 64 && cin_chunks == 1 && !has_in &&
       conv_smem_bytes(64, false, 1, 2, flags, 1) <= 113 * 1024) {
     // two small CTAs per SM: weights streamed with the halo boxes, one tile's prologue/epilogue overlaps the
     // other's MMAs, and the next layer's CTAs (PDL) can start as soon as one of the two slots frees up
@@ -240,7 +238,7 @@ static int launch_conv_t(const ConvPlan& p, cudaStream_t s) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = opt().use_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p.maps, p.args);
   if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "conv3x3 launch: %s", cudaGetErrorString(e));
   return RUMPY_OK;
@@ -295,7 +293,7 @@ int conv_ca_plan_build(ConvPlan* p, CaFusedArgs* ca, const ConvDesc& d, float* u
   a.tiles_y = (d.H + kTileH - 1) / kTileH;
   a.m_tiles = d.N * a.tiles_x * a.tiles_y;
   a.n_tiles = 1; a.cin_chunks = 1; a.a_chunks_per_map = 1; a.o_chunks_per_map = 1; a.cout = 64;
-  a.alpha = 1.f; a.bias = d.bias; a.pool_partial = d.pool_partial; a.dbg = g_debug_timeline;
+  a.alpha = 1.f; a.bias = d.bias; a.pool_partial = d.pool_partial; a.dbg = opt().timeline;
   a.stages = 4; a.stg_bufs = 2;
   p->bn = 64; p->resident = true;
   p->smem = conv_ca_smem_bytes(a.stages);
@@ -329,7 +327,7 @@ int conv_ca_launch(const ConvPlan& p, const CaFusedArgs& ca, cudaStream_t s) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = opt().use_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_ca_kernel, p.maps, p.args, ca);
   if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "conv_ca launch: %s", cudaGetErrorString(e));
   return RUMPY_OK;
@@ -351,14 +349,6 @@ extern "C" {
 
 int rumpy_version(void) { return RUMPY_B200_VERSION; }
 /* debug hook, not part of the public header: per-CTA clock64 timeline (16 slots per CTA) for conv kernels */
-int rumpy_debug_set_timeline(void* buf) { g_debug_timeline = static_cast<long long*>(buf); return 0; }
-int rumpy_debug_set_pdl(int on) { g_use_pdl = on; return 0; }
-int rumpy_debug_set_conv2x(int on) { g_conv_2x = on; return 0; }
-int rumpy_debug_set_fused_ca(int on) { g_use_fused_ca = on; return 0; }
-int rumpy_debug_get_fused_ca(void) { return g_use_fused_ca; }
-int rumpy_debug_set_trunk(int on) { g_use_trunk = on; return 0; }
-int rumpy_debug_get_trunk(void) { return g_use_trunk; }
-int rumpy_debug_set_trunk_bwd(int on) { g_use_trunk_bwd = on; return 0; }
 const char* rumpy_last_error(void) { return g_last_error.c_str(); }
 int rumpy_device_check(void) { return device_info(nullptr); }
 
@@ -458,7 +448,7 @@ int ca_apply_launch(const float* pool_partial, int partials_per_img, float* comp
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = opt().use_pdl ? 1 : 0;
   const int HW = H * W;
   __nv_bfloat16* xob = static_cast<__nv_bfloat16*>(x_out_bf16);
   cudaError_t le;

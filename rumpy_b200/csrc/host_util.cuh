@@ -16,6 +16,42 @@
 #include <vector>
 
 namespace rb {
+// Per-handle execution options (rumpy_net_set_option / rumpy_net_set_trunk_events / rumpy_net_set_timeline in
+// include/rumpy_b200.h).  There is NO process-global switch: every rumpy_net_* entry point installs its handle's
+// options for the duration of the call on the calling thread (OptScope); code that runs outside a net handle (the
+// stand-alone conv / wgrad entry points) sees the defaults.
+struct Options {
+  int use_trunk = 1;          // whole 64-channel body in ONE kernel when the shape fits (0: one kernel per layer)
+  int use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
+  int cluster_groups = 2;     // epilogue groups of the cluster kernel (2 or 4)
+  int use_band = 0;           // role-swapped band kernel (trunk_band.cuh): experiment, slower than the cluster kernel
+  int use_trunk_bwd = 1;      // backward of the RCAN body in the persistent dataflow kernel (trunk_bwd.cuh)
+  int use_fused_ca = 0;       // conv2 + CALayer in one kernel (conv3x3_ca.cuh): correct, not faster
+  int wgrad_chunks = 4;       // chunks of the batched wgrad (gradient ranges handed to the all-reduce one by one)
+  int wgrad_tiles_per_split = 64;   // pixel tiles per split-K job (measured: 32 -> 14.97, 64 -> 14.76, 128 -> 14.73 ms)
+  int use_pdl = 1;            // programmatic dependent launch between per-layer kernels
+  int conv_2x = 0;            // experiment: two small conv CTAs per SM
+  int trunk_sync_mode = 8;    // dataflow kernel: release store of the tile epoch (needed, DESIGN.md trunk protocol)
+  int trunk_dbg_layers = 0;   // > 0: trunk kernels write a clock64 timeline of this many layers to `timeline`
+  long long* timeline = nullptr;
+  cudaEvent_t trunk_ev0 = nullptr, trunk_ev1 = nullptr;   // recorded right before / after the trunk kernel
+  // everything a cached plan depends on
+  unsigned plan_sig() const {
+    return unsigned(use_trunk) | unsigned(use_cluster) << 1 | unsigned(use_trunk_bwd) << 2 | unsigned(use_band) << 3 |
+           unsigned(use_fused_ca) << 4 | unsigned(cluster_groups == 4) << 5 | unsigned(use_pdl) << 6 |
+           unsigned(conv_2x) << 7 | unsigned(wgrad_chunks) << 8 | unsigned(wgrad_tiles_per_split) << 12 |
+           unsigned(timeline != nullptr) << 28;
+  }
+};
+const Options& opt();
+struct OptScope {
+  const Options* prev;
+  explicit OptScope(const Options* o);
+  ~OptScope();
+};
+}  // namespace rb
+
+namespace rb {
 
 extern thread_local std::string g_last_error;
 int set_error(int code, const char* fmt, ...);

@@ -36,11 +36,6 @@ using QScaleJob = QScaleJobHost;   // q_scale_kernel job (w1 == nullptr: no q-la
 
 enum OpType { OP_HEAD, OP_QSCALE, OP_CONV, OP_CA, OP_CONV_CA, OP_TRUNK, OP_TRUNK_BWD, OP_TAIL_BWD, OP_CA_BWD, OP_ADD, OP_HEAD_WGRAD, OP_LAM, OP_CSAM, OP_DQ, OP_QGRAD, OP_CSAM_BWD, OP_LAM_BWD, OP_HAN_PG };
 
-extern int g_use_fused_ca;
-extern int g_use_cluster;
-extern int g_use_band;
-int g_use_trunk_bwd = 1;   // backward of the RCAN body in the persistent dataflow kernel (trunk_bwd.cuh)
-int g_use_trunk = 1;   // whole 64-channel body in the persistent dataflow kernel (trunk_pipe.cuh) when the shape fits
 
 struct Op {
   OpType type;
@@ -71,6 +66,7 @@ struct BlockRec { const void* in_b; void* t; void* u; float* sv; int conv1, conv
 struct GroupRec { std::vector<BlockRec> blocks; const void* tail_in_b; int conv_tail; };
 
 struct Net {
+  Options opt;                // per-handle execution options (rumpy_net_set_option)
   int arch, C, n_groups, n_blocks, reduction, scale;
   float res_scale;
   int in_feats, out_feats, u_f32;
@@ -272,10 +268,8 @@ struct Bump {
   void* take(size_t bytes) { void* p = base ? base + off : nullptr; off = align_up(off + bytes, 1024); return p; }
 };
 
-int g_wgrad_chunks = 4;             // chunks of the batched wgrad (gradient ranges handed to the all-reduce one by one)
-int g_wgrad_tiles_per_split = 64;   // pixel tiles per split-K job of the batched wgrad kernel (measured: 32 -> 14.97, 64 -> 14.76, 128 -> 14.73, 256 -> 15.12 ms per RCAN train step)
 static int wgrad_splits(int m_tiles) {
-  int s = (m_tiles + g_wgrad_tiles_per_split - 1) / g_wgrad_tiles_per_split;
+  int s = (m_tiles + opt().wgrad_tiles_per_split - 1) / opt().wgrad_tiles_per_split;
   if (s > 64) s = 64;
   if (s < 1) s = 1;
   return s;
@@ -362,7 +356,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   const float* cur_f = head_f;    // its fp32 residual-stream copy
   const int Cr = n->arch == 0 ? C / n->reduction : 1;
   // ---- the whole body (every 64->64 conv, CA, skips) as ONE persistent dataflow kernel when the shape fits
-  const bool use_trunk = g_use_trunk && C == 64 && trunk_supported(N, H, W, C, Cr);
+  const bool use_trunk = opt().use_trunk && C == 64 && trunk_supported(N, H, W, C, Cr);
   std::unique_ptr<TrunkPlan> trunk;
   std::vector<GroupRec> groups;
   const void* trunk_body_in = nullptr;
@@ -472,7 +466,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     float* pool_compact = static_cast<float*>(bp.take(size_t(N) * 64 * C * 4));
     const size_t n_rcab = size_t(n->n_groups) * n->n_blocks;
     unsigned long long* ca_counters = static_cast<unsigned long long*>(bp.take(n_rcab * sizeof(unsigned long long)));
-    const bool fuse_ca = g_use_fused_ca && !n->qrcan && n->u_f32 && build && conv_ca_supported(N, H, W, C, C);
+    const bool fuse_ca = opt().use_fused_ca && !n->qrcan && n->u_f32 && build && conv_ca_supported(N, H, W, C, C);
     if (build) { n->ca_counters = ca_counters; n->ca_counters_bytes = n_rcab * sizeof(unsigned long long); n->ca_counters_dirty = true; }
     int cai = 0;
     for (int g = 0; g < n->n_groups; ++g) {
@@ -721,7 +715,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       conv_op(bops, n->convs[n->conv_body], d, true);
       sites.push_back({n->conv_body, GB_body, body_in_b, H, W, 1.f, nullptr, 0});
     }
-    const bool use_trunk_bwd = g_use_trunk_bwd && use_trunk && n->arch == 0;
+    const bool use_trunk_bwd = opt().use_trunk_bwd && use_trunk && n->arch == 0;
     if (use_trunk_bwd) {
       // ---- the whole backward body as ONE persistent dataflow kernel (trunk_bwd.cuh); the gradient stream Q lives
       // in tensor memory, P (gradient w.r.t. the group input) is updated in place once per group
@@ -938,7 +932,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
       size_t job_cursor = 0, cs_cursor = 0;
       int last_site_param = 0;
       std::vector<int> chunk_job_end, chunk_rjob_end, chunk_first_param;
-      const size_t per_chunk = (njobs + g_wgrad_chunks - 1) / size_t(g_wgrad_chunks);
+      const size_t per_chunk = (njobs + opt().wgrad_chunks - 1) / size_t(opt().wgrad_chunks);
       for (const Site& s : sites) {
         const ConvW& cw = n->convs[s.conv];
         if (!wg_jobs.empty() && wg_jobs.size() >= per_chunk * (chunk_job_end.size() + 1)) {
@@ -1023,12 +1017,12 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
 
 static int ensure_plan(Net* n, const void* packed, void* workspace, int N, int H, int W, int training) {
   if (n->plan_packed != packed || n->plan_ws != workspace || n->pN != N || n->pH != H || n->pW != W ||
-      n->p_training != training || n->p_trunk != g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd + 8 * g_use_band) {
+      n->p_training != training || n->p_trunk != int(opt().plan_sig())) {
     size_t bytes = 0;
     n->plan_packed = nullptr;
     if (int e = build_plan(n, packed, workspace, N, H, W, training, &bytes, true)) return e;
     n->plan_packed = packed; n->plan_ws = workspace; n->pN = N; n->pH = H; n->pW = W; n->p_training = training;
-    n->p_trunk = g_use_trunk + 2 * g_use_cluster + 4 * g_use_trunk_bwd + 8 * g_use_band;
+    n->p_trunk = int(opt().plan_sig());
   }
   return RUMPY_OK;
 }
@@ -1128,8 +1122,66 @@ int rumpy_net_set_metadata(void* net, const float* metadata, int N, int M) {
   return RUMPY_OK;
 }
 
-int rumpy_debug_set_wgrad_chunks(int chunks) { rb::g_wgrad_chunks = chunks < 1 ? 1 : (chunks > 8 ? 8 : chunks); return 0; }
-int rumpy_debug_set_wgrad_split(int tiles) { rb::g_wgrad_tiles_per_split = tiles < 1 ? 1 : tiles; return 0; }
+
+/* Per-handle execution options (no process-global switches).  Takes effect for plans built afterwards: the cached
+ * plan is rebuilt by the next forward when an option it depends on changed. */
+int rumpy_net_set_option(void* net, const char* name, long long value) {
+  if (!net || !name) return set_error(RUMPY_ERR_ARG, "net_set_option: null");
+  Options& o = static_cast<Net*>(net)->opt;
+  const std::string k(name);
+  const int v = int(value);
+  if (k == "trunk") o.use_trunk = v != 0;
+  else if (k == "cluster") o.use_cluster = v != 0;
+  else if (k == "cluster_groups") o.cluster_groups = v == 4 ? 4 : 2;
+  else if (k == "band") o.use_band = v != 0;
+  else if (k == "trunk_bwd") o.use_trunk_bwd = v != 0;
+  else if (k == "fused_ca") o.use_fused_ca = v != 0;
+  else if (k == "wgrad_chunks") o.wgrad_chunks = v < 1 ? 1 : (v > 8 ? 8 : v);
+  else if (k == "wgrad_tiles_per_split") o.wgrad_tiles_per_split = v < 1 ? 1 : v;
+  else if (k == "pdl") o.use_pdl = v != 0;
+  else if (k == "conv_2x") o.conv_2x = v != 0;
+  else if (k == "trunk_sync_mode") o.trunk_sync_mode = v;
+  else return set_error(RUMPY_ERR_ARG, "net_set_option: unknown option '%s'", name);
+  return RUMPY_OK;
+}
+
+long long rumpy_net_get_option(void* net, const char* name) {
+  if (!net || !name) return -1;
+  const Options& o = static_cast<Net*>(net)->opt;
+  const std::string k(name);
+  if (k == "trunk") return o.use_trunk;
+  if (k == "cluster") return o.use_cluster;
+  if (k == "cluster_groups") return o.cluster_groups;
+  if (k == "band") return o.use_band;
+  if (k == "trunk_bwd") return o.use_trunk_bwd;
+  if (k == "fused_ca") return o.use_fused_ca;
+  if (k == "wgrad_chunks") return o.wgrad_chunks;
+  if (k == "wgrad_tiles_per_split") return o.wgrad_tiles_per_split;
+  if (k == "pdl") return o.use_pdl;
+  if (k == "conv_2x") return o.conv_2x;
+  if (k == "trunk_sync_mode") return o.trunk_sync_mode;
+  return -1;
+}
+
+/* Measurement hook: CUDA events (cudaEvent_t, caller-owned) recorded on the launching stream right before / after
+ * the trunk kernel of every forward of THIS handle; NULL, NULL switches it off. */
+int rumpy_net_set_trunk_events(void* net, void* ev_start, void* ev_stop) {
+  if (!net) return set_error(RUMPY_ERR_ARG, "net_set_trunk_events: null");
+  Options& o = static_cast<Net*>(net)->opt;
+  o.trunk_ev0 = static_cast<cudaEvent_t>(ev_start);
+  o.trunk_ev1 = static_cast<cudaEvent_t>(ev_stop);
+  return RUMPY_OK;
+}
+
+/* Diagnostics: device buffer (caller-owned, int64) that the kernels of THIS handle fill with clock64 stamps; `layers`
+ * > 0 also asks the trunk kernels for a per-layer timeline of that many layers.  NULL / 0 switches it off. */
+int rumpy_net_set_timeline(void* net, void* buf, int layers) {
+  if (!net) return set_error(RUMPY_ERR_ARG, "net_set_timeline: null");
+  Options& o = static_cast<Net*>(net)->opt;
+  o.timeline = static_cast<long long*>(buf);
+  o.trunk_dbg_layers = buf ? layers : 0;
+  return RUMPY_OK;
+}
 
 int rumpy_net_destroy(void* net) {
   delete static_cast<Net*>(net);
@@ -1178,6 +1230,7 @@ long long rumpy_net_packed_bytes(void* net, int training) {
 long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training) {
   if (!net) return -1;
   size_t bytes = 0;
+  OptScope scope(&static_cast<Net*>(net)->opt);
   if (build_plan(static_cast<Net*>(net), nullptr, nullptr, N, H, W, training, &bytes, false)) return -1;
   return (long long)bytes;
 }
@@ -1187,6 +1240,7 @@ long long rumpy_net_workspace_bytes(void* net, int N, int H, int W, int training
 int rumpy_net_pack(void* net_, const float* const* params, void* packed, int training, void* stream) {
   Net* n = static_cast<Net*>(net_);
   if (!n || !params || !packed) return set_error(RUMPY_ERR_ARG, "net_pack: null");
+  OptScope scope(&n->opt);
   if (int e = device_info(nullptr)) return e;
   char* pk = static_cast<char*>(packed);
   const size_t total = training ? n->packed_bytes_train : n->packed_bytes;
@@ -1222,6 +1276,7 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
   Net* n = static_cast<Net*>(net_);
   if (!n || !params || !packed || !x_nchw || !y_nchw || !workspace)
     return set_error(RUMPY_ERR_ARG, "net_forward: null pointer");
+  OptScope scope(&n->opt);
   if (int e = device_info(nullptr)) return e;
   cudaStream_t stream = cudaStream_t(stream_);
   if (int e = ensure_plan(n, packed, workspace, N, H, W, training)) return e;
@@ -1303,6 +1358,7 @@ int rumpy_net_backward(void* net_, const float* const* params, const void* packe
   Net* n = static_cast<Net*>(net_);
   if (!n || !params || !packed || !x_nchw || !dy_nchw || !grads || !workspace)
     return set_error(RUMPY_ERR_ARG, "net_backward: null pointer");
+  OptScope scope(&n->opt);
   int sms = 0;
   if (int e = device_info(&sms)) return e;
   cudaStream_t stream = cudaStream_t(stream_);

@@ -5,15 +5,8 @@
 
 namespace rb {
 
-extern long long* g_debug_timeline;
-int g_use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
-int g_cluster_groups = 2;     // epilogue groups of the cluster kernel (2 or 4)
-int g_use_band = 0;           // role-swapped band kernel (trunk_band.cuh): opt-in (RUMPY_B200_BAND=1), slower than the cluster kernel so far
 constexpr int kClusterMaxDyn = 227 * 1024 - 8192;
 constexpr int kBandMaxDyn = 227 * 1024 - 2048;   // the band kernel has < 2 KB of static shared memory
-int g_trunk_sync_mode = 8;   // release store of the tile epoch (needed: see DESIGN.md trunk protocol)
-cudaEvent_t g_trunk_ev0 = nullptr, g_trunk_ev1 = nullptr;   // optional: recorded around the trunk kernel (bench)
-int g_trunk_dbg_layers = 0;   // > 0: the kernel writes a [grid][layers][2][8] clock64 timeline to g_debug_timeline
 
 static size_t al(size_t v) { return (v + 1023) / 1024 * 1024; }
 
@@ -76,7 +69,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
   // ---- one cluster per image?  pick the decomposition with the fewest tiles per CTA that keeps all N clusters
   // co-resident (clusters are independent, so this is a performance condition, not a correctness one)
   plan->cluster = false;
-  if (g_use_cluster && allow_cluster) {
+  if (opt().use_cluster && allow_cluster) {
     static bool attr_set = false;
     if (!attr_set) {
       // dynamic + static (3.2 KB with 2 epilogue groups, 5.8 KB with 4) must stay within 227 KB
@@ -97,13 +90,13 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         const int perim = kClusterTileH * th + kClusterTileW * tw;
         if (th * tw > best_tiles || (th * tw == best_tiles && perim >= best_perim)) continue;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(cluster_threads(g_cluster_groups)); cfg.dynamicSmemBytes = smem;
+        cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(cluster_threads(opt().cluster_groups)); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int active = 0;
-        if ((g_cluster_groups == 4 ? cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel_t<4>, &cfg)
+        if ((opt().cluster_groups == 4 ? cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel_t<4>, &cfg)
                                    : cudaOccupancyMaxActiveClusters(&active, trunk_cluster_kernel_t<2>, &cfg)) != cudaSuccess) {
           (void)cudaGetLastError();
           continue;
@@ -112,7 +105,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         best_tiles = th * tw; best_perim = perim;
         plan->cluster = true;
         plan->cluster_size = C;
-        plan->cluster_groups = g_cluster_groups;
+        plan->cluster_groups = opt().cluster_groups;
         plan->cluster_smem = smem;
         ClusterArgs& c = plan->cargs;
         memset(&c, 0, sizeof(c));
@@ -129,7 +122,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
   // largest cluster (most SMs) whose bands fit (<= 3 chunks of <= 143 linear pixels, shared memory) with all N
   // clusters co-resident.
   plan->band = false;
-  if (g_use_band && allow_cluster && W + 1 >= 4) {
+  if (opt().use_band && allow_cluster && W + 1 >= 4) {
     static bool attr_set = false;
     if (!attr_set) {
       if (cudaFuncSetAttribute(trunk_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBandMaxDyn) != cudaSuccess)
@@ -215,8 +208,8 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
   }
   if (plan->band) {
     BandArgs& b = plan->bargs;
-    b.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
-    b.dbg_layers = g_trunk_dbg_layers;
+    b.dbg = opt().trunk_dbg_layers > 0 ? opt().timeline : nullptr;
+    b.dbg_layers = opt().trunk_dbg_layers;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(b.N * b.C); cfg.blockDim = dim3(kBandThreads);
     cfg.dynamicSmemBytes = plan->band_smem; cfg.stream = s;
@@ -224,16 +217,16 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = b.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
+    if (opt().trunk_ev0) cudaEventRecord(opt().trunk_ev0, s);
     cudaError_t e = cudaLaunchKernelEx(&cfg, trunk_band_kernel, plan->w_tap_map, b);
     if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "trunk_band launch: %s", cudaGetErrorString(e));
-    if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
+    if (opt().trunk_ev1) cudaEventRecord(opt().trunk_ev1, s);
     return RUMPY_OK;
   }
   if (plan->cluster) {
     ClusterArgs& c = plan->cargs;
-    c.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
-    c.dbg_layers = g_trunk_dbg_layers;
+    c.dbg = opt().trunk_dbg_layers > 0 ? opt().timeline : nullptr;
+    c.dbg_layers = opt().trunk_dbg_layers;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(c.N * plan->cluster_size); cfg.blockDim = dim3(cluster_threads(plan->cluster_groups));
     cfg.dynamicSmemBytes = plan->cluster_smem; cfg.stream = s;
@@ -241,11 +234,11 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = plan->cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
+    if (opt().trunk_ev0) cudaEventRecord(opt().trunk_ev0, s);
     cudaError_t e = plan->cluster_groups == 4 ? cudaLaunchKernelEx(&cfg, trunk_cluster_kernel_t<4>, plan->w_map, c)
                                               : cudaLaunchKernelEx(&cfg, trunk_cluster_kernel_t<2>, plan->w_map, c);
     if (e != cudaSuccess) return set_error(RUMPY_ERR_CUDA, "trunk_cluster launch: %s", cudaGetErrorString(e));
-    if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
+    if (opt().trunk_ev1) cudaEventRecord(opt().trunk_ev1, s);
     return RUMPY_OK;
   }
   if (cudaMemsetAsync(plan->flags_dev, 0, plan->flags_bytes, s) != cudaSuccess)
@@ -257,13 +250,13 @@ int trunk_launch(TrunkPlan* plan, const float* const* params, cudaStream_t s) {
       return set_error(RUMPY_ERR_CUDA, "trunk cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
-  a.dbg = g_trunk_dbg_layers > 0 ? g_debug_timeline : nullptr;
-  a.dbg_layers = g_trunk_dbg_layers;
-  a.sync_mode = g_trunk_sync_mode;
-  if (g_trunk_ev0) cudaEventRecord(g_trunk_ev0, s);
+  a.dbg = opt().trunk_dbg_layers > 0 ? opt().timeline : nullptr;
+  a.dbg_layers = opt().trunk_dbg_layers;
+  a.sync_mode = opt().trunk_sync_mode;
+  if (opt().trunk_ev0) cudaEventRecord(opt().trunk_ev0, s);
   trunk_pipe_kernel<<<plan->grid, kTrunkThreads, kTrunkSmemBytes, s>>>(plan->w_map, a);
   if (int e = check_launch("trunk_pipe")) return e;
-  if (g_trunk_ev1) cudaEventRecord(g_trunk_ev1, s);
+  if (opt().trunk_ev1) cudaEventRecord(opt().trunk_ev1, s);
   return RUMPY_OK;
 }
 
@@ -400,19 +393,3 @@ int dq_reduce_launch(const float* g_f32, const void* out_bf16, const void* x_bf1
 }
 
 }  // namespace rb
-
-extern "C" {
-int rumpy_debug_set_trunk_timeline(int layers) { rb::g_trunk_dbg_layers = layers; return 0; }
-int rumpy_debug_set_trunk_sync_mode(int mode) { rb::g_trunk_sync_mode = mode; return 0; }
-int rumpy_debug_set_trunk_cluster(int on) { rb::g_use_cluster = on; return 0; }
-/* role-swapped band kernel (trunk_band.cuh) on / off; takes effect for plans built afterwards */
-int rumpy_debug_set_trunk_band(int on) { rb::g_use_band = on; return 0; }
-/* epilogue groups of the cluster kernel: 2 (320 threads) or 4 (576 threads); takes effect for plans built afterwards */
-int rumpy_debug_set_cluster_groups(int groups) { rb::g_cluster_groups = groups == 4 ? 4 : 2; return 0; }
-/* bench hook: CUDA events (cudaEvent_t) recorded right before / after the trunk kernel of every forward; NULL = off */
-int rumpy_debug_set_trunk_events(void* ev_start, void* ev_stop) {
-  rb::g_trunk_ev0 = static_cast<cudaEvent_t>(ev_start);
-  rb::g_trunk_ev1 = static_cast<cudaEvent_t>(ev_stop);
-  return 0;
-}
-}

@@ -70,6 +70,8 @@ class TrunkEngine:
             _lib.call('rumpy_net_create', ctypes.byref(h), 2 if arch == ARCH_HAN else arch, n_feats, n_groups, n_blocks, reduction, scale,
                       float(res_scale), in_feats, out_feats, int(u_f32))
         self.handle = h
+        for name, value in _lib.env_options().items():
+            _lib.call('rumpy_net_set_option', h, name.encode(), int(value))
         n = self.lib.rumpy_net_num_params(h)
         if n != len(self.params):
             raise _lib.RumpyB200Error(f'parameter count mismatch: native {n} vs module {len(self.params)}')
@@ -96,6 +98,33 @@ class TrunkEngine:
                 self.handle = None
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ per-handle options
+    def set_option(self, name, value):
+        """rumpy_net_set_option: execution knobs of THIS engine ('trunk', 'cluster', 'cluster_groups', 'band',
+        'trunk_bwd', 'fused_ca', 'wgrad_chunks', ...).  Plans, workspaces and graphs built under the old value go."""
+        _lib.call('rumpy_net_set_option', self.handle, name.encode(), int(value))
+        self._ws.clear()
+        self._graphs.clear()
+        self._last_infer_shape = None
+        self._chunk_key = None
+
+    def get_option(self, name):
+        return int(self.lib.rumpy_net_get_option(self.handle, name.encode()))
+
+    def set_trunk_events(self, ev0, ev1):
+        """CUDA events recorded right before / after the trunk kernel of every forward (None, None = off)."""
+        _lib.call('rumpy_net_set_trunk_events', self.handle, None if ev0 is None else ev0.cuda_event,
+                  None if ev1 is None else ev1.cuda_event)
+        self._graphs.clear()
+        self._last_infer_shape = None
+
+    def set_timeline(self, buf, layers=0):
+        """Device int64 tensor the kernels fill with clock64 stamps (None = off)."""
+        _lib.call('rumpy_net_set_timeline', self.handle, None if buf is None else buf.data_ptr(), int(layers))
+        self._timeline = buf
+        self._graphs.clear()
+        self._last_infer_shape = None
 
     # ------------------------------------------------------------------ parameter tracking
     def _param_ptrs(self):

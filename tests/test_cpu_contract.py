@@ -33,6 +33,15 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, s), f'{s} declared in include/rumpy_b200.h but not exported'
     assert sorted(_lib.SIGNATURES) == syms, 'ctypes SIGNATURES and header disagree'
     assert lib.rumpy_version() == 100
+    # ... and nothing else: no undeclared entry points, no process-global debug switches (every knob is a per-handle
+    # option, rumpy_net_set_option)
+    import shutil
+    import subprocess
+    if shutil.which('nm'):
+        out = subprocess.run(['nm', '-D', '--defined-only', _lib.LIB_PATH], capture_output=True, text=True).stdout
+        exported = sorted(line.split()[-1] for line in out.splitlines()
+                          if ' T ' in line and line.split()[-1].startswith('rumpy_'))
+        assert exported == syms, f'exported but not declared: {sorted(set(exported) - set(syms))}'
 
 
 def test_no_gpu_fails_loudly():

@@ -18,8 +18,6 @@ MODES = {'per-layer': (0, 0), 'dataflow': (1, 0), 'cluster': (1, 1)}
 def _lib():
     from rumpy_b200 import _lib
     lib = _lib.load()
-    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
     return lib
 
 
@@ -41,9 +39,9 @@ def test_han_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
     outs = {}
     try:
         for mode, (trunk, cluster) in MODES.items():
-            lib.rumpy_debug_set_trunk(trunk)
-            lib.rumpy_debug_set_trunk_cluster(cluster)
             eng = net.native_engine()
+            eng.set_option('trunk', trunk)
+            eng.set_option('cluster', cluster)
             eng._ws.clear()
             eng._graphs.clear()
             eng._last_infer_shape = None
@@ -55,8 +53,8 @@ def test_han_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
             err = float(np.abs(outs[mode] - ref).max())
             assert err <= 1e-2, f'{name} [{mode}]: max-abs {err} vs the reference output'
     finally:
-        lib.rumpy_debug_set_trunk(1)
-        lib.rumpy_debug_set_trunk_cluster(1)
+        net.native_engine().set_option('trunk', 1)
+        net.native_engine().set_option('cluster', 1)
 
 
 def test_han_handler_cfg2_batch_vs_oracle(tmp_path):
@@ -92,18 +90,13 @@ def test_han_gradients_and_adam_steps_vs_reference_golden(golden_dir, name, bwd)
     gold = np.load(os.path.join(golden_dir, 'han.npz'))
     nb, scale, sd, x = recipe.hcase_tensors(name)
     y = recipe.make_input((x.shape[0], 3, x.shape[2] * scale, x.shape[3] * scale), recipe.HCASES[name][4] + 1000)
-    lib = _lib()
-    lib.rumpy_debug_set_trunk_bwd.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_bwd(bwd)
-    try:
-        _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam)
-    finally:
-        lib.rumpy_debug_set_trunk_bwd(1)
+    _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam, bwd)
 
 
-def _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam):
+def _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam, bwd):
     net = _han(nb, scale, sd).train()
     eng = net.native_engine()
+    eng.set_option('trunk_bwd', bwd)
     xt, yt = torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV)
     out = eng.forward(xt, training=True)
     loss, dy = train_native.l1_loss(out, yt, want_grad=True)
@@ -120,6 +113,7 @@ def _check_han_training(gold, name, nb, scale, sd, x, y, train_native, FusedAdam
             cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-30))
             assert cos >= (0.999 if ref.size >= 64 else 0.995), (k, cos)   # 27-tap csa.conv.weight: few elements
     net = _han(nb, scale, sd).train()
+    net.native_engine().set_option('trunk_bwd', bwd)
     opt = FusedAdam(list(net.parameters()), lr=1e-4)
     losses = [train_native.train_step(net, opt, xt, yt)[0].item() for _ in range(3)]
     np.testing.assert_allclose(losses, gold[name + '::train_losses'], rtol=0.01)
@@ -141,16 +135,16 @@ def test_qhan_forward_and_gradients_vs_reference_golden(golden_dir):
     lib = _lib()
     try:
         for mode, (trunk, cluster) in MODES.items():
-            lib.rumpy_debug_set_trunk(trunk)
-            lib.rumpy_debug_set_trunk_cluster(cluster)
             eng = net.native_engine()
+            eng.set_option('trunk', trunk)
+            eng.set_option('cluster', cluster)
             eng._ws.clear(); eng._graphs.clear(); eng._last_infer_shape = None
             with torch.no_grad():
                 out = net(xt, attrs).cpu().numpy()
             assert float(np.abs(out - gold['qhan::out']).max()) <= 1e-2, mode
     finally:
-        lib.rumpy_debug_set_trunk(1)
-        lib.rumpy_debug_set_trunk_cluster(1)
+        net.native_engine().set_option('trunk', 1)
+        net.native_engine().set_option('cluster', 1)
     net.train()
     eng = net.native_engine()
     y = recipe.make_input((x.shape[0], 3, x.shape[2] * kw['scale'], x.shape[3] * kw['scale']), recipe.QHCASE['xseed'] + 1000)

@@ -23,8 +23,6 @@ def _dev():
 def _lib():
     from rumpy_b200 import _lib
     lib = _lib.load()
-    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
     return lib
 
 
@@ -51,9 +49,9 @@ def test_qrcan_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
     outs = {}
     try:
         for mode, (trunk, cluster) in MODES.items():
-            lib.rumpy_debug_set_trunk(trunk)
-            lib.rumpy_debug_set_trunk_cluster(cluster)
             eng = net.native_engine()
+            eng.set_option('trunk', trunk)
+            eng.set_option('cluster', cluster)
             eng._ws.clear()
             eng._graphs.clear()
             eng._last_infer_shape = None
@@ -65,8 +63,8 @@ def test_qrcan_matches_reference_golden_in_every_trunk_mode(golden_dir, name):
             err = float(np.abs(outs[mode] - ref).max())
             assert err <= 1e-2, f'{name} [{mode}]: max-abs {err} vs the reference output'
     finally:
-        lib.rumpy_debug_set_trunk(1)
-        lib.rumpy_debug_set_trunk_cluster(1)
+        net.native_engine().set_option('trunk', 1)
+        net.native_engine().set_option('cluster', 1)
     for mode in ('dataflow', 'cluster'):
         assert float(np.abs(outs[mode] - outs['per-layer']).max()) <= 5e-3
 
@@ -166,12 +164,8 @@ def test_qrcan_gradients_vs_reference_golden(golden_dir, name, trunk):
     gold = np.load(os.path.join(golden_dir, 'qrcan.npz'))
     kw, has_q, sd, x, meta = recipe.qcase_tensors(name)
     net = _qrcan(kw, sd).train()
-    lib = _lib()
-    lib.rumpy_debug_set_trunk(trunk)
-    try:
-        _check_qrcan_gradients(net, gold, name, kw, has_q, x, train_native)
-    finally:
-        lib.rumpy_debug_set_trunk(1)
+    net.native_engine().set_option('trunk', trunk)
+    _check_qrcan_gradients(net, gold, name, kw, has_q, x, train_native)
 
 
 def _check_qrcan_gradients(net, gold, name, kw, has_q, x, train_native):

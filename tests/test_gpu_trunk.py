@@ -31,10 +31,6 @@ def _dev():
 def _lib():
     from rumpy_b200 import _lib
     lib = _lib.load()
-    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_cluster_groups.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_band.argtypes = [ctypes.c_int]
     return lib
 
 
@@ -52,13 +48,9 @@ def _run_modes(net, x):
     outs, modes = {}, {}
     try:
         for name, (trunk, cluster, groups, band) in MODES.items():
-            lib.rumpy_debug_set_trunk(trunk)
-            lib.rumpy_debug_set_trunk_band(band)
-            lib.rumpy_debug_set_trunk_cluster(cluster)
-            lib.rumpy_debug_set_cluster_groups(groups)
             eng = net.native_engine()
-            eng._ws.clear()
-            eng._graphs.clear()
+            for opt_name, v in (('trunk', trunk), ('band', band), ('cluster', cluster), ('cluster_groups', groups)):
+                eng.set_option(opt_name, v)
             with torch.no_grad():
                 a = eng.forward(x).clone()
                 b = eng.forward(x).clone()
@@ -67,10 +59,9 @@ def _run_modes(net, x):
             outs[name] = a
             modes[name] = lib.rumpy_net_trunk_mode(eng.handle)
     finally:
-        lib.rumpy_debug_set_trunk(1)
-        lib.rumpy_debug_set_trunk_cluster(1)
-        lib.rumpy_debug_set_cluster_groups(DEFAULT_GROUPS)
-        lib.rumpy_debug_set_trunk_band(0)
+        eng = net.native_engine()
+        for opt_name, v in (('trunk', 1), ('band', 0), ('cluster', 1), ('cluster_groups', DEFAULT_GROUPS)):
+            eng.set_option(opt_name, v)
     return outs, modes
 
 

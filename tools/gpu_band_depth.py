@@ -8,8 +8,6 @@ from rumpy_b200 import _lib
 from rumpy_b200.SISR.models.advanced.architectures import RCAN
 
 lib = _lib.load()
-for f in ('rumpy_debug_set_trunk', 'rumpy_debug_set_trunk_band', 'rumpy_debug_set_trunk_cluster'):
-    getattr(lib, f).argtypes = [ctypes.c_int]
 dev = torch.device('cuda:0')
 shape = tuple(int(v) for v in os.environ.get('SHAPE', '16,3,48,48').split(','))
 for g, b in [tuple(int(v) for v in t.split("x")) for t in os.environ.get("NETS", "1x3,1x20,2x20,10x20").split(",")]:
@@ -21,8 +19,7 @@ for g, b in [tuple(int(v) for v in t.split("x")) for t in os.environ.get("NETS",
     x = torch.from_numpy(recipe.make_input(shape, seed=8)).to(dev)
     outs = {}
     for name, (trunk, band) in {'per-layer': (0, 0), 'band': (1, 1), 'band2': (1, 1), 'cluster': (1, 0)}.items():
-        lib.rumpy_debug_set_trunk(trunk); lib.rumpy_debug_set_trunk_band(band)
-        eng = net.native_engine(); eng._ws.clear(); eng._graphs.clear()
+        eng = net.native_engine(); eng.set_option('trunk', trunk); eng.set_option('band', band)
         with torch.no_grad():
             outs[name] = eng.forward(x).clone()
         torch.cuda.synchronize()
@@ -33,4 +30,3 @@ for g, b in [tuple(int(v) for v in t.split("x")) for t in os.environ.get("NETS",
         d = (o - base).abs()
         return f'max {float(d.max()):.4g} nan {int(torch.isnan(o).sum())} imgs_bad {[int(i) for i in torch.nonzero(torch.isnan(o).flatten(1).any(1)).flatten()][:16]}'
     print(f'{g}x{b}: band(mode {outs["band_mode"]}) {stat(outs["band"])} | rerun equal {bool((outs["band"] == outs["band2"]).all())} | cluster(mode {outs["cluster_mode"]}) {stat(outs["cluster"])}', flush=True)
-lib.rumpy_debug_set_trunk(1); lib.rumpy_debug_set_trunk_band(1)

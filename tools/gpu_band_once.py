@@ -9,6 +9,7 @@ G, B = int(os.environ.get('G', 2)), int(os.environ.get('B', 20))
 net = RCAN(n_resgroups=G, n_resblocks=B).to(dev).eval()
 x = torch.rand((16, 3, 48, 48), device=dev)
 eng = net.native_engine()
+eng.set_option('band', int(os.environ.get('BAND', 1)))
 with torch.no_grad():
     for _ in range(int(os.environ.get('REPS', 3))):
         eng.forward(x)

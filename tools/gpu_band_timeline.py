@@ -7,17 +7,15 @@ import torch, recipe
 from rumpy_b200 import _lib
 from rumpy_b200.SISR.models.advanced.architectures import RCAN
 lib = _lib.load()
-lib.rumpy_debug_set_timeline.argtypes = [ctypes.c_void_p]
-lib.rumpy_debug_set_trunk_timeline.argtypes = [ctypes.c_int]
 dev = torch.device('cuda:0')
 G, B = int(os.environ.get('G', 2)), int(os.environ.get('B', 4))
 net = RCAN(n_resgroups=G, n_resblocks=B).to(dev).eval()
 x = torch.rand((16, 3, 48, 48), device=dev)
 LAYERS = G * (2 * B + 1) + 1
 dbg = torch.zeros((96, LAYERS, 16), dtype=torch.int64, device=dev)
-lib.rumpy_debug_set_timeline(dbg.data_ptr())
-lib.rumpy_debug_set_trunk_timeline(LAYERS)
 eng = net.native_engine()
+eng.set_option('band', int(os.environ.get('BAND', 1)))
+eng.set_timeline(dbg, LAYERS)
 with torch.no_grad():
     for _ in range(3): eng.forward(x)
 torch.cuda.synchronize()
@@ -34,4 +32,4 @@ for cta in (48, 53):
               f'  pool +{rel(4):6d}  epi_done +{rel(3):6d} | acc_empty ok {rel(8):5d} {rel(9):5d} {rel(10):5d} | chunk issued {rel(5):5d} {rel(6):5d} {rel(7):5d}'
               f' | epi loaded {rel(11):5d} {rel(12):5d} {rel(13):5d} | cp0 {rel(14):5d} {rel(15):5d}')
         prev = r[0].item()
-lib.rumpy_debug_set_trunk_timeline(0)
+eng.set_timeline(None)

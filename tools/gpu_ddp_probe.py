@@ -16,7 +16,6 @@ dev = torch.device('cuda', local)
 dist.init_process_group('nccl', device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 lib = _lib.load()
-lib.rumpy_debug_set_wgrad_chunks.argtypes = [ctypes.c_int]
 x, y = torch.rand((16, 3, 64, 64), device=dev), torch.rand((16, 3, 256, 256), device=dev)
 sd = {k: torch.from_numpy(v) for k, v in recipe.make_weights(recipe.rcan_spec(), seed=8).items()}
 
@@ -29,10 +28,10 @@ class Plain(parallel.GradAllReduce):          # all-reduce after the whole backw
 for name, chunks, ar in (('no all-reduce', 4, None), ('after backward', 4, Plain()), ('overlapped, 4 chunks', 4,
                          parallel.GradAllReduce()), ('overlapped, 8 chunks', 8, parallel.GradAllReduce()),
                          ('overlapped, 4 chunks, 4 MB buckets', 4, parallel.GradAllReduce(bucket_bytes=4 << 20))):
-    lib.rumpy_debug_set_wgrad_chunks(chunks)
     net = RCAN()
     net.load_state_dict(sd)
     net = net.to(dev).train()
+    net.native_engine().set_option('wgrad_chunks', chunks)
     opt = FusedAdam(list(net.parameters()), lr=1e-4)
     for _ in range(5):
         train_native.train_step(net, opt, x, y, allreduce=ar)

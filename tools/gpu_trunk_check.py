@@ -34,10 +34,8 @@ def compare(name, net, xshape, time_it=False, flop_per_px=31835520):
     x = torch.from_numpy(recipe.make_input(xshape, seed=8)).to(dev)
     outs = {}
     for mode, (trunk, cluster) in (('per-layer', (0, 0)), ('trunk-flags', (1, 0)), ('trunk-cluster', (1, 1))):
-        lib.rumpy_debug_set_trunk(trunk)
-        lib.rumpy_debug_set_trunk_cluster(cluster)
         eng = net.native_engine()
-        eng._ws.clear(); eng._graphs.clear()
+        eng.set_option('trunk', trunk); eng.set_option('cluster', cluster)
         with torch.no_grad():
             o1 = eng.forward(x).clone()
             o2 = eng.forward(x).clone()
@@ -54,8 +52,7 @@ def compare(name, net, xshape, time_it=False, flop_per_px=31835520):
     for mode in ('trunk-flags', 'trunk-cluster'):
         d = (outs['per-layer'] - outs[mode]).abs().max().item()
         print(f'[{name}] max |{mode} - per-layer| = {d:.3e} (out absmax {outs["per-layer"].abs().max().item():.3f})', flush=True)
-    lib.rumpy_debug_set_trunk(1)
-    lib.rumpy_debug_set_trunk_cluster(1)
+    net.native_engine().set_option('trunk', 1); net.native_engine().set_option('cluster', 1)
 
 
 def timeline(net, xshape, layers=12):
@@ -65,13 +62,11 @@ def timeline(net, xshape, layers=12):
     with torch.no_grad():
         eng.forward(x)
     buf = torch.zeros(148 * layers * 2 * 16, dtype=torch.int64, device=dev)
-    lib.rumpy_debug_set_timeline(ctypes.c_void_p(buf.data_ptr()))
-    lib.rumpy_debug_set_trunk_timeline(layers)
+    eng.set_timeline(buf, layers)
     with torch.no_grad():
         eng.forward(x)
     torch.cuda.synchronize()
-    lib.rumpy_debug_set_trunk_timeline(0)
-    lib.rumpy_debug_set_timeline(None)
+    eng.set_timeline(None)
     t = buf.cpu().numpy().reshape(148, layers, 2, 16)
     names = ['deps_ok', 'mma_start', 'mma_commit', 'epi_start', 'pool_done', 'y_ready', 'published', '-', 'bias_bar', 'staged',
              'store_go', 'store_done', 'pool_red', 'cnt_seen', 'y_seen', 'mean_ok']
@@ -88,10 +83,7 @@ def timeline(net, xshape, layers=12):
 
 if __name__ == '__main__':
     which = sys.argv[1:] or ['small', 'rcan2']
-    lib.rumpy_debug_set_trunk.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_cluster.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_trunk_timeline.argtypes = [ctypes.c_int]
-    lib.rumpy_debug_set_timeline.argtypes = [ctypes.c_void_p]
+    sync_mode, no_cluster = None, False
     if 'small' in which:
         compare('RCAN 1g2b 2x16x16', build('rcan', n_resgroups=1, n_resblocks=2), (2, 3, 16, 16))
         compare('RCAN 2g3b 3x20x37 ragged', build('rcan', n_resgroups=2, n_resblocks=3), (3, 3, 20, 37))
@@ -108,12 +100,12 @@ if __name__ == '__main__':
     if 'syncmodes' in which:
         net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
         eng = net.native_engine()
-        lib.rumpy_debug_set_trunk(0)
+        eng.set_option('trunk', 0)
         with torch.no_grad():
             ref = eng.forward(x).clone()
-        lib.rumpy_debug_set_trunk(1)
+        eng.set_option('trunk', 1)
         for mode in (15, 0, 8, 4, 12, 1, 2, 3, 9):
-            lib.rumpy_debug_set_trunk_sync_mode(mode)
+            eng.set_option('trunk_sync_mode', mode)
             with torch.no_grad():
                 outs = [eng.forward(x).clone() for _ in range(6)]
                 torch.cuda.synchronize()
@@ -121,10 +113,10 @@ if __name__ == '__main__':
             det = all(bool((o == outs[0]).all()) for o in outs)
             print(f'sync_mode {mode:2d}: deterministic {det}, max diff vs per-layer '
                   f'{max((o - ref).abs().max().item() for o in outs):.3e}, eager {ms:.3f} ms', flush=True)
-        lib.rumpy_debug_set_trunk_sync_mode(8)
+        eng.set_option('trunk_sync_mode', 8)
     for w in which:
         if w.startswith('sync='):
-            lib.rumpy_debug_set_trunk_sync_mode(int(w[5:])); print('sync_mode', w[5:])
+            sync_mode = int(w[5:]); print('sync_mode', w[5:])
     if 'ctimeline' in which:
         net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
         eng = net.native_engine()
@@ -132,13 +124,11 @@ if __name__ == '__main__':
             eng.forward(x)
         layers = 10
         buf = torch.zeros(148 * layers * 16, dtype=torch.int64, device=dev)
-        lib.rumpy_debug_set_timeline(ctypes.c_void_p(buf.data_ptr()))
-        lib.rumpy_debug_set_trunk_timeline(layers)
+        eng.set_timeline(buf, layers)
         with torch.no_grad():
             eng.forward(x)
         torch.cuda.synchronize()
-        lib.rumpy_debug_set_trunk_timeline(0)
-        lib.rumpy_debug_set_timeline(None)
+        eng.set_timeline(None)
         t = buf.cpu().numpy().reshape(148, layers, 16)
         names = ['in_full', 'mma_issued', 'last_acc', 'last_tile_done', 'pool_full']
         for cta in (0, 1, 5):
@@ -149,8 +139,8 @@ if __name__ == '__main__':
     if 'timeline' in which:
         timeline(build('rcan'), (16, 3, 48, 48), layers=6)
     if 'timeline3' in which:
-        lib.rumpy_debug_set_trunk_cluster(0)
-        timeline(build('rcan'), (16, 3, 64, 64), layers=8)
+        net3 = build('rcan'); net3.native_engine().set_option('cluster', 0)
+        timeline(net3, (16, 3, 64, 64), layers=8)
     if 'time2' in which:
         net = build('rcan'); x = torch.from_numpy(recipe.make_input((16, 3, 48, 48), seed=8)).to(dev)
         with torch.no_grad():
