@@ -185,6 +185,13 @@ class BaseModel(nn.Module):
                 new_state_dict[k] = v
         return new_state_dict
 
+    def _copy_stream(self, dev):
+        st = getattr(self, '_copy_stream_obj', None)
+        if st is None or st.device != dev:
+            st = torch.cuda.Stream(device=dev)
+            object.__setattr__(self, '_copy_stream_obj', st)
+        return st
+
     @staticmethod
     def _to_host(t):
         """Device -> host through page-locked memory (PyTorch's caching host allocator): a pageable `.cpu()` of the
@@ -218,15 +225,44 @@ class BaseModel(nn.Module):
         if not self.net.training:
             self.net.train()
         dev = self._torch_device()
-        x, y = x.to(device=dev, non_blocking=True), y.to(device=dev, non_blocking=True)
+        main = torch.cuda.current_stream(dev)
+        copy = self._copy_stream(dev)
+        # Host <-> device copies ride a second stream (the reference does H2D -> step -> D2H serially, :473-485):
+        #   * x (LR batch, 0.8 MB at 16 x 64 x 64) goes first on the compute stream, the 16x larger HR batch follows on
+        #     the copy stream WHILE the forward runs -- it is only needed at the loss;
+        #   * the SR batch and the loss are final after the forward, so their device-to-host copies run on the copy
+        #     stream underneath the backward + optimiser step.
+        x = x.to(device=dev, non_blocking=True)
+        if y.device != dev:
+            copy.wait_stream(main)                       # orders reuse of the previous step's buffers
+            with torch.cuda.stream(copy):
+                y = y.to(device=dev, non_blocking=True)
+                y_ready = torch.cuda.Event()
+                y_ready.record(copy)
+        else:
+            y_ready = None
+        host = {}
+
+        def start_result_copies(loss, out):
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main)
+            with torch.cuda.stream(copy):
+                copy.wait_event(fwd_done)
+                host['loss'] = torch.empty((), dtype=torch.float32, pin_memory=True)
+                host['loss'].copy_(loss, non_blocking=True)
+                if not keep_on_device:
+                    host['out'] = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+                    host['out'].copy_(out, non_blocking=True)
         loss, out = train_native.train_step(self.net, self.optimizer, x, y, grad_clip=self.grad_clip,
-                                            allreduce=self._ddp, metadata=kwargs.get('extra_channels'))
+                                            allreduce=self._ddp, metadata=kwargs.get('extra_channels'),
+                                            y_ready=y_ready, after_loss=start_result_copies)
         if self.learning_rate_scheduler is not None and not scheduler_skip:
             self.learning_rate_scheduler.step()
+        copy.synchronize()                               # results are on the host (the step itself may still run)
         if keep_on_device:
-            return loss.detach().cpu().numpy(), out.detach()
-        out_host = self._to_host(out.detach())           # also orders the loss read below after the step
-        return loss.detach().cpu().numpy(), out_host
+            return host['loss'].numpy().copy(), out.detach()
+        main.synchronize()                               # like the reference, the call returns with the step done
+        return host['loss'].numpy().copy(), host['out']
 
     def run_eval(self, x, y=None, request_loss=False, tag=None, timing=False, keep_on_device=False, *args, **kwargs):
         if self.net.training:

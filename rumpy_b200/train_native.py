@@ -35,16 +35,24 @@ def l1_loss(out, y, want_grad=False, gscale=1.0):
     return (loss, dy) if want_grad else loss
 
 
-def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None, metadata=None):
+def train_step(net, optimizer, x, y, grad_clip=None, allreduce=None, metadata=None, y_ready=None, after_loss=None):
     """One optimiser step on batch (x, y); returns (loss 0-dim device tensor, SR output on device).
-    metadata: the [N, M, 1, 1] vector of the meta-attention networks (QRCAN), else None."""
+    metadata: the [N, M, 1, 1] vector of the meta-attention networks (QRCAN), else None.
+    y_ready: CUDA event after which `y` is valid (its host-to-device copy runs on another stream while the forward
+    computes; the compute stream waits for it right before the loss).  after_loss(loss, out): called once the forward
+    and the loss are enqueued -- the handler starts the device-to-host copy of the SR batch there, so that it
+    overlaps the backward and the optimiser step."""
     eng = net.native_engine()
     if metadata is not None:
         eng.set_metadata(metadata, x.shape[0])
     if getattr(optimizer, 'flat_g', None) is not None and eng.flat_grads is not optimizer.flat_g:
         optimizer.attach_engine(eng)       # engine writes gradients straight into the optimiser's flat buffer
     out = eng.forward(x, training=True)
+    if y_ready is not None:
+        torch.cuda.current_stream().wait_event(y_ready)
     loss, dy = l1_loss(out, y, want_grad=True)
+    if after_loss is not None:
+        after_loss(loss, out)
     chunks = eng.backward_chunks() if (allreduce is not None and allreduce.world_size > 1) else None
     eng.backward(x, dy)
     flat_g = eng.flat_grads
