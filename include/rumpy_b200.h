@@ -145,7 +145,8 @@ int rumpy_net_trunk_mode(void* net);
  * applies to the calls made with that handle only (re-entrant; two handles with different options can run side by
  * side).  An option change takes effect with the next forward (the cached launch plan is rebuilt when it depends on
  * the option).  Names (value): "trunk" (1; 0 = one kernel per layer), "cluster" (1; 0 = dataflow kernel only),
- * "cluster_groups" (2 | 4 epilogue groups of the cluster kernel), "band" (0; 1 = role-swapped band kernel,
+ * "cluster_groups" (2 | 4 epilogue groups of the cluster kernel), "cluster_split" (1; 0 = one hand-over barrier per
+ * layer), "band" (0; 1 = role-swapped band kernel,
  * experiment), "trunk_bwd" (1; 0 = per-layer backward), "fused_ca" (0), "wgrad_chunks" (4; 1..8), "wgrad_tiles_per_split"
  * (64), "pdl" (1), "conv_2x" (0), "trunk_sync_mode" (8).  Unknown names return RUMPY_ERR_ARG / -1. */
 int rumpy_net_set_option(void* net, const char* name, long long value);

@@ -1133,6 +1133,7 @@ int rumpy_net_set_option(void* net, const char* name, long long value) {
   if (k == "trunk") o.use_trunk = v != 0;
   else if (k == "cluster") o.use_cluster = v != 0;
   else if (k == "cluster_groups") o.cluster_groups = v == 4 ? 4 : 2;
+  else if (k == "cluster_split") o.cluster_split = v != 0;
   else if (k == "band") o.use_band = v != 0;
   else if (k == "trunk_bwd") o.use_trunk_bwd = v != 0;
   else if (k == "fused_ca") o.use_fused_ca = v != 0;
@@ -1152,6 +1153,7 @@ long long rumpy_net_get_option(void* net, const char* name) {
   if (k == "trunk") return o.use_trunk;
   if (k == "cluster") return o.use_cluster;
   if (k == "cluster_groups") return o.cluster_groups;
+  if (k == "cluster_split") return o.cluster_split;
   if (k == "band") return o.use_band;
   if (k == "trunk_bwd") return o.use_trunk_bwd;
   if (k == "fused_ca") return o.use_fused_ca;

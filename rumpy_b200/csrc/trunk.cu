@@ -87,7 +87,10 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         if (C > 8) continue;
         const size_t smem = cluster_smem_bytes(th, tw, C);
         if (smem > size_t(kClusterMaxDyn)) continue;
-        const int perim = kClusterTileH * th + kClusterTileW * tw;
+        // vertical strips (one tile wide, the whole image height) allow the two-phase hand-over (trunk_cluster.cuh
+        // `split`): preferred among decompositions with the same tile count, then the smaller perimeter
+        const bool can_split = opt().cluster_split && tw == 1 && cy == 1 && th >= 3;
+        const int perim = kClusterTileH * th + kClusterTileW * tw - (can_split ? 1000 : 0);
         if (th * tw > best_tiles || (th * tw == best_tiles && perim >= best_perim)) continue;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(N * C); cfg.blockDim = dim3(cluster_threads(opt().cluster_groups)); cfg.dynamicSmemBytes = smem;
@@ -115,6 +118,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         c.out_bf16 = static_cast<__nv_bfloat16*>(plan->out_bufs.back());
         c.n_layers = a.n_layers; c.N = N; c.H = H; c.W = W; c.cx = cx; c.cy = cy; c.th = th; c.tw = tw; c.cr = Cr;
         c.inv_hw = a.inv_hw;
+        c.split = can_split ? th - 1 : 0;
         for (const TrunkLayer& l : plan->layers) c.n_ca += l.kind == kTrunkCA ? 1 : 0;
       }
   }

@@ -31,6 +31,12 @@ struct ClusterArgs {
   __nv_bfloat16* out_bf16;         // bf16 NHWC: output of the last layer
   long long* dbg;                  // optional timeline [grid][dbg_layers][16]
   int n_layers, n_ca, N, H, W, cx, cy, th, tw, cr, dbg_layers;   // n_ca = number of kTrunkCA layers
+  // Two-phase layer hand-over (vertical strips only: tw == 1, cy == 1, th >= 3): tiles [0, split) of a layer -- own
+  // pixels and the halo columns the neighbours owe for those rows -- complete barrier A, the remaining tiles barrier
+  // B.  Tile j of the next layer reads rows of tiles j-1 .. j+1 only, so its MMAs start after A when j + 1 < split:
+  // the last tile's epilogue (and, on channel-attention layers, its apply pass) runs underneath the next layer's
+  // first MMAs instead of in front of them.  split == 0: one barrier per layer (any rectangle).
+  int split;
   float inv_hw;
 };
 
@@ -57,9 +63,10 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
   __shared__ __align__(8) uint64_t w_full[3];
   __shared__ __align__(8) uint64_t w_empty[3];
   __shared__ __align__(8) uint64_t acc_full[kTrunkMaxK];
-  __shared__ __align__(8) uint64_t in_full[2];
+  __shared__ __align__(8) uint64_t in_full[2];     // barrier A (all of the layer when split == 0)
+  __shared__ __align__(8) uint64_t in_full_b[2];   // barrier B (tiles >= split)
   __shared__ __align__(8) uint64_t pool_full[2];
-  __shared__ uint32_t tmem_base_s, halo_bytes_s;
+  __shared__ uint32_t tmem_base_s, halo_bytes_s, halo_bytes_b_s;
   __shared__ __align__(16) float y_s[NG][64];
   __shared__ float bias_s[NG][KC], alpha_s[NG][KC], red_s[NG][4][64];
 
@@ -93,25 +100,29 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
     *reinterpret_cast<uint4*>(buf0 + i) = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     // halo pixels this CTA is owed per layer: the halo cells that lie inside the image (each has one owner)
-    int halo = 0;
+    int halo = 0, halo_b = 0;   // halo_b: owed by the neighbours' tiles >= split (rows of those tiles; cy == 1 there)
     for (int hy = 0; hy < PR; ++hy)
       for (int hx = 0; hx < PP; ++hx) {
         if (hy != 0 && hy != PR - 1 && hx != 0 && hx != PP - 1) continue;
         const int y = ry * RH + hy - 1, x = rx * RW + hx - 1;
-        halo += (y >= 0 && y < args.H && x >= 0 && x < args.W) ? 1 : 0;
+        if (!(y >= 0 && y < args.H && x >= 0 && x < args.W)) continue;
+        if (args.split > 0 && hy - 1 >= kClusterTileH * args.split) ++halo_b; else ++halo;
       }
     for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < kTrunkMaxK; ++i) mbar_init(&acc_full[i], 1);
     // in_full: one arrival per epilogue group + the arming arrival; the halo pixels complete transaction bytes.
     // Both parities are armed here for layers 0 / 1 (CA layers 0 / 1); later phases are re-armed by their consumer.
     halo_bytes_s = uint32_t(halo) * 128u;
+    halo_bytes_b_s = uint32_t(halo_b) * 128u;
     for (int i = 0; i < 2; ++i) {
       mbar_init(&in_full[i], NG + 1);
+      mbar_init(&in_full_b[i], NG + 1);
       mbar_init(&pool_full[i], 1);
     }
     fence_mbar_init();
     for (int i = 0; i < 2; ++i) {
       mbar_expect_tx(&in_full[i], uint32_t(halo) * 128u);
+      if (args.split > 0) mbar_expect_tx(&in_full_b[i], uint32_t(halo_b) * 128u);
       mbar_expect_tx(&pool_full[i], uint32_t(pool_slots) * 64u * 4u);
     }
   }
@@ -126,7 +137,8 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
   if (warp == kWarpMma) {
     // ===================================================================== MMA issuer
     constexpr uint32_t kIdesc = make_idesc_bf16(128, 64);
-    const uint32_t halo_bytes = halo_bytes_s;
+    const uint32_t halo_bytes = halo_bytes_s, halo_bytes_b = halo_bytes_b_s;
+    const int split = args.split;
     // descriptors: everything but the 14-bit start-address field (16-byte units) is constant for the whole kernel
     const uint64_t adesc0 = make_smem_desc(0, plane, uint32_t(PP) * 16, 0);
     const uint64_t bdesc0 = make_smem_desc(smem_u32(w_s), 16, 1024, kLayoutSw128);
@@ -140,6 +152,14 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
       if (lane == 0) CL_STAMP(L, 0);
       const uint32_t abuf16 = (smem_u32(buf0 + (L & 1) * buf_bytes) & 0x3FFFF) >> 4;
       for (int j = 0; j < n_tiles; ++j) {
+        if (split > 0 && j == split - 1) {
+          // tile j reads rows of tile j + 1 = the first tile behind barrier B (tiles before it needed A only)
+          mbar_wait_cluster(&in_full_b[L & 1], uint32_t(L >> 1) & 1u);
+          if (lane == 0 && L + 2 < n_layers) mbar_expect_tx(&in_full_b[L & 1], halo_bytes_b);
+          fence_proxy_async_smem();
+          tc_fence_after();
+          if (lane == 0) CL_STAMP(L, 5);
+        }
         const int ta = j / tw, tb = j - ta * tw;
         const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
         const uint32_t tile16 = abuf16 + uint32_t(kClusterTileH * ta * PP + kClusterTileW * tb);
@@ -193,6 +213,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
 
     // One pixel's KC bf16 channels (KCH chunks) -> this CTA's buffer, and (edge pixels) the neighbours' halo cells.
     // `par` selects the destination buffer AND the mbarrier whose transaction count the remote bytes complete.
+    const int split = args.split;
     auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[KCH]) {
       uint8_t* ob = buf0 + par * buf_bytes + plane0;
       const uint32_t cell = uint32_t((qy + 1) * PP + qx + 1) * 16;
@@ -211,16 +232,17 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         const uint32_t drank = uint32_t(nry * args.cx + nrx);
         const uint32_t rcell = uint32_t((qy + 1 - dy * RH) * PP + (qx + 1 - dx * RW)) * 16;
         const uint32_t raddr = mapa_u32(smem_u32(ob) + rcell, drank);
-        const uint32_t rbar = mapa_u32(smem_u32(&in_full[par]), drank);
+        const uint32_t rbar = mapa_u32(smem_u32(split > 0 && qy >= kClusterTileH * split ? &in_full_b[par] : &in_full[par]), drank);
 #pragma unroll
         for (int c = 0; c < KCH; ++c) st_async_v4(raddr + c * plane, ch[c], rbar);   // KCH x 16 B of this pixel
       }
     };
     // every thread of the group has written its half pixels of ALL tiles: one local arrival per group and layer
-    auto group_done = [&](int par) {
+    // (with a split: once after tile split - 1 on barrier A, once at the end of the layer on barrier B)
+    auto group_done = [&](int par, bool second = false) {
       fence_proxy_async_smem();
       named_bar_sync(bar_id, 128);
-      if (row == 0) mbar_arrive(&in_full[par]);
+      if (row == 0) mbar_arrive(second ? &in_full_b[par] : &in_full[par]);
     };
 
     // ---- residual stream (fp32 -> TMEM) and the layer-0 operand (bf16 -> buffer 0 + neighbours' halos)
@@ -244,8 +266,9 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
       for (int c = 0; c < KCH; ++c)
         ch[c] = valid ? __ldg(reinterpret_cast<const uint4*>(args.x_init + pix) + c) : make_uint4(0, 0, 0, 0);
       write_pixel(0, qy, qx, valid, ch);
+      if (split > 0 && j == split - 1) group_done(0);
     }
-    group_done(0);
+    group_done(0, split > 0);
     tmem_st_wait();
 
     int ca_seen = 0;
@@ -444,16 +467,18 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
       };
 
+      // hand-over of tiles [0, split): the next layer's first MMAs may start while the remaining tiles finish
+      auto early = [&](int j) { if (split > 0 && j == split - 1 && !last) group_done(par_out); };
       if (kind != kTrunkCA) {
-        for (int j = 0; j < n_tiles; ++j) plain(j);
+        for (int j = 0; j < n_tiles; ++j) { plain(j); early(j); }
       } else {
         for (int j = 0; j < n_tiles; ++j) ca_pool(j);
         ca_y();
-        for (int j = 0; j < n_tiles; ++j) ca_apply(j);
+        for (int j = 0; j < n_tiles; ++j) { ca_apply(j); early(j); }
         ++ca_seen;
       }
       tmem_st_wait();   // the residual-stream updates of this layer (one wait per layer, not per tile)
-      if (!last) group_done(par_out); else named_bar_sync(bar_id, 128);
+      if (!last) group_done(par_out, split > 0); else named_bar_sync(bar_id, 128);
     }
   }
 

@@ -79,3 +79,48 @@ def shard_round_robin(items, rank=None, world=None):
     if world is None:
         world = dist.get_world_size() if is_distributed() else 1
     return list(items)[rank::world]
+
+
+class FramesInFlight:
+    """Whole-frame inference with `depth` frames in flight on ONE GPU (the per-GPU half of image-sharded inference,
+    SURVEY 8e: ranks take frames round-robin, each rank runs its frames through this).
+
+    A large frame runs one kernel per layer: compute-bound convs alternate with the HBM-bound channel-attention pass
+    (`x + u*y`, 14 B per element), and within one frame the two cannot overlap -- the pass needs the global pool of the
+    conv before it.  Two independent frames can: each in-flight frame gets its own engine (own activation workspace;
+    parameters are shared, the packed bf16 weights are per engine) and its own CUDA stream, so one frame's memory-bound
+    kernels co-run with the other's tensor-core kernels.  Results are identical to running the frames one by one."""
+
+    def __init__(self, net, depth=2):
+        import torch
+        from . import engine as _engine
+        if depth < 1:
+            raise ValueError('depth >= 1')
+        arch, kw = net._engine_kwargs()
+        params = list(net.parameters())
+        self.net = net
+        self.engines = [net.native_engine()] + [_engine.TrunkEngine(arch, params, **kw) for _ in range(depth - 1)]
+        dev = params[0].device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+
+    def run(self, frames, consume=None):
+        """frames: iterable of N x C x H x W CUDA tensors.  Returns the outputs in order (or passes each to
+        `consume(index, out)` on the frame's stream and returns nothing, to keep memory flat)."""
+        import torch
+        main = torch.cuda.current_stream()
+        outs = []
+        with torch.no_grad():
+            for i, f in enumerate(frames):
+                k = i % len(self.engines)
+                st = self.streams[k]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    out = self.engines[k].forward(f)
+                    f.record_stream(st)
+                    if consume is not None:
+                        consume(i, out)
+                    else:
+                        outs.append(out)
+            for st in self.streams:
+                main.wait_stream(st)
+        return None if consume is not None else outs

@@ -141,3 +141,20 @@ def test_qmodel_checkpoint_is_written_without_metadata_keys(tmp_path):
     assert os.path.exists(path)
     state = torch.load(path, map_location='cpu', weights_only=False)
     assert state['model_name'] == 'qrcan' and 'metadata_keys_used_in_training' not in state
+
+
+def test_frames_in_flight_gives_the_sequential_results():
+    """parallel.FramesInFlight (two frames in flight on two streams / two engines sharing the parameters) must return
+    exactly what one-frame-at-a-time inference returns, in order."""
+    from rumpy_b200 import parallel
+    net, _ = _rcan(8, g=2, b=2)
+    frames = [_x((1, 3, 100, 200), seed=20 + s) for s in range(5)]
+    with torch.no_grad():
+        want = [net.native_engine().forward(f).clone() for f in frames]
+    got = parallel.FramesInFlight(net, depth=2).run(frames)
+    torch.cuda.synchronize()
+    assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(want, got))
+    seen = {}
+    parallel.FramesInFlight(net, depth=3).run(frames, consume=lambda i, out: seen.__setitem__(i, out.clone()))
+    torch.cuda.synchronize()
+    assert sorted(seen) == [0, 1, 2, 3, 4] and all(torch.equal(want[i], seen[i]) for i in range(5))

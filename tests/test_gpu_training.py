@@ -99,9 +99,11 @@ def test_backward_is_deterministic():
     assert torch.equal(flats[0], flats[1])
 
 
-def test_loss_curve_within_1pct_of_oracle_200_steps():
-    """Per-step L1 training loss vs the CPU oracle (Adam 1e-4) on the same batches: <= 1 % at every step.
-    (tools/loss_curve_1k.py runs the full 1 000 steps; 200 keeps the suite short.)"""
+def test_loss_curve_within_1pct_of_oracle_1000_steps():
+    """north_star: "per-step training loss within 1 % over 1k steps" -- L1 loss of every one of 1 000 Adam (1e-4) steps
+    against the CPU oracle on the same batches, at reduced depth (2 groups x 2 RCAB), where fp32 training is
+    well-conditioned.  (Full depth: tests/test_gpu_full_config.py, where the fp32 reference's own trajectory is chaotic
+    after ~100 steps and the assertion is shaped accordingly.)"""
     from rumpy_b200 import train_native
     from rumpy_b200.optim import FusedAdam
     arch, kw, sd, _, _ = recipe.case_tensors('rcan_small')
@@ -110,11 +112,14 @@ def test_loss_curve_within_1pct_of_oracle_200_steps():
     net = _build(arch, kw, sd)
     opt = FusedAdam(list(net.parameters()), lr=1e-4)
     tr = sr_torch_cpu.Trainer({k: torch.from_numpy(v) for k, v in sd.items()}, arch, lr=1e-4, **kw)
-    for step in range(200):
+    worst = 0.0
+    for step in range(1000):
         x, y = batches[step % len(batches)]
         l_gpu = train_native.train_step(net, opt, torch.from_numpy(x).to(DEV), torch.from_numpy(y).to(DEV))[0].item()
         l_cpu, _ = tr.step(torch.from_numpy(x), torch.from_numpy(y))
         assert abs(l_gpu - l_cpu) <= 0.01 * l_cpu, (step, l_gpu, l_cpu)
+        worst = max(worst, abs(l_gpu - l_cpu) / l_cpu)
+    print(f'worst per-step deviation over 1000 steps: {worst * 100:.3f} %')
 
 
 def test_fused_adam_and_grad_clip_match_torch():

@@ -130,12 +130,12 @@ if __name__ == '__main__':
         torch.cuda.synchronize()
         eng.set_timeline(None)
         t = buf.cpu().numpy().reshape(148, layers, 16)
-        names = ['in_full', 'mma_issued', 'last_acc', 'last_tile_done', 'pool_full']
+        names = ['in_full', 'mma_issued', 'last_acc', 'last_tile_done', 'pool_full', 'in_full_b']
         for cta in (0, 1, 5):
             base = t[cta, 0, 0]
             print(f'--- cluster CTA {cta}: cycles since layer-0 in_full')
             for L in range(layers):
-                print(f'  L{L:02d}: ' + ' '.join(f'{names[s]}={int(t[cta, L, s] - base) if t[cta, L, s] else -1:>7}' for s in range(5)))
+                print(f'  L{L:02d}: ' + ' '.join(f'{names[s]}={int(t[cta, L, s] - base) if t[cta, L, s] else -1:>7}' for s in range(6)))
     if 'timeline' in which:
         timeline(build('rcan'), (16, 3, 48, 48), layers=6)
     if 'timeline3' in which:
