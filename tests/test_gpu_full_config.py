@@ -51,13 +51,13 @@ def _kind(name):
 def _check_grads(named, grads, ref, tol=0.03, cos_min=0.999):
     """Every parameter's gradient against the oracle's.
 
-    Per tensor: max error <= `tol` of the tensor's own max magnitude, cosine >= `cos_min` -- for every tensor whose
-    reference gradient is within a decade of the largest one of its kind (conv weights / biases / channel-attention FC).
-    Tensors far below that scale exist only in the channel-attention FCs: a 4-unit hidden ReLU layer fed by 16 per-image
-    means, where a unit whose pre-activation sits at zero for some image makes d/dW DISCONTINUOUS (measured: the
-    reference gradient of such a tensor is 1e-7 against 1e-4 typical, and flips with a 1e-6 perturbation of the input);
-    they are held to `tol` of the KIND's scale instead, and each kind's concatenated gradient must agree in direction
-    (cosine >= 0.9999) and norm (1 %)."""
+    Conv weights and biases, every tensor: max error <= `tol` of the tensor's OWN max magnitude, cosine >= `cos_min`.
+    Channel-attention FC tensors: the same on their own scale (10 %, see below) when the reference gradient is within a
+    decade of the largest CA-FC gradient of the network; tensors far below that scale come from a 4-unit hidden ReLU
+    layer fed by 16 per-image means, where a unit whose pre-activation sits at zero for some image makes d/dW
+    DISCONTINUOUS (measured: the reference gradient of such a tensor is 1e-7 against 1e-4 typical and flips sign with
+    the bf16 noise of its input) -- those are held to the tolerance on the KIND's scale instead.  Each kind's
+    concatenated gradient must agree in direction (cosine >= 0.9999) and norm (1 %)."""
     named = [k for k, _ in named]
     got = {k: g.detach().cpu().numpy().astype(np.float64) for k, g in zip(named, grads)}
     want = {k: ref[k].numpy().astype(np.float64) for k in named}
@@ -75,7 +75,7 @@ def _check_grads(named, grads, ref, tol=0.03, cos_min=0.999):
         w_err, w_cos, n_floor = (0.0, None), (1.0, None), 0
         for k in keys:
             own = float(np.abs(want[k]).max())
-            well_scaled = own >= 0.1 * kind_scale
+            well_scaled = kind != 'ca_fc' or own >= 0.1 * kind_scale
             n_floor += not well_scaled
             err = float(np.abs(got[k] - want[k]).max()) / (own if well_scaled else kind_scale)
             if err > w_err[0]:
@@ -85,7 +85,7 @@ def _check_grads(named, grads, ref, tol=0.03, cos_min=0.999):
                 if cos < w_cos[0]:
                     w_cos = (cos, k)
         worst[kind] = (w_err, w_cos, n_floor, len(keys), cos_all)
-        print(f'{kind}: {len(keys)} tensors ({n_floor} below a tenth of the kind scale {kind_scale:.2e}), worst error '
+        print(f'{kind}: {len(keys)} tensors ({n_floor} judged on the kind scale {kind_scale:.2e}), worst error '
               f'{w_err[0]:.4f} ({w_err[1]}), worst cosine {w_cos[0]:.6f} ({w_cos[1]}), concatenated cosine {cos_all:.6f}, '
               f'norm ratio {norm_ratio:.4f}')
         # the channel-attention FC gradients come from s[n,c] = sum_hw g*u, a sum of signed products with heavy
@@ -93,7 +93,6 @@ def _check_grads(named, grads, ref, tol=0.03, cos_min=0.999):
         # largest tensor with cosine 0.9996, against 1.3 % for the worst conv weight) -> 10 % for that kind
         assert w_err[0] <= (0.10 if kind == 'ca_fc' else tol), (kind, w_err)
         assert w_cos[0] >= cos_min, (kind, w_cos)
-    assert worst['conv_weight'][2] == 0, 'every conv weight gradient must pass on its own scale'
     return worst
 
 
