@@ -445,6 +445,14 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
       };
 
       // ---------------------------------------------------------------- phase 2: x + u*y from the same accumulator
+      // The tensor-memory reads of a tile (accumulator + residual stream, 2 x KC columns) do not depend on y: tile 0's
+      // are issued BEFORE the wait for the pool exchange, tile j + 1's before tile j's results are written out, so the
+      // ~400-cycle TMEM round trip leaves the critical path pool -> y -> apply -> hand-over.
+      uint32_t av[KC], as[KC];
+      auto ca_prefetch = [&](int j) {
+        tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), av);
+        tmem_ld(lane_addr + uint32_t(j * 64), as);
+      };
       auto ca_apply = [&](int j) {
         const int ta = j / tw, tb = j - ta * tw;
         const int qy = kClusterTileH * ta + ly, qx = kClusterTileW * tb + lx;
@@ -452,16 +460,17 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         const bool valid = y < args.H && x < args.W;
         const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + KC * e;
         const float* yv = y_e + KC * e;
-        uint32_t v[KC], s[KC];
         float f[KC];
-        tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
-        tmem_ld(lane_addr + uint32_t(j * 64), s);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < KC; ++i) f[i] = fmaf(__uint_as_float(v[i]) + bias_e[i], yv[i], __uint_as_float(s[i]));
+        for (int i = 0; i < KC; ++i) f[i] = fmaf(__uint_as_float(av[i]) + bias_e[i], yv[i], __uint_as_float(as[i]));
+        {
+          uint32_t sv[KC];
 #pragma unroll
-        for (int i = 0; i < KC; ++i) s[i] = __float_as_uint(f[i]);
-        tmem_st(lane_addr + uint32_t(j * 64), s);
+          for (int i = 0; i < KC; ++i) sv[i] = __float_as_uint(f[i]);
+          tmem_st(lane_addr + uint32_t(j * 64), sv);
+        }
+        if (j + 1 < n_tiles) ca_prefetch(j + 1);
         tc_fence_before();
         emit(qy, qx, valid, pix, f);
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 3);
@@ -473,6 +482,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         for (int j = 0; j < n_tiles; ++j) { plain(j); early(j); }
       } else {
         for (int j = 0; j < n_tiles; ++j) ca_pool(j);
+        ca_prefetch(0);
         ca_y();
         for (int j = 0; j < n_tiles; ++j) { ca_apply(j); early(j); }
         ++ca_seen;

@@ -85,13 +85,14 @@ class FramesInFlight:
     """Whole-frame inference with `depth` frames in flight on ONE GPU (the per-GPU half of image-sharded inference,
     SURVEY 8e: ranks take frames round-robin, each rank runs its frames through this).
 
-    A large frame runs one kernel per layer: compute-bound convs alternate with the HBM-bound channel-attention pass
-    (`x + u*y`, 14 B per element), and within one frame the two cannot overlap -- the pass needs the global pool of the
-    conv before it.  Two independent frames can: each in-flight frame gets its own engine (own activation workspace;
-    parameters are shared, the packed bf16 weights are per engine) and its own CUDA stream, so one frame's memory-bound
-    kernels co-run with the other's tensor-core kernels.  Results are identical to running the frames one by one."""
+    Each in-flight frame gets its own engine (own activation workspace; parameters are shared, the packed bf16
+    weights are per engine) and its own CUDA stream; results are identical to running the frames one by one.
+    depth = 1 is the default and the fastest on a B200 for 1080p RCAN frames (bench.py `frame_1080p`: two frames in
+    flight measured 174.8 ms per frame against 168.7 ms one at a time -- the persistent conv kernels fill every SM,
+    so the other frame's HBM-bound channel-attention pass cannot co-run); larger depths serve callers whose frames
+    are small enough to leave SMs idle, or whose output consumer (`consume`) is slow."""
 
-    def __init__(self, net, depth=2):
+    def __init__(self, net, depth=1):
         import torch
         from . import engine as _engine
         if depth < 1:
