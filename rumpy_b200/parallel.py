@@ -87,10 +87,12 @@ class FramesInFlight:
 
     Each in-flight frame gets its own engine (own activation workspace; parameters are shared, the packed bf16
     weights are per engine) and its own CUDA stream; results are identical to running the frames one by one.
-    depth = 1 is the default and the fastest on a B200 for 1080p RCAN frames (bench.py `frame_1080p`: two frames in
-    flight measured 174.8 ms per frame against 168.7 ms one at a time -- the persistent conv kernels fill every SM,
-    so the other frame's HBM-bound channel-attention pass cannot co-run); larger depths serve callers whose frames
-    are small enough to leave SMs idle, or whose output consumer (`consume`) is slow."""
+    Why more than one: a large frame runs one kernel per layer, compute-bound convs alternating with the HBM-bound
+    channel-attention pass, and within one frame the two cannot overlap (the pass needs the global pool of the conv
+    before it); a second frame on another stream can fill the gaps.  Measured on 1080p RCAN frames (bench.py
+    `frame_1080p`, which times both): two in flight 147.6 ms per frame against 159.0 one at a time with the bf16
+    pre-attention activation of the inference plans; with the fp32 one (round 1's plan) it was the other way round,
+    174.8 against 168.7."""
 
     def __init__(self, net, depth=1):
         import torch
