@@ -24,6 +24,7 @@ struct Options {
   int use_trunk = 1;          // whole 64-channel body in ONE kernel when the shape fits (0: one kernel per layer)
   int use_cluster = 1;        // prefer the one-cluster-per-image kernel (trunk_cluster.cuh) when it fits
   int cluster_groups = 2;     // epilogue groups of the cluster kernel (2 or 4)
+  int cluster_dbg = 0;        // cluster kernel timing experiments (garbage results): see ClusterArgs::dbg_flags
   int cluster_split = 1;      // cluster kernel: two-phase layer hand-over on vertical strips (trunk_cluster.cuh)
   int use_band = 0;           // role-swapped band kernel (trunk_band.cuh): experiment, slower than the cluster kernel
   int use_trunk_bwd = 1;      // backward of the RCAN body in the persistent dataflow kernel (trunk_bwd.cuh)
@@ -42,7 +43,7 @@ struct Options {
     return unsigned(use_trunk) | unsigned(use_cluster) << 1 | unsigned(use_trunk_bwd) << 2 | unsigned(use_band) << 3 |
            unsigned(use_fused_ca) << 4 | unsigned(cluster_groups == 4) << 5 | unsigned(use_pdl) << 6 |
            unsigned(conv_2x) << 7 | unsigned(wgrad_chunks) << 8 | unsigned(wgrad_tiles_per_split) << 12 |
-           unsigned(timeline != nullptr) << 28 | unsigned(cluster_split) << 29 | unsigned(infer_u_bf16) << 30;
+           unsigned(timeline != nullptr) << 28 | unsigned(cluster_split) << 29 | unsigned(infer_u_bf16) << 30 | unsigned(cluster_dbg != 0) << 31;
   }
 };
 const Options& opt();

@@ -1140,6 +1140,7 @@ int rumpy_net_set_option(void* net, const char* name, long long value) {
   else if (k == "cluster") o.use_cluster = v != 0;
   else if (k == "cluster_groups") o.cluster_groups = v == 4 ? 4 : 2;
   else if (k == "cluster_split") o.cluster_split = v != 0;
+  else if (k == "cluster_dbg") o.cluster_dbg = v;
   else if (k == "infer_u_bf16") o.infer_u_bf16 = v != 0;
   else if (k == "band") o.use_band = v != 0;
   else if (k == "trunk_bwd") o.use_trunk_bwd = v != 0;

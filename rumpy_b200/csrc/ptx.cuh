@@ -296,6 +296,25 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     if ((++spins & 1023u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) mbar_watchdog_fail(bar, parity);
   }
 }
+// mbarrier waits whose watchdog traps INLINE.  mbar_wait / mbar_wait_cluster above report through a __noinline__
+// printf helper; a call site inside a hot loop makes ptxas keep every live value in callee-saved registers (or spill
+// it) and give up uniform registers across it.  Use these in the MMA-issuing warp and in register-heavy epilogues.
+__device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) asm volatile("trap;");
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster_trap(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) asm volatile("trap;");
+  }
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

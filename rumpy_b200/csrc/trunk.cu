@@ -119,6 +119,7 @@ int trunk_plan_finish(TrunkPlan* plan, int N, int H, int W, int Cr, const void* 
         c.n_layers = a.n_layers; c.N = N; c.H = H; c.W = W; c.cx = cx; c.cy = cy; c.th = th; c.tw = tw; c.cr = Cr;
         c.inv_hw = a.inv_hw;
         c.split = can_split ? th - 1 : 0;
+        c.dbg_flags = opt().cluster_dbg;
         for (const TrunkLayer& l : plan->layers) c.n_ca += l.kind == kTrunkCA ? 1 : 0;
       }
   }

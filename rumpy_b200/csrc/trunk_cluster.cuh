@@ -17,8 +17,12 @@
 //   * fp32 residual stream + accumulators live in TMEM, weights stream through one 72 KB buffer in kx thirds (as
 //     in trunk_pipe.cuh).
 // Warp roles, NG epilogue groups (template parameter, 2 or 4): warps 0 .. 4*NG-1 epilogue (group e = warp / 4 owns
-// channels [64/NG * e, 64/NG * (e+1)) of every tile) | 4*NG MMA issuer | 4*NG+1 weight producer.  NG = 4 (576 threads,
-// <= 112 registers) halves the exposed epilogue / channel-attention tails that NG = 2 (320 threads) leaves.
+// channels [64/NG * e, 64/NG * (e+1)) of every tile) | 4*NG MMA issuer 0 | 4*NG+1 weight producer | 4*NG+2 MMA issuer 1.
+// TWO MMA-ISSUING WARPS: a 128x64x16 MMA keeps the tensor pipe busy for only 48 cycles (operand reads), the pipe
+// accepts hardly more than one MMA ahead, and one warp needs 55-70 cycles per MMA for the descriptor arithmetic
+// (vector registers -> R2UR -> UTCHMMA; tools/experiments/umma_env_test.cu: 58-63 cycles per MMA with one issuer,
+// 48.2-49.5 with two).  Consecutive tiles (different accumulators, so no ordering between them) alternate between the
+// two warps; each one follows the hand-over barriers of the layers its tiles belong to.
 #pragma once
 #include "trunk_pipe.cuh"
 
@@ -37,11 +41,12 @@ struct ClusterArgs {
   // the last tile's epilogue (and, on channel-attention layers, its apply pass) runs underneath the next layer's
   // first MMAs instead of in front of them.  split == 0: one barrier per layer (any rectangle).
   int split;
+  int dbg_flags;   // timing experiments only (results are garbage): 1 skip the epilogue's TMEM reads, 2 skip its local stores
   float inv_hw;
 };
 
-constexpr int kClusterThreads = 320;   // NG = 2
-__host__ __device__ constexpr int cluster_threads(int ng) { return (4 * ng + 2) * 32; }
+constexpr int kClusterThreads = 352;   // NG = 2
+__host__ __device__ constexpr int cluster_threads(int ng) { return (4 * ng + 3) * 32; }
 constexpr int kClusterTileH = 16, kClusterTileW = 8;
 
 __host__ __device__ inline size_t cluster_buf_bytes(int th, int tw) {
@@ -71,7 +76,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
   __shared__ float bias_s[NG][KC], alpha_s[NG][KC], red_s[NG][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarpMma = 4 * NG, kWarpW = 4 * NG + 1;
+  constexpr int kWarpMma = 4 * NG, kWarpW = 4 * NG + 1, kWarpMma2 = 4 * NG + 2;
   const int n_layers = args.n_layers;
   const int th = args.th, tw = args.tw, n_tiles = th * tw;
   const int C = args.cx * args.cy;
@@ -108,7 +113,8 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         if (!(y >= 0 && y < args.H && x >= 0 && x < args.W)) continue;
         if (args.split > 0 && hy - 1 >= kClusterTileH * args.split) ++halo_b; else ++halo;
       }
-    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    // w_empty: one tcgen05.commit per issuing warp (after its last MMAs of the layer that read the third)
+    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], n_tiles >= 2 ? 2 : 1); }
     for (int i = 0; i < kTrunkMaxK; ++i) mbar_init(&acc_full[i], 1);
     // in_full: one arrival per epilogue group + the arming arrival; the halo pixels complete transaction bytes.
     // Both parities are armed here for layers 0 / 1 (CA layers 0 / 1); later phases are re-armed by their consumer.
@@ -134,8 +140,10 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
   cluster_sync_all();   // every CTA's buffers are zeroed and its barriers initialised before any remote access
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp == kWarpMma) {
-    // ===================================================================== MMA issuer
+  if (warp == kWarpMma || warp == kWarpMma2) {
+    // ===================================================================== MMA issuers
+    const int me = warp == kWarpMma ? 0 : 1;
+    const bool two = n_tiles >= 2;                 // one tile per CTA: issuer 0 alone
     constexpr uint32_t kIdesc = make_idesc_bf16(128, 64);
     const uint32_t halo_bytes = halo_bytes_s, halo_bytes_b = halo_bytes_b_s;
     const int split = args.split;
@@ -143,46 +151,70 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
     const uint64_t adesc0 = make_smem_desc(0, plane, uint32_t(PP) * 16, 0);
     const uint64_t bdesc0 = make_smem_desc(smem_u32(w_s), 16, 1024, kLayoutSw128);
     const uint32_t kstep = (2 * plane) >> 4;   // K = 16 channels = two planes
-    for (int L = 0; L < n_layers; ++L) {
-      // own tiles of layer L-1 and every halo pixel owed by the neighbours have landed in buffer L&1
-      mbar_wait_cluster(&in_full[L & 1], uint32_t(L >> 1) & 1u);
-      if (lane == 0 && L + 2 < n_layers) mbar_expect_tx(&in_full[L & 1], halo_bytes);   // arm layer L+2's phase
-      fence_proxy_async_smem();   // generic-proxy writes of the epilogue threads -> async-proxy (tensor core) reads
-      tc_fence_after();
-      if (lane == 0) CL_STAMP(L, 0);
-      const uint32_t abuf16 = (smem_u32(buf0 + (L & 1) * buf_bytes) & 0x3FFFF) >> 4;
-      for (int j = 0; j < n_tiles; ++j) {
-        if (split > 0 && j == split - 1) {
-          // tile j reads rows of tile j + 1 = the first tile behind barrier B (tiles before it needed A only)
-          mbar_wait_cluster(&in_full_b[L & 1], uint32_t(L >> 1) & 1u);
-          if (lane == 0 && L + 2 < n_layers) mbar_expect_tx(&in_full_b[L & 1], halo_bytes_b);
-          fence_proxy_async_smem();
-          tc_fence_after();
-          if (lane == 0) CL_STAMP(L, 5);
-        }
-        const int ta = j / tw, tb = j - ta * tw;
-        const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
-        const uint32_t tile16 = abuf16 + uint32_t(kClusterTileH * ta * PP + kClusterTileW * tb);
-        for (int kx = 0; kx < 3; ++kx) {
-          if (j == 0) { mbar_wait(&w_full[kx], uint32_t(L & 1)); tc_fence_after(); }
-          if (elect_one()) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              // tap (ky,kx) of tile (ta,tb): the resident plane, start moved by whole pixels
-              const uint64_t adesc = adesc0 + uint64_t(tile16 + uint32_t(ky * PP + kx));
-              const uint64_t bdesc = bdesc0 + uint64_t(((kx * 3 + ky) * 8192) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)   // K = 16 channels = planes 2k, 2k+1 (LBO = plane stride)
-                umma_bf16(d_tmem, adesc + uint64_t(k * kstep), bdesc + uint64_t(2 * k), kIdesc, (kx | ky | k) != 0);
+    if (two || me == 0) {
+      int g = 0;                                   // running tile counter: tile g belongs to issuer g & 1
+      for (int L = 0; L < n_layers; ++L) {
+        const uint32_t abuf16 = (smem_u32(buf0 + (L & 1) * buf_bytes) & 0x3FFFF) >> 4;
+        bool have_a = false, have_b = split == 0, have_w = false;
+        int my_last = -1;
+        for (int j = 0; j < n_tiles; ++j)
+          if (!two || ((g + j) & 1) == me) my_last = j;
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          if (two && (g & 1) != me) continue;
+          if (!have_a) {
+            // own tiles [0, split) of layer L-1 and the halo pixels owed for them have landed in buffer L & 1
+            mbar_wait_cluster_trap(&in_full[L & 1], uint32_t(L >> 1) & 1u);
+            // the issuer of tile 0 arms layer L+2's phase (it is the only one sure to pass here before anything of
+            // layer L+1 is produced)
+            if (j == 0 && lane == 0 && L + 2 < n_layers) mbar_expect_tx(&in_full[L & 1], halo_bytes);
+            have_a = true;
+            if (j >= split - 1) {   // (also split == 0: have_b is set and the single barrier is this one)
+              if (!have_b) {
+                mbar_wait_cluster_trap(&in_full_b[L & 1], uint32_t(L >> 1) & 1u);
+                have_b = true;
+              }
             }
-            if (j == n_tiles - 1) umma_commit(&w_empty[kx]);
+            fence_proxy_async_smem();   // generic-proxy writes of the epilogue threads -> async-proxy (tensor core) reads
+            tc_fence_after();
+            if (j == 0 && lane == 0) CL_STAMP(L, 0);
           }
+          if (!have_b && j >= split - 1) {
+            // tile j reads rows of tile j + 1 >= split: those complete barrier B
+            mbar_wait_cluster_trap(&in_full_b[L & 1], uint32_t(L >> 1) & 1u);
+            have_b = true;
+            fence_proxy_async_smem();
+            tc_fence_after();
+          }
+          if (split > 0 && j == n_tiles - 1 && lane == 0) {
+            // the issuer of the last tile has passed barrier B of this layer: it arms layer L+2's phase
+            if (L + 2 < n_layers) mbar_expect_tx(&in_full_b[L & 1], halo_bytes_b);
+            CL_STAMP(L, 5);
+          }
+          const int ta = j / tw, tb = j - ta * tw;
+          const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
+          const uint32_t tile16 = abuf16 + uint32_t(kClusterTileH * ta * PP + kClusterTileW * tb);
+          for (int kx = 0; kx < 3; ++kx) {
+            if (!have_w) { mbar_wait_trap(&w_full[kx], uint32_t(L & 1)); tc_fence_after(); }
+            if (elect_one()) {
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                // tap (ky,kx) of tile (ta,tb): the resident plane, start moved by whole pixels
+                const uint64_t adesc = adesc0 + uint64_t(tile16 + uint32_t(ky * PP + kx));
+                const uint64_t bdesc = bdesc0 + uint64_t(((kx * 3 + ky) * 8192) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)   // K = 16 channels = planes 2k, 2k+1 (LBO = plane stride)
+                  umma_bf16(d_tmem, adesc + uint64_t(k * kstep), bdesc + uint64_t(2 * k), kIdesc, (kx | ky | k) != 0);
+              }
+              if (j == my_last) umma_commit(&w_empty[kx]);   // this issuer's last read of the third in this layer
+            }
+            __syncwarp();
+          }
+          have_w = true;
+          if (elect_one()) umma_commit(&acc_full[j]);
           __syncwarp();
+          if (j == n_tiles - 1 && lane == 0) CL_STAMP(L, 1);
         }
-        if (elect_one()) umma_commit(&acc_full[j]);
-        __syncwarp();
       }
-      if (lane == 0) CL_STAMP(L, 1);
     }
   } else if (warp == kWarpW) {
     // ===================================================================== weight producer (three kx thirds)
@@ -217,8 +249,10 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
     auto write_pixel = [&](int par, int qy, int qx, bool valid, const uint4 (&ch)[KCH]) {
       uint8_t* ob = buf0 + par * buf_bytes + plane0;
       const uint32_t cell = uint32_t((qy + 1) * PP + qx + 1) * 16;
+      if (!(args.dbg_flags & 2)) {
 #pragma unroll
-      for (int c = 0; c < KCH; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
+        for (int c = 0; c < KCH; ++c) *reinterpret_cast<uint4*>(ob + c * plane + cell) = ch[c];
+      }
       if (!valid) return;
       const int dyv = qy == 0 ? -1 : (qy == RH - 1 ? 1 : 0);
       const int dxv = qx == 0 ? -1 : (qx == RW - 1 ? 1 : 0);
@@ -318,7 +352,12 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
         uint32_t v[KC];
         float f[KC];
-        tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+        if (args.dbg_flags & 1) {
+#pragma unroll
+          for (int i = 0; i < KC; ++i) v[i] = 0;
+        } else {
+          tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
+        }
         if (kind == kTrunkRelu) {
           tmem_ld_wait();
 #pragma unroll

@@ -15,6 +15,7 @@ LAYERS = G * (2 * B + 1) + 1
 dbg = torch.zeros((96, LAYERS, 16), dtype=torch.int64, device=dev)
 eng = net.native_engine()
 eng.set_option('cluster_split', int(os.environ.get('SPLIT', 1)))
+eng.set_option('cluster_dbg', int(os.environ.get('DBG', 0)))
 with torch.no_grad():
     eng.forward(x)
     eng.set_timeline(dbg, LAYERS)
@@ -22,7 +23,7 @@ with torch.no_grad():
 torch.cuda.synchronize()
 print('mode', lib.rumpy_net_trunk_mode(eng.handle), 'split', eng.get_option('cluster_split'))
 d = dbg.cpu()
-for cta in (48, 50, 53):
+for cta in (48,):
     t0 = d[cta, 0, 0].item()
     print(f'--- CTA {cta}')
     prev = t0
