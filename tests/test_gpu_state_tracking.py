@@ -143,12 +143,17 @@ def test_qmodel_checkpoint_is_written_without_metadata_keys(tmp_path):
     assert state['model_name'] == 'qrcan' and 'metadata_keys_used_in_training' not in state
 
 
-def test_frames_in_flight_gives_the_sequential_results():
-    """parallel.FramesInFlight (two frames in flight on two streams / two engines sharing the parameters) must return
-    exactly what one-frame-at-a-time inference returns, in order."""
+@pytest.mark.parametrize('shape,mode', [((1, 3, 100, 200), 1), ((2, 3, 48, 48), 2), ((1, 3, 300, 520), 0)])
+def test_frames_in_flight_gives_the_sequential_results(shape, mode):
+    """parallel.FramesInFlight (two / three frames in flight on as many streams and engines sharing the parameters) must
+    return exactly what one-frame-at-a-time inference returns, in order -- for every trunk path (dataflow kernel,
+    cluster kernel, one kernel per layer): the kernels of different frames run concurrently on one GPU."""
     from rumpy_b200 import parallel
     net, _ = _rcan(8, g=2, b=2)
-    frames = [_x((1, 3, 100, 200), seed=20 + s) for s in range(5)]
+    frames = [_x(shape, seed=20 + s) for s in range(5)]
+    with torch.no_grad():
+        net.native_engine().forward(frames[0])
+    assert net.native_engine().lib.rumpy_net_trunk_mode(net.native_engine().handle) == mode
     with torch.no_grad():
         want = [net.native_engine().forward(f).clone() for f in frames]
     got = parallel.FramesInFlight(net, depth=2).run(frames)
