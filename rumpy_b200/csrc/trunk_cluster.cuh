@@ -73,7 +73,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
   __shared__ __align__(8) uint64_t pool_full[2];
   __shared__ uint32_t tmem_base_s, halo_bytes_s, halo_bytes_b_s;
   __shared__ __align__(16) float y_s[NG][64];
-  __shared__ float bias_s[NG][KC], alpha_s[NG][KC], red_s[NG][4][64];
+  __shared__ __align__(16) float bias_s[NG][KC], alpha_s[NG][KC], red_s[NG][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpMma = 4 * NG, kWarpW = 4 * NG + 1, kWarpMma2 = 4 * NG + 2;
@@ -415,8 +415,16 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
           float f[KC];
           tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
           tmem_ld_wait();
+          // (bias read with unconditional 16-byte loads: under the `valid` select the compiler emitted 32 predicated
+          // scalar LDS -- 363 shared-memory wavefronts per layer next to the tensor core's operand reads)
+          float b[KC];
 #pragma unroll
-          for (int i = 0; i < KC; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[i] : 0.f;
+          for (int i4 = 0; i4 < KC / 4; ++i4) {
+            const float4 t = reinterpret_cast<const float4*>(bias_e)[i4];
+            b[4 * i4] = t.x; b[4 * i4 + 1] = t.y; b[4 * i4 + 2] = t.z; b[4 * i4 + 3] = t.w;
+          }
+#pragma unroll
+          for (int i = 0; i < KC; ++i) f[i] = valid ? __uint_as_float(v[i]) + b[i] : 0.f;
           if constexpr (KC == 32) {
             red_s[e][q][lane] = lane_transpose_sum32(f, lane);
           } else {
