@@ -239,8 +239,12 @@ int rumpy_adam_step(float* p, const float* g, float* m, float* v, long long n, f
  *   (u8 / 255).  lr_nchw: device fp32 [N][C][H][W] in [0,1] (values outside are clamped; the reference's `.byte()` is
  *   undefined there); out_nchw: device fp32 [N][C][H*scale][W*scale]; workspace: rumpy_bicubic_workspace(H, W, scale)
  *   bytes, 16-byte aligned (tap tables: one entry per output column and per group of four output rows, written by
- *   the call itself); scale 2..8, N*C <= 65535; bit-exact with Pillow.  'lanczos' (standard_eval.py:252-253) is not
- *   provided. */
+ *   the call itself); scale 2..8, N*C <= 65535; bit-exact with Pillow.
+ * rumpy_lanczos_upsample: the same baseline with Pillow's Lanczos-3 filter (`--lanczos_upsample`,
+ *   standard_eval.py:252-253: `Image.resize(..., LANCZOS)`); same arguments and layout, workspace
+ *   rumpy_lanczos_workspace(H, W, scale) bytes.  The tap tables are evaluated on the HOST by the call (Pillow uses libm's
+ *   sin in double precision; the device's is not correctly rounded) and uploaded on the caller's stream; bit-exact
+ *   with Pillow. */
 long long rumpy_psnr_y_workspace(int N);
 int rumpy_psnr_y(const float* sr, const float* hr, float* psnr, void* workspace, int N, int H, int W, float max_value,
                  void* stream);
@@ -248,6 +252,9 @@ int rumpy_quantize_u8(const float* src_nchw, unsigned char* dst_nhwc, int N, int
 int rumpy_patch_batch(const unsigned char* const* lr_imgs, const unsigned char* const* hr_imgs, const int* geom,
                       float* lr_out, float* hr_out, int N, int crop, int scale, void* stream);
 long long rumpy_bicubic_workspace(int H, int W, int scale);
+long long rumpy_lanczos_workspace(int H, int W, int scale);
+int rumpy_lanczos_upsample(const float* lr_nchw, float* out_nchw, void* workspace, int N, int C, int H, int W, int scale,
+                           void* stream);
 int rumpy_bicubic_upsample(const float* lr_nchw, float* out_nchw, void* workspace, int N, int C, int H, int W, int scale,
                            void* stream);
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     'rumpy_patch_batch': [_vp, _vp, _vp, _fp, _fp, _i, _i, _i, _vp],
     'rumpy_bicubic_workspace': [_i, _i, _i],
     'rumpy_bicubic_upsample': [_fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
+    'rumpy_lanczos_workspace': [_i, _i, _i],
+    'rumpy_lanczos_upsample': [_fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     'rumpy_net_backward_chunks': [_vp, _vp, _i],
     'rumpy_net_set_backward_events': [_vp, _vp, _i],
     'rumpy_net_destroy': [_vp],
@@ -62,7 +64,7 @@ SIGNATURES = {
 }
 
 _LONGLONG = {'rumpy_net_packed_bytes', 'rumpy_net_workspace_bytes', 'rumpy_conv3x3_wgrad_workspace',
-             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace', 'rumpy_bicubic_workspace', 'rumpy_net_get_option'}
+             'rumpy_l1_workspace_floats', 'rumpy_psnr_y_workspace', 'rumpy_bicubic_workspace', 'rumpy_lanczos_workspace', 'rumpy_net_get_option'}
 
 _lib = None
 

@@ -15,7 +15,9 @@
 // from the element count; reductions run in a fixed order (deterministic).
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
+#include <vector>
 
 #include "../../include/rumpy_b200.h"
 #include "host_util.cuh"
@@ -352,6 +354,83 @@ __global__ void __launch_bounds__(256, 6) bicubic_up_kernel(const float* __restr
   }
 }
 
+
+// ---- Lanczos baseline (standard_eval.py:252-253: `--lanczos_upsample`, Image.resize(..., LANCZOS)) ------------------
+// Same two-pass 8-bit resampler as the bicubic baseline with Pillow's Lanczos-3 filter (support 3: up to seven taps per
+// output index).  The tap tables come from the host (libm sin, see rumpy_lanczos_upsample); the kernel is a plain
+// tiled FIR: one CTA = one 16 x 64 output tile of one plane, its LR footprint quantised like to_pil_image in shared
+// memory, horizontal pass into a uint8 intermediate (Pillow's intermediate image is uint8), vertical pass, v / 255.
+// An evaluation-time baseline, launched once per image: correctness against Pillow is the bar, not the roofline.
+constexpr int kLanTaps = 7;
+struct __align__(16) LanTap {
+  int k[kLanTaps];
+  int lo;
+  int n, pad0, pad1, pad2;
+};
+
+// Resample.c precompute_coeffs + normalize_coeffs_8bpc, Lanczos-3, upscaling (filterscale = 1); host, libm
+inline LanTap lanczos_coeffs(int xx, int in_size, int out_size) {
+  auto sinc = [](double v) { if (v == 0.0) return 1.0; v = v * M_PI; return sin(v) / v; };
+  auto filt = [&](double v) { return (-3.0 <= v && v < 3.0) ? sinc(v) * sinc(v / 3) : 0.0; };
+  const double scale = double(in_size) / double(out_size);
+  const double center = (double(xx) + 0.5) * scale;
+  int lo = int(center - 3.0 + 0.5), hi = int(center + 3.0 + 0.5);
+  lo = lo < 0 ? 0 : lo;
+  hi = hi > in_size ? in_size : hi;
+  LanTap e{};
+  e.lo = lo;
+  e.n = hi - lo;
+  double w[kLanTaps], ww = 0.0;
+  for (int x = 0; x < e.n; ++x) { w[x] = filt(double(x + lo) - center + 0.5); ww += w[x]; }
+  for (int x = 0; x < e.n; ++x) {
+    const double v = ww != 0.0 ? w[x] / ww : w[x];
+    e.k[x] = int(v < 0.0 ? -0.5 + v * double(1 << kBicPrec) : 0.5 + v * double(1 << kBicPrec));
+  }
+  return e;
+}
+
+constexpr int kLanTH = 16, kLanTW = 64;
+constexpr int kLanRows = kLanTH / 2 + kLanTaps + 1, kLanCols = kLanTW / 2 + kLanTaps + 1;   // footprint for scale >= 2
+
+// grid (ceil(OW / 64), ceil(OH / 16), N * C), block 256
+__global__ void __launch_bounds__(256) lanczos_up_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         const LanTap* __restrict__ taps, int H, int W, int scale) {
+  __shared__ LanTap s_cx[kLanTW], s_cy[kLanTH];
+  __shared__ uint8_t s_lr[kLanRows][kLanCols + 3];
+  __shared__ uint8_t s_tmp[kLanRows][kLanTW];
+  const int OH = H * scale, OW = W * scale;
+  const int ox0 = blockIdx.x * kLanTW, oy0 = blockIdx.y * kLanTH;
+  const int tw = min(kLanTW, OW - ox0), th = min(kLanTH, OH - oy0);
+  const int tid = threadIdx.x;
+  if (tid < tw) s_cx[tid] = taps[ox0 + tid];
+  else if (tid >= kLanTW && tid - kLanTW < th) s_cy[tid - kLanTW] = taps[OW + oy0 + tid - kLanTW];
+  __syncthreads();
+  const int x_lo = s_cx[0].lo, cols = s_cx[tw - 1].lo + s_cx[tw - 1].n - x_lo;
+  const int y_lo = s_cy[0].lo, rows = s_cy[th - 1].lo + s_cy[th - 1].n - y_lo;
+  const float* sp = src + size_t(blockIdx.z) * H * W + size_t(y_lo) * W + x_lo;
+  for (int i = tid; i < rows * cols; i += 256) {
+    const int r = i / cols, c = i - r * cols;
+    s_lr[r][c] = uint8_t(quant1(sp[r * W + c]));                  // to_pil_image: pic.mul(255).byte()
+  }
+  __syncthreads();
+  for (int i = tid; i < rows * tw; i += 256) {                    // horizontal pass -> uint8 intermediate
+    const int r = i / tw, x = i - r * tw;
+    const LanTap& e = s_cx[x];
+    int acc = 1 << (kBicPrec - 1);
+    for (int t = 0; t < e.n; ++t) acc += int(s_lr[r][e.lo - x_lo + t]) * e.k[t];
+    s_tmp[r][x] = uint8_t(bic_clip8(acc));
+  }
+  __syncthreads();
+  float* dp = dst + size_t(blockIdx.z) * OH * OW;
+  for (int i = tid; i < th * tw; i += 256) {                      // vertical pass, ToTensor's v / 255
+    const int y = i / tw, x = i - y * tw;
+    const LanTap& e = s_cy[y];
+    int acc = 1 << (kBicPrec - 1);
+    for (int t = 0; t < e.n; ++t) acc += int(s_tmp[e.lo - y_lo + t][x]) * e.k[t];
+    dp[size_t(oy0 + y) * OW + ox0 + x] = bic_div255(bic_clip8(acc));
+  }
+}
+
 }  // namespace rb
 
 using namespace rb;
@@ -411,6 +490,34 @@ int rumpy_patch_batch(const unsigned char* const* lr_imgs, const unsigned char* 
   patch_batch_kernel<<<dim3((side * side + 255) / 256, N, 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lr_imgs, hr_imgs, geom, lr_out, hr_out, crop, scale);
   return check_launch("patch_batch");
+}
+
+long long rumpy_lanczos_workspace(int H, int W, int scale) {
+  if (H < 1 || W < 1 || scale < 2 || scale > 8) return -1LL;
+  // column taps + row taps (LanTap each) + the horizontally resampled uint8 intermediate of ONE plane batch
+  return (long long)(W * scale + H * scale) * (long long)sizeof(LanTap);
+}
+
+int rumpy_lanczos_upsample(const float* lr_nchw, float* out_nchw, void* workspace, int N, int C, int H, int W, int scale,
+                           void* stream) {
+  if (!lr_nchw || !out_nchw || !workspace) return set_error(RUMPY_ERR_ARG, "lanczos_upsample: null pointer");
+  if (N < 1 || C < 1 || H < 1 || W < 1 || scale < 2 || scale > 8 || (long long)N * C > 65535)
+    return set_error(RUMPY_ERR_ARG, "lanczos_upsample: N=%d C=%d H=%d W=%d scale=%d", N, C, H, W, scale);
+  if (int e = device_info(nullptr)) return e;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int OW = W * scale, OH = H * scale;
+  // tap tables on the host: Pillow evaluates sin() of libm in double; the same libm here gives the same bits
+  // (CUDA's double sin is 2-ulp accurate, not correctly rounded).  The vector lives until the copy has been staged:
+  // cudaMemcpyAsync from pageable memory returns after the driver has copied the source.
+  static thread_local std::vector<LanTap> taps;
+  taps.resize(size_t(OW) + OH);
+  for (int x = 0; x < OW; ++x) taps[x] = lanczos_coeffs(x, W, OW);
+  for (int y = 0; y < OH; ++y) taps[size_t(OW) + y] = lanczos_coeffs(y, H, OH);
+  if (cudaMemcpyAsync(workspace, taps.data(), taps.size() * sizeof(LanTap), cudaMemcpyHostToDevice, s) != cudaSuccess)
+    return set_error(RUMPY_ERR_CUDA, "lanczos_upsample: table upload: %s", cudaGetErrorString(cudaGetLastError()));
+  const dim3 grid((OW + 63) / 64, (OH + 15) / 16, N * C);
+  lanczos_up_kernel<<<grid, 256, 0, s>>>(lr_nchw, out_nchw, static_cast<const LanTap*>(workspace), H, W, scale);
+  return check_launch("lanczos_upsample");
 }
 
 long long rumpy_bicubic_workspace(int H, int W, int scale) {

@@ -170,6 +170,27 @@ def bicubic_upsample_device(lr, scale):
     return out
 
 
+def lanczos_upsample_device(lr, scale):
+    """`EvalHub._low_res_prep(lr, upsample_function='lanczos')` (reference evaluation/standard_eval.py:252-253, the
+    `--lanczos_upsample` switch) on the device: ToPILImage -> `Image.resize(..., LANCZOS)` -> ToTensor per image,
+    bit-exact with Pillow.  N x C x H x W fp32 CUDA tensor in [0,1] -> N x C x sH x sW fp32 CUDA tensor."""
+    from rumpy_b200 import _lib
+    if not lr.is_cuda:
+        raise _lib.RumpyB200Error('lanczos_upsample_device: CUDA tensors only (no CPU fallback)')
+    if lr.dim() != 4:
+        raise ValueError(f'lanczos_upsample_device: expected an N x C x H x W tensor, got {tuple(lr.shape)}')
+    lr = lr.contiguous().float()
+    n, c, h, w = lr.shape
+    ws_bytes = _lib.load().rumpy_lanczos_workspace(h, w, int(scale))
+    if ws_bytes < 0:
+        raise _lib.RumpyB200Error(f'lanczos_upsample_device: unsupported H={h} W={w} scale={scale} (scale 2..8)')
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=lr.device)
+    out = torch.empty((n, c, h * int(scale), w * int(scale)), dtype=torch.float32, device=lr.device)
+    _lib.call('rumpy_lanczos_upsample', lr.data_ptr(), out.data_ptr(), ws.data_ptr(), n, c, h, w, int(scale),
+              torch.cuda.current_stream().cuda_stream)
+    return out
+
+
 class DevicePairSet(PairSet):
     """PairSet whose uint8 images live in HBM and whose training batches (crop + flips + transpose + ToTensor) are
     produced by ONE kernel per batch (`rumpy_patch_batch`).  Draws the same random numbers in the same order as

@@ -72,7 +72,8 @@ def eval_run(config, **kw):
     import torch
     import torch.distributed as dist
     from rumpy_b200 import parallel
-    from rumpy_b200.shared_framework.data import PairSet, bicubic_upsample_device, psnr_y_device, quantize_u8_device
+    from rumpy_b200.shared_framework.data import (PairSet, bicubic_upsample_device, lanczos_upsample_device, psnr_y_device,
+                                                  quantize_u8_device)
     from rumpy_b200.shared_framework.models import define_model
 
     if config:
@@ -88,9 +89,6 @@ def eval_run(config, **kw):
                                '(INTEGRATION.md section 1)' % ', '.join('--' + k for k in outside))
     if kw['data_type'] != 'single-frame' or int(kw['in_features']) != 3 or kw['use_mps'] or kw['recursive']:
         raise click.UsageError('rumpy_b200 eval_sisr: single-frame RGB images on a CUDA device only')
-    if kw['lanczos_upsample']:
-        raise click.UsageError('rumpy_b200 eval_sisr: the Lanczos baseline has an oracle (oracle/pil_resample.py) but no '
-                               'device kernel yet; drop --lanczos_upsample for the bicubic baseline')
     metrics = [] if kw['model_only'] else list(kw['metrics'] or [])
     if any(m != 'PSNR' for m in metrics):
         raise click.UsageError('rumpy_b200 eval_sisr: PSNR is the metric computed on the device (SSIM / LPIPS need '
@@ -113,7 +111,8 @@ def eval_run(config, **kw):
         name, lr, hr = ds.sample(idx)
         t0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0[0].record()
-        interp = bicubic_upsample_device(lr[None].to(dev), int(kw['scale']))
+        upsample = lanczos_upsample_device if kw['lanczos_upsample'] else bicubic_upsample_device   # standard_eval.py:252
+        interp = upsample(lr[None].to(dev), int(kw['scale']))
         t0[1].record()
         score = float(psnr_y_device(interp, hr[None].to(dev))[0]) if metrics else float('nan')
         rows.append({'image': name, 'model': 'LR', 'runtime': t0[0].elapsed_time(t0[1]) * 1e-3 if kw['time_models'] else '',

@@ -167,6 +167,39 @@ def test_bicubic_baseline_1080p_frame_vs_pillow():
     assert torch.equal(crop[:, :, 16:-16, 16:-16], got[:, :, 2016:2144, 3616:3824])
 
 
+@pytest.mark.parametrize('shape,scale', [((1, 3, 1, 1), 2), ((2, 3, 37, 20), 4), ((1, 1, 5, 131), 3),
+                                         ((3, 3, 48, 48), 4), ((1, 3, 65, 33), 2), ((1, 2, 17, 19), 8), ((1, 3, 9, 70), 5)])
+def test_lanczos_baseline_bit_exact_vs_oracle_and_pillow(shape, scale):
+    """`rumpy_lanczos_upsample` (`--lanczos_upsample`, standard_eval.py:252-253) against the oracle's restatement of
+    Pillow's Lanczos-3 resampler (pinned to Pillow in tests/test_oracle_golden.py) AND against Pillow itself: ragged
+    shapes, images smaller than the filter support, every scale, saturated content."""
+    from PIL import Image
+    from oracle import pil_resample
+    from rumpy_b200.shared_framework.data import lanczos_upsample_device
+    rs = np.random.RandomState(11)
+    x = rs.rand(*shape).astype(np.float32)
+    x[0, 0] = (rs.rand(*shape[2:]) > 0.5).astype(np.float32)
+    want = pil_resample.low_res_prep(x, scale, 'lanczos')
+    dev = torch.from_numpy(x).to(DEV)
+    got = lanczos_upsample_device(dev, scale)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert torch.equal(got, lanczos_upsample_device(dev, scale))          # deterministic
+    u8 = pil_resample.to_u8(x[0, 0])
+    pil = np.asarray(Image.fromarray(u8).resize((shape[3] * scale, shape[2] * scale), resample=Image.LANCZOS))
+    assert np.array_equal(torch.round(got[0, 0] * 255).to(torch.uint8).cpu().numpy(), pil)
+
+
+def test_lanczos_baseline_1080p_frame_vs_pillow():
+    from PIL import Image
+    from rumpy_b200.shared_framework.data import lanczos_upsample_device
+    rs = np.random.RandomState(9)
+    img = rs.randint(0, 256, size=(1080, 1920, 3)).astype(np.uint8)
+    x = torch.from_numpy(img.transpose(2, 0, 1).astype(np.float32) / np.float32(255.0))[None].to(DEV)
+    got = lanczos_upsample_device(x, 4)
+    want = np.asarray(Image.fromarray(img).resize((7680, 4320), resample=Image.LANCZOS)).transpose(2, 0, 1)
+    assert torch.equal(got[0].cpu(), torch.from_numpy(want.copy()).float().div(255))      # ToTensor (true division)
+
+
 def test_glue_rejects_cpu_tensors():
     from rumpy_b200 import _lib
     from rumpy_b200.shared_framework.data import bicubic_upsample_device, psnr_y_device, quantize_u8_device
