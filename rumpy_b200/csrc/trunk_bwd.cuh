@@ -66,7 +66,7 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
   __shared__ float red_s[2][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarpA = 8, kWarpMma = 9, kWarpW = 10;
+  constexpr int kWarpA = 8, kWarpMma = 9, kWarpW = 10, kWarpMma2 = 11;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;
   uint8_t* a_s = smem + kTrunkWBytes;
@@ -79,7 +79,7 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTrunkAStages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], my_k >= 2 ? 2 : 1); }
     for (int i = 0; i < kTrunkMaxK; ++i) mbar_init(&acc_full[i], 1);
     fence_mbar_init();
   }
@@ -92,8 +92,11 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
 
   if (warp == kWarpA) {
     // ===================================================================== A-operand producer (conv layers only)
-    int stage = 0;
-    uint32_t phase = 0;
+    // Two MMA issuers => two independent stage rings (stages {0,1} feed issuer 0, {2,3} issuer 1): a parity wait only
+    // tells consecutive phases apart, so every ring must have exactly one consumer.  One tile per CTA: one ring of 4.
+    const bool two = my_k >= 2;
+    uint32_t cnt[2] = {0, 0};   // groups loaded into each ring
+    int g = 0;                  // running tile counter: tile g belongs to issuer g & 1
     for (int L = 0; L < n_layers; ++L) {
       const TrunkBwdLayer* lay = args.layers + L;
       if (lane == 0 && L + 1 < n_layers) {
@@ -104,7 +107,8 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
       if (lay->w_idx < 0) continue;
       const CUtensorMap* im = args.in_maps + lay->in_map;
       const int wait_epoch = lay->wait_epoch;
-      for (int j = 0; j < my_k; ++j) {
+      for (int j = 0; j < my_k; ++j, ++g) {
+        const int ring = two ? (g & 1) : 0;
         const int t = cta + j * G;
         const int n = t / P, rem = t - n * P;
         const int ty = rem / args.tiles_x, tx = rem - ty * args.tiles_x;
@@ -117,50 +121,67 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
           __syncwarp();
         }
         for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t c = cnt[ring]++;
+          const int stage = two ? 2 * ring + int(c & 1u) : int(c & 3u);
+          const uint32_t phase = (two ? (c >> 1) : (c >> 2)) & 1u;
           mbar_wait(&a_empty[stage], phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(&a_full[stage], kAStageBytes);
             tma_load_4d(a_s + stage * kAStageBytes, im, &a_full[stage], 0, tx * kTileW + kx - 1, ty * kTileH - 1, n);
           }
           __syncwarp();
-          if (++stage == kTrunkAStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == kWarpMma) {
-    // ===================================================================== MMA issuer
+  } else if (warp == kWarpMma || warp == kWarpMma2) {
+    // ===================================================================== MMA issuers (two warps, see trunk_pipe.cuh)
+    const int me = warp == kWarpMma ? 0 : 1;
+    const bool two = my_k >= 2;
     constexpr uint32_t kIdesc = make_idesc_bf16(128, 64);
-    int stage = 0, cl = 0;   // cl: ordinal of the conv layer (parity of the weight / accumulator barriers)
-    uint32_t phase = 0;
-    for (int L = 0; L < n_layers; ++L) {
-      if (args.layers[L].w_idx < 0) continue;
-      for (int j = 0; j < my_k; ++j) {
-        const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
-        for (int kx = 0; kx < 3; ++kx) {
-          if (j == 0) mbar_wait(&w_full[kx], uint32_t(cl & 1));
-          mbar_wait(&a_full[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint32_t a_addr = smem_u32(a_s + stage * kAStageBytes);
-            const uint32_t b_addr = smem_u32(w_s + kx * kTrunkWThird);
+    int cl = 0, g = 0;   // cl: ordinal of the conv layer (parity of the weight / accumulator barriers)
+    uint32_t cnt = 0;    // groups consumed from this issuer's own stage ring (stages {2 me, 2 me + 1}; one ring of 4 when alone)
+    if (two || me == 0) {
+      for (int L = 0; L < n_layers; ++L) {
+        if (args.layers[L].w_idx < 0) continue;
+        int my_last = -1;
+        for (int j = 0; j < my_k; ++j)
+          if (!two || ((g + j) & 1) == me) my_last = j;
+        bool have_w = false;
+        for (int j = 0; j < my_k; ++j, ++g) {
+          if (two && (g & 1) != me) continue;
+          const uint32_t d_tmem = tmem_base + uint32_t(kTrunkAccCol + j * 64);
+          for (int kx = 0; kx < 3; ++kx) {
+            if (!have_w) mbar_wait_trap(&w_full[kx], uint32_t(cl & 1));
+            const uint32_t c = cnt++;
+            const int stage = two ? 2 * me + int(c & 1u) : int(c & 3u);
+            mbar_wait_trap(&a_full[stage], (two ? (c >> 1) : (c >> 2)) & 1u);
+            {
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t a_addr = smem_u32(a_s + stage * kAStageBytes);
+                const uint32_t b_addr = smem_u32(w_s + kx * kTrunkWThird);
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              const uint64_t adesc = make_smem_desc(a_addr + ky * (kTileW * 128), 16, 1024, kLayoutSw128);
-              const uint64_t bdesc = make_smem_desc(b_addr + ky * 8192, 16, 1024, kLayoutSw128);
+                for (int ky = 0; ky < 3; ++ky) {
+                  const uint64_t adesc = make_smem_desc(a_addr + ky * (kTileW * 128), 16, 1024, kLayoutSw128);
+                  const uint64_t bdesc = make_smem_desc(b_addr + ky * 8192, 16, 1024, kLayoutSw128);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (kx | ky | k) != 0);
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (kx | ky | k) != 0);
+                }
+                umma_commit(&a_empty[stage]);
+                if (j == my_last) umma_commit(&w_empty[kx]);
+              }
+              __syncwarp();
             }
-            umma_commit(&a_empty[stage]);
-            if (j == my_k - 1) umma_commit(&w_empty[kx]);
           }
-          __syncwarp();
-          if (++stage == kTrunkAStages) { stage = 0; phase ^= 1; }
+          {
+            have_w = true;
+            if (elect_one()) umma_commit(&acc_full[j]);
+            __syncwarp();
+          }
         }
-        if (elect_one()) umma_commit(&acc_full[j]);
-        __syncwarp();
+        ++cl;
       }
-      ++cl;
     }
   } else if (warp == kWarpW) {
     // ===================================================================== weight producer (three kx thirds)
