@@ -211,7 +211,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one elected lane)
-    if (RESIDENT_B) mbar_wait(&b_bar, 0);
+    if (RESIDENT_B) mbar_wait_trap(&b_bar, 0);
     if (lane == 0) RB_STAMP(3);
     int stage = 0;
     uint32_t phase = 0;
@@ -219,12 +219,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      mbar_wait_trap(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
         for (int kx = 0; kx < 3; ++kx) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_trap(&full_bar[stage], phase);
           tc_fence_after();
           if (it == 0 && chunk == 0 && kx == 0 && lane == 0) RB_STAMP(4);
           if (elect_one()) {
