@@ -162,6 +162,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.out_nchw = d.out_nchw;
   a.cout_real = d.cout_real;
   a.dbg = opt().timeline;
+  a.dbg_mode = opt().conv_dbg;
   uint32_t flags = d.flags & (kConvRelu | kConvPool);
   if (d.y_bf16) flags |= kConvOutBf16;
   if (d.y_f32) flags |= kConvOutF32;

@@ -59,7 +59,9 @@ struct ConvArgs {
   float* pool_partial;   // [m_tiles][2][cout]
   float* out_nchw;       // BN == 16 variant only: fp32 NCHW [N][cout_real][H][W]
   int cout_real;         // BN == 16 variant only: number of real output channels (<= 16)
-  long long* dbg;        // optional per-CTA timeline (16 clock64 slots per CTA); nullptr in production
+  long long* dbg;        // optional per-CTA timeline (2 x 16 clock64 slots per CTA); nullptr in production
+  int dbg_mode;          // timing experiments (garbage results), 0 in production: 1 = A boxes fetched only for the first
+                         // `stages` fills, 4 = no MMAs issued, 8 = timeline stamps from the pooled convs only
   uint32_t flags;
 };
 
@@ -94,13 +96,17 @@ __host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, 
   return s;
 }
 
-#define RB_STAMP(slot) do { if (args.dbg) args.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+#define RB_STAMP_ON (args.dbg && (!(args.dbg_mode & 8) || (args.flags & kConvPool)))   // mode 8: pooled convs only
+#define RB_STAMP(slot) do { if (RB_STAMP_ON) args.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+// second region (after gridDim.x * 16 slots): the epilogue of this CTA's third tile (its TMA-issuing thread) in slots
+// 0..7, cycles the MMA warp waited for an accumulator / for A stages and the producer for free stages in 12..14
+#define RB_STAMP2(slot) do { if (RB_STAMP_ON && it == 2 && et == 0) args.dbg[(gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ long long global_timer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define RB_STAMP_NS(slot) do { if (args.dbg) args.dbg[blockIdx.x * 16 + (slot)] = global_timer_ns(); } while (0)
+#define RB_STAMP_NS(slot) do { if (RB_STAMP_ON) args.dbg[blockIdx.x * 16 + (slot)] = global_timer_ns(); } while (0)
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
@@ -187,6 +193,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     grid_dep_wait();   // weights are static; activations come from the previous kernel
     int stage = 0;
     uint32_t phase = 0;
+    long long w_empty = 0;
     for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
       const int n = mt / tiles_per_img;
       const int rem = mt - n * tiles_per_img;
@@ -195,8 +202,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       int mi = 0, cc = 0;  // input map index / 64-channel chunk inside that map
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
         for (int kx = 0; kx < 3; ++kx) {
+          const long long t0 = args.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (elect_one()) {
+          if (args.dbg) w_empty += clock64() - t0;
+          if ((args.dbg_mode & 1) && (phase || mt != mt_first)) {
+            if (elect_one()) mbar_arrive(&full_bar[stage]);
+          } else if (elect_one()) {
             uint8_t* sa = stage0 + stage * kStageBytes;
             mbar_expect_tx(&full_bar[stage], kStageBytes);
             // box {64 ch, 16 px, 10 rows}: rows y0-1 .. y0+8 at column offset kx-1 serve ky = 0, 1, 2
@@ -209,6 +220,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
         if (++cc == args.a_chunks_per_map) { cc = 0; ++mi; }
       }
     }
+    if (RB_STAMP_ON && lane == 0) args.dbg[(gridDim.x + blockIdx.x) * 16 + 14] = w_empty;
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (one elected lane)
     if (RESIDENT_B) mbar_wait_trap(&b_bar, 0);
@@ -216,15 +228,20 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    long long w_acc = 0, w_full = 0;
     for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const long long t0 = args.dbg ? clock64() : 0;
       mbar_wait_trap(&tmem_empty_bar[acc], acc_phase ^ 1);
+      if (args.dbg) w_acc += clock64() - t0;
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
         for (int kx = 0; kx < 3; ++kx) {
+          const long long t1 = args.dbg ? clock64() : 0;
           mbar_wait_trap(&full_bar[stage], phase);
+          if (args.dbg) w_full += clock64() - t1;
           tc_fence_after();
           if (it == 0 && chunk == 0 && kx == 0 && lane == 0) RB_STAMP(4);
           if (elect_one()) {
@@ -233,6 +250,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                                                : a_addr + kAStageBytes;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
+              if (args.dbg_mode & 4) break;
               // tap (ky,kx): rows [16*ky, 16*ky+128) of the box -- a 2 KB (two swizzle atoms) shift
               const uint64_t adesc = make_smem_desc(a_addr + ky * (kTileW * 128), 16, 1024, kLayoutSw128);
               const uint64_t bdesc = make_smem_desc(b_addr + ky * kBBlock, 16, 1024, kLayoutSw128);
@@ -250,6 +268,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       if (it == 0 && lane == 0) RB_STAMP(5);
+    }
+    if (RB_STAMP_ON && lane == 0) {
+      args.dbg[(gridDim.x + blockIdx.x) * 16 + 12] = w_acc;
+      args.dbg[(gridDim.x + blockIdx.x) * 16 + 13] = w_full;
     }
   } else {
     // ===================================================================== epilogue (128 threads)
@@ -340,11 +362,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             if (et == 0) tma_store_wait_read0();
             named_bar_sync(1, 128);
           }
+          RB_STAMP2(0);
           if (j == 0) {
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             if (et == 0) RB_STAMP(it == 0 ? 6 : 9);
           }
+          RB_STAMP2(1);
           uint32_t v[64];
           {
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + j * 64);
@@ -352,6 +376,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
             tmem_ld_wait();
           }
+          RB_STAMP2(2);
           if (j == kChunksPerTile - 1) {
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
@@ -415,11 +440,14 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
                                pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]));
             }
           }
+          RB_STAMP2(3);
           fence_proxy_async_smem();
           // double-buffered staging: the store issued one chunk ago must have finished READING the other
           // buffer before anyone refills it in the next chunk -- checked here, a whole chunk later
           if (!has_in && stg_bufs == 2 && et == 0) tma_store_wait_read0();
+          RB_STAMP2(4);
           named_bar_sync(2, 128);
+          RB_STAMP2(5);
           if (et == 0) {
             RB_STAMP(it == 0 ? 8 : 10);
             if (flags & kConvOutF32) {
@@ -439,6 +467,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
               issue_inputs(cc + 1);
             }
           }
+          RB_STAMP2(6);
           if (flags & kConvPool) {
             // channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves
             const int c = et & 63, half = et >> 6;
@@ -461,6 +490,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = s;
             if (has_in && stg_bufs == 1) named_bar_sync(3, 128);  // single slot: readers finish before the next input TMA
           }
+          RB_STAMP2(7);
         }
       }
       if (et == 0) { RB_STAMP(11); tma_store_wait_all0(); RB_STAMP(12); }

@@ -34,6 +34,7 @@ struct Options {
   int use_pdl = 1;            // programmatic dependent launch between per-layer kernels
   int infer_u_bf16 = 1;       // per-layer inference: pre-attention activation u in bf16 (net.cu build_plan)
   int conv_2x = 0;            // experiment: two small conv CTAs per SM
+  int conv_dbg = 0;           // per-layer conv kernel timing experiments (garbage results): see ConvArgs::dbg_mode
   int trunk_sync_mode = 8;    // dataflow kernel: release store of the tile epoch (needed, DESIGN.md trunk protocol)
   int trunk_dbg_layers = 0;   // > 0: trunk kernels write a clock64 timeline of this many layers to `timeline`
   long long* timeline = nullptr;
@@ -43,7 +44,7 @@ struct Options {
     return unsigned(use_trunk) | unsigned(use_cluster) << 1 | unsigned(use_trunk_bwd) << 2 | unsigned(use_band) << 3 |
            unsigned(use_fused_ca) << 4 | unsigned(cluster_groups == 4) << 5 | unsigned(use_pdl) << 6 |
            unsigned(conv_2x) << 7 | unsigned(wgrad_chunks) << 8 | unsigned(wgrad_tiles_per_split) << 12 |
-           unsigned(timeline != nullptr) << 28 | unsigned(cluster_split) << 29 | unsigned(infer_u_bf16) << 30 | unsigned(cluster_dbg != 0) << 31;
+           unsigned(timeline != nullptr) << 28 | unsigned(cluster_split) << 29 | unsigned(infer_u_bf16) << 30 | unsigned(cluster_dbg != 0 || conv_dbg != 0) << 31;
   }
 };
 const Options& opt();

@@ -1149,6 +1149,7 @@ int rumpy_net_set_option(void* net, const char* name, long long value) {
   else if (k == "wgrad_tiles_per_split") o.wgrad_tiles_per_split = v < 1 ? 1 : v;
   else if (k == "pdl") o.use_pdl = v != 0;
   else if (k == "conv_2x") o.conv_2x = v != 0;
+  else if (k == "conv_dbg") o.conv_dbg = v;
   else if (k == "trunk_sync_mode") o.trunk_sync_mode = v;
   else return set_error(RUMPY_ERR_ARG, "net_set_option: unknown option '%s'", name);
   return RUMPY_OK;
