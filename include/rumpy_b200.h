@@ -62,7 +62,7 @@ int rumpy_pack_bias(const float* bias, float* bias_packed, int cout, int rows_pa
  *   y_bf16    [N,H,W,Cout] bf16 or NULL; with out_shuffle_r = r > 1 the tensor [N,H*r,W*r,Cout/r^2] written
  *             in pixel-shuffled order (conv + nn.PixelShuffle of common.Upsampler, common.py:30-41)
  *   y_f32     [N,H,W,Cout] fp32 or NULL
- *   pool_partial [N*ceil(H/8)*ceil(W/16)][2][Cout] fp32, required with RUMPY_CONV_POOL
+ *   pool_partial [N][rumpy_pool_rows(H, W, Cout)][Cout] fp32, required with RUMPY_CONV_POOL (Cin == Cout)
  * Replaces: nn.Conv2d.forward at common.py:6-9 (+ the elementwise ops fused above); with dgrad-packed
  * weights it is also the conv's input-gradient (autograd's convolution_backward, base_architecture.py:432). */
 int rumpy_conv3x3(const void* x_bf16, const void* w_packed, const float* bias, const float* residual,
@@ -104,6 +104,9 @@ int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const
  * whole networks convert inside the head / tail convs).  Either output of nchw_to_nhwc may be NULL. */
 int rumpy_nchw_to_nhwc(const float* x_nchw, float* y_f32, void* y_bf16, int N, int C, int H, int W, void* stream);
 int rumpy_nhwc_to_nchw(const void* x_nhwc, int x_is_bf16, float* y_nchw, int N, int C, int H, int W, void* stream);
+/* Rows per image of a pool_partial buffer (two per conv tile; the tile geometry depends on C).  Pure host arithmetic. */
+int rumpy_pool_rows(int H, int W, int C);
+
 /* Per-image channel sums in pool_partial format, for a stand-alone CALayer.forward (architectures.py:41-42:
  * nn.AdaptiveAvgPool2d(1)); inside an RCAB the sums come from rumpy_conv3x3(..., RUMPY_CONV_POOL). */
 int rumpy_pool_sum(const float* x_nhwc, float* pool_partial, int N, int H, int W, int C, void* stream);

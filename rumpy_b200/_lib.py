@@ -30,6 +30,7 @@ SIGNATURES = {
     'rumpy_nchw_to_nhwc': [_fp, _fp, _vp, _i, _i, _i, _i, _vp],
     'rumpy_nhwc_to_nchw': [_vp, _i, _fp, _i, _i, _i, _i, _vp],
     'rumpy_pool_sum': [_fp, _fp, _i, _i, _i, _i, _vp],
+    'rumpy_pool_rows': [_i, _i, _i],
     'rumpy_net_create': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i],
     'rumpy_net_create_q': [_c.POINTER(_c.c_void_p), _i, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _c.c_char_p, _i, _i],
     'rumpy_net_set_metadata': [_vp, _fp, _i, _i],

@@ -99,7 +99,7 @@ def _rcab_nhwc(blk, xf, xb, N, H, W, C):
     t = torch.empty_like(xb)
     conv_nhwc(blk.body[0], xb, N, H, W, out_bf16=t, relu=True)
     u = torch.empty_like(xf)
-    pp = torch.empty((N * ops.tiles_per_image(H, W), 2, C), dtype=torch.float32, device=xf.device)
+    pp = torch.empty((N, ops.pool_rows(H, W, C), C), dtype=torch.float32, device=xf.device)
     conv_nhwc(blk.body[2], t, N, H, W, out_f32=u, pool_partial=pp)
     out = torch.empty_like(xf)
     outb = torch.empty_like(xb)

@@ -63,10 +63,10 @@ int device_info(int* num_sms) {
 
 // 4-D NHWC map {C, W, H, N} with explicit strides (bytes) and box {box_c, 16, 8, 1}, 128B swizzle, zero OOB fill.
 int make_map_nhwc(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, uint64_t stride_w,
-                  uint64_t stride_h, uint64_t stride_n, int box_h) {
+                  uint64_t stride_h, uint64_t stride_n, int box_h, int box_w) {
   const cuuint64_t dims[4] = {cuuint64_t(C), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
   const cuuint64_t strides[3] = {stride_w, stride_h, stride_n};
-  const cuuint32_t box[4] = {cuuint32_t(f32 ? 32 : 64), kTileW, cuuint32_t(box_h), 1};
+  const cuuint32_t box[4] = {cuuint32_t(f32 ? 32 : 64), cuuint32_t(box_w), cuuint32_t(box_h), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error(RUMPY_ERR_ARG, "tensor base not 16B aligned");
   CUresult r = get_encode_fn()(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
@@ -80,13 +80,13 @@ int make_map_nhwc(CUtensorMap* m, bool f32, const void* base, int C, int W, int 
 // Dense NHWC tensor, optionally viewed through a pixel (un)shuffle of factor r: sub-pixel q=(i,j) of the
 // [N, H*r, W*r, C] tensor is the strided [N,H,W,C] view starting at (i, j).
 int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
-                      int box_h) {
+                      int box_h, int box_w) {
   const uint64_t es = f32 ? 4 : 2;
   const int i = q / r, j = q % r;
   const uint64_t Wf = uint64_t(W) * r, Hf = uint64_t(H) * r;
   const char* b = static_cast<const char*>(base) + (uint64_t(i) * Wf + j) * C * es;
   return make_map_nhwc(m, f32, b, C, W, H, N, uint64_t(r) * C * es, uint64_t(r) * Wf * C * es, Hf * Wf * C * es,
-                       box_h);
+                       box_h, box_w);
 }
 
 // packed weights [9][rows][k] bf16 -> 3-D map {k, rows, 9}, box {64, bn, taps} (9 taps resident, 3 streaming)
@@ -146,9 +146,6 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   p->bn = bn;
   p->resident = resident;
   a.N = d.N; a.H = d.H; a.W = d.W;
-  a.tiles_x = (d.W + kTileW - 1) / kTileW;
-  a.tiles_y = (d.H + kTileH - 1) / kTileH;
-  a.m_tiles = d.N * a.tiles_x * a.tiles_y;
   a.n_tiles = thin ? 1 : d.Cout / bn;
   a.cin_chunks = cin_chunks;
   a.a_chunks_per_map = cin_chunks / (rin * rin);
@@ -170,6 +167,8 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   if (d.mask) flags |= kConvMask;
   if (!thin && !(flags & (kConvOutBf16 | kConvOutF32))) return set_error(RUMPY_ERR_ARG, "conv3x3: no output");
   if ((flags & kConvPool) && !d.pool_partial) return set_error(RUMPY_ERR_ARG, "conv3x3: POOL needs pool_partial");
+  if ((flags & kConvPool) && (d.Cin != d.Cout || resident != (size_t(9) * cin_chunks * 64 * 128 <= 96 * 1024)))
+    return set_error(RUMPY_ERR_ARG, "conv3x3: POOL needs Cin == Cout and the default BN (pool rows: conv_pool_rows)");
   if (rout > 1 && (flags & (kConvOutF32 | kConvResF32 | kConvMask | kConvPool)))
     return set_error(RUMPY_ERR_ARG, "conv3x3: shuffle store supports bf16 output only");
   a.flags = flags;
@@ -202,6 +201,11 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
     p->smem = conv_smem_bytes(64, false, 1, 2, flags, 1);
     ctas_per_sm = 2;
   }
+  // resident weights: 16 x 8 tiles fed by one halo box; streamed weights: 8 x 16 tiles, one box per kx (conv3x3_tc.cuh)
+  const int th = p->resident ? kTallH : kTileH, tw = p->resident ? kTallW : kTileW;
+  a.tiles_x = (d.W + tw - 1) / tw;
+  a.tiles_y = (d.H + th - 1) / th;
+  a.m_tiles = d.N * a.tiles_x * a.tiles_y;
   int grid = sms * ctas_per_sm < a.m_tiles * a.n_tiles ? sms * ctas_per_sm : a.m_tiles * a.n_tiles;
   grid -= grid % a.n_tiles;
   if (grid < a.n_tiles) grid = a.n_tiles;
@@ -209,19 +213,20 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   // tensor maps
   const int cin_sub = d.Cin / (rin * rin);
   for (int q = 0; q < rin * rin; ++q)
-    if (int e = make_map_nhwc_sub(&p->maps.a[q], false, d.x, cin_sub, d.W, d.H, d.N, rin, q, kABoxH)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.a[q], false, d.x, cin_sub, d.W, d.H, d.N, rin, q,
+                                  p->resident ? kTallBoxH : kABoxH, p->resident ? kTallBoxW : kTileW)) return e;
   if (int e = make_map_weights(&p->maps.w, d.w, d.Cin, thin ? 16 : d.Cout, bn, p->resident ? 9 : 3)) return e;
   if (d.y_bf16) {
     const int cout_sub = d.Cout / (rout * rout);
     for (int q = 0; q < rout * rout; ++q)
-      if (int e = make_map_nhwc_sub(&p->maps.ob[q], false, d.y_bf16, cout_sub, d.W, d.H, d.N, rout, q, kTileH)) return e;
+      if (int e = make_map_nhwc_sub(&p->maps.ob[q], false, d.y_bf16, cout_sub, d.W, d.H, d.N, rout, q, th, tw)) return e;
   }
   if (d.y_f32)
-    if (int e = make_map_nhwc_sub(&p->maps.of, true, d.y_f32, d.Cout, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.of, true, d.y_f32, d.Cout, d.W, d.H, d.N, 1, 0, th, tw)) return e;
   if (d.residual)
-    if (int e = make_map_nhwc_sub(&p->maps.rf, true, d.residual, d.Cout, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.rf, true, d.residual, d.Cout, d.W, d.H, d.N, 1, 0, th, tw)) return e;
   if (d.mask)
-    if (int e = make_map_nhwc_sub(&p->maps.mb, false, d.mask, d.Cout, d.W, d.H, d.N, 1, 0, kTileH)) return e;
+    if (int e = make_map_nhwc_sub(&p->maps.mb, false, d.mask, d.Cout, d.W, d.H, d.N, 1, 0, th, tw)) return e;
   return RUMPY_OK;
 }
 
@@ -466,12 +471,13 @@ int ca_apply_launch(const float* pool_partial, int partials_per_img, float* comp
 
 extern "C" {
 
+int rumpy_pool_rows(int H, int W, int C) { return (H > 0 && W > 0 && C >= 64) ? conv_pool_rows(H, W, C) : 0; }
+
 int rumpy_ca_apply(const float* pool_partial, const void* u, int u_is_f32, const float* x_in, const float* w1,
                    const float* b1, const float* w2, const float* b2, float* x_out, void* x_out_bf16,
                    float* save_mean, float* save_hid, float* save_y, int N, int H, int W, int C, int Cr,
                    void* stream) {
-  const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
-  return ca_apply_launch(pool_partial, tiles * 2, nullptr, u, u_is_f32, x_in, w1, b1, w2, b2, x_out, x_out_bf16,
+  return ca_apply_launch(pool_partial, conv_pool_rows(H, W, C), nullptr, u, u_is_f32, x_in, w1, b1, w2, b2, x_out, x_out_bf16,
                          save_mean, save_hid, save_y, N, H, W, C, Cr, cudaStream_t(stream), nullptr);
 }
 
@@ -498,9 +504,9 @@ int rumpy_nhwc_to_nchw(const void* x, int x_is_bf16, float* y, int N, int C, int
 int rumpy_pool_sum(const float* x_nhwc, float* pool_partial, int N, int H, int W, int C, void* stream) {
   if (int e = device_info(nullptr)) return e;
   if (!x_nhwc || !pool_partial || C <= 0 || C > 256) return set_error(RUMPY_ERR_ARG, "pool_sum: bad args");
-  const int tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
   const int block = (1024 / C) * C;
-  pool_sum_kernel<<<N, block, block * sizeof(float), cudaStream_t(stream)>>>(x_nhwc, pool_partial, tiles * 2, H * W, C);
+  pool_sum_kernel<<<N, block, block * sizeof(float), cudaStream_t(stream)>>>(x_nhwc, pool_partial,
+                                                                              conv_pool_rows(H, W, C), H * W, C);
   return check_launch("pool_sum");
 }
 

@@ -69,6 +69,15 @@ constexpr int kTileH = 8, kTileW = 16, kTileM = 128;
 constexpr int kABoxH = kTileH + 2;                 // A box rows: the tile plus one halo row above and below
 constexpr int kABytes = kTileM * 128;              // one 128-pixel x 64-channel bf16 operand / staging tile
 constexpr int kAStageBytes = kABoxH * kTileW * 128;  // 20 KB: serves the three ky taps of one (kx, chunk)
+// Resident-weights geometry (64 input channels): the tile is 16 rows x 8 pixels and ONE halo box {64 ch, 10 px, 18 rows}
+// serves all nine taps: tap (ky,kx) is the same descriptor with the start address moved by (ky*10 + kx) * 128 B and
+// SBO = 1280 B (next image row = next 8-pixel group).  The tensor core applies the 128-byte swizzle to the absolute
+// shared-memory address, so a start that is not atom-aligned reads exactly what TMA wrote
+// (tools/experiments/umma_sw128_shift_test.cu: exact at pitch 16 and 10).  23 KB fetched per tile instead of 60 KB.
+constexpr int kTallH = 16, kTallW = 8;
+constexpr int kTallBoxH = kTallH + 2, kTallBoxW = kTallW + 2;
+constexpr int kTallBoxBytes = kTallBoxH * kTallBoxW * 128;            // 23,040
+constexpr int kTallStageBytes = (kTallBoxBytes + 1023) & ~1023;       // stages stay 1024-byte aligned
 constexpr int kStgF32Bytes = 2 * kABytes;          // fp32 staging: two 32-channel halves
 constexpr int kStgBf16Bytes = kABytes;
 constexpr int kMaxStages = 8;
@@ -92,7 +101,7 @@ __host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, 
   size_t s = 1024;
   if (bn != 16) s += size_t(stg_bufs) * conv_stg_buf_bytes(flags);
   if (resident_b) s += size_t(9) * cin_chunks * conv_b_block_bytes(bn);
-  s += size_t(stages) * (kAStageBytes + (resident_b ? 0 : 3 * conv_b_block_bytes(bn)));
+  s += size_t(stages) * (resident_b ? kTallStageBytes : kAStageBytes + 3 * conv_b_block_bytes(bn));
   return s;
 }
 
@@ -121,7 +130,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   constexpr uint32_t kTmemCols = 2 * BN;   // 32 is the minimum TMEM allocation
   constexpr int kChunksPerTile = BN / 64;  // 0 for the thin (BN = 16) NCHW-output variant
   constexpr uint32_t kIdesc = make_idesc_bf16(128, BN);
-  constexpr int kStageBytes = kAStageBytes + (RESIDENT_B ? 0 : 3 * kBBlock);
+  constexpr int kStageBytes = RESIDENT_B ? kTallStageBytes : kAStageBytes + 3 * kBBlock;
+  constexpr int TH = RESIDENT_B ? kTallH : kTileH, TW = RESIDENT_B ? kTallW : kTileW;   // tile geometry
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -197,11 +207,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
       const int n = mt / tiles_per_img;
       const int rem = mt - n * tiles_per_img;
-      const int y0 = (rem / args.tiles_x) * kTileH;
-      const int x0 = (rem % args.tiles_x) * kTileW;
+      const int y0 = (rem / args.tiles_x) * TH;
+      const int x0 = (rem % args.tiles_x) * TW;
       int mi = 0, cc = 0;  // input map index / 64-channel chunk inside that map
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
-        for (int kx = 0; kx < 3; ++kx) {
+        for (int kx = 0; kx < (RESIDENT_B ? 1 : 3); ++kx) {
           const long long t0 = args.dbg ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (args.dbg) w_empty += clock64() - t0;
@@ -209,10 +219,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             if (elect_one()) mbar_arrive(&full_bar[stage]);
           } else if (elect_one()) {
             uint8_t* sa = stage0 + stage * kStageBytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
-            // box {64 ch, 16 px, 10 rows}: rows y0-1 .. y0+8 at column offset kx-1 serve ky = 0, 1, 2
-            tma_load_4d(sa, &maps.a[mi], &full_bar[stage], cc * 64, x0 + kx - 1, y0 - 1, n);
-            if (!RESIDENT_B) tma_load_3d(sa + kAStageBytes, &maps.w, &full_bar[stage], chunk * 64, n_tile * BN, kx * 3);
+            if constexpr (RESIDENT_B) {
+              // one halo box {64 ch, 10 px, 18 rows} serves all nine taps
+              mbar_expect_tx(&full_bar[stage], kTallBoxBytes);
+              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], cc * 64, x0 - 1, y0 - 1, n);
+            } else {
+              mbar_expect_tx(&full_bar[stage], kStageBytes);
+              // box {64 ch, 16 px, 10 rows}: rows y0-1 .. y0+8 at column offset kx-1 serve ky = 0, 1, 2
+              tma_load_4d(sa, &maps.a[mi], &full_bar[stage], cc * 64, x0 + kx - 1, y0 - 1, n);
+              tma_load_3d(sa + kAStageBytes, &maps.w, &full_bar[stage], chunk * 64, n_tile * BN, kx * 3);
+            }
           }
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -238,16 +254,32 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
-        for (int kx = 0; kx < 3; ++kx) {
+        for (int kx = 0; kx < (RESIDENT_B ? 1 : 3); ++kx) {
           const long long t1 = args.dbg ? clock64() : 0;
           mbar_wait_trap(&full_bar[stage], phase);
           if (args.dbg) w_full += clock64() - t1;
           tc_fence_after();
           if (it == 0 && chunk == 0 && kx == 0 && lane == 0) RB_STAMP(4);
-          if (elect_one()) {
+          if (RESIDENT_B && elect_one()) {
             const uint32_t a_addr = smem_u32(stage0 + stage * kStageBytes);
-            const uint32_t b_addr = RESIDENT_B ? smem_u32(b_res + (chunk * 9 + kx * 3) * kBBlock)
-                                               : a_addr + kAStageBytes;
+            const uint32_t b_addr = smem_u32(b_res + chunk * 9 * kBBlock);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              if (args.dbg_mode & 4) break;
+              // packed tap slot = kx*3 + ky: the box shifted by ky rows and kx pixels; 8-pixel groups one box row
+              // (1280 B) apart
+              const uint64_t adesc = make_smem_desc(a_addr + ((tap % 3) * kTallBoxW + tap / 3) * 128, 16,
+                                                    kTallBoxW * 128, kLayoutSw128);
+              const uint64_t bdesc = make_smem_desc(b_addr + tap * kBBlock, 16, 1024, kLayoutSw128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (chunk | tap | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);
+          }
+          if (!RESIDENT_B && elect_one()) {
+            const uint32_t a_addr = smem_u32(stage0 + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kAStageBytes;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               if (args.dbg_mode & 4) break;
@@ -278,7 +310,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;               // pixel row of the tile == TMEM lane
     const int et = (warp - 2) * 32 + lane;       // 0..127, et==0 is the TMA issuing thread
-    const int ly = row >> 4, lx = row & 15;
+    const int ly = RESIDENT_B ? row >> 3 : row >> 4, lx = RESIDENT_B ? row & 7 : row & 15;
     for (int i = et; i < BN; i += 128) bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
     named_bar_sync(1, 128);
     grid_dep_wait();   // residual / mask inputs and every global write must follow the previous kernel
@@ -288,8 +320,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
         const int n = mt / tiles_per_img;
         const int rem = mt - n * tiles_per_img;
-        const int y = (rem / args.tiles_x) * kTileH + ly;
-        const int x = (rem % args.tiles_x) * kTileW + lx;
+        const int y = (rem / args.tiles_x) * TH + ly;
+        const int x = (rem % args.tiles_x) * TW + lx;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -320,7 +352,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
         const int t_oc = n_tile * kChunksPerTile + (cidx % kChunksPerTile);
         const int t_n = t_mt / tiles_per_img;
         const int t_rem = t_mt - t_n * tiles_per_img;
-        const int t_y0 = (t_rem / args.tiles_x) * kTileH, t_x0 = (t_rem % args.tiles_x) * kTileW;
+        const int t_y0 = (t_rem / args.tiles_x) * TH, t_x0 = (t_rem % args.tiles_x) * TW;
         const int slot = (stg_bufs == 2) ? (cidx & 1) : 0;
         uint8_t* sf = smem + slot * stg_buf_bytes;
         uint8_t* sb = sf + (use_f32 ? kStgF32Bytes : 0);
@@ -338,8 +370,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
         const int n = mt / tiles_per_img;
         const int rem = mt - n * tiles_per_img;
-        const int y0 = (rem / args.tiles_x) * kTileH;
-        const int x0 = (rem % args.tiles_x) * kTileW;
+        const int y0 = (rem / args.tiles_x) * TH;
+        const int x0 = (rem % args.tiles_x) * TW;
         const bool valid = (y0 + ly < args.H) && (x0 + lx < args.W);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;

@@ -100,7 +100,14 @@ struct ConvPlan {
 };
 
 int make_map_nhwc_sub(CUtensorMap* m, bool f32, const void* base, int C, int W, int H, int N, int r, int q,
-                      int box_h);
+                      int box_h, int box_w = kTileW);
+// Rows per image of the pool-partial buffer a pooled C-channel conv writes (two 64-pixel halves per tile; the tile
+// geometry of conv3x3_tc.cuh depends on whether the weights stay resident in shared memory, i.e. on C).
+inline int conv_pool_rows(int H, int W, int C) {
+  const bool tall = size_t(9) * (C / 64) * 64 * 128 <= 96 * 1024;
+  const int th = tall ? kTallH : kTileH, tw = tall ? kTallW : kTileW;
+  return 2 * ((H + th - 1) / th) * ((W + tw - 1) / tw);
+}
 int conv_plan_build(ConvPlan* p, const ConvDesc& d);
 // RCAB tail fused kernel (conv2 + channel attention + skip), conv3x3_ca.cuh.  d: x = conv2 input (bf16), w/bias,
 // residual = x_in (fp32), y_f32 / y_bf16 = x_out, pool_partial; u_store (fp32 NHWC) may be null (inference).

@@ -318,7 +318,8 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
   for (auto& g : G_bufs) g = static_cast<float*>(bp.take(px * C * 4));
   struct { std::vector<float*>* v; bool han; float* operator[](int g) const { return (*v)[han ? g : (g & 1)]; } } G_f{&G_bufs, han};
   float* han_body_f = han ? static_cast<float*>(bp.take(px * C * 4)) : nullptr;   // body conv output (no skip in HAN)
-  const int tiles = ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW);
+  const int tiles = ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW);   // dataflow trunk kernels
+  const int pool_rows = conv_pool_rows(H, W, C);   // per image, written by the pooled per-layer convs
   int ci = 0;  // conv cursor
   // ---- head
   {
@@ -467,7 +468,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
     void* xb_shared = training ? nullptr : bp.take(px * C * 2);
     void* t_shared = training ? nullptr : bp.take(px * C * 2);
     void* u_shared = training ? nullptr : bp.take(u_bytes);
-    float* pool_shared = training ? nullptr : static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
+    float* pool_shared = training ? nullptr : static_cast<float*>(bp.take(size_t(N) * pool_rows * C * 4));
     void* gb[2] = {bp.take(px * C * 2), bp.take(px * C * 2)};
     float* pool_compact = static_cast<float*>(bp.take(size_t(N) * 64 * C * 4));
     const size_t n_rcab = size_t(n->n_groups) * n->n_blocks;
@@ -482,7 +483,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         void* t = training ? bp.take(px * C * 2) : t_shared;
         void* u = training ? bp.take(u_bytes) : u_shared;
         void* xb = training ? bp.take(px * C * 2) : xb_shared;
-        float* pool = training ? static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4)) : pool_shared;
+        float* pool = training ? static_cast<float*>(bp.take(size_t(N) * pool_rows * C * 4)) : pool_shared;
         float* sv = training ? static_cast<float*>(bp.take(size_t(N) * (2 * C + Cr) * 4)) : nullptr;
         BlockRec br{cur_b, t, u, sv, ci, ci + 1, cai};
         ConvDesc d1{};
@@ -838,7 +839,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           int ca_chunks = int((vec + 4095) / 4096);     // >= 16 vectors per thread: pure streaming kernel
           { const int cap = (148 * 4 + N - 1) / N; if (ca_chunks > cap) ca_chunks = cap; if (ca_chunks < 1) ca_chunks = 1; }
           float* du_cs = static_cast<float*>(bp.take(size_t(N) * ca_chunks * C * 4));
-          float* dt_pool = static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
+          float* dt_pool = static_cast<float*>(bp.take(size_t(N) * pool_rows * C * 4));
           Op cb{};
           cb.type = OP_CA_BWD;
           cb.ca = n->cas[br.ca];
@@ -854,7 +855,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
           d1.x = dt; d1.residual = Q; d1.y_f32 = Q; d1.N = N; d1.H = H; d1.W = W; d1.Cin = C; d1.Cout = C; d1.alpha = 1.f;
           conv_op(bops, n->convs[br.conv1], d1, true);
           sites.push_back({br.conv2, du, br.t, H, W, 1.f, du_cs, N * ca_chunks});
-          sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * tiles * 2});
+          sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * pool_rows});
         }
         void* GB_new = bp.take(px * C * 2);
         Op add{};
@@ -890,7 +891,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         ConvDesc d2{};
         d2.x = GB_cur; d2.mask = br.t; d2.y_bf16 = dt; d2.N = N; d2.H = H; d2.W = W; d2.Cin = C; d2.Cout = C;
         d2.alpha = n->res_scale;
-        float* dt_pool = static_cast<float*>(bp.take(size_t(N) * tiles * 2 * C * 4));
+        float* dt_pool = static_cast<float*>(bp.take(size_t(N) * pool_rows * C * 4));
         d2.flags = kConvPool; d2.pool_partial = dt_pool;
         conv_op(bops, n->convs[br.conv2], d2, true);
         ConvDesc d1{};
@@ -899,7 +900,7 @@ static int build_plan(Net* n, const void* packed, void* ws, int N, int H, int W,
         if (qed && b > 0) d1.bf16_scale = q_of(b - 1);
         conv_op(bops, n->convs[br.conv1], d1, true);
         sites.push_back({br.conv2, GB_cur, br.t, H, W, n->res_scale, nullptr, 0});
-        sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * tiles * 2});
+        sites.push_back({br.conv1, dt, br.in_b, H, W, 1.f, dt_pool, N * pool_rows});
         GB_cur = GB_new;
       }
       if (qed) { Op qg{}; qg.type = OP_QGRAD; qg.ca_chunks = kDqSlices; bops.push_back(qg); }   // q*dq slices
@@ -1349,7 +1350,7 @@ int rumpy_net_forward(void* net_, const float* const* params, const void* packed
         if (int e = conv_ca_launch(op.conv, op.cafused, stream)) return e;
         break;
       case OP_CA:
-        if (int e = ca_apply_launch(op.pool, 2 * ((H + kTileH - 1) / kTileH) * ((W + kTileW - 1) / kTileW),
+        if (int e = ca_apply_launch(op.pool, conv_pool_rows(H, W, n->C),
                                     op.pool_compact, op.u, n->plan_u_f32, op.x_in, params[op.ca.w1], params[op.ca.b1],
                                     params[op.ca.w2], params[op.ca.b2], op.x_out, op.x_out_b, op.save_mean,
                                     op.save_hid, op.save_y, N, H, W, n->C, n->C / n->reduction, stream, op.q_scale))

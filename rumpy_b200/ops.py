@@ -34,8 +34,9 @@ def device_check():
     _lib.call('rumpy_device_check')
 
 
-def tiles_per_image(H, W):
-    return ((H + 7) // 8) * ((W + 15) // 16)
+def pool_rows(H, W, C):
+    """Rows per image of a pool_partial buffer (rumpy_pool_rows)."""
+    return _lib.load().rumpy_pool_rows(int(H), int(W), int(C))
 
 
 def pack_conv3x3(w_oihw, rows_padded=0, shuffle_r=1, dgrad=False, out=None):
@@ -127,7 +128,7 @@ def nhwc_to_nchw(x):
 def pool_sum(x_nhwc):
     _chk(x_nhwc, torch.float32, 'x')
     N, H, W, C = x_nhwc.shape
-    pp = torch.empty((N * tiles_per_image(H, W), 2, C), dtype=torch.float32, device=x_nhwc.device)
+    pp = torch.empty((N, pool_rows(H, W, C), C), dtype=torch.float32, device=x_nhwc.device)
     _lib.call('rumpy_pool_sum', x_nhwc.data_ptr(), pp.data_ptr(), N, H, W, C, _stream())
     return pp
 

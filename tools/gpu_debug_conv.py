@@ -68,7 +68,7 @@ def _conv_case(N, H, W, Cin, Cout, *, wkind='rand', relu=False, bias=True, resid
     wp = ops.pack_conv3x3(w)
     yb = torch.full((N, H, W, Cout), float('nan'), dtype=torch.bfloat16, device='cuda') if out_bf16 else None
     yf = torch.full((N, H, W, Cout), float('nan'), dtype=torch.float32, device='cuda') if out_f32 else None
-    pp = torch.full((N * ops.tiles_per_image(H, W), 2, Cout), float('nan'), device='cuda') if pool else None
+    pp = torch.full((N, ops.pool_rows(H, W, Cout), Cout), float('nan'), device='cuda') if pool else None
     ops.conv3x3(xb, wp, b, residual=res, mask=msk, out_bf16=yb, out_f32=yf, pool_partial=pp, N=N, H=H, W=W,
                 Cin=Cin, Cout=Cout, relu=relu, alpha=alpha)
     torch.cuda.synchronize()
@@ -283,7 +283,7 @@ def c32_ca_apply():
         w2 = torch.rand((C, Cr), generator=gen, device='cuda') - 0.5
         b2 = torch.rand((C,), generator=gen, device='cuda') - 0.5
         # pool partials as the conv epilogue would emit them: here simply spread the sums over the partial slots
-        tiles = ops.tiles_per_image(H, W)
+        tiles = ops.pool_rows(H, W, C) // 2
         pp = torch.zeros((N * tiles, 2, C), device='cuda')
         pp.view(N, tiles * 2, C)[:, 0, :] = u.float().sum(dim=(1, 2))
         xo = torch.empty_like(xin)
