@@ -71,11 +71,10 @@ _lib = None
 
 # developer switches, read when an engine is created and applied to ITS handle (rumpy_net_set_option): env var ->
 # (option, value when the variable holds that string)
-ENV_OPTIONS = {'RUMPY_B200_PDL': ('pdl', {'0': 0}), 'RUMPY_B200_CONV2X': ('conv_2x', {'1': 1}),
-               'RUMPY_B200_TRUNK': ('trunk', {'0': 0}), 'RUMPY_B200_BAND': ('band', {'1': 1}),
+ENV_OPTIONS = {'RUMPY_B200_PDL': ('pdl', {'0': 0}),                'RUMPY_B200_TRUNK': ('trunk', {'0': 0}), 'RUMPY_B200_BAND': ('band', {'1': 1}),
                'RUMPY_B200_CLUSTER': ('cluster', {'0': 0}), 'RUMPY_B200_CLUSTER_GROUPS': ('cluster_groups', {'2': 2, '4': 4}),
                'RUMPY_B200_FUSED_CA': ('fused_ca', {'1': 1}), 'RUMPY_B200_CLUSTER_SPLIT': ('cluster_split', {'0': 0}),
-               'RUMPY_B200_CONV_DBG': ('conv_dbg', {str(i): i for i in range(1, 8)})}
+               'RUMPY_B200_CONV_DBG': ('conv_dbg', {str(i): i for i in range(1, 128)})}
 
 
 def env_options():

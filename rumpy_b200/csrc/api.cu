@@ -191,16 +191,7 @@ int conv_plan_build(ConvPlan* p, const ConvDesc& d) {
   a.stages = stages;
   a.stg_bufs = bufs;
   p->smem = conv_smem_bytes(bn, resident, cin_chunks, stages, flags, bufs);
-  int ctas_per_sm = 1;
-  if (opt().conv_2x && !thin && bn == 64 && cin_chunks == 1 && !has_in &&
-      conv_smem_bytes(64, false, 1, 2, flags, 1) <= 113 * 1024) {
-    // two small CTAs per SM: weights streamed with the halo boxes, one tile's prologue/epilogue overlaps the
-    // other's MMAs, and the next layer's CTAs (PDL) can start as soon as one of the two slots frees up
-    p->resident = false;
-    a.stages = 2; a.stg_bufs = 1;
-    p->smem = conv_smem_bytes(64, false, 1, 2, flags, 1);
-    ctas_per_sm = 2;
-  }
+  const int ctas_per_sm = 1;
   // resident weights: 16 x 8 tiles fed by one halo box; streamed weights: 8 x 16 tiles, one box per kx (conv3x3_tc.cuh)
   const int th = p->resident ? kTallH : kTileH, tw = p->resident ? kTallW : kTileW;
   a.tiles_x = (d.W + tw - 1) / tw;
@@ -329,7 +320,7 @@ int conv_ca_launch(const ConvPlan& p, const CaFusedArgs& ca, cudaStream_t s) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
+  cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kConvCaThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

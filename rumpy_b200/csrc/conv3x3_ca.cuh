@@ -40,7 +40,8 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1)
+constexpr int kConvCaThreads = 192;
+__global__ void __launch_bounds__(kConvCaThreads, 1)
 conv3x3_ca_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args, const CaFusedArgs ca) {
   constexpr int BN = 64;
   constexpr int kBBlock = BN * 128;

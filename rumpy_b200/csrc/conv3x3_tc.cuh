@@ -61,7 +61,8 @@ struct ConvArgs {
   int cout_real;         // BN == 16 variant only: number of real output channels (<= 16)
   long long* dbg;        // optional per-CTA timeline (2 x 16 clock64 slots per CTA); nullptr in production
   int dbg_mode;          // timing experiments (garbage results), 0 in production: 1 = A boxes fetched only for the first
-                         // `stages` fills, 4 = no MMAs issued, 8 = timeline stamps from the pooled convs only
+                         // `stages` fills, 4 = no MMAs issued, 8 = timeline stamps from the pooled convs only,
+                         // 16 = epilogue stages nothing (drains the accumulator only), 32 = no pool sums, 64 = no stores
   uint32_t flags;
 };
 
@@ -81,8 +82,13 @@ constexpr int kTallStageBytes = (kTallBoxBytes + 1023) & ~1023;       // stages 
 constexpr int kStgF32Bytes = 2 * kABytes;          // fp32 staging: two 32-channel halves
 constexpr int kStgBf16Bytes = kABytes;
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 192;
-constexpr size_t kConvSmemBudget = 227 * 1024 - 3072;
+constexpr int kEpiGroups = 2;                      // epilogue groups of 4 warps: one 32-channel half each
+constexpr int kEpiThreads = 128 * kEpiGroups;
+constexpr int kEpiSets = 2;                        // epilogue sets (even / odd tiles) of kEpiGroups groups each
+constexpr int kWarpStore = 2 + 4 * kEpiGroups * kEpiSets;   // warp that issues the output stores
+constexpr int kWarpMma2 = kWarpStore + 1;          // second MMA-issuing warp (odd tiles); warp 1 issues the even tiles
+constexpr int kConvThreads = (kWarpMma2 + 1) * 32;
+constexpr size_t kConvSmemBudget = 227 * 1024 - 5120;   // static shared memory: barriers, bias, pool sums (~4.5 KB)
 
 __host__ __device__ constexpr int conv_b_block_bytes(int bn) { return bn * 128; }
 
@@ -105,11 +111,12 @@ __host__ inline size_t conv_smem_bytes(int bn, bool resident_b, int cin_chunks, 
   return s;
 }
 
+constexpr int kDbgTile = 40;   // the steady-state tile whose epilogue / MMA issue the second timeline region records
 #define RB_STAMP_ON (args.dbg && (!(args.dbg_mode & 8) || (args.flags & kConvPool)))   // mode 8: pooled convs only
 #define RB_STAMP(slot) do { if (RB_STAMP_ON) args.dbg[blockIdx.x * 16 + (slot)] = clock64(); } while (0)
 // second region (after gridDim.x * 16 slots): the epilogue of this CTA's third tile (its TMA-issuing thread) in slots
 // 0..7, cycles the MMA warp waited for an accumulator / for A stages and the producer for free stages in 12..14
-#define RB_STAMP2(slot) do { if (RB_STAMP_ON && it == 2 && et == 0) args.dbg[(gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
+#define RB_STAMP2(slot) do { if (RB_STAMP_ON && it == kDbgTile && et == 0 && tp == 0) args.dbg[(gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ long long global_timer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -123,7 +130,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <int BN, bool RESIDENT_B>
-__global__ void __launch_bounds__(kConvThreads, RESIDENT_B ? 1 : 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   static_assert(BN == 16 || BN == 64 || BN == 128 || BN == 256, "BN must be 16, 64, 128 or 256");
   constexpr int kBBlock = BN * 128;
@@ -140,8 +147,11 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t b_bar;
   __shared__ __align__(8) uint64_t in_bar[2];
+  __shared__ __align__(8) uint64_t stg_full[2];    // epilogue -> store warp: slot staged
+  __shared__ __align__(8) uint64_t stg_empty[2];   // store warp -> epilogue: slot read out
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[BN];
+  __shared__ __align__(16) float bias_s[BN];
+  __shared__ __align__(16) float pool_s[kEpiSets * 8][64];   // per epilogue warp channel sums of the current chunk
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -168,7 +178,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 128);
+      mbar_init(&tmem_empty_bar[i], BN == 16 ? 128 : kEpiThreads);
+      mbar_init(&stg_full[i], kEpiThreads);
+      mbar_init(&stg_empty[i], 1);
     }
     mbar_init(&b_bar, 1);
     mbar_init(&in_bar[0], 1);
@@ -201,10 +213,16 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       __syncwarp();
     }
     grid_dep_wait();   // weights are static; activations come from the previous kernel
-    int stage = 0;
-    uint32_t phase = 0;
+    // two stage rings, one per MMA issuer (tile parity): a parity wait needs a single consumer per ring
+    // (resident weights only; the streamed-weights variant keeps one issuer and one ring -- its tiles are 12+ fills
+    // long and halving the ring cost more than the second issuer gained: EDSR 256-channel step 27.3 -> 32.6 ms)
+    const int ring_size[2] = {RESIDENT_B ? stages - stages / 2 : stages, RESIDENT_B ? stages / 2 : 0};
+    int ring_pos[2] = {0, 0};
+    uint32_t ring_phase[2] = {0, 0};
     long long w_empty = 0;
-    for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
+    int it_p = 0;
+    for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it_p) {
+      const int ring = RESIDENT_B ? (it_p & 1) : 0;
       const int n = mt / tiles_per_img;
       const int rem = mt - n * tiles_per_img;
       const int y0 = (rem / args.tiles_x) * TH;
@@ -212,10 +230,12 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       int mi = 0, cc = 0;  // input map index / 64-channel chunk inside that map
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
         for (int kx = 0; kx < (RESIDENT_B ? 1 : 3); ++kx) {
+          const int stage = ring * ring_size[0] + ring_pos[ring];
+          const uint32_t phase = ring_phase[ring];
           const long long t0 = args.dbg ? clock64() : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_sleep(&empty_bar[stage], phase ^ 1, 200);
           if (args.dbg) w_empty += clock64() - t0;
-          if ((args.dbg_mode & 1) && (phase || mt != mt_first)) {
+          if ((args.dbg_mode & 1) && (phase || it_p > 1)) {
             if (elect_one()) mbar_arrive(&full_bar[stage]);
           } else if (elect_one()) {
             uint8_t* sa = stage0 + stage * kStageBytes;
@@ -231,30 +251,45 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             }
           }
           __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++ring_pos[ring] == ring_size[ring]) { ring_pos[ring] = 0; ring_phase[ring] ^= 1; }
         }
         if (++cc == args.a_chunks_per_map) { cc = 0; ++mi; }
       }
     }
     if (RB_STAMP_ON && lane == 0) args.dbg[(gridDim.x + blockIdx.x) * 16 + 14] = w_empty;
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one elected lane)
+  } else if (warp == 1 || warp == kWarpMma2) {
+    // ===================================================================== MMA issuers (one elected lane each)
+    // Two warps on different schedulers, alternating tiles: issuer `me` owns accumulator `me`.  One thread issues an
+    // MMA every ~56-68 cycles here; two reach the tensor pipe's own rate.  Each issuer has its own stage ring (a
+    // parity wait on a shared ring can be more than one phase away from the barrier and alias).
+    const int me = warp == 1 ? 0 : 1;
     if (RESIDENT_B) mbar_wait_trap(&b_bar, 0);
-    if (lane == 0) RB_STAMP(3);
-    int stage = 0;
-    uint32_t phase = 0;
+    if (lane == 0 && me == 0) RB_STAMP(3);
+    if (RESIDENT_B || me == 0) {   // streamed weights: one issuer, one ring
+    const int ring_size = !RESIDENT_B ? stages : (me == 0 ? stages - stages / 2 : stages / 2);   // see the producer
+    const int ring_base = (RESIDENT_B && me == 1) ? stages - stages / 2 : 0;
+    int ring_pos = 0;
+    uint32_t ring_phase = 0;
     int it = 0;
     long long w_acc = 0, w_full = 0;
     for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+      if (RESIDENT_B && (it & 1) != me) continue;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long t0 = args.dbg ? clock64() : 0;
       mbar_wait_trap(&tmem_empty_bar[acc], acc_phase ^ 1);
       if (args.dbg) w_acc += clock64() - t0;
+      if (RB_STAMP_ON && it == kDbgTile && lane == 0) {
+        args.dbg[(gridDim.x + blockIdx.x) * 16 + 10] = t0;          // tile kDbgTile: MMA warp ready for the tile
+        args.dbg[(gridDim.x + blockIdx.x) * 16 + 11] = clock64();   // ... accumulator free, issue starts
+      }
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
       for (int chunk = 0; chunk < cin_chunks; ++chunk) {
         for (int kx = 0; kx < (RESIDENT_B ? 1 : 3); ++kx) {
+          const int stage = ring_base + ring_pos;
+          const uint32_t phase = ring_phase;
+          if (++ring_pos == ring_size) { ring_pos = 0; ring_phase ^= 1; }
           const long long t1 = args.dbg ? clock64() : 0;
           mbar_wait_trap(&full_bar[stage], phase);
           if (args.dbg) w_full += clock64() - t1;
@@ -294,29 +329,77 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           }
           __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
       if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       if (it == 0 && lane == 0) RB_STAMP(5);
+      if (RB_STAMP_ON && it == kDbgTile && lane == 0) args.dbg[(gridDim.x + blockIdx.x) * 16 + 15] = clock64();  // issued
     }
-    if (RB_STAMP_ON && lane == 0) {
+    if (RB_STAMP_ON && lane == 0 && me == 0) {
       args.dbg[(gridDim.x + blockIdx.x) * 16 + 12] = w_acc;
       args.dbg[(gridDim.x + blockIdx.x) * 16 + 13] = w_full;
     }
+    }
+  } else if (warp == kWarpStore) {
+    // ===================================================================== store warp (offload configuration)
+    // Issues the output stores of every staged chunk, so that no epilogue thread queues behind the producer's boxes
+    // in the TMA unit (measured at 1080p: ~650 cycles per tile on the epilogue's critical path), and hands the
+    // staging slot back once the store has read it.  One lane: bulk groups are per thread.
+    const bool has_in_s = (flags & (kConvResF32 | kConvMask)) != 0;
+    if (BN != 16 && !has_in_s && args.stg_bufs == 2 && lane == 0) {
+      const bool use_f32_s = (flags & kConvOutF32) != 0;
+      grid_dep_wait();
+      int cc = 0;
+      for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride) {
+        const int n = mt / tiles_per_img;
+        const int rem = mt - n * tiles_per_img;
+        const int y0 = (rem / args.tiles_x) * TH;
+        const int x0 = (rem % args.tiles_x) * TW;
+        for (int j = 0; j < kChunksPerTile; ++j, ++cc) {
+          const int oc = n_tile * kChunksPerTile + j;
+          const int slot = cc & 1;
+          uint8_t* stg_f32 = smem + slot * stg_buf_bytes;
+          uint8_t* stg_bf16 = stg_f32 + (use_f32_s ? kStgF32Bytes : 0);
+          mbar_wait_sleep(&stg_full[slot], uint32_t(cc >> 1) & 1u, 200);
+          if (args.dbg_mode & 64) { mbar_arrive(&stg_empty[slot]); continue; }
+          if (flags & kConvOutF32) {
+            tma_store_4d(&maps.of, stg_f32, oc * 64, x0, y0, n);
+            tma_store_4d(&maps.of, stg_f32 + kABytes, oc * 64 + 32, x0, y0, n);
+          }
+          if (flags & kConvOutBf16) {
+            const int mi = oc / args.o_chunks_per_map;
+            const int c0 = (oc % args.o_chunks_per_map) * 64;
+            tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
+          }
+          tma_store_commit();
+          tma_store_wait_read0();          // this chunk's store has read its slot: the epilogue may refill it (chunk
+          mbar_arrive(&stg_empty[slot]);   // cc+2, two tiles from now -- releasing cc-1 here instead came one store
+                                           // issue too late for chunk cc+1 and stalled the accumulator drain)
+        }
+      }
+      tma_store_wait_all0();
+    }
   } else {
-    // ===================================================================== epilogue (128 threads)
+    // ===================================================================== epilogue (2 sets x 2 groups x 128 threads)
+    // Set tp (warps 2+8tp .. 9+8tp) takes the tiles of parity tp = accumulator tp = staging slot tp, so that two
+    // tiles' epilogue chains (shared-memory round trips that queue behind the tensor core's operand reads) overlap;
+    // inside a set, group g owns channels [32g, 32g+32) of every 64-channel chunk of every pixel row.  Configurations
+    // with TMA inputs (residual / mask), one staging slot or several chunks per tile run on set 0 alone.
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;               // pixel row of the tile == TMEM lane
-    const int et = (warp - 2) * 32 + lane;       // 0..127, et==0 is the TMA issuing thread
+    const int tp = (warp - 2) >> 3;              // epilogue set
+    const int grp = ((warp - 2) >> 2) & 1;       // channel half
+    const int et = ((warp - 2) & 7) * 32 + lane; // 0..255 inside the set; et==0 issues TMA in the non-offload configurations
     const int ly = RESIDENT_B ? row >> 3 : row >> 4, lx = RESIDENT_B ? row & 7 : row & 15;
-    for (int i = et; i < BN; i += 128) bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
-    named_bar_sync(1, 128);
+    for (int i = et + tp * kEpiThreads; i < BN; i += kEpiSets * kEpiThreads)
+      bias_s[i] = args.bias ? args.bias[n_tile * BN + i] : 0.f;
+    named_bar_sync(1, kEpiSets * kEpiThreads);
     grid_dep_wait();   // residual / mask inputs and every global write must follow the previous kernel
     int it = 0;
     if constexpr (BN == 16) {
-      // thin tail conv (C -> out_feats <= 16): fp32 NCHW written straight from registers, no staging
+      // thin tail conv (C -> out_feats <= 16): fp32 NCHW written straight from registers, no staging; group 0 only
+      if (grp == 0 && tp == 0)
       for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
         const int n = mt / tiles_per_img;
         const int rem = mt - n * tiles_per_img;
@@ -342,6 +425,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     } else {
       const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
       const bool use_f32 = (flags & (kConvOutF32 | kConvResF32)) != 0;
+      const bool offload = !has_in && stg_bufs == 2;   // the store warp issues the stores (see above)
+      const bool split = offload && kChunksPerTile == 1;   // both sets work, one tile parity each
+      const uint32_t bar_a = split ? 2u + 2u * tp : 2u, bar_b = bar_a + 1;   // the set's named barriers
       const uint32_t swz = uint32_t(row & 7);
       int cc = 0;  // running chunk counter -> staging slot
       const int my_tiles = (mt_first < args.m_tiles) ? (args.m_tiles - 1 - mt_first) / mt_stride + 1 : 0;
@@ -366,8 +452,13 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
         }
         if (flags & kConvMask) tma_load_4d(sb, &maps.mb, &in_bar[slot], t_oc * 64, t_x0, t_y0, t_n);
       };
-      if (has_in && stg_bufs == 2 && et == 0 && total_chunks > 0) issue_inputs(0);
+      if (has_in && stg_bufs == 2 && et == 0 && tp == 0 && total_chunks > 0) issue_inputs(0);
+      if (split || tp == 0)
       for (int mt = mt_first; mt < args.m_tiles; mt += mt_stride, ++it) {
+        if (split) {
+          if ((it & 1) != tp) continue;
+          cc = it;   // one chunk per tile: the global chunk index (staging slot = tile parity)
+        }
         const int n = mt / tiles_per_img;
         const int rem = mt - n * tiles_per_img;
         const int y0 = (rem / args.tiles_x) * TH;
@@ -381,8 +472,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
           uint8_t* stg = smem + slot * stg_buf_bytes;
           uint8_t* stg_f32 = stg;
           uint8_t* stg_bf16 = stg + (use_f32 ? kStgF32Bytes : 0);
-          uint8_t* my_f32 = stg_f32 + row * 128;
+          uint8_t* my_f32 = stg_f32 + grp * kABytes + row * 128;   // this group's 32-channel fp32 half
           uint8_t* my_bf16 = stg_bf16 + row * 128;
+          RB_STAMP2(0);
           if (has_in && stg_bufs == 1 && et == 0) {
             // single slot: wait until the previous chunk's stores have read it, then fetch this chunk's inputs
             tma_store_wait_read0();
@@ -392,46 +484,48 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             // single slot without inputs (two-CTAs-per-SM configuration): the previous chunk's store must have
             // read the slot before anyone overwrites it
             if (et == 0) tma_store_wait_read0();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, kEpiThreads);
           }
-          RB_STAMP2(0);
           if (j == 0) {
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            mbar_wait_sleep(&tmem_full_bar[acc], acc_phase, 100);
             tc_fence_after();
-            if (et == 0) RB_STAMP(it == 0 ? 6 : 9);
+            if (et == 0 && tp == 0) RB_STAMP(it == 0 ? 6 : 9);
           }
           RB_STAMP2(1);
-          uint32_t v[64];
-          {
-            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + j * 64);
-            tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            tmem_ld32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-            tmem_ld_wait();
-          }
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN + j * 64 + grp * 32), v);
+          tmem_ld_wait();
           RB_STAMP2(2);
           if (j == kChunksPerTile - 1) {
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
           }
           if (has_in) mbar_wait(&in_bar[slot], uint32_t(cc / stg_bufs) & 1u);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          // (after the accumulator was handed back: a late slot must not hold up the MMA warp)
+          if (offload && cc >= 2) mbar_wait(&stg_empty[slot], uint32_t((cc >> 1) - 1) & 1u);
+          if (!(args.dbg_mode & 16)) {
             float f[32];
+            const float4* b4 = reinterpret_cast<const float4*>(&bias_s[j * 64 + grp * 32]);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = __uint_as_float(v[h * 32 + i]) + bias_s[j * 64 + h * 32 + i];
-              if (flags & kConvRelu) x = fmaxf(x, 0.f);
-              f[i] = x * args.alpha;
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = b4[i];
+              const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = __uint_as_float(v[i * 4 + e]) + bb[e];
+                if (flags & kConvRelu) x = fmaxf(x, 0.f);
+                f[i * 4 + e] = x * args.alpha;
+              }
             }
             if (args.ch_scale != nullptr) {
-              const float* cs = args.ch_scale + size_t(n) * args.cout + oc * 64 + h * 32;
+              const float* cs = args.ch_scale + size_t(n) * args.cout + oc * 64 + grp * 32;
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] *= __ldg(cs + i);
             }
             if (flags & kConvMask) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
-                const uint4 m = *reinterpret_cast<const uint4*>(my_bf16 + (((uint32_t(h * 4 + c)) ^ swz) << 4));
+                const uint4 m = *reinterpret_cast<const uint4*>(my_bf16 + (((uint32_t(grp * 4 + c)) ^ swz) << 4));
                 const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -445,7 +539,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             if (flags & kConvResF32) {
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                const float4 r = *reinterpret_cast<const float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4));
+                const float4 r = *reinterpret_cast<const float4*>(my_f32 + ((uint32_t(c) ^ swz) << 4));
                 f[c * 4 + 0] += r.x; f[c * 4 + 1] += r.y; f[c * 4 + 2] += r.z; f[c * 4 + 3] += r.w;
               }
             }
@@ -456,76 +550,116 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
             if (flags & kConvOutF32) {
 #pragma unroll
               for (int c = 0; c < 8; ++c)
-                *reinterpret_cast<float4*>(my_f32 + h * kABytes + ((uint32_t(c) ^ swz) << 4)) =
+                *reinterpret_cast<float4*>(my_f32 + ((uint32_t(c) ^ swz) << 4)) =
                     make_float4(f[c * 4], f[c * 4 + 1], f[c * 4 + 2], f[c * 4 + 3]);
             }
             if ((flags & kConvOutBf16) && args.bf16_scale != nullptr) {
-              const float* bs = args.bf16_scale + size_t(n) * args.cout + oc * 64 + h * 32;
+              const float* bs = args.bf16_scale + size_t(n) * args.cout + oc * 64 + grp * 32;
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] *= __ldg(bs + i);
             }
             if (flags & kConvOutBf16) {
 #pragma unroll
               for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(my_bf16 + ((uint32_t(h * 4 + c) ^ swz) << 4)) =
+                *reinterpret_cast<uint4*>(my_bf16 + ((uint32_t(grp * 4 + c) ^ swz) << 4)) =
                     make_uint4(pack_bf16x2(f[c * 8], f[c * 8 + 1]), pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]),
                                pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]));
             }
           }
           RB_STAMP2(3);
           fence_proxy_async_smem();
-          // double-buffered staging: the store issued one chunk ago must have finished READING the other
-          // buffer before anyone refills it in the next chunk -- checked here, a whole chunk later
-          if (!has_in && stg_bufs == 2 && et == 0) tma_store_wait_read0();
-          RB_STAMP2(4);
-          named_bar_sync(2, 128);
-          RB_STAMP2(5);
-          if (et == 0) {
-            RB_STAMP(it == 0 ? 8 : 10);
-            if (flags & kConvOutF32) {
-              tma_store_4d(&maps.of, stg_f32, oc * 64, x0, y0, n);
-              tma_store_4d(&maps.of, stg_f32 + kABytes, oc * 64 + 32, x0, y0, n);
-            }
-            if (flags & kConvOutBf16) {
-              const int mi = oc / args.o_chunks_per_map;
-              const int c0 = (oc % args.o_chunks_per_map) * 64;
-              tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
-            }
-            tma_store_commit();
-            if (has_in && stg_bufs == 2 && cc + 1 < total_chunks) {
-              // prefetch the next chunk's inputs into the other slot once its previous store (chunk cc-1) has
-              // been read out; the store just committed (this chunk) may stay in flight
-              tma_store_wait_read1();
-              issue_inputs(cc + 1);
+          if (offload) {
+            mbar_arrive(&stg_full[slot]);   // -> store warp
+            RB_STAMP2(4);
+            if (flags & kConvPool) named_bar_sync(bar_a, kEpiThreads);   // the pool below reads other threads' rows
+            RB_STAMP2(5);
+          } else {
+            // double-buffered staging: the store issued one chunk ago must have finished READING the other
+            // buffer before anyone refills it in the next chunk -- checked here, a whole chunk later
+            if (!has_in && stg_bufs == 2 && et == 0) tma_store_wait_read0();
+            RB_STAMP2(4);
+            named_bar_sync(2, kEpiThreads);
+            RB_STAMP2(5);
+            if (et == 0) {
+              RB_STAMP(it == 0 ? 8 : 10);
+              if (flags & kConvOutF32) {
+                tma_store_4d(&maps.of, stg_f32, oc * 64, x0, y0, n);
+                tma_store_4d(&maps.of, stg_f32 + kABytes, oc * 64 + 32, x0, y0, n);
+              }
+              if (flags & kConvOutBf16) {
+                const int mi = oc / args.o_chunks_per_map;
+                const int c0 = (oc % args.o_chunks_per_map) * 64;
+                tma_store_4d(&maps.ob[mi], stg_bf16, c0, x0, y0, n);
+              }
+              tma_store_commit();
+              if (has_in && stg_bufs == 2 && cc + 1 < total_chunks) {
+                // prefetch the next chunk's inputs into the other slot once its previous store (chunk cc-1) has
+                // been read out; the store just committed (this chunk) may stay in flight
+                tma_store_wait_read1();
+                issue_inputs(cc + 1);
+              }
             }
           }
           RB_STAMP2(6);
-          if (flags & kConvPool) {
-            // channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves
-            const int c = et & 63, half = et >> 6;
-            float s = 0.f;
+          if ((flags & kConvPool) && !(args.dbg_mode & 32)) {
+            // Channel sums over the tile's valid pixels (invalid rows were zeroed), two 64-row halves.  Thread t sums
+            // 8 channels (one 16-byte unit per row) over rows 4*(t>>3) .. +3, lanes with the same unit combine by
+            // shuffle, the 8 warps (16 rows each) through shared memory.
+            const int c8 = et & 7, r0 = (et >> 3) * 4;
+            float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (flags & kConvOutF32) {
-              const uint8_t* base = stg_f32 + (c >> 5) * kABytes + (c & 3) * 4;
-              const uint32_t ch = uint32_t((c & 31) >> 2);
-#pragma unroll 8
-              for (int r = half * 64; r < half * 64 + 64; ++r)
-                s += *reinterpret_cast<const float*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
+              // fp32 staging: two 32-channel halves; s[0..3] = channels 4*c8.., s[4..7] = channels 32 + 4*c8..
+#pragma unroll
+              for (int r = r0; r < r0 + 4; ++r) {
+                const uint32_t off = uint32_t(r) * 128 + ((uint32_t(c8) ^ uint32_t(r & 7)) << 4);
+                const float4 a = *reinterpret_cast<const float4*>(stg_f32 + off);
+                const float4 b = *reinterpret_cast<const float4*>(stg_f32 + kABytes + off);
+                s[0] += a.x; s[1] += a.y; s[2] += a.z; s[3] += a.w;
+                s[4] += b.x; s[5] += b.y; s[6] += b.z; s[7] += b.w;
+              }
             } else {
-              const uint8_t* base = stg_bf16 + (c & 7) * 2;
-              const uint32_t ch = uint32_t(c >> 3);
-#pragma unroll 8
-              for (int r = half * 64; r < half * 64 + 64; ++r) {
-                const uint16_t b = *reinterpret_cast<const uint16_t*>(base + r * 128 + ((ch ^ uint32_t(r & 7)) << 4));
-                s += __uint_as_float(uint32_t(b) << 16);
+#pragma unroll
+              for (int r = r0; r < r0 + 4; ++r) {
+                const uint4 a = *reinterpret_cast<const uint4*>(stg_bf16 + uint32_t(r) * 128 +
+                                                                ((uint32_t(c8) ^ uint32_t(r & 7)) << 4));
+                const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  s[2 * e] += __uint_as_float(w[e] << 16);
+                  s[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                }
               }
             }
-            args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = s;
-            if (has_in && stg_bufs == 1) named_bar_sync(3, 128);  // single slot: readers finish before the next input TMA
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              s[e] += __shfl_xor_sync(0xffffffffu, s[e], 8);
+              s[e] += __shfl_xor_sync(0xffffffffu, s[e], 16);
+            }
+            RB_STAMP2(8);
+            const int ew = tp * 8 + (et >> 5);   // the set's warp 0..7 = rows 16*w .. 16*w+15
+            if (lane < 8) {
+              if (flags & kConvOutF32) {
+                *reinterpret_cast<float4*>(&pool_s[ew][4 * c8]) = make_float4(s[0], s[1], s[2], s[3]);
+                *reinterpret_cast<float4*>(&pool_s[ew][32 + 4 * c8]) = make_float4(s[4], s[5], s[6], s[7]);
+              } else {
+                *reinterpret_cast<float4*>(&pool_s[ew][8 * c8]) = make_float4(s[0], s[1], s[2], s[3]);
+                *reinterpret_cast<float4*>(&pool_s[ew][8 * c8 + 4]) = make_float4(s[4], s[5], s[6], s[7]);
+              }
+            }
+            named_bar_sync(bar_b, kEpiThreads);   // (also: every reader of the slot is done before the next input TMA)
+            RB_STAMP2(9);
+            if (et < 128) {
+              const int c = et & 63, half = et >> 6;
+              const int w0 = tp * 8 + 4 * half;
+              const float t = (pool_s[w0][c] + pool_s[w0 + 1][c]) + (pool_s[w0 + 2][c] + pool_s[w0 + 3][c]);
+              args.pool_partial[(size_t(mt) * 2 + half) * args.cout + oc * 64 + c] = t;
+            }
           }
           RB_STAMP2(7);
         }
       }
-      if (et == 0) { RB_STAMP(11); tma_store_wait_all0(); RB_STAMP(12); }
+      if (!offload && et == 0 && tp == 0) { RB_STAMP(11); tma_store_wait_all0(); RB_STAMP(12); }
+      if (offload && et == 0 && tp == 0) RB_STAMP(11);
     }
   }
 

@@ -33,7 +33,6 @@ struct Options {
   int wgrad_tiles_per_split = 64;   // pixel tiles per split-K job (measured: 32 -> 14.97, 64 -> 14.76, 128 -> 14.73 ms)
   int use_pdl = 1;            // programmatic dependent launch between per-layer kernels
   int infer_u_bf16 = 1;       // per-layer inference: pre-attention activation u in bf16 (net.cu build_plan)
-  int conv_2x = 0;            // experiment: two small conv CTAs per SM
   int conv_dbg = 0;           // per-layer conv kernel timing experiments (garbage results): see ConvArgs::dbg_mode
   int trunk_sync_mode = 8;    // dataflow kernel: release store of the tile epoch (needed, DESIGN.md trunk protocol)
   int trunk_dbg_layers = 0;   // > 0: trunk kernels write a clock64 timeline of this many layers to `timeline`
@@ -43,7 +42,7 @@ struct Options {
   unsigned plan_sig() const {
     return unsigned(use_trunk) | unsigned(use_cluster) << 1 | unsigned(use_trunk_bwd) << 2 | unsigned(use_band) << 3 |
            unsigned(use_fused_ca) << 4 | unsigned(cluster_groups == 4) << 5 | unsigned(use_pdl) << 6 |
-           unsigned(conv_2x) << 7 | unsigned(wgrad_chunks) << 8 | unsigned(wgrad_tiles_per_split) << 12 |
+           unsigned(wgrad_chunks) << 8 | unsigned(wgrad_tiles_per_split) << 12 |
            unsigned(timeline != nullptr) << 28 | unsigned(cluster_split) << 29 | unsigned(infer_u_bf16) << 30 | unsigned(cluster_dbg != 0 || conv_dbg != 0) << 31;
   }
 };

@@ -1149,7 +1149,6 @@ int rumpy_net_set_option(void* net, const char* name, long long value) {
   else if (k == "wgrad_chunks") o.wgrad_chunks = v < 1 ? 1 : (v > 8 ? 8 : v);
   else if (k == "wgrad_tiles_per_split") o.wgrad_tiles_per_split = v < 1 ? 1 : v;
   else if (k == "pdl") o.use_pdl = v != 0;
-  else if (k == "conv_2x") o.conv_2x = v != 0;
   else if (k == "conv_dbg") o.conv_dbg = v;
   else if (k == "trunk_sync_mode") o.trunk_sync_mode = v;
   else return set_error(RUMPY_ERR_ARG, "net_set_option: unknown option '%s'", name);
@@ -1171,7 +1170,6 @@ long long rumpy_net_get_option(void* net, const char* name) {
   if (k == "wgrad_chunks") return o.wgrad_chunks;
   if (k == "wgrad_tiles_per_split") return o.wgrad_tiles_per_split;
   if (k == "pdl") return o.use_pdl;
-  if (k == "conv_2x") return o.conv_2x;
   if (k == "trunk_sync_mode") return o.trunk_sync_mode;
   return -1;
 }

@@ -310,6 +310,17 @@ __device__ __forceinline__ void mbar_wait_trap(uint64_t* bar, uint32_t parity) {
     if ((++spins & 1023u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) asm volatile("trap;");
   }
 }
+// Wait with back-off: for warps with slack (epilogue, producer, store warp) that share a scheduler with the MMA-issuing
+// warp -- a tight try_wait loop competes with it for issue slots.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if ((++spins & 1023u) == 0 && clock64() - t0 > RB_WATCHDOG_CYCLES) asm volatile("trap;");
+  }
+}
 __device__ __forceinline__ void mbar_wait_cluster_trap(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();

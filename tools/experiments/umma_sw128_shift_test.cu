@@ -70,6 +70,49 @@ shift_kernel(const __nv_bfloat16* act, const __nv_bfloat16* w, float* out, int v
   if (warp == 0) { tc_fence_after(); tmem_dealloc<64>(tmem); }
 }
 
+// Rate: `iters` x 36 MMAs (nine taps x four K steps) from one issuing thread, nothing else running.
+//   layout 0: aligned reference -- every tap reads the box at offset 0 with SBO = 1024 (dense atoms)
+//   layout 1: the shifted taps of the conv (start (ky*pitch+kx)*128, SBO = pitch*128)
+__global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters, int layout) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* a_s = smem + 9 * 8192;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (9 * 8192 + kPix * 128) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3c003c00u, 0, 0x3c003c00u, 0);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<64>(&tmem_base_s);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    constexpr uint32_t kIdesc = make_idesc_bf16(128, 64);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap % 3, kx = tap / 3;
+        const uint32_t start = smem_u32(a_s + (layout ? (ky * kPitch + kx) * 128 : 0));
+        const uint64_t adesc = make_smem_desc(start, 16, layout ? kPitch * 128 : 1024, kLayoutSw128);
+        const uint64_t bdesc = make_smem_desc(smem_u32(w_s + tap * 8192), 16, 1024, kLayoutSw128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), kIdesc, (it | tap | k) != 0);
+      }
+    }
+    const long long t1 = clock64();
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t2 = clock64();
+    out[0] = t1 - t0; out[1] = t2 - t0;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<64>(tmem); }
+}
+
 int main() {
   std::vector<__nv_bfloat16> act(kPix * 64), w(9 * 64 * 64);
   std::vector<float> actf(kPix * 64), wf(9 * 64 * 64);
@@ -111,5 +154,16 @@ int main() {
     printf("variant %d (base offset %s): max |err| = %.4g (ref absmax %.4g), %d of 128 rows wrong -> %s\n", variant,
            variant == 0 ? "0" : "(start>>7)&7", maxerr, maxref, bad_rows, maxerr < 1e-3 * maxref ? "MATCH" : "mismatch");
   }
+  long long* dt; cudaMalloc(&dt, 16);
+  cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int layout = 0; layout < 2; ++layout)
+    for (int iters : {1, 4, 64}) {
+      rate_kernel<<<1, 128, smem>>>(dt, iters, layout);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("rate: CUDA error %s\n", cudaGetErrorString(e)); return 1; }
+      long long h[2]; cudaMemcpy(h, dt, 16, cudaMemcpyDeviceToHost);
+      printf("layout %d (%s), %2d x 36 MMAs: issue %.1f cycles/MMA, issue+drain %.1f cycles/MMA\n", layout,
+             layout ? "shifted taps, SBO = pitch*128" : "aligned, SBO = 1024", iters, double(h[0]) / (iters * 36), double(h[1]) / (iters * 36));
+    }
   return 0;
 }

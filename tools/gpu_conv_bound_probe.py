@@ -1,5 +1,5 @@
 """What bounds the per-layer conv kernel at 1080p: frame time with parts of the kernel switched off (ConvArgs::dbg_mode:
-1 = A boxes fetched only for the first fills, 2 = epilogue drains nothing, 4 = no MMAs).  Results are garbage in modes != 0."""
+1 = A boxes fetched only for the first fills, 4 = no MMAs, 16 = epilogue stages nothing, 32 = no pool sums).  Results are garbage in modes != 0."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -20,5 +20,5 @@ for mode in [int(v) for v in os.environ.get('MODES', '0,1,2,4,3,5,6,7').split(',
         e0.record()
         for _ in range(3): eng.forward(xf)
         e1.record(); e1.synchronize()
-    print(f'conv_dbg={mode} (no-A-fetch {mode & 1}, no-epilogue {(mode >> 1) & 1}, no-MMA {(mode >> 2) & 1}): 1080p frame {e0.elapsed_time(e1) / 3:.1f} ms', flush=True)
+    print(f'conv_dbg={mode} (no-A-fetch {mode & 1}, no-MMA {(mode >> 2) & 1}, no-staging {(mode >> 4) & 1}, no-pool {(mode >> 5) & 1}, no-stores {(mode >> 6) & 1}): 1080p frame {e0.elapsed_time(e1) / 3:.1f} ms', flush=True)
     del eng; torch.cuda.empty_cache()

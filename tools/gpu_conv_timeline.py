@@ -29,7 +29,9 @@ for cta in (0, 1, 73, 147):
           f' | last tile acc ready {rel(9)} staged {rel(10)} | loop end {rel(11)} stores done {rel(12)} exit {rel(13)}'
           f' | cycles/tile {rel(11) / per_cta:.0f}  ns total {int(r[15] - r[14])}')
     b = int(e[0])
-    print('    third tile epilogue: wait acc %d | tmem_ld %d | math+sts %d | fence+storewait %d | barrier %d | tma store %d | pool %d'
+    print('    tile 40 epilogue: wait acc %d | tmem_ld %d | math+sts %d | fence+storewait %d | barrier %d | tma store %d | pool %d'
           % tuple(int(e[k + 1] - e[k]) for k in range(7)))
     print('    waits over the whole kernel: MMA warp on accumulator %d, on A stages %d; producer on free stages %d (cycles, of %d)'
           % (int(e[12]), int(e[13]), int(e[14]), rel(13)))
+    print('    tile 40, relative to the MMA warp being ready for it: accumulator free +%d, MMAs issued +%d, epilogue sees the accumulator +%d, epilogue was ready for it at +%d, epilogue done +%d'
+          % (int(e[11] - e[10]), int(e[15] - e[10]), int(e[1] - e[10]), int(e[0] - e[10]), int(e[7] - e[10])))
