@@ -178,8 +178,10 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], BN == 16 ? 128 : kEpiThreads);
-      mbar_init(&stg_full[i], kEpiThreads);
+      // one arrival per epilogue WARP (lane 0 after __syncwarp): 32 lanes arriving on one barrier are 32 serialised
+      // shared-memory operations on the data pipe the tensor core reads its operands through
+      mbar_init(&tmem_empty_bar[i], BN == 16 ? 4 : kEpiThreads / 32);
+      mbar_init(&stg_full[i], kEpiThreads / 32);
       mbar_init(&stg_empty[i], 1);
     }
     mbar_init(&b_bar, 1);
@@ -413,7 +415,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
         tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * BN), v);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         if (y < args.H && x < args.W) {
 #pragma unroll
           for (int c = 0; c < 16; ++c)
@@ -498,7 +501,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
           RB_STAMP2(2);
           if (j == kChunksPerTile - 1) {
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);  // accumulator drained -> MMA may reuse it
           }
           if (has_in) mbar_wait(&in_bar[slot], uint32_t(cc / stg_bufs) & 1u);
           // (after the accumulator was handed back: a late slot must not hold up the MMA warp)
@@ -569,7 +573,8 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
           RB_STAMP2(3);
           fence_proxy_async_smem();
           if (offload) {
-            mbar_arrive(&stg_full[slot]);   // -> store warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stg_full[slot]);   // -> store warp
             RB_STAMP2(4);
             if (flags & kConvPool) named_bar_sync(bar_a, kEpiThreads);   // the pool below reads other threads' rows
             RB_STAMP2(5);
