@@ -318,6 +318,17 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
                            ? lay->alpha * __ldg(lay->q_scale + n * 64 + KC * e + row) : lay->alpha;
       }
       named_bar_sync(bar_id, 128);
+      // This group's KC bias values, ONCE per layer and thread (16-byte broadcast loads): read per tile -- and, in the
+      // ReLU path, as 32 predicated scalar loads -- they were 770 of a layer's shared-memory wavefronts, on the data
+      // pipe the tensor core reads its operands through (ncu source page, profiles/README.md).
+      float breg[KC];
+#pragma unroll
+      for (int i4 = 0; i4 < KC / 4; ++i4) {
+        const float4 t = reinterpret_cast<const float4*>(bias_e)[i4];
+        breg[4 * i4] = t.x; breg[4 * i4 + 1] = t.y; breg[4 * i4 + 2] = t.z; breg[4 * i4 + 3] = t.w;
+      }
+      const bool alpha_vec = kind == kTrunkRes && lay->q_scale != nullptr;   // per-channel alpha (meta-attention) only
+      const float alpha_u = lay->alpha;
 
       // KC fp32 results of this thread's part of a pixel -> bf16 chunks -> buffer / halos (or global, last layer)
       auto emit = [&](int qy, int qx, bool valid, size_t pix, const float (&f)[KC]) {
@@ -361,7 +372,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         if (kind == kTrunkRelu) {
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < KC; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[i], 0.f);
+          for (int i = 0; i < KC; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + breg[i], 0.f);
         } else {
           if (lay->no_res) {
             tmem_ld_wait();
@@ -383,7 +394,13 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
             for (int i = 0; i < KC; ++i) f[i] = __uint_as_float(s[i]);
           }
 #pragma unroll
-          for (int i = 0; i < KC; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[i]) * alpha_e[i] + f[i];
+          if (alpha_vec) {
+#pragma unroll
+            for (int i = 0; i < KC; ++i) f[i] = (__uint_as_float(v[i]) + breg[i]) * alpha_e[i] + f[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < KC; ++i) f[i] = (__uint_as_float(v[i]) + breg[i]) * alpha_u + f[i];
+          }
           if (update_s) {
 #pragma unroll
             for (int i = 0; i < KC; ++i) v[i] = __float_as_uint(f[i]);
@@ -417,14 +434,12 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
           tmem_ld_wait();
           // (bias read with unconditional 16-byte loads: under the `valid` select the compiler emitted 32 predicated
           // scalar LDS -- 363 shared-memory wavefronts per layer next to the tensor core's operand reads)
-          float b[KC];
+          // u = accumulator + bias goes back to tensor memory (its own port): the apply pass needs no bias
 #pragma unroll
-          for (int i4 = 0; i4 < KC / 4; ++i4) {
-            const float4 t = reinterpret_cast<const float4*>(bias_e)[i4];
-            b[4 * i4] = t.x; b[4 * i4 + 1] = t.y; b[4 * i4 + 2] = t.z; b[4 * i4 + 3] = t.w;
-          }
+          for (int i = 0; i < KC; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + breg[i]);
+          tmem_st(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
 #pragma unroll
-          for (int i = 0; i < KC; ++i) f[i] = valid ? __uint_as_float(v[i]) + b[i] : 0.f;
+          for (int i = 0; i < KC; ++i) f[i] = valid ? __uint_as_float(v[i]) : 0.f;
           if constexpr (KC == 32) {
             red_s[e][q][lane] = lane_transpose_sum32(f, lane);
           } else {
@@ -496,6 +511,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
       // are issued BEFORE the wait for the pool exchange, tile j + 1's before tile j's results are written out, so the
       // ~400-cycle TMEM round trip leaves the critical path pool -> y -> apply -> hand-over.
       uint32_t av[KC], as[KC];
+      float yreg[KC];
       auto ca_prefetch = [&](int j) {
         tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), av);
         tmem_ld(lane_addr + uint32_t(j * 64), as);
@@ -506,11 +522,10 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         const int y = ry * RH + qy, x = rx * RW + qx;
         const bool valid = y < args.H && x < args.W;
         const size_t pix = ((size_t(n) * args.H + y) * args.W + x) * 64 + KC * e;
-        const float* yv = y_e + KC * e;
         float f[KC];
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < KC; ++i) f[i] = fmaf(__uint_as_float(av[i]) + bias_e[i], yv[i], __uint_as_float(as[i]));
+        for (int i = 0; i < KC; ++i) f[i] = fmaf(__uint_as_float(av[i]), yreg[i], __uint_as_float(as[i]));
         {
           uint32_t sv[KC];
 #pragma unroll
@@ -529,8 +544,17 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         for (int j = 0; j < n_tiles; ++j) { plain(j); early(j); }
       } else {
         for (int j = 0; j < n_tiles; ++j) ca_pool(j);
+        tmem_st_wait();     // u is back in tensor memory
         ca_prefetch(0);
         ca_y();
+        {
+          const float* yv = y_e + KC * e;   // this group's KC channel scales, once per layer
+#pragma unroll
+          for (int i4 = 0; i4 < KC / 4; ++i4) {
+            const float4 t = reinterpret_cast<const float4*>(yv)[i4];
+            yreg[4 * i4] = t.x; yreg[4 * i4 + 1] = t.y; yreg[4 * i4 + 2] = t.z; yreg[4 * i4 + 3] = t.w;
+          }
+        }
         for (int j = 0; j < n_tiles; ++j) { ca_apply(j); early(j); }
         ++ca_seen;
       }
