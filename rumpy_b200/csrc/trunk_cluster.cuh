@@ -544,6 +544,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         for (int j = 0; j < n_tiles; ++j) { plain(j); early(j); }
       } else {
         for (int j = 0; j < n_tiles; ++j) ca_pool(j);
+        if (row == 0 && e == 0) CL_STAMP(L, 9);
         tmem_st_wait();     // u is back in tensor memory
         ca_prefetch(0);
         ca_y();
@@ -555,7 +556,12 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
             yreg[4 * i4] = t.x; yreg[4 * i4 + 1] = t.y; yreg[4 * i4 + 2] = t.z; yreg[4 * i4 + 3] = t.w;
           }
         }
-        for (int j = 0; j < n_tiles; ++j) { ca_apply(j); early(j); }
+        if (row == 0 && e == 0) CL_STAMP(L, 6);
+        for (int j = 0; j < n_tiles; ++j) {
+          ca_apply(j);
+          early(j);
+          if (row == 0 && e == 0 && j < 2) CL_STAMP(L, 7 + j);
+        }
         ++ca_seen;
       }
       tmem_st_wait();   // the residual-stream updates of this layer (one wait per layer, not per tile)

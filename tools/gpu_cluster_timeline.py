@@ -31,6 +31,6 @@ for cta in (48,):
         r = d[cta, L]
         rel = lambda k: (r[k].item() - r[0].item()) if r[k].item() else 0
         print(f'L{L:3d} start {r[0].item() - t0:8d} (+{r[0].item() - prev:6d})  B_ok +{rel(5):6d}  mma_issued +{rel(1):6d}  last_acc +{rel(2):6d}'
-              f'  pool +{rel(4):6d}  last_tile_done +{rel(3):6d}')
+              f'  pool_pass_done +{rel(9):6d}  pool +{rel(4):6d}  y +{rel(6):6d}  apply0 +{rel(7):6d}  apply1 +{rel(8):6d}  last_tile_done +{rel(3):6d}')
         prev = r[0].item()
 eng.set_timeline(None)
