@@ -65,6 +65,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Explicit shared-window load (a pointer derived from the dynamic shared-memory base is generic to the compiler: LD.E).
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------ programmatic dependent launch (PDL)
 // launch_dependents: the next kernel in the stream (launched with the programmatic-serialization attribute) may
 // start its prologue now; grid_dep_wait: block until the previous kernel has completed and its writes are visible.

@@ -317,6 +317,16 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         alpha_e[row] = (kind == kTrunkRes && lay->q_scale != nullptr)
                            ? lay->alpha * __ldg(lay->q_scale + n * 64 + KC * e + row) : lay->alpha;
       }
+      if (kind == kTrunkCA && e == 0 && row < 8 + 2 * args.cr) {
+        // the layer's FC parameters (w1 / w2 256*cr B each, b1, b2) towards L2 now: ca_y reads each of them once per
+        // CTA, first touch, in the serial chain after the layer's last MMA
+        const int cr = args.cr;
+        const char* pf = row < 2 * cr ? reinterpret_cast<const char*>(lay->w1) + row * 128
+                       : row < 4 * cr ? reinterpret_cast<const char*>(lay->w2) + (row - 2 * cr) * 128
+                       : row < 4 * cr + 2 ? reinterpret_cast<const char*>(lay->b2) + (row - 4 * cr) * 128
+                                          : reinterpret_cast<const char*>(lay->b1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      }
       named_bar_sync(bar_id, 128);
       // This group's KC bias values, ONCE per layer and thread (16-byte broadcast loads): read per tile -- and, in the
       // ReLU path, as 32 predicated scalar loads -- they were 770 of a layer's shared-memory wavefronts, on the data
@@ -432,8 +442,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
           float f[KC];
           tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
           tmem_ld_wait();
-          // (bias read with unconditional 16-byte loads: under the `valid` select the compiler emitted 32 predicated
-          // scalar LDS -- 363 shared-memory wavefronts per layer next to the tensor core's operand reads)
+          if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 14);
           // u = accumulator + bias goes back to tensor memory (its own port): the apply pass needs no bias
 #pragma unroll
           for (int i = 0; i < KC; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + breg[i]);
@@ -448,6 +457,7 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
           }
         }
         tc_fence_before();
+        if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 15);
         named_bar_sync(bar_id, 128);
         if (row < KC) {
           // this tile's channel sum -> slot (rank, j) of EVERY CTA of the cluster (fixed slot => fixed sum order)
@@ -482,11 +492,21 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
           if (ca_seen + 2 < args.n_ca)                                     // arm this barrier for CA layer +2
             mbar_expect_tx(&pool_full[cpar], uint32_t(pool_slots) * 64u * 4u);
         }
-        float ssum = 0.f;
-        const float* ps = pool_s + size_t(cpar) * pool_slots * 64 + c;
-        for (int sl = hsel; sl < pool_slots; sl += 2) ssum += ps[sl * 64];
+        // this thread's half of the slots of channel c: four independent partial sums (one dependent generic load
+        // per slot was 600 cycles of the chain every CA layer waits on)
+        const uint32_t ps = smem_u32(pool_s + size_t(cpar) * pool_slots * 64 + c);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        int sl = hsel;
+        for (; sl + 6 < pool_slots; sl += 8) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s4[k] += lds_f32(ps + uint32_t(sl + 2 * k) * 256u);
+        }
+        for (; sl < pool_slots; sl += 2) s4[0] += lds_f32(ps + uint32_t(sl) * 256u);
+        const float ssum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         red_s[e][hsel][c] = ssum;
+        if (row == 0 && e == 0) CL_STAMP(L, 10);
         named_bar_sync(bar_id, 128);
+        if (row == 0 && e == 0) CL_STAMP(L, 11);
         const float m0 = (red_s[e][0][lane] + red_s[e][1][lane]) * args.inv_hw;
         const float m1 = (red_s[e][0][lane + 32] + red_s[e][1][lane + 32]) * args.inv_hw;
 #pragma unroll
@@ -503,7 +523,9 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
           yacc = fmaf(__ldg(w2 + c * cr + h), fmaxf(sdot + __ldg(b1 + h), 0.f), yacc);
         }
         if (hsel == 0) y_e[c] = (1.f / (1.f + __expf(-yacc))) * (lay->q_scale ? __ldg(lay->q_scale + n * 64 + c) : 1.f);
+        if (row == 0 && e == 0) CL_STAMP(L, 12);
         named_bar_sync(bar_id, 128);
+        if (row == 0 && e == 0) CL_STAMP(L, 13);
       };
 
       // ---------------------------------------------------------------- phase 2: x + u*y from the same accumulator

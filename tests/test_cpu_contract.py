@@ -236,3 +236,14 @@ def test_gloo_world_size_2_allreduce(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_pool_rows_is_host_arithmetic():
+    """rumpy_pool_rows needs no device: two partial rows per conv tile, 16 x 8 tiles at 64 channels (weights resident in
+    shared memory), 8 x 16 above."""
+    from rumpy_b200 import _lib
+    lib = _lib.load()
+    for H, W in ((48, 48), (37, 29), (1080, 1920), (1, 1)):
+        assert lib.rumpy_pool_rows(H, W, 64) == 2 * ((H + 15) // 16) * ((W + 7) // 8)
+        assert lib.rumpy_pool_rows(H, W, 128) == 2 * ((H + 7) // 8) * ((W + 15) // 16)
+    assert lib.rumpy_pool_rows(0, 8, 64) == 0

@@ -81,6 +81,28 @@ def test_blocks_vs_reference_golden(golden_dir):
         assert err <= 2e-2 * max(1.0, np.abs(ref).max()), f'{tag}: {err}'
 
 
+def test_pooled_conv_partials_sum_to_the_output(golden_dir):
+    """RUMPY_CONV_POOL on ragged shapes (both tile geometries: resident weights at 64 channels, streamed at 128): the
+    partial rows (rumpy_pool_rows per image) add up to the channel sums of the bf16 output the same call stored."""
+    from rumpy_b200 import ops
+    dev = _dev()
+    for C, (H, W) in ((64, (37, 29)), (64, (16, 8)), (128, (21, 35))):
+        N = 2
+        g = torch.Generator(device='cuda').manual_seed(C + H)
+        x = (torch.rand((N, H, W, C), generator=g, device=dev) - 0.5).to(torch.bfloat16)
+        w = (torch.rand((C, C, 3, 3), generator=g, device=dev) - 0.5) / 24
+        b = torch.rand((C,), generator=g, device=dev)
+        y = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dev)
+        rows = ops.pool_rows(H, W, C)
+        pp = torch.full((N, rows, C), float('nan'), device=dev)
+        ops.conv3x3(x, ops.pack_conv3x3(w), b, out_bf16=y, pool_partial=pp, N=N, H=H, W=W, Cin=C, Cout=C)
+        torch.cuda.synchronize()
+        want = y.double().sum(dim=(1, 2)).cpu().numpy()
+        got = pp.double().sum(dim=1).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() <= 1e-4 * max(1.0, np.abs(want).max()), (C, H, W)
+
+
 def test_pixel_shuffle_store_bit_exact():
     """The shuffle folded into the conv store must be a pure index permutation: compare the shuffled store
     with the un-shuffled store of the same conv, permuted by the oracle -- bit for bit."""

@@ -32,5 +32,9 @@ for cta in (48,):
         rel = lambda k: (r[k].item() - r[0].item()) if r[k].item() else 0
         print(f'L{L:3d} start {r[0].item() - t0:8d} (+{r[0].item() - prev:6d})  B_ok +{rel(5):6d}  mma_issued +{rel(1):6d}  last_acc +{rel(2):6d}'
               f'  pool_pass_done +{rel(9):6d}  pool +{rel(4):6d}  y +{rel(6):6d}  apply0 +{rel(7):6d}  apply1 +{rel(8):6d}  last_tile_done +{rel(3):6d}')
+        if r[4].item():
+            d_ = lambda a, b: r[a].item() - r[b].item()
+            print(f'       CA chain: acc->tmem_ld {d_(14, 2)}  transpose-sum {d_(15, 14)}  barrier+push+barrier {d_(9, 15)} | exchange wait {d_(4, 9)} | '
+                  f'slot sums {d_(10, 4)}  barrier {d_(11, 10)}  FC+sigmoid {d_(12, 11)}  barrier {d_(13, 12)}  y regs {d_(6, 13)} | apply0 {d_(7, 6)} apply1 {d_(8, 7)}')
         prev = r[0].item()
 eng.set_timeline(None)
