@@ -231,7 +231,7 @@ static int launch_conv_t(const ConvPlan& p, cudaStream_t s) {
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(kConvThreads); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
+  cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(conv_threads(RES)); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -84,10 +84,12 @@ constexpr int kStgBf16Bytes = kABytes;
 constexpr int kMaxStages = 8;
 constexpr int kEpiGroups = 2;                      // epilogue groups of 4 warps: one 32-channel half each
 constexpr int kEpiThreads = 128 * kEpiGroups;
-constexpr int kEpiSets = 2;                        // epilogue sets (even / odd tiles) of kEpiGroups groups each
-constexpr int kWarpStore = 2 + 4 * kEpiGroups * kEpiSets;   // warp that issues the output stores
-constexpr int kWarpMma2 = kWarpStore + 1;          // second MMA-issuing warp (odd tiles); warp 1 issues the even tiles
-constexpr int kConvThreads = (kWarpMma2 + 1) * 32;
+// Warp roles: 0 TMA producer | 1 MMA issuer (even tiles) | 2 .. epilogue sets of kEpiGroups x 4 warps | store warp |
+// second MMA issuer.  Resident weights: two epilogue sets (even / odd tiles) and two issuers = 20 warps; streamed
+// weights: one set, one issuer = 11 warps (and twice the registers per thread).
+__host__ __device__ constexpr int conv_epi_sets(bool resident) { return resident ? 2 : 1; }
+__host__ __device__ constexpr int conv_warp_store(bool resident) { return 2 + 4 * kEpiGroups * conv_epi_sets(resident); }
+__host__ __device__ constexpr int conv_threads(bool resident) { return (conv_warp_store(resident) + (resident ? 2 : 1)) * 32; }
 constexpr size_t kConvSmemBudget = 227 * 1024 - 5120;   // static shared memory: barriers, bias, pool sums (~4.5 KB)
 
 __host__ __device__ constexpr int conv_b_block_bytes(int bn) { return bn * 128; }
@@ -130,7 +132,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 template <int BN, bool RESIDENT_B>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(conv_threads(RESIDENT_B), 1)
 conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   static_assert(BN == 16 || BN == 64 || BN == 128 || BN == 256, "BN must be 16, 64, 128 or 256");
   constexpr int kBBlock = BN * 128;
@@ -151,6 +153,9 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
   __shared__ __align__(8) uint64_t stg_empty[2];   // store warp -> epilogue: slot read out
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[BN];
+  constexpr int kEpiSets = conv_epi_sets(RESIDENT_B);
+  constexpr int kWarpStore = conv_warp_store(RESIDENT_B);
+  constexpr int kWarpMma2 = RESIDENT_B ? kWarpStore + 1 : -1;   // second MMA-issuing warp (odd tiles)
   __shared__ __align__(16) float pool_s[kEpiSets * 8][64];   // per epilogue warp channel sums of the current chunk
 
   const int warp = threadIdx.x >> 5;
@@ -429,7 +434,7 @@ conv3x3_tc_kernel(const __grid_constant__ ConvMaps maps, const ConvArgs args) {
       const bool has_in = (flags & (kConvResF32 | kConvMask)) != 0;
       const bool use_f32 = (flags & (kConvOutF32 | kConvResF32)) != 0;
       const bool offload = !has_in && stg_bufs == 2;   // the store warp issues the stores (see above)
-      const bool split = offload && kChunksPerTile == 1;   // both sets work, one tile parity each
+      const bool split = kEpiSets == 2 && offload && kChunksPerTile == 1;   // both sets work, one tile parity each
       const uint32_t bar_a = split ? 2u + 2u * tp : 2u, bar_b = bar_a + 1;   // the set's named barriers
       const uint32_t swz = uint32_t(row & 7);
       int cc = 0;  // running chunk counter -> staging slot
