@@ -454,10 +454,12 @@ trunk_bwd_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkBwdArgs a
             uint32_t s[32];
             float f[32];
             tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
+            float yy[32], cf[32];
+            lds_bcast32(&y_s[e][h * 32], yy);
+            lds_bcast32(&coef_s[e][h * 32], cf);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              f[i] = valid ? fmaf(__uint_as_float(s[i]), y_s[e][h * 32 + i], coef_s[e][h * 32 + i]) : 0.f;
+            for (int i = 0; i < 32; ++i) f[i] = valid ? fmaf(__uint_as_float(s[i]), yy[i], cf[i]) : 0.f;
             stage_bf16(f, h);
             red_s[e][q][h * 32 + lane] = lane_transpose_sum32(f, lane);
           }

@@ -132,6 +132,15 @@ __device__ __forceinline__ void xpose_step(float (&f)[32], int lane) {
     f[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
   }
 }
+// 32 broadcast floats from shared memory as eight unconditional 16-byte loads (inside a `valid ? ... : 0` select the
+// compiler emits 32 predicated scalar loads instead: four times the shared-memory wavefronts).
+__device__ __forceinline__ void lds_bcast32(const float* p, float (&b)[32]) {
+#pragma unroll
+  for (int i4 = 0; i4 < 8; ++i4) {
+    const float4 t = reinterpret_cast<const float4*>(p)[i4];
+    b[4 * i4] = t.x; b[4 * i4 + 1] = t.y; b[4 * i4 + 2] = t.z; b[4 * i4 + 3] = t.w;
+  }
+}
 __device__ __forceinline__ float lane_transpose_sum32(float (&f)[32], int lane) {
   xpose_step<16>(f, lane);
   xpose_step<8>(f, lane);
@@ -169,7 +178,7 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
   __shared__ __align__(8) uint64_t acc_full[kTrunkMaxK];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float y_s[kTrunkMaxK][64];
-  __shared__ float bias_s[2][64], alpha_s[2][64], red_s[2][4][64];
+  __shared__ __align__(16) float bias_s[2][64], alpha_s[2][64], red_s[2][4][64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpA = 8, kWarpMma = 9, kWarpW = 10, kWarpMma2 = 11;
@@ -412,9 +421,11 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
           float f[32];
           tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
           if (kind == kTrunkRelu) {
+            float bb[32];
+            lds_bcast32(bias_e + h * 32, bb);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bias_e[h * 32 + i], 0.f);
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(__uint_as_float(v[i]) + bb[i], 0.f);
           } else {
             if (lay->no_res) {
               tmem_ld_wait();
@@ -435,8 +446,13 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(s[i]);
             }
+            {
+              float bb[32], aa[32];
+              lds_bcast32(bias_e + h * 32, bb);
+              lds_bcast32(alpha_e + h * 32, aa);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bias_e[h * 32 + i]) * alpha_e[h * 32 + i] + f[i];
+              for (int i = 0; i < 32; ++i) f[i] = (__uint_as_float(v[i]) + bb[i]) * aa[i] + f[i];
+            }
             if (update_s) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(f[i]);
@@ -475,9 +491,11 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
           uint32_t v[32];
           float f[32];
           tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
+          float bb[32];
+          lds_bcast32(bias_e + h * 32, bb);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bias_e[h * 32 + i] : 0.f;
+          for (int i = 0; i < 32; ++i) f[i] = valid ? __uint_as_float(v[i]) + bb[i] : 0.f;
           if (u_map >= 0) stage_bf16(f, h);
           red_s[e][q][h * 32 + lane] = lane_transpose_sum32(f, lane);
         }
@@ -564,10 +582,12 @@ trunk_pipe_kernel(const __grid_constant__ CUtensorMap w_map, const TrunkArgs arg
           float f[32];
           tmem_ld32(lane_addr + uint32_t(kTrunkAccCol + j * 64 + h * 32), v);
           tmem_ld32(lane_addr + uint32_t(j * 64 + h * 32), s);
+          float bb[32], yy[32];
+          lds_bcast32(bias_e + h * 32, bb);
+          lds_bcast32(yv + h * 32, yy);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            f[i] = fmaf(__uint_as_float(v[i]) + bias_e[h * 32 + i], yv[h * 32 + i], __uint_as_float(s[i]));
+          for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]) + bb[i], yy[i], __uint_as_float(s[i]));
 #pragma unroll
           for (int i = 0; i < 32; ++i) s[i] = __float_as_uint(f[i]);
           tmem_st32(lane_addr + uint32_t(j * 64 + h * 32), s);
