@@ -180,6 +180,54 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 16 lanes x 32 fp32 columns in the accumulator-fragment shape (tools/experiments/tmem_ld_16x256b_map.cu): register
+// 4k + 2s + b of thread t = TMEM lane base + (t >> 2) + 8s, column 8k + 2(t & 3) + b.  A thread holds 8 columns of
+// 4 rows (with the second call at lane base + 16), so per-column sums over a warp's 32 rows are local adds + a 7-shuffle
+// reduce-scatter (colsum32_frag below) instead of the 31 shuffles of a full lane transpose.
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_frag(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// cs[2k + b] = this thread's partial sum of column 8k + 2(lane & 3) + b  ->  the warp's sum of column
+// frag_col(lane), one column per lane (reduce-scatter over lane bits 4, 3, 2).
+__device__ __forceinline__ int frag_col(int lane) {
+  const int j = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  return 8 * (j >> 1) + 2 * (lane & 3) + (j & 1);
+}
+__device__ __forceinline__ float colsum32_frag(float (&cs)[8], int lane) {
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? cs[i] : cs[i + 4], keep = up ? cs[i + 4] : cs[i];
+      cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? cs[i] : cs[i + 2], keep = up ? cs[i + 2] : cs[i];
+      cs[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  const bool up = (lane & 4) != 0;
+  const float send = up ? cs[0] : cs[1], keep = up ? cs[1] : cs[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 4);
+}
 // 32 registers per thread -> 32 lanes x 32 consecutive fp32 columns (thread i -> TMEM lane base+i).
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(

@@ -437,24 +437,57 @@ trunk_cluster_kernel_t(const __grid_constant__ CUtensorMap w_map, const ClusterA
         mbar_wait(&acc_full[j], uint32_t(L & 1));
         tc_fence_after();
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 2);
-        {
+        if constexpr (KC == 32) {
+          // Fragment-shaped reads: this thread gets 8 columns of 4 of the warp's 32 pixels (per call: rows (lane >> 2)
+          // and + 8 of a 16-lane half) -- the per-column sums are local adds + 7 shuffles.  u = accumulator + bias
+          // goes back to tensor memory (its own port) in the same shape: the apply pass needs no bias.
+          const int tq = lane & 3, tr = lane >> 2;
+          const uint32_t a0 = lane_addr + uint32_t(kTrunkAccCol + j * 64);
+          uint32_t r0[16], r1[16];
+          tmem_ld_frag(a0, r0);
+          tmem_ld_frag(a0 + (16u << 16), r1);
+          float b8[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 t = *reinterpret_cast<const float2*>(bias_e + 8 * k + 2 * tq);
+            b8[2 * k] = t.x; b8[2 * k + 1] = t.y;
+          }
+          const int y0 = ry * RH + kClusterTileH * ta + 4 * q, x0 = rx * RW + kClusterTileW * tb + tr;
+          const bool xin = x0 < args.W;
+          tmem_ld_wait();
+          if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 14);
+          float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int hs = 0; hs < 4; ++hs) {   // pixel row 4q + hs of the tile: half hs >> 1, register pair hs & 1
+            const bool ok = xin && (y0 + hs) < args.H;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int i = 4 * k + 2 * (hs & 1) + b;
+                uint32_t& reg = (hs >> 1) ? r1[i] : r0[i];
+                const float u = __uint_as_float(reg) + b8[2 * k + b];
+                reg = __float_as_uint(u);
+                cs[2 * k + b] += ok ? u : 0.f;
+              }
+            }
+          }
+          tmem_st_frag(a0, r0);
+          tmem_st_frag(a0 + (16u << 16), r1);
+          red_s[e][q][frag_col(lane)] = colsum32_frag(cs, lane);
+        } else {
           uint32_t v[KC];
           float f[KC];
           tmem_ld(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
           tmem_ld_wait();
           if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 14);
-          // u = accumulator + bias goes back to tensor memory (its own port): the apply pass needs no bias
 #pragma unroll
           for (int i = 0; i < KC; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + breg[i]);
           tmem_st(lane_addr + uint32_t(kTrunkAccCol + j * 64), v);
 #pragma unroll
           for (int i = 0; i < KC; ++i) f[i] = valid ? __uint_as_float(v[i]) : 0.f;
-          if constexpr (KC == 32) {
-            red_s[e][q][lane] = lane_transpose_sum32(f, lane);
-          } else {
-            const float cs = lane_transpose_sum16(f, lane);   // column (lane >> 1), at both lanes of the pair
-            if ((lane & 1) == 0) red_s[e][q][lane >> 1] = cs;
-          }
+          const float cs = lane_transpose_sum16(f, lane);   // column (lane >> 1), at both lanes of the pair
+          if ((lane & 1) == 0) red_s[e][q][lane >> 1] = cs;
         }
         tc_fence_before();
         if (row == 0 && e == 0 && j == n_tiles - 1) CL_STAMP(L, 15);
