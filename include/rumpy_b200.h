@@ -152,7 +152,9 @@ int rumpy_net_trunk_mode(void* net);
  * layer), "band" (0; 1 = role-swapped band kernel,
  * experiment), "trunk_bwd" (1; 0 = per-layer backward), "fused_ca" (0), "wgrad_chunks" (4; 1..8), "wgrad_tiles_per_split"
  * (64), "pdl" (1), "trunk_sync_mode" (8), "infer_u_bf16" (1; 0 = the per-layer inference path keeps the
- * pre-attention activation in fp32).  Unknown names return RUMPY_ERR_ARG / -1. */
+ * pre-attention activation in fp32), "cluster_dbg" / "conv_dbg" (0; timing experiments that switch parts of the cluster /
+ * per-layer conv kernel off -- results are garbage, tools/gpu_conv_bound_probe.py).  Unknown names return
+ * RUMPY_ERR_ARG / -1. */
 int rumpy_net_set_option(void* net, const char* name, long long value);
 long long rumpy_net_get_option(void* net, const char* name);
 /* Measurement hook (bench.py's roofline timing): two caller-owned CUDA events (cudaEvent_t) recorded on the launching
