@@ -1171,6 +1171,8 @@ long long rumpy_net_get_option(void* net, const char* name) {
   if (k == "wgrad_tiles_per_split") return o.wgrad_tiles_per_split;
   if (k == "pdl") return o.use_pdl;
   if (k == "trunk_sync_mode") return o.trunk_sync_mode;
+  if (k == "cluster_dbg") return o.cluster_dbg;
+  if (k == "conv_dbg") return o.conv_dbg;
   return -1;
 }
 
