@@ -90,9 +90,10 @@ class FramesInFlight:
     Why more than one: a large frame runs one kernel per layer, compute-bound convs alternating with the HBM-bound
     channel-attention pass, and within one frame the two cannot overlap (the pass needs the global pool of the conv
     before it); a second frame on another stream can fill the gaps.  Measured on 1080p RCAN frames (bench.py
-    `frame_1080p`, which times both): two in flight 147.6 ms per frame against 159.0 one at a time with the bf16
-    pre-attention activation of the inference plans; with the fp32 one (round 1's plan) it was the other way round,
-    174.8 against 168.7."""
+    `frame_1080p`, which times both and reports the faster): with the final conv kernel of round 2 (which fills the
+    shared-memory pipe of every SM by itself) two in flight are 139.6 ms per frame against 141.0 one at a time; with the
+    earlier conv kernel it was 147.6 against 159.0, and with the fp32 pre-attention activation of round 1's plan the
+    other way round, 174.8 against 168.7."""
 
     def __init__(self, net, depth=1):
         import torch
