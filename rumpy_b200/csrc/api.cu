@@ -225,11 +225,21 @@ template <int BN, bool RES>
 static int launch_conv_t(const ConvPlan& p, cudaStream_t s) {
   auto kern = conv3x3_tc_kernel<BN, RES>;
   static bool attr_set = false;
+  static int max_dyn = 0;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kConvSmemBudget)) != cudaSuccess)
+    // dynamic + this instantiation's static shared memory (barriers, bias, pool sums) must fit the 227 KB of a CTA
+    cudaFuncAttributes fa{};
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess)
+      return set_error(RUMPY_ERR_CUDA, "cudaFuncGetAttributes: %s", cudaGetErrorString(cudaGetLastError()));
+    max_dyn = 227 * 1024 - int(fa.sharedSizeBytes);
+    if (max_dyn > int(kConvSmemBudget)) max_dyn = int(kConvSmemBudget);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn) != cudaSuccess)
       return set_error(RUMPY_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
     attr_set = true;
   }
+  if (int(p.smem) > max_dyn)
+    return set_error(RUMPY_ERR_ARG, "conv3x3: %zu B of dynamic shared memory do not fit next to the kernel's static part",
+                     p.smem);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.grid); cfg.blockDim = dim3(conv_threads(RES)); cfg.dynamicSmemBytes = p.smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
